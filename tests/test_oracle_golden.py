@@ -1,0 +1,97 @@
+"""Pin the oracle (oracle/*.py) against the reference's own KAT and against
+fixtures generated from the live reference (oracle/make_golden.py)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import filters_oracle as fo
+from oracle.scattering1d_oracle import ScatteringOracle
+from oracle.phase_oracle import PhaseOracle
+
+SCAT = ['H', 'P', 'S', 'T']
+
+
+def rel_l2(a, b, axis=None):
+    return np.linalg.norm(a - b, axis=axis) / np.maximum(np.linalg.norm(b, axis=axis), 1e-30)
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_kat_test_data_1d(golden_dir):
+    """kymatio/tests/scattering1d/test_torch_scattering1d.py:82-113 (test_sample_scattering)."""
+    d = load(golden_dir, 'kat_test_data_1d.npz')
+    J, Q = int(d['J']), int(d['Q'])
+    o = ScatteringOracle(J, d['x'].shape[-1], Q, 2 ** J)
+    Sx = o(d['x'])
+    assert Sx.shape == d['Sx'].shape
+    assert rel_l2(Sx, d['Sx']) < 5e-7
+    assert np.allclose(Sx, d['Sx'], rtol=1e-5, atol=1e-8)      # torch.allclose defaults
+
+
+@pytest.mark.parametrize('name', SCAT)
+def test_geometry_filters_meta(golden_dir, name):
+    d = load(golden_dir, 'scat_%s.npz' % name)
+    J, Q, T, N = int(d['J']), int(d['Q']), int(d['T']), int(d['N'])
+    g = fo.geometry(N, J, Q, T)
+    assert (g['J_pad'], g['pad_left'], g['pad_right']) == (int(d['J_pad']), int(d['pad_left']), int(d['pad_right']))
+    assert [g['ind_start'][j] for j in range(J + 1)] == list(d['ind_start'])
+    assert [g['ind_end'][j] for j in range(J + 1)] == list(d['ind_end'])
+    bank = fo.filter_factory(g['J_pad'], J, Q, T)
+    filt = list(bank['phi'])
+    for p in bank['psi1'] + bank['psi2']:
+        filt += p['levels']
+    assert len(filt) == int(d['n_filters'])
+    assert [a.shape[0] for a in filt] == list(d['filter_len'])
+    sha = [hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() for a in filt]
+    assert sha == list(d['filter_sha256'])                       # bit-exact float64 filters
+    assert bank['t_max_phi'] == int(d['t_max_phi'])
+    keys = fo.path_keys(J, Q, T, int(d['max_order']))
+    gk = [tuple(int(v) for v in row if v >= 0) for row in d['keys']]
+    assert keys == gk
+
+
+@pytest.mark.parametrize('name', SCAT)
+def test_scattering_vs_reference(golden_dir, name):
+    """Single-precision oracle == reference to 1e-5 per path; the float64 oracle is
+    the 'truth' both are compared with.  On CTG-like inputs (baseline 140 bpm) some
+    second-order paths carry ~1e-6 of the signal energy and the reference's own fp32
+    rounding noise is ~2e-5 of those paths, hence the looser float64 bound."""
+    d = load(golden_dir, 'scat_%s.npz' % name)
+    args = (int(d['J']), int(d['N']), int(d['Q']), int(d['T']), int(d['max_order']))
+    S32 = ScatteringOracle(*args, cdtype=np.complex64)(d['x'])
+    S64 = ScatteringOracle(*args)(d['x'])
+    assert S32.shape == d['S'].shape and S64.shape == d['S'].shape
+    assert rel_l2(S32, d['S'], axis=-1).max() < 1e-5
+    assert rel_l2(S64, d['S'], axis=-1).max() < 5e-5
+    assert rel_l2(S64, d['S']) < 1e-6
+    randn = slice(d['x'].shape[0] // 2, None)               # second half of the batch is randn
+    assert rel_l2(S64[randn], d['S'][randn], axis=-1).max() < 1e-5
+
+
+@pytest.mark.parametrize('name', ['H', 'P', 'S'])
+def test_phase_vs_reference(golden_dir, name):
+    d = load(golden_dir, 'phase_%s.npz' % name)
+    J, Q, T, N = int(d['J']), int(d['Q']), int(d['T']), int(d['N'])
+    n_out = d['scattering'].shape[-1]
+    o = PhaseOracle(J, Q, T, N, n_out)
+    assert np.array_equal(o.center_freqs, d['center_freqs'])
+    assert np.array_equal(o.i_idx, d['i_idx']) and np.array_equal(o.j_idx, d['j_idx'])
+    assert np.array_equal(o.powers, d['powers'])
+    assert np.array_equal(o.autoc_idx, d['autoc_idx'])
+    x = d['x'][:2]
+    sub_w = np.nonzero(d['phase_mask'])[0] if bool(d['subset']) else None
+    sub_c = np.nonzero(d['cross_mask'])[0] if bool(d['subset']) else None
+    for mode, ref, sub in (('within', d['within'][:2], sub_w), ('cross', d['cross'][:2], sub_c)):
+        xin = x[:, 0] if mode == 'within' else x
+        plain = o(xin, mode=mode, pair_subset=sub)
+        assert plain.shape == ref.shape
+        aligned = o.align_branches(xin, ref, mode=mode, pair_subset=sub)
+        overall = rel_l2(aligned, ref)
+        per_path = rel_l2(aligned, ref, axis=-1)
+        # fp32 reference vs fp64 oracle: p*theta is rounded in fp32 with p up to ~100
+        assert overall < 5e-5, (mode, overall, rel_l2(plain, ref))
+        assert np.median(per_path) < 5e-5 and per_path.max() < 2e-3, (mode, per_path.max())
