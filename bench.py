@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""bench.py -- Scattering1D signals/s (J=6, Q=8, T=64, N=4800) on 1..8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the fused cascade over one batch of BASELINE.json's
+configs[1]: 8192 two-channel CTG-shaped samples = 16384 signals PER GPU (weak
+scaling; the batch shards with no collective).  `value` is device-resident
+throughput (CUDA events on the launch stream, max over ranks); `e2e` is the same
+metric through the host-buffer C-ABI entry point with pinned host tensors, H2D
+and D2H inside the timed region.  `--impl reference` times the CPU port of the
+reference (oracle/, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'vae-teb_b200')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+J, Q, T, N = 6, 8, 64, 4800
+SAMPLES_PER_GPU = 8192                    # two-channel samples -> 2 signals each
+METRIC = 'Scattering1D signals/s (J=6,Q=8,N=4800)'
+UNIT = 'signals/s'
+BYTES_PER_SIGNAL = N * 4 + 126 * 75 * 4   # 57 000 B algorithmic
+FLOPS_PER_SIGNAL = 31.56e6                # reference-equivalent FFT flops
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8): 'hw_slowdown',
+                getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+                getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+                getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
+            }
+            while not self.stop_flag.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:                     # clocks are evidence, not a dependency
+            self.reasons.add('unavailable:%s' % type(e).__name__)
+
+    def summary(self):
+        sm = sorted(self.sm)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.sm_max,
+                'reasons': sorted(self.reasons)}
+
+
+def cpu_port_rate(n_signals, workers):
+    """signals/s of the numpy port of the reference (oracle/) on `workers` host threads."""
+    import numpy as np
+    import scipy.fft
+    from oracle.scattering1d_oracle import ScatteringOracle
+    from tebscat.synth import ctg_batch
+    x = ctg_batch(n_signals // 2, N, seed=1234).reshape(n_signals, N).numpy()
+    orc = ScatteringOracle(J, N, Q, T, 2, cdtype=np.complex64)
+    with scipy.fft.set_workers(workers):
+        orc(x[:8])                                 # warm-up
+        t0 = time.perf_counter()
+        orc(x)
+        dt = time.perf_counter() - t0
+    return n_signals / dt, dt
+
+
+def run_reference(args):
+    """The reference arm: CPU port of kymatio's torch-CPU path, all host threads, bounded sample."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 256
+    rates = []
+    for _ in range(max(1, args.warmup)):
+        cpu_port_rate(32, cores)
+    for _ in range(args.steps):
+        r, _ = cpu_port_rate(sample, cores)
+        rates.append(r)
+    value = sum(rates) / len(rates)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sample / value,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'Scattering1D J=6 Q=8 T=64 N=4800 orders 0-2 (CPU port of the reference, '
+                               'bounded sample of %d signals per step)' % sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d CTG signals per step, numpy/scipy complex64 port (oracle/)' % sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from tebscat import Scattering1D, _lib
+    from tebscat.synth import ctg_batch
+    import ctypes
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    S = Scattering1D(J, N, Q, T=T).to(dev)
+    n_sig = 2 * SAMPLES_PER_GPU
+    # a few hundred distinct synthetic records tiled up to the batch (generation is host-side and slow)
+    base = ctg_batch(256, N, seed=1234 + rank)                      # (256, 2, N)
+    x_host = base.repeat(SAMPLES_PER_GPU // 256, 1, 1).contiguous().pin_memory()   # (8192, 2, N)
+    x_dev = x_host.to(dev)
+    out, _ = S(x_dev)                                               # builds the plan, warms up
+    torch.cuda.synchronize()
+    C, n_out = out.shape[-2], out.shape[-1]
+    del out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------
+    for _ in range(args.warmup):
+        S(x_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches = 0
+    ev[0].record()
+    for i in range(args.steps):
+        S(x_dev)
+        launches += _lib.load().tebscat_last_launch_count()
+        ev[i + 1].record()
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * n_sig * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI entry point -------------------------
+    out_host = torch.empty((n_sig, C, n_out), dtype=torch.float32, pin_memory=True)
+    S.scattering_host(x_host, out=out_host, device=local)           # warm-up (allocates the pipeline)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        S.scattering_host(x_host, out=out_host, device=local)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_sig * args.steps / float(t.item())
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        kernel_ms = sum(per_launch_ms) / len(per_launch_ms)
+        achieved_gbs = n_sig * BYTES_PER_SIGNAL / (kernel_ms * 1e-3) / 1e9
+        fp32 = ctypes.c_double(0.0)
+        _lib.load().tebscat_bench_fp32_peak(local, ctypes.byref(fp32))
+        achieved_tf = n_sig * FLOPS_PER_SIGNAL / (kernel_ms * 1e-3) / 1e12
+        cores = os.cpu_count() or 1
+        cpu_rate, cpu_dt = cpu_port_rate(512, cores)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'Scattering1D J=6 Q=8 T=64 N=4800 orders 0-2, batch 8192 two-channel '
+                                   'signals (16384 signals) per GPU -- BASELINE configs[1]',
+                       'signals_per_gpu': n_sig, 'l2': 'inputs+outputs 934 MB per step, larger than L2',
+                       'parallelism': 'batch-sharded x%d, no collective' % world},
+            'clocks': sampler.summary(),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': n_sig * N * 4,
+                    'd2h_bytes_per_step': n_sig * C * n_out * 4},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'hbm', 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': achieved_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                         'kernel': 'scat1d_kernel', 'kernel_ms': kernel_ms,
+                         'note': 'the fused cascade is FP32-pipe bound (554 flop/B); see fp32',
+                         'fp32': {'achieved': achieved_tf, 'peak': fp32.value, 'unit': 'TFLOP/s',
+                                  'frac': achieved_tf / fp32.value if fp32.value else None,
+                                  'flops_per_signal': FLOPS_PER_SIGNAL,
+                                  'peak_source': 'FMA microbenchmark in this run (tebscat_bench_fp32_peak)'}},
+            'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '512 CTG signals, %.1f s, numpy/scipy complex64 port (oracle/)' % cpu_dt},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='tebscat', choices=['tebscat', 'reference'])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'tebscat' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

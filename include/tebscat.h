@@ -1,0 +1,101 @@
+/*
+ * tebscat -- C ABI of the B200-native wavelet-scattering hot path of VAE-TEB.
+ *
+ * This is the drop-in boundary.  Nothing like it exists in
+ * the reference, whose plugin API is the op-by-op kymatio backend class
+ *   kymatio/kymatio/scattering1d/backend/torch_backend.py:17-174
+ * (pad, rfft, cdgmm, subsample_fourier, ifft, modulus, irfft, unpad, concatenate).
+ * An op-by-op backend cannot express a fused cascade, so the boundary sits one
+ * level higher: one call replaces the whole of
+ *   kymatio/kymatio/scattering1d/core/scattering1d.py:197-399      (tebscat_scat1d_*)
+ *   hdf5_dataset/kymatio_phase_scattering.py:220-360               (tebscat_phase_*)
+ * The Python frontends in vae-teb_b200/tebscat/ bind these entry points with
+ * ctypes and keep the reference's Scattering1D / KymatioPhaseScattering1D surface.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all device pointers are fp32, contiguous,
+ *    on the plan's device; the caller owns every buffer it passes in;
+ *  - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream,
+ *    the same stream convention as the reference's skcuda backend,
+ *    kymatio/kymatio/scattering1d/backend/torch_skcuda_backend.py:87,164);
+ *  - every function returns 0 on success or a TEBSCAT_E* code; the message is
+ *    available from tebscat_last_error() (thread-local); nothing throws;
+ *  - a plan is immutable after creation: forward calls are re-entrant from several
+ *    host threads on different streams.  One plan per device.
+ */
+#ifndef TEBSCAT_H_
+#define TEBSCAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEBSCAT_ABI_VERSION 1
+
+enum {
+    TEBSCAT_OK = 0,
+    TEBSCAT_EINVAL = 1,      /* bad argument / inconsistent plan description   */
+    TEBSCAT_ECUDA = 2,       /* a CUDA runtime call failed                     */
+    TEBSCAT_EUNSUPPORTED = 3 /* valid request this build cannot serve          */
+};
+
+/* Geometry of one Scattering1D instance plus the sizes of its flat tables.
+ * Replaces the attributes set by ScatteringBase1D.build
+ * (kymatio/kymatio/scattering1d/frontend/base_frontend.py:27-77). */
+typedef struct tebscat_plan_desc {
+    int32_t abi_version;   /* TEBSCAT_ABI_VERSION                                      */
+    int32_t N;             /* input length                                             */
+    int32_t log2_Np;       /* J_pad                                                    */
+    int32_t pad_left;      /* reflect padding on the left                              */
+    int32_t n_paths;       /* C: number of output channels (meta()['key'] order)       */
+    int32_t n_out;         /* ind_end[log2T] - ind_start[log2T]                        */
+    int32_t n_threads;     /* CTA size the schedule was built for                      */
+    int32_t smem_complex;  /* complex64 slots of shared memory the schedule addresses  */
+    int32_t n_tasks;       /* entries of `tasks` (8 x int32 each)                      */
+    int32_t n_steps;       /* entries of `steps` (2 x int32 each: [task_begin, task_end)) */
+    int32_t reserved[6];
+} tebscat_plan_desc;
+
+typedef struct tebscat_plan tebscat_plan;
+
+/* Upload the filter arena (fp32, bit-reversed bin order) and the
+ * step schedule to `device`.  Replaces ScatteringTorch1D.register_filters /
+ * load_filters (kymatio/kymatio/scattering1d/frontend/torch_frontend.py:75-116). */
+int tebscat_plan_create(const tebscat_plan_desc* desc,
+                        const float* filter_arena_host, size_t n_floats,
+                        const int32_t* tasks_host, const int32_t* steps_host,
+                        int device, tebscat_plan** out);
+
+void tebscat_plan_destroy(tebscat_plan* plan);
+
+/* S[b, c, :] for b < B.  x_dev: [B, N]; S_dev: [B, n_paths, n_out]; both device
+ * fp32 contiguous.  Replaces core.scattering1d
+ * (kymatio/kymatio/scattering1d/core/scattering1d.py:197-399) as called from
+ * ScatteringTorch1D.scattering (frontend/torch_frontend.py:219-227). */
+int tebscat_scat1d_forward(const tebscat_plan* plan, const float* x_dev, int64_t B,
+                           float* S_dev, void* stream);
+
+/* Same transform with HOST buffers: pinned staging, chunked H2D / compute / D2H
+ * overlap on the plan's own streams; returns when S_host is complete.  This is
+ * the call the dataset builder makes per record
+ * (hdf5_dataset/create_hdf5_dataset.py:418-441: .to(device) ... .cpu().numpy()). */
+int tebscat_scat1d_forward_host(tebscat_plan* plan, const float* x_host, int64_t B,
+                                float* S_host);
+
+/* Number of kernels the last forward call on this thread launched. */
+int tebscat_last_launch_count(void);
+
+/* Measured FP32 FMA peak of `device` in TFLOP/s (bench.py's FP32 roofline denominator;
+ * MEASURED_PEAKS.json has no FP32 figure). */
+int tebscat_bench_fp32_peak(int device, double* tflops_out);
+
+const char* tebscat_last_error(void);
+int tebscat_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEBSCAT_H_ */

@@ -1,0 +1,41 @@
+// Host emulator of the step interpreter (TEST INFRASTRUCTURE ONLY).
+//
+// Compiles vae-teb_b200/csrc/scat_core.cuh as plain C++ and executes the threads of
+// every step one after another.  It lets the CPU-only test-suite check the
+// schedule builder and the task semantics (index maps, twiddles, swizzle) against
+// the oracle without a GPU.  It is never loaded by the product path.
+#define TEBSCAT_HOST_EMU 1
+#include "../../vae-teb_b200/csrc/scat_core.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace tebscat;
+
+extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths, int n_out,
+                                  int smem_complex, int n_tasks, int n_steps,
+                                  const float* arena, const int32_t* tasks, const int32_t* steps,
+                                  const float* x, long long B, float* out) {
+    std::vector<float2> S((size_t)smem_complex);
+    std::vector<float2> tw(kTwA + kTwB);
+    const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
+    for (int a = 0; a < kTwA; ++a) tw[a] = make_float2((float)cos(w0 * 128.0 * a), (float)sin(w0 * 128.0 * a));
+    for (int b = 0; b < kTwB; ++b) tw[kTwA + b] = make_float2((float)cos(w0 * b), (float)sin(w0 * b));
+    for (long long b = 0; b < B; ++b) {
+        // poison shared memory so that reads of never-written slots show up as NaNs
+        for (auto& z : S) z = make_float2(NAN, NAN);
+        SignalCtx c;
+        c.x = x + b * N;
+        c.out = out + b * (long long)n_paths * n_out;
+        c.N = N; c.pad_left = pad_left; c.log2_Np = log2_Np; c.n_out = n_out;
+        for (int s = 0; s < n_steps; ++s) {
+            for (int ti = steps[2 * s]; ti < steps[2 * s + 1]; ++ti) {
+                Task t;
+                memcpy(&t, tasks + 8 * ti, sizeof(Task));
+                for (int lt = 0; lt < t.nt; ++lt) exec_task(S.data(), tw.data(), tw.data() + kTwA, arena, c, t, lt);
+            }
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,52 @@
+"""Shared helpers of the test-suite (oracle access, emulator binding, tolerances)."""
+import ctypes
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+EMU_PATH = os.path.join(ROOT, 'tests', 'emu', 'libemu_scat.so')
+
+CONFIGS = {
+    # name: (J, N, Q, T, max_order)
+    'H': (6, 4800, 8, 64, 2),
+    'P': (11, 5760, 4, 16, 1),
+    'S': (4, 1000, 4, 16, 2),
+    'T': (5, 700, 2, 8, 2),
+    'K': (6, 512, 16, 64, 2),
+}
+
+
+def rel_l2(a, b, axis=None):
+    return np.linalg.norm(a - b, axis=axis) / np.maximum(np.linalg.norm(b, axis=axis), 1e-30)
+
+
+def path_tolerance(ref64, ref32, rel=1e-5, noise_factor=4.0):
+    """Per-path L2 error budget: rel-L2 <= 1e-5 (north_star), or -- on paths whose energy
+    is so far below the signal's that the REFERENCE's own fp32 arithmetic is noisier than
+    that -- `noise_factor` times the single-precision oracle's distance to the float64 one."""
+    return np.maximum(rel * np.linalg.norm(ref64, axis=-1),
+                      noise_factor * np.linalg.norm(ref32.astype(np.float64) - ref64, axis=-1))
+
+
+def emu_available():
+    return os.path.exists(EMU_PATH)
+
+
+def emu_forward(plan, x):
+    """Run the schedule of `plan` through the host emulator (tests/emu)."""
+    lib = ctypes.CDLL(EMU_PATH)
+    x = np.ascontiguousarray(x, np.float32)
+    B = x.shape[0]
+    out = np.full((B, plan.n_paths, plan.n_out), np.nan, np.float32)
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    tasks = np.ascontiguousarray(plan.tasks, np.int32)
+    steps = np.ascontiguousarray(plan.steps, np.int32)
+    arena = np.ascontiguousarray(plan.arena, np.float32)
+    rc = lib.emu_scat1d_forward(plan.N, plan.geo.J_pad, plan.geo.pad_left, plan.n_paths, plan.n_out,
+                                plan.smem_complex, tasks.shape[0], steps.shape[0],
+                                arena.ctypes.data_as(fp), tasks.ctypes.data_as(ip), steps.ctypes.data_as(ip),
+                                x.ctypes.data_as(fp), ctypes.c_longlong(B), out.ctypes.data_as(fp))
+    assert rc == 0
+    return out

@@ -1,0 +1,154 @@
+"""Host-side behaviour of the Scattering1D frontend (no GPU): geometry, filters, meta
+ordering and the error behaviour of the reference's frontend, re-expressed from
+kymatio/tests/scattering1d/test_torch_scattering1d.py and test_utils_scattering1d.py."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import CONFIGS, GOLDEN, ROOT
+from tebscat import Scattering1D
+from tebscat import filterbank as fbk
+from tebscat.meta import compute_meta, output_size
+
+
+@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T'])
+def test_geometry_filters_meta_match_reference(name):
+    d = np.load(os.path.join(GOLDEN, 'scat_%s.npz' % name))
+    J, N, Q, T, mo = CONFIGS[name]
+    S = Scattering1D(J, N, Q, max_order=mo, T=T)
+    assert (S.J_pad, S.pad_left, S.pad_right) == (int(d['J_pad']), int(d['pad_left']), int(d['pad_right']))
+    assert [S.ind_start[j] for j in range(J + 1)] == list(d['ind_start'])
+    assert [S.ind_end[j] for j in range(J + 1)] == list(d['ind_end'])
+    # buffers tensor0.. in the reference's registration order, fp32 (L,1)
+    bufs = dict(S.named_buffers())
+    assert len(bufs) == int(d['n_filters'])
+    assert [bufs['tensor%d' % i].shape[0] for i in range(len(bufs))] == list(d['filter_len'])
+    assert all(b.dtype == torch.float32 and b.shape[1] == 1 for b in bufs.values())
+    np.testing.assert_array_equal(S.psi1_f[0]['levels'][0].numpy()[:, 0], d['psi1_0'].astype(np.float32))
+    np.testing.assert_array_equal(S.psi1_f[-1]['levels'][0].numpy()[:, 0], d['psi1_last'].astype(np.float32))
+    np.testing.assert_array_equal(S.psi2_f[-1]['levels'][-1].numpy()[:, 0], d['psi2_last_top'].astype(np.float32))
+    np.testing.assert_array_equal(S.phi_f['levels'][0].numpy()[:, 0], d['phi_0'].astype(np.float32))
+    m = S.meta()
+    assert [tuple(int(v) for v in row if v >= 0) for row in d['keys']] == m['key']      # bit-exact ordering
+    np.testing.assert_array_equal(m['order'], d['order'])
+    np.testing.assert_array_equal(m['xi'], d['meta_xi'])
+    np.testing.assert_array_equal(m['sigma'], d['meta_sigma'])
+    np.testing.assert_array_equal(m['j'], d['meta_j'])
+    assert tuple(d['output_size']) == S.output_size(detail=True)
+    assert S.output_size() == len(m['key'])
+
+
+def test_compute_padding_and_border_indices():
+    """test_utils_scattering1d.py:8-53."""
+    assert fbk.padding(5, 16) == (8, 8)
+    with pytest.raises(ValueError) as ve:
+        fbk.padding(3, 16)
+    assert 'should be larger' in ve.value.args[0]
+    with pytest.raises(ValueError) as ve:
+        fbk.padding(6, 16)
+    assert 'Too large padding value' in ve.value.args[0]
+    rng = np.random.RandomState(42)
+    J_signal, J = 10, 6
+    n = 2 ** J_signal
+    i0 = rng.randint(0, n // 2 + 1, 1)[0]
+    i1 = rng.randint(i0 + 1, n, 1)[0]
+    x = np.ones(n)
+    x[i0:i1] = 0.
+    start, end = fbk.border_indices(J, i0, i1)
+    for j in range(J + 1):
+        xs = x[::2 ** j]
+        assert np.max(xs[start[j]:end[j]]) == 0.
+        if start[j] > 0:
+            assert np.min(xs[:start[j]]) > 0.
+        if end[j] < xs.shape[-1]:
+            assert np.min(xs[end[j]:]) > 0.
+
+
+def test_filter_properties():
+    """kymatio/tests/scattering1d/test_filters_scattering1d.py: periodisation == decimation,
+    l1 norm, Morlet zero mean, Gaussian symmetry."""
+    n = 1024
+    psi = fbk.morlet_spectrum(n, 0.2, 0.02)
+    assert abs(psi[0]) < 1e-12                                    # zero mean
+    assert abs(np.abs(np.fft.ifft(psi)).sum() - 1.0) < 1e-9       # l1 normalised
+    g = fbk.gauss_spectrum(n, 0.01)
+    np.testing.assert_allclose(g[1:], g[1:][::-1], atol=1e-14)    # symmetric
+    for k in (2, 4, 8):
+        np.testing.assert_allclose(np.fft.ifft(fbk.fold(psi, k)), np.fft.ifft(psi)[::k], atol=1e-12)
+    with pytest.raises(ValueError):
+        fbk.morlet_spectrum(n, 0.2, 0.02, P_max=5.1)
+    with pytest.raises(ValueError):
+        fbk.gauss_spectrum(n, 0.02, P_max=-1)
+
+
+def test_constructor_errors_and_options():
+    with pytest.raises(ValueError) as ve:
+        Scattering1D(4, (512, 2), 4)
+    assert 'exactly one element' in ve.value.args[0]
+    with pytest.raises(ValueError) as ve:
+        Scattering1D(4, 512.0, 4)
+    assert 'integer or a 1-tuple' in ve.value.args[0]
+    with pytest.raises(ValueError) as ve:
+        Scattering1D(4, 512, 4, T=64)
+    assert 'cannot exceed 2**J' in ve.value.args[0]
+    with pytest.raises(ImportError):
+        Scattering1D(4, 512, 4, backend='numpy')
+    S = Scattering1D(4, (512,), (4, 1))                           # tuple shape, (Q1, 1) and T=None accepted
+    assert S.T == 16 and S.N == 512
+    x = torch.zeros(2, 512)
+    S.average = False
+    with pytest.raises(ValueError) as ve:
+        S(x)
+    assert 'mutually incompatible' in ve.value.args[0]
+    S.average = True
+    S.out_type = 'doesnotexist'
+    with pytest.raises(RuntimeError) as ve:
+        S(x)
+    assert "must be one of 'array' or 'list'" in ve.value.args[0]
+    S.out_type = 'list'
+    with pytest.raises(NotImplementedError):
+        S(x)
+    S.out_type = 'array'
+    with pytest.raises(TypeError) as ve:
+        S(None)
+    assert 'should be not empty' in ve.value.args[0]
+    with pytest.raises(RuntimeError) as ve:
+        S(torch.zeros(512, 2).t())
+    assert 'must be contiguous' in ve.value.args[0]
+    with pytest.raises(ValueError):
+        S(torch.zeros(2, 100))
+    with pytest.raises(TypeError):
+        S(torch.zeros(2, 512, dtype=torch.float64))
+    with pytest.raises(TypeError) as ve:                          # no CPU path: the input must live on the GPU
+        S(x)
+    assert 'GPU' in ve.value.args[0]
+
+
+def test_large_support_is_refused_loudly():
+    S = Scattering1D(10, 2 ** 16, 8)
+    with pytest.raises(NotImplementedError):
+        S._schedule()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The C-ABI library loads and exports what include/tebscat.h declares (no compute)."""
+    from tebscat import _lib
+    header = open(os.path.join(ROOT, 'include', 'tebscat.h')).read()
+    names = set(re.findall(r'\b(tebscat_[a-z0-9_]+)\s*\(', header))
+    assert {'tebscat_plan_create', 'tebscat_scat1d_forward', 'tebscat_last_error'} <= names
+    lib = _lib.load()
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+    assert lib.tebscat_abi_version() == _lib.ABI_VERSION
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from tebscat import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libtebscat.so')
+    with pytest.raises(_lib.TebscatError) as ve:
+        _lib.load()
+    assert 'no CPU fallback' in str(ve.value)

@@ -1,0 +1,150 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI via
+the Scattering1D frontend, against the numpy oracle, the committed golden outputs of the
+live reference and the reference's own known-answer fixture."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import CONFIGS, GOLDEN, path_tolerance, rel_l2
+from oracle.scattering1d_oracle import ScatteringOracle
+
+pytestmark = pytest.mark.gpu
+
+_mods = {}
+
+
+def module_of(name):
+    from tebscat import Scattering1D
+    if name not in _mods:
+        J, N, Q, T, mo = CONFIGS[name]
+        _mods[name] = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    return _mods[name]
+
+
+def gpu_forward(name, x):
+    S, P = module_of(name)(torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda())
+    torch.cuda.synchronize()
+    return S.cpu().numpy(), P
+
+
+@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T', 'K'])
+def test_parity_with_oracle(name):
+    from tebscat.synth import ctg_batch, randn_batch
+    J, N, Q, T, mo = CONFIGS[name]
+    x = np.concatenate([randn_batch(4, N, 2, seed=4321).reshape(8, N).numpy(),
+                        ctg_batch(4, N, seed=1234).reshape(8, N).numpy()])
+    out, P = gpu_forward(name, x)
+    ref64 = ScatteringOracle(J, N, Q, T, mo)(x)
+    ref32 = ScatteringOracle(J, N, Q, T, mo, cdtype=np.complex64)(x)
+    assert out.shape == ref64.shape and tuple(P.shape) == (16, 1) + ref64.shape[1:]
+    err = np.linalg.norm(out.astype(np.float64) - ref64, axis=-1)
+    tol = path_tolerance(ref64, ref32)
+    assert np.all(err <= tol), float((err / tol).max())
+    # randn rows: the north-star bound, rel-L2 <= 1e-5 for every coefficient path
+    assert rel_l2(out[:8].astype(np.float64), ref64[:8], axis=-1).max() < 1e-5
+    assert rel_l2(out.astype(np.float64), ref64) < 1e-6
+
+
+def test_reference_known_answer_fixture():
+    """kymatio/tests/scattering1d/test_torch_scattering1d.py:82-113 on test_data_1d.npz."""
+    d = np.load(os.path.join(GOLDEN, 'kat_test_data_1d.npz'))
+    out, _ = gpu_forward('K', d['x'])
+    assert out.shape == d['Sx'].shape
+    assert np.allclose(out, d['Sx'], rtol=1e-5, atol=1e-7)
+    assert rel_l2(out, d['Sx'], axis=-1).max() < 1e-5
+
+
+@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T'])
+def test_golden_reference_outputs(name):
+    d = np.load(os.path.join(GOLDEN, 'scat_%s.npz' % name))
+    out, _ = gpu_forward(name, d['x'])
+    J, N, Q, T, mo = CONFIGS[name]
+    ref64 = ScatteringOracle(J, N, Q, T, mo)(d['x'])
+    tol = np.maximum(1e-5 * np.linalg.norm(ref64, axis=-1),
+                     4.0 * np.linalg.norm(d['S'].astype(np.float64) - ref64, axis=-1))
+    assert np.all(np.linalg.norm(out.astype(np.float64) - ref64, axis=-1) <= tol)
+    assert rel_l2(out, d['S']) < 2e-6
+    half = d['x'].shape[0] // 2                     # second half of the fixture batch is randn
+    assert rel_l2(out[half:], d['S'][half:], axis=-1).max() < 1e-5
+
+
+def test_simple_signals():
+    """The disabled-but-valid properties of test_torch_scattering1d.py:47-77."""
+    J, N, Q, T, mo = CONFIGS['H']
+    S = module_of('H')
+    meta = S.meta()
+    z, _ = S(torch.zeros(2, N, device='cuda'))
+    assert z.abs().max().item() == 0.0
+    c, _ = S(torch.full((1, N), 0.7345, device='cuda'))
+    assert c[:, 1:].abs().max().item() < 1e-6
+    assert abs(c[0, 0].mean().item() - 0.7345) < 1e-5
+    t = torch.arange(N, dtype=torch.float32)
+    for k in (37, 401, 1500):
+        s, _ = S(torch.cos(2 * np.pi * k * t / N)[None].cuda())
+        assert s[:, torch.from_numpy(meta['order']) != 1, :].abs().max().item() < 1e-2
+
+
+def test_batch_shape_agnostic_and_views():
+    """test_torch_scattering1d.py:338-386: any leading batch dims, (N,) allowed."""
+    J, N, Q, T, mo = CONFIGS['S']
+    S = module_of('S')
+    x = torch.randn(2, 3, N, device='cuda')
+    a, P = S(x)
+    assert a.shape == (2, 3, S.output_size(), S._sched[1].n_out) and P.shape[0] == 6
+    b, _ = S(x.reshape(6, N))
+    assert torch.equal(a.reshape(6, *a.shape[2:]), b)
+    v, _ = S(x[0, 0])
+    assert v.shape == a.shape[2:] and torch.equal(v, a[0, 0])
+    e, _ = S(torch.zeros(0, N, device='cuda'))
+    assert e.shape[0] == 0
+
+
+def test_host_entry_point_matches_device_entry_point():
+    J, N, Q, T, mo = CONFIGS['H']
+    S = module_of('H')
+    x = torch.randn(2500, N).pin_memory()          # > 2 chunks of the host pipeline
+    h = S.scattering_host(x)
+    d, _ = S(x.cuda())
+    assert torch.equal(h, d.cpu())
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 2: 8192 two-channel signals.  Size-independent checks: rows of a
+    repeated signal are bit-identical wherever they sit in the batch, positive homogeneity
+    S(a x) = a S(x) for a = 2^k (exact in binary floating point), and a sample of rows
+    against the oracle."""
+    from tebscat.synth import ctg_batch
+    J, N, Q, T, mo = CONFIGS['H']
+    S = module_of('H')
+    base = ctg_batch(64, N, seed=99).reshape(128, N)
+    x = base.repeat(128, 1).cuda()                 # 16384 signals
+    out, _ = S(x)
+    torch.cuda.synchronize()
+    assert out.shape == (16384, 126, 75)
+    assert torch.equal(out[:128], out[-128:]) and torch.equal(out[:128], out[8192:8320])
+    scaled, _ = S(x[:256] * 4.0)
+    assert torch.equal(scaled, out[:256] * 4.0)
+    pick = [0, 77, 127]
+    ref64 = ScatteringOracle(J, N, Q, T, mo)(base[pick].numpy())
+    ref32 = ScatteringOracle(J, N, Q, T, mo, cdtype=np.complex64)(base[pick].numpy())
+    got = out[pick].cpu().numpy().astype(np.float64)
+    assert np.all(np.linalg.norm(got - ref64, axis=-1) <= path_tolerance(ref64, ref32))
+
+
+def test_plan_validation_errors():
+    """The C ABI refuses malformed plans with an error code and a message (never throws)."""
+    import ctypes
+    from tebscat import _lib
+    from tebscat.schedule import build_plan
+    from tebscat.torch_frontend import _DevicePlan
+    J, N, Q, T, mo = CONFIGS['T']
+    p = build_plan(J, N, Q, T, mo)
+    p.tasks = p.tasks.copy()
+    p.tasks[3, 1] = 5000                            # thread range outside the CTA
+    with pytest.raises(ValueError) as ve:
+        _DevicePlan(p, 0)
+    assert 'outside the CTA' in str(ve.value)
+    rc = _lib.load().tebscat_scat1d_forward(None, None, 1, None, None)
+    assert rc == _lib.TEBSCAT_EINVAL

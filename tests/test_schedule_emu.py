@@ -1,0 +1,111 @@
+"""CPU checks of the host logic: schedule validity and, through the host emulator
+of the kernel's step interpreter (tests/emu), its semantics against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import CONFIGS, GOLDEN, emu_available, emu_forward, path_tolerance, rel_l2
+from oracle.scattering1d_oracle import ScatteringOracle
+from tebscat.schedule import (OP_FFT, OP_LOAD, OP_MULFOLD, OP_STORE, SMEM_BYTES_MAX, TW_SLOTS,
+                              bitrev_indices, build_plan, radix_split)
+
+_plans = {}
+
+
+def plan_of(name, **kw):
+    key = (name, tuple(sorted(kw.items())))
+    if key not in _plans:
+        J, N, Q, T, mo = CONFIGS[name]
+        _plans[key] = build_plan(J, N, Q, T, mo, **kw)
+    return _plans[key]
+
+
+def test_bitrev_and_radix_split():
+    assert list(bitrev_indices(8)) == [0, 4, 2, 6, 1, 5, 3, 7]
+    for n in range(1, 14):
+        s = radix_split(n)
+        assert sum(s) == n and max(s) <= 4 and len(s) == -(-n // 4)
+
+
+def _touched(t):
+    """(reads, writes) slot intervals of one task row."""
+    op = t[0] & 0xff
+    a, b, c, d = int(t[3]), int(t[4]), int(t[5]), int(t[6])
+    if op == OP_LOAD:
+        return [], [(a, a + (1 << 13))]
+    if op == OP_FFT:
+        return [(a, a + (1 << b))], [(a, a + (1 << b))]
+    if op == OP_MULFOLD:
+        return [(a, a + (1 << b))], [(d, d + (1 << (b - c)))]
+    if op == OP_STORE:
+        return [(a, a + c + d)], []
+    return [], []
+
+
+@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T', 'K'])
+def test_schedule_is_well_formed(name):
+    p = plan_of(name)
+    assert (p.smem_complex + TW_SLOTS) * 8 <= SMEM_BYTES_MAX
+    assert p.tasks.shape[1] == 8 and p.steps.shape[1] == 2
+    assert p.steps[0, 0] == 0 and p.steps[-1, 1] == p.tasks.shape[0]
+    assert np.all(p.steps[1:, 0] == p.steps[:-1, 1])
+    stored = []
+    for b, e in p.steps:
+        rows = p.tasks[b:e]
+        # thread ranges of one step are disjoint, 32-aligned and inside the CTA
+        spans = sorted((int(r[1]), int(r[1] + r[2])) for r in rows)
+        assert all(s[0] % 32 == 0 and s[1] <= p.n_threads for s in spans)
+        assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+        # no task of a step writes slots another task of the same step touches
+        acc = [_touched(r) for r in rows]
+        for i in range(len(rows)):
+            for j in range(len(rows)):
+                if i == j:
+                    continue
+                for w0, w1 in acc[i][1]:
+                    for r0, r1 in acc[j][0] + acc[j][1]:
+                        assert w1 <= r0 or r1 <= w0, 'hazard inside a step'
+        stored += [int(r[4]) for r in rows if (r[0] & 0xff) == OP_STORE]
+    assert sorted(stored) == list(range(p.n_paths))          # every channel written exactly once
+
+
+@pytest.mark.skipif(not emu_available(), reason='host emulator not built (run __graft_entry__.build())')
+@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T', 'K'])
+@pytest.mark.parametrize('max_parallel', [1, 64])
+def test_emulated_kernel_matches_oracle(name, max_parallel):
+    J, N, Q, T, mo = CONFIGS[name]
+    p = plan_of(name, max_parallel=max_parallel)
+    rng = np.random.RandomState(7)
+    x = rng.randn(2, N).astype(np.float32)
+    x[1] = 140.0 + np.cumsum(rng.randn(N)).astype(np.float32)      # baseline-dominated, CTG-like
+    out = emu_forward(p, x).astype(np.float64)
+    assert not np.isnan(out).any()
+    ref64 = ScatteringOracle(J, N, Q, T, mo)(x)
+    ref32 = ScatteringOracle(J, N, Q, T, mo, cdtype=np.complex64)(x)
+    err = np.linalg.norm(out - ref64, axis=-1)
+    assert np.all(err <= path_tolerance(ref64, ref32)), (err / path_tolerance(ref64, ref32)).max()
+    assert rel_l2(out[0], ref64[0], axis=-1).max() < 1e-5      # randn row: plain 1e-5 per path
+
+
+@pytest.mark.skipif(not emu_available(), reason='host emulator not built')
+def test_emulated_kernel_matches_reference_kat():
+    """The reference's own known-answer fixture (test_torch_scattering1d.py:82-113)."""
+    d = np.load(os.path.join(GOLDEN, 'kat_test_data_1d.npz'))
+    out = emu_forward(plan_of('K'), d['x'])
+    assert out.shape == d['Sx'].shape
+    assert rel_l2(out, d['Sx'], axis=-1).max() < 1e-5
+    assert np.allclose(out, d['Sx'], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.skipif(not emu_available(), reason='host emulator not built')
+@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T'])
+def test_emulated_kernel_matches_golden_reference_outputs(name):
+    d = np.load(os.path.join(GOLDEN, 'scat_%s.npz' % name))
+    out = emu_forward(plan_of(name), d['x']).astype(np.float64)
+    J, N, Q, T, mo = CONFIGS[name]
+    ref64 = ScatteringOracle(J, N, Q, T, mo)(d['x'])
+    tol = np.maximum(1e-5 * np.linalg.norm(ref64, axis=-1),
+                     4.0 * np.linalg.norm(d['S'].astype(np.float64) - ref64, axis=-1))
+    assert np.all(np.linalg.norm(out - ref64, axis=-1) <= tol)
+    assert rel_l2(out, d['S']) < 2e-6

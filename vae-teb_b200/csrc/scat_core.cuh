@@ -1,0 +1,295 @@
+// scat_core.cuh -- the per-CTA "step interpreter" of the fused scattering cascade.
+//
+// One CTA owns one signal at a time.  The whole cascade of
+//   kymatio/kymatio/scattering1d/core/scattering1d.py:269-370
+// (reflect pad, FFT, psi multiply + Fourier periodisation, reduced-length iFFT,
+// modulus, FFT, second-order bank, phi low-pass, unpad) runs out of shared memory
+// as a host-built schedule of STEPS; each step is a set of independent TASKS
+// assigned to disjoint thread ranges and ends in one __syncthreads().
+//
+// Spectral data lives in BIT-REVERSED bin order: forward transforms are
+// decimation-in-frequency (natural in -> bit-reversed out), inverse transforms
+// decimation-in-time (bit-reversed in -> natural out), both in place.  In that
+// order the Fourier periodisation of torch_backend.py:18-48,
+//   out[m] = mean_i in[i * L/k + m],
+// is a sum over k ADJACENT slots, so "filter multiply + periodise" is one
+// streaming pass and no transposition ever happens.  Filters are stored
+// pre-permuted (plan.py).
+//
+// The same source compiles as plain C++ (TEBSCAT_HOST_EMU) where a test harness
+// executes the threads of a step one after another -- valid because within a
+// step no task reads a slot another thread writes.  That build is test
+// infrastructure only; the product path is the CUDA kernel in tebscat.cu.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+#ifdef TEBSCAT_HOST_EMU
+#define TEB_D inline
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+#define TEB_LDG(p) (*(p))
+#define TEB_UNROLL
+#else
+#include <cuda_runtime.h>
+#define TEB_D __device__ __forceinline__
+#define TEB_LDG(p) __ldg(p)
+#define TEB_UNROLL _Pragma("unroll")
+#endif
+
+namespace tebscat {
+
+// ---- task encoding (8 x int32); keep in sync with tebscat/schedule.py ---------
+enum : int32_t {
+    OP_NOP = 0,
+    OP_LOAD = 1,     // a=dst                              reflect-padded signal -> (x, 0)
+    OP_FFT = 2,      // a=region b=log2L c=log2B d=log2R e=flags(FFT_INV | FFT_MOD)
+    OP_MULFOLD = 3,  // a=src b=log2Lsrc c=log2k d=dst e=filter offset (floats); scale 2^-sexp
+    OP_STORE = 4     // a=src b=channel c=first index d=count e=flags(ST_IMAG)
+};
+enum : int32_t { FFT_INV = 1, FFT_MOD = 2, ST_IMAG = 1 };
+
+struct Task {
+    int32_t op;    // opcode | (sexp << 8)
+    int32_t t0;    // first thread of the range
+    int32_t nt;    // threads in the range
+    int32_t a, b, c, d, e;
+};
+
+struct SignalCtx {
+    const float* x;     // this signal's N input samples
+    float* out;         // this signal's [n_paths, n_out] block
+    int32_t N, pad_left, log2_Np, n_out;
+};
+
+constexpr int kLog2TwMax = 13;                 // twiddle tables cover lengths up to 8192
+constexpr int kTwA = 1 << (kLog2TwMax - 7);    // coarse table entries: W^(128 a)
+constexpr int kTwB = 128;                      // fine table entries:   W^b
+
+// ---- complex helpers -----------------------------------------------------------
+TEB_D float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+TEB_D float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+TEB_D float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+TEB_D float2 cmulc(float2 a, float2 b) {   // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+// multiply by exp(SGN * i*pi/2)
+template <int SGN> TEB_D float2 rot90(float2 a) {
+    return SGN < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+// multiply by the constant (c + SGN*i*s)
+template <int SGN> TEB_D float2 cmulk(float2 a, float c, float s) {
+    return SGN < 0 ? make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s))
+                   : make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.y, c, a.x * s));
+}
+
+// shared-memory slot of logical complex index i: XOR swizzle that keeps every access
+// pattern of the passes below (unit stride, stride 2^m, 16 contiguous per thread)
+// free of bank conflicts for 8-byte accesses.
+TEB_D int swz(int i) { return i ^ ((i >> 4) & 15); }
+
+// ---- register DFTs --------------------------------------------------------------
+// dft<R, SGN>(v): v[] <- DFT_R of v[] with kernel exp(SGN*2*pi*i*j*q/R); on return
+// register r holds frequency qmap<R>(r).
+template <int R> TEB_D constexpr int qmap(int r) {
+    return R == 16 ? ((r >> 2) + 4 * (r & 3)) : R == 8 ? ((r >> 2) + 2 * (r & 3)) : r;
+}
+template <int LOGR> TEB_D constexpr int brev(int q) {
+    int r = 0;
+    for (int b = 0; b < LOGR; ++b) r |= ((q >> b) & 1) << (LOGR - 1 - b);
+    return r;
+}
+
+template <int SGN> TEB_D void dft2(float2& a, float2& b) {
+    float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+template <int SGN> TEB_D void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = rot90<SGN>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = cadd(t1, t3);
+    a3 = csub(t1, t3);
+}
+
+template <int R, int SGN> struct Dft;
+template <int SGN> struct Dft<2, SGN> {
+    static TEB_D void run(float2 (&v)[2]) { dft2<SGN>(v[0], v[1]); }
+};
+template <int SGN> struct Dft<4, SGN> {
+    static TEB_D void run(float2 (&v)[4]) { dft4<SGN>(v[0], v[1], v[2], v[3]); }
+};
+template <int SGN> struct Dft<8, SGN> {
+    static TEB_D void run(float2 (&v)[8]) {
+        const float h = 0.70710678118654752f;
+        TEB_UNROLL for (int b = 0; b < 4; ++b) dft2<SGN>(v[b], v[4 + b]);
+        v[5] = cmulk<SGN>(v[5], h, h);        // w8^1
+        v[6] = rot90<SGN>(v[6]);              // w8^2
+        v[7] = cmulk<SGN>(v[7], -h, h);       // w8^3
+        dft4<SGN>(v[0], v[1], v[2], v[3]);
+        dft4<SGN>(v[4], v[5], v[6], v[7]);
+    }
+};
+template <int SGN> struct Dft<16, SGN> {
+    static TEB_D void run(float2 (&v)[16]) {
+        const float h = 0.70710678118654752f, c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;
+        TEB_UNROLL for (int b = 0; b < 4; ++b) dft4<SGN>(v[b], v[4 + b], v[8 + b], v[12 + b]);
+        // v[4*q1 + b] *= w16^(b*q1)
+        v[5] = cmulk<SGN>(v[5], c1, s1);      // w16^1
+        v[6] = cmulk<SGN>(v[6], h, h);        // w16^2
+        v[7] = cmulk<SGN>(v[7], s1, c1);      // w16^3
+        v[9] = cmulk<SGN>(v[9], h, h);        // w16^2
+        v[10] = rot90<SGN>(v[10]);            // w16^4
+        v[11] = cmulk<SGN>(v[11], -h, h);     // w16^6
+        v[13] = cmulk<SGN>(v[13], s1, c1);    // w16^3
+        v[14] = cmulk<SGN>(v[14], -h, h);     // w16^6
+        v[15] = cmulk<SGN>(v[15], -c1, -s1);  // w16^9
+        TEB_UNROLL for (int q1 = 0; q1 < 4; ++q1)
+            dft4<SGN>(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
+    }
+};
+
+// W_8192^k = exp(-2*pi*i*k/8192) from the two shared-memory tables
+TEB_D float2 twiddle(const float2* twA, const float2* twB, int k) {
+    return cmul(twA[k >> 7], twB[k & 127]);
+}
+
+// powers w[q] = W^(k1*q), q = 1..R-1, from log2(R) table lookups and a product tree
+template <int R> TEB_D void twiddle_powers(const float2* twA, const float2* twB, int k1, float2 (&w)[R]) {
+    const int mask = (1 << kLog2TwMax) - 1;
+    TEB_UNROLL for (int q = 1; q < R; q <<= 1) w[q] = twiddle(twA, twB, (k1 * q) & mask);
+    TEB_UNROLL for (int q = 3; q < R; ++q) {
+        if ((q & (q - 1)) != 0) {                  // not a power of two
+            int hi = 1;
+            while ((hi << 1) <= q) hi <<= 1;       // top set bit
+            w[q] = cmul(w[hi], w[q - hi]);
+        }
+    }
+}
+
+// One radix-2^LOGR pass over butterfly u of a length-2^logL transform stored at `base`.
+//   forward (INV=0): decimation in frequency, block size 2^logB, natural -> bit-reversed
+//   inverse (INV=1): decimation in time, the exact adjoint of the forward pass
+template <int LOGR, bool INV, bool MOD>
+TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int base, int logB, int u) {
+    constexpr int R = 1 << LOGR;
+    const int logs = logB - LOGR;                  // log2 of the sub-block stride
+    const int i0 = u & ((1 << logs) - 1);
+    const int blk = u >> logs;
+    const int p0 = base + (blk << logB) + i0;
+    float2 v[R];
+    float2 w[R];
+    const int k1 = i0 << (kLog2TwMax - logB);
+    if (logs > 0) twiddle_powers<R>(twA, twB, k1, w);
+    if (!INV) {
+        TEB_UNROLL for (int j = 0; j < R; ++j) v[j] = S[swz(p0 + (j << logs))];
+        Dft<R, -1>::run(v);
+        TEB_UNROLL for (int r = 0; r < R; ++r) {
+            const int q = qmap<R>(r);
+            float2 y = v[r];
+            if (q != 0 && logs > 0) y = cmul(y, w[q]);
+            S[swz(p0 + (brev<LOGR>(q) << logs))] = y;
+        }
+    } else {
+        TEB_UNROLL for (int q = 0; q < R; ++q) {
+            float2 y = S[swz(p0 + (brev<LOGR>(q) << logs))];
+            if (q != 0 && logs > 0) y = cmulc(y, w[q]);
+            v[q] = y;
+        }
+        Dft<R, +1>::run(v);
+        TEB_UNROLL for (int r = 0; r < R; ++r) {
+            float2 y = v[r];
+            if (MOD) y = make_float2(sqrtf(fmaf(y.x, y.x, y.y * y.y)), 0.f);
+            S[swz(p0 + (qmap<R>(r) << logs))] = y;
+        }
+    }
+}
+
+template <int LOGR>
+TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task& t, int lt) {
+    const int n_bfly = 1 << (t.b - LOGR);
+    const bool inv = (t.e & FFT_INV) != 0, mod = (t.e & FFT_MOD) != 0;
+    for (int u = lt; u < n_bfly; u += t.nt) {
+        if (!inv) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, t.c, u);
+        else if (!mod) fft_butterfly<LOGR, true, false>(S, twA, twB, t.a, t.c, u);
+        else fft_butterfly<LOGR, true, true>(S, twA, twB, t.a, t.c, u);
+    }
+}
+
+// dst[m] = 2^-sexp * sum_{i<k} src[m*k + i] * filt[m*k + i]      (bit-reversed bin order)
+TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& t, int lt) {
+    const int logk = t.c;
+    const int k = 1 << logk;
+    const int n_dst = 1 << (t.b - logk);
+    const float scale = ldexpf(1.0f, -(t.op >> 8));
+    const float* f = arena + t.e;
+    for (int m = lt; m < n_dst; m += t.nt) {
+        float ax = 0.f, ay = 0.f;
+        const int s0 = t.a + (m << logk);
+        const float* fm = f + (m << logk);
+        if (logk >= 2) {
+            for (int i = 0; i < k; i += 4) {
+                const float4 g = TEB_LDG(reinterpret_cast<const float4*>(fm + i));
+                float2 z0 = S[swz(s0 + i)], z1 = S[swz(s0 + i + 1)];
+                float2 z2 = S[swz(s0 + i + 2)], z3 = S[swz(s0 + i + 3)];
+                ax = fmaf(z0.x, g.x, ax); ay = fmaf(z0.y, g.x, ay);
+                ax = fmaf(z1.x, g.y, ax); ay = fmaf(z1.y, g.y, ay);
+                ax = fmaf(z2.x, g.z, ax); ay = fmaf(z2.y, g.z, ay);
+                ax = fmaf(z3.x, g.w, ax); ay = fmaf(z3.y, g.w, ay);
+            }
+        } else {
+            for (int i = 0; i < k; ++i) {
+                const float g = TEB_LDG(fm + i);
+                const float2 z = S[swz(s0 + i)];
+                ax = fmaf(z.x, g, ax);
+                ay = fmaf(z.y, g, ay);
+            }
+        }
+        S[swz(t.d + m)] = make_float2(ax * scale, ay * scale);
+    }
+}
+
+// reflect padding of torch_backend.py:50-78 (F.pad(..., mode='reflect'); pad < N)
+TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
+    const int Np = 1 << c.log2_Np;
+    for (int i = lt; i < Np; i += t.nt) {
+        int r = i - c.pad_left;
+        if (r < 0) r = -r;
+        if (r >= c.N) r = 2 * (c.N - 1) - r;
+        S[swz(t.a + i)] = make_float2(TEB_LDG(c.x + r), 0.f);
+    }
+}
+
+// unpad (torch_backend.py:80-102) + concatenate (kymatio/backend/torch_backend.py:143-145)
+TEB_D void store_task(const float2* S, const SignalCtx& c, const Task& t, int lt) {
+    float* o = c.out + (int64_t)t.b * c.n_out;
+    for (int i = lt; i < t.d; i += t.nt) {
+        const float2 z = S[swz(t.a + t.c + i)];
+        o[i] = (t.e & ST_IMAG) ? z.y : z.x;
+    }
+}
+
+TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const float* __restrict__ arena,
+                     const SignalCtx& c, const Task& t, int lt) {
+    switch (t.op & 0xff) {
+        case OP_LOAD: load_task(S, c, t, lt); break;
+        case OP_FFT:
+            switch (t.d) {
+                case 4: fft_task<4>(S, twA, twB, t, lt); break;
+                case 3: fft_task<3>(S, twA, twB, t, lt); break;
+                case 2: fft_task<2>(S, twA, twB, t, lt); break;
+                default: fft_task<1>(S, twA, twB, t, lt); break;
+            }
+            break;
+        case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
+        case OP_STORE: store_task(S, c, t, lt); break;
+        default: break;
+    }
+}
+
+}  // namespace tebscat

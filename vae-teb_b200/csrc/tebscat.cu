@@ -1,0 +1,296 @@
+// tebscat.cu -- C ABI (include/tebscat.h) + the sm_100a kernels of the scattering path.
+//
+// Product path only: there is no CPU fallback here.  Every entry point fails with
+// TEBSCAT_ECUDA when no CUDA device is usable.
+#include "../../include/tebscat.h"
+#include "scat_core.cuh"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+using namespace tebscat;
+
+// ---------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(TEBSCAT_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------
+struct KParams {
+    const float* arena;      // filters, fp32, bit-reversed bin order
+    const float2* tw;        // kTwA coarse + kTwB fine twiddles
+    const int4* tasks;       // 2 x int4 per task
+    const int2* steps;       // [task_begin, task_end) per step
+    int32_t n_steps;
+    int32_t smem_complex;
+    int32_t N, pad_left, log2_Np, n_paths, n_out;
+};
+
+// One CTA per SM, persistent over the batch: signal b, b + gridDim.x, ...
+__global__ void __launch_bounds__(512, 1)
+scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ out, long long B) {
+    extern __shared__ __align__(16) float2 smem[];
+    float2* S = smem;
+    float2* twA = smem + p.smem_complex;
+    float2* twB = twA + kTwA;
+    for (int i = threadIdx.x; i < kTwA + kTwB; i += blockDim.x) twA[i] = p.tw[i];
+    __syncthreads();
+
+    const int tid = threadIdx.x;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        SignalCtx c;
+        c.x = x + b * p.N;
+        c.out = out + b * (long long)p.n_paths * p.n_out;
+        c.N = p.N;
+        c.pad_left = p.pad_left;
+        c.log2_Np = p.log2_Np;
+        c.n_out = p.n_out;
+        for (int s = 0; s < p.n_steps; ++s) {
+            const int2 st = __ldg(p.steps + s);
+            for (int ti = st.x; ti < st.y; ++ti) {
+                const int4 lo = __ldg(p.tasks + 2 * ti);
+                const int lt = tid - lo.y;
+                if ((unsigned)lt < (unsigned)lo.z) {
+                    const int4 hi = __ldg(p.tasks + 2 * ti + 1);
+                    Task t;
+                    t.op = lo.x; t.t0 = lo.y; t.nt = lo.z; t.a = lo.w;
+                    t.b = hi.x; t.c = hi.y; t.d = hi.z; t.e = hi.w;
+                    exec_task(S, twA, twB, p.arena, c, t, lt);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------
+struct HostPipe {            // resources of the host-buffer entry point, created lazily
+    bool ready = false;
+    int64_t chunk = 0;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    float* d_x[2] = {nullptr, nullptr};
+    float* d_S[2] = {nullptr, nullptr};
+};
+
+struct tebscat_plan {
+    tebscat_plan_desc desc;
+    int device = 0;
+    int n_sms = 0;
+    size_t smem_bytes = 0;
+    float* d_arena = nullptr;
+    float2* d_tw = nullptr;
+    int32_t* d_tasks = nullptr;
+    int32_t* d_steps = nullptr;
+    KParams kp;
+    HostPipe pipe;
+    std::mutex pipe_mu;
+};
+
+static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, const int32_t* steps,
+                             size_t n_floats) {
+    const int cap = d.smem_complex;
+    for (int s = 0; s < d.n_steps; ++s) {
+        const int b = steps[2 * s], e = steps[2 * s + 1];
+        if (b < 0 || e < b || e > d.n_tasks) return fail(TEBSCAT_EINVAL, "step %d: bad task range [%d,%d)", s, b, e);
+    }
+    for (int i = 0; i < d.n_tasks; ++i) {
+        const int32_t* t = tasks + 8 * i;
+        const int op = t[0] & 0xff;
+        if (t[1] < 0 || t[2] <= 0 || t[1] + t[2] > d.n_threads)
+            return fail(TEBSCAT_EINVAL, "task %d: thread range [%d,+%d) outside the CTA", i, t[1], t[2]);
+        switch (op) {
+            case OP_LOAD:
+                if (t[3] < 0 || (t[3] & 15) || t[3] + (1 << d.log2_Np) > cap) return fail(TEBSCAT_EINVAL, "task %d: LOAD out of range", i);
+                break;
+            case OP_FFT:
+                if (t[4] < 1 || t[4] > kLog2TwMax || t[5] > t[4] || t[6] < 1 || t[6] > 4 || t[6] > t[5] ||
+                    t[3] < 0 || (t[3] & 15) || ((t[3] + (1 << t[4]) + 15) & ~15) > cap)
+                    return fail(TEBSCAT_EINVAL, "task %d: bad FFT pass (L=2^%d B=2^%d R=2^%d at %d)", i, t[4], t[5], t[6], t[3]);
+                break;
+            case OP_MULFOLD: {
+                const int n_dst = 1 << (t[4] - t[5]);
+                if (t[5] < 0 || t[5] > t[4] || t[3] < 0 || (t[3] & 15) || ((t[3] + (1 << t[4]) + 15) & ~15) > cap ||
+                    t[6] < 0 || (t[6] & 15) || ((t[6] + n_dst + 15) & ~15) > cap || t[7] < 0 ||
+                    (size_t)t[7] + ((size_t)1 << t[4]) > n_floats || (t[7] & 3))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD", i);
+                break;
+            }
+            case OP_STORE:
+                if (t[4] < 0 || t[4] >= d.n_paths || t[6] != d.n_out || t[3] < 0 || (t[3] & 15) || t[5] < 0 ||
+                    ((t[3] + t[5] + t[6] + 15) & ~15) > cap)
+                    return fail(TEBSCAT_EINVAL, "task %d: bad STORE", i);
+                break;
+            case OP_NOP:
+                break;
+            default:
+                return fail(TEBSCAT_EINVAL, "task %d: unknown opcode %d", i, op);
+        }
+    }
+    return TEBSCAT_OK;
+}
+
+extern "C" int tebscat_abi_version(void) { return TEBSCAT_ABI_VERSION; }
+extern "C" const char* tebscat_last_error(void) { return g_err; }
+extern "C" int tebscat_last_launch_count(void) { return g_launches; }
+
+extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* arena, size_t n_floats,
+                                   const int32_t* tasks, const int32_t* steps, int device,
+                                   tebscat_plan** out) {
+    if (!desc || !arena || !tasks || !steps || !out) return fail(TEBSCAT_EINVAL, "null argument");
+    if (desc->abi_version != TEBSCAT_ABI_VERSION)
+        return fail(TEBSCAT_EINVAL, "ABI version %d != %d", desc->abi_version, TEBSCAT_ABI_VERSION);
+    if (desc->log2_Np < 1 || desc->log2_Np > kLog2TwMax)
+        return fail(TEBSCAT_EUNSUPPORTED, "padded length 2^%d exceeds the single-CTA limit 2^%d", desc->log2_Np, kLog2TwMax);
+    if (desc->N < 2 || desc->pad_left < 0 || desc->pad_left >= desc->N ||
+        (1 << desc->log2_Np) - desc->N - desc->pad_left >= desc->N || (1 << desc->log2_Np) < desc->N)
+        return fail(TEBSCAT_EINVAL, "Indefinite padding size (larger than tensor).");
+    if (desc->n_threads != 512) return fail(TEBSCAT_EUNSUPPORTED, "schedules must target 512-thread CTAs");
+    if (desc->n_paths < 1 || desc->n_out < 1 || desc->n_tasks < 1 || desc->n_steps < 1 || desc->smem_complex < 1)
+        return fail(TEBSCAT_EINVAL, "empty plan");
+    if (int rc = validate_schedule(*desc, tasks, steps, n_floats)) return rc;
+
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(TEBSCAT_EINVAL, "device %d not in [0,%d)", device, n_dev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+
+    tebscat_plan* p = new tebscat_plan();
+    p->desc = *desc;
+    p->device = device;
+    p->n_sms = prop.multiProcessorCount;
+    p->smem_bytes = ((size_t)desc->smem_complex + kTwA + kTwB) * sizeof(float2);
+    if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+        delete p;
+        return fail(TEBSCAT_EUNSUPPORTED, "schedule needs %zu B of shared memory, device offers %zu",
+                    p->smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
+    }
+    std::vector<float2> tw(kTwA + kTwB);
+    const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
+    for (int a = 0; a < kTwA; ++a) tw[a] = make_float2((float)cos(w0 * 128.0 * a), (float)sin(w0 * 128.0 * a));
+    for (int b = 0; b < kTwB; ++b) tw[kTwA + b] = make_float2((float)cos(w0 * b), (float)sin(w0 * b));
+
+    CU(cudaMalloc(&p->d_arena, n_floats * sizeof(float)));
+    CU(cudaMalloc(&p->d_tw, tw.size() * sizeof(float2)));
+    CU(cudaMalloc(&p->d_tasks, (size_t)desc->n_tasks * 8 * sizeof(int32_t)));
+    CU(cudaMalloc(&p->d_steps, (size_t)desc->n_steps * 2 * sizeof(int32_t)));
+    CU(cudaMemcpy(p->d_arena, arena, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_tasks, tasks, (size_t)desc->n_tasks * 8 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_steps, steps, (size_t)desc->n_steps * 2 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(scat1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+
+    KParams& k = p->kp;
+    k.arena = p->d_arena;
+    k.tw = p->d_tw;
+    k.tasks = reinterpret_cast<const int4*>(p->d_tasks);
+    k.steps = reinterpret_cast<const int2*>(p->d_steps);
+    k.n_steps = desc->n_steps;
+    k.smem_complex = desc->smem_complex;
+    k.N = desc->N;
+    k.pad_left = desc->pad_left;
+    k.log2_Np = desc->log2_Np;
+    k.n_paths = desc->n_paths;
+    k.n_out = desc->n_out;
+    *out = p;
+    return TEBSCAT_OK;
+}
+
+extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->pipe.ready) {
+        for (int i = 0; i < 2; ++i) {
+            cudaStreamDestroy(p->pipe.stream[i]);
+            cudaEventDestroy(p->pipe.done[i]);
+            cudaFree(p->pipe.d_x[i]);
+            cudaFree(p->pipe.d_S[i]);
+        }
+    }
+    cudaFree(p->d_arena);
+    cudaFree(p->d_tw);
+    cudaFree(p->d_tasks);
+    cudaFree(p->d_steps);
+    delete p;
+}
+
+static int launch_scat1d(const tebscat_plan* p, const float* x, int64_t B, float* S, cudaStream_t st) {
+    if (B == 0) return TEBSCAT_OK;
+    const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
+    scat1d_kernel<<<grid, p->desc.n_threads, p->smem_bytes, st>>>(p->kp, x, S, (long long)B);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+extern "C" int tebscat_scat1d_forward(const tebscat_plan* p, const float* x_dev, int64_t B, float* S_dev,
+                                      void* stream) {
+    g_launches = 0;
+    if (!p || B < 0 || (B > 0 && (!x_dev || !S_dev))) return fail(TEBSCAT_EINVAL, "null argument");
+    int cur = -1;
+    CU(cudaGetDevice(&cur));
+    if (cur != p->device) CU(cudaSetDevice(p->device));
+    int rc = launch_scat1d(p, x_dev, B, S_dev, (cudaStream_t)stream);
+    if (cur != p->device && cur >= 0) cudaSetDevice(cur);
+    return rc;
+}
+
+extern "C" int tebscat_scat1d_forward_host(tebscat_plan* p, const float* x_host, int64_t B, float* S_host) {
+    g_launches = 0;
+    if (!p || B < 0 || (B > 0 && (!x_host || !S_host))) return fail(TEBSCAT_EINVAL, "null argument");
+    if (B == 0) return TEBSCAT_OK;
+    std::lock_guard<std::mutex> lock(p->pipe_mu);
+    CU(cudaSetDevice(p->device));
+    HostPipe& hp = p->pipe;
+    const size_t in_f = (size_t)p->desc.N, out_f = (size_t)p->desc.n_paths * p->desc.n_out;
+    if (!hp.ready) {
+        hp.chunk = (int64_t)p->n_sms * 8;          // 8 signals per SM per chunk
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
+            CU(cudaMalloc(&hp.d_x[i], hp.chunk * in_f * sizeof(float)));
+            CU(cudaMalloc(&hp.d_S[i], hp.chunk * out_f * sizeof(float)));
+        }
+        hp.ready = true;
+    }
+    int slot = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += hp.chunk, slot ^= 1) {
+        const int64_t nb = (B - b0 < hp.chunk) ? (B - b0) : hp.chunk;
+        cudaStream_t st = hp.stream[slot];
+        // the slot's previous D2H is ordered before this H2D by stream order
+        CU(cudaMemcpyAsync(hp.d_x[slot], x_host + b0 * in_f, nb * in_f * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (int rc = launch_scat1d(p, hp.d_x[slot], nb, hp.d_S[slot], st)) return rc;
+        CU(cudaMemcpyAsync(S_host + b0 * out_f, hp.d_S[slot], nb * out_f * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(hp.stream[0]));
+    CU(cudaStreamSynchronize(hp.stream[1]));
+    return TEBSCAT_OK;
+}

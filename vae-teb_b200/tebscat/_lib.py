@@ -1,0 +1,78 @@
+"""ctypes binding of the C ABI declared in include/tebscat.h.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).
+There is no fallback: if the library is missing or no CUDA device is usable the
+product path raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtebscat.so')
+ABI_VERSION = 1
+
+TEBSCAT_OK, TEBSCAT_EINVAL, TEBSCAT_ECUDA, TEBSCAT_EUNSUPPORTED = 0, 1, 2, 3
+
+
+class PlanDesc(ctypes.Structure):
+    _fields_ = [('abi_version', ctypes.c_int32), ('N', ctypes.c_int32), ('log2_Np', ctypes.c_int32),
+                ('pad_left', ctypes.c_int32), ('n_paths', ctypes.c_int32), ('n_out', ctypes.c_int32),
+                ('n_threads', ctypes.c_int32), ('smem_complex', ctypes.c_int32),
+                ('n_tasks', ctypes.c_int32), ('n_steps', ctypes.c_int32),
+                ('reserved', ctypes.c_int32 * 6)]
+
+
+class PhaseDesc(ctypes.Structure):
+    _fields_ = [('abi_version', ctypes.c_int32), ('N', ctypes.c_int32), ('log2_Np', ctypes.c_int32),
+                ('pad_left', ctypes.c_int32), ('n_filters', ctypes.c_int32), ('n_pairs', ctypes.c_int32),
+                ('dec', ctypes.c_int32), ('n_bins', ctypes.c_int32), ('out_start', ctypes.c_int32),
+                ('n_out', ctypes.c_int32), ('reserved', ctypes.c_int32 * 6)]
+
+
+_lib = None
+
+
+class TebscatError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libtebscat.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TebscatError(
+            'tebscat CUDA library not found at %s; build it with '
+            '`python -c "import __graft_entry__ as g; g.build()"` from the repository root. '
+            'There is no CPU fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32p, fp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)
+    lib.tebscat_abi_version.restype = ctypes.c_int
+    lib.tebscat_last_error.restype = ctypes.c_char_p
+    lib.tebscat_last_launch_count.restype = ctypes.c_int
+    lib.tebscat_plan_create.restype = ctypes.c_int
+    lib.tebscat_plan_create.argtypes = [ctypes.POINTER(PlanDesc), fp, ctypes.c_size_t, i32p, i32p,
+                                        ctypes.c_int, ctypes.POINTER(vp)]
+    lib.tebscat_plan_destroy.restype = None
+    lib.tebscat_plan_destroy.argtypes = [vp]
+    lib.tebscat_scat1d_forward.restype = ctypes.c_int
+    lib.tebscat_scat1d_forward.argtypes = [vp, vp, ctypes.c_int64, vp, vp]
+    lib.tebscat_scat1d_forward_host.restype = ctypes.c_int
+    lib.tebscat_scat1d_forward_host.argtypes = [vp, vp, ctypes.c_int64, vp]
+    lib.tebscat_bench_fp32_peak.restype = ctypes.c_int
+    lib.tebscat_bench_fp32_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    if lib.tebscat_abi_version() != ABI_VERSION:
+        raise TebscatError('libtebscat.so ABI %d != binding %d; rebuild' % (lib.tebscat_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != TEBSCAT_OK:
+        msg = load().tebscat_last_error().decode('utf-8', 'replace')
+        if rc == TEBSCAT_EUNSUPPORTED:
+            raise NotImplementedError(msg)
+        if rc == TEBSCAT_EINVAL:
+            raise ValueError(msg)
+        raise TebscatError(msg)

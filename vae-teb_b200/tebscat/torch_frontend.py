@@ -1,0 +1,252 @@
+"""``Scattering1D`` -- the reference's torch frontend surface on the fused CUDA path.
+
+Same constructor, attributes, ``forward``/``scattering`` (returning ``[S, P]``),
+``meta()`` and ``output_size()`` as ``ScatteringTorch1D``
+(kymatio/scattering1d/frontend/torch_frontend.py:10-255 with
+frontend/base_frontend.py:12-119), so it drops into
+``hdf5_dataset/kymatio_phase_scattering.py:92-95`` and
+``hdf5_dataset/create_hdf5_dataset.py:360``.  The transform itself is one call
+into libtebscat.so (include/tebscat.h); there is no torch/CPU implementation
+behind it.
+
+Differences from the fork, all on the lenient side:
+ * ``T=None`` means ``2**J`` (the fork crashes);
+ * ``Q`` may be an int or a ``(Q1, 1)`` tuple (the fork takes ints only);
+ * options outside the fused fast path (``average=False``, ``out_type='list'``,
+   ``vectorize=False``, ``oversampling>0``) raise ``NotImplementedError``.
+"""
+import ctypes
+import math
+import numbers
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import filterbank as fbk
+from .meta import compute_meta, output_size
+from .schedule import build_plan
+
+
+class _DevicePlan:
+    """Owner of one tebscat_plan handle (one per device)."""
+
+    def __init__(self, plan, device_index):
+        lib = _lib.load()
+        desc = _lib.PlanDesc()
+        desc.abi_version = _lib.ABI_VERSION
+        desc.N = plan.N
+        desc.log2_Np = plan.geo.J_pad
+        desc.pad_left = plan.geo.pad_left
+        desc.n_paths = plan.n_paths
+        desc.n_out = plan.n_out
+        desc.n_threads = plan.n_threads
+        desc.smem_complex = plan.smem_complex
+        desc.n_tasks = plan.tasks.shape[0]
+        desc.n_steps = plan.steps.shape[0]
+        arena = np.ascontiguousarray(plan.arena, np.float32)
+        tasks = np.ascontiguousarray(plan.tasks, np.int32)
+        steps = np.ascontiguousarray(plan.steps, np.int32)
+        handle = ctypes.c_void_p()
+        rc = lib.tebscat_plan_create(
+            ctypes.byref(desc), arena.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), arena.size,
+            tasks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+            steps.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(device_index), ctypes.byref(handle))
+        _lib.check(rc)
+        self.handle = handle
+        self._lib = lib
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self._lib.tebscat_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Scattering1D(nn.Module):
+    def __init__(self, J, shape, Q=1, max_order=2, average=True, oversampling=0, vectorize=True,
+                 out_type='array', backend='torch', T=None):
+        super().__init__()
+        self.frontend_name = 'torch'
+        self.J = J
+        self.shape = shape
+        self.Q = Q
+        self.max_order = max_order
+        self.average = average
+        self.oversampling = oversampling
+        self.vectorize = vectorize
+        self.out_type = out_type
+        self.T = T
+        if isinstance(backend, str):
+            if not backend.startswith('torch'):
+                raise ImportError('The backend ' + backend + ' can not be called from the frontend torch.')
+        self.backend = 'tebscat'
+        self.build()
+        self.create_filters()
+        self.register_filters()
+        self._plans = {}
+        self._host_plan = None
+        self._sched = None
+
+    # ---- base_frontend.py:27-77 ------------------------------------------------
+    def build(self):
+        self.r_psi = fbk.R_PSI
+        self.sigma0 = fbk.SIGMA0
+        self.alpha = fbk.ALPHA
+        self.P_max = fbk.P_MAX
+        self.eps = fbk.EPS
+        self.criterion_amplitude = fbk.CRITERION_AMPLITUDE
+        self.normalize = 'l1'
+        if isinstance(self.shape, numbers.Integral):
+            self.N = int(self.shape)
+        elif isinstance(self.shape, tuple):
+            self.N = self.shape[0]
+            if len(self.shape) > 1:
+                raise ValueError("If shape is specified as a tuple, it must "
+                                 "have exactly one element")
+        else:
+            raise ValueError("shape must be an integer or a 1-tuple")
+        if self.T is None:
+            self.T = 2 ** self.J
+        elif self.T > 2 ** self.J:
+            raise ValueError("The temporal support T of the low-pass filter "
+                             "cannot exceed 2**J (got {} > {})".format(self.T, 2 ** self.J))
+        if self.max_order not in (1, 2):
+            raise ValueError('max_order must be 1 or 2, got {}'.format(self.max_order))
+        self._Q1 = fbk._as_Q1(self.Q)
+        geo = fbk.build_geometry(self.N, self.J, self._Q1, self.T)
+        self.J_pad = geo.J_pad
+        self.pad_left, self.pad_right = geo.pad_left, geo.pad_right
+        self.ind_start, self.ind_end = geo.ind_start, geo.ind_end
+        self._geo = geo
+
+    # ---- base_frontend.py:79-85 + torch_frontend.py:75-97 ----------------------
+    def create_filters(self):
+        self._bank = fbk.build_filter_bank(self.J_pad, self.J, self._Q1, self.T)
+
+    def register_filters(self):
+        """Filters as fp32 ``(L, 1)`` buffers ``tensor0..`` in the reference's order
+        (phi levels, psi1, psi2 levels) and the dict views ``phi_f/psi1_f/psi2_f``."""
+        n = 0
+
+        def reg(a):
+            nonlocal n
+            t = torch.from_numpy(a).float().view(-1, 1)
+            self.register_buffer('tensor' + str(n), t)
+            n += 1
+            return t
+
+        b = self._bank
+        self.phi_f = {'levels': [reg(a) for a in b.phi.levels], 'xi': 0, 'sigma': b.phi.sigma, 'j': 0}
+        self.psi1_f = [{'levels': [reg(a) for a in p.levels], 'xi': p.xi, 'sigma': p.sigma, 'j': p.j}
+                       for p in b.psi1]
+        self.psi2_f = [{'levels': [reg(a) for a in p.levels], 'xi': p.xi, 'sigma': p.sigma, 'j': p.j}
+                       for p in b.psi2]
+
+    def load_filters(self):
+        buffers = dict(self.named_buffers())
+        n = 0
+        for f in [self.phi_f] + self.psi1_f + self.psi2_f:
+            for level in range(len(f['levels'])):
+                f['levels'][level] = buffers['tensor' + str(n)]
+                n += 1
+
+    # ---- metadata ----------------------------------------------------------------
+    def meta(self):
+        return compute_meta(self.J, self._Q1, self.T, max_order=self.max_order)
+
+    def output_size(self, detail=False):
+        return output_size(self.J, self._Q1, self.T, max_order=self.max_order, detail=detail)
+
+    # ---- plan handling -------------------------------------------------------------
+    def _schedule(self):
+        key = (self.J, self.N, self._Q1, self.T, self.max_order)
+        if self._sched is None or self._sched[0] != key:
+            self._sched = (key, build_plan(self.J, self.N, self._Q1, self.T, self.max_order))
+            self._plans = {}
+        return self._sched[1]
+
+    def _plan_for(self, device_index):
+        sched = self._schedule()
+        if device_index not in self._plans:
+            self._plans[device_index] = _DevicePlan(sched, device_index)
+        return self._plans[device_index]
+
+    def _check_options(self):
+        if self.out_type not in ('array', 'list'):
+            raise RuntimeError("The out_type must be one of 'array' or 'list'.")
+        if not self.average and self.out_type == 'array' and self.vectorize:
+            raise ValueError("Options average=False, out_type='array' and "
+                             "vectorize=True are mutually incompatible. "
+                             "Please set out_type to 'list' or vectorize to "
+                             "False.")
+        if not self.vectorize:
+            warnings.warn("The vectorize option is deprecated and will be "
+                          "removed in version 0.3. Please set "
+                          "out_type='list' for equivalent functionality.", DeprecationWarning)
+        if (not self.average) or self.out_type != 'array' or (not self.vectorize) or self.oversampling != 0:
+            raise NotImplementedError(
+                'the fused CUDA path implements average=True, out_type=\'array\', vectorize=True, '
+                'oversampling=0 (got average=%r out_type=%r vectorize=%r oversampling=%r); '
+                'there is no fallback path' % (self.average, self.out_type, self.vectorize, self.oversampling))
+
+    # ---- forward ----------------------------------------------------------------------
+    def forward(self, x):
+        if x is None:
+            raise TypeError('The input should be not empty.')
+        if not x.is_contiguous():
+            raise RuntimeError('Tensors must be contiguous.')
+        return self.scattering(x)
+
+    def scattering(self, x):
+        if len(x.shape) < 1:
+            raise ValueError('Input tensor x should have at least one axis, got {}'.format(len(x.shape)))
+        self._check_options()
+        if x.shape[-1] != self.N:
+            raise ValueError('Input length {} does not match shape={}'.format(x.shape[-1], self.N))
+        if x.dtype is not torch.float32:
+            raise TypeError('Input and filter must be of the same dtype.')
+        if x.device.type != 'cuda':
+            raise TypeError('Input must be on GPU.')
+        batch_shape = x.shape[:-1]
+        x2 = x.reshape(-1, self.N)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        B = x2.shape[0]
+        plan = self._plan_for(x.device.index if x.device.index is not None else torch.cuda.current_device())
+        sched = self._sched[1]
+        C, n_out = sched.n_paths, sched.n_out
+        S = torch.empty((B, C, n_out), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = _lib.load().tebscat_scat1d_forward(plan.handle, x2.data_ptr(), B, S.data_ptr(), stream)
+        _lib.check(rc)
+        P = S.view(B, 1, C, n_out)                       # core/scattering1d.py:395-397: P is S before the reshape
+        return [S.reshape(batch_shape + (C, n_out)), P]
+
+    def scattering_host(self, x, out=None, device=0):
+        """End-to-end path on HOST tensors: pinned staging, chunked H2D / kernel / D2H
+        overlap inside the library (tebscat_scat1d_forward_host).  Returns S on the host."""
+        self._check_options()
+        if x.device.type != 'cpu' or x.dtype is not torch.float32:
+            raise TypeError('scattering_host expects a float32 CPU tensor')
+        if x.shape[-1] != self.N:
+            raise ValueError('Input length {} does not match shape={}'.format(x.shape[-1], self.N))
+        batch_shape = x.shape[:-1]
+        x2 = x.reshape(-1, self.N).contiguous()
+        B = x2.shape[0]
+        plan = self._plan_for(device)
+        sched = self._sched[1]
+        C, n_out = sched.n_paths, sched.n_out
+        if out is None:
+            out = torch.empty((B, C, n_out), dtype=torch.float32, pin_memory=True)
+        rc = _lib.load().tebscat_scat1d_forward_host(plan.handle, x2.data_ptr(), B, out.data_ptr())
+        _lib.check(rc)
+        return out.reshape(batch_shape + (C, n_out))
+
+
+ScatteringTorch1D = Scattering1D
+__all__ = ['Scattering1D', 'ScatteringTorch1D']
