@@ -206,7 +206,9 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     CU(cudaMemcpy(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_tasks, tasks, (size_t)desc->n_tasks * 8 * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_steps, steps, (size_t)desc->n_steps * 2 * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CU(cudaFuncSetAttribute(scat1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    // the attribute belongs to the kernel, not to the plan: always allow the device maximum
+    CU(cudaFuncSetAttribute(scat1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)prop.sharedMemPerBlockOptin));
 
     KParams& k = p->kp;
     k.arena = p->d_arena;
