@@ -85,6 +85,12 @@ int tebscat_scat1d_forward(const tebscat_plan* plan, const float* x_dev, int64_t
 int tebscat_scat1d_forward_host(tebscat_plan* plan, const float* x_host, int64_t B,
                                 float* S_host);
 
+/* Diagnostic: run the transform once and return clock64() of CTA 0 at every step
+ * boundary of its first signal (n_steps + 1 values).  Used to calibrate the host
+ * scheduler's cost model; not on the product path. */
+int tebscat_scat1d_profile_steps(const tebscat_plan* plan, const float* x_dev, int64_t B,
+                                 float* S_dev, long long* step_clocks_host, void* stream);
+
 /* Number of kernels the last forward call on this thread launched. */
 int tebscat_last_launch_count(void);
 

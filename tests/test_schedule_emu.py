@@ -28,12 +28,12 @@ def test_bitrev_and_radix_split():
         assert sum(s) == n and max(s) <= 4 and len(s) == -(-n // 4)
 
 
-def _touched(t):
+def _touched(t, np_len):
     """(reads, writes) slot intervals of one task row."""
     op = t[0] & 0xff
     a, b, c, d = int(t[3]), int(t[4]), int(t[5]), int(t[6])
     if op == OP_LOAD:
-        return [], [(a, a + (1 << 13))]
+        return [], [(a, a + np_len)]
     if op == OP_FFT:
         return [(a, a + (1 << b))], [(a, a + (1 << b))]
     if op == OP_MULFOLD:
@@ -58,7 +58,7 @@ def test_schedule_is_well_formed(name):
         assert all(s[0] % 32 == 0 and s[1] <= p.n_threads for s in spans)
         assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
         # no task of a step writes slots another task of the same step touches
-        acc = [_touched(r) for r in rows]
+        acc = [_touched(r, 1 << p.geo.J_pad) for r in rows]
         for i in range(len(rows)):
             for j in range(len(rows)):
                 if i == j:

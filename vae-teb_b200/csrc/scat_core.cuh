@@ -32,11 +32,13 @@ struct float4 { float x, y, z, w; };
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 #define TEB_LDG(p) (*(p))
 #define TEB_UNROLL
+#define TEB_UNROLL4
 #else
 #include <cuda_runtime.h>
 #define TEB_D __device__ __forceinline__
 #define TEB_LDG(p) __ldg(p)
 #define TEB_UNROLL _Pragma("unroll")
+#define TEB_UNROLL4 _Pragma("unroll 4")
 #endif
 
 namespace tebscat {
@@ -87,10 +89,13 @@ template <int SGN> TEB_D float2 cmulk(float2 a, float c, float s) {
                    : make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.y, c, a.x * s));
 }
 
-// shared-memory slot of logical complex index i: XOR swizzle that keeps every access
-// pattern of the passes below (unit stride, stride 2^m, 16 contiguous per thread)
-// free of bank conflicts for 8-byte accesses.
-TEB_D int swz(int i) { return i ^ ((i >> 4) & 15); }
+// shared-memory slot of logical complex index i: one pad slot after every 16.  It keeps
+// every access pattern of the passes below (unit stride across lanes, 16 contiguous per
+// thread, stride 2^m) free of bank conflicts for 8-byte accesses, and it is AFFINE for
+// strides that are multiples of 16: pad(p + j*s) = pad(p) + j*(s + s/16), so a butterfly
+// addresses its R elements with one pad() and constant increments.  Buffers start on
+// multiples of 16 slots.
+TEB_D int swz(int i) { return i + (i >> 4); }
 
 // ---- register DFTs --------------------------------------------------------------
 // dft<R, SGN>(v): v[] <- DFT_R of v[] with kernel exp(SGN*2*pi*i*j*q/R); on return
@@ -159,17 +164,17 @@ TEB_D float2 twiddle(const float2* twA, const float2* twB, int k) {
     return cmul(twA[k >> 7], twB[k & 127]);
 }
 
-// powers w[q] = W^(k1*q), q = 1..R-1, from log2(R) table lookups and a product tree
-template <int R> TEB_D void twiddle_powers(const float2* twA, const float2* twB, int k1, float2 (&w)[R]) {
-    const int mask = (1 << kLog2TwMax) - 1;
-    TEB_UNROLL for (int q = 1; q < R; q <<= 1) w[q] = twiddle(twA, twB, (k1 * q) & mask);
-    TEB_UNROLL for (int q = 3; q < R; ++q) {
-        if ((q & (q - 1)) != 0) {                  // not a power of two
-            int hi = 1;
-            while ((hi << 1) <= q) hi <<= 1;       // top set bit
-            w[q] = cmul(w[hi], w[q - hi]);
+// w^q for q = 1..R-1 from the base powers wb[i] = w^(2^i): at most popcount(q)-1 products
+template <int LOGR> TEB_D float2 twiddle_power(const float2 (&wb)[LOGR], int q) {
+    float2 w = make_float2(1.f, 0.f);
+    bool first = true;
+    TEB_UNROLL for (int i = 0; i < LOGR; ++i) {
+        if ((q >> i) & 1) {
+            w = first ? wb[i] : cmul(w, wb[i]);
+            first = false;
         }
     }
+    return w;
 }
 
 // One radix-2^LOGR pass over butterfly u of a length-2^logL transform stored at `base`.
@@ -183,29 +188,39 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
     const int blk = u >> logs;
     const int p0 = base + (blk << logB) + i0;
     float2 v[R];
-    float2 w[R];
-    const int k1 = i0 << (kLog2TwMax - logB);
-    if (logs > 0) twiddle_powers<R>(twA, twB, k1, w);
+    float2 wb[LOGR];
+    if (logs > 0) {
+        const int k1 = i0 << (kLog2TwMax - logB);
+        TEB_UNROLL for (int i = 0; i < LOGR; ++i) wb[i] = twiddle(twA, twB, k1 << i);
+    }
+    // element j of the butterfly lives at slot swz(p0 + j*s)
+    int slot[R];
+    if (logs >= 4) {
+        const int s0 = swz(p0), ds = (1 << logs) + (1 << (logs - 4));
+        TEB_UNROLL for (int j = 0; j < R; ++j) slot[j] = s0 + j * ds;
+    } else {
+        TEB_UNROLL for (int j = 0; j < R; ++j) slot[j] = swz(p0 + (j << logs));
+    }
     if (!INV) {
-        TEB_UNROLL for (int j = 0; j < R; ++j) v[j] = S[swz(p0 + (j << logs))];
+        TEB_UNROLL for (int j = 0; j < R; ++j) v[j] = S[slot[j]];
         Dft<R, -1>::run(v);
         TEB_UNROLL for (int r = 0; r < R; ++r) {
             const int q = qmap<R>(r);
             float2 y = v[r];
-            if (q != 0 && logs > 0) y = cmul(y, w[q]);
-            S[swz(p0 + (brev<LOGR>(q) << logs))] = y;
+            if (q != 0 && logs > 0) y = cmul(y, twiddle_power<LOGR>(wb, q));
+            S[slot[brev<LOGR>(q)]] = y;
         }
     } else {
         TEB_UNROLL for (int q = 0; q < R; ++q) {
-            float2 y = S[swz(p0 + (brev<LOGR>(q) << logs))];
-            if (q != 0 && logs > 0) y = cmulc(y, w[q]);
+            float2 y = S[slot[brev<LOGR>(q)]];
+            if (q != 0 && logs > 0) y = cmulc(y, twiddle_power<LOGR>(wb, q));
             v[q] = y;
         }
         Dft<R, +1>::run(v);
         TEB_UNROLL for (int r = 0; r < R; ++r) {
             float2 y = v[r];
             if (MOD) y = make_float2(sqrtf(fmaf(y.x, y.x, y.y * y.y)), 0.f);
-            S[swz(p0 + (qmap<R>(r) << logs))] = y;
+            S[slot[qmap<R>(r)]] = y;
         }
     }
 }
@@ -214,10 +229,12 @@ template <int LOGR>
 TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task& t, int lt) {
     const int n_bfly = 1 << (t.b - LOGR);
     const bool inv = (t.e & FFT_INV) != 0, mod = (t.e & FFT_MOD) != 0;
-    for (int u = lt; u < n_bfly; u += t.nt) {
-        if (!inv) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, t.c, u);
-        else if (!mod) fft_butterfly<LOGR, true, false>(S, twA, twB, t.a, t.c, u);
-        else fft_butterfly<LOGR, true, true>(S, twA, twB, t.a, t.c, u);
+    if (!inv) {
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, t.c, u);
+    } else if (!mod) {
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, false>(S, twA, twB, t.a, t.c, u);
+    } else {
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, true>(S, twA, twB, t.a, t.c, u);
     }
 }
 
@@ -228,7 +245,7 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
     const int n_dst = 1 << (t.b - logk);
     const float scale = ldexpf(1.0f, -(t.op >> 8));
     const float* f = arena + t.e;
-    for (int m = lt; m < n_dst; m += t.nt) {
+    TEB_UNROLL4 for (int m = lt; m < n_dst; m += t.nt) {
         float ax = 0.f, ay = 0.f;
         const int s0 = t.a + (m << logk);
         const float* fm = f + (m << logk);

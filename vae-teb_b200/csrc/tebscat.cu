@@ -43,15 +43,21 @@ static int fail(int code, const char* fmt, ...) {
 struct KParams {
     const float* arena;      // filters, fp32, bit-reversed bin order
     const float2* tw;        // kTwA coarse + kTwB fine twiddles
-    const int4* tasks;       // 2 x int4 per task
-    const int2* steps;       // [task_begin, task_end) per step
+    const int4* warp_tab;    // [n_steps][kWarps] x 2 int4: the task of every warp in every step
+    long long* prof;         // optional: clock64() of CTA 0 at every step boundary (first signal)
     int32_t n_steps;
     int32_t smem_complex;
     int32_t N, pad_left, log2_Np, n_paths, n_out;
 };
 
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+
 // One CTA per SM, persistent over the batch: signal b, b + gridDim.x, ...
-__global__ void __launch_bounds__(512, 1)
+// Every warp walks its own column of the task table and fetches the record of the NEXT
+// step before it executes the current one, so descriptor latency never sits on the
+// critical path between two barriers.
+__global__ void __launch_bounds__(kThreads, 1)
 scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ out, long long B) {
     extern __shared__ __align__(16) float2 smem[];
     float2* S = smem;
@@ -61,6 +67,9 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
     __syncthreads();
 
     const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int4* tab = p.warp_tab + 2 * warp;
+    int4 lo = __ldg(tab), hi = __ldg(tab + 1);
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         SignalCtx c;
         c.x = x + b * p.N;
@@ -69,21 +78,22 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
         c.pad_left = p.pad_left;
         c.log2_Np = p.log2_Np;
         c.n_out = p.n_out;
+        const bool prof = p.prof != nullptr && blockIdx.x == 0 && b == blockIdx.x && tid == 0;
         for (int s = 0; s < p.n_steps; ++s) {
-            const int2 st = __ldg(p.steps + s);
-            for (int ti = st.x; ti < st.y; ++ti) {
-                const int4 lo = __ldg(p.tasks + 2 * ti);
-                const int lt = tid - lo.y;
-                if ((unsigned)lt < (unsigned)lo.z) {
-                    const int4 hi = __ldg(p.tasks + 2 * ti + 1);
-                    Task t;
-                    t.op = lo.x; t.t0 = lo.y; t.nt = lo.z; t.a = lo.w;
-                    t.b = hi.x; t.c = hi.y; t.d = hi.z; t.e = hi.w;
-                    exec_task(S, twA, twB, p.arena, c, t, lt);
-                }
+            const int sn = (s + 1 == p.n_steps) ? 0 : s + 1;          // wraps to the next signal
+            const int4 nlo = __ldg(tab + 2 * kWarps * sn), nhi = __ldg(tab + 2 * kWarps * sn + 1);
+            if (prof) p.prof[s] = clock64();
+            if ((lo.x & 0xff) != OP_NOP) {
+                Task t;
+                t.op = lo.x; t.t0 = lo.y; t.nt = lo.z; t.a = lo.w;
+                t.b = hi.x; t.c = hi.y; t.d = hi.z; t.e = hi.w;
+                exec_task(S, twA, twB, p.arena, c, t, tid - lo.y);
             }
             __syncthreads();
+            lo = nlo;
+            hi = nhi;
         }
+        if (prof) p.prof[p.n_steps] = clock64();
     }
 }
 
@@ -106,8 +116,7 @@ struct tebscat_plan {
     size_t smem_bytes = 0;
     float* d_arena = nullptr;
     float2* d_tw = nullptr;
-    int32_t* d_tasks = nullptr;
-    int32_t* d_steps = nullptr;
+    int32_t* d_warp_tab = nullptr;
     KParams kp;
     HostPipe pipe;
     std::mutex pipe_mu;
@@ -115,7 +124,7 @@ struct tebscat_plan {
 
 static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, const int32_t* steps,
                              size_t n_floats) {
-    const int cap = d.smem_complex;
+    const int cap = (int)(((int64_t)d.smem_complex * 16) / 17);   // logical slots (1 pad slot per 16)
     for (int s = 0; s < d.n_steps; ++s) {
         const int b = steps[2 * s], e = steps[2 * s + 1];
         if (b < 0 || e < b || e > d.n_tasks) return fail(TEBSCAT_EINVAL, "step %d: bad task range [%d,%d)", s, b, e);
@@ -171,7 +180,7 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     if (desc->N < 2 || desc->pad_left < 0 || desc->pad_left >= desc->N ||
         (1 << desc->log2_Np) - desc->N - desc->pad_left >= desc->N || (1 << desc->log2_Np) < desc->N)
         return fail(TEBSCAT_EINVAL, "Indefinite padding size (larger than tensor).");
-    if (desc->n_threads != 512) return fail(TEBSCAT_EUNSUPPORTED, "schedules must target 512-thread CTAs");
+    if (desc->n_threads != kThreads) return fail(TEBSCAT_EUNSUPPORTED, "schedules must target 512-thread CTAs");
     if (desc->n_paths < 1 || desc->n_out < 1 || desc->n_tasks < 1 || desc->n_steps < 1 || desc->smem_complex < 1)
         return fail(TEBSCAT_EINVAL, "empty plan");
     if (int rc = validate_schedule(*desc, tasks, steps, n_floats)) return rc;
@@ -200,12 +209,23 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
 
     CU(cudaMalloc(&p->d_arena, n_floats * sizeof(float)));
     CU(cudaMalloc(&p->d_tw, tw.size() * sizeof(float2)));
-    CU(cudaMalloc(&p->d_tasks, (size_t)desc->n_tasks * 8 * sizeof(int32_t)));
-    CU(cudaMalloc(&p->d_steps, (size_t)desc->n_steps * 2 * sizeof(int32_t)));
+    // per-warp view of the schedule: record (step, warp) = the task whose thread range covers the warp
+    std::vector<int32_t> wt((size_t)desc->n_steps * kWarps * 8, 0);
+    for (int st = 0; st < desc->n_steps; ++st) {
+        for (int ti = steps[2 * st]; ti < steps[2 * st + 1]; ++ti) {
+            const int32_t* t = tasks + 8 * ti;
+            if ((t[1] & 31) || (t[2] & 31)) { delete p; return fail(TEBSCAT_EINVAL, "task %d: thread range not warp aligned", ti); }
+            for (int w = t[1] / 32; w < (t[1] + t[2]) / 32; ++w) {
+                int32_t* rec = wt.data() + ((size_t)st * kWarps + w) * 8;
+                if ((rec[0] & 0xff) != OP_NOP) { delete p; return fail(TEBSCAT_EINVAL, "step %d: overlapping thread ranges", st); }
+                memcpy(rec, t, 8 * sizeof(int32_t));
+            }
+        }
+    }
+    CU(cudaMalloc(&p->d_warp_tab, wt.size() * sizeof(int32_t)));
+    CU(cudaMemcpy(p->d_warp_tab, wt.data(), wt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_arena, arena, n_floats * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(p->d_tasks, tasks, (size_t)desc->n_tasks * 8 * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(p->d_steps, steps, (size_t)desc->n_steps * 2 * sizeof(int32_t), cudaMemcpyHostToDevice));
     // the attribute belongs to the kernel, not to the plan: always allow the device maximum
     CU(cudaFuncSetAttribute(scat1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)prop.sharedMemPerBlockOptin));
@@ -213,8 +233,8 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     KParams& k = p->kp;
     k.arena = p->d_arena;
     k.tw = p->d_tw;
-    k.tasks = reinterpret_cast<const int4*>(p->d_tasks);
-    k.steps = reinterpret_cast<const int2*>(p->d_steps);
+    k.warp_tab = reinterpret_cast<const int4*>(p->d_warp_tab);
+    k.prof = nullptr;
     k.n_steps = desc->n_steps;
     k.smem_complex = desc->smem_complex;
     k.N = desc->N;
@@ -239,8 +259,7 @@ extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
     }
     cudaFree(p->d_arena);
     cudaFree(p->d_tw);
-    cudaFree(p->d_tasks);
-    cudaFree(p->d_steps);
+    cudaFree(p->d_warp_tab);
     delete p;
 }
 
@@ -263,6 +282,28 @@ extern "C" int tebscat_scat1d_forward(const tebscat_plan* p, const float* x_dev,
     int rc = launch_scat1d(p, x_dev, B, S_dev, (cudaStream_t)stream);
     if (cur != p->device && cur >= 0) cudaSetDevice(cur);
     return rc;
+}
+
+extern "C" int tebscat_scat1d_profile_steps(const tebscat_plan* p, const float* x_dev, int64_t B, float* S_dev,
+                                            long long* step_clocks_host, void* stream) {
+    g_launches = 0;
+    if (!p || !x_dev || !S_dev || !step_clocks_host || B < 1) return fail(TEBSCAT_EINVAL, "null argument");
+    CU(cudaSetDevice(p->device));
+    long long* d_prof = nullptr;
+    const size_t n = (size_t)p->desc.n_steps + 1;
+    CU(cudaMalloc(&d_prof, n * sizeof(long long)));
+    CU(cudaMemsetAsync(d_prof, 0, n * sizeof(long long), (cudaStream_t)stream));
+    KParams kp = p->kp;
+    kp.prof = d_prof;
+    const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
+    scat1d_kernel<<<grid, p->desc.n_threads, p->smem_bytes, (cudaStream_t)stream>>>(kp, x_dev, S_dev, (long long)B);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaMemcpy(step_clocks_host, d_prof, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_prof);
+    if (e != cudaSuccess) return fail(TEBSCAT_ECUDA, "profile run failed: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return TEBSCAT_OK;
 }
 
 extern "C" int tebscat_scat1d_forward_host(tebscat_plan* p, const float* x_host, int64_t B, float* S_host) {

@@ -60,6 +60,8 @@ def load():
     lib.tebscat_scat1d_forward.argtypes = [vp, vp, ctypes.c_int64, vp, vp]
     lib.tebscat_scat1d_forward_host.restype = ctypes.c_int
     lib.tebscat_scat1d_forward_host.argtypes = [vp, vp, ctypes.c_int64, vp]
+    lib.tebscat_scat1d_profile_steps.restype = ctypes.c_int
+    lib.tebscat_scat1d_profile_steps.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp]
     lib.tebscat_bench_fp32_peak.restype = ctypes.c_int
     lib.tebscat_bench_fp32_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     if lib.tebscat_abi_version() != ABI_VERSION:

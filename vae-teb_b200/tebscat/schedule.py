@@ -139,7 +139,7 @@ class ScatPlan:
     arena: np.ndarray              # float32
     tasks: np.ndarray              # int32 [n_tasks, 8]
     steps: np.ndarray              # int32 [n_steps, 2]
-    smem_complex: int
+    smem_complex: int              # PHYSICAL complex slots (logical slots + 1 pad per 16)
     n_threads: int = N_THREADS
     stats: Dict[str, float] = field(default_factory=dict)
 
@@ -513,11 +513,13 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     bank = fbk.build_filter_bank(geo.J_pad, J, Q1, T)
     arena = _Arena()
     chains, keys, n_out = build_chains(bank, geo, T, max_order, arena)
-    capacity = (SMEM_BYTES_MAX // 8 - TW_SLOTS) & ~15
+    # logical slots; the kernel pads one slot per 16 (scat_core.cuh: swz)
+    capacity = ((SMEM_BYTES_MAX // 8 - TW_SLOTS) * 16 // 17) & ~15
     steps, high, sched = schedule_chains(chains, capacity, max_parallel)
     tasks, ranges = emit(steps)
     n_tasks = tasks.shape[0]
     stats = dict(n_steps=len(steps), n_tasks=n_tasks, smem_complex=high,
                  mean_tasks_per_step=n_tasks / max(1, len(steps)), **sched)
+    logical = _round16(high)
     return ScatPlan(J, Q1, T, N, max_order, geo, bank, keys, n_out, arena.finish(), tasks, ranges,
-                    _round16(high), N_THREADS, stats)
+                    logical + logical // 16, N_THREADS, stats)
