@@ -54,19 +54,20 @@ typedef struct tebscat_plan_desc {
     int32_t n_out;         /* ind_end[log2T] - ind_start[log2T]                        */
     int32_t n_threads;     /* CTA size the schedule was built for                      */
     int32_t smem_complex;  /* complex64 slots of shared memory the schedule addresses  */
-    int32_t n_tasks;       /* entries of `tasks` (8 x int32 each)                      */
+    int32_t n_tasks;       /* entries of `tasks` (12 x int32 each)                     */
     int32_t n_steps;       /* entries of `steps` (2 x int32 each: [task_begin, task_end)) */
     int32_t reserved[6];
 } tebscat_plan_desc;
 
 typedef struct tebscat_plan tebscat_plan;
 
-/* Upload the filter arena (fp32, bit-reversed bin order) and the
- * step schedule to `device`.  Replaces ScatteringTorch1D.register_filters /
+/* Upload the filter arena (fp32, bit-reversed bin order), the step
+ * schedule and the channel table of its batched stores to `device`.  Replaces ScatteringTorch1D.register_filters /
  * load_filters (kymatio/kymatio/scattering1d/frontend/torch_frontend.py:75-116). */
 int tebscat_plan_create(const tebscat_plan_desc* desc,
                         const float* filter_arena_host, size_t n_floats,
                         const int32_t* tasks_host, const int32_t* steps_host,
+                        const int32_t* channel_table_host, size_t n_channel_entries,
                         int device, tebscat_plan** out);
 
 void tebscat_plan_destroy(tebscat_plan* plan);

@@ -16,7 +16,7 @@ using namespace tebscat;
 extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths, int n_out,
                                   int smem_complex, int n_tasks, int n_steps,
                                   const float* arena, const int32_t* tasks, const int32_t* steps,
-                                  const float* x, long long B, float* out) {
+                                  const int32_t* chan, const float* x, long long B, float* out) {
     std::vector<float2> S((size_t)smem_complex);
     std::vector<float2> tw(kTwA + kTwB);
     const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
@@ -28,11 +28,12 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
         SignalCtx c;
         c.x = x + b * N;
         c.out = out + b * (long long)n_paths * n_out;
+        c.chan = chan;
         c.N = N; c.pad_left = pad_left; c.log2_Np = log2_Np; c.n_out = n_out;
         for (int s = 0; s < n_steps; ++s) {
             for (int ti = steps[2 * s]; ti < steps[2 * s + 1]; ++ti) {
                 Task t;
-                memcpy(&t, tasks + 8 * ti, sizeof(Task));
+                memcpy(&t, tasks + kTaskInts * ti, sizeof(Task));
                 for (int lt = 0; lt < t.nt; ++lt) exec_task(S.data(), tw.data(), tw.data() + kTwA, arena, c, t, lt);
             }
         }

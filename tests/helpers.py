@@ -44,9 +44,10 @@ def emu_forward(plan, x):
     tasks = np.ascontiguousarray(plan.tasks, np.int32)
     steps = np.ascontiguousarray(plan.steps, np.int32)
     arena = np.ascontiguousarray(plan.arena, np.float32)
+    chan = np.ascontiguousarray(plan.chan, np.int32)
     rc = lib.emu_scat1d_forward(plan.N, plan.geo.J_pad, plan.geo.pad_left, plan.n_paths, plan.n_out,
                                 plan.smem_complex, tasks.shape[0], steps.shape[0],
                                 arena.ctypes.data_as(fp), tasks.ctypes.data_as(ip), steps.ctypes.data_as(ip),
-                                x.ctypes.data_as(fp), ctypes.c_longlong(B), out.ctypes.data_as(fp))
+                                chan.ctypes.data_as(ip), x.ctypes.data_as(fp), ctypes.c_longlong(B), out.ctypes.data_as(fp))
     assert rc == 0
     return out

@@ -7,7 +7,7 @@ import pytest
 
 from helpers import CONFIGS, GOLDEN, emu_available, emu_forward, path_tolerance, rel_l2
 from oracle.scattering1d_oracle import ScatteringOracle
-from tebscat.schedule import (OP_FFT, OP_LOAD, OP_MULFOLD, OP_STORE, SMEM_BYTES_MAX, TW_SLOTS,
+from tebscat.schedule import (OP_FFT, OP_LOAD, OP_MULFOLD, OP_STOREB, SMEM_BYTES_MAX, TASK_INTS, TW_SLOTS,
                               bitrev_indices, build_plan, radix_split)
 
 _plans = {}
@@ -34,12 +34,12 @@ def _touched(t, np_len):
     a, b, c, d = int(t[3]), int(t[4]), int(t[5]), int(t[6])
     if op == OP_LOAD:
         return [], [(a, a + np_len)]
-    if op == OP_FFT:
-        return [(a, a + (1 << b))], [(a, a + (1 << b))]
+    if op == OP_FFT:                       # b butterflies of radix 2^d
+        return [(a, a + (b << d))], [(a, a + (b << d))]
     if op == OP_MULFOLD:
         return [(a, a + (1 << b))], [(d, d + (1 << (b - c)))]
-    if op == OP_STORE:
-        return [(a, a + c + d)], []
+    if op == OP_STOREB:                    # b slots of 2^f
+        return [(a, a + (b << int(t[8])))], []
     return [], []
 
 
@@ -47,7 +47,7 @@ def _touched(t, np_len):
 def test_schedule_is_well_formed(name):
     p = plan_of(name)
     assert (p.smem_complex + TW_SLOTS) * 8 <= SMEM_BYTES_MAX
-    assert p.tasks.shape[1] == 8 and p.steps.shape[1] == 2
+    assert p.tasks.shape[1] == TASK_INTS and p.steps.shape[1] == 2
     assert p.steps[0, 0] == 0 and p.steps[-1, 1] == p.tasks.shape[0]
     assert np.all(p.steps[1:, 0] == p.steps[:-1, 1])
     stored = []
@@ -66,7 +66,9 @@ def test_schedule_is_well_formed(name):
                 for w0, w1 in acc[i][1]:
                     for r0, r1 in acc[j][0] + acc[j][1]:
                         assert w1 <= r0 or r1 <= w0, 'hazard inside a step'
-        stored += [int(r[4]) for r in rows if (r[0] & 0xff) == OP_STORE]
+        for r in rows:
+            if (r[0] & 0xff) == OP_STOREB:
+                stored += [int(v) for v in p.chan[int(r[7]):int(r[7]) + int(r[4])]]
     assert sorted(stored) == list(range(p.n_paths))          # every channel written exactly once
 
 

@@ -32,43 +32,61 @@ struct float4 { float x, y, z, w; };
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 #define TEB_LDG(p) (*(p))
 #define TEB_UNROLL
+#define TEB_UNROLL2
 #define TEB_UNROLL4
+#define TEB_FFS(x) __builtin_ffs((int)(x))
 #else
 #include <cuda_runtime.h>
 #define TEB_D __device__ __forceinline__
 #define TEB_LDG(p) __ldg(p)
 #define TEB_UNROLL _Pragma("unroll")
+#define TEB_UNROLL2 _Pragma("unroll 2")
 #define TEB_UNROLL4 _Pragma("unroll 4")
+#define TEB_FFS(x) __ffs((int)(x))
 #endif
 
 namespace tebscat {
 
-// ---- task encoding (8 x int32); keep in sync with tebscat/schedule.py ---------
+// ---- task encoding (12 x int32); keep in sync with tebscat/schedule.py ----------
 enum : int32_t {
     OP_NOP = 0,
     OP_LOAD = 1,     // a=dst                              reflect-padded signal -> (x, 0)
-    OP_FFT = 2,      // a=region b=log2L c=log2B d=log2R e=flags(FFT_INV | FFT_MOD)
-    OP_MULFOLD = 3,  // a=src b=log2Lsrc c=log2k d=dst e=filter offset (floats); scale 2^-sexp
-    OP_STORE = 4     // a=src b=channel c=first index d=count e=flags(ST_IMAG)
+    OP_FFT = 2,      // a=region b=butterflies (all blocks) c=log2B d=log2R e=flags(FFT_INV|FFT_MOD)
+    OP_MULFOLD = 3,  // a=src b=log2Lsrc c=log2k d=dst e=filter offset (floats) f=chunk mask; scale 2^-sexp
+    OP_STOREB = 4    // a=pool base b=slots c=first index d=count e=channel-table offset f=log2 slot length
 };
-enum : int32_t { FFT_INV = 1, FFT_MOD = 2, ST_IMAG = 1 };
+enum : int32_t { FFT_INV = 1, FFT_MOD = 2 };
+constexpr int kTaskInts = 12;
 
 struct Task {
     int32_t op;    // opcode | (sexp << 8)
     int32_t t0;    // first thread of the range
     int32_t nt;    // threads in the range
-    int32_t a, b, c, d, e;
+    int32_t a, b, c, d, e, f, g, h, pad;
 };
 
 struct SignalCtx {
-    const float* x;     // this signal's N input samples
-    float* out;         // this signal's [n_paths, n_out] block
+    const float* x;          // this signal's N input samples
+    float* out;              // this signal's [n_paths, n_out] block
+    const int32_t* chan;     // channel table of the batched stores
     int32_t N, pad_left, log2_Np, n_out;
 };
 
 constexpr int kLog2TwMax = 13;                 // twiddle tables cover lengths up to 8192
 constexpr int kTwA = 1 << (kLog2TwMax - 7);    // coarse table entries: W^(128 a)
 constexpr int kTwB = 128;                      // fine table entries:   W^b
+
+// modulus (kymatio/backend/torch_backend.py:57): MUFU.SQRT on the device (<= 2 ulp, no
+// slow path), sqrtf in the host emulator.
+#ifdef TEBSCAT_HOST_EMU
+TEB_D float teb_sqrt(float v) { return sqrtf(v); }
+#else
+TEB_D float teb_sqrt(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+#endif
 
 // ---- complex helpers -----------------------------------------------------------
 TEB_D float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -219,7 +237,7 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
         Dft<R, +1>::run(v);
         TEB_UNROLL for (int r = 0; r < R; ++r) {
             float2 y = v[r];
-            if (MOD) y = make_float2(sqrtf(fmaf(y.x, y.x, y.y * y.y)), 0.f);
+            if (MOD) y = make_float2(teb_sqrt(fmaf(y.x, y.x, y.y * y.y)), 0.f);
             S[slot[qmap<R>(r)]] = y;
         }
     }
@@ -227,7 +245,7 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
 
 template <int LOGR>
 TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task& t, int lt) {
-    const int n_bfly = 1 << (t.b - LOGR);
+    const int n_bfly = t.b;
     const bool inv = (t.e & FFT_INV) != 0, mod = (t.e & FFT_MOD) != 0;
     if (!inv) {
         for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, t.c, u);
@@ -239,35 +257,54 @@ TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task&
 }
 
 // dst[m] = 2^-sexp * sum_{i<k} src[m*k + i] * filt[m*k + i]      (bit-reversed bin order)
+// Filters are real fp32 in global memory (L2 resident).  Every work item covers four
+// consecutive source slots with one 128-bit filter load; for k >= 4 only the 4-slot chunks
+// named in the task's mask are visited (the host clears chunks where the filter is below
+// 1e-9 of its peak for every output bin -- e.g. 2 of 16 chunks for the phi low-pass).
 TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& t, int lt) {
     const int logk = t.c;
-    const int k = 1 << logk;
-    const int n_dst = 1 << (t.b - logk);
     const float scale = ldexpf(1.0f, -(t.op >> 8));
     const float* f = arena + t.e;
-    TEB_UNROLL4 for (int m = lt; m < n_dst; m += t.nt) {
-        float ax = 0.f, ay = 0.f;
-        const int s0 = t.a + (m << logk);
-        const float* fm = f + (m << logk);
-        if (logk >= 2) {
-            for (int i = 0; i < k; i += 4) {
+    if (logk >= 2) {
+        const int n_dst = 1 << (t.b - logk);
+        const unsigned mask = (unsigned)t.f;
+        TEB_UNROLL2 for (int m = lt; m < n_dst; m += t.nt) {
+            float ax = 0.f, ay = 0.f;
+            const int s0 = t.a + (m << logk);
+            const float* fm = f + (m << logk);
+            unsigned rest = mask;
+            while (rest) {
+                const int ch = TEB_FFS(rest) - 1;
+                rest &= rest - 1;
+                const int i = ch << 2;
                 const float4 g = TEB_LDG(reinterpret_cast<const float4*>(fm + i));
-                float2 z0 = S[swz(s0 + i)], z1 = S[swz(s0 + i + 1)];
-                float2 z2 = S[swz(s0 + i + 2)], z3 = S[swz(s0 + i + 3)];
+                const int q = swz(s0 + i);          // 4 slots of one 16-group: contiguous
+                const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
                 ax = fmaf(z0.x, g.x, ax); ay = fmaf(z0.y, g.x, ay);
                 ax = fmaf(z1.x, g.y, ax); ay = fmaf(z1.y, g.y, ay);
                 ax = fmaf(z2.x, g.z, ax); ay = fmaf(z2.y, g.z, ay);
                 ax = fmaf(z3.x, g.w, ax); ay = fmaf(z3.y, g.w, ay);
             }
-        } else {
-            for (int i = 0; i < k; ++i) {
-                const float g = TEB_LDG(fm + i);
-                const float2 z = S[swz(s0 + i)];
-                ax = fmaf(z.x, g, ax);
-                ay = fmaf(z.y, g, ay);
+            S[swz(t.d + m)] = make_float2(ax * scale, ay * scale);
+        }
+    } else {
+        const int n_items = 1 << (t.b - 2);                    // 4 source slots per item
+        TEB_UNROLL4 for (int it = lt; it < n_items; it += t.nt) {
+            const float4 g = TEB_LDG(reinterpret_cast<const float4*>(f + 4 * it));
+            const int q = swz(t.a + 4 * it);
+            const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
+            if (logk == 0) {
+                const int o = swz(t.d + 4 * it);
+                S[o] = make_float2(z0.x * g.x * scale, z0.y * g.x * scale);
+                S[o + 1] = make_float2(z1.x * g.y * scale, z1.y * g.y * scale);
+                S[o + 2] = make_float2(z2.x * g.z * scale, z2.y * g.z * scale);
+                S[o + 3] = make_float2(z3.x * g.w * scale, z3.y * g.w * scale);
+            } else {
+                const int o = swz(t.d + 2 * it);
+                S[o] = make_float2(fmaf(z0.x, g.x, z1.x * g.y) * scale, fmaf(z0.y, g.x, z1.y * g.y) * scale);
+                S[o + 1] = make_float2(fmaf(z2.x, g.z, z3.x * g.w) * scale, fmaf(z2.y, g.z, z3.y * g.w) * scale);
             }
         }
-        S[swz(t.d + m)] = make_float2(ax * scale, ay * scale);
     }
 }
 
@@ -283,11 +320,13 @@ TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
 }
 
 // unpad (torch_backend.py:80-102) + concatenate (kymatio/backend/torch_backend.py:143-145)
-TEB_D void store_task(const float2* S, const SignalCtx& c, const Task& t, int lt) {
-    float* o = c.out + (int64_t)t.b * c.n_out;
-    for (int i = lt; i < t.d; i += t.nt) {
-        const float2 z = S[swz(t.a + t.c + i)];
-        o[i] = (t.e & ST_IMAG) ? z.y : z.x;
+// for a pool of `b` finished low-pass outputs: slot s goes to channel chan[e + s].
+TEB_D void storeb_task(const float2* S, const SignalCtx& c, const Task& t, int lt) {
+    const int total = t.b * t.d;
+    for (int i = lt; i < total; i += t.nt) {
+        const int slot = i / t.d, n = i - slot * t.d;
+        const int ch = TEB_LDG(c.chan + t.e + slot);
+        c.out[(int64_t)ch * c.n_out + n] = S[swz(t.a + (slot << t.f) + t.c + n)].x;
     }
 }
 
@@ -304,7 +343,7 @@ TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const floa
             }
             break;
         case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
-        case OP_STORE: store_task(S, c, t, lt); break;
+        case OP_STOREB: storeb_task(S, c, t, lt); break;
         default: break;
     }
 }

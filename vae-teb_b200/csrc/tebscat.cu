@@ -43,7 +43,8 @@ static int fail(int code, const char* fmt, ...) {
 struct KParams {
     const float* arena;      // filters, fp32, bit-reversed bin order
     const float2* tw;        // kTwA coarse + kTwB fine twiddles
-    const int4* warp_tab;    // [n_steps][kWarps] x 2 int4: the task of every warp in every step
+    const int4* warp_tab;    // [n_steps][kWarps] x 3 int4: the task of every warp in every step
+    const int32_t* chan;     // channel table of the batched stores
     long long* prof;         // optional: clock64() of CTA 0 at every step boundary (first signal)
     int32_t n_steps;
     int32_t smem_complex;
@@ -54,9 +55,10 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 
 // One CTA per SM, persistent over the batch: signal b, b + gridDim.x, ...
-// Every warp walks its own column of the task table and fetches the record of the NEXT
-// step before it executes the current one, so descriptor latency never sits on the
-// critical path between two barriers.
+// Every warp walks its own column of the task table.  A 12-int record is held ONE INT PER
+// LANE (lane l keeps field l), so the two records prefetched ahead of the executing one
+// cost two registers, and the fields are broadcast with shuffles when the step starts.
+// Descriptor latency (an L2 hit) therefore never sits between two barriers.
 __global__ void __launch_bounds__(kThreads, 1)
 scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ out, long long B) {
     extern __shared__ __align__(16) float2 smem[];
@@ -67,33 +69,47 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
     __syncthreads();
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int4* tab = p.warp_tab + 2 * warp;
-    int4 lo = __ldg(tab), hi = __ldg(tab + 1);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int32_t* tab = reinterpret_cast<const int32_t*>(p.warp_tab) + kTaskInts * warp + (lane < kTaskInts ? lane : 0);
+    const int stride = kTaskInts * kWarps;
+    const int n_steps = p.n_steps;
+    int cur = __ldg(tab);
+    int nxt = __ldg(tab + stride * (1 % n_steps));
+    int s_fetch = 2 % n_steps;
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         SignalCtx c;
         c.x = x + b * p.N;
         c.out = out + b * (long long)p.n_paths * p.n_out;
+        c.chan = p.chan;
         c.N = p.N;
         c.pad_left = p.pad_left;
         c.log2_Np = p.log2_Np;
         c.n_out = p.n_out;
         const bool prof = p.prof != nullptr && blockIdx.x == 0 && b == blockIdx.x && tid == 0;
-        for (int s = 0; s < p.n_steps; ++s) {
-            const int sn = (s + 1 == p.n_steps) ? 0 : s + 1;          // wraps to the next signal
-            const int4 nlo = __ldg(tab + 2 * kWarps * sn), nhi = __ldg(tab + 2 * kWarps * sn + 1);
+        for (int s = 0; s < n_steps; ++s) {
+            const int fut = __ldg(tab + stride * s_fetch);             // wraps into the next signal
+            s_fetch = (s_fetch + 1 == n_steps) ? 0 : s_fetch + 1;
             if (prof) p.prof[s] = clock64();
-            if ((lo.x & 0xff) != OP_NOP) {
+            const int op = __shfl_sync(0xffffffffu, cur, 0);
+            if ((op & 0xff) != OP_NOP) {
                 Task t;
-                t.op = lo.x; t.t0 = lo.y; t.nt = lo.z; t.a = lo.w;
-                t.b = hi.x; t.c = hi.y; t.d = hi.z; t.e = hi.w;
-                exec_task(S, twA, twB, p.arena, c, t, tid - lo.y);
+                t.op = op;
+                t.t0 = __shfl_sync(0xffffffffu, cur, 1);
+                t.nt = __shfl_sync(0xffffffffu, cur, 2);
+                t.a = __shfl_sync(0xffffffffu, cur, 3);
+                t.b = __shfl_sync(0xffffffffu, cur, 4);
+                t.c = __shfl_sync(0xffffffffu, cur, 5);
+                t.d = __shfl_sync(0xffffffffu, cur, 6);
+                t.e = __shfl_sync(0xffffffffu, cur, 7);
+                t.f = __shfl_sync(0xffffffffu, cur, 8);
+                t.g = 0; t.h = 0; t.pad = 0;
+                exec_task(S, twA, twB, p.arena, c, t, tid - t.t0);
             }
             __syncthreads();
-            lo = nlo;
-            hi = nhi;
+            cur = nxt;
+            nxt = fut;
         }
-        if (prof) p.prof[p.n_steps] = clock64();
+        if (prof) p.prof[n_steps] = clock64();
     }
 }
 
@@ -117,44 +133,49 @@ struct tebscat_plan {
     float* d_arena = nullptr;
     float2* d_tw = nullptr;
     int32_t* d_warp_tab = nullptr;
+    int32_t* d_chan = nullptr;
     KParams kp;
     HostPipe pipe;
     std::mutex pipe_mu;
 };
 
 static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, const int32_t* steps,
-                             size_t n_floats) {
+                             size_t n_floats, size_t n_chan) {
     const int cap = (int)(((int64_t)d.smem_complex * 16) / 17);   // logical slots (1 pad slot per 16)
     for (int s = 0; s < d.n_steps; ++s) {
         const int b = steps[2 * s], e = steps[2 * s + 1];
         if (b < 0 || e < b || e > d.n_tasks) return fail(TEBSCAT_EINVAL, "step %d: bad task range [%d,%d)", s, b, e);
     }
+    auto fits = [&](int64_t off, int64_t len) { return off >= 0 && (off & 15) == 0 && ((off + len + 15) & ~(int64_t)15) <= cap; };
     for (int i = 0; i < d.n_tasks; ++i) {
-        const int32_t* t = tasks + 8 * i;
+        const int32_t* t = tasks + kTaskInts * i;
         const int op = t[0] & 0xff;
-        if (t[1] < 0 || t[2] <= 0 || t[1] + t[2] > d.n_threads)
+        if (t[1] < 0 || t[2] <= 0 || t[1] + t[2] > d.n_threads || (t[1] & 31) || (t[2] & 31))
             return fail(TEBSCAT_EINVAL, "task %d: thread range [%d,+%d) outside the CTA", i, t[1], t[2]);
         switch (op) {
             case OP_LOAD:
-                if (t[3] < 0 || (t[3] & 15) || t[3] + (1 << d.log2_Np) > cap) return fail(TEBSCAT_EINVAL, "task %d: LOAD out of range", i);
+                if (!fits(t[3], (int64_t)1 << d.log2_Np)) return fail(TEBSCAT_EINVAL, "task %d: LOAD out of range", i);
                 break;
-            case OP_FFT:
-                if (t[4] < 1 || t[4] > kLog2TwMax || t[5] > t[4] || t[6] < 1 || t[6] > 4 || t[6] > t[5] ||
-                    t[3] < 0 || (t[3] & 15) || ((t[3] + (1 << t[4]) + 15) & ~15) > cap)
-                    return fail(TEBSCAT_EINVAL, "task %d: bad FFT pass (L=2^%d B=2^%d R=2^%d at %d)", i, t[4], t[5], t[6], t[3]);
-                break;
-            case OP_MULFOLD: {
-                const int n_dst = 1 << (t[4] - t[5]);
-                if (t[5] < 0 || t[5] > t[4] || t[3] < 0 || (t[3] & 15) || ((t[3] + (1 << t[4]) + 15) & ~15) > cap ||
-                    t[6] < 0 || (t[6] & 15) || ((t[6] + n_dst + 15) & ~15) > cap || t[7] < 0 ||
-                    (size_t)t[7] + ((size_t)1 << t[4]) > n_floats || (t[7] & 3))
-                    return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD", i);
+            case OP_FFT: {
+                // a=region b=butterflies c=log2B d=log2R: the butterflies cover b*R slots in blocks of 2^c
+                if (t[5] < 1 || t[5] > kLog2TwMax || t[6] < 1 || t[6] > 4 || t[6] > t[5] || t[4] < 1 ||
+                    (((int64_t)t[4] << t[6]) & (((int64_t)1 << t[5]) - 1)) || !fits(t[3], (int64_t)t[4] << t[6]))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad FFT pass (%d butterflies, B=2^%d R=2^%d at %d)", i, t[4], t[5], t[6], t[3]);
                 break;
             }
-            case OP_STORE:
-                if (t[4] < 0 || t[4] >= d.n_paths || t[6] != d.n_out || t[3] < 0 || (t[3] & 15) || t[5] < 0 ||
-                    ((t[3] + t[5] + t[6] + 15) & ~15) > cap)
-                    return fail(TEBSCAT_EINVAL, "task %d: bad STORE", i);
+            case OP_MULFOLD: {
+                if (t[4] < 2 || t[4] > kLog2TwMax || t[5] < 0 || t[5] > t[4] || t[5] > 6 || !fits(t[3], (int64_t)1 << t[4]) ||
+                    !fits(t[6] & ~15, (t[6] & 15) + ((int64_t)1 << (t[4] - t[5]))) || t[7] < 0 ||
+                    (size_t)t[7] + ((size_t)1 << t[4]) > n_floats || (t[7] & 3) || (t[6] & 3 && t[5] < 2))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD", i);
+                if (t[5] >= 2 && ((unsigned)t[8] == 0u || ((unsigned)t[8] >> (1 << (t[5] - 2))) != 0u))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD chunk mask", i);
+                break;
+            }
+            case OP_STOREB:
+                if (t[4] < 1 || t[6] != d.n_out || t[5] < 0 || t[8] < 0 || t[8] > kLog2TwMax || t[5] + t[6] > (1 << t[8]) ||
+                    !fits(t[3], (int64_t)t[4] << t[8]) || t[7] < 0 || (size_t)t[7] + (size_t)t[4] > n_chan)
+                    return fail(TEBSCAT_EINVAL, "task %d: bad STOREB", i);
                 break;
             case OP_NOP:
                 break;
@@ -170,9 +191,9 @@ extern "C" const char* tebscat_last_error(void) { return g_err; }
 extern "C" int tebscat_last_launch_count(void) { return g_launches; }
 
 extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* arena, size_t n_floats,
-                                   const int32_t* tasks, const int32_t* steps, int device,
-                                   tebscat_plan** out) {
-    if (!desc || !arena || !tasks || !steps || !out) return fail(TEBSCAT_EINVAL, "null argument");
+                                   const int32_t* tasks, const int32_t* steps,
+                                   const int32_t* chan, size_t n_chan, int device, tebscat_plan** out) {
+    if (!desc || !arena || !tasks || !steps || !chan || !out) return fail(TEBSCAT_EINVAL, "null argument");
     if (desc->abi_version != TEBSCAT_ABI_VERSION)
         return fail(TEBSCAT_EINVAL, "ABI version %d != %d", desc->abi_version, TEBSCAT_ABI_VERSION);
     if (desc->log2_Np < 1 || desc->log2_Np > kLog2TwMax)
@@ -183,7 +204,9 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     if (desc->n_threads != kThreads) return fail(TEBSCAT_EUNSUPPORTED, "schedules must target 512-thread CTAs");
     if (desc->n_paths < 1 || desc->n_out < 1 || desc->n_tasks < 1 || desc->n_steps < 1 || desc->smem_complex < 1)
         return fail(TEBSCAT_EINVAL, "empty plan");
-    if (int rc = validate_schedule(*desc, tasks, steps, n_floats)) return rc;
+    for (size_t i = 0; i < n_chan; ++i)
+        if (chan[i] < 0 || chan[i] >= desc->n_paths) return fail(TEBSCAT_EINVAL, "channel table entry %zu out of range", i);
+    if (int rc = validate_schedule(*desc, tasks, steps, n_floats, n_chan)) return rc;
 
     int n_dev = 0;
     CU(cudaGetDeviceCount(&n_dev));
@@ -210,20 +233,21 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     CU(cudaMalloc(&p->d_arena, n_floats * sizeof(float)));
     CU(cudaMalloc(&p->d_tw, tw.size() * sizeof(float2)));
     // per-warp view of the schedule: record (step, warp) = the task whose thread range covers the warp
-    std::vector<int32_t> wt((size_t)desc->n_steps * kWarps * 8, 0);
+    std::vector<int32_t> wt((size_t)desc->n_steps * kWarps * kTaskInts, 0);
     for (int st = 0; st < desc->n_steps; ++st) {
         for (int ti = steps[2 * st]; ti < steps[2 * st + 1]; ++ti) {
-            const int32_t* t = tasks + 8 * ti;
-            if ((t[1] & 31) || (t[2] & 31)) { delete p; return fail(TEBSCAT_EINVAL, "task %d: thread range not warp aligned", ti); }
+            const int32_t* t = tasks + kTaskInts * ti;
             for (int w = t[1] / 32; w < (t[1] + t[2]) / 32; ++w) {
-                int32_t* rec = wt.data() + ((size_t)st * kWarps + w) * 8;
+                int32_t* rec = wt.data() + ((size_t)st * kWarps + w) * kTaskInts;
                 if ((rec[0] & 0xff) != OP_NOP) { delete p; return fail(TEBSCAT_EINVAL, "step %d: overlapping thread ranges", st); }
-                memcpy(rec, t, 8 * sizeof(int32_t));
+                memcpy(rec, t, kTaskInts * sizeof(int32_t));
             }
         }
     }
     CU(cudaMalloc(&p->d_warp_tab, wt.size() * sizeof(int32_t)));
     CU(cudaMemcpy(p->d_warp_tab, wt.data(), wt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&p->d_chan, (n_chan ? n_chan : 1) * sizeof(int32_t)));
+    CU(cudaMemcpy(p->d_chan, chan, n_chan * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_arena, arena, n_floats * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     // the attribute belongs to the kernel, not to the plan: always allow the device maximum
@@ -234,6 +258,7 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     k.arena = p->d_arena;
     k.tw = p->d_tw;
     k.warp_tab = reinterpret_cast<const int4*>(p->d_warp_tab);
+    k.chan = p->d_chan;
     k.prof = nullptr;
     k.n_steps = desc->n_steps;
     k.smem_complex = desc->smem_complex;
@@ -260,6 +285,7 @@ extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
     cudaFree(p->d_arena);
     cudaFree(p->d_tw);
     cudaFree(p->d_warp_tab);
+    cudaFree(p->d_chan);
     delete p;
 }
 

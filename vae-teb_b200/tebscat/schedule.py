@@ -1,21 +1,29 @@
 """Host-side plan builder: filter arena + step schedule for the fused cascade kernel.
 
 The CUDA kernel (csrc/scat_core.cuh) is an interpreter of STEPS; each step is a
-set of TASKS on disjoint thread ranges of one 512-thread CTA followed by one
-barrier.  This module turns the cascade of
-``kymatio/scattering1d/core/scattering1d.py:269-370`` into that form:
+set of TASKS on disjoint, warp-aligned thread ranges of one 512-thread CTA
+followed by one barrier.  This module turns the cascade of
+``kymatio/scattering1d/core/scattering1d.py:269-370`` into that form.
 
-* every transform of the cascade becomes a CHAIN of tasks
-  (MULFOLD -> inverse FFT passes [+ modulus] -> forward FFT passes, or
-  MULFOLD -> inverse FFT passes -> STORE for the phi low-pass leaves);
-* chains that do not depend on each other are packed side by side into the same
+Design (what makes the steps full):
+
+* Same-length transforms are BATCHED: first-order filters that share the
+  subsampling 2^k1 are processed ``8192 / L1`` at a time in one contiguous buffer,
+  their children (second order) are grouped by length the same way, and every FFT
+  pass of a batch is ONE task whose butterflies span all blocks of the buffer.
+* The phi low-pass leaves (one per output channel) are tiny: their spectra are
+  collected in a ping-pong POOL and inverse-transformed / unpadded / stored
+  (core :287-292, :320-327, :357-364) by one batched task per pass.
+* "Filter multiply + periodise" (MULFOLD) visits only the 4-bin chunks where the
+  filter is not negligible (below 1e-9 of its peak for every output bin).
+* Chains of tasks that do not depend on each other are packed side by side into
   steps by a list scheduler under two resources: the 512 threads of the CTA and
-  the shared-memory slots their buffers need;
-* filters are cast to fp32 exactly like ``register_filters``
-  (``frontend/torch_frontend.py:75-97``), permuted to bit-reversed bin order and
-  laid out in one flat arena.
+  the shared-memory slots of their buffers.
 
-Task encoding (8 x int32) must match ``csrc/scat_core.cuh``.
+Filters are cast to fp32 exactly like ``register_filters``
+(``frontend/torch_frontend.py:75-97``), permuted to bit-reversed bin order and
+laid out in one flat arena.  Task encoding (12 x int32) must match
+``csrc/scat_core.cuh``.
 """
 from __future__ import annotations
 
@@ -27,14 +35,17 @@ import numpy as np
 
 from . import filterbank as fbk
 
-OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STORE = 0, 1, 2, 3, 4
+OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB = 0, 1, 2, 3, 4
 FFT_INV, FFT_MOD = 1, 2
-ST_IMAG = 1
+TASK_INTS = 12
 
 N_THREADS = 512
 LOG2_NP_MAX = 13                  # single-CTA limit of the kernel (kLog2TwMax)
 SMEM_BYTES_MAX = 227 * 1024
 TW_SLOTS = 64 + 128               # twiddle tables live behind the schedule's slots
+MASK_THRESHOLD = 1e-9             # relative filter magnitude below which a 4-bin chunk is skipped
+BATCH_SLOTS = 8192                # target size of one batch buffer (complex slots)
+POOL_SLOTS = 2048                 # size of one half of the leaf pool
 
 
 def bitrev_indices(n: int) -> np.ndarray:
@@ -56,6 +67,10 @@ def radix_split(n: int) -> List[int]:
     return [base + 1] * extra + [base] * (m - extra)
 
 
+def _round16(n: int) -> int:
+    return (n + 15) & ~15
+
+
 # ------------------------------------------------------------------------------------
 # symbolic tasks / chains
 # ------------------------------------------------------------------------------------
@@ -66,60 +81,117 @@ class Buf:
     name: str = ''
     off: int = -1
     readers_left: int = 0          # chains that still have to read it before it can be freed
+    producer_done: bool = False
+
+
+LEAF = 'leaf'                      # destination marker: a slot of the leaf pool
 
 
 @dataclass
 class TaskSpec:
     op: int
-    work: int                      # independent work items (butterflies / outputs / samples)
-    cost: float                    # relative cost of one work item
-    a: object = 0                  # ints, or Buf (resolved to .off at emission)
+    work: int                      # independent work items
+    lat: float                     # cycles of one work item on an otherwise idle SM
+    instr: float                   # warp instructions of one work item
+    a: object = 0                  # int, or (Buf, offset)
     b: int = 0
     c: int = 0
-    d: object = 0
+    d: object = 0                  # int, (Buf, offset) or LEAF
     e: int = 0
+    f: int = 0
     sexp: int = 0
+    channel: int = -1              # output channel of a leaf MULFOLD
 
 
 @dataclass
 class Chain:
     name: str
-    tasks: List[TaskSpec]
-    reads: Optional[Buf] = None            # buffer read by the first task (must be complete)
-    after: Optional['Chain'] = None        # chain that produces `reads`
+    stages: List[List[TaskSpec]]
+    after: List['Chain'] = field(default_factory=list)
+    reads: List[Buf] = field(default_factory=list)     # buffers read by stage 0
     owns: List[Buf] = field(default_factory=list)      # allocated when the chain starts
-    frees_own_at_end: bool = True
-    priority: float = 0.0
+    frees_own_at_end: bool = False
+    depth: int = 0
+    pool_half: int = -1            # >= 0 for the flush chains of the leaf pool
     # scheduler state
-    pos: int = 0
+    stage: int = 0
+    issued: List[bool] = field(default_factory=list)
     done_step: int = -1
+    priority: float = 0.0
 
 
-def _fft_tasks(buf: Buf, n: int, inverse: bool, modulus: bool = False) -> List[TaskSpec]:
-    """Passes of one in-place length-2^n transform (forward: DIF, inverse: DIT)."""
-    cost = {1: 30.0, 2: 70.0, 3: 170.0, 4: 400.0}
+_FFT_LAT = {1: 450.0, 2: 800.0, 3: 1400.0, 4: 2400.0}
+_FFT_INSTR = {1: 60.0, 2: 120.0, 3: 260.0, 4: 520.0}
+
+
+def _fft_stages(ref, n: int, count: int, inverse: bool, modulus: bool = False) -> List[List[TaskSpec]]:
+    """Passes of `count` in-place length-2^n transforms stored back to back at `ref`."""
     out = []
     if not inverse:
         logB = n
         for r in radix_split(n):
-            out.append(TaskSpec(OP_FFT, 1 << (n - r), cost[r], a=buf, b=n, c=logB, d=r, e=0))
+            out.append([TaskSpec(OP_FFT, count << (n - r), _FFT_LAT[r], _FFT_INSTR[r], a=ref,
+                                 b=count << (n - r), c=logB, d=r, e=0)])
             logB -= r
     else:
         logB = 0
         split = radix_split(n)[::-1]
         for i, r in enumerate(split):
             logB += r
-            last = i == len(split) - 1
-            flags = FFT_INV | (FFT_MOD if (modulus and last) else 0)
-            out.append(TaskSpec(OP_FFT, 1 << (n - r), cost[r], a=buf, b=n, c=logB, d=r, e=flags))
+            flags = FFT_INV | (FFT_MOD if (modulus and i == len(split) - 1) else 0)
+            out.append([TaskSpec(OP_FFT, count << (n - r), _FFT_LAT[r], _FFT_INSTR[r], a=ref,
+                                 b=count << (n - r), c=logB, d=r, e=flags)])
     return out
 
 
-def _mulfold(src: Buf, log_src: int, logk: int, dst: Buf, filt_off: int) -> TaskSpec:
+class _Arena:
+    def __init__(self):
+        self.chunks: List[np.ndarray] = []
+        self.size = 0
+        self.by_off: Dict[int, np.ndarray] = {}
+        self._masks: Dict[Tuple[int, int], int] = {}
+
+    def add(self, f64: np.ndarray) -> int:
+        f32 = f64.astype(np.float32)                       # the reference's .float() cast
+        perm = f32[bitrev_indices(f32.shape[0])]
+        off = self.size
+        pad = (-perm.shape[0]) % 4
+        self.chunks.append(np.concatenate([perm, np.zeros(pad, np.float32)]))
+        self.by_off[off] = perm
+        self.size += perm.shape[0] + pad
+        return off
+
+    def chunk_mask(self, off: int, logk: int) -> int:
+        """Bit c set <=> some output bin has a non-negligible filter value in 4-bin chunk c."""
+        key = (off, logk)
+        if key not in self._masks:
+            f = np.abs(self.by_off[off].astype(np.float64))
+            k = 1 << logk
+            peak = f.max()
+            sig = (f.reshape(-1, k // 4, 4).max(axis=2) > MASK_THRESHOLD * peak).any(axis=0)
+            mask = 0
+            for c, on in enumerate(sig):
+                if on:
+                    mask |= 1 << c
+            self._masks[key] = mask if mask else 1
+        return self._masks[key]
+
+    def finish(self) -> np.ndarray:
+        return np.concatenate(self.chunks) if self.chunks else np.zeros(4, np.float32)
+
+
+def _mulfold(arena: _Arena, src, log_src: int, logk: int, dst, filt_off: int, channel: int = -1) -> TaskSpec:
     log_dst = log_src - logk
+    if logk >= 2:
+        mask = arena.chunk_mask(filt_off, logk)
+        nch = bin(mask).count('1')
+        work, lat, instr = 1 << log_dst, 350.0 + 40.0 * nch, 12.0 + 22.0 * nch
+    else:
+        mask = 0
+        work, lat, instr = 1 << (log_src - 2), 420.0, 40.0
     # mean over k blocks (2^-logk) and the 1/L of the following inverse transform (2^-log_dst)
-    return TaskSpec(OP_MULFOLD, 1 << log_dst, 8.0 + 6.0 * (1 << logk), a=src, b=log_src, c=logk,
-                    d=dst, e=filt_off, sexp=logk + log_dst)
+    return TaskSpec(OP_MULFOLD, work, lat, instr, a=src, b=log_src, c=logk, d=dst, e=filt_off, f=mask,
+                    sexp=logk + log_dst, channel=channel)
 
 
 # ------------------------------------------------------------------------------------
@@ -137,8 +209,9 @@ class ScatPlan:
     keys: List[Tuple[int, ...]]
     n_out: int
     arena: np.ndarray              # float32
-    tasks: np.ndarray              # int32 [n_tasks, 8]
+    tasks: np.ndarray              # int32 [n_tasks, 12]
     steps: np.ndarray              # int32 [n_steps, 2]
+    chan: np.ndarray               # int32 channel table of the batched stores
     smem_complex: int              # PHYSICAL complex slots (logical slots + 1 pad per 16)
     n_threads: int = N_THREADS
     stats: Dict[str, float] = field(default_factory=dict)
@@ -146,28 +219,6 @@ class ScatPlan:
     @property
     def n_paths(self) -> int:
         return len(self.keys)
-
-
-class _Arena:
-    def __init__(self):
-        self.chunks: List[np.ndarray] = []
-        self.size = 0
-
-    def add(self, f64: np.ndarray) -> int:
-        f32 = f64.astype(np.float32)                       # the reference's .float() cast
-        perm = f32[bitrev_indices(f32.shape[0])]
-        off = self.size
-        pad = (-perm.shape[0]) % 4
-        self.chunks.append(np.concatenate([perm, np.zeros(pad, np.float32)]))
-        self.size += perm.shape[0] + pad
-        return off
-
-    def finish(self) -> np.ndarray:
-        return np.concatenate(self.chunks) if self.chunks else np.zeros(4, np.float32)
-
-
-def _round16(n: int) -> int:
-    return (n + 15) & ~15
 
 
 class _Allocator:
@@ -203,14 +254,15 @@ class _Allocator:
         self.free = merged
 
 
-def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int,
-                 arena: _Arena) -> Tuple[List[Chain], List[Tuple[int, ...]], int]:
-    """The cascade as a forest of chains, in the reference's channel order."""
+def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int, arena: _Arena):
+    """The cascade as a forest of chains of batched tasks, in the reference's channel order."""
     n = geo.J_pad
     log2_T = int(math.floor(math.log2(T)))
     lf = n - log2_T                                       # log2 of the final (output-rate) length
     if lf < 0:
         raise ValueError('T is larger than the padded support')
+    if lf < 2:
+        raise NotImplementedError('output-rate length below 4 samples is not supported')
     i0, i1 = geo.ind_start[log2_T], geo.ind_end[log2_T]
     n_out = i1 - i0
 
@@ -225,62 +277,89 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
                 if p2.j > p1.j:
                     keys.append((n1, n2))
     channel = {k: c for c, k in enumerate(keys)}
-
     chains: List[Chain] = []
 
-    def lowpass(src: Buf, log_src: int, level: int, key, parent: Chain) -> Chain:
-        """phi[level] multiply, periodise down to 2^lf, inverse transform, unpad, store."""
-        y = Buf(1 << lf, 'Y%s' % (key,))
-        tasks = [_mulfold(src, log_src, log_src - lf, y, phi_off[level])]
-        tasks += _fft_tasks(y, lf, inverse=True)
-        tasks.append(TaskSpec(OP_STORE, n_out, 6.0, a=y, b=channel[key], c=i0, d=n_out, e=0))
-        ch = Chain('S%s' % (key,), tasks, reads=src, after=parent, owns=[y])
-        chains.append(ch)
-        return ch
+    def leaf(src, log_src: int, level: int, key) -> TaskSpec:
+        """phi[level] multiply + periodise down to 2^lf into a pool slot (core :287-289)."""
+        return _mulfold(arena, src, log_src, log_src - lf, LEAF, phi_off[level], channel[key])
 
     # root: pad + forward transform of the signal (core/scattering1d.py:278-280)
     u0 = Buf(1 << n, 'U0')
-    root = Chain('root', [TaskSpec(OP_LOAD, 1 << n, 8.0, a=u0)] + _fft_tasks(u0, n, inverse=False),
-                 owns=[u0], frees_own_at_end=False)
+    root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
+                 _fft_stages((u0, 0), n, 1, inverse=False), owns=[u0], depth=0)
     chains.append(root)
-    lowpass(u0, n, 0, (), root)                                        # S0 (:285-292)
+    chains.append(Chain('S0', [[leaf((u0, 0), n, 0, ())]], after=[root], reads=[u0], depth=1))   # :285-292
 
-    for n1, p1 in enumerate(bank.psi1):                                # :300
+    # first order, batched by subsampling k1 (:300-318)
+    groups: Dict[int, List[int]] = {}
+    for n1, p1 in enumerate(bank.psi1):
         k1 = max(min(p1.j, log2_T), 0)                                 # :304
         if not p1.xi < 0.5 / (2 ** k1):
             raise AssertionError('psi1 aliasing assertion of the reference violated')
+        groups.setdefault(k1, []).append(n1)
+    for k1 in sorted(groups):
         l1 = n - k1
-        x1 = Buf(1 << l1, 'U1[%d]' % n1)
-        t = [_mulfold(u0, n, k1, x1, psi1_off[n1])]                    # :307-311
-        t += _fft_tasks(x1, l1, inverse=True, modulus=True)            # :312-315
-        t += _fft_tasks(x1, l1, inverse=False)                         # :318
-        c1 = Chain('U1[%d]' % n1, t, reads=u0, after=root, owns=[x1], frees_own_at_end=False)
-        chains.append(c1)
-        lowpass(x1, l1, k1, (n1,), c1)                                 # :320-327
-        if max_order == 2:
-            for n2, p2 in enumerate(bank.psi2):                        # :337
-                if p2.j > p1.j:
-                    if not p2.xi < p1.xi:
-                        raise AssertionError('psi2 ordering assertion of the reference violated')
-                    k2 = max(min(p2.j - k1, log2_T - k1), 0)           # :344-345
-                    l2 = l1 - k2
-                    x2 = Buf(1 << l2, 'U2[%d,%d]' % (n1, n2))
-                    t = [_mulfold(x1, l1, k2, x2, psi2_off[n2][k1])]   # :347-348
-                    t += _fft_tasks(x2, l2, inverse=True, modulus=True)
-                    t += _fft_tasks(x2, l2, inverse=False)             # :355
-                    c2 = Chain('U2[%d,%d]' % (n1, n2), t, reads=x1, after=c1, owns=[x2],
-                               frees_own_at_end=False)
+        per_batch = max(1, BATCH_SLOTS >> l1)
+        members = groups[k1]
+        for s in range(0, len(members), per_batch):
+            batch = members[s:s + per_batch]
+            nb = len(batch)
+            x1 = Buf(nb << l1, 'U1[k1=%d:%d]' % (k1, batch[0]))
+            st = [[_mulfold(arena, (u0, 0), n, k1, (x1, i << l1), psi1_off[n1]) for i, n1 in enumerate(batch)]]
+            st += _fft_stages((x1, 0), l1, nb, inverse=True, modulus=True)             # :312-315
+            st += _fft_stages((x1, 0), l1, nb, inverse=False)                          # :318
+            c1 = Chain(x1.name, st, after=[root], reads=[u0], owns=[x1], depth=1)
+            chains.append(c1)
+            # low-pass leaves of the batch (:320-327)
+            chains.append(Chain('S1' + x1.name, [[leaf((x1, i << l1), l1, k1, (n1,)) for i, n1 in enumerate(batch)]],
+                                after=[c1], reads=[x1], depth=2))
+            if max_order != 2:
+                continue
+            # second order, grouped by child length (:337-364)
+            kids: Dict[int, List[Tuple[int, int, int]]] = {}
+            for i, n1 in enumerate(batch):
+                p1 = bank.psi1[n1]
+                for n2, p2 in enumerate(bank.psi2):
+                    if p2.j > p1.j:
+                        if not p2.xi < p1.xi:
+                            raise AssertionError('psi2 ordering assertion of the reference violated')
+                        k2 = max(min(p2.j - k1, log2_T - k1), 0)       # :344-345
+                        kids.setdefault(k2, []).append((i, n1, n2))
+            for k2 in sorted(kids):
+                l2 = l1 - k2
+                fam = kids[k2]
+                per = max(1, BATCH_SLOTS >> l2)
+                for s2 in range(0, len(fam), per):
+                    sub = fam[s2:s2 + per]
+                    x2 = Buf(len(sub) << l2, 'U2[%d,k2=%d]' % (batch[0], k2))
+                    st = [[_mulfold(arena, (x1, i << l1), l1, k2, (x2, c << l2), psi2_off[n2][k1])
+                           for c, (i, n1, n2) in enumerate(sub)]]                       # :347-348
+                    st += _fft_stages((x2, 0), l2, len(sub), inverse=True, modulus=True)
+                    st += _fft_stages((x2, 0), l2, len(sub), inverse=False)             # :355
+                    c2 = Chain(x2.name, st, after=[c1], reads=[x1], owns=[x2], depth=2)
                     chains.append(c2)
-                    lowpass(x2, l2, k1 + k2, (n1, n2), c2)             # :358-364
-    return chains, keys, n_out
+                    chains.append(Chain('S2' + x2.name,
+                                        [[leaf((x2, c << l2), l2, k1 + k2, (n1, n2)) for c, (i, n1, n2) in enumerate(sub)]],
+                                        after=[c2], reads=[x2], depth=3))               # :358-364
+    return chains, keys, n_out, lf, i0
 
 
+# ------------------------------------------------------------------------------------
+# list scheduler
+# ------------------------------------------------------------------------------------
 def _want_threads(work: int) -> int:
     return min(N_THREADS, max(32, (work + 31) & ~31))
 
 
-def _task_time(t: TaskSpec, nt: int) -> float:
-    return math.ceil(t.work / nt) * t.cost
+def _step_time(items: List[Tuple[TaskSpec, int]]) -> float:
+    """Cost model of one step: the slowest thread, or the issue slots of the 4 schedulers."""
+    lat = 0.0
+    issue = 0.0
+    for t, nt in items:
+        iters = math.ceil(t.work / nt)
+        lat = max(lat, iters * t.lat)
+        issue += (nt // 32) * iters * t.instr
+    return max(lat, issue / (4 * 0.75)) + 250.0
 
 
 def _split_threads(tasks: List[TaskSpec]) -> Optional[List[int]]:
@@ -291,19 +370,18 @@ def _split_threads(tasks: List[TaskSpec]) -> Optional[List[int]]:
     nts = [32] * n
     left = N_THREADS - 32 * n
     while left > 0:
-        times = [_task_time(t, nt) for t, nt in zip(tasks, nts)]
+        times = [math.ceil(t.work / nt) * t.lat for t, nt in zip(tasks, nts)]
         order = sorted(range(n), key=lambda i: -times[i])
         grew = False
         for i in order:
-            if nts[i] >= _want_threads(tasks[i].work):
+            want = _want_threads(tasks[i].work)
+            if nts[i] >= want:
                 if i == order[0]:
                     break                                # the slowest task cannot go faster
                 continue
-            # smallest increment that removes one iteration
             it = math.ceil(tasks[i].work / nts[i])
             need = nts[i] + 32
-            while need < N_THREADS and math.ceil(tasks[i].work / need) >= it and \
-                    need < _want_threads(tasks[i].work):
+            while need < want and math.ceil(tasks[i].work / need) >= it:
                 need += 32
             if need - nts[i] > left:
                 if i == order[0]:
@@ -318,64 +396,102 @@ def _split_threads(tasks: List[TaskSpec]) -> Optional[List[int]]:
     return nts
 
 
-def schedule_chains(chains: List[Chain], capacity: int, max_parallel: int = 64,
-                    stretch: float = 1.15, step_overhead: float = 150.0):
-    """Greedy list scheduling of chains into steps.
+class _LeafPool:
+    """Ping-pong pool of 2^lf-slot leaf spectra; a full half is flushed by one batched
+    inverse transform + unpad + store (the flush chain)."""
 
-    Resources: the 512 threads of the CTA (per step) and `capacity` shared-memory
-    slots (over buffer lifetimes).  A chain may start once the chain producing the
-    buffer it reads has finished and its own buffers fit; a buffer is released when
-    every chain reading it has executed its first task.  Starting a chain that has
-    dependants also RESERVES room for their buffers so that a subtree, once begun,
-    can always be finished and its memory returned (no deadlock, depth first).
-    """
+    def __init__(self, lf: int, i0: int, n_out: int):
+        self.lf, self.i0, self.n_out = lf, i0, n_out
+        self.per_half = max(2, POOL_SLOTS >> lf)
+        self.bufs = [Buf(self.per_half << lf, 'pool0'), Buf(self.per_half << lf, 'pool1')]
+        self.fill = [0, 0]
+        self.channels: List[List[int]] = [[], []]
+        self.busy = [False, False]                      # half is being flushed
+        self.cur = 0
+        self.chan_table: List[int] = []
+
+    def room(self) -> int:
+        return 0 if self.busy[self.cur] else self.per_half - self.fill[self.cur]
+
+    def take(self, channel: int) -> int:
+        h = self.cur
+        slot = self.fill[h]
+        self.fill[h] += 1
+        self.channels[h].append(channel)
+        return self.bufs[h].off + (slot << self.lf)
+
+    def flush_chain(self, h: int) -> Chain:
+        cnt = self.fill[h]
+        table_off = len(self.chan_table)
+        self.chan_table += self.channels[h]
+        ref = (self.bufs[h], 0)
+        st = _fft_stages(ref, self.lf, cnt, inverse=True)
+        st.append([TaskSpec(OP_STOREB, cnt * self.n_out, 150.0, 14.0, a=ref, b=cnt, c=self.i0, d=self.n_out,
+                            e=table_off, f=self.lf)])
+        ch = Chain('flush%d@%d' % (h, table_off), st, depth=9, pool_half=h)
+        self.busy[h] = True
+        self.fill[h] = 0
+        self.channels[h] = []
+        return ch
+
+    def rotate(self):
+        """Make `cur` point at a half that can take leaves, if there is one."""
+        if self.room() == 0:
+            o = 1 - self.cur
+            if not self.busy[o] and self.fill[o] < self.per_half:
+                self.cur = o
+
+
+def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out: int,
+                    max_parallel: int = 64, stretch: float = 1.10):
+    """Greedy list scheduling of chains into steps (see module docstring)."""
     children: Dict[int, List[Chain]] = {}
     for ch in chains:
-        if ch.after is not None:
-            children.setdefault(id(ch.after), []).append(ch)
-    readers: Dict[int, int] = {}
+        for a in ch.after:
+            children.setdefault(id(a), []).append(ch)
     for ch in chains:
-        if ch.reads is not None:
-            readers[id(ch.reads)] = readers.get(id(ch.reads), 0) + 1
-    bufs = {id(b): b for ch in chains for b in ch.owns}
-    for k, v in readers.items():
-        bufs[k].readers_left = v
+        for b in ch.reads:
+            b.readers_left += 1
 
     own_size = {id(c): sum(_round16(b.size) for b in c.owns) for c in chains}
-    depth: Dict[int, int] = {}
     weight: Dict[int, float] = {}
     need: Dict[int, int] = {}
 
-    def visit(c: Chain, d: int):
-        depth[id(c)] = d
-        w = sum(t.work * t.cost for t in c.tasks)
+    def visit(c: Chain):
+        w = sum(t.work * t.instr for st in c.stages for t in st)
         nd = 0
         for k in children.get(id(c), []):
-            visit(k, d + 1)
+            if id(k) not in weight:
+                visit(k)
             w += weight[id(k)]
             nd += own_size[id(k)] + need[id(k)]
         weight[id(c)] = w
-        need[id(c)] = nd if d > 0 else 0          # the root does not reserve for the whole tree
+        need[id(c)] = nd if c.depth > 0 else 0          # the root does not reserve for the whole tree
 
     for c in chains:
-        if c.after is None:
-            visit(c, 0)
-    parent_of = {id(c): c.after for c in chains}
+        if id(c) not in weight:
+            visit(c)
+    parent_of = {id(c): (c.after[0] if c.after else None) for c in chains}
     for c in chains:
-        c.priority = depth[id(c)] * 1e12 + weight[id(c)]
-        c.pos = 0
+        c.priority = c.depth * 1e12 + weight[id(c)]
+        c.stage = 0
+        c.issued = [False] * len(c.stages[0])
         c.done_step = -1
 
     alloc = _Allocator(capacity)
-    free_slots = capacity
-    reserve_left: Dict[int, int] = {}              # chain id -> slots still reserved for its subtree
+    pool = _LeafPool(lf, i0, n_out)
+    for b in pool.bufs:
+        b.off = alloc.alloc(b.size)
+        assert b.off >= 0
+    free_slots = capacity - sum(_round16(b.size) for b in pool.bufs)
+    reserve_left: Dict[int, int] = {}
     pending = list(chains)
     active: List[Chain] = []
     steps: List[List[List[int]]] = []
-    producer_done: Dict[int, bool] = {}
     step_idx = 0
     est_time = 0.0
-    est_work = 0.0
+    est_issue = 0.0
+    by_id = {id(c): c for c in chains}
 
     def release(buf: Buf):
         nonlocal free_slots
@@ -384,20 +500,23 @@ def schedule_chains(chains: List[Chain], capacity: int, max_parallel: int = 64,
         buf.off = -2
 
     def release_if_dead(buf: Buf):
-        if buf.readers_left == 0 and producer_done.get(id(buf), False) and buf.off >= 0:
+        if buf.readers_left == 0 and buf.producer_done and buf.off >= 0:
             release(buf)
 
     def ancestors(c: Chain):
-        a = parent_of[id(c)]
+        a = parent_of.get(id(c))
         while a is not None:
             yield a
-            a = parent_of[id(a)]
+            a = parent_of.get(id(a))
+
+    def subtree_done(ch: Chain) -> bool:
+        return ch.done_step >= 0 and all(subtree_done(k) for k in children.get(id(ch), []))
 
     def try_start(c: Chain, force: bool) -> bool:
         nonlocal free_slots
-        mine = own_size[id(c)]
+        mine = own_size.get(id(c), 0)
         reserved_others = sum(reserve_left.values()) - sum(reserve_left.get(id(a), 0) for a in ancestors(c))
-        if not force and free_slots - reserved_others < mine + need[id(c)]:
+        if not force and free_slots - reserved_others < mine + need.get(id(c), 0):
             return False
         offs = []
         for b in c.owns:
@@ -413,24 +532,48 @@ def schedule_chains(chains: List[Chain], capacity: int, max_parallel: int = 64,
         for a in ancestors(c):
             if id(a) in reserve_left:
                 reserve_left[id(a)] = max(0, reserve_left[id(a)] - mine)
-        if need[id(c)] > 0:
+        if need.get(id(c), 0) > 0:
             reserve_left[id(c)] = need[id(c)]
         return True
 
-    while pending or active:
-        startable = [c for c in pending if c.after is None or
-                     (c.after.done_step >= 0 and c.after.done_step < step_idx)]
+    def resolve(ref):
+        if isinstance(ref, tuple):
+            assert ref[0].off >= 0, 'task touches a released buffer (%s)' % ref[0].name
+            return ref[0].off + ref[1]
+        return int(ref)
+
+    def start_flush(h: int):
+        ch = pool.flush_chain(h)
+        ch.priority = 9e12
+        ch.stage = 0
+        ch.issued = [False] * len(ch.stages[0])
+        by_id[id(ch)] = ch
+        active.append(ch)
+        pool.rotate()
+
+    guard = 0
+    while pending or active or pool.fill[0] or pool.fill[1]:
+        guard += 1
+        if guard > 100000:
+            raise RuntimeError('scheduler did not terminate')
+        if not pending and not active:
+            for h in (0, 1):
+                if pool.fill[h] and not pool.busy[h]:
+                    start_flush(h)
+        # ---- start chains whose inputs are complete ------------------------------------
+        startable = [c for c in pending if all(a.done_step >= 0 and a.done_step < step_idx for a in c.after)]
         startable.sort(key=lambda c: -c.priority)
-        demand = sum(_want_threads(c.tasks[c.pos].work) for c in active)
+        demand = sum(sum(_want_threads(t.work) for t, done in zip(c.stages[c.stage], c.issued) if not done)
+                     for c in active)
         for c in startable:
             if len(active) >= max_parallel:
                 break
-            if demand >= 2 * N_THREADS and depth[id(c)] <= 1:
+            if demand >= 2 * N_THREADS and c.depth <= 1:
                 continue                          # enough queued work; do not open new subtrees
             if try_start(c, force=False):
                 pending.remove(c)
                 active.append(c)
-                demand += _want_threads(c.tasks[0].work)
+                demand += sum(_want_threads(t.work) for t in c.stages[0])
         if not active:
             for c in startable:                   # progress guarantee
                 if try_start(c, force=True):
@@ -441,58 +584,77 @@ def schedule_chains(chains: List[Chain], capacity: int, max_parallel: int = 64,
             raise RuntimeError('schedule deadlock: %d chains cannot be placed in %d slots'
                                % (len(pending), capacity))
 
-        # choose the tasks of this step
+        # ---- choose the tasks of this step ------------------------------------------------
         active.sort(key=lambda c: -c.priority)
-        chosen: List[Chain] = []
-        nts: List[int] = []
-        cur_max = 0.0
+        cands: List[Tuple[Chain, int, TaskSpec]] = []
         for c in active:
-            trial = chosen + [c]
-            split = _split_threads([k.tasks[k.pos] for k in trial])
+            for ti, t in enumerate(c.stages[c.stage]):
+                if not c.issued[ti]:
+                    cands.append((c, ti, t))
+        chosen: List[Tuple[Chain, int, TaskSpec]] = []
+        nts: List[int] = []
+        cur_time = 0.0
+        pool_room = pool.room()
+        for cand in cands:
+            t = cand[2]
+            if t.d is LEAF and pool_room <= 0:
+                continue
+            trial = chosen + [cand]
+            split = _split_threads([k[2] for k in trial])
             if split is None:
                 break
-            tmax = max(_task_time(k.tasks[k.pos], nt) for k, nt in zip(trial, split))
-            if chosen and tmax > stretch * cur_max + 1e-9:
+            tt = _step_time(list(zip([k[2] for k in trial], split)))
+            alone = _step_time([(t, _want_threads(t.work))])
+            if chosen and tt > stretch * max(cur_time, alone):
                 continue
-            chosen, nts, cur_max = trial, split, max(tmax, cur_max) if chosen else tmax
+            chosen, nts, cur_time = trial, split, tt
+            if t.d is LEAF:
+                pool_room -= 1
+        if not chosen:
+            raise RuntimeError('scheduler stalled on the leaf pool')
         this_step: List[List[int]] = []
         used = 0
-        for c, nt in zip(chosen, nts):
-            t = c.tasks[c.pos]
-            a = t.a.off if isinstance(t.a, Buf) else t.a
-            d = t.d.off if isinstance(t.d, Buf) else t.d
-            assert a >= 0 and d >= 0, 'task touches a released buffer'
-            this_step.append([t.op | (t.sexp << 8), used, nt, int(a), t.b, t.c, int(d), t.e])
+        for (c, ti, t), nt in zip(chosen, nts):
+            dst = pool.take(t.channel) if t.d is LEAF else resolve(t.d)
+            this_step.append([t.op | (t.sexp << 8), used, nt, resolve(t.a), t.b, t.c, dst, t.e, t.f, 0, 0, 0])
             used += nt
-            est_work += t.work * t.cost
-        est_time += cur_max + step_overhead
+            est_issue += (nt // 32) * math.ceil(t.work / nt) * t.instr
+            c.issued[ti] = True
+        est_time += cur_time
         steps.append(this_step)
-        for c in chosen:
-            if c.pos == 0 and c.reads is not None:
-                c.reads.readers_left -= 1
-                release_if_dead(c.reads)
-            c.pos += 1
-            if c.pos == len(c.tasks):
+
+        # ---- advance chains --------------------------------------------------------------------
+        for c in list({id(k[0]): k[0] for k in chosen}.values()):
+            if not all(c.issued):
+                continue
+            if c.stage == 0:
+                for b in c.reads:
+                    b.readers_left -= 1
+                    release_if_dead(b)
+            c.stage += 1
+            if c.stage == len(c.stages):
                 c.done_step = step_idx
                 active.remove(c)
-                reserve_left.pop(id(c), None) if not children.get(id(c)) else None
                 for b in c.owns:
-                    producer_done[id(b)] = True
+                    b.producer_done = True
                     if c.frees_own_at_end:
                         release(b)
                     else:
                         release_if_dead(b)
-        # a reservation ends when the whole subtree of its chain has finished
+                if c.pool_half >= 0:
+                    pool.busy[c.pool_half] = False
+                    pool.rotate()
+            else:
+                c.issued = [False] * len(c.stages[c.stage])
         for cid in list(reserve_left.keys()):
-            def subtree_done(ch: Chain) -> bool:
-                return ch.done_step >= 0 and all(subtree_done(k) for k in children.get(id(ch), []))
-            owner = next(c for c in chains if id(c) == cid)
-            if subtree_done(owner):
+            if subtree_done(by_id[cid]):
                 reserve_left.pop(cid)
+        if pool.fill[pool.cur] == pool.per_half and not pool.busy[pool.cur]:
+            start_flush(pool.cur)
         step_idx += 1
-    sched_stats = dict(est_time=est_time, est_work=est_work,
-                       est_fill=est_work / (N_THREADS * max(est_time, 1.0)))
-    return steps, alloc.high_water, sched_stats
+    sched_stats = dict(est_cycles=est_time, est_issue=est_issue,
+                       est_fill=est_issue / (4 * 0.75) / max(est_time, 1.0))
+    return steps, alloc.high_water, pool.chan_table, sched_stats
 
 
 def emit(steps) -> Tuple[np.ndarray, np.ndarray]:
@@ -500,7 +662,8 @@ def emit(steps) -> Tuple[np.ndarray, np.ndarray]:
     for st in steps:
         ranges.append([len(rows), len(rows) + len(st)])
         rows.extend(st)
-    return np.asarray(rows, dtype=np.int32).reshape(-1, 8), np.asarray(ranges, dtype=np.int32).reshape(-1, 2)
+    return (np.asarray(rows, dtype=np.int32).reshape(-1, TASK_INTS),
+            np.asarray(ranges, dtype=np.int32).reshape(-1, 2))
 
 
 def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int = 64) -> ScatPlan:
@@ -512,14 +675,14 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
             'the large-support path is not built yet' % (geo.J_pad, LOG2_NP_MAX))
     bank = fbk.build_filter_bank(geo.J_pad, J, Q1, T)
     arena = _Arena()
-    chains, keys, n_out = build_chains(bank, geo, T, max_order, arena)
+    chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena)
     # logical slots; the kernel pads one slot per 16 (scat_core.cuh: swz)
     capacity = ((SMEM_BYTES_MAX // 8 - TW_SLOTS) * 16 // 17) & ~15
-    steps, high, sched = schedule_chains(chains, capacity, max_parallel)
+    steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel)
     tasks, ranges = emit(steps)
     n_tasks = tasks.shape[0]
-    stats = dict(n_steps=len(steps), n_tasks=n_tasks, smem_complex=high,
+    stats = dict(n_steps=len(steps), n_tasks=n_tasks, smem_logical=high,
                  mean_tasks_per_step=n_tasks / max(1, len(steps)), **sched)
     logical = _round16(high)
     return ScatPlan(J, Q1, T, N, max_order, geo, bank, keys, n_out, arena.finish(), tasks, ranges,
-                    logical + logical // 16, N_THREADS, stats)
+                    np.asarray(chan, dtype=np.int32), logical + logical // 16, N_THREADS, stats)

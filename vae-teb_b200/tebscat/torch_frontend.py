@@ -49,11 +49,13 @@ class _DevicePlan:
         arena = np.ascontiguousarray(plan.arena, np.float32)
         tasks = np.ascontiguousarray(plan.tasks, np.int32)
         steps = np.ascontiguousarray(plan.steps, np.int32)
+        chan = np.ascontiguousarray(plan.chan, np.int32)
         handle = ctypes.c_void_p()
+        i32p = ctypes.POINTER(ctypes.c_int32)
         rc = lib.tebscat_plan_create(
             ctypes.byref(desc), arena.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), arena.size,
-            tasks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-            steps.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(device_index), ctypes.byref(handle))
+            tasks.ctypes.data_as(i32p), steps.ctypes.data_as(i32p), chan.ctypes.data_as(i32p), chan.size,
+            int(device_index), ctypes.byref(handle))
         _lib.check(rc)
         self.handle = handle
         self._lib = lib
