@@ -268,24 +268,36 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
     if (logk >= 2) {
         const int n_dst = 1 << (t.b - logk);
         const unsigned mask = (unsigned)t.f;
-        TEB_UNROLL2 for (int m = lt; m < n_dst; m += t.nt) {
-            float ax = 0.f, ay = 0.f;
-            const int s0 = t.a + (m << logk);
-            const float* fm = f + (m << logk);
+        // four outputs per thread and trip: the chunk loop is uniform over the task, so the
+        // four 128-bit filter loads of one chunk are in flight together
+        for (int m0 = lt; m0 < n_dst; m0 += 4 * t.nt) {
+            float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f};
             unsigned rest = mask;
             while (rest) {
-                const int ch = TEB_FFS(rest) - 1;
+                const int i = (TEB_FFS(rest) - 1) << 2;
                 rest &= rest - 1;
-                const int i = ch << 2;
-                const float4 g = TEB_LDG(reinterpret_cast<const float4*>(fm + i));
-                const int q = swz(s0 + i);          // 4 slots of one 16-group: contiguous
-                const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
-                ax = fmaf(z0.x, g.x, ax); ay = fmaf(z0.y, g.x, ay);
-                ax = fmaf(z1.x, g.y, ax); ay = fmaf(z1.y, g.y, ay);
-                ax = fmaf(z2.x, g.z, ax); ay = fmaf(z2.y, g.z, ay);
-                ax = fmaf(z3.x, g.w, ax); ay = fmaf(z3.y, g.w, ay);
+                float4 g[4];
+                TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + j * t.nt;
+                    g[j] = (m < n_dst) ? TEB_LDG(reinterpret_cast<const float4*>(f + (m << logk) + i))
+                                       : float4{0.f, 0.f, 0.f, 0.f};
+                }
+                TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + j * t.nt;
+                    if (m < n_dst) {
+                        const int q = swz(t.a + (m << logk) + i);      // 4 slots of one 16-group: contiguous
+                        const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
+                        ax[j] = fmaf(z0.x, g[j].x, ax[j]); ay[j] = fmaf(z0.y, g[j].x, ay[j]);
+                        ax[j] = fmaf(z1.x, g[j].y, ax[j]); ay[j] = fmaf(z1.y, g[j].y, ay[j]);
+                        ax[j] = fmaf(z2.x, g[j].z, ax[j]); ay[j] = fmaf(z2.y, g[j].z, ay[j]);
+                        ax[j] = fmaf(z3.x, g[j].w, ax[j]); ay[j] = fmaf(z3.y, g[j].w, ay[j]);
+                    }
+                }
             }
-            S[swz(t.d + m)] = make_float2(ax * scale, ay * scale);
+            TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                const int m = m0 + j * t.nt;
+                if (m < n_dst) S[swz(t.d + m)] = make_float2(ax[j] * scale, ay[j] * scale);
+            }
         }
     } else {
         const int n_items = 1 << (t.b - 2);                    // 4 source slots per item
@@ -311,11 +323,19 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
 // reflect padding of torch_backend.py:50-78 (F.pad(..., mode='reflect'); pad < N)
 TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
     const int Np = 1 << c.log2_Np;
-    for (int i = lt; i < Np; i += t.nt) {
-        int r = i - c.pad_left;
-        if (r < 0) r = -r;
-        if (r >= c.N) r = 2 * (c.N - 1) - r;
-        S[swz(t.a + i)] = make_float2(TEB_LDG(c.x + r), 0.f);
+    for (int i0 = lt; i0 < Np; i0 += 8 * t.nt) {
+        float v[8];
+        TEB_UNROLL for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j * t.nt;
+            int r = i - c.pad_left;
+            if (r < 0) r = -r;
+            if (r >= c.N) r = 2 * (c.N - 1) - r;
+            v[j] = (i < Np) ? TEB_LDG(c.x + r) : 0.f;
+        }
+        TEB_UNROLL for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j * t.nt;
+            if (i < Np) S[swz(t.a + i)] = make_float2(v[j], 0.f);
+        }
     }
 }
 
