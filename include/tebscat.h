@@ -92,6 +92,42 @@ int tebscat_scat1d_forward_host(tebscat_plan* plan, const float* x_host, int64_t
 int tebscat_scat1d_profile_steps(const tebscat_plan* plan, const float* x_dev, int64_t B,
                                  float* S_dev, long long* step_clocks_host, void* stream);
 
+/* ---- phase-harmonic correlation (hdf5_dataset/kymatio_phase_scattering.py) ---------- */
+
+/* Geometry of KymatioPhaseScattering1D's phase path (:100-160, :233-273). */
+typedef struct tebscat_phase_desc {
+    int32_t abi_version;
+    int32_t N;             /* input length                                                     */
+    int32_t n_filters;     /* F: first-order filters (rows of psi1_filters, :123-124)          */
+    int32_t n_pairs;       /* P: pairs (i, j) with xi_j >= xi_i (:141-152)                      */
+    int32_t n_out;         /* N // dec: length of the decimated output (:258-268)              */
+    int32_t n_cols_pad;    /* columns of the smoothing operator, n_out rounded up to 80        */
+    int32_t reserved[10];
+} tebscat_phase_desc;
+
+typedef struct tebscat_phase_plan tebscat_phase_plan;
+
+/* `stage_a` is a plan whose schedule ends in STOREZ tasks (n_paths = F, n_out = N); its
+ * ownership passes to the phase plan.  G_host: [N][n_cols_pad][2] fp32, the operator
+ * reflect-pad -> FFT -> phi -> truncate -> iFFT -> slice of _apply_phi_filter (:233-273).
+ * i_idx/j_idx/powers replace the buffers of _build_coupling_indices (:134-160). */
+int tebscat_phase_plan_create(const tebscat_phase_desc* desc, tebscat_plan* stage_a,
+                              const float* G_host, const int32_t* i_idx, const int32_t* j_idx,
+                              const float* powers, tebscat_phase_plan** out);
+
+void tebscat_phase_plan_destroy(tebscat_phase_plan* plan);
+
+/* out[b, s, :] = Re smooth( |z_i| exp(i p theta_i) conj(z_j) ) for the selected pairs s,
+ * z_i from channel ch_i and z_j from channel ch_j of x_dev [B, n_channels, N]
+ * (ch_i == ch_j: _compute_phase_correlation :275-301; else
+ * _compute_cross_channel_phase_correlation :303-360).  pair_subset_host (nullable) selects
+ * pairs like `same_pairs_only` / the dataset masks (create_hdf5_dataset.py:440-441).
+ * apply_low_pass == 0 returns the full-rate real part, out [B, n_sel, N] (:356-360).
+ * Calls on one phase plan are serialised (it owns an L2-sized workspace). */
+int tebscat_phase_forward(tebscat_phase_plan* plan, const float* x_dev, int64_t B, int n_channels,
+                          int ch_i, int ch_j, const int32_t* pair_subset_host, int n_subset,
+                          int apply_low_pass, float* out_dev, void* stream);
+
 /* Number of kernels the last forward call on this thread launched. */
 int tebscat_last_launch_count(void);
 

@@ -16,7 +16,8 @@ using namespace tebscat;
 extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths, int n_out,
                                   int smem_complex, int n_tasks, int n_steps,
                                   const float* arena, const int32_t* tasks, const int32_t* steps,
-                                  const int32_t* chan, const float* x, long long B, float* out) {
+                                  const int32_t* chan, const float* x, long long B, float* out,
+                                  float* zc, float* zp, int z_mode) {
     std::vector<float2> S((size_t)smem_complex);
     std::vector<float2> tw(kTwA + kTwB);
     const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
@@ -29,6 +30,9 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
         c.x = x + b * N;
         c.out = out + b * (long long)n_paths * n_out;
         c.chan = chan;
+        c.zc = reinterpret_cast<float2*>(zc) + b * (long long)n_paths * n_out;
+        c.zp = reinterpret_cast<float2*>(zp) + b * (long long)n_paths * n_out;
+        c.z_mode = z_mode;
         c.N = N; c.pad_left = pad_left; c.log2_Np = log2_Np; c.n_out = n_out;
         for (int s = 0; s < n_steps; ++s) {
             for (int ti = steps[2 * s]; ti < steps[2 * s + 1]; ++ti) {

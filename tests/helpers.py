@@ -34,12 +34,15 @@ def emu_available():
     return os.path.exists(EMU_PATH)
 
 
-def emu_forward(plan, x):
-    """Run the schedule of `plan` through the host emulator (tests/emu)."""
+def emu_forward(plan, x, stage_a=False):
+    """Run the schedule of `plan` through the host emulator (tests/emu).  With stage_a=True the
+    plan is a phase stage-A schedule and the (cartesian, polar) analytic signals are returned."""
     lib = ctypes.CDLL(EMU_PATH)
     x = np.ascontiguousarray(x, np.float32)
     B = x.shape[0]
-    out = np.full((B, plan.n_paths, plan.n_out), np.nan, np.float32)
+    out = np.full((B, plan.n_paths, plan.n_out) if not stage_a else (1,), np.nan, np.float32)
+    zshape = (B, plan.n_paths, plan.n_out, 2) if stage_a else (1,)
+    zc, zp = np.full(zshape, np.nan, np.float32), np.full(zshape, np.nan, np.float32)
     fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
     tasks = np.ascontiguousarray(plan.tasks, np.int32)
     steps = np.ascontiguousarray(plan.steps, np.int32)
@@ -48,6 +51,9 @@ def emu_forward(plan, x):
     rc = lib.emu_scat1d_forward(plan.N, plan.geo.J_pad, plan.geo.pad_left, plan.n_paths, plan.n_out,
                                 plan.smem_complex, tasks.shape[0], steps.shape[0],
                                 arena.ctypes.data_as(fp), tasks.ctypes.data_as(ip), steps.ctypes.data_as(ip),
-                                chan.ctypes.data_as(ip), x.ctypes.data_as(fp), ctypes.c_longlong(B), out.ctypes.data_as(fp))
+                                chan.ctypes.data_as(ip), x.ctypes.data_as(fp), ctypes.c_longlong(B), out.ctypes.data_as(fp),
+                                zc.ctypes.data_as(fp), zp.ctypes.data_as(fp), 3 if stage_a else 0)
     assert rc == 0
+    if stage_a:
+        return zc[..., 0] + 1j * zc[..., 1], zp
     return out

@@ -1,0 +1,144 @@
+"""GPU parity of the phase-harmonic correlation path (KymatioPhaseScattering1D) against the
+float64 oracle and the committed outputs of the live reference.
+
+PARITY UNPINNED by the reference's own tests (it has none for this module).  Tolerances: the
+reference rounds p*theta in fp32 with p up to ~100 and its theta flips sign at the two
+reflect-symmetry samples, so comparisons go through the oracle's branch
+alignment and use: overall rel-L2 <= 5e-5, per-path median <= 5e-5, per-path max <= 2e-3 --
+the same numbers the oracle itself is pinned with against the reference (test_oracle_golden)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, rel_l2
+from oracle.phase_oracle import PhaseOracle
+
+pytestmark = pytest.mark.gpu
+
+CFG = {'H': (6, 8, 64, 4800, 2), 'P': (11, 4, 16, 5760, 1), 'S': (4, 4, 16, 1000, 2)}
+_mods = {}
+
+
+def module_of(name):
+    from tebscat import KymatioPhaseScattering1D
+    if name not in _mods:
+        J, Q, T, N, mo = CFG[name]
+        _mods[name] = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), max_order=mo)
+    return _mods[name]
+
+
+def check(ours, oracle_aligned, tag):
+    overall = rel_l2(ours, oracle_aligned)
+    per_path = rel_l2(ours, oracle_aligned, axis=-1)
+    assert overall < 5e-5, (tag, overall)
+    assert np.median(per_path) < 5e-5 and per_path.max() < 2e-3, (tag, np.median(per_path), per_path.max())
+
+
+@pytest.mark.parametrize('name', ['H', 'S', 'P'])
+def test_phase_matches_oracle_and_reference(name):
+    d = np.load(os.path.join(GOLDEN, 'phase_%s.npz' % name))
+    J, Q, T, N, mo = CFG[name]
+    m = module_of(name)
+    x = torch.from_numpy(d['x']).cuda()
+    n_out = d['scattering'].shape[-1]
+    o = PhaseOracle(J, Q, T, N, n_out)
+    subset = bool(d['subset'])
+    sel = m.get_optimal_coefficients_for_fhr(J, Q, T)
+    pm = sel['recommendations']['use_phase_mask'].cpu().numpy()
+    cm = sel['recommendations']['use_cross_mask'].cpu().numpy()
+    assert np.array_equal(pm, d['phase_mask']) and np.array_equal(cm, d['cross_mask'])     # identical masks
+
+    rw = m(x, compute_phase=True, phase_channels=[0], phase_pairs=pm if subset else None)
+    rc = m(x, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1], phase_pairs=cm if subset else None)
+    assert set(rw) == {'scattering', 'phase_corr', 'autoc_idx'}
+    assert set(rc) == {'scattering', 'cross_phase_corr', 'autoc_idx'}
+    assert torch.equal(rw['autoc_idx'].cpu(), torch.from_numpy(d['autoc_idx']))
+    within = rw['phase_corr'].cpu().numpy().astype(np.float64)
+    cross = rc['cross_phase_corr'].cpu().numpy().astype(np.float64)
+    assert within.shape == d['within'].shape and cross.shape == d['cross'].shape
+    # scattering part of the result dict
+    assert rel_l2(rw['scattering'].cpu().numpy(), d['scattering']) < 2e-6
+
+    sub_w = np.nonzero(pm)[0] if subset else None
+    sub_c = np.nonzero(cm)[0] if subset else None
+    xin = d['x']
+    check(within, o.align_branches(xin[:, 0], within, mode='within', pair_subset=sub_w), 'within/oracle')
+    check(cross, o.align_branches(xin, cross, mode='cross', pair_subset=sub_c), 'cross/oracle')
+    # against the live reference's fp32 outputs: both sides carry fp32 noise of p*theta
+    for ours, ref, mode, sub in ((within, d['within'], 'within', sub_w), (cross, d['cross'], 'cross', sub_c)):
+        aligned_to_ref = o.align_branches(xin[:, 0] if mode == 'within' else xin, ref, mode=mode, pair_subset=sub)
+        aligned_to_us = o.align_branches(xin[:, 0] if mode == 'within' else xin, ours, mode=mode, pair_subset=sub)
+        # distance to the reference after removing each side's branch choice
+        diff = (ours - aligned_to_us) - (ref - aligned_to_ref)
+        assert np.linalg.norm(diff) / np.linalg.norm(ref) < 1e-4, mode
+
+
+def test_full_rate_product_and_same_pairs():
+    """cross_phase_low_pass=False (:356-360) and cross_phase_same_pairs_only (:325-328)."""
+    J, Q, T, N, mo = CFG['S']
+    m = module_of('S')
+    d = np.load(os.path.join(GOLDEN, 'phase_S.npz'))
+    x = torch.from_numpy(d['x'][:2]).cuda()
+    o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1])
+    r = m(x, compute_phase=False, compute_cross_phase=True, cross_phase_low_pass=False)
+    full = r['cross_phase_corr'].cpu().numpy().astype(np.float64)
+    ref = o(d['x'][:2], mode='cross', low_pass=False)
+    assert full.shape == ref.shape == (2, len(o.i_idx), N)
+    inner = slice(2, N - 2)                      # the two boundary samples carry the branch ambiguity
+    assert rel_l2(full[..., inner], ref[..., inner]) < 5e-5
+    r2 = m(x, compute_phase=False, compute_cross_phase=True, cross_phase_same_pairs_only=True)
+    same = r2['cross_phase_corr'].cpu().numpy().astype(np.float64)
+    ref2 = o.align_branches(d['x'][:2], same, mode='cross', pair_subset=o.autoc_idx)
+    assert same.shape == ref2.shape
+    check(same, ref2, 'same-pairs')
+
+
+def test_within_autocorrelation_is_nonnegative_and_2d_input():
+    m = module_of('S')
+    x = torch.randn(3, 1000, device='cuda')
+    r = m(x, compute_phase=True)                                     # 2-D input path (:432-439)
+    pc = r['phase_corr']
+    assert pc.shape[0] == 3 and pc.shape[1] == len(m.i_idx)
+    v = m.verify_phase_correlation_properties(x)
+    assert v['passed'], v['details']
+    r3 = m(x.unsqueeze(1), compute_phase=True)                       # the same through the 3-D path
+    assert torch.equal(r3['phase_corr'], pc)
+    none = m(x, compute_phase=False)
+    assert set(none) == {'scattering'}
+
+
+def test_forward_validation_errors():
+    m = module_of('S')
+    x3 = torch.randn(2, 2, 1000, device='cuda')
+    with pytest.raises(ValueError) as e:
+        m(x3, scattering_channel=2)
+    assert 'scattering_channel 2 >= 2' in str(e.value)
+    with pytest.raises(ValueError) as e:
+        m(x3[:, :1], compute_cross_phase=True)
+    assert 'at least 2 channels' in str(e.value)
+    with pytest.raises(ValueError) as e:
+        m(x3, compute_cross_phase=True, phase_channels=[0, 5])
+    assert 'Invalid phase_channels' in str(e.value)
+    with pytest.raises(ValueError) as e:
+        m(x3, phase_channels=[0, 1])
+    assert 'exactly 1 channel' in str(e.value)
+    with pytest.raises(ValueError) as e:
+        m(x3[:, 0], compute_cross_phase=True)
+    assert 'multi-channel input' in str(e.value)
+    with pytest.raises(ValueError) as e:
+        m(x3[:, 0], scattering_channel=1)
+    assert 'must be 0' in str(e.value)
+    with pytest.raises(ValueError) as e:
+        m(torch.randn(1000, device='cuda'))
+    assert 'must be 2D or 3D' in str(e.value)
+
+
+def test_batch_chunking_is_consistent():
+    """More samples than one workspace chunk (96): rows must not depend on their position."""
+    m = module_of('S')
+    base = torch.randn(5, 2, 1000, device='cuda')
+    x = base.repeat(41, 1, 1)                                        # 205 samples
+    out = m(x, compute_phase=False, compute_cross_phase=True)['cross_phase_corr']
+    assert torch.equal(out[:5], out[-5:]) and torch.equal(out[:5], out[100:105])

@@ -1,0 +1,65 @@
+"""CPU checks of the phase path's host logic: pair tables and masks against the golden
+reference fixtures, the smoothing operator against the oracle, and stage A (analytic
+signals) through the host emulator of the step interpreter."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, emu_available, emu_forward
+from oracle.phase_oracle import PhaseOracle
+from tebscat.phase import PhasePlan
+
+CFG = {'H': (6, 8, 64, 4800), 'P': (11, 4, 16, 5760), 'S': (4, 4, 16, 1000)}
+_plans = {}
+
+
+def plan_of(name, n_out_scat):
+    if name not in _plans:
+        J, Q, T, N = CFG[name]
+        _plans[name] = PhasePlan(J, Q, T, N, n_out_scat)
+    return _plans[name]
+
+
+@pytest.mark.parametrize('name', ['H', 'P', 'S'])
+def test_pair_tables_match_reference(name):
+    d = np.load(os.path.join(GOLDEN, 'phase_%s.npz' % name))
+    p = plan_of(name, d['scattering'].shape[-1])
+    assert np.array_equal(p.center_freqs, d['center_freqs'])          # same fp32 values -> same masks
+    assert np.array_equal(p.i_idx, d['i_idx']) and np.array_equal(p.j_idx, d['j_idx'])
+    assert np.array_equal(p.powers, d['powers'])
+    assert np.array_equal(p.autoc_idx, d['autoc_idx'])
+    assert (p.geo.J_pad, p.geo.pad_left, p.geo.pad_right) == (int(d['J_pad']), int(d['pad_left']), int(d['pad_right']))
+    ref_len = d['within'].shape[-1]
+    assert p.n_out == ref_len                                          # e.g. 66 != 63 for the ragged config
+
+
+@pytest.mark.parametrize('name', ['H', 'S'])
+def test_smoothing_operator_matches_oracle(name):
+    d = np.load(os.path.join(GOLDEN, 'phase_%s.npz' % name))
+    J, Q, T, N = CFG[name]
+    p = plan_of(name, d['scattering'].shape[-1])
+    o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1])
+    rng = np.random.RandomState(3)
+    c = rng.randn(4, N) + 1j * rng.randn(4, N)
+    G = p.G[:, :p.n_out, 0].astype(np.float64) + 1j * p.G[:, :p.n_out, 1]
+    ref = o._smooth(c)
+    assert np.abs(c @ G - ref).max() < 1e-6 * np.abs(ref).max()
+    assert np.all(p.G[:, p.n_out:] == 0)
+
+
+@pytest.mark.skipif(not emu_available(), reason='host emulator not built')
+@pytest.mark.parametrize('name', ['H', 'S'])
+def test_stage_a_emulated_matches_oracle(name):
+    d = np.load(os.path.join(GOLDEN, 'phase_%s.npz' % name))
+    J, Q, T, N = CFG[name]
+    p = plan_of(name, d['scattering'].shape[-1])
+    o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1])
+    x = np.random.RandomState(5).randn(2, N).astype(np.float32)
+    z, zp = emu_forward(p.stage_a, x, stage_a=True)
+    ref = o.analytic(x)
+    assert not np.isnan(z).any()
+    err = np.linalg.norm(z - ref, axis=-1) / np.linalg.norm(ref, axis=-1)
+    assert err.max() < 1e-5, err.max()
+    assert np.allclose(zp[..., 0], np.abs(z), rtol=1e-6, atol=1e-9)
+    assert np.allclose(zp[..., 1], np.angle(z), atol=1e-6)

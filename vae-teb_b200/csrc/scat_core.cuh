@@ -53,8 +53,10 @@ enum : int32_t {
     OP_LOAD = 1,     // a=dst                              reflect-padded signal -> (x, 0)
     OP_FFT = 2,      // a=region b=butterflies (all blocks) c=log2B d=log2R e=flags(FFT_INV|FFT_MOD)
     OP_MULFOLD = 3,  // a=src b=log2Lsrc c=log2k d=dst e=filter offset (floats) f=chunk mask; scale 2^-sexp
-    OP_STOREB = 4    // a=pool base b=slots c=first index d=count e=channel-table offset f=log2 slot length
+    OP_STOREB = 4,   // a=pool base b=slots c=first index d=count e=channel-table offset f=log2 slot length
+    OP_STOREZ = 5    // a=src b=row (filter index) c=first index d=count: complex crop -> global (phase stage A)
 };
+enum : int32_t { Z_CART = 1, Z_POLAR = 2 };
 enum : int32_t { FFT_INV = 1, FFT_MOD = 2 };
 constexpr int kTaskInts = 12;
 
@@ -69,6 +71,9 @@ struct SignalCtx {
     const float* x;          // this signal's N input samples
     float* out;              // this signal's [n_paths, n_out] block
     const int32_t* chan;     // channel table of the batched stores
+    float2* zc;              // phase stage A: analytic signals of this job, cartesian [F][N]
+    float2* zp;              // phase stage A: analytic signals of this job, polar (|z|, theta) [F][N]
+    int32_t z_mode;          // Z_CART | Z_POLAR
     int32_t N, pad_left, log2_Np, n_out;
 };
 
@@ -350,6 +355,18 @@ TEB_D void storeb_task(const float2* S, const SignalCtx& c, const Task& t, int l
     }
 }
 
+// Phase stage A (hdf5_dataset/kymatio_phase_scattering.py:220-231): the unpadded analytic
+// signal z = ifft(fft(pad(x)) psi1_f)[pad_left : pad_left + N], stored for the pair stage as
+// (re, im) and/or as (|z|, atan2(im, re)) -- the polar form of _accelerate_phase (:214-215).
+TEB_D void storez_task(const float2* S, const SignalCtx& c, const Task& t, int lt) {
+    const int64_t row = (int64_t)t.b * t.d;
+    for (int i = lt; i < t.d; i += t.nt) {
+        const float2 z = S[swz(t.a + t.c + i)];
+        if (c.z_mode & Z_CART) c.zc[row + i] = z;
+        if (c.z_mode & Z_POLAR) c.zp[row + i] = make_float2(sqrtf(fmaf(z.x, z.x, z.y * z.y)), atan2f(z.y, z.x));
+    }
+}
+
 TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const float* __restrict__ arena,
                      const SignalCtx& c, const Task& t, int lt) {
     switch (t.op & 0xff) {
@@ -364,6 +381,7 @@ TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const floa
             break;
         case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
         case OP_STOREB: storeb_task(S, c, t, lt); break;
+        case OP_STOREZ: storez_task(S, c, t, lt); break;
         default: break;
     }
 }

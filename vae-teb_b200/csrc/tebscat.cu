@@ -46,6 +46,11 @@ struct KParams {
     const int4* warp_tab;    // [n_steps][kWarps] x 3 int4: the task of every warp in every step
     const int32_t* chan;     // channel table of the batched stores
     long long* prof;         // optional: clock64() of CTA 0 at every step boundary (first signal)
+    float2* zc;              // phase stage A outputs (null for the scattering transform)
+    float2* zp;
+    long long x_stride;      // floats between the signals of consecutive jobs
+    long long z_stride;      // float2 between the zc/zp blocks of consecutive jobs
+    int32_t z_mode;
     int32_t n_steps;
     int32_t smem_complex;
     int32_t N, pad_left, log2_Np, n_paths, n_out;
@@ -78,9 +83,12 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
     int s_fetch = 2 % n_steps;
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         SignalCtx c;
-        c.x = x + b * p.N;
+        c.x = x + b * p.x_stride;
         c.out = out + b * (long long)p.n_paths * p.n_out;
         c.chan = p.chan;
+        c.zc = p.zc + b * p.z_stride;
+        c.zp = p.zp + b * p.z_stride;
+        c.z_mode = p.z_mode;
         c.N = p.N;
         c.pad_left = p.pad_left;
         c.log2_Np = p.log2_Np;
@@ -177,6 +185,10 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                     !fits(t[3], (int64_t)t[4] << t[8]) || t[7] < 0 || (size_t)t[7] + (size_t)t[4] > n_chan)
                     return fail(TEBSCAT_EINVAL, "task %d: bad STOREB", i);
                 break;
+            case OP_STOREZ:
+                if (t[4] < 0 || t[4] >= d.n_paths || t[6] != d.n_out || t[5] < 0 || !fits(t[3], (int64_t)t[5] + t[6]))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad STOREZ", i);
+                break;
             case OP_NOP:
                 break;
             default:
@@ -260,6 +272,11 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     k.warp_tab = reinterpret_cast<const int4*>(p->d_warp_tab);
     k.chan = p->d_chan;
     k.prof = nullptr;
+    k.zc = nullptr;
+    k.zp = nullptr;
+    k.x_stride = desc->N;
+    k.z_stride = 0;
+    k.z_mode = 0;
     k.n_steps = desc->n_steps;
     k.smem_complex = desc->smem_complex;
     k.N = desc->N;
@@ -361,5 +378,298 @@ extern "C" int tebscat_scat1d_forward_host(tebscat_plan* p, const float* x_host,
     }
     CU(cudaStreamSynchronize(hp.stream[0]));
     CU(cudaStreamSynchronize(hp.stream[1]));
+    return TEBSCAT_OK;
+}
+
+// =================================================================================
+// Phase-harmonic correlation (hdf5_dataset/kymatio_phase_scattering.py:211-360)
+// =================================================================================
+//
+// Stage A (per sample and channel) runs on the step interpreter above with a schedule whose
+// leaves are STOREZ tasks: z_f = ifft(fft(pad(x)) psi1_f)[pad_left : pad_left+N] for every
+// first-order filter f, written to an L2-resident workspace as (re, im) for the 'j' channel
+// and as (|z|, theta) for the 'i' channel.
+//
+// Stage B is one kernel.  For every (sample, pair (i, j)) it forms the phase-accelerated
+// product  c(t) = |z_i| exp(i p theta_i) conj(z_j)  (:211-218, :283 / :339) on the fly and
+// contracts it with the precomputed operator of _apply_phi_filter (:233-273)
+//     out[n] = Re sum_t c(t) G[t, n],
+// G = reflect-pad -> FFT(Np) -> phi -> keep bins [0, Np/dec) -> iFFT(Np/dec) -> slice,
+// built once on the host in float64.  The contraction is a register-tiled FP32 GEMM
+// (128 (sample, pair) rows x 80 output samples per CTA, K = time in slabs of 16); rows never
+// materialise in memory -- the reference materialises (B, P, N) complex64 three times.
+
+constexpr int kPR = 128;        // rows per CTA
+constexpr int kPC = 80;         // output columns per CTA
+constexpr int kPK = 16;         // time samples per slab
+constexpr int kPThreads = 256;
+
+struct PairParams {
+    const float2* zp;           // [Bc][F][N] (|z|, theta) of the 'i' channel
+    const float2* zc;           // [Bc][F][N] (re, im)     of the 'j' channel
+    const float2* G;            // [N][n_cols_pad] (re, im) of the smoothing operator
+    const int32_t* i_idx;
+    const int32_t* j_idx;
+    const float* powers;
+    const int32_t* subset;      // selected pairs or null
+    float* out;                 // [rows][n_out]
+    long long rows;             // Bc * n_sel
+    int32_t n_sel, F, N, n_out, n_cols_pad;
+};
+
+__device__ __forceinline__ float2 accelerated_product(float2 pz, float2 zj, float power) {
+    // theta * p in fp32 like the reference (:215), then an exact-enough reduction to [-pi, pi]
+    const float ph = pz.y * power;
+    const float k = rintf(ph * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, ph);
+    r = fmaf(-k, -1.7484555314695172e-7f, r);
+    float sn, cs;
+    __sincosf(r, &sn, &cs);
+    const float ar = pz.x * cs, ai = pz.x * sn;
+    // (ar + i ai) * conj(zj)
+    return make_float2(fmaf(ar, zj.x, ai * zj.y), fmaf(ai, zj.x, -ar * zj.y));
+}
+
+__global__ void __launch_bounds__(kPThreads, 2) phase_pair_kernel(const PairParams p) {
+    __shared__ __align__(16) float2 sA[kPK][kPR + 2];
+    __shared__ __align__(16) float2 sG[kPK][kPC];
+    __shared__ int32_t s_zp[kPR], s_zc[kPR];
+    __shared__ float s_pw[kPR];
+
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * kPR;
+    const int col0 = blockIdx.y * kPC;
+    if (tid < kPR) {
+        const long long r = row0 + tid;
+        int zp_off = -1, zc_off = -1;
+        float pw = 1.f;
+        if (r < p.rows) {
+            const int b = (int)(r / p.n_sel), s = (int)(r - (long long)b * p.n_sel);
+            const int pair = p.subset ? p.subset[s] : s;
+            zp_off = (b * p.F + p.i_idx[pair]) * p.N;
+            zc_off = (b * p.F + p.j_idx[pair]) * p.N;
+            pw = p.powers[pair];
+        }
+        s_zp[tid] = zp_off;
+        s_zc[tid] = zc_off;
+        s_pw[tid] = pw;
+    }
+    __syncthreads();
+
+    const int cg = tid & 15, rg = tid >> 4;
+    float acc[8][5];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) acc[r][c] = 0.f;
+
+    for (int t0 = 0; t0 < p.N; t0 += kPK) {
+        // A slab: 128 rows x 16 samples, 8 per thread, 16 consecutive samples of a row per half-warp
+#pragma unroll
+        for (int pass = 0; pass < kPR * kPK / kPThreads; ++pass) {
+            const int e = tid + pass * kPThreads;
+            const int tl = e & (kPK - 1), row = e >> 4;
+            const int t = t0 + tl;
+            float2 a = make_float2(0.f, 0.f);
+            const int zo = s_zp[row];
+            if (zo >= 0 && t < p.N) {
+                const float2 c = accelerated_product(__ldg(p.zp + zo + t), __ldg(p.zc + s_zc[row] + t), s_pw[row]);
+                a = make_float2(c.x, -c.y);             // Re(c G) = c.x G.x - c.y G.y
+            }
+            sA[tl][row] = a;
+        }
+#pragma unroll
+        for (int pass = 0; pass < kPK * kPC / kPThreads; ++pass) {
+            const int e = tid + pass * kPThreads;
+            const int tl = e / kPC, col = e - tl * kPC;
+            const int t = t0 + tl;
+            sG[tl][col] = (t < p.N) ? __ldg(p.G + (long long)t * p.n_cols_pad + col0 + col) : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int tl = 0; tl < kPK; ++tl) {
+            float2 a[8], g[5];
+            const float4* ap = reinterpret_cast<const float4*>(&sA[tl][rg * 8]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 v = ap[r];
+                a[2 * r] = make_float2(v.x, v.y);
+                a[2 * r + 1] = make_float2(v.z, v.w);
+            }
+#pragma unroll
+            for (int c = 0; c < 5; ++c) g[c] = sG[tl][cg + 16 * c];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) acc[r][c] = fmaf(a[r].x, g[c].x, fmaf(a[r].y, g[c].y, acc[r][c]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const long long row = row0 + rg * 8 + r;
+        if (row >= p.rows) continue;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const int col = col0 + cg + 16 * c;
+            if (col < p.n_out) p.out[row * p.n_out + col] = acc[r][c];
+        }
+    }
+}
+
+// cross_phase_low_pass=False (:356-360): the full-rate real part of the product
+__global__ void phase_product_kernel(const PairParams p) {
+    const long long total = p.rows * p.N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / p.N;
+        const int t = (int)(e - r * p.N);
+        const int b = (int)(r / p.n_sel), s = (int)(r - (long long)b * p.n_sel);
+        const int pair = p.subset ? p.subset[s] : s;
+        const float2 c = accelerated_product(__ldg(p.zp + (long long)(b * p.F + p.i_idx[pair]) * p.N + t),
+                                             __ldg(p.zc + (long long)(b * p.F + p.j_idx[pair]) * p.N + t), p.powers[pair]);
+        p.out[e] = c.x;
+    }
+}
+
+struct tebscat_phase_plan {
+    tebscat_phase_desc desc;
+    tebscat_plan* stage_a = nullptr;
+    int device = 0;
+    float2* d_G = nullptr;
+    int32_t* d_i = nullptr;
+    int32_t* d_j = nullptr;
+    float* d_pw = nullptr;
+    int32_t* d_subset = nullptr;
+    float2* d_zc = nullptr;
+    float2* d_zp = nullptr;
+    int64_t ws_samples = 0;
+    std::mutex mu;
+};
+
+extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_plan* stage_a, const float* G_host,
+                                         const int32_t* i_idx, const int32_t* j_idx, const float* powers,
+                                         tebscat_phase_plan** out) {
+    if (!d || !stage_a || !G_host || !i_idx || !j_idx || !powers || !out) return fail(TEBSCAT_EINVAL, "null argument");
+    if (d->abi_version != TEBSCAT_ABI_VERSION) return fail(TEBSCAT_EINVAL, "ABI version mismatch");
+    if (d->N != stage_a->desc.N || d->n_filters != stage_a->desc.n_paths || stage_a->desc.n_out != d->N)
+        return fail(TEBSCAT_EINVAL, "stage-A plan does not match the phase description");
+    if (d->n_pairs < 1 || d->n_out < 1 || d->n_cols_pad < d->n_out || d->n_cols_pad % kPC != 0)
+        return fail(TEBSCAT_EINVAL, "bad phase description");
+    for (int k = 0; k < d->n_pairs; ++k)
+        if (i_idx[k] < 0 || i_idx[k] >= d->n_filters || j_idx[k] < 0 || j_idx[k] >= d->n_filters)
+            return fail(TEBSCAT_EINVAL, "pair %d references a filter outside [0,%d)", k, d->n_filters);
+    CU(cudaSetDevice(stage_a->device));
+    tebscat_phase_plan* p = new tebscat_phase_plan();
+    p->desc = *d;
+    p->stage_a = stage_a;
+    p->device = stage_a->device;
+    const size_t g_elems = (size_t)d->N * d->n_cols_pad;
+    CU(cudaMalloc(&p->d_G, g_elems * sizeof(float2)));
+    CU(cudaMemcpy(p->d_G, G_host, g_elems * sizeof(float2), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&p->d_i, d->n_pairs * sizeof(int32_t)));
+    CU(cudaMalloc(&p->d_j, d->n_pairs * sizeof(int32_t)));
+    CU(cudaMalloc(&p->d_pw, d->n_pairs * sizeof(float)));
+    CU(cudaMalloc(&p->d_subset, d->n_pairs * sizeof(int32_t)));
+    CU(cudaMemcpy(p->d_i, i_idx, d->n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_j, j_idx, d->n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_pw, powers, d->n_pairs * sizeof(float), cudaMemcpyHostToDevice));
+    *out = p;
+    return TEBSCAT_OK;
+}
+
+extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_G);
+    cudaFree(p->d_i);
+    cudaFree(p->d_j);
+    cudaFree(p->d_pw);
+    cudaFree(p->d_subset);
+    cudaFree(p->d_zc);
+    cudaFree(p->d_zp);
+    tebscat_plan_destroy(p->stage_a);
+    delete p;
+}
+
+static int launch_stage_a(const tebscat_plan* a, const float* x, long long x_stride, int64_t jobs,
+                          float2* zc, float2* zp, int z_mode, cudaStream_t st) {
+    KParams kp = a->kp;
+    kp.x_stride = x_stride;
+    kp.zc = zc;
+    kp.zp = zp;
+    kp.z_stride = (long long)a->desc.n_paths * a->desc.N;
+    kp.z_mode = z_mode;
+    const int grid = (int)(jobs < (int64_t)a->n_sms ? jobs : (int64_t)a->n_sms);
+    scat1d_kernel<<<grid, a->desc.n_threads, a->smem_bytes, st>>>(kp, x, nullptr, (long long)jobs);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, int64_t B, int n_channels,
+                                     int ch_i, int ch_j, const int32_t* pair_subset_host, int n_subset,
+                                     int apply_low_pass, float* out_dev, void* stream) {
+    g_launches = 0;
+    if (!p || B < 0 || (B > 0 && (!x_dev || !out_dev))) return fail(TEBSCAT_EINVAL, "null argument");
+    if (n_channels < 1 || ch_i < 0 || ch_i >= n_channels || ch_j < 0 || ch_j >= n_channels)
+        return fail(TEBSCAT_EINVAL, "channel index outside [0,%d)", n_channels);
+    if (pair_subset_host && (n_subset < 1 || n_subset > p->desc.n_pairs)) return fail(TEBSCAT_EINVAL, "bad pair subset size");
+    if (pair_subset_host)
+        for (int k = 0; k < n_subset; ++k)
+            if (pair_subset_host[k] < 0 || pair_subset_host[k] >= p->desc.n_pairs)
+                return fail(TEBSCAT_EINVAL, "pair subset entry %d outside [0,%d)", k, p->desc.n_pairs);
+    if (B == 0) return TEBSCAT_OK;
+    std::lock_guard<std::mutex> lock(p->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(p->device));
+    const tebscat_phase_desc& d = p->desc;
+    const int n_sel = pair_subset_host ? n_subset : d.n_pairs;
+    const size_t per_sample = (size_t)d.n_filters * d.N;
+    const int64_t chunk = B < 96 ? B : 96;                 // 96 samples of workspace: L2-sized at N=4800, F=38
+    if (p->ws_samples < chunk) {
+        CU(cudaStreamSynchronize(st));
+        cudaFree(p->d_zc);
+        cudaFree(p->d_zp);
+        p->d_zc = p->d_zp = nullptr;
+        CU(cudaMalloc(&p->d_zc, (size_t)chunk * per_sample * sizeof(float2)));
+        CU(cudaMalloc(&p->d_zp, (size_t)chunk * per_sample * sizeof(float2)));
+        p->ws_samples = chunk;
+    }
+    if (pair_subset_host) CU(cudaMemcpyAsync(p->d_subset, pair_subset_host, n_sel * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const long long x_stride = (long long)n_channels * d.N;
+    const size_t out_per_sample = (size_t)n_sel * (apply_low_pass ? d.n_out : d.N);
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        const float* xb = x_dev + b0 * x_stride;
+        if (ch_i == ch_j) {
+            if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_i * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_CART | Z_POLAR, st)) return rc;
+        } else {
+            if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_i * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_POLAR, st)) return rc;
+            if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_j * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_CART, st)) return rc;
+        }
+        PairParams pp;
+        pp.zp = p->d_zp;
+        pp.zc = p->d_zc;
+        pp.G = p->d_G;
+        pp.i_idx = p->d_i;
+        pp.j_idx = p->d_j;
+        pp.powers = p->d_pw;
+        pp.subset = pair_subset_host ? p->d_subset : nullptr;
+        pp.out = out_dev + (size_t)b0 * out_per_sample;
+        pp.rows = (long long)nb * n_sel;
+        pp.n_sel = n_sel;
+        pp.F = d.n_filters;
+        pp.N = d.N;
+        pp.n_out = d.n_out;
+        pp.n_cols_pad = d.n_cols_pad;
+        if (apply_low_pass) {
+            dim3 grid((unsigned)((pp.rows + kPR - 1) / kPR), (unsigned)(d.n_cols_pad / kPC));
+            phase_pair_kernel<<<grid, kPThreads, 0, st>>>(pp);
+        } else {
+            phase_product_kernel<<<1184, 256, 0, st>>>(pp);
+        }
+        CU(cudaGetLastError());
+        ++g_launches;
+    }
     return TEBSCAT_OK;
 }

@@ -4,6 +4,7 @@
     from tebscat import KymatioPhaseScattering1D      # hdf5_dataset/kymatio_phase_scattering.py surface
 """
 from .torch_frontend import Scattering1D, ScatteringTorch1D
+from .phase import KymatioPhaseScattering1D
 
-__all__ = ['Scattering1D', 'ScatteringTorch1D']
+__all__ = ['Scattering1D', 'ScatteringTorch1D', 'KymatioPhaseScattering1D']
 __version__ = '0.1.0'

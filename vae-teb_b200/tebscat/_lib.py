@@ -23,10 +23,9 @@ class PlanDesc(ctypes.Structure):
 
 
 class PhaseDesc(ctypes.Structure):
-    _fields_ = [('abi_version', ctypes.c_int32), ('N', ctypes.c_int32), ('log2_Np', ctypes.c_int32),
-                ('pad_left', ctypes.c_int32), ('n_filters', ctypes.c_int32), ('n_pairs', ctypes.c_int32),
-                ('dec', ctypes.c_int32), ('n_bins', ctypes.c_int32), ('out_start', ctypes.c_int32),
-                ('n_out', ctypes.c_int32), ('reserved', ctypes.c_int32 * 6)]
+    _fields_ = [('abi_version', ctypes.c_int32), ('N', ctypes.c_int32), ('n_filters', ctypes.c_int32),
+                ('n_pairs', ctypes.c_int32), ('n_out', ctypes.c_int32), ('n_cols_pad', ctypes.c_int32),
+                ('reserved', ctypes.c_int32 * 10)]
 
 
 _lib = None
@@ -60,6 +59,13 @@ def load():
     lib.tebscat_scat1d_forward.argtypes = [vp, vp, ctypes.c_int64, vp, vp]
     lib.tebscat_scat1d_forward_host.restype = ctypes.c_int
     lib.tebscat_scat1d_forward_host.argtypes = [vp, vp, ctypes.c_int64, vp]
+    lib.tebscat_phase_plan_create.restype = ctypes.c_int
+    lib.tebscat_phase_plan_create.argtypes = [ctypes.POINTER(PhaseDesc), vp, fp, i32p, i32p, fp, ctypes.POINTER(vp)]
+    lib.tebscat_phase_plan_destroy.restype = None
+    lib.tebscat_phase_plan_destroy.argtypes = [vp]
+    lib.tebscat_phase_forward.restype = ctypes.c_int
+    lib.tebscat_phase_forward.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, i32p,
+                                          ctypes.c_int, ctypes.c_int, vp, vp]
     lib.tebscat_scat1d_profile_steps.restype = ctypes.c_int
     lib.tebscat_scat1d_profile_steps.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp]
     lib.tebscat_bench_fp32_peak.restype = ctypes.c_int

@@ -35,7 +35,7 @@ import numpy as np
 
 from . import filterbank as fbk
 
-OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB = 0, 1, 2, 3, 4
+OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ = 0, 1, 2, 3, 4, 5
 FFT_INV, FFT_MOD = 1, 2
 TASK_INTS = 12
 
@@ -480,10 +480,12 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
 
     alloc = _Allocator(capacity)
     pool = _LeafPool(lf, i0, n_out)
-    for b in pool.bufs:
-        b.off = alloc.alloc(b.size)
-        assert b.off >= 0
-    free_slots = capacity - sum(_round16(b.size) for b in pool.bufs)
+    has_leaves = any(t.d is LEAF for c in chains for st in c.stages for t in st)
+    if has_leaves:
+        for b in pool.bufs:
+            b.off = alloc.alloc(b.size)
+            assert b.off >= 0
+    free_slots = capacity - (sum(_round16(b.size) for b in pool.bufs) if has_leaves else 0)
     reserve_left: Dict[int, int] = {}
     pending = list(chains)
     active: List[Chain] = []
@@ -657,6 +659,11 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
     return steps, alloc.high_water, pool.chan_table, sched_stats
 
 
+def smem_capacity() -> int:
+    """Logical complex slots a schedule may address (the kernel pads one slot per 16)."""
+    return ((SMEM_BYTES_MAX // 8 - TW_SLOTS) * 16 // 17) & ~15
+
+
 def emit(steps) -> Tuple[np.ndarray, np.ndarray]:
     rows, ranges = [], []
     for st in steps:
@@ -676,8 +683,7 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     bank = fbk.build_filter_bank(geo.J_pad, J, Q1, T)
     arena = _Arena()
     chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena)
-    # logical slots; the kernel pads one slot per 16 (scat_core.cuh: swz)
-    capacity = ((SMEM_BYTES_MAX // 8 - TW_SLOTS) * 16 // 17) & ~15
+    capacity = smem_capacity()
     steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel)
     tasks, ranges = emit(steps)
     n_tasks = tasks.shape[0]
