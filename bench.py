@@ -126,6 +126,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from tebscat import Scattering1D, _lib
     from tebscat.synth import ctg_batch
+    from tebscat.sharding import max_over_ranks
     import ctypes
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -170,10 +171,7 @@ def run_gpu(args):
     sampler.join()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = max_over_ranks(total_ms, dev)
     value = world * n_sig * args.steps / (total_ms_max * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI entry point -------------------------
@@ -185,10 +183,28 @@ def run_gpu(args):
         S.scattering_host(x_host, out=out_host, device=local)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_sig * args.steps / float(t.item())
+    e2e_value = world * n_sig * args.steps / max_over_ranks(e2e_s, dev)
+
+    # ---- secondary: cross-channel phase scattering (BASELINE configs[2]) on a bounded batch ----
+    phase = None
+    if rank == 0 and not args.no_phase:
+        from tebscat import KymatioPhaseScattering1D
+        pm = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=dev)
+        xb = x_dev[:512]
+        pm(xb, compute_phase=False, compute_cross_phase=True)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(3):
+            pm(xb, compute_phase=False, compute_cross_phase=True)
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / 3
+        phase = {'metric': 'cross-channel phase scattering FHR x UP pairs/s (J=6,Q=8,N=4800, 741 pairs)',
+                 'value': 512 / (pms * 1e-3), 'unit': 'signal-pairs/s', 'batch': 512, 'ms': pms,
+                 'achieved_fp32_tflops': 512 * 2 * 741 * 4800 * 80 * 2 / (pms * 1e-3) / 1e12,
+                 'note': 'includes the scattering transform of the FHR channel and stage A of both channels'}
+        del pm
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
@@ -221,6 +237,7 @@ def run_gpu(args):
                                   'peak_source': 'FMA microbenchmark in this run (tebscat_bench_fp32_peak)'}},
             'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': '512 CTG signals, %.1f s, numpy/scipy complex64 port (oracle/)' % cpu_dt},
+            'phase': phase,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -233,6 +250,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='tebscat', choices=['tebscat', 'reference'])
+    ap.add_argument('--no-phase', action='store_true', help='skip the secondary phase-scattering measurement')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'tebscat' else args.warmup
     if args.impl == 'reference':
