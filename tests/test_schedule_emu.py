@@ -25,7 +25,7 @@ def test_bitrev_and_radix_split():
     assert list(bitrev_indices(8)) == [0, 4, 2, 6, 1, 5, 3, 7]
     for n in range(1, 14):
         s = radix_split(n)
-        assert sum(s) == n and max(s) <= 4 and len(s) == -(-n // 4)
+        assert sum(s) == n and max(s) <= 4 and len(s) == -(-n // 4) and all(r == 4 for r in s[:-1])
 
 
 def _touched(t, np_len):

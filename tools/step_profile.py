@@ -15,7 +15,7 @@ import torch                                    # noqa: E402
 from tebscat import Scattering1D, _lib          # noqa: E402
 from tebscat.synth import ctg_batch             # noqa: E402
 
-CFG = {'H': (6, 4800, 8, 64, 2), 'P': (11, 5760, 4, 16, 1)}
+CFG = {'H': (6, 4800, 8, 64, 2), 'P': (11, 5760, 4, 16, 1), 'K': (6, 512, 16, 64, 2), 'T': (5, 700, 2, 8, 2)}
 name = sys.argv[1] if len(sys.argv) > 1 else 'H'
 J, N, Q, T, mo = CFG[name]
 S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()

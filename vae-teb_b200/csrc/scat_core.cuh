@@ -248,10 +248,42 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
     }
 }
 
+// Unit-stride pass of a small radix (the remainder pass: last DIF / first DIT pass, no
+// twiddles): every thread takes 16 contiguous slots per trip -- 16/R butterflies whose loads
+// are all in flight together -- instead of one tiny butterfly per trip.
+template <int LOGR, bool INV>
+TEB_D void fft_unit_stride_task(float2* S, const Task& t, int lt) {
+    constexpr int R = 1 << LOGR;
+    const int n_groups = (t.b << LOGR) >> 4;                 // groups of 16 slots
+    for (int gidx = lt; gidx < n_groups; gidx += t.nt) {
+        const int q0 = swz(t.a + (gidx << 4));               // 16 slots of one group: contiguous
+        float2 v[16];
+        TEB_UNROLL for (int j = 0; j < 16; ++j) v[j] = S[q0 + j];
+        TEB_UNROLL for (int b = 0; b < 16 / R; ++b) {
+            float2 w[R];
+            if (!INV) {
+                TEB_UNROLL for (int j = 0; j < R; ++j) w[j] = v[b * R + j];
+                Dft<R, -1>::run(w);
+                TEB_UNROLL for (int r = 0; r < R; ++r) v[b * R + brev<LOGR>(qmap<R>(r))] = w[r];
+            } else {
+                TEB_UNROLL for (int q = 0; q < R; ++q) w[q] = v[b * R + brev<LOGR>(q)];
+                Dft<R, +1>::run(w);
+                TEB_UNROLL for (int r = 0; r < R; ++r) v[b * R + qmap<R>(r)] = w[r];
+            }
+        }
+        TEB_UNROLL for (int j = 0; j < 16; ++j) S[q0 + j] = v[j];
+    }
+}
+
 template <int LOGR>
 TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task& t, int lt) {
     const int n_bfly = t.b;
     const bool inv = (t.e & FFT_INV) != 0, mod = (t.e & FFT_MOD) != 0;
+    if (LOGR <= 2 && t.c == LOGR && !mod && (((n_bfly << LOGR) & 15) == 0)) {
+        if (!inv) fft_unit_stride_task<LOGR, false>(S, t, lt);
+        else fft_unit_stride_task<LOGR, true>(S, t, lt);
+        return;
+    }
     if (!inv) {
         for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, t.c, u);
     } else if (!mod) {

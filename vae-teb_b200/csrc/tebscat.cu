@@ -64,6 +64,15 @@ constexpr int kWarps = kThreads / 32;
 // LANE (lane l keeps field l), so the two records prefetched ahead of the executing one
 // cost two registers, and the fields are broadcast with shuffles when the step starts.
 // Descriptor latency (an L2 hit) therefore never sits between two barriers.
+__device__ __forceinline__ int fetch_field(const int32_t* p) {
+    // volatile: the prefetch must be ISSUED here, two steps ahead of its use; as a plain load
+    // the compiler sinks it to the consumer behind the barrier and the L2 latency is exposed
+    int v;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ out, long long B) {
     extern __shared__ __align__(16) float2 smem[];
@@ -78,8 +87,8 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
     const int32_t* tab = reinterpret_cast<const int32_t*>(p.warp_tab) + kTaskInts * warp + (lane < kTaskInts ? lane : 0);
     const int stride = kTaskInts * kWarps;
     const int n_steps = p.n_steps;
-    int cur = __ldg(tab);
-    int nxt = __ldg(tab + stride * (1 % n_steps));
+    int cur = fetch_field(tab);
+    int nxt = fetch_field(tab + stride * (1 % n_steps));
     int s_fetch = 2 % n_steps;
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         SignalCtx c;
@@ -93,9 +102,9 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
         c.pad_left = p.pad_left;
         c.log2_Np = p.log2_Np;
         c.n_out = p.n_out;
-        const bool prof = p.prof != nullptr && blockIdx.x == 0 && b == blockIdx.x && tid == 0;
+        const bool prof = PROF && blockIdx.x == 0 && b == blockIdx.x && tid == 0;
         for (int s = 0; s < n_steps; ++s) {
-            const int fut = __ldg(tab + stride * s_fetch);             // wraps into the next signal
+            const int fut = fetch_field(tab + stride * s_fetch);       // wraps into the next signal
             s_fetch = (s_fetch + 1 == n_steps) ? 0 : s_fetch + 1;
             if (prof) p.prof[s] = clock64();
             const int op = __shfl_sync(0xffffffffu, cur, 0);
@@ -263,7 +272,9 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     CU(cudaMemcpy(p->d_arena, arena, n_floats * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     // the attribute belongs to the kernel, not to the plan: always allow the device maximum
-    CU(cudaFuncSetAttribute(scat1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(scat1d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)prop.sharedMemPerBlockOptin));
+    CU(cudaFuncSetAttribute(scat1d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)prop.sharedMemPerBlockOptin));
 
     KParams& k = p->kp;
@@ -309,7 +320,7 @@ extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
 static int launch_scat1d(const tebscat_plan* p, const float* x, int64_t B, float* S, cudaStream_t st) {
     if (B == 0) return TEBSCAT_OK;
     const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
-    scat1d_kernel<<<grid, p->desc.n_threads, p->smem_bytes, st>>>(p->kp, x, S, (long long)B);
+    scat1d_kernel<false><<<grid, p->desc.n_threads, p->smem_bytes, st>>>(p->kp, x, S, (long long)B);
     CU(cudaGetLastError());
     ++g_launches;
     return TEBSCAT_OK;
@@ -339,7 +350,7 @@ extern "C" int tebscat_scat1d_profile_steps(const tebscat_plan* p, const float* 
     KParams kp = p->kp;
     kp.prof = d_prof;
     const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
-    scat1d_kernel<<<grid, p->desc.n_threads, p->smem_bytes, (cudaStream_t)stream>>>(kp, x_dev, S_dev, (long long)B);
+    scat1d_kernel<true><<<grid, p->desc.n_threads, p->smem_bytes, (cudaStream_t)stream>>>(kp, x_dev, S_dev, (long long)B);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaMemcpy(step_clocks_host, d_prof, n * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -600,7 +611,7 @@ static int launch_stage_a(const tebscat_plan* a, const float* x, long long x_str
     kp.z_stride = (long long)a->desc.n_paths * a->desc.N;
     kp.z_mode = z_mode;
     const int grid = (int)(jobs < (int64_t)a->n_sms ? jobs : (int64_t)a->n_sms);
-    scat1d_kernel<<<grid, a->desc.n_threads, a->smem_bytes, st>>>(kp, x, nullptr, (long long)jobs);
+    scat1d_kernel<false><<<grid, a->desc.n_threads, a->smem_bytes, st>>>(kp, x, nullptr, (long long)jobs);
     CU(cudaGetLastError());
     ++g_launches;
     return TEBSCAT_OK;

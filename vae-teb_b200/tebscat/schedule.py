@@ -59,12 +59,13 @@ def bitrev_indices(n: int) -> np.ndarray:
 
 
 def radix_split(n: int) -> List[int]:
-    """Split log2(L)=n into the fewest passes of log2-radix <= 4, as evenly as possible."""
+    """Passes of a length-2^n forward (DIF) transform as log2-radices: radix 16 as often as
+    possible, the remainder LAST -- the last DIF pass (first DIT pass: inverse transforms use
+    the reversed list) has unit stride and needs no twiddles, so it is the cheapest place
+    for a small radix."""
     if n <= 0:
         return []
-    m = -(-n // 4)
-    base, extra = divmod(n, m)
-    return [base + 1] * extra + [base] * (m - extra)
+    return [4] * (n // 4) + ([n % 4] if n % 4 else [])
 
 
 def _round16(n: int) -> int:
@@ -120,18 +121,30 @@ class Chain:
     priority: float = 0.0
 
 
-_FFT_LAT = {1: 450.0, 2: 800.0, 3: 1400.0, 4: 2400.0}
-_FFT_INSTR = {1: 60.0, 2: 120.0, 3: 260.0, 4: 520.0}
+# Cost model calibrated on B200 with tools/step_floor.py / tools/step_profile.py:
+# a step lasts  STEP_OVERHEAD + max_t(lat_t) + sum_t warps_t/4 * trips_t * instr_t  cycles, where lat is
+# the dependent-issue latency of one work item on an idle SM and instr the issue cycles one
+# more warp per scheduler adds (one R16 butterfly alone: 1850 cycles; 4 warps/scheduler: 3330).
+_FFT_LAT = {1: 350.0, 2: 500.0, 3: 800.0, 4: 1400.0}
+_FFT_INSTR = {1: 40.0, 2: 110.0, 3: 250.0, 4: 480.0}
+STEP_OVERHEAD = 450.0
 
 
 def _fft_stages(ref, n: int, count: int, inverse: bool, modulus: bool = False) -> List[List[TaskSpec]]:
     """Passes of `count` in-place length-2^n transforms stored back to back at `ref`."""
     out = []
+
+    def task(r, logB, flags):
+        bfly = count << (n - r)
+        if r <= 2 and logB == r and not (flags & FFT_MOD) and ((count << n) & 15) == 0:
+            # unit-stride remainder pass: the kernel takes 16 slots per thread and trip
+            return TaskSpec(OP_FFT, (count << n) >> 4, 500.0, 300.0, a=ref, b=bfly, c=logB, d=r, e=flags)
+        return TaskSpec(OP_FFT, bfly, _FFT_LAT[r], _FFT_INSTR[r], a=ref, b=bfly, c=logB, d=r, e=flags)
+
     if not inverse:
         logB = n
         for r in radix_split(n):
-            out.append([TaskSpec(OP_FFT, count << (n - r), _FFT_LAT[r], _FFT_INSTR[r], a=ref,
-                                 b=count << (n - r), c=logB, d=r, e=0)])
+            out.append([task(r, logB, 0)])
             logB -= r
     else:
         logB = 0
@@ -139,8 +152,7 @@ def _fft_stages(ref, n: int, count: int, inverse: bool, modulus: bool = False) -
         for i, r in enumerate(split):
             logB += r
             flags = FFT_INV | (FFT_MOD if (modulus and i == len(split) - 1) else 0)
-            out.append([TaskSpec(OP_FFT, count << (n - r), _FFT_LAT[r], _FFT_INSTR[r], a=ref,
-                                 b=count << (n - r), c=logB, d=r, e=flags)])
+            out.append([task(r, logB, flags)])
     return out
 
 
@@ -185,10 +197,11 @@ def _mulfold(arena: _Arena, src, log_src: int, logk: int, dst, filt_off: int, ch
     if logk >= 2:
         mask = arena.chunk_mask(filt_off, logk)
         nch = bin(mask).count('1')
-        work, lat, instr = 1 << log_dst, 350.0 + 40.0 * nch, 12.0 + 22.0 * nch
+        # the kernel takes four outputs per thread and trip
+        work, lat, instr = -(-(1 << log_dst) // 4), 900.0 + 150.0 * nch, 250.0 + 200.0 * nch
     else:
         mask = 0
-        work, lat, instr = 1 << (log_src - 2), 420.0, 40.0
+        work, lat, instr = 1 << (log_src - 2), 700.0, 120.0
     # mean over k blocks (2^-logk) and the 1/L of the following inverse transform (2^-log_dst)
     return TaskSpec(OP_MULFOLD, work, lat, instr, a=src, b=log_src, c=logk, d=dst, e=filt_off, f=mask,
                     sexp=logk + log_dst, channel=channel)
@@ -352,40 +365,38 @@ def _want_threads(work: int) -> int:
 
 
 def _step_time(items: List[Tuple[TaskSpec, int]]) -> float:
-    """Cost model of one step: the slowest thread, or the issue slots of the 4 schedulers."""
+    """Cost model of one step (cycles): fixed overhead + the longest dependent latency + the
+    issue cycles all warps of the step add on the four schedulers."""
     lat = 0.0
     issue = 0.0
     for t, nt in items:
-        iters = math.ceil(t.work / nt)
-        lat = max(lat, iters * t.lat)
-        issue += (nt // 32) * iters * t.instr
-    return max(lat, issue / (4 * 0.75)) + 250.0
+        trips = math.ceil(t.work / nt)
+        lat = max(lat, t.lat + (trips - 1) * t.instr)
+        issue += (nt / 128.0) * trips * t.instr
+    return STEP_OVERHEAD + lat + issue
 
 
 def _split_threads(tasks: List[TaskSpec]) -> Optional[List[int]]:
-    """Thread counts (multiples of 32, sum <= 512) that minimise the slowest task."""
+    """Thread counts (multiples of 32, sum <= 512) for the tasks of one step: start from one
+    warp each and keep giving warps to the task with the most trips left."""
     n = len(tasks)
     if 32 * n > N_THREADS:
         return None
     nts = [32] * n
     left = N_THREADS - 32 * n
     while left > 0:
-        times = [math.ceil(t.work / nt) * t.lat for t, nt in zip(tasks, nts)]
+        times = [(math.ceil(t.work / nt) - 1) * t.instr + t.lat for t, nt in zip(tasks, nts)]
         order = sorted(range(n), key=lambda i: -times[i])
         grew = False
         for i in order:
             want = _want_threads(tasks[i].work)
             if nts[i] >= want:
-                if i == order[0]:
-                    break                                # the slowest task cannot go faster
                 continue
             it = math.ceil(tasks[i].work / nts[i])
             need = nts[i] + 32
             while need < want and math.ceil(tasks[i].work / need) >= it:
                 need += 32
             if need - nts[i] > left:
-                if i == order[0]:
-                    break
                 continue
             left -= need - nts[i]
             nts[i] = need
@@ -443,7 +454,7 @@ class _LeafPool:
 
 
 def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out: int,
-                    max_parallel: int = 64, stretch: float = 1.10):
+                    max_parallel: int = 64, pack_gain: float = 0.97):
     """Greedy list scheduling of chains into steps (see module docstring)."""
     children: Dict[int, List[Chain]] = {}
     for ch in chains:
@@ -607,7 +618,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
                 break
             tt = _step_time(list(zip([k[2] for k in trial], split)))
             alone = _step_time([(t, _want_threads(t.work))])
-            if chosen and tt > stretch * max(cur_time, alone):
+            if chosen and tt > pack_gain * (cur_time + alone):
                 continue
             chosen, nts, cur_time = trial, split, tt
             if t.d is LEAF:
@@ -654,8 +665,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
         if pool.fill[pool.cur] == pool.per_half and not pool.busy[pool.cur]:
             start_flush(pool.cur)
         step_idx += 1
-    sched_stats = dict(est_cycles=est_time, est_issue=est_issue,
-                       est_fill=est_issue / (4 * 0.75) / max(est_time, 1.0))
+    sched_stats = dict(est_cycles=est_time, est_issue=est_issue)
     return steps, alloc.high_water, pool.chan_table, sched_stats
 
 
