@@ -35,6 +35,7 @@ static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b;
 #define TEB_UNROLL2
 #define TEB_UNROLL4
 #define TEB_FFS(x) __builtin_ffs((int)(x))
+#define __popc(x) __builtin_popcount(x)
 #else
 #include <cuda_runtime.h>
 #define TEB_D __device__ __forceinline__
@@ -305,6 +306,43 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
     if (logk >= 2) {
         const int n_dst = 1 << (t.b - logk);
         const unsigned mask = (unsigned)t.f;
+        if (__popc(mask) <= 2) {
+            // at most two active chunks (every phi low-pass leaf): all filter loads of a trip --
+            // 2 chunks x 4 outputs -- are issued before the first one is consumed (one L2 round trip)
+            const int i0 = (TEB_FFS(mask) - 1) << 2;
+            const unsigned m2 = mask & (mask - 1);
+            const int i1 = m2 ? ((TEB_FFS(m2) - 1) << 2) : i0;
+            for (int m0 = lt; m0 < n_dst; m0 += 4 * t.nt) {
+                float4 g0[4], g1[4];
+                TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + j * t.nt;
+                    const bool ok = m < n_dst;
+                    g0[j] = ok ? TEB_LDG(reinterpret_cast<const float4*>(f + (m << logk) + i0)) : float4{0.f, 0.f, 0.f, 0.f};
+                    g1[j] = (ok && m2) ? TEB_LDG(reinterpret_cast<const float4*>(f + (m << logk) + i1)) : float4{0.f, 0.f, 0.f, 0.f};
+                }
+                TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + j * t.nt;
+                    if (m < n_dst) {
+                        const int q = swz(t.a + (m << logk) + i0);
+                        const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
+                        float ax = z0.x * g0[j].x, ay = z0.y * g0[j].x;
+                        ax = fmaf(z1.x, g0[j].y, ax); ay = fmaf(z1.y, g0[j].y, ay);
+                        ax = fmaf(z2.x, g0[j].z, ax); ay = fmaf(z2.y, g0[j].z, ay);
+                        ax = fmaf(z3.x, g0[j].w, ax); ay = fmaf(z3.y, g0[j].w, ay);
+                        if (m2) {
+                            const int r = swz(t.a + (m << logk) + i1);
+                            const float2 y0 = S[r], y1 = S[r + 1], y2 = S[r + 2], y3 = S[r + 3];
+                            ax = fmaf(y0.x, g1[j].x, ax); ay = fmaf(y0.y, g1[j].x, ay);
+                            ax = fmaf(y1.x, g1[j].y, ax); ay = fmaf(y1.y, g1[j].y, ay);
+                            ax = fmaf(y2.x, g1[j].z, ax); ay = fmaf(y2.y, g1[j].z, ay);
+                            ax = fmaf(y3.x, g1[j].w, ax); ay = fmaf(y3.y, g1[j].w, ay);
+                        }
+                        S[swz(t.d + m)] = make_float2(ax * scale, ay * scale);
+                    }
+                }
+            }
+            return;
+        }
         // four outputs per thread and trip: the chunk loop is uniform over the task, so the
         // four 128-bit filter loads of one chunk are in flight together
         for (int m0 = lt; m0 < n_dst; m0 += 4 * t.nt) {
