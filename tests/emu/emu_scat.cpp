@@ -19,10 +19,10 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
                                   const int32_t* chan, const float* x, long long B, float* out,
                                   float* zc, float* zp, int z_mode) {
     std::vector<float2> S((size_t)smem_complex);
-    std::vector<float2> tw(kTwA + kTwB);
+    std::vector<float2> tw(kTwAP + kTwBP, make_float2(0.f, 0.f));
     const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
-    for (int a = 0; a < kTwA; ++a) tw[a] = make_float2((float)cos(w0 * 128.0 * a), (float)sin(w0 * 128.0 * a));
-    for (int b = 0; b < kTwB; ++b) tw[kTwA + b] = make_float2((float)cos(w0 * b), (float)sin(w0 * b));
+    for (int a = 0; a < kTwA; ++a) tw[a + (a >> 4)] = make_float2((float)cos(w0 * 128.0 * a), (float)sin(w0 * 128.0 * a));
+    for (int b = 0; b < kTwB; ++b) tw[kTwAP + b + (b >> 4)] = make_float2((float)cos(w0 * b), (float)sin(w0 * b));
     for (long long b = 0; b < B; ++b) {
         // poison shared memory so that reads of never-written slots show up as NaNs
         for (auto& z : S) z = make_float2(NAN, NAN);
@@ -38,7 +38,7 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
             for (int ti = steps[2 * s]; ti < steps[2 * s + 1]; ++ti) {
                 Task t;
                 memcpy(&t, tasks + kTaskInts * ti, sizeof(Task));
-                for (int lt = 0; lt < t.nt; ++lt) exec_task(S.data(), tw.data(), tw.data() + kTwA, arena, c, t, lt);
+                for (int lt = 0; lt < t.nt; ++lt) exec_task(S.data(), tw.data(), tw.data() + kTwAP, arena, c, t, lt);
             }
         }
     }

@@ -26,15 +26,15 @@ __global__ void __launch_bounds__(512) k(float* out, int iters, float a, float b
     if (s == 12345.678f) out[0] = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
 }
-template <int MODE> void run(const char* name) {
+template <int MODE> void run(const char* name, int threads = 512) {
     float* d; long long* c; cudaMalloc(&d, 64); cudaMalloc(&c, 8);
     const int iters = 4096;
-    k<MODE><<<148, 512>>>(d, iters, 0.999f, 0.001f, c);
-    k<MODE><<<148, 512>>>(d, iters, 0.999f, 0.001f, c);
+    k<MODE><<<148, threads>>>(d, iters, 0.999f, 0.001f, c);
+    k<MODE><<<148, threads>>>(d, iters, 0.999f, 0.001f, c);
     cudaDeviceSynchronize();
     long long h; cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
-    double winstr = 16.0 * iters * 16;    // warp-instr per SM (16 warps)
-    printf("%-28s cycles %lld  warp-instr/cycle/SM %.2f  (per SMSP %.2f)\n", name, h, winstr / h, winstr / h / 4);
+    double winstr = 16.0 * iters * (threads / 32);    // warp-instr per SM
+    printf("%-28s threads %4d cycles %lld  warp-instr/cycle/SM %.2f  (per SMSP %.2f)\n", name, threads, h, winstr / h, winstr / h / 4);
 }
 int main() {
     run<0>("FFMA r,c[],c[]");
@@ -43,5 +43,10 @@ int main() {
     run<3>("FADD r,r distinct");
     run<4>("FMUL r,r distinct");
     run<5>("FADD r,rS");
+    run<3>("FADD r,r distinct", 128);
+    run<3>("FADD r,r distinct", 256);
+    run<2>("FFMA r,r,r distinct", 128);
+    run<1>("FFMA r,rS,rS", 128);
+    run<1>("FFMA r,rS,rS", 256);
     return 0;
 }

@@ -58,7 +58,7 @@ enum : int32_t {
     OP_STOREZ = 5    // a=src b=row (filter index) c=first index d=count: complex crop -> global (phase stage A)
 };
 enum : int32_t { Z_CART = 1, Z_POLAR = 2 };
-enum : int32_t { FFT_INV = 1, FFT_MOD = 2 };
+enum : int32_t { FFT_INV = 1, FFT_MOD = 2, FFT_FUSE_FWD = 4 };
 constexpr int kTaskInts = 12;
 
 struct Task {
@@ -81,6 +81,10 @@ struct SignalCtx {
 constexpr int kLog2TwMax = 13;                 // twiddle tables cover lengths up to 8192
 constexpr int kTwA = 1 << (kLog2TwMax - 7);    // coarse table entries: W^(128 a)
 constexpr int kTwB = 128;                      // fine table entries:   W^b
+// both tables are stored with one pad entry per 16 so that lanes reading entries a
+// power-of-two apart (the usual case: k = i0 * 2^m) hit distinct banks
+constexpr int kTwAP = kTwA + kTwA / 16;
+constexpr int kTwBP = kTwB + kTwB / 16;
 
 // modulus (kymatio/backend/torch_backend.py:57): MUFU.SQRT on the device (<= 2 ulp, no
 // slow path), sqrtf in the host emulator.
@@ -185,7 +189,8 @@ template <int SGN> struct Dft<16, SGN> {
 
 // W_8192^k = exp(-2*pi*i*k/8192) from the two shared-memory tables
 TEB_D float2 twiddle(const float2* twA, const float2* twB, int k) {
-    return cmul(twA[k >> 7], twB[k & 127]);
+    const int a = k >> 7, b = k & 127;
+    return cmul(twA[a + (a >> 4)], twB[b + (b >> 4)]);
 }
 
 // w^q for q = 1..R-1 from the base powers wb[i] = w^(2^i): at most popcount(q)-1 products
@@ -204,7 +209,7 @@ template <int LOGR> TEB_D float2 twiddle_power(const float2 (&wb)[LOGR], int q) 
 // One radix-2^LOGR pass over butterfly u of a length-2^logL transform stored at `base`.
 //   forward (INV=0): decimation in frequency, block size 2^logB, natural -> bit-reversed
 //   inverse (INV=1): decimation in time, the exact adjoint of the forward pass
-template <int LOGR, bool INV, bool MOD>
+template <int LOGR, bool INV, bool MOD, bool FUSE = false>
 TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int base, int logB, int u) {
     constexpr int R = 1 << LOGR;
     const int logs = logB - LOGR;                  // log2 of the sub-block stride
@@ -217,7 +222,8 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
         const int k1 = i0 << (kLog2TwMax - logB);
         TEB_UNROLL for (int i = 0; i < LOGR; ++i) wb[i] = twiddle(twA, twB, k1 << i);
     }
-    // element j of the butterfly lives at slot swz(p0 + j*s)
+    // element j of the butterfly lives at slot swz(p0 + j*s); for strides that are multiples of
+    // 16 the padded layout is affine in j
     int slot[R];
     if (logs >= 4) {
         const int s0 = swz(p0), ds = (1 << logs) + (1 << (logs - 4));
@@ -225,68 +231,89 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
     } else {
         TEB_UNROLL for (int j = 0; j < R; ++j) slot[j] = swz(p0 + (j << logs));
     }
+#define TEB_SLOT(j) slot[j]
     if (!INV) {
-        TEB_UNROLL for (int j = 0; j < R; ++j) v[j] = S[slot[j]];
+        TEB_UNROLL for (int j = 0; j < R; ++j) v[j] = S[TEB_SLOT(j)];
         Dft<R, -1>::run(v);
         TEB_UNROLL for (int r = 0; r < R; ++r) {
             const int q = qmap<R>(r);
             float2 y = v[r];
             if (q != 0 && logs > 0) y = cmul(y, twiddle_power<LOGR>(wb, q));
-            S[slot[brev<LOGR>(q)]] = y;
+            S[TEB_SLOT(brev<LOGR>(q))] = y;
         }
     } else {
         TEB_UNROLL for (int q = 0; q < R; ++q) {
-            float2 y = S[slot[brev<LOGR>(q)]];
+            float2 y = S[TEB_SLOT(brev<LOGR>(q))];
             if (q != 0 && logs > 0) y = cmulc(y, twiddle_power<LOGR>(wb, q));
             v[q] = y;
         }
         Dft<R, +1>::run(v);
-        TEB_UNROLL for (int r = 0; r < R; ++r) {
-            float2 y = v[r];
-            if (MOD) y = make_float2(teb_sqrt(fmaf(y.x, y.x, y.y * y.y)), 0.f);
-            S[slot[qmap<R>(r)]] = y;
+        if (!FUSE) {
+            TEB_UNROLL for (int r = 0; r < R; ++r) {
+                float2 y = v[r];
+                if (MOD) y = make_float2(teb_sqrt(fmaf(y.x, y.x, y.y * y.y)), 0.f);
+                S[TEB_SLOT(qmap<R>(r))] = y;
+            }
+        } else {
+            // The last inverse pass and the first forward pass of "ifft -> modulus -> fft" touch
+            // the same R elements of the same thread: take the modulus in registers and go
+            // straight into the forward butterfly (one shared-memory round trip and one barrier less).
+            float2 f[R];
+            TEB_UNROLL for (int r = 0; r < R; ++r)
+                f[qmap<R>(r)] = make_float2(teb_sqrt(fmaf(v[r].x, v[r].x, v[r].y * v[r].y)), 0.f);
+            Dft<R, -1>::run(f);
+            TEB_UNROLL for (int r = 0; r < R; ++r) {
+                const int q = qmap<R>(r);
+                float2 y = f[r];
+                if (q != 0 && logs > 0) y = cmul(y, twiddle_power<LOGR>(wb, q));
+                S[TEB_SLOT(brev<LOGR>(q))] = y;
+            }
         }
     }
 }
 
+#undef TEB_SLOT
+
 // Unit-stride pass of a small radix (the remainder pass: last DIF / first DIT pass, no
-// twiddles): every thread takes 16 contiguous slots per trip -- 16/R butterflies whose loads
-// are all in flight together -- instead of one tiny butterfly per trip.
+// twiddles): 16 contiguous slots per thread and trip -- 16/R butterflies whose loads are
+// all in flight together -- instead of one tiny butterfly per trip.
 template <int LOGR, bool INV>
-TEB_D void fft_unit_stride_task(float2* S, const Task& t, int lt) {
+TEB_D void fft_unit_stride_group(float2* S, int first_slot) {
     constexpr int R = 1 << LOGR;
-    const int n_groups = (t.b << LOGR) >> 4;                 // groups of 16 slots
-    for (int gidx = lt; gidx < n_groups; gidx += t.nt) {
-        const int q0 = swz(t.a + (gidx << 4));               // 16 slots of one group: contiguous
-        float2 v[16];
-        TEB_UNROLL for (int j = 0; j < 16; ++j) v[j] = S[q0 + j];
-        TEB_UNROLL for (int b = 0; b < 16 / R; ++b) {
-            float2 w[R];
-            if (!INV) {
-                TEB_UNROLL for (int j = 0; j < R; ++j) w[j] = v[b * R + j];
-                Dft<R, -1>::run(w);
-                TEB_UNROLL for (int r = 0; r < R; ++r) v[b * R + brev<LOGR>(qmap<R>(r))] = w[r];
-            } else {
-                TEB_UNROLL for (int q = 0; q < R; ++q) w[q] = v[b * R + brev<LOGR>(q)];
-                Dft<R, +1>::run(w);
-                TEB_UNROLL for (int r = 0; r < R; ++r) v[b * R + qmap<R>(r)] = w[r];
-            }
+    const int q0 = swz(first_slot);                          // 16 slots of one group: contiguous
+    float2 v[16];
+    TEB_UNROLL for (int j = 0; j < 16; ++j) v[j] = S[q0 + j];
+    TEB_UNROLL for (int b = 0; b < 16 / R; ++b) {
+        float2 w[R];
+        if (!INV) {
+            TEB_UNROLL for (int j = 0; j < R; ++j) w[j] = v[b * R + j];
+            Dft<R, -1>::run(w);
+            TEB_UNROLL for (int r = 0; r < R; ++r) v[b * R + brev<LOGR>(qmap<R>(r))] = w[r];
+        } else {
+            TEB_UNROLL for (int q = 0; q < R; ++q) w[q] = v[b * R + brev<LOGR>(q)];
+            Dft<R, +1>::run(w);
+            TEB_UNROLL for (int r = 0; r < R; ++r) v[b * R + qmap<R>(r)] = w[r];
         }
-        TEB_UNROLL for (int j = 0; j < 16; ++j) S[q0 + j] = v[j];
     }
+    TEB_UNROLL for (int j = 0; j < 16; ++j) S[q0 + j] = v[j];
 }
 
 template <int LOGR>
 TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task& t, int lt) {
     const int n_bfly = t.b;
-    const bool inv = (t.e & FFT_INV) != 0, mod = (t.e & FFT_MOD) != 0;
+    const bool inv = (t.e & FFT_INV) != 0, mod = (t.e & FFT_MOD) != 0, fuse = (t.e & FFT_FUSE_FWD) != 0;
     if (LOGR <= 2 && t.c == LOGR && !mod && (((n_bfly << LOGR) & 15) == 0)) {
-        if (!inv) fft_unit_stride_task<LOGR, false>(S, t, lt);
-        else fft_unit_stride_task<LOGR, true>(S, t, lt);
+        const int n_groups = (n_bfly << LOGR) >> 4;
+        for (int g = lt; g < n_groups; g += t.nt) {
+            if (!inv) fft_unit_stride_group<(LOGR <= 2 ? LOGR : 1), false>(S, t.a + (g << 4));
+            else fft_unit_stride_group<(LOGR <= 2 ? LOGR : 1), true>(S, t.a + (g << 4));
+        }
         return;
     }
     if (!inv) {
         for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, t.c, u);
+    } else if (fuse) {
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, true, true>(S, twA, twB, t.a, t.c, u);
     } else if (!mod) {
         for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, false>(S, twA, twB, t.a, t.c, u);
     } else {

@@ -78,8 +78,8 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
     extern __shared__ __align__(16) float2 smem[];
     float2* S = smem;
     float2* twA = smem + p.smem_complex;
-    float2* twB = twA + kTwA;
-    for (int i = threadIdx.x; i < kTwA + kTwB; i += blockDim.x) twA[i] = p.tw[i];
+    float2* twB = twA + kTwAP;
+    for (int i = threadIdx.x; i < kTwAP + kTwBP; i += blockDim.x) twA[i] = p.tw[i];
     __syncthreads();
 
     const int tid = threadIdx.x;
@@ -90,18 +90,22 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
     int cur = fetch_field(tab);
     int nxt = fetch_field(tab + stride * (1 % n_steps));
     int s_fetch = 2 % n_steps;
+    __shared__ SignalCtx c;          // per-signal context lives in shared memory: nothing to keep in
+                                     // registers across the (partly out-of-line) task bodies
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
-        SignalCtx c;
-        c.x = x + b * p.x_stride;
-        c.out = out + b * (long long)p.n_paths * p.n_out;
-        c.chan = p.chan;
-        c.zc = p.zc + b * p.z_stride;
-        c.zp = p.zp + b * p.z_stride;
-        c.z_mode = p.z_mode;
-        c.N = p.N;
-        c.pad_left = p.pad_left;
-        c.log2_Np = p.log2_Np;
-        c.n_out = p.n_out;
+        if (tid == 0) {
+            c.x = x + b * p.x_stride;
+            c.out = out + b * (long long)p.n_paths * p.n_out;
+            c.chan = p.chan;
+            c.zc = p.zc + b * p.z_stride;
+            c.zp = p.zp + b * p.z_stride;
+            c.z_mode = p.z_mode;
+            c.N = p.N;
+            c.pad_left = p.pad_left;
+            c.log2_Np = p.log2_Np;
+            c.n_out = p.n_out;
+        }
+        __syncthreads();             // (the last step of the previous signal ended in a barrier too)
         const bool prof = PROF && blockIdx.x == 0 && b == blockIdx.x && tid == 0;
         for (int s = 0; s < n_steps; ++s) {
             const int fut = fetch_field(tab + stride * s_fetch);       // wraps into the next signal
@@ -240,16 +244,16 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     p->desc = *desc;
     p->device = device;
     p->n_sms = prop.multiProcessorCount;
-    p->smem_bytes = ((size_t)desc->smem_complex + kTwA + kTwB) * sizeof(float2);
+    p->smem_bytes = ((size_t)desc->smem_complex + kTwAP + kTwBP) * sizeof(float2);
     if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
         delete p;
         return fail(TEBSCAT_EUNSUPPORTED, "schedule needs %zu B of shared memory, device offers %zu",
                     p->smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
     }
-    std::vector<float2> tw(kTwA + kTwB);
+    std::vector<float2> tw(kTwAP + kTwBP, make_float2(0.f, 0.f));
     const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
-    for (int a = 0; a < kTwA; ++a) tw[a] = make_float2((float)cos(w0 * 128.0 * a), (float)sin(w0 * 128.0 * a));
-    for (int b = 0; b < kTwB; ++b) tw[kTwA + b] = make_float2((float)cos(w0 * b), (float)sin(w0 * b));
+    for (int a = 0; a < kTwA; ++a) tw[a + (a >> 4)] = make_float2((float)cos(w0 * 128.0 * a), (float)sin(w0 * 128.0 * a));
+    for (int b = 0; b < kTwB; ++b) tw[kTwAP + b + (b >> 4)] = make_float2((float)cos(w0 * b), (float)sin(w0 * b));
 
     CU(cudaMalloc(&p->d_arena, n_floats * sizeof(float)));
     CU(cudaMalloc(&p->d_tw, tw.size() * sizeof(float2)));
@@ -272,10 +276,18 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     CU(cudaMemcpy(p->d_arena, arena, n_floats * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     // the attribute belongs to the kernel, not to the plan: always allow the device maximum
+    cudaFuncAttributes fa0, fa1;
+    CU(cudaFuncGetAttributes(&fa0, scat1d_kernel<false>));
+    CU(cudaFuncGetAttributes(&fa1, scat1d_kernel<true>));
     CU(cudaFuncSetAttribute(scat1d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)prop.sharedMemPerBlockOptin));
+                            (int)(prop.sharedMemPerBlockOptin - fa0.sharedSizeBytes)));
     CU(cudaFuncSetAttribute(scat1d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)prop.sharedMemPerBlockOptin));
+                            (int)(prop.sharedMemPerBlockOptin - fa1.sharedSizeBytes)));
+    if (p->smem_bytes + fa0.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin ||
+        p->smem_bytes + fa1.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) {
+        tebscat_plan_destroy(p);
+        return fail(TEBSCAT_EUNSUPPORTED, "schedule needs more shared memory than the device offers");
+    }
 
     KParams& k = p->kp;
     k.arena = p->d_arena;

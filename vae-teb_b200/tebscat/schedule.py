@@ -36,13 +36,13 @@ import numpy as np
 from . import filterbank as fbk
 
 OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ = 0, 1, 2, 3, 4, 5
-FFT_INV, FFT_MOD = 1, 2
+FFT_INV, FFT_MOD, FFT_FUSE_FWD = 1, 2, 4
 TASK_INTS = 12
 
 N_THREADS = 512
 LOG2_NP_MAX = 13                  # single-CTA limit of the kernel (kLog2TwMax)
 SMEM_BYTES_MAX = 227 * 1024
-TW_SLOTS = 64 + 128               # twiddle tables live behind the schedule's slots
+TW_SLOTS = 68 + 136 + 4 + 16      # padded twiddle tables + the kernel's static shared memory
 MASK_THRESHOLD = 1e-9             # relative filter magnitude below which a 4-bin chunk is skipped
 BATCH_SLOTS = 8192                # target size of one batch buffer (complex slots)
 POOL_SLOTS = 2048                 # size of one half of the leaf pool
@@ -102,6 +102,7 @@ class TaskSpec:
     f: int = 0
     sexp: int = 0
     channel: int = -1              # output channel of a leaf MULFOLD
+    tpi: int = 1                   # threads per work item (32 for warp-local FFT tasks)
 
 
 @dataclass
@@ -130,30 +131,48 @@ _FFT_INSTR = {1: 40.0, 2: 110.0, 3: 250.0, 4: 480.0}
 STEP_OVERHEAD = 450.0
 
 
-def _fft_stages(ref, n: int, count: int, inverse: bool, modulus: bool = False) -> List[List[TaskSpec]]:
-    """Passes of `count` in-place length-2^n transforms stored back to back at `ref`."""
-    out = []
+def _global_pass(ref, n: int, count: int, logB: int, r: int, flags: int) -> TaskSpec:
+    bfly = count << (n - r)
+    if r <= 2 and logB == r and not (flags & FFT_MOD) and ((count << n) & 15) == 0:
+        # unit-stride remainder pass: the kernel takes 16 slots per thread and trip
+        return TaskSpec(OP_FFT, (count << n) >> 4, 500.0, 300.0, a=ref, b=bfly, c=logB, d=r, e=flags)
+    lat, instr = _FFT_LAT[r], _FFT_INSTR[r]
+    if flags & FFT_FUSE_FWD:
+        lat, instr = 1.8 * lat, 1.8 * instr
+    return TaskSpec(OP_FFT, bfly, lat, instr, a=ref, b=bfly, c=logB, d=r, e=flags)
 
-    def task(r, logB, flags):
-        bfly = count << (n - r)
-        if r <= 2 and logB == r and not (flags & FFT_MOD) and ((count << n) & 15) == 0:
-            # unit-stride remainder pass: the kernel takes 16 slots per thread and trip
-            return TaskSpec(OP_FFT, (count << n) >> 4, 500.0, 300.0, a=ref, b=bfly, c=logB, d=r, e=flags)
-        return TaskSpec(OP_FFT, bfly, _FFT_LAT[r], _FFT_INSTR[r], a=ref, b=bfly, c=logB, d=r, e=flags)
 
-    if not inverse:
-        logB = n
-        for r in radix_split(n):
-            out.append([task(r, logB, 0)])
-            logB -= r
-    else:
-        logB = 0
-        split = radix_split(n)[::-1]
-        for i, r in enumerate(split):
-            logB += r
-            flags = FFT_INV | (FFT_MOD if (modulus and i == len(split) - 1) else 0)
-            out.append([task(r, logB, flags)])
-    return out
+def _fft_stages(ref, n: int, count: int, kind: str) -> List[List[TaskSpec]]:
+    """Stages of `count` in-place length-2^n transforms stored back to back at `ref`.
+
+    kind: 'fwd' (DIF), 'inv' (DIT), 'inv_mod' (DIT ending in the modulus) or 'pair'
+    (inverse, modulus, forward -- core/scattering1d.py:312-318 / :350-355).  In a 'pair' the
+    last inverse and the first forward pass touch the same 16 elements per thread and are
+    fused into one task (one shared-memory round trip and one barrier less).
+
+    (Running the small-block passes warp-locally with __syncwarp() instead of CTA barriers was
+    measured 30 % SLOWER on B200: warps executing different passes thrash the instruction cache.)"""
+    if n < 4:
+        raise NotImplementedError('transforms shorter than 16 samples are not supported')
+    dif = []
+    logB = n
+    for r in radix_split(n):
+        dif.append((logB, r))
+        logB -= r
+    dit = dif[::-1]
+    if kind == 'fwd':
+        return [[_global_pass(ref, n, count, b, r, 0)] for b, r in dif]
+    if kind in ('inv', 'inv_mod'):
+        mod = FFT_MOD if kind == 'inv_mod' else 0
+        return [[_global_pass(ref, n, count, b, r, FFT_INV | (mod if i == len(dit) - 1 else 0))]
+                for i, (b, r) in enumerate(dit)]
+    if kind == 'pair':
+        out = [[_global_pass(ref, n, count, b, r, FFT_INV)] for b, r in dit[:-1]]
+        b, r = dit[-1]
+        out.append([_global_pass(ref, n, count, b, r, FFT_INV | FFT_MOD | FFT_FUSE_FWD)])
+        out += [[_global_pass(ref, n, count, b2, r2, 0)] for b2, r2 in dif[1:]]
+        return out
+    raise ValueError(kind)
 
 
 class _Arena:
@@ -299,7 +318,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
     # root: pad + forward transform of the signal (core/scattering1d.py:278-280)
     u0 = Buf(1 << n, 'U0')
     root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
-                 _fft_stages((u0, 0), n, 1, inverse=False), owns=[u0], depth=0)
+                 _fft_stages((u0, 0), n, 1, 'fwd'), owns=[u0], depth=0)
     chains.append(root)
     chains.append(Chain('S0', [[leaf((u0, 0), n, 0, ())]], after=[root], reads=[u0], depth=1))   # :285-292
 
@@ -319,8 +338,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
             nb = len(batch)
             x1 = Buf(nb << l1, 'U1[k1=%d:%d]' % (k1, batch[0]))
             st = [[_mulfold(arena, (u0, 0), n, k1, (x1, i << l1), psi1_off[n1]) for i, n1 in enumerate(batch)]]
-            st += _fft_stages((x1, 0), l1, nb, inverse=True, modulus=True)             # :312-315
-            st += _fft_stages((x1, 0), l1, nb, inverse=False)                          # :318
+            st += _fft_stages((x1, 0), l1, nb, 'pair')                                 # :312-318
             c1 = Chain(x1.name, st, after=[root], reads=[u0], owns=[x1], depth=1)
             chains.append(c1)
             # low-pass leaves of the batch (:320-327)
@@ -347,8 +365,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
                     x2 = Buf(len(sub) << l2, 'U2[%d,k2=%d]' % (batch[0], k2))
                     st = [[_mulfold(arena, (x1, i << l1), l1, k2, (x2, c << l2), psi2_off[n2][k1])
                            for c, (i, n1, n2) in enumerate(sub)]]                       # :347-348
-                    st += _fft_stages((x2, 0), l2, len(sub), inverse=True, modulus=True)
-                    st += _fft_stages((x2, 0), l2, len(sub), inverse=False)             # :355
+                    st += _fft_stages((x2, 0), l2, len(sub), 'pair')                    # :350-355
                     c2 = Chain(x2.name, st, after=[c1], reads=[x1], owns=[x2], depth=2)
                     chains.append(c2)
                     chains.append(Chain('S2' + x2.name,
@@ -360,8 +377,8 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
 # ------------------------------------------------------------------------------------
 # list scheduler
 # ------------------------------------------------------------------------------------
-def _want_threads(work: int) -> int:
-    return min(N_THREADS, max(32, (work + 31) & ~31))
+def _want_threads(work: int, tpi: int = 1) -> int:
+    return min(N_THREADS, max(32, (work * tpi + 31) & ~31))
 
 
 def _step_time(items: List[Tuple[TaskSpec, int]]) -> float:
@@ -370,7 +387,7 @@ def _step_time(items: List[Tuple[TaskSpec, int]]) -> float:
     lat = 0.0
     issue = 0.0
     for t, nt in items:
-        trips = math.ceil(t.work / nt)
+        trips = math.ceil(t.work * t.tpi / nt)
         lat = max(lat, t.lat + (trips - 1) * t.instr)
         issue += (nt / 128.0) * trips * t.instr
     return STEP_OVERHEAD + lat + issue
@@ -385,16 +402,16 @@ def _split_threads(tasks: List[TaskSpec]) -> Optional[List[int]]:
     nts = [32] * n
     left = N_THREADS - 32 * n
     while left > 0:
-        times = [(math.ceil(t.work / nt) - 1) * t.instr + t.lat for t, nt in zip(tasks, nts)]
+        times = [(math.ceil(t.work * t.tpi / nt) - 1) * t.instr + t.lat for t, nt in zip(tasks, nts)]
         order = sorted(range(n), key=lambda i: -times[i])
         grew = False
         for i in order:
-            want = _want_threads(tasks[i].work)
+            want = _want_threads(tasks[i].work, tasks[i].tpi)
             if nts[i] >= want:
                 continue
-            it = math.ceil(tasks[i].work / nts[i])
+            it = math.ceil(tasks[i].work * tasks[i].tpi / nts[i])
             need = nts[i] + 32
-            while need < want and math.ceil(tasks[i].work / need) >= it:
+            while need < want and math.ceil(tasks[i].work * tasks[i].tpi / need) >= it:
                 need += 32
             if need - nts[i] > left:
                 continue
@@ -436,7 +453,7 @@ class _LeafPool:
         table_off = len(self.chan_table)
         self.chan_table += self.channels[h]
         ref = (self.bufs[h], 0)
-        st = _fft_stages(ref, self.lf, cnt, inverse=True)
+        st = _fft_stages(ref, self.lf, cnt, 'inv')
         st.append([TaskSpec(OP_STOREB, cnt * self.n_out, 150.0, 14.0, a=ref, b=cnt, c=self.i0, d=self.n_out,
                             e=table_off, f=self.lf)])
         ch = Chain('flush%d@%d' % (h, table_off), st, depth=9, pool_half=h)
@@ -576,7 +593,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
         # ---- start chains whose inputs are complete ------------------------------------
         startable = [c for c in pending if all(a.done_step >= 0 and a.done_step < step_idx for a in c.after)]
         startable.sort(key=lambda c: -c.priority)
-        demand = sum(sum(_want_threads(t.work) for t, done in zip(c.stages[c.stage], c.issued) if not done)
+        demand = sum(sum(_want_threads(t.work, t.tpi) for t, done in zip(c.stages[c.stage], c.issued) if not done)
                      for c in active)
         for c in startable:
             if len(active) >= max_parallel:
@@ -586,7 +603,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
             if try_start(c, force=False):
                 pending.remove(c)
                 active.append(c)
-                demand += sum(_want_threads(t.work) for t in c.stages[0])
+                demand += sum(_want_threads(t.work, t.tpi) for t in c.stages[0])
         if not active:
             for c in startable:                   # progress guarantee
                 if try_start(c, force=True):
@@ -617,7 +634,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
             if split is None:
                 break
             tt = _step_time(list(zip([k[2] for k in trial], split)))
-            alone = _step_time([(t, _want_threads(t.work))])
+            alone = _step_time([(t, _want_threads(t.work, t.tpi))])
             if chosen and tt > pack_gain * (cur_time + alone):
                 continue
             chosen, nts, cur_time = trial, split, tt
@@ -631,7 +648,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
             dst = pool.take(t.channel) if t.d is LEAF else resolve(t.d)
             this_step.append([t.op | (t.sexp << 8), used, nt, resolve(t.a), t.b, t.c, dst, t.e, t.f, 0, 0, 0])
             used += nt
-            est_issue += (nt // 32) * math.ceil(t.work / nt) * t.instr
+            est_issue += (nt // 32) * math.ceil(t.work * t.tpi / nt) * t.instr
             c.issued[ti] = True
         est_time += cur_time
         steps.append(this_step)
