@@ -310,14 +310,16 @@ TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task&
         }
         return;
     }
+    // the modulus / fused passes are always radix 16 (the last inverse pass of any transform
+    // of 16 samples or more): only that instantiation carries them, which keeps the kernel small
     if (!inv) {
         for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, t.c, u);
-    } else if (fuse) {
-        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, true, true>(S, twA, twB, t.a, t.c, u);
-    } else if (!mod) {
-        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, false>(S, twA, twB, t.a, t.c, u);
+    } else if (LOGR == 4 && fuse) {
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<4, true, true, true>(S, twA, twB, t.a, t.c, u);
+    } else if (LOGR == 4 && mod) {
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<4, true, true>(S, twA, twB, t.a, t.c, u);
     } else {
-        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, true>(S, twA, twB, t.a, t.c, u);
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, false>(S, twA, twB, t.a, t.c, u);
     }
 }
 

@@ -180,6 +180,7 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
             case OP_FFT: {
                 // a=region b=butterflies c=log2B d=log2R: the butterflies cover b*R slots in blocks of 2^c
                 if (t[5] < 1 || t[5] > kLog2TwMax || t[6] < 1 || t[6] > 4 || t[6] > t[5] || t[4] < 1 ||
+                    ((t[7] & (FFT_MOD | FFT_FUSE_FWD)) && (t[6] != 4 || !(t[7] & FFT_INV))) ||
                     (((int64_t)t[4] << t[6]) & (((int64_t)1 << t[5]) - 1)) || !fits(t[3], (int64_t)t[4] << t[6]))
                     return fail(TEBSCAT_EINVAL, "task %d: bad FFT pass (%d butterflies, B=2^%d R=2^%d at %d)", i, t[4], t[5], t[6], t[3]);
                 break;
