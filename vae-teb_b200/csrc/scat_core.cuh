@@ -53,7 +53,7 @@ enum : int32_t {
     OP_NOP = 0,
     OP_LOAD = 1,     // a=dst                              reflect-padded signal -> (x, 0)
     OP_FFT = 2,      // a=region b=butterflies (all blocks) c=log2B d=log2R e=flags(FFT_INV|FFT_MOD)
-    OP_MULFOLD = 3,  // a=src b=log2Lsrc c=log2k d=dst e=filter offset (floats) f=chunk mask; scale 2^-sexp
+    OP_MULFOLD = 3,  // a=src b=log2Lsrc c=log2k d=dst e=filter offset (floats) f=chunk mask g=fused first inverse radix; scale 2^-sexp
     OP_STOREB = 4,   // a=pool base b=slots c=first index d=count e=channel-table offset f=log2 slot length
     OP_STOREZ = 5    // a=src b=row (filter index) c=first index d=count: complex crop -> global (phase stage A)
 };
@@ -411,10 +411,24 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
             const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
             if (logk == 0) {
                 const int o = swz(t.d + 4 * it);
-                S[o] = make_float2(z0.x * g.x * scale, z0.y * g.x * scale);
-                S[o + 1] = make_float2(z1.x * g.y * scale, z1.y * g.y * scale);
-                S[o + 2] = make_float2(z2.x * g.z * scale, z2.y * g.z * scale);
-                S[o + 3] = make_float2(z3.x * g.w * scale, z3.y * g.w * scale);
+                float2 w0 = make_float2(z0.x * g.x * scale, z0.y * g.x * scale);
+                float2 w1 = make_float2(z1.x * g.y * scale, z1.y * g.y * scale);
+                float2 w2 = make_float2(z2.x * g.z * scale, z2.y * g.z * scale);
+                float2 w3 = make_float2(z3.x * g.w * scale, z3.y * g.w * scale);
+                // optionally the first (unit-stride, twiddle-free) inverse pass of the transform
+                // that follows, on the four slots this thread owns: one round trip less
+                if (t.g == 1) {
+                    dft2<+1>(w0, w1);
+                    dft2<+1>(w2, w3);
+                } else if (t.g == 2) {
+                    float2 a0 = w0, a1 = w2, a2 = w1, a3 = w3;        // inputs in bit-reversed order
+                    dft4<+1>(a0, a1, a2, a3);
+                    w0 = a0; w1 = a1; w2 = a2; w3 = a3;
+                }
+                S[o] = w0;
+                S[o + 1] = w1;
+                S[o + 2] = w2;
+                S[o + 3] = w3;
             } else {
                 const int o = swz(t.d + 2 * it);
                 S[o] = make_float2(fmaf(z0.x, g.x, z1.x * g.y) * scale, fmaf(z0.y, g.x, z1.y * g.y) * scale);

@@ -123,7 +123,8 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
                 t.d = __shfl_sync(0xffffffffu, cur, 6);
                 t.e = __shfl_sync(0xffffffffu, cur, 7);
                 t.f = __shfl_sync(0xffffffffu, cur, 8);
-                t.g = 0; t.h = 0; t.pad = 0;
+                t.g = __shfl_sync(0xffffffffu, cur, 9);
+                t.h = 0; t.pad = 0;
                 exec_task(S, twA, twB, p.arena, c, t, tid - t.t0);
             }
             __syncthreads();
@@ -192,6 +193,8 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                     return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD", i);
                 if (t[5] >= 2 && ((unsigned)t[8] == 0u || ((unsigned)t[8] >> (1 << (t[5] - 2))) != 0u))
                     return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD chunk mask", i);
+                if (t[9] != 0 && (t[5] != 0 || t[9] < 0 || t[9] > 2))
+                    return fail(TEBSCAT_EINVAL, "task %d: a first inverse pass can only be fused into a k=1 MULFOLD", i);
                 break;
             }
             case OP_STOREB:

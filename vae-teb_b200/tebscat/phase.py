@@ -101,8 +101,8 @@ class PhasePlan:
         for f, p in enumerate(self.bank.psi1):
             off = arena.add(p.levels[0])
             x = sch.Buf(1 << n, 'Z[%d]' % f)
-            st = [[sch._mulfold(arena, (u0, 0), n, 0, (x, 0), off)]]
-            st += sch._fft_stages((x, 0), n, 1, 'inv')
+            mf = [sch._mulfold(arena, (u0, 0), n, 0, (x, 0), off)]
+            st = [mf] + sch._fuse_first_inverse_pass(mf, sch._fft_stages((x, 0), n, 1, 'inv'), n)
             st.append([sch.TaskSpec(sch.OP_STOREZ, self.N, 200.0, 40.0, a=(x, 0), b=f, c=self.geo.pad_left, d=self.N)])
             chains.append(sch.Chain(x.name, st, after=[root], reads=[u0], owns=[x], frees_own_at_end=True, depth=1))
         steps, high, chan, stats = sch.schedule_chains(chains, sch.smem_capacity(), n, 0, self.N)

@@ -100,6 +100,7 @@ class TaskSpec:
     d: object = 0                  # int, (Buf, offset) or LEAF
     e: int = 0
     f: int = 0
+    g: int = 0
     sexp: int = 0
     channel: int = -1              # output channel of a leaf MULFOLD
     tpi: int = 1                   # threads per work item (32 for warp-local FFT tasks)
@@ -209,6 +210,21 @@ class _Arena:
 
     def finish(self) -> np.ndarray:
         return np.concatenate(self.chunks) if self.chunks else np.zeros(4, np.float32)
+
+
+def _fuse_first_inverse_pass(mulfolds: List[TaskSpec], stages: List[List[TaskSpec]], n: int):
+    """If the transform's first inverse pass is the unit-stride remainder pass (radix 2 or 4) and
+    every MULFOLD feeding it is a plain k=1 product, let the MULFOLD do that pass on the four
+    slots each of its threads owns and drop the pass (core :307-312 in one round trip)."""
+    r0 = radix_split(n)[-1]
+    if r0 <= 2 and len(radix_split(n)) > 1 and all(m.c == 0 for m in mulfolds):
+        first = stages[0][0]
+        if first.op == OP_FFT and first.c == r0 and first.d == r0 and (first.e & FFT_INV) and not (first.e & (FFT_MOD | FFT_FUSE_FWD)):
+            for m in mulfolds:
+                m.g = r0
+                m.instr += 10.0
+            return stages[1:]
+    return stages
 
 
 def _mulfold(arena: _Arena, src, log_src: int, logk: int, dst, filt_off: int, channel: int = -1) -> TaskSpec:
@@ -337,8 +353,8 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
             batch = members[s:s + per_batch]
             nb = len(batch)
             x1 = Buf(nb << l1, 'U1[k1=%d:%d]' % (k1, batch[0]))
-            st = [[_mulfold(arena, (u0, 0), n, k1, (x1, i << l1), psi1_off[n1]) for i, n1 in enumerate(batch)]]
-            st += _fft_stages((x1, 0), l1, nb, 'pair')                                 # :312-318
+            mf = [_mulfold(arena, (u0, 0), n, k1, (x1, i << l1), psi1_off[n1]) for i, n1 in enumerate(batch)]
+            st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x1, 0), l1, nb, 'pair'), l1)   # :307-318
             c1 = Chain(x1.name, st, after=[root], reads=[u0], owns=[x1], depth=1)
             chains.append(c1)
             # low-pass leaves of the batch (:320-327)
@@ -363,9 +379,9 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
                 for s2 in range(0, len(fam), per):
                     sub = fam[s2:s2 + per]
                     x2 = Buf(len(sub) << l2, 'U2[%d,k2=%d]' % (batch[0], k2))
-                    st = [[_mulfold(arena, (x1, i << l1), l1, k2, (x2, c << l2), psi2_off[n2][k1])
-                           for c, (i, n1, n2) in enumerate(sub)]]                       # :347-348
-                    st += _fft_stages((x2, 0), l2, len(sub), 'pair')                    # :350-355
+                    mf = [_mulfold(arena, (x1, i << l1), l1, k2, (x2, c << l2), psi2_off[n2][k1])
+                          for c, (i, n1, n2) in enumerate(sub)]                         # :347-348
+                    st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x2, 0), l2, len(sub), 'pair'), l2)   # :350-355
                     c2 = Chain(x2.name, st, after=[c1], reads=[x1], owns=[x2], depth=2)
                     chains.append(c2)
                     chains.append(Chain('S2' + x2.name,
@@ -646,7 +662,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
         used = 0
         for (c, ti, t), nt in zip(chosen, nts):
             dst = pool.take(t.channel) if t.d is LEAF else resolve(t.d)
-            this_step.append([t.op | (t.sexp << 8), used, nt, resolve(t.a), t.b, t.c, dst, t.e, t.f, 0, 0, 0])
+            this_step.append([t.op | (t.sexp << 8), used, nt, resolve(t.a), t.b, t.c, dst, t.e, t.f, t.g, 0, 0])
             used += nt
             est_issue += (nt // 32) * math.ceil(t.work * t.tpi / nt) * t.instr
             c.issued[ti] = True
