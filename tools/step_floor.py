@@ -38,3 +38,13 @@ run([[load]] + [[f16(256, 256, 12)]] * 64, '8 warps, one R16 butterfly each (s=2
 f8 = lambda nb, nt, logB: [OP_FFT, 0, nt, 0, nb, logB, 3, 0, 0, 0, 0, 0]
 run([[load]] + [[f8(1024, 512, 13)]] * 64, '16 warps, two R8 butterflies each (s=1024)')
 run([[load]] + [[f8(512, 512, 3)]] * 64, '16 warps, one R8 unit stride')
+
+# ---- MULFOLD variants (filters: offset 0 of the arena = phi level 0, 8192 floats) -------------
+OP_MULFOLD = 3
+mf = lambda logk, nt, mask, sexp=13: [OP_MULFOLD | (sexp << 8), 0, nt, 0, 13, logk, 8192, 0, mask, 0, 0, 0]   # filter offset 0: any data
+run([[load]] + [[mf(0, 512, 0)]] * 32, 'MULFOLD k=1  8192->8192, 512 thr (4 items/thr)')
+run([[load]] + [[mf(1, 512, 0)]] * 32, 'MULFOLD k=2  8192->4096, 512 thr (4 items/thr)')
+run([[load]] + [[mf(2, 512, 1)]] * 32, 'MULFOLD k=4  1 chunk, 2048 out, 512 thr (1 trip)')
+run([[load]] + [[mf(2, 256, 1)]] * 32, 'MULFOLD k=4  1 chunk, 2048 out, 256 thr (2 trips)')
+run([[load]] + [[mf(6, 32, 0x8001)]] * 32, 'MULFOLD k=64 2 chunks, 128 out, 32 thr (1 trip)')
+run([[load]] + [[mf(4, 128, 0xf)]] * 32, 'MULFOLD k=16 4 chunks, 512 out, 128 thr (1 trip)')

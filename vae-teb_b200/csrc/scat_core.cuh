@@ -333,9 +333,13 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
     const float scale = ldexpf(1.0f, -(t.op >> 8));
     const float* f = arena + t.e;
     if (logk >= 2) {
+        // Filter layout for k >= 4: COMPACTED by the host to the active chunks only,
+        // f[(m * nch + c) * 4 + r], so that consecutive outputs read consecutive memory
+        // (the natural layout would stride by k floats: one L2 request per lane).
         const int n_dst = 1 << (t.b - logk);
         const unsigned mask = (unsigned)t.f;
-        if (__popc(mask) <= 2) {
+        const int nch = __popc(mask);
+        if (nch <= 2) {
             // at most two active chunks (every phi low-pass leaf): all filter loads of a trip --
             // 2 chunks x 4 outputs -- are issued before the first one is consumed (one L2 round trip)
             const int i0 = (TEB_FFS(mask) - 1) << 2;
@@ -346,8 +350,9 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
                 TEB_UNROLL for (int j = 0; j < 4; ++j) {
                     const int m = m0 + j * t.nt;
                     const bool ok = m < n_dst;
-                    g0[j] = ok ? TEB_LDG(reinterpret_cast<const float4*>(f + (m << logk) + i0)) : float4{0.f, 0.f, 0.f, 0.f};
-                    g1[j] = (ok && m2) ? TEB_LDG(reinterpret_cast<const float4*>(f + (m << logk) + i1)) : float4{0.f, 0.f, 0.f, 0.f};
+                    const float4* fm = reinterpret_cast<const float4*>(f) + m * nch;
+                    g0[j] = ok ? TEB_LDG(fm) : float4{0.f, 0.f, 0.f, 0.f};
+                    g1[j] = (ok && m2) ? TEB_LDG(fm + 1) : float4{0.f, 0.f, 0.f, 0.f};
                 }
                 TEB_UNROLL for (int j = 0; j < 4; ++j) {
                     const int m = m0 + j * t.nt;
@@ -377,13 +382,14 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
         for (int m0 = lt; m0 < n_dst; m0 += 4 * t.nt) {
             float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f};
             unsigned rest = mask;
+            int c = 0;
             while (rest) {
                 const int i = (TEB_FFS(rest) - 1) << 2;
                 rest &= rest - 1;
                 float4 g[4];
                 TEB_UNROLL for (int j = 0; j < 4; ++j) {
                     const int m = m0 + j * t.nt;
-                    g[j] = (m < n_dst) ? TEB_LDG(reinterpret_cast<const float4*>(f + (m << logk) + i))
+                    g[j] = (m < n_dst) ? TEB_LDG(reinterpret_cast<const float4*>(f) + m * nch + c)
                                        : float4{0.f, 0.f, 0.f, 0.f};
                 }
                 TEB_UNROLL for (int j = 0; j < 4; ++j) {
@@ -397,6 +403,7 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
                         ax[j] = fmaf(z3.x, g[j].w, ax[j]); ay[j] = fmaf(z3.y, g[j].w, ay[j]);
                     }
                 }
+                ++c;
             }
             TEB_UNROLL for (int j = 0; j < 4; ++j) {
                 const int m = m0 + j * t.nt;

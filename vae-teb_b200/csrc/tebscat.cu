@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -189,10 +190,15 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
             case OP_MULFOLD: {
                 if (t[4] < 2 || t[4] > kLog2TwMax || t[5] < 0 || t[5] > t[4] || t[5] > 6 || !fits(t[3], (int64_t)1 << t[4]) ||
                     !fits(t[6] & ~15, (t[6] & 15) + ((int64_t)1 << (t[4] - t[5]))) || t[7] < 0 ||
-                    (size_t)t[7] + ((size_t)1 << t[4]) > n_floats || (t[7] & 3) || (t[6] & 3 && t[5] < 2))
+                    (t[7] & 3) || (t[6] & 3 && t[5] < 2))
                     return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD", i);
                 if (t[5] >= 2 && ((unsigned)t[8] == 0u || ((unsigned)t[8] >> (1 << (t[5] - 2))) != 0u))
                     return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD chunk mask", i);
+                {   // filter extent: natural layout for k < 4, compacted to the active chunks for k >= 4
+                    const size_t need = t[5] >= 2 ? ((size_t)1 << (t[4] - t[5])) * 4 * __builtin_popcount((unsigned)t[8])
+                                                  : ((size_t)1 << t[4]);
+                    if ((size_t)t[7] + need > n_floats) return fail(TEBSCAT_EINVAL, "task %d: MULFOLD filter outside the arena", i);
+                }
                 if (t[9] != 0 && (t[5] != 0 || t[9] < 0 || t[9] > 2))
                     return fail(TEBSCAT_EINVAL, "task %d: a first inverse pass can only be fused into a k=1 MULFOLD", i);
                 break;

@@ -208,6 +208,21 @@ class _Arena:
             self._masks[key] = mask if mask else 1
         return self._masks[key]
 
+    def compact(self, off: int, logk: int, mask: int) -> int:
+        """Copy of filter `off` restricted to the active 4-bin chunks of a k=2^logk fold, laid out
+        [output bin][active chunk][4] so that consecutive outputs read consecutive memory."""
+        key = ('c', off, logk, mask)
+        if key not in self._masks:
+            k = 1 << logk
+            f = self.by_off[off].reshape(-1, k // 4, 4)
+            sel = [c for c in range(k // 4) if (mask >> c) & 1]
+            comp = np.ascontiguousarray(f[:, sel, :]).reshape(-1)
+            new = self.size
+            self.chunks.append(comp)
+            self.size += comp.shape[0]
+            self._masks[key] = new
+        return self._masks[key]
+
     def finish(self) -> np.ndarray:
         return np.concatenate(self.chunks) if self.chunks else np.zeros(4, np.float32)
 
@@ -232,6 +247,7 @@ def _mulfold(arena: _Arena, src, log_src: int, logk: int, dst, filt_off: int, ch
     if logk >= 2:
         mask = arena.chunk_mask(filt_off, logk)
         nch = bin(mask).count('1')
+        filt_off = arena.compact(filt_off, logk, mask)
         # the kernel takes four outputs per thread and trip
         work, lat, instr = -(-(1 << log_dst) // 4), 900.0 + 150.0 * nch, 250.0 + 200.0 * nch
     else:
