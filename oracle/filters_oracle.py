@@ -34,7 +34,10 @@ def periodize(h_f, nperiods=1):
 
 # --- filter_bank.py:139-165 ---------------------------------------------------
 def l1_factor(h_f):
-    return 1.0 / np.abs(scipy.fft.ifft(h_f)).sum()
+    l1 = np.abs(scipy.fft.ifft(h_f)).sum()
+    if l1 < 1e-7:                                                       # :156-158
+        raise ValueError('Zero division error is very likely to occur, aborting computations now.')
+    return 1.0 / l1
 
 
 # --- filter_bank.py:74-136 ----------------------------------------------------

@@ -148,3 +148,21 @@ def test_plan_validation_errors():
     assert 'outside the CTA' in str(ve.value)
     rc = _lib.load().tebscat_scat1d_forward(None, None, 1, None, None)
     assert rc == _lib.TEBSCAT_EINVAL
+
+
+@pytest.mark.parametrize('cfg', [(7, 8, 512, 128, 2), (8, 8, 1000, 256, 2), (10, 4, 5000, 1024, 1), (5, 8, 512, 24, 2),
+                                 (3, 8, 2048, 6, 2), (10, 12, 5000, 768, 2)])
+def test_other_configurations(cfg):
+    """Wide folds (k > 128), output-rate lengths of 2..8 samples (tiny transforms), T < 2**J,
+    non power-of-two T, unbatchable buffers."""
+    from tebscat import Scattering1D
+    J, Q, N, T, mo = cfg
+    S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    x = np.random.RandomState(3).randn(3, N).astype(np.float32)
+    out, _ = S(torch.from_numpy(x).cuda())
+    out = out.cpu().numpy().astype(np.float64)
+    ref = ScatteringOracle(J, N, Q, T, mo)(x)
+    assert out.shape == ref.shape
+    nr = np.linalg.norm(ref, axis=-1)
+    err = np.linalg.norm(out - ref, axis=-1)
+    assert np.all(err <= 1e-5 * nr + 1e-10 * nr.max()), float((err / nr).max())

@@ -7,7 +7,7 @@ import pytest
 
 from helpers import CONFIGS, GOLDEN, emu_available, emu_forward, path_tolerance, rel_l2
 from oracle.scattering1d_oracle import ScatteringOracle
-from tebscat.schedule import (OP_FFT, OP_LOAD, OP_MULFOLD, OP_STOREB, SMEM_BYTES_MAX, TASK_INTS, TW_SLOTS,
+from tebscat.schedule import (OP_FFT, OP_LOAD, OP_MULFOLD, OP_STOREB, OP_TINY, SMEM_BYTES_MAX, TASK_INTS, TW_SLOTS,
                               bitrev_indices, build_plan, radix_split)
 
 _plans = {}
@@ -36,6 +36,8 @@ def _touched(t, np_len):
         return [], [(a, a + np_len)]
     if op == OP_FFT:                       # b butterflies of radix 2^d
         return [(a, a + (b << d))], [(a, a + (b << d))]
+    if op == OP_TINY:                      # b transforms of 2^c
+        return [(a, a + (b << c))], [(a, a + (b << c))]
     if op == OP_MULFOLD:
         return [(a, a + (1 << b))], [(d, d + (1 << (b - c)))]
     if op == OP_STOREB:                    # b slots of 2^f
@@ -111,3 +113,32 @@ def test_emulated_kernel_matches_golden_reference_outputs(name):
                      4.0 * np.linalg.norm(d['S'].astype(np.float64) - ref64, axis=-1))
     assert np.all(np.linalg.norm(out - ref64, axis=-1) <= tol)
     assert rel_l2(out, d['S']) < 2e-6
+
+
+@pytest.mark.skipif(not emu_available(), reason='host emulator not built')
+def test_config_sweep_through_emulator():
+    """The scheduler must produce a correct schedule for any (J, Q, N, T, max_order) the reference
+    accepts: batched / unbatched buffers, folds wider than 128 bins, output-rate lengths down to
+    2 samples (tiny transforms), T < 2**J and non power-of-two T."""
+    rng = np.random.RandomState(11)
+    cfgs = [(2, 1, 64, 4, 2), (3, 2, 100, 8, 2), (4, 12, 257, 16, 2), (5, 8, 512, 24, 2), (6, 1, 2048, 64, 1),
+            (7, 8, 512, 128, 2), (7, 4, 3000, 32, 2), (8, 8, 1000, 256, 2), (8, 2, 5000, 128, 1),
+            (8, 4, 257, 256, 2), (10, 4, 5000, 1024, 1), (10, 12, 5000, 768, 2), (6, 12, 3000, 16, 2),
+            (5, 1, 5000, 8, 2), (3, 8, 2048, 6, 2)]
+    checked = 0
+    for J, Q, N, T, mo in cfgs:
+        try:
+            orc = ScatteringOracle(J, N, Q, T, mo)
+        except Exception:
+            continue                                   # the reference itself rejects it
+        p = build_plan(J, N, Q, T, mo)
+        x = rng.randn(2, N).astype(np.float32)
+        out = emu_forward(p, x).astype(np.float64)
+        ref = orc(x)
+        assert out.shape == ref.shape, (J, Q, N, T, mo)
+        nr = np.linalg.norm(ref, axis=-1)
+        err = np.linalg.norm(out - ref, axis=-1)
+        # paths whose energy is below 1e-5 of the strongest one are rounding noise in fp32
+        assert np.all(err <= 1e-5 * nr + 1e-10 * nr.max()), (J, Q, N, T, mo, float((err / nr).max()))
+        checked += 1
+    assert checked >= 12

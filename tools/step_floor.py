@@ -41,7 +41,7 @@ run([[load]] + [[f8(512, 512, 3)]] * 64, '16 warps, one R8 unit stride')
 
 # ---- MULFOLD variants (filters: offset 0 of the arena = phi level 0, 8192 floats) -------------
 OP_MULFOLD = 3
-mf = lambda logk, nt, mask, sexp=13: [OP_MULFOLD | (sexp << 8), 0, nt, 0, 13, logk, 8192, 0, mask, 0, 0, 0]   # filter offset 0: any data
+mf = lambda logk, nt, mask, sexp=13: [OP_MULFOLD | (sexp << 8), 0, nt, 0, 13, logk, 8192, 0, mask, 0, 2 if logk >= 2 else 0, 0]   # filter offset 0: any data
 run([[load]] + [[mf(0, 512, 0)]] * 32, 'MULFOLD k=1  8192->8192, 512 thr (4 items/thr)')
 run([[load]] + [[mf(1, 512, 0)]] * 32, 'MULFOLD k=2  8192->4096, 512 thr (4 items/thr)')
 run([[load]] + [[mf(2, 512, 1)]] * 32, 'MULFOLD k=4  1 chunk, 2048 out, 512 thr (1 trip)')

@@ -55,7 +55,8 @@ enum : int32_t {
     OP_FFT = 2,      // a=region b=butterflies (all blocks) c=log2B d=log2R e=flags(FFT_INV|FFT_MOD)
     OP_MULFOLD = 3,  // a=src b=log2Lsrc c=log2k d=dst e=filter offset (floats) f=chunk mask g=fused first inverse radix; scale 2^-sexp
     OP_STOREB = 4,   // a=pool base b=slots c=first index d=count e=channel-table offset f=log2 slot length
-    OP_STOREZ = 5    // a=src b=row (filter index) c=first index d=count: complex crop -> global (phase stage A)
+    OP_STOREZ = 5,   // a=src b=row (filter index) c=first index d=count: complex crop -> global (phase stage A)
+    OP_TINY = 6      // a=region b=transforms c=log2L (1..3) e=flags: whole transforms of 2, 4 or 8 samples
 };
 enum : int32_t { Z_CART = 1, Z_POLAR = 2 };
 enum : int32_t { FFT_INV = 1, FFT_MOD = 2, FFT_FUSE_FWD = 4 };
@@ -323,6 +324,52 @@ TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task&
     }
 }
 
+// Transforms of 2, 4 or 8 samples (output-rate lengths of short signals): one thread per
+// transform, direct O(L^2) DFT with the eighth roots of unity as constants.  Same conventions
+// as the passes above: spectra in bit-reversed order, inverse unnormalised, optional modulus
+// and "inverse -> modulus -> forward" in one go.
+TEB_D void tiny_task(float2* S, const Task& t, int lt) {
+    const int n = t.c, L = 1 << n;
+    const bool inv = (t.e & FFT_INV) != 0, mod = (t.e & FFT_MOD) != 0, fuse = (t.e & FFT_FUSE_FWD) != 0;
+    const float h = 0.70710678118654752f;
+    const float wr[8] = {1.f, h, 0.f, -h, -1.f, -h, 0.f, h};          // exp(-2 pi i m / 8)
+    const float wi[8] = {0.f, -h, -1.f, -h, 0.f, h, 1.f, h};
+    for (int u = lt; u < t.b; u += t.nt) {
+        const int base = t.a + (u << n);
+        float2 x[8], y[8];
+        for (int p = 0; p < L; ++p) x[p] = S[swz(base + p)];
+        auto rev = [&](int k) { int r = 0; for (int b = 0; b < n; ++b) r |= ((k >> b) & 1) << (n - 1 - b); return r; };
+        if (inv) {
+            for (int tt = 0; tt < L; ++tt) {                        // x_t = sum_k X_k conj(W)^(k t)
+                float ax = 0.f, ay = 0.f;
+                for (int k = 0; k < L; ++k) {
+                    const int m = ((k * tt) << (3 - n)) & 7;
+                    const float2 X = x[rev(k)];
+                    ax += X.x * wr[m] + X.y * wi[m];
+                    ay += X.y * wr[m] - X.x * wi[m];
+                }
+                y[tt] = (mod || fuse) ? make_float2(teb_sqrt(fmaf(ax, ax, ay * ay)), 0.f) : make_float2(ax, ay);
+            }
+            if (fuse) {
+                for (int p = 0; p < L; ++p) x[p] = y[p];
+            } else {
+                for (int p = 0; p < L; ++p) S[swz(base + p)] = y[p];
+                continue;
+            }
+        }
+        for (int k = 0; k < L; ++k) {                               // X_k = sum_t x_t W^(k t)
+            float ax = 0.f, ay = 0.f;
+            for (int tt = 0; tt < L; ++tt) {
+                const int m = ((k * tt) << (3 - n)) & 7;
+                ax += x[tt].x * wr[m] - x[tt].y * wi[m];
+                ay += x[tt].y * wr[m] + x[tt].x * wi[m];
+            }
+            y[rev(k)] = make_float2(ax, ay);
+        }
+        for (int p = 0; p < L; ++p) S[swz(base + p)] = y[p];
+    }
+}
+
 // dst[m] = 2^-sexp * sum_{i<k} src[m*k + i] * filt[m*k + i]      (bit-reversed bin order)
 // Filters are real fp32 in global memory (L2 resident).  Every work item covers four
 // consecutive source slots with one 128-bit filter load; for k >= 4 only the 4-slot chunks
@@ -338,8 +385,9 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
         // (the natural layout would stride by k floats: one L2 request per lane).
         const int n_dst = 1 << (t.b - logk);
         const unsigned mask = (unsigned)t.f;
-        const int nch = __popc(mask);
-        if (nch <= 2) {
+        const int logcw = t.h;                         // chunk width 2^logcw bins (4, or k/32 for k > 128)
+        const int nch = __popc(mask) << (logcw - 2);   // active 4-bin groups per output
+        if (nch <= 2 && logcw == 2) {
             // at most two active chunks (every phi low-pass leaf): all filter loads of a trip --
             // 2 chunks x 4 outputs -- are issued before the first one is consumed (one L2 round trip)
             const int i0 = (TEB_FFS(mask) - 1) << 2;
@@ -384,26 +432,28 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
             unsigned rest = mask;
             int c = 0;
             while (rest) {
-                const int i = (TEB_FFS(rest) - 1) << 2;
+                const int i_chunk = (TEB_FFS(rest) - 1) << logcw;
                 rest &= rest - 1;
-                float4 g[4];
-                TEB_UNROLL for (int j = 0; j < 4; ++j) {
-                    const int m = m0 + j * t.nt;
-                    g[j] = (m < n_dst) ? TEB_LDG(reinterpret_cast<const float4*>(f) + m * nch + c)
-                                       : float4{0.f, 0.f, 0.f, 0.f};
-                }
-                TEB_UNROLL for (int j = 0; j < 4; ++j) {
-                    const int m = m0 + j * t.nt;
-                    if (m < n_dst) {
-                        const int q = swz(t.a + (m << logk) + i);      // 4 slots of one 16-group: contiguous
-                        const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
-                        ax[j] = fmaf(z0.x, g[j].x, ax[j]); ay[j] = fmaf(z0.y, g[j].x, ay[j]);
-                        ax[j] = fmaf(z1.x, g[j].y, ax[j]); ay[j] = fmaf(z1.y, g[j].y, ay[j]);
-                        ax[j] = fmaf(z2.x, g[j].z, ax[j]); ay[j] = fmaf(z2.y, g[j].z, ay[j]);
-                        ax[j] = fmaf(z3.x, g[j].w, ax[j]); ay[j] = fmaf(z3.y, g[j].w, ay[j]);
+                for (int sub = 0; sub < (1 << (logcw - 2)); ++sub, ++c) {
+                    const int i = i_chunk + (sub << 2);
+                    float4 g[4];
+                    TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                        const int m = m0 + j * t.nt;
+                        g[j] = (m < n_dst) ? TEB_LDG(reinterpret_cast<const float4*>(f) + m * nch + c)
+                                           : float4{0.f, 0.f, 0.f, 0.f};
+                    }
+                    TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                        const int m = m0 + j * t.nt;
+                        if (m < n_dst) {
+                            const int q = swz(t.a + (m << logk) + i);      // 4 slots of one 16-group: contiguous
+                            const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
+                            ax[j] = fmaf(z0.x, g[j].x, ax[j]); ay[j] = fmaf(z0.y, g[j].x, ay[j]);
+                            ax[j] = fmaf(z1.x, g[j].y, ax[j]); ay[j] = fmaf(z1.y, g[j].y, ay[j]);
+                            ax[j] = fmaf(z2.x, g[j].z, ax[j]); ay[j] = fmaf(z2.y, g[j].z, ay[j]);
+                            ax[j] = fmaf(z3.x, g[j].w, ax[j]); ay[j] = fmaf(z3.y, g[j].w, ay[j]);
+                        }
                     }
                 }
-                ++c;
             }
             TEB_UNROLL for (int j = 0; j < 4; ++j) {
                 const int m = m0 + j * t.nt;
@@ -502,6 +552,7 @@ TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const floa
         case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
         case OP_STOREB: storeb_task(S, c, t, lt); break;
         case OP_STOREZ: storez_task(S, c, t, lt); break;
+        case OP_TINY: tiny_task(S, t, lt); break;
         default: break;
     }
 }

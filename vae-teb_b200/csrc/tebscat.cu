@@ -125,7 +125,8 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
                 t.e = __shfl_sync(0xffffffffu, cur, 7);
                 t.f = __shfl_sync(0xffffffffu, cur, 8);
                 t.g = __shfl_sync(0xffffffffu, cur, 9);
-                t.h = 0; t.pad = 0;
+                t.h = __shfl_sync(0xffffffffu, cur, 10);
+                t.pad = 0;
                 exec_task(S, twA, twB, p.arena, c, t, tid - t.t0);
             }
             __syncthreads();
@@ -188,14 +189,18 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                 break;
             }
             case OP_MULFOLD: {
-                if (t[4] < 2 || t[4] > kLog2TwMax || t[5] < 0 || t[5] > t[4] || t[5] > 6 || !fits(t[3], (int64_t)1 << t[4]) ||
+                if (t[4] < 2 || t[4] > kLog2TwMax || t[5] < 0 || t[5] > t[4] || !fits(t[3], (int64_t)1 << t[4]) ||
                     !fits(t[6] & ~15, (t[6] & 15) + ((int64_t)1 << (t[4] - t[5]))) || t[7] < 0 ||
-                    (t[7] & 3) || (t[6] & 3 && t[5] < 2))
+                    (t[7] & 3) || (t[5] == 0 && (t[6] & 3)) || (t[5] == 1 && (t[6] & 1)))
                     return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD", i);
-                if (t[5] >= 2 && ((unsigned)t[8] == 0u || ((unsigned)t[8] >> (1 << (t[5] - 2))) != 0u))
-                    return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD chunk mask", i);
+                if (t[5] >= 2) {
+                    const int logcw = t[10], n_chunks = 1 << (t[5] - logcw);
+                    if (logcw < 2 || logcw > t[5] || n_chunks > 32 || (unsigned)t[8] == 0u ||
+                        (n_chunks < 32 && ((unsigned)t[8] >> n_chunks) != 0u))
+                        return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD chunk mask", i);
+                }
                 {   // filter extent: natural layout for k < 4, compacted to the active chunks for k >= 4
-                    const size_t need = t[5] >= 2 ? ((size_t)1 << (t[4] - t[5])) * 4 * __builtin_popcount((unsigned)t[8])
+                    const size_t need = t[5] >= 2 ? (((size_t)1 << (t[4] - t[5])) << t[10]) * __builtin_popcount((unsigned)t[8])
                                                   : ((size_t)1 << t[4]);
                     if ((size_t)t[7] + need > n_floats) return fail(TEBSCAT_EINVAL, "task %d: MULFOLD filter outside the arena", i);
                 }
@@ -207,6 +212,10 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                 if (t[4] < 1 || t[6] != d.n_out || t[5] < 0 || t[8] < 0 || t[8] > kLog2TwMax || t[5] + t[6] > (1 << t[8]) ||
                     !fits(t[3], (int64_t)t[4] << t[8]) || t[7] < 0 || (size_t)t[7] + (size_t)t[4] > n_chan)
                     return fail(TEBSCAT_EINVAL, "task %d: bad STOREB", i);
+                break;
+            case OP_TINY:
+                if (t[4] < 1 || t[5] < 1 || t[5] > 3 || !fits(t[3], (int64_t)t[4] << t[5]))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad TINY transform", i);
                 break;
             case OP_STOREZ:
                 if (t[4] < 0 || t[4] >= d.n_paths || t[6] != d.n_out || t[5] < 0 || !fits(t[3], (int64_t)t[5] + t[6]))

@@ -35,7 +35,7 @@ import numpy as np
 
 from . import filterbank as fbk
 
-OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ = 0, 1, 2, 3, 4, 5
+OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY = 0, 1, 2, 3, 4, 5, 6
 FFT_INV, FFT_MOD, FFT_FUSE_FWD = 1, 2, 4
 TASK_INTS = 12
 
@@ -101,6 +101,7 @@ class TaskSpec:
     e: int = 0
     f: int = 0
     g: int = 0
+    h: int = 0
     sexp: int = 0
     channel: int = -1              # output channel of a leaf MULFOLD
     tpi: int = 1                   # threads per work item (32 for warp-local FFT tasks)
@@ -153,8 +154,12 @@ def _fft_stages(ref, n: int, count: int, kind: str) -> List[List[TaskSpec]]:
 
     (Running the small-block passes warp-locally with __syncwarp() instead of CTA barriers was
     measured 30 % SLOWER on B200: warps executing different passes thrash the instruction cache.)"""
+    if n < 1:
+        raise NotImplementedError('length-1 transforms are not supported')
     if n < 4:
-        raise NotImplementedError('transforms shorter than 16 samples are not supported')
+        # 2, 4 or 8 samples: one thread per transform does the whole thing (csrc: tiny_task)
+        flags = {'fwd': 0, 'inv': FFT_INV, 'inv_mod': FFT_INV | FFT_MOD, 'pair': FFT_INV | FFT_FUSE_FWD}[kind]
+        return [[TaskSpec(OP_TINY, count, 400.0 + 60.0 * (1 << n), 8.0 * (1 << (2 * n)), a=ref, b=count, c=n, e=flags)]]
     dif = []
     logB = n
     for r in radix_split(n):
@@ -193,14 +198,19 @@ class _Arena:
         self.size += perm.shape[0] + pad
         return off
 
+    @staticmethod
+    def chunk_log2(logk: int) -> int:
+        """log2 of the chunk width: 4 bins, or k/32 when the fold has more than 32 four-bin chunks."""
+        return max(2, logk - 5)
+
     def chunk_mask(self, off: int, logk: int) -> int:
-        """Bit c set <=> some output bin has a non-negligible filter value in 4-bin chunk c."""
+        """Bit c set <=> some output bin has a non-negligible filter value in chunk c (<= 32 chunks)."""
         key = (off, logk)
         if key not in self._masks:
             f = np.abs(self.by_off[off].astype(np.float64))
-            k = 1 << logk
+            k, cw = 1 << logk, 1 << self.chunk_log2(logk)
             peak = f.max()
-            sig = (f.reshape(-1, k // 4, 4).max(axis=2) > MASK_THRESHOLD * peak).any(axis=0)
+            sig = (f.reshape(-1, k // cw, cw).max(axis=2) > MASK_THRESHOLD * peak).any(axis=0)
             mask = 0
             for c, on in enumerate(sig):
                 if on:
@@ -209,13 +219,13 @@ class _Arena:
         return self._masks[key]
 
     def compact(self, off: int, logk: int, mask: int) -> int:
-        """Copy of filter `off` restricted to the active 4-bin chunks of a k=2^logk fold, laid out
-        [output bin][active chunk][4] so that consecutive outputs read consecutive memory."""
+        """Copy of filter `off` restricted to the active chunks of a k=2^logk fold, laid out
+        [output bin][active chunk][chunk width] so that consecutive outputs read consecutive memory."""
         key = ('c', off, logk, mask)
         if key not in self._masks:
-            k = 1 << logk
-            f = self.by_off[off].reshape(-1, k // 4, 4)
-            sel = [c for c in range(k // 4) if (mask >> c) & 1]
+            k, cw = 1 << logk, 1 << self.chunk_log2(logk)
+            f = self.by_off[off].reshape(-1, k // cw, cw)
+            sel = [c for c in range(k // cw) if (mask >> c) & 1]
             comp = np.ascontiguousarray(f[:, sel, :]).reshape(-1)
             new = self.size
             self.chunks.append(comp)
@@ -246,7 +256,7 @@ def _mulfold(arena: _Arena, src, log_src: int, logk: int, dst, filt_off: int, ch
     log_dst = log_src - logk
     if logk >= 2:
         mask = arena.chunk_mask(filt_off, logk)
-        nch = bin(mask).count('1')
+        nch = bin(mask).count('1') << (_Arena.chunk_log2(logk) - 2)     # in units of four bins
         filt_off = arena.compact(filt_off, logk, mask)
         # the kernel takes four outputs per thread and trip
         work, lat, instr = -(-(1 << log_dst) // 4), 900.0 + 150.0 * nch, 250.0 + 200.0 * nch
@@ -254,8 +264,10 @@ def _mulfold(arena: _Arena, src, log_src: int, logk: int, dst, filt_off: int, ch
         mask = 0
         work, lat, instr = 1 << (log_src - 2), 700.0, 120.0
     # mean over k blocks (2^-logk) and the 1/L of the following inverse transform (2^-log_dst)
+    if mask >= 1 << 31:
+        mask -= 1 << 32                                    # the task table holds int32 fields
     return TaskSpec(OP_MULFOLD, work, lat, instr, a=src, b=log_src, c=logk, d=dst, e=filt_off, f=mask,
-                    sexp=logk + log_dst, channel=channel)
+                    h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst, channel=channel)
 
 
 # ------------------------------------------------------------------------------------
@@ -318,15 +330,16 @@ class _Allocator:
         self.free = merged
 
 
-def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int, arena: _Arena):
+def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int, arena: _Arena,
+                 batch_slots: int = BATCH_SLOTS):
     """The cascade as a forest of chains of batched tasks, in the reference's channel order."""
     n = geo.J_pad
     log2_T = int(math.floor(math.log2(T)))
     lf = n - log2_T                                       # log2 of the final (output-rate) length
     if lf < 0:
         raise ValueError('T is larger than the padded support')
-    if lf < 2:
-        raise NotImplementedError('output-rate length below 4 samples is not supported')
+    if lf < 1:
+        raise NotImplementedError('output-rate length below 2 samples is not supported')
     i0, i1 = geo.ind_start[log2_T], geo.ind_end[log2_T]
     n_out = i1 - i0
 
@@ -363,7 +376,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
         groups.setdefault(k1, []).append(n1)
     for k1 in sorted(groups):
         l1 = n - k1
-        per_batch = max(1, BATCH_SLOTS >> l1)
+        per_batch = max(1, batch_slots >> l1)
         members = groups[k1]
         for s in range(0, len(members), per_batch):
             batch = members[s:s + per_batch]
@@ -391,7 +404,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
             for k2 in sorted(kids):
                 l2 = l1 - k2
                 fam = kids[k2]
-                per = max(1, BATCH_SLOTS >> l2)
+                per = max(1, batch_slots >> l2)
                 for s2 in range(0, len(fam), per):
                     sub = fam[s2:s2 + per]
                     x2 = Buf(len(sub) << l2, 'U2[%d,k2=%d]' % (batch[0], k2))
@@ -460,9 +473,9 @@ class _LeafPool:
     """Ping-pong pool of 2^lf-slot leaf spectra; a full half is flushed by one batched
     inverse transform + unpad + store (the flush chain)."""
 
-    def __init__(self, lf: int, i0: int, n_out: int):
+    def __init__(self, lf: int, i0: int, n_out: int, pool_slots: int = POOL_SLOTS):
         self.lf, self.i0, self.n_out = lf, i0, n_out
-        self.per_half = max(2, POOL_SLOTS >> lf)
+        self.per_half = max(1, pool_slots >> lf)
         self.bufs = [Buf(self.per_half << lf, 'pool0'), Buf(self.per_half << lf, 'pool1')]
         self.fill = [0, 0]
         self.channels: List[List[int]] = [[], []]
@@ -503,7 +516,7 @@ class _LeafPool:
 
 
 def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out: int,
-                    max_parallel: int = 64, pack_gain: float = 0.97):
+                    max_parallel: int = 64, pack_gain: float = 0.97, pool_slots: int = POOL_SLOTS):
     """Greedy list scheduling of chains into steps (see module docstring)."""
     children: Dict[int, List[Chain]] = {}
     for ch in chains:
@@ -539,7 +552,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
         c.done_step = -1
 
     alloc = _Allocator(capacity)
-    pool = _LeafPool(lf, i0, n_out)
+    pool = _LeafPool(lf, i0, n_out, pool_slots)
     has_leaves = any(t.d is LEAF for c in chains for st in c.stages for t in st)
     if has_leaves:
         for b in pool.bufs:
@@ -678,7 +691,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
         used = 0
         for (c, ti, t), nt in zip(chosen, nts):
             dst = pool.take(t.channel) if t.d is LEAF else resolve(t.d)
-            this_step.append([t.op | (t.sexp << 8), used, nt, resolve(t.a), t.b, t.c, dst, t.e, t.f, t.g, 0, 0])
+            this_step.append([t.op | (t.sexp << 8), used, nt, resolve(t.a), t.b, t.c, dst, t.e, t.f, t.g, t.h, 0])
             used += nt
             est_issue += (nt // 32) * math.ceil(t.work * t.tpi / nt) * t.instr
             c.issued[ti] = True
@@ -740,10 +753,21 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
             'padded length 2**%d exceeds the single-CTA shared-memory design (max 2**%d); '
             'the large-support path is not built yet' % (geo.J_pad, LOG2_NP_MAX))
     bank = fbk.build_filter_bank(geo.J_pad, J, Q1, T)
-    arena = _Arena()
-    chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena)
     capacity = smem_capacity()
-    steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel)
+    # batches as large as shared memory allows: retry with smaller batches / pool when the
+    # buffers of a configuration (large output-rate lengths, T << 2**J) do not fit
+    last_err = None
+    for batch_slots, pool_slots in ((BATCH_SLOTS, POOL_SLOTS), (4096, 2048), (2048, 1024), (1024, 512), (512, 256)):
+        arena = _Arena()
+        chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots)
+        try:
+            steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel,
+                                                       pool_slots=pool_slots)
+            break
+        except (RuntimeError, AssertionError) as e:
+            last_err = e
+    else:
+        raise NotImplementedError('no schedule fits shared memory for this configuration: %s' % last_err)
     tasks, ranges = emit(steps)
     n_tasks = tasks.shape[0]
     stats = dict(n_steps=len(steps), n_tasks=n_tasks, smem_logical=high,
