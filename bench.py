@@ -9,7 +9,8 @@ scaling; the batch shards with no collective).  `value` is device-resident
 throughput (CUDA events on the launch stream, max over ranks); `e2e` is the same
 metric through the host-buffer C-ABI entry point with pinned host tensors, H2D
 and D2H inside the timed region.  `--impl reference` times the CPU port of the
-reference (oracle/, all host threads) on a bounded sample of the same workload.
+reference (oracle/scattering1d_torch_port.py, all host threads) on a bounded sample of the
+same workload.
 """
 import argparse
 import json
@@ -77,18 +78,20 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_port_rate(n_signals, workers):
-    """signals/s of the numpy port of the reference (oracle/) on `workers` host threads."""
-    import numpy as np
-    import scipy.fft
-    from oracle.scattering1d_oracle import ScatteringOracle
+    """signals/s of the torch-CPU port of the reference (oracle/scattering1d_torch_port.py: the
+    reference's own torch calls, op for op) on `workers` host threads, batches of 64 signals
+    (BASELINE configs[0]: batch 32 x 2 channels)."""
+    import torch
+    from oracle.scattering1d_torch_port import TorchPort
     from tebscat.synth import ctg_batch
-    x = ctg_batch(n_signals // 2, N, seed=1234).reshape(n_signals, N).numpy()
-    orc = ScatteringOracle(J, N, Q, T, 2, cdtype=np.complex64)
-    with scipy.fft.set_workers(workers):
-        orc(x[:8])                                 # warm-up
-        t0 = time.perf_counter()
-        orc(x)
-        dt = time.perf_counter() - t0
+    torch.set_num_threads(workers)
+    x = ctg_batch(n_signals // 2, N, seed=1234).reshape(n_signals, N)
+    port = TorchPort(J, N, Q, T, 2)
+    port(x[:8])                                    # warm-up
+    t0 = time.perf_counter()
+    for b0 in range(0, n_signals, 64):
+        port(x[b0:b0 + 64])
+    dt = time.perf_counter() - t0
     return n_signals / dt, dt
 
 
@@ -98,10 +101,10 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 256
+    sample = 1024
     rates = []
     for _ in range(max(1, args.warmup)):
-        cpu_port_rate(32, cores)
+        cpu_port_rate(64, cores)
     for _ in range(args.steps):
         r, _ = cpu_port_rate(sample, cores)
         rates.append(r)
@@ -114,7 +117,7 @@ def run_reference(args):
         'config': {'workload': 'Scattering1D J=6 Q=8 T=64 N=4800 orders 0-2 (CPU port of the reference, '
                                'bounded sample of %d signals per step)' % sample},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d CTG signals per step, numpy/scipy complex64 port (oracle/)' % sample},
+                         'sample': '%d CTG signals per step in batches of 64, torch-CPU port of the reference (oracle/scattering1d_torch_port.py)' % sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -214,7 +217,7 @@ def run_gpu(args):
         _lib.load().tebscat_bench_fp32_peak(local, ctypes.byref(fp32))
         achieved_tf = n_sig * FLOPS_PER_SIGNAL / (kernel_ms * 1e-3) / 1e12
         cores = os.cpu_count() or 1
-        cpu_rate, cpu_dt = cpu_port_rate(512, cores)
+        cpu_rate, cpu_dt = cpu_port_rate(1024, cores)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True,
@@ -236,7 +239,7 @@ def run_gpu(args):
                                   'flops_per_signal': FLOPS_PER_SIGNAL,
                                   'peak_source': 'FMA microbenchmark in this run (tebscat_bench_fp32_peak)'}},
             'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': '512 CTG signals, %.1f s, numpy/scipy complex64 port (oracle/)' % cpu_dt},
+                             'sample': '1024 CTG signals in batches of 64, %.1f s, torch-CPU port of the reference (oracle/scattering1d_torch_port.py)' % cpu_dt},
             'phase': phase,
         }
         print(json.dumps(line), flush=True)

@@ -72,6 +72,18 @@ def test_scattering_vs_reference(golden_dir, name):
     assert rel_l2(S64[randn], d['S'][randn], axis=-1).max() < 1e-5
 
 
+@pytest.mark.parametrize('name', SCAT)
+def test_torch_port_vs_reference(golden_dir, name):
+    """The torch-CPU port timed as the CPU baseline issues the reference's own torch calls."""
+    import torch
+    from oracle.scattering1d_torch_port import TorchPort
+    d = load(golden_dir, 'scat_%s.npz' % name)
+    port = TorchPort(int(d['J']), int(d['N']), int(d['Q']), int(d['T']), int(d['max_order']))
+    S = port(torch.from_numpy(d['x'])).numpy()
+    assert S.shape == d['S'].shape
+    assert rel_l2(S, d['S'], axis=-1).max() < 2e-6
+
+
 @pytest.mark.parametrize('name', ['H', 'P', 'S'])
 def test_phase_vs_reference(golden_dir, name):
     d = load(golden_dir, 'phase_%s.npz' % name)
