@@ -128,6 +128,16 @@ int tebscat_phase_forward(tebscat_phase_plan* plan, const float* x_dev, int64_t 
                           int ch_i, int ch_j, const int32_t* pair_subset_host, int n_subset,
                           int apply_low_pass, float* out_dev, void* stream);
 
+/* Single-pass dataset entry: within-channel correlations of channel ch_i for the
+ * pairs `within_subset` and cross-channel correlations ch_i x ch_j for `cross_subset`, sharing the
+ * analytic signals of ch_i.  Replaces the two st_model(...) calls and the 903 -> 44 / 130 masking
+ * of hdf5_dataset/create_hdf5_dataset.py:421-441.  out_within [B, n_within, n_out],
+ * out_cross [B, n_cross, n_out]. */
+int tebscat_phase_forward_dual(tebscat_phase_plan* plan, const float* x_dev, int64_t B, int n_channels,
+                               int ch_i, int ch_j, const int32_t* within_subset_host, int n_within,
+                               const int32_t* cross_subset_host, int n_cross,
+                               float* out_within_dev, float* out_cross_dev, void* stream);
+
 /* Number of kernels the last forward call on this thread launched. */
 int tebscat_last_launch_count(void);
 

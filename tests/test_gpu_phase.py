@@ -142,3 +142,21 @@ def test_batch_chunking_is_consistent():
     x = base.repeat(41, 1, 1)                                        # 205 samples
     out = m(x, compute_phase=False, compute_cross_phase=True)['cross_phase_corr']
     assert torch.equal(out[:5], out[-5:]) and torch.equal(out[:5], out[100:105])
+
+
+def test_single_pass_dataset_entry_matches_two_calls():
+    """forward_dataset == the two st_model(...) calls + masking of
+    create_hdf5_dataset.py:421-441, bit for bit."""
+    J, Q, T, N, mo = CFG['P']
+    m = module_of('P')
+    sel = m.get_optimal_coefficients_for_fhr(J, Q, T)
+    pm, cm = sel['recommendations']['use_phase_mask'], sel['recommendations']['use_cross_mask']
+    from tebscat.synth import ctg_batch
+    x = ctg_batch(5, N, seed=9).cuda()
+    a = m(x, compute_phase=True, compute_cross_phase=False, phase_channels=[0])
+    b = m(x, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1])
+    one = m.forward_dataset(x, pm, cm)
+    assert one['phase_corr'].shape == (5, int(pm.sum()), 360) and one['cross_phase_corr'].shape == (5, int(cm.sum()), 360)
+    assert torch.equal(one['scattering'], a['scattering'])
+    assert torch.equal(one['phase_corr'], a['phase_corr'][:, pm])
+    assert torch.equal(one['cross_phase_corr'], b['cross_phase_corr'][:, cm])

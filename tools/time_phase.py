@@ -35,3 +35,5 @@ ms = timeit(dataset_step)
 print('P dataset step (S + 44 within + 130 cross) B=%d: %.1f ms -> %.0f segments/s' % (B, ms, B / ms * 1e3))
 ms = timeit(lambda: mp(xp, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1]))
 print('P cross all 903 pairs B=%d: %.1f ms -> %.0f /s' % (B, ms, B / ms * 1e3))
+ms = timeit(lambda: mp.forward_dataset(xp, pm, cm))
+print('P single-pass dataset entry B=%d: %.1f ms -> %.0f segments/s' % (B, ms, B / ms * 1e3))

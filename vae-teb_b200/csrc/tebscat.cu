@@ -582,9 +582,12 @@ struct tebscat_phase_plan {
     int32_t* d_j = nullptr;
     float* d_pw = nullptr;
     int32_t* d_subset = nullptr;
+    int32_t* d_subset2 = nullptr;
     float2* d_zc = nullptr;
     float2* d_zp = nullptr;
+    float2* d_zc2 = nullptr;       // second cartesian workspace of the dataset entry point
     int64_t ws_samples = 0;
+    int64_t ws2_samples = 0;
     std::mutex mu;
 };
 
@@ -612,6 +615,7 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
     CU(cudaMalloc(&p->d_j, d->n_pairs * sizeof(int32_t)));
     CU(cudaMalloc(&p->d_pw, d->n_pairs * sizeof(float)));
     CU(cudaMalloc(&p->d_subset, d->n_pairs * sizeof(int32_t)));
+    CU(cudaMalloc(&p->d_subset2, d->n_pairs * sizeof(int32_t)));
     CU(cudaMemcpy(p->d_i, i_idx, d->n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_j, j_idx, d->n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_pw, powers, d->n_pairs * sizeof(float), cudaMemcpyHostToDevice));
@@ -627,8 +631,10 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
     cudaFree(p->d_j);
     cudaFree(p->d_pw);
     cudaFree(p->d_subset);
+    cudaFree(p->d_subset2);
     cudaFree(p->d_zc);
     cudaFree(p->d_zp);
+    cudaFree(p->d_zc2);
     tebscat_plan_destroy(p->stage_a);
     delete p;
 }
@@ -712,6 +718,93 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
         }
         CU(cudaGetLastError());
         ++g_launches;
+    }
+    return TEBSCAT_OK;
+}
+
+static int launch_pairs(const tebscat_phase_plan* p, const float2* zp, const float2* zc, const int32_t* subset_dev,
+                        int n_sel, int64_t nb, float* out, cudaStream_t st) {
+    const tebscat_phase_desc& d = p->desc;
+    PairParams pp;
+    pp.zp = zp;
+    pp.zc = zc;
+    pp.G = p->d_G;
+    pp.i_idx = p->d_i;
+    pp.j_idx = p->d_j;
+    pp.powers = p->d_pw;
+    pp.subset = subset_dev;
+    pp.out = out;
+    pp.rows = (long long)nb * n_sel;
+    pp.n_sel = n_sel;
+    pp.F = d.n_filters;
+    pp.N = d.N;
+    pp.n_out = d.n_out;
+    pp.n_cols_pad = d.n_cols_pad;
+    dim3 grid((unsigned)((pp.rows + kPR - 1) / kPR), (unsigned)(d.n_cols_pad / kPC));
+    phase_pair_kernel<<<grid, kPThreads, 0, st>>>(pp);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+// Single-pass dataset entry: within-channel correlations of channel ch_i for the
+// pairs `within_subset` AND cross-channel correlations ch_i x ch_j for `cross_subset`, with the
+// analytic signals of ch_i computed once.  Replaces the two st_model(...) calls and the masking
+// of hdf5_dataset/create_hdf5_dataset.py:421-441.
+extern "C" int tebscat_phase_forward_dual(tebscat_phase_plan* p, const float* x_dev, int64_t B, int n_channels,
+                                          int ch_i, int ch_j, const int32_t* within_subset_host, int n_within,
+                                          const int32_t* cross_subset_host, int n_cross,
+                                          float* out_within_dev, float* out_cross_dev, void* stream) {
+    g_launches = 0;
+    if (!p || B < 0 || (B > 0 && (!x_dev || !out_within_dev || !out_cross_dev))) return fail(TEBSCAT_EINVAL, "null argument");
+    if (n_channels < 2 || ch_i < 0 || ch_i >= n_channels || ch_j < 0 || ch_j >= n_channels || ch_i == ch_j)
+        return fail(TEBSCAT_EINVAL, "the dataset entry point needs two distinct channels in [0,%d)", n_channels);
+    if (!within_subset_host || !cross_subset_host || n_within < 1 || n_cross < 1 ||
+        n_within + n_cross > 2 * p->desc.n_pairs)
+        return fail(TEBSCAT_EINVAL, "bad pair subsets");
+    for (int k = 0; k < n_within; ++k)
+        if (within_subset_host[k] < 0 || within_subset_host[k] >= p->desc.n_pairs) return fail(TEBSCAT_EINVAL, "within subset entry out of range");
+    for (int k = 0; k < n_cross; ++k)
+        if (cross_subset_host[k] < 0 || cross_subset_host[k] >= p->desc.n_pairs) return fail(TEBSCAT_EINVAL, "cross subset entry out of range");
+    if (n_within > p->desc.n_pairs || n_cross > p->desc.n_pairs) return fail(TEBSCAT_EINVAL, "subset larger than the pair list");
+    if (B == 0) return TEBSCAT_OK;
+    std::lock_guard<std::mutex> lock(p->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(p->device));
+    const tebscat_phase_desc& d = p->desc;
+    const size_t per_sample = (size_t)d.n_filters * d.N;
+    const int64_t chunk = B < 96 ? B : 96;
+    if (p->ws_samples < chunk || p->ws2_samples < chunk) {
+        CU(cudaStreamSynchronize(st));
+        if (p->ws_samples < chunk) {
+            cudaFree(p->d_zc);
+            cudaFree(p->d_zp);
+            p->d_zc = p->d_zp = nullptr;
+            CU(cudaMalloc(&p->d_zc, (size_t)chunk * per_sample * sizeof(float2)));
+            CU(cudaMalloc(&p->d_zp, (size_t)chunk * per_sample * sizeof(float2)));
+            p->ws_samples = chunk;
+        }
+        if (p->ws2_samples < chunk) {
+            cudaFree(p->d_zc2);
+            p->d_zc2 = nullptr;
+            CU(cudaMalloc(&p->d_zc2, (size_t)chunk * per_sample * sizeof(float2)));
+            p->ws2_samples = chunk;
+        }
+    }
+    // both subsets live in the plan's subset buffer (n_pairs entries each half)
+    static_assert(sizeof(int32_t) == 4, "");
+    int32_t* sub_w = p->d_subset;
+    int32_t* sub_c = p->d_subset2;
+    CU(cudaMemcpyAsync(sub_w, within_subset_host, n_within * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sub_c, cross_subset_host, n_cross * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const long long x_stride = (long long)n_channels * d.N;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        const float* xb = x_dev + b0 * x_stride;
+        if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_i * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_CART | Z_POLAR, st)) return rc;
+        if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_j * d.N, x_stride, nb, p->d_zc2, p->d_zp, Z_CART, st)) return rc;
+        if (int rc = launch_pairs(p, p->d_zp, p->d_zc, sub_w, n_within, nb, out_within_dev + (size_t)b0 * n_within * d.n_out, st)) return rc;
+        if (int rc = launch_pairs(p, p->d_zp, p->d_zc2, sub_c, n_cross, nb, out_cross_dev + (size_t)b0 * n_cross * d.n_out, st)) return rc;
     }
     return TEBSCAT_OK;
 }

@@ -66,6 +66,9 @@ def load():
     lib.tebscat_phase_forward.restype = ctypes.c_int
     lib.tebscat_phase_forward.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, i32p,
                                           ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.tebscat_phase_forward_dual.restype = ctypes.c_int
+    lib.tebscat_phase_forward_dual.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               i32p, ctypes.c_int, i32p, ctypes.c_int, vp, vp, vp]
     lib.tebscat_scat1d_profile_steps.restype = ctypes.c_int
     lib.tebscat_scat1d_profile_steps.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp]
     lib.tebscat_bench_fp32_peak.restype = ctypes.c_int

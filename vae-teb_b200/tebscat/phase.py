@@ -308,6 +308,56 @@ class KymatioPhaseScattering1D(nn.Module):
             results['autoc_idx'] = self.autoc_idx
         return results
 
+    def forward_dataset(self, x, phase_pairs, cross_pairs, scattering_channel=0, phase_channels=(0, 1)):
+        """Single-pass dataset entry: what ``create_hdf5_dataset.py:418-441`` gets from
+        two ``st_model(...)`` calls plus masking, in one call --
+
+            {'scattering': S(x[:, scattering_channel]),
+             'phase_corr': within-channel correlations of phase_channels[0] for `phase_pairs`,
+             'cross_phase_corr': phase_channels[0] x phase_channels[1] for `cross_pairs`,
+             'autoc_idx': ...}
+
+        with the scattering transform and the analytic signals of phase_channels[0] computed once
+        and only the selected pairs contracted.  `phase_pairs` / `cross_pairs`: boolean masks over
+        the P pairs (e.g. get_optimal_coefficients_for_fhr()['recommendations']) or index arrays."""
+        x = x.to(self.device)
+        if self.tukey_alpha is not None:
+            x = x * self._create_tukey_window(x.shape[-1], self.tukey_alpha, x.device)
+        if x.dim() != 3 or x.shape[1] < 2:
+            raise ValueError("Cross-channel correlation requires at least 2 channels")
+        B, C, N = x.shape
+        if N != self.N:
+            raise ValueError('Input length {} does not match shape={}'.format(N, self.N))
+        ch_i, ch_j = int(phase_channels[0]), int(phase_channels[1])
+        if len(phase_channels) != 2 or max(ch_i, ch_j) >= C or ch_i == ch_j:
+            raise ValueError("Invalid phase_channels for cross-channel correlation")
+        if scattering_channel >= C:
+            raise ValueError(f"scattering_channel {scattering_channel} >= {C}")
+
+        def as_index(sel):
+            a = np.asarray(sel.cpu() if torch.is_tensor(sel) else sel).reshape(-1)
+            return (np.nonzero(a)[0] if a.dtype == np.bool_ else a).astype(np.int32)
+
+        sub_w, sub_c = np.ascontiguousarray(as_index(phase_pairs)), np.ascontiguousarray(as_index(cross_pairs))
+        if sub_w.size == 0 or sub_c.size == 0:
+            raise ValueError('forward_dataset needs at least one within-channel and one cross-channel pair')
+        if x.dtype is not torch.float32:
+            raise TypeError('Input and filter must be of the same dtype.')
+        x = x.contiguous()
+        S, _ = self.scattering(x[:, scattering_channel, :].contiguous())
+        index = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        plan = self._dev_plan(index)
+        n_out = self._plan.n_out
+        within = torch.empty((B, sub_w.size, n_out), dtype=torch.float32, device=x.device)
+        cross = torch.empty((B, sub_c.size, n_out), dtype=torch.float32, device=x.device)
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        rc = _lib.load().tebscat_phase_forward_dual(
+            plan.handle, x.data_ptr(), B, C, ch_i, ch_j, sub_w.ctypes.data_as(i32p), int(sub_w.size),
+            sub_c.ctypes.data_as(i32p), int(sub_c.size), within.data_ptr(), cross.data_ptr(),
+            torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(rc)
+        return {'scattering': S, 'phase_corr': within, 'cross_phase_corr': cross, 'autoc_idx': self.autoc_idx}
+
     def meta(self):
         return self.scattering.meta()
 
