@@ -43,6 +43,7 @@ CONFIGS = {
     'P': (11, 4, 16, 5760, 1, 2),       # production dataset config (create_hdf5_dataset.py:360)
     'S': (4, 4, 16, 1000, 2, 4),        # small ragged-length config
     'T': (5, 2, 8, 700, 2, 3),          # T < 2**J
+    'O': (5, 4, 32, 1200, 2, 2, 1),     # oversampling = 1
 }
 
 
@@ -51,8 +52,9 @@ def digest(a):
 
 
 def scat_fixture(name):
-    J, Q, T, N, max_order, B = CONFIGS[name]
-    S = ScatteringTorch1D(J, N, Q, max_order=max_order, T=T)
+    J, Q, T, N, max_order, B = CONFIGS[name][:6]
+    oversampling = CONFIGS[name][6] if len(CONFIGS[name]) > 6 else 0
+    S = ScatteringTorch1D(J, N, Q, max_order=max_order, T=T, oversampling=oversampling)
     x = torch.cat([ctg_batch(B, N, seed=1234)[:, 0], randn_batch(B, N, 1, seed=4321)[:, 0]], 0)
     with torch.no_grad():
         out, _ = S(x)
@@ -63,7 +65,7 @@ def scat_fixture(name):
         filt += [np.asarray(a) for a in p['levels']]
     np.savez_compressed(
         os.path.join(OUT, 'scat_%s.npz' % name),
-        J=J, Q=Q, T=T, N=N, max_order=max_order, x=x.numpy(), S=out.numpy(),
+        J=J, Q=Q, T=T, N=N, max_order=max_order, oversampling=oversampling, x=x.numpy(), S=out.numpy(),
         J_pad=S.J_pad, pad_left=S.pad_left, pad_right=S.pad_right,
         ind_start=np.array([S.ind_start[j] for j in range(J + 1)]),
         ind_end=np.array([S.ind_end[j] for j in range(J + 1)]),
@@ -82,7 +84,7 @@ def scat_fixture(name):
 
 
 def phase_fixture(name, B):
-    J, Q, T, N, max_order, _ = CONFIGS[name]
+    J, Q, T, N, max_order, _ = CONFIGS[name][:6]
     m = kps.KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cpu'),
                                      max_order=max_order)
     x = torch.cat([ctg_batch(B, N, seed=77), randn_batch(B, N, 2, seed=78)], 0)

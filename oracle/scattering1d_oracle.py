@@ -1,7 +1,7 @@
 """ORACLE (test infrastructure only -- never imported by the product path).
 
 numpy restatement of the reference's 1-D scattering cascade for
-``average=True, oversampling=0, vectorize=True, out_type='array'``:
+``average=True, vectorize=True, out_type='array'`` (any ``oversampling``):
 
   kymatio/kymatio/scattering1d/core/scattering1d.py:269-399   (cascade, ordering)
   kymatio/kymatio/scattering1d/backend/torch_backend.py:18-128 (pad, rfft, ifft,
@@ -40,8 +40,9 @@ def subsample_fourier(x_f, k):
 
 
 class ScatteringOracle:
-    def __init__(self, J, N, Q, T, max_order=2, cdtype=np.complex128):
+    def __init__(self, J, N, Q, T, max_order=2, cdtype=np.complex128, oversampling=0):
         self.J, self.N, self.Q, self.T, self.max_order = J, N, Q, T, max_order
+        self.oversampling = oversampling
         self.cdtype = cdtype
         self.rdtype = np.float64 if cdtype == np.complex128 else np.float32
         self.geo = fo.geometry(N, J, Q, T)
@@ -65,21 +66,22 @@ class ScatteringOracle:
         x = x.reshape(-1, x.shape[-1]).astype(self.rdtype)
         g = self.geo
         log2_T = math.floor(math.log2(self.T))
+        os_ = self.oversampling
         i0, i1 = g['ind_start'], g['ind_end']
         out = []
 
         U0_f = self._fft(reflect_pad(x, g['pad_left'], g['pad_right']))          # :278-280
-        k0 = log2_T                                                            # :285
+        k0 = max(log2_T - os_, 0)                                              # :285
         S0 = self._ifft(subsample_fourier(U0_f * self.phi[0], 2 ** k0)).real   # :288-290
         out.append(S0[:, i0[k0]:i1[k0]])                                       # :292
         order2 = []
         for n1, p1 in enumerate(self.psi1):                                    # :300
             j1 = p1['j']
-            k1 = max(min(j1, log2_T), 0)                                       # :304
+            k1 = max(min(j1 - os_, log2_T - os_), 0)                           # :304
             assert p1['xi'] < 0.5 / (2 ** k1)                                  # :306
             U1 = np.abs(self._ifft(subsample_fourier(U0_f * p1['levels'][0], 2 ** k1)))   # :307-315
             U1_f = self._fft(U1)                                               # :318
-            k1_J = max(log2_T - k1, 0)                                         # :322
+            k1_J = max(log2_T - k1 - os_, 0)                                   # :322
             S1 = self._ifft(subsample_fourier(U1_f * self.phi[k1], 2 ** k1_J)).real       # :323-325
             out.append(S1[:, i0[k1_J + k1]:i1[k1_J + k1]])                     # :327
             if self.max_order == 2:
@@ -87,10 +89,10 @@ class ScatteringOracle:
                     j2 = p2['j']
                     if j2 > j1:
                         assert p2['xi'] < p1['xi']                             # :341
-                        k2 = max(min(j2 - k1, log2_T - k1), 0)                 # :344-345
+                        k2 = max(min(j2 - k1 - os_, log2_T - k1 - os_), 0)     # :344-345
                         U2 = np.abs(self._ifft(subsample_fourier(U1_f * p2['levels'][k1], 2 ** k2)))
                         U2_f = self._fft(U2)                                   # :355
-                        k2_J = max(log2_T - k2 - k1, 0)                        # :358
+                        k2_J = max(log2_T - k2 - k1 - os_, 0)                  # :358
                         S2 = self._ifft(subsample_fourier(U2_f * self.phi[k1 + k2], 2 ** k2_J)).real
                         order2.append(S2[:, i0[k1 + k2 + k2_J]:i1[k1 + k2 + k2_J]])   # :364
         out.extend(order2)                                                     # :372-375

@@ -15,7 +15,9 @@ CONFIGS = {
     'S': (4, 1000, 4, 16, 2),
     'T': (5, 700, 2, 8, 2),
     'K': (6, 512, 16, 64, 2),
+    'O': (5, 1200, 4, 32, 2),           # golden fixture with oversampling = 1
 }
+OVERSAMPLING = {'O': 1}
 
 
 def rel_l2(a, b, axis=None):

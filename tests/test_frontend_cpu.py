@@ -108,9 +108,6 @@ def test_constructor_errors_and_options():
     with pytest.raises(RuntimeError) as ve:
         S(x)
     assert "must be one of 'array' or 'list'" in ve.value.args[0]
-    S.out_type = 'list'
-    with pytest.raises(NotImplementedError):
-        S(x)
     S.out_type = 'array'
     with pytest.raises(TypeError) as ve:
         S(None)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import CONFIGS, GOLDEN, path_tolerance, rel_l2
+from helpers import CONFIGS, GOLDEN, OVERSAMPLING, path_tolerance, rel_l2
 from oracle.scattering1d_oracle import ScatteringOracle
 
 pytestmark = pytest.mark.gpu
@@ -19,7 +19,7 @@ def module_of(name):
     from tebscat import Scattering1D
     if name not in _mods:
         J, N, Q, T, mo = CONFIGS[name]
-        _mods[name] = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+        _mods[name] = Scattering1D(J, N, Q, max_order=mo, T=T, oversampling=OVERSAMPLING.get(name, 0)).cuda()
     return _mods[name]
 
 
@@ -56,12 +56,12 @@ def test_reference_known_answer_fixture():
     assert rel_l2(out, d['Sx'], axis=-1).max() < 1e-5
 
 
-@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T'])
+@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T', 'O'])
 def test_golden_reference_outputs(name):
     d = np.load(os.path.join(GOLDEN, 'scat_%s.npz' % name))
     out, _ = gpu_forward(name, d['x'])
     J, N, Q, T, mo = CONFIGS[name]
-    ref64 = ScatteringOracle(J, N, Q, T, mo)(d['x'])
+    ref64 = ScatteringOracle(J, N, Q, T, mo, oversampling=OVERSAMPLING.get(name, 0))(d['x'])
     tol = np.maximum(1e-5 * np.linalg.norm(ref64, axis=-1),
                      4.0 * np.linalg.norm(d['S'].astype(np.float64) - ref64, axis=-1))
     assert np.all(np.linalg.norm(out.astype(np.float64) - ref64, axis=-1) <= tol)
@@ -166,3 +166,27 @@ def test_other_configurations(cfg):
     nr = np.linalg.norm(ref, axis=-1)
     err = np.linalg.norm(out - ref, axis=-1)
     assert np.all(err <= 1e-5 * nr + 1e-10 * nr.max()), float((err / nr).max())
+
+
+def test_output_conventions_list_and_dict():
+    """out_type='list' and vectorize=False (core/scattering1d.py:379-384,
+    frontend/torch_frontend.py:240-253; test_torch_scattering1d.py:195-243 test_coordinates):
+    same numbers as the vectorised array, keyed / ordered by meta()['key']."""
+    from tebscat import Scattering1D
+    S = Scattering1D(4, 700, 2, T=16).cuda()
+    x = torch.randn(3, 2, 700, device='cuda')
+    arr, _ = S(x)
+    meta = S.meta()
+    S.out_type = 'list'
+    lst, _ = S(x)
+    assert isinstance(lst, list) and len(lst) == arr.shape[-2] and set(lst[0]) == {'coef', 'j'}
+    for c, item in enumerate(lst):
+        assert item['coef'].shape == (3, 2, arr.shape[-1]) and torch.equal(item['coef'], arr[..., c, :])
+        assert len(item['j']) == meta['order'][c]
+    S.out_type = 'array'
+    S.vectorize = False
+    with pytest.warns(DeprecationWarning):
+        dct, _ = S(x)
+    assert list(dct.keys()) == meta['key']
+    for c, k in enumerate(meta['key']):
+        assert dct[k].shape == (3, 2, 1, arr.shape[-1]) and torch.equal(dct[k][..., 0, :], arr[..., c, :])

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import CONFIGS, GOLDEN, emu_available, emu_forward, path_tolerance, rel_l2
+from helpers import CONFIGS, GOLDEN, OVERSAMPLING, emu_available, emu_forward, path_tolerance, rel_l2
 from oracle.scattering1d_oracle import ScatteringOracle
 from tebscat.schedule import (OP_FFT, OP_LOAD, OP_MULFOLD, OP_STOREB, OP_TINY, SMEM_BYTES_MAX, TASK_INTS, TW_SLOTS,
                               bitrev_indices, build_plan, radix_split)
@@ -17,7 +17,7 @@ def plan_of(name, **kw):
     key = (name, tuple(sorted(kw.items())))
     if key not in _plans:
         J, N, Q, T, mo = CONFIGS[name]
-        _plans[key] = build_plan(J, N, Q, T, mo, **kw)
+        _plans[key] = build_plan(J, N, Q, T, mo, oversampling=OVERSAMPLING.get(name, 0), **kw)
     return _plans[key]
 
 
@@ -103,12 +103,12 @@ def test_emulated_kernel_matches_reference_kat():
 
 
 @pytest.mark.skipif(not emu_available(), reason='host emulator not built')
-@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T'])
+@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T', 'O'])
 def test_emulated_kernel_matches_golden_reference_outputs(name):
     d = np.load(os.path.join(GOLDEN, 'scat_%s.npz' % name))
     out = emu_forward(plan_of(name), d['x']).astype(np.float64)
     J, N, Q, T, mo = CONFIGS[name]
-    ref64 = ScatteringOracle(J, N, Q, T, mo)(d['x'])
+    ref64 = ScatteringOracle(J, N, Q, T, mo, oversampling=OVERSAMPLING.get(name, 0))(d['x'])
     tol = np.maximum(1e-5 * np.linalg.norm(ref64, axis=-1),
                      4.0 * np.linalg.norm(d['S'].astype(np.float64) - ref64, axis=-1))
     assert np.all(np.linalg.norm(out - ref64, axis=-1) <= tol)

@@ -331,16 +331,18 @@ class _Allocator:
 
 
 def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int, arena: _Arena,
-                 batch_slots: int = BATCH_SLOTS):
+                 batch_slots: int = BATCH_SLOTS, oversampling: int = 0):
     """The cascade as a forest of chains of batched tasks, in the reference's channel order."""
     n = geo.J_pad
     log2_T = int(math.floor(math.log2(T)))
-    lf = n - log2_T                                       # log2 of the final (output-rate) length
+    os_ = int(oversampling)
+    kf = max(log2_T - os_, 0)                             # final subsampling (:285, :322, :358)
+    lf = n - kf                                           # log2 of the final (output-rate) length
     if lf < 0:
         raise ValueError('T is larger than the padded support')
     if lf < 1:
         raise NotImplementedError('output-rate length below 2 samples is not supported')
-    i0, i1 = geo.ind_start[log2_T], geo.ind_end[log2_T]
+    i0, i1 = geo.ind_start[kf], geo.ind_end[kf]
     n_out = i1 - i0
 
     phi_off = [arena.add(a) for a in bank.phi.levels]
@@ -370,7 +372,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
     # first order, batched by subsampling k1 (:300-318)
     groups: Dict[int, List[int]] = {}
     for n1, p1 in enumerate(bank.psi1):
-        k1 = max(min(p1.j, log2_T), 0)                                 # :304
+        k1 = max(min(p1.j - os_, log2_T - os_), 0)                     # :304
         if not p1.xi < 0.5 / (2 ** k1):
             raise AssertionError('psi1 aliasing assertion of the reference violated')
         groups.setdefault(k1, []).append(n1)
@@ -399,7 +401,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
                     if p2.j > p1.j:
                         if not p2.xi < p1.xi:
                             raise AssertionError('psi2 ordering assertion of the reference violated')
-                        k2 = max(min(p2.j - k1, log2_T - k1), 0)       # :344-345
+                        k2 = max(min(p2.j - k1 - os_, log2_T - k1 - os_), 0)   # :344-345
                         kids.setdefault(k2, []).append((i, n1, n2))
             for k2 in sorted(kids):
                 l2 = l1 - k2
@@ -745,7 +747,8 @@ def emit(steps) -> Tuple[np.ndarray, np.ndarray]:
             np.asarray(ranges, dtype=np.int32).reshape(-1, 2))
 
 
-def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int = 64) -> ScatPlan:
+def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int = 64,
+               oversampling: int = 0) -> ScatPlan:
     Q1 = fbk._as_Q1(Q)
     geo = fbk.build_geometry(N, J, Q1, T)
     if geo.J_pad > LOG2_NP_MAX:
@@ -759,7 +762,7 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     last_err = None
     for batch_slots, pool_slots in ((BATCH_SLOTS, POOL_SLOTS), (4096, 2048), (2048, 1024), (1024, 512), (512, 256)):
         arena = _Arena()
-        chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots)
+        chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling)
         try:
             steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel,
                                                        pool_slots=pool_slots)

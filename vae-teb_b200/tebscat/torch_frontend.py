@@ -12,8 +12,9 @@ behind it.
 Differences from the fork, all on the lenient side:
  * ``T=None`` means ``2**J`` (the fork crashes, SURVEY.md item 2);
  * ``Q`` may be an int or a ``(Q1, 1)`` tuple (the fork takes ints only);
- * options outside the fused fast path (``average=False``, ``out_type='list'``,
-   ``vectorize=False``, ``oversampling>0``) raise ``NotImplementedError``.
+ * ``average=False`` (un-averaged U1/U2 outputs) raises ``NotImplementedError``; ``oversampling``,
+   ``out_type='list'`` and ``vectorize=False`` are supported (the latter two are views of the
+   fused array result).
 """
 import ctypes
 import math
@@ -166,9 +167,10 @@ class Scattering1D(nn.Module):
 
     # ---- plan handling -------------------------------------------------------------
     def _schedule(self):
-        key = (self.J, self.N, self._Q1, self.T, self.max_order)
+        key = (self.J, self.N, self._Q1, self.T, self.max_order, int(self.oversampling))
         if self._sched is None or self._sched[0] != key:
-            self._sched = (key, build_plan(self.J, self.N, self._Q1, self.T, self.max_order))
+            self._sched = (key, build_plan(self.J, self.N, self._Q1, self.T, self.max_order,
+                                           oversampling=int(self.oversampling)))
             self._plans = {}
         return self._sched[1]
 
@@ -190,11 +192,11 @@ class Scattering1D(nn.Module):
             warnings.warn("The vectorize option is deprecated and will be "
                           "removed in version 0.3. Please set "
                           "out_type='list' for equivalent functionality.", DeprecationWarning)
-        if (not self.average) or self.out_type != 'array' or (not self.vectorize) or self.oversampling != 0:
-            raise NotImplementedError(
-                'the fused CUDA path implements average=True, out_type=\'array\', vectorize=True, '
-                'oversampling=0 (got average=%r out_type=%r vectorize=%r oversampling=%r); '
-                'there is no fallback path' % (self.average, self.out_type, self.vectorize, self.oversampling))
+        if not self.average:
+            raise NotImplementedError('the fused CUDA path implements average=True only '
+                                      '(un-averaged U1/U2 outputs are not built); there is no fallback path')
+        if int(self.oversampling) < 0:
+            raise ValueError('oversampling must be >= 0')
 
     # ---- forward ----------------------------------------------------------------------
     def forward(self, x):
@@ -227,7 +229,20 @@ class Scattering1D(nn.Module):
         rc = _lib.load().tebscat_scat1d_forward(plan.handle, x2.data_ptr(), B, S.data_ptr(), stream)
         _lib.check(rc)
         P = S.view(B, 1, C, n_out)                       # core/scattering1d.py:395-397: P is S before the reshape
-        return [S.reshape(batch_shape + (C, n_out)), P]
+        if self.out_type == 'array' and self.vectorize:
+            return [S.reshape(batch_shape + (C, n_out)), P]
+        # the other output conventions are views of the same fused result (core :379-384,
+        # torch_frontend.py:240-253); in the reference P aliases S in these cases too
+        meta = self.meta()
+        if self.out_type == 'array':                     # vectorize=False: dict keyed by the filter indices
+            out = {meta['key'][c]: S[:, c:c + 1, :].reshape(batch_shape + (1, n_out)) for c in range(C)}
+            return [out, out]
+        out = []                                         # out_type == 'list'
+        for c in range(C):
+            key = meta['key'][c]
+            j = tuple(int(v) for v in meta['j'][c][:len(key)])
+            out.append({'coef': S[:, c, :].reshape(batch_shape + (n_out,)), 'j': j})
+        return [out, out]
 
     def scattering_host(self, x, out=None, device=0):
         """End-to-end path on HOST tensors: pinned staging, chunked H2D / kernel / D2H
