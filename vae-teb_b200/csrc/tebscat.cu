@@ -437,8 +437,8 @@ extern "C" int tebscat_scat1d_forward_host(tebscat_plan* p, const float* x_host,
 // contracts it with the precomputed operator of _apply_phi_filter (:233-273)
 //     out[n] = Re sum_t c(t) G[t, n],
 // G = reflect-pad -> FFT(Np) -> phi -> keep bins [0, Np/dec) -> iFFT(Np/dec) -> slice,
-// built once on the host in float64.  The contraction is a register-tiled FP32 GEMM
-// (128 (sample, pair) rows x 80 output samples per CTA, K = time in slabs of 16); rows never
+// built once on the host in float64.  The contraction is a GEMM (128 (sample, pair) rows x 80
+// output samples per CTA, K = time in slabs of 16) on the tensor cores in 3xTF32; rows never
 // materialise in memory -- the reference materialises (B, P, N) complex64 three times.
 
 constexpr int kPR = 128;        // rows per CTA
@@ -472,11 +472,44 @@ __device__ __forceinline__ float2 accelerated_product(float2 pz, float2 zj, floa
     return make_float2(fmaf(ar, zj.x, ai * zj.y), fmaf(ai, zj.x, -ar * zj.y));
 }
 
+// ---- tensor-core contraction ------------------------------------------------------------
+// out = A' B' with A' = [Re c, -Im c] (rows x 2N) and B' = [Re G; Im G] (2N x n_out) is a real
+// GEMM.  It runs on the tensor cores as 3xTF32: every fp32 operand is split into a TF32 head and a
+// TF32 tail, and hi*hi + lo*hi + hi*lo is accumulated in fp32 (relative error ~2^-21 per product,
+// i.e. fp32-class accuracy; a plain TF32 product would be 1e-3).  mma.sync.m16n8k8 issues at
+// 1 instruction/cycle/SM on B200 (tools/micro/mma_rate.cu): 991 MAC/cycle/SM, 330 after the
+// three-way split, vs 128 FMA/cycle/SM on the FP32 pipe -- and the phase-acceleration math of
+// the other resident CTA overlaps it on the FP32 pipe.
+// Layout of the work inside a CTA (128 rows x 80 columns, 8 warps, K in slabs of 16 samples):
+//  * warp w owns rows 16w..16w+15.  Its A' fragments never touch shared memory: with the K
+//    index of an 8-wide MMA step ordered [Re c(t..t+3), -Im c(t..t+3)], lane (g, tq) needs exactly
+//    c(row g, t+tq) and c(row g+8, t+tq) -- it computes those two products itself;
+//  * B' is staged once per slab in "fragment-major" order, already split into TF32 head and
+//    tail: one 128-bit load gives a lane (b0, b1) = (Re G, Im G)[t+tq][8n+g] as (hi, hi, lo, lo);
+//  * the MMAs of a slab accumulate into a zeroed fragment that is then added to the running
+//    sum with ordinary fp32 adds: the tensor core's accumulator truncates, and over the
+//    K = 2N = 9600 of a whole row that bias would reach 5e-5.
+constexpr int kBLane = 44;      // words per lane slot of the B' slab (10 tiles x 4 + 4 pad: conflict free)
+constexpr size_t kPairSmem = (size_t)(kPK / 4) * 32 * kBLane * sizeof(uint32_t) + kPR * (2 * sizeof(int32_t) + sizeof(float));
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    const float r = v - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __global__ void __launch_bounds__(kPThreads, 2) phase_pair_kernel(const PairParams p) {
-    __shared__ __align__(16) float2 sA[kPK][kPR + 2];
-    __shared__ __align__(16) float2 sG[kPK][kPC];
-    __shared__ int32_t s_zp[kPR], s_zc[kPR];
-    __shared__ float s_pw[kPR];
+    extern __shared__ __align__(16) uint32_t psm[];
+    uint32_t* sB = psm;                                 // [ks][lane][kBLane]
+    int32_t* s_zp = reinterpret_cast<int32_t*>(sB + (kPK / 4) * 32 * kBLane);
+    int32_t* s_zc = s_zp + kPR;
+    float* s_pw = reinterpret_cast<float*>(s_zc + kPR);
 
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kPR;
@@ -498,63 +531,76 @@ __global__ void __launch_bounds__(kPThreads, 2) phase_pair_kernel(const PairPara
     }
     __syncthreads();
 
-    const int cg = tid & 15, rg = tid >> 4;
-    float acc[8][5];
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+    // the two rows whose products this lane generates
+    const int zp0 = s_zp[warp * 16 + g], zc0 = s_zc[warp * 16 + g];
+    const int zp1 = s_zp[warp * 16 + g + 8], zc1 = s_zc[warp * 16 + g + 8];
+    const float pw0 = s_pw[warp * 16 + g], pw1 = s_pw[warp * 16 + g + 8];
+
+    float total[kPC / 8][4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int n = 0; n < kPC / 8; ++n)
 #pragma unroll
-        for (int c = 0; c < 5; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < 4; ++c) total[n][c] = 0.f;
 
     for (int t0 = 0; t0 < p.N; t0 += kPK) {
-        // A slab: 128 rows x 16 samples, 8 per thread, 16 consecutive samples of a row per half-warp
-#pragma unroll
-        for (int pass = 0; pass < kPR * kPK / kPThreads; ++pass) {
-            const int e = tid + pass * kPThreads;
-            const int tl = e & (kPK - 1), row = e >> 4;
-            const int t = t0 + tl;
-            float2 a = make_float2(0.f, 0.f);
-            const int zo = s_zp[row];
-            if (zo >= 0 && t < p.N) {
-                const float2 c = accelerated_product(__ldg(p.zp + zo + t), __ldg(p.zc + s_zc[row] + t), s_pw[row]);
-                a = make_float2(c.x, -c.y);             // Re(c G) = c.x G.x - c.y G.y
-            }
-            sA[tl][row] = a;
-        }
+        // stage B': G[t0 + tl][col0 + col] -> slot (ks = tl/4, tq = tl%4, g = col%8), tile n = col/8
 #pragma unroll
         for (int pass = 0; pass < kPK * kPC / kPThreads; ++pass) {
             const int e = tid + pass * kPThreads;
             const int tl = e / kPC, col = e - tl * kPC;
             const int t = t0 + tl;
-            sG[tl][col] = (t < p.N) ? __ldg(p.G + (long long)t * p.n_cols_pad + col0 + col) : make_float2(0.f, 0.f);
+            const float2 gv = (t < p.N) ? __ldg(p.G + (long long)t * p.n_cols_pad + col0 + col) : make_float2(0.f, 0.f);
+            uint4 w;
+            split_tf32(gv.x, w.x, w.z);
+            split_tf32(gv.y, w.y, w.w);
+            *reinterpret_cast<uint4*>(sB + ((tl >> 2) * 32 + (col & 7) * 4 + (tl & 3)) * kBLane + (col >> 3) * 4) = w;
         }
         __syncthreads();
-#pragma unroll 4
-        for (int tl = 0; tl < kPK; ++tl) {
-            float2 a[8], g[5];
-            const float4* ap = reinterpret_cast<const float4*>(&sA[tl][rg * 8]);
+        float acc[kPC / 8][4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float4 v = ap[r];
-                a[2 * r] = make_float2(v.x, v.y);
-                a[2 * r + 1] = make_float2(v.z, v.w);
+        for (int n = 0; n < kPC / 8; ++n)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[n][c] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < kPK / 4; ++ks) {
+            const int t = t0 + 4 * ks + tq;
+            float2 c0 = make_float2(0.f, 0.f), c1 = make_float2(0.f, 0.f);
+            if (t < p.N) {
+                if (zp0 >= 0) c0 = accelerated_product(__ldg(p.zp + zp0 + t), __ldg(p.zc + zc0 + t), pw0);
+                if (zp1 >= 0) c1 = accelerated_product(__ldg(p.zp + zp1 + t), __ldg(p.zc + zc1 + t), pw1);
             }
+            // A' fragment: a0 = (row g, Re), a1 = (row g+8, Re), a2 = (row g, -Im), a3 = (row g+8, -Im)
+            uint32_t a_hi[4], a_lo[4];
+            split_tf32(c0.x, a_hi[0], a_lo[0]);
+            split_tf32(c1.x, a_hi[1], a_lo[1]);
+            split_tf32(-c0.y, a_hi[2], a_lo[2]);
+            split_tf32(-c1.y, a_hi[3], a_lo[3]);
+            const uint4* bq = reinterpret_cast<const uint4*>(sB + (ks * 32 + lane) * kBLane);
 #pragma unroll
-            for (int c = 0; c < 5; ++c) g[c] = sG[tl][cg + 16 * c];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < 5; ++c) acc[r][c] = fmaf(a[r].x, g[c].x, fmaf(a[r].y, g[c].y, acc[r][c]));
+            for (int n = 0; n < kPC / 8; ++n) {
+                const uint4 b = bq[n];                  // (hi Re, hi Im, lo Re, lo Im) of G[t][8n + g]
+                mma_tf32(acc[n], a_lo, b.x, b.y);
+                mma_tf32(acc[n], a_hi, b.z, b.w);
+                mma_tf32(acc[n], a_hi, b.x, b.y);
+            }
         }
+#pragma unroll
+        for (int n = 0; n < kPC / 8; ++n)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) total[n][c] += acc[n][c];
         __syncthreads();
     }
+    // accumulator fragment: rows g, g+8 of the warp's 16; columns 8n + 2*tq, +1
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const long long row = row0 + rg * 8 + r;
+    for (int half = 0; half < 2; ++half) {
+        const long long row = row0 + warp * 16 + g + 8 * half;
         if (row >= p.rows) continue;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const int col = col0 + cg + 16 * c;
-            if (col < p.n_out) p.out[row * p.n_out + col] = acc[r][c];
+        for (int n = 0; n < kPC / 8; ++n) {
+            const int col = col0 + 8 * n + 2 * tq;
+            if (col < p.n_out) p.out[row * p.n_out + col] = total[n][2 * half];
+            if (col + 1 < p.n_out) p.out[row * p.n_out + col + 1] = total[n][2 * half + 1];
         }
     }
 }
@@ -604,6 +650,7 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
         if (i_idx[k] < 0 || i_idx[k] >= d->n_filters || j_idx[k] < 0 || j_idx[k] >= d->n_filters)
             return fail(TEBSCAT_EINVAL, "pair %d references a filter outside [0,%d)", k, d->n_filters);
     CU(cudaSetDevice(stage_a->device));
+    CU(cudaFuncSetAttribute(phase_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
     tebscat_phase_plan* p = new tebscat_phase_plan();
     p->desc = *d;
     p->stage_a = stage_a;
@@ -712,7 +759,7 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
         pp.n_cols_pad = d.n_cols_pad;
         if (apply_low_pass) {
             dim3 grid((unsigned)((pp.rows + kPR - 1) / kPR), (unsigned)(d.n_cols_pad / kPC));
-            phase_pair_kernel<<<grid, kPThreads, 0, st>>>(pp);
+            phase_pair_kernel<<<grid, kPThreads, kPairSmem, st>>>(pp);
         } else {
             phase_product_kernel<<<1184, 256, 0, st>>>(pp);
         }
@@ -741,7 +788,7 @@ static int launch_pairs(const tebscat_phase_plan* p, const float2* zp, const flo
     pp.n_out = d.n_out;
     pp.n_cols_pad = d.n_cols_pad;
     dim3 grid((unsigned)((pp.rows + kPR - 1) / kPR), (unsigned)(d.n_cols_pad / kPC));
-    phase_pair_kernel<<<grid, kPThreads, 0, st>>>(pp);
+    phase_pair_kernel<<<grid, kPThreads, kPairSmem, st>>>(pp);
     CU(cudaGetLastError());
     ++g_launches;
     return TEBSCAT_OK;
