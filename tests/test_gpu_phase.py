@@ -136,12 +136,12 @@ def test_forward_validation_errors():
 
 
 def test_batch_chunking_is_consistent():
-    """More samples than one workspace chunk (96): rows must not depend on their position."""
+    """More samples than one workspace chunk (296): rows must not depend on their position."""
     m = module_of('S')
     base = torch.randn(5, 2, 1000, device='cuda')
-    x = base.repeat(41, 1, 1)                                        # 205 samples
+    x = base.repeat(130, 1, 1)                                       # 650 samples: three chunks
     out = m(x, compute_phase=False, compute_cross_phase=True)['cross_phase_corr']
-    assert torch.equal(out[:5], out[-5:]) and torch.equal(out[:5], out[100:105])
+    assert torch.equal(out[:5], out[-5:]) and torch.equal(out[:5], out[300:305])
 
 
 def test_single_pass_dataset_entry_matches_two_calls():

@@ -543,6 +543,18 @@ __global__ void __launch_bounds__(kPThreads, 2) phase_pair_kernel(const PairPara
 #pragma unroll
         for (int c = 0; c < 4; ++c) total[n][c] = 0.f;
 
+    // raw inputs of the products, fetched one MMA step ahead (software pipeline: the loads of
+    // step k+1 are in flight while the 30 MMAs of step k issue)
+    float2 r_zp0, r_zc0, r_zp1, r_zc1;
+    auto fetch = [&](int t) {
+        const bool in = t < p.N;
+        r_zp0 = (in && zp0 >= 0) ? __ldg(p.zp + zp0 + t) : make_float2(0.f, 0.f);
+        r_zc0 = (in && zp0 >= 0) ? __ldg(p.zc + zc0 + t) : make_float2(0.f, 0.f);
+        r_zp1 = (in && zp1 >= 0) ? __ldg(p.zp + zp1 + t) : make_float2(0.f, 0.f);
+        r_zc1 = (in && zp1 >= 0) ? __ldg(p.zc + zc1 + t) : make_float2(0.f, 0.f);
+    };
+    fetch(tq);
+
     for (int t0 = 0; t0 < p.N; t0 += kPK) {
         // stage B': G[t0 + tl][col0 + col] -> slot (ks = tl/4, tq = tl%4, g = col%8), tile n = col/8
 #pragma unroll
@@ -564,12 +576,10 @@ __global__ void __launch_bounds__(kPThreads, 2) phase_pair_kernel(const PairPara
             for (int c = 0; c < 4; ++c) acc[n][c] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < kPK / 4; ++ks) {
-            const int t = t0 + 4 * ks + tq;
-            float2 c0 = make_float2(0.f, 0.f), c1 = make_float2(0.f, 0.f);
-            if (t < p.N) {
-                if (zp0 >= 0) c0 = accelerated_product(__ldg(p.zp + zp0 + t), __ldg(p.zc + zc0 + t), pw0);
-                if (zp1 >= 0) c1 = accelerated_product(__ldg(p.zp + zp1 + t), __ldg(p.zc + zc1 + t), pw1);
-            }
+            // zero magnitude (padding rows / samples beyond N) gives a zero product
+            const float2 c0 = accelerated_product(r_zp0, r_zc0, pw0);
+            const float2 c1 = accelerated_product(r_zp1, r_zc1, pw1);
+            fetch(t0 + 4 * (ks + 1) + tq);              // next step (possibly of the next slab)
             // A' fragment: a0 = (row g, Re), a1 = (row g+8, Re), a2 = (row g, -Im), a3 = (row g+8, -Im)
             uint32_t a_hi[4], a_lo[4];
             split_tf32(c0.x, a_hi[0], a_lo[0]);
@@ -618,6 +628,10 @@ __global__ void phase_product_kernel(const PairParams p) {
         p.out[e] = c.x;
     }
 }
+
+// samples per workspace chunk: two stage-A jobs per SM and launch (148 SMs), 0.86 GB of
+// analytic signals at N=4800, F=38
+constexpr int64_t kPhaseChunk = 296;
 
 struct tebscat_phase_plan {
     tebscat_phase_desc desc;
@@ -720,7 +734,7 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
     const tebscat_phase_desc& d = p->desc;
     const int n_sel = pair_subset_host ? n_subset : d.n_pairs;
     const size_t per_sample = (size_t)d.n_filters * d.N;
-    const int64_t chunk = B < 96 ? B : 96;                 // 96 samples of workspace: L2-sized at N=4800, F=38
+    const int64_t chunk = B < kPhaseChunk ? B : kPhaseChunk;
     if (p->ws_samples < chunk) {
         CU(cudaStreamSynchronize(st));
         cudaFree(p->d_zc);
@@ -820,7 +834,7 @@ extern "C" int tebscat_phase_forward_dual(tebscat_phase_plan* p, const float* x_
     CU(cudaSetDevice(p->device));
     const tebscat_phase_desc& d = p->desc;
     const size_t per_sample = (size_t)d.n_filters * d.N;
-    const int64_t chunk = B < 96 ? B : 96;
+    const int64_t chunk = B < kPhaseChunk ? B : kPhaseChunk;
     if (p->ws_samples < chunk || p->ws2_samples < chunk) {
         CU(cudaStreamSynchronize(st));
         if (p->ws_samples < chunk) {
