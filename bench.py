@@ -32,6 +32,18 @@ BYTES_PER_SIGNAL = N * 4 + 126 * 75 * 4   # 57 000 B algorithmic
 FLOPS_PER_SIGNAL = 31.56e6                # reference-equivalent FFT flops
 
 
+def measured_traffic(n_sig):
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu capture (profiles/)."""
+    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    if t.get('signals_per_launch') != n_sig:
+        return None
+    return t['dram_bytes_read'] + t['dram_bytes_write']
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -231,7 +243,8 @@ def run_gpu(args):
                     'd2h_bytes_per_step': n_sig * C * n_out * 4},
             'gpu_launches': launches,
             'roofline': {'bound': 'hbm', 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                         'frac': achieved_gbs / hbm_peak, 'traffic': measured_traffic(n_sig),
+                         'algorithmic_bytes': n_sig * BYTES_PER_SIGNAL, 'peak_source': peak_src,
                          'kernel': 'scat1d_kernel', 'kernel_ms': kernel_ms,
                          'note': 'the fused cascade is FP32-pipe bound (554 flop/B); see fp32',
                          'fp32': {'achieved': achieved_tf, 'peak': fp32.value, 'unit': 'TFLOP/s',
