@@ -113,6 +113,7 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
             s_fetch = (s_fetch + 1 == n_steps) ? 0 : s_fetch + 1;
             if (prof) p.prof[s] = clock64();
             const int op = __shfl_sync(0xffffffffu, cur, 0);
+            const int warp_sync_only = __shfl_sync(0xffffffffu, cur, 11);
             if ((op & 0xff) != OP_NOP) {
                 Task t;
                 t.op = op;
@@ -127,9 +128,20 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
                 t.g = __shfl_sync(0xffffffffu, cur, 9);
                 t.h = __shfl_sync(0xffffffffu, cur, 10);
                 t.pad = 0;
+#ifdef TEBSCAT_PROF_PHASES
+                if (prof) p.prof[n_steps + 1 + 3 * s] = clock64();
+#endif
                 exec_task(S, twA, twB, p.arena, c, t, tid - t.t0);
+#ifdef TEBSCAT_PROF_PHASES
+                if (prof) p.prof[n_steps + 2 + 3 * s] = clock64();
+#endif
             }
-            __syncthreads();
+            // the plan marks the steps after which no warp touches a slot another warp has touched
+            // since the last CTA barrier: there a warp-level fence is enough and the warps drift
+            if (warp_sync_only) __syncwarp(); else __syncthreads();
+#ifdef TEBSCAT_PROF_PHASES
+            if (prof) p.prof[n_steps + 3 + 3 * s] = clock64();
+#endif
             cur = nxt;
             nxt = fut;
         }
@@ -287,6 +299,12 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
                 memcpy(rec, t, kTaskInts * sizeof(int32_t));
             }
         }
+        // field 11 of a step's tasks: 1 = the barrier after the step may be a warp-level fence.
+        // Every warp of the CTA (idle ones included) must take the same kind of barrier.
+        int relaxed = steps[2 * st] < steps[2 * st + 1] ? 1 : 0;
+        for (int ti = steps[2 * st]; ti < steps[2 * st + 1]; ++ti) relaxed &= (tasks[kTaskInts * ti + 11] & 1);
+        if (st == desc->n_steps - 1) relaxed = 0;
+        for (int w = 0; w < kWarps; ++w) wt[((size_t)st * kWarps + w) * kTaskInts + 11] = relaxed;
     }
     CU(cudaMalloc(&p->d_warp_tab, wt.size() * sizeof(int32_t)));
     CU(cudaMemcpy(p->d_warp_tab, wt.data(), wt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -375,7 +393,11 @@ extern "C" int tebscat_scat1d_profile_steps(const tebscat_plan* p, const float* 
     if (!p || !x_dev || !S_dev || !step_clocks_host || B < 1) return fail(TEBSCAT_EINVAL, "null argument");
     CU(cudaSetDevice(p->device));
     long long* d_prof = nullptr;
+#ifdef TEBSCAT_PROF_PHASES
+    const size_t n = 4 * (size_t)p->desc.n_steps + 1;     // + (decode, exec, barrier) stamps of every step
+#else
     const size_t n = (size_t)p->desc.n_steps + 1;
+#endif
     CU(cudaMalloc(&d_prof, n * sizeof(long long)));
     CU(cudaMemsetAsync(d_prof, 0, n * sizeof(long long), (cudaStream_t)stream));
     KParams kp = p->kp;

@@ -28,6 +28,7 @@ laid out in one flat arena.  Task encoding (12 x int32) must match
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -733,6 +734,101 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
     return steps, alloc.high_water, pool.chan_table, sched_stats
 
 
+# ------------------------------------------------------------------------------------
+# barrier relaxation (post-pass over the emitted schedule)
+# ------------------------------------------------------------------------------------
+def task_accesses(t, log2_Np):
+    """(slots, warps, is_write) arrays of one task row: a superset of what each warp touches."""
+    op = t[0] & 0xff
+    t0, nt = int(t[1]), int(t[2])
+    a, b, c, d, e, f, g, h = (int(v) for v in t[3:11])
+    out = []
+    def add(slots, lt, write):
+        slots = np.asarray(slots); lt = np.asarray(lt)
+        if slots.ndim == 2:
+            lt = np.broadcast_to(lt[:, None], slots.shape)
+        w = (t0 + lt) >> 5
+        out.append((slots.reshape(-1).astype(np.int64), w.reshape(-1).astype(np.int64), write))
+    if op == OP_NOP:
+        pass
+    elif op == OP_LOAD:
+        i = np.arange(1 << log2_Np)
+        add(a + i, i % nt, True)
+    elif op == OP_FFT:
+        logB, logR, flags = c, d, e
+        if logR <= 2 and logB == logR and not (flags & FFT_MOD) and ((b << logR) & 15) == 0:
+            gidx = np.arange((b << logR) >> 4)
+            s = a + 16 * gidx[:, None] + np.arange(16)[None, :]
+            add(s, gidx % nt, False); add(s, gidx % nt, True)
+        else:
+            u = np.arange(b)
+            logs = logB - logR
+            i0 = u & ((1 << logs) - 1); blk = u >> logs
+            s = (a + (blk << logB) + i0)[:, None] + (np.arange(1 << logR) << logs)[None, :]
+            add(s, u % nt, False); add(s, u % nt, True)
+    elif op == OP_MULFOLD:
+        log_src, logk = b, c
+        if logk >= 2:
+            m = np.arange(1 << (log_src - logk))
+            add(a + (m[:, None] << logk) + np.arange(1 << logk)[None, :], m % nt, False)
+            add(d + m, m % nt, True)
+        else:
+            it = np.arange(1 << (log_src - 2))
+            add(a + 4 * it[:, None] + np.arange(4)[None, :], it % nt, False)
+            if logk == 0:
+                add(d + 4 * it[:, None] + np.arange(4)[None, :], it % nt, True)
+            else:
+                add(d + 2 * it[:, None] + np.arange(2)[None, :], it % nt, True)
+    elif op == OP_STOREB:
+        s = a + np.arange(b << f)
+        for w in range(nt // 32):
+            add(s, np.full(s.shape, 32 * w), False)
+    elif op == OP_STOREZ:
+        i = np.arange(d)
+        add(a + c + i, i % nt, False)
+    elif op == OP_TINY:
+        u = np.arange(b)
+        s = a + (u[:, None] << c) + np.arange(1 << c)[None, :]
+        add(s, u % nt, False); add(s, u % nt, True)
+    else:
+        raise ValueError(op)
+    return out
+
+def elide_barriers(tasks, steps, capacity, log2_Np):
+    """keep[s] = the barrier after step s must be a CTA barrier.  Between two CTA barriers the warps run
+    unsynchronised (warp-level fences only), so a step may join the current region only if none of its
+    accesses touches a slot that ANOTHER warp has written -- or, for writes, read -- since the region began."""
+    n_steps = steps.shape[0]
+    keep = np.ones(n_steps, bool)            # keep[s]: CTA barrier after step s
+    writer = np.full(capacity + 16, -1, np.int64)       # -1 none, else warp
+    readers = np.zeros(capacity + 16, np.int64)         # bitmask of warps
+    def record(acc):
+        for s, w, wr in acc:
+            if wr:
+                writer[s] = w
+            else:
+                np.bitwise_or.at(readers, s, 1 << w)
+    prev = None
+    for st in range(n_steps):
+        acc = []
+        for ti in range(steps[st, 0], steps[st, 1]):
+            acc += task_accesses(tasks[ti], log2_Np)
+        conflict = False
+        for s, w, wr in acc:
+            lw = writer[s]
+            if np.any((lw >= 0) & (lw != w)):
+                conflict = True; break
+            if wr and np.any(readers[s] & ~(1 << w)):
+                conflict = True; break
+        if st > 0:
+            keep[st - 1] = conflict
+        if conflict or st == 0:
+            writer[:] = -1; readers[:] = 0
+        record(acc)
+    keep[n_steps - 1] = True
+    return keep
+
+
 def smem_capacity() -> int:
     """Logical complex slots a schedule may address (the kernel pads one slot per 16)."""
     return ((SMEM_BYTES_MAX // 8 - TW_SLOTS) * 16 // 17) & ~15
@@ -773,7 +869,14 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
         raise NotImplementedError('no schedule fits shared memory for this configuration: %s' % last_err)
     tasks, ranges = emit(steps)
     n_tasks = tasks.shape[0]
-    stats = dict(n_steps=len(steps), n_tasks=n_tasks, smem_logical=high,
+    n_relaxed = 0
+    if os.environ.get('TEBSCAT_RELAX', '1') != '0':
+        keep = elide_barriers(tasks, ranges, capacity, geo.J_pad)
+        for st in range(ranges.shape[0]):
+            if not keep[st]:
+                tasks[ranges[st, 0]:ranges[st, 1], 11] = 1
+                n_relaxed += 1
+    stats = dict(n_steps=len(steps), n_tasks=n_tasks, n_relaxed=n_relaxed, smem_logical=high,
                  mean_tasks_per_step=n_tasks / max(1, len(steps)), **sched)
     logical = _round16(high)
     return ScatPlan(J, Q1, T, N, max_order, geo, bank, keys, n_out, arena.finish(), tasks, ranges,
