@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TEBSCAT_ABI_VERSION 1
+#define TEBSCAT_ABI_VERSION 2
 
 enum {
     TEBSCAT_OK = 0,

@@ -7,7 +7,8 @@ import pytest
 
 from helpers import CONFIGS, GOLDEN, OVERSAMPLING, emu_available, emu_forward, path_tolerance, rel_l2
 from oracle.scattering1d_oracle import ScatteringOracle
-from tebscat.schedule import (OP_FFT, OP_LOAD, OP_MULFOLD, OP_STOREB, OP_TINY, SMEM_BYTES_MAX, TASK_INTS, TW_SLOTS,
+from tebscat.schedule import (FFT_PACK, OP_FFT, OP_LOAD, OP_MULFOLD, OP_MULFOLD2, OP_STOREB, OP_TINY, SMEM_BYTES_MAX,
+                              TASK_INTS, TW_SLOTS,
                               bitrev_indices, build_plan, radix_split)
 
 _plans = {}
@@ -35,11 +36,16 @@ def _touched(t, np_len):
     if op == OP_LOAD:
         return [], [(a, a + np_len)]
     if op == OP_FFT:                       # b butterflies of radix 2^d
-        return [(a, a + (b << d))], [(a, a + (b << d))]
+        reads = [(a, a + (b << d))]
+        if int(t[7]) & FFT_PACK and int(t[9]) > 0:         # packed pass: g partner blocks of 2^c at f
+            reads.append((int(t[8]), int(t[8]) + (int(t[9]) << c)))
+        return reads, [(a, a + (b << d))]
     if op == OP_TINY:                      # b transforms of 2^c
         return [(a, a + (b << c))], [(a, a + (b << c))]
     if op == OP_MULFOLD:
         return [(a, a + (1 << b))], [(d, d + (1 << (b - c)))]
+    if op == OP_MULFOLD2:                  # two destinations: d and g
+        return [(a, a + (1 << b))], [(d, d + (1 << (b - c))), (int(t[9]), int(t[9]) + (1 << (b - c)))]
     if op == OP_STOREB:                    # b slots of 2^f
         return [(a, a + (b << int(t[8])))], []
     return [], []
@@ -70,7 +76,8 @@ def test_schedule_is_well_formed(name):
                         assert w1 <= r0 or r1 <= w0, 'hazard inside a step'
         for r in rows:
             if (r[0] & 0xff) == OP_STOREB:
-                stored += [int(v) for v in p.chan[int(r[7]):int(r[7]) + int(r[4])]]
+                # (real-part channel, imaginary-part channel or -1) per pool slot
+                stored += [int(v) for v in p.chan[2 * int(r[7]):2 * (int(r[7]) + int(r[4]))] if v >= 0]
     assert sorted(stored) == list(range(p.n_paths))          # every channel written exactly once
 
 

@@ -35,6 +35,7 @@ static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b;
 #define TEB_UNROLL2
 #define TEB_UNROLL4
 #define TEB_FFS(x) __builtin_ffs((int)(x))
+#define TEB_CLZ(x) __builtin_clz((unsigned)(x))
 #define __popc(x) __builtin_popcount(x)
 #else
 #include <cuda_runtime.h>
@@ -44,6 +45,7 @@ static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b;
 #define TEB_UNROLL2 _Pragma("unroll 2")
 #define TEB_UNROLL4 _Pragma("unroll 4")
 #define TEB_FFS(x) __ffs((int)(x))
+#define TEB_CLZ(x) __clz((int)(x))
 #endif
 
 namespace tebscat {
@@ -56,10 +58,14 @@ enum : int32_t {
     OP_MULFOLD = 3,  // a=src b=log2Lsrc c=log2k d=dst e=filter offset (floats) f=chunk mask g=fused first inverse radix; scale 2^-sexp
     OP_STOREB = 4,   // a=pool base b=slots c=first index d=count e=channel-table offset f=log2 slot length
     OP_STOREZ = 5,   // a=src b=row (filter index) c=first index d=count: complex crop -> global (phase stage A)
-    OP_TINY = 6      // a=region b=transforms c=log2L (1..3) e=flags: whole transforms of 2, 4 or 8 samples
+    OP_TINY = 6,     // a=region b=transforms c=log2L (1..3) e=flags: whole transforms of 2, 4 or 8 samples
+    OP_MULFOLD2 = 7  // like MULFOLD with k >= 1 on a PACKED source (spectrum of u_a + i u_b): a=src b=log2Lsrc c=log2k
+                     // d=dst of the a-child e=filter offset f=chunk mask g=dst of the b-child h=log2 chunk width
 };
 enum : int32_t { Z_CART = 1, Z_POLAR = 2 };
-enum : int32_t { FFT_INV = 1, FFT_MOD = 2, FFT_FUSE_FWD = 4 };
+// FFT_PACK (with FFT_INV | FFT_FUSE_FWD): the moduli of two transforms -- block i at `a` and block i
+// at `f` (its partner, for i < g) -- enter ONE forward transform as real and imaginary part.
+enum : int32_t { FFT_INV = 1, FFT_MOD = 2, FFT_FUSE_FWD = 4, FFT_PACK = 8 };
 constexpr int kTaskInts = 12;
 
 struct Task {
@@ -211,7 +217,8 @@ template <int LOGR> TEB_D float2 twiddle_power(const float2 (&wb)[LOGR], int q) 
 //   forward (INV=0): decimation in frequency, block size 2^logB, natural -> bit-reversed
 //   inverse (INV=1): decimation in time, the exact adjoint of the forward pass
 template <int LOGR, bool INV, bool MOD, bool FUSE = false>
-TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int base, int logB, int u) {
+TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int base, int logB, int u,
+                         int partner = 0, int n_paired = 0) {
     constexpr int R = 1 << LOGR;
     const int logs = logB - LOGR;                  // log2 of the sub-block stride
     const int i0 = u & ((1 << logs) - 1);
@@ -262,6 +269,20 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
             float2 f[R];
             TEB_UNROLL for (int r = 0; r < R; ++r)
                 f[qmap<R>(r)] = make_float2(teb_sqrt(fmaf(v[r].x, v[r].x, v[r].y * v[r].y)), 0.f);
+            if (blk < n_paired) {
+                // Packed pair: the partner transform's last inverse pass; its modulus becomes the
+                // IMAGINARY part, so one forward transform serves both real signals
+                // (FFT(u_a + i u_b) = U_a + i U_b; the consumers separate or keep them packed).
+                const int delta = (partner - base) + ((partner - base) >> 4);    // both multiples of 16
+                TEB_UNROLL for (int q = 0; q < R; ++q) {
+                    float2 y = S[TEB_SLOT(brev<LOGR>(q)) + delta];
+                    if (q != 0 && logs > 0) y = cmulc(y, twiddle_power<LOGR>(wb, q));
+                    v[q] = y;
+                }
+                Dft<R, +1>::run(v);
+                TEB_UNROLL for (int r = 0; r < R; ++r)
+                    f[qmap<R>(r)].y = teb_sqrt(fmaf(v[r].x, v[r].x, v[r].y * v[r].y));
+            }
             Dft<R, -1>::run(f);
             TEB_UNROLL for (int r = 0; r < R; ++r) {
                 const int q = qmap<R>(r);
@@ -316,7 +337,8 @@ TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task&
     if (!inv) {
         for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, t.c, u);
     } else if (LOGR == 4 && fuse) {
-        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<4, true, true, true>(S, twA, twB, t.a, t.c, u);
+        const int n_paired = (t.e & FFT_PACK) ? t.g : 0;
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<4, true, true, true>(S, twA, twB, t.a, t.c, u, t.f, n_paired);
     } else if (LOGR == 4 && mod) {
         for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<4, true, true>(S, twA, twB, t.a, t.c, u);
     } else {
@@ -495,6 +517,114 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
     }
 }
 
+// Slot of bin -k in a bit-reversed spectrum when p is the slot of bin k: the highest set bit of p
+// stays, every bit below it flips (the mirror image inside p's dyadic block).
+TEB_D int mirror_slot(int p) { return p ? (p ^ ((1 << (31 - TEB_CLZ(p))) - 1)) : 0; }
+
+// MULFOLD on a PACKED source Z = FFT(u_a + i u_b) of two real signals (see FFT_PACK):
+//   U_a[k] = (Z[k] + conj Z[-k]) / 2,   U_b[k] = (Z[k] - conj Z[-k]) / (2i),
+// so with A = sum f Z[p] and Bc = sum f Z[mirror(p)] over the k slots of an output bin
+//   dst_a[m] = (A + conj Bc) / 2,       dst_b[m] = -i (A - conj Bc) / 2
+// (the 1/2 is folded into the task's power-of-two scale).  One filter load serves both children.
+TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task& t, int lt) {
+    const int logk = t.c;
+    const float scale = ldexpf(1.0f, -(t.op >> 8));
+    const float* f = arena + t.e;
+    if (logk >= 2) {
+        const int n_dst = 1 << (t.b - logk);
+        const unsigned mask = (unsigned)t.f;
+        const int logcw = t.h;
+        const int nch = __popc(mask) << (logcw - 2);
+        for (int m0 = lt; m0 < n_dst; m0 += 2 * t.nt) {
+            float ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f}, bx[2] = {0.f, 0.f}, by[2] = {0.f, 0.f};
+            unsigned rest = mask;
+            int c = 0;
+            while (rest) {
+                const int i_chunk = (TEB_FFS(rest) - 1) << logcw;
+                rest &= rest - 1;
+                for (int sub = 0; sub < (1 << (logcw - 2)); ++sub, ++c) {
+                    const int i = i_chunk + (sub << 2);
+                    float4 g[2];
+                    TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                        const int m = m0 + j * t.nt;
+                        g[j] = (m < n_dst) ? TEB_LDG(reinterpret_cast<const float4*>(f) + m * nch + c)
+                                           : float4{0.f, 0.f, 0.f, 0.f};
+                    }
+                    TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                        const int m = m0 + j * t.nt;
+                        if (m < n_dst) {
+                            const int p = (m << logk) + i;                 // multiple of 4
+                            const int q = swz(t.a + p);
+                            const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
+                            float2 y0, y1, y2, y3;
+                            if (p >= 4) {                                   // mirrors of p..p+3: pm, pm-1, pm-2, pm-3
+                                const int r = swz(t.a + mirror_slot(p) - 3);
+                                y3 = S[r]; y2 = S[r + 1]; y1 = S[r + 2]; y0 = S[r + 3];
+                            } else {                                        // slots 0,1,2,3 <-> 0,1,3,2
+                                y0 = z0; y1 = z1; y2 = z3; y3 = z2;
+                            }
+                            ax[j] = fmaf(z0.x, g[j].x, ax[j]); ay[j] = fmaf(z0.y, g[j].x, ay[j]);
+                            ax[j] = fmaf(z1.x, g[j].y, ax[j]); ay[j] = fmaf(z1.y, g[j].y, ay[j]);
+                            ax[j] = fmaf(z2.x, g[j].z, ax[j]); ay[j] = fmaf(z2.y, g[j].z, ay[j]);
+                            ax[j] = fmaf(z3.x, g[j].w, ax[j]); ay[j] = fmaf(z3.y, g[j].w, ay[j]);
+                            bx[j] = fmaf(y0.x, g[j].x, bx[j]); by[j] = fmaf(y0.y, g[j].x, by[j]);
+                            bx[j] = fmaf(y1.x, g[j].y, bx[j]); by[j] = fmaf(y1.y, g[j].y, by[j]);
+                            bx[j] = fmaf(y2.x, g[j].z, bx[j]); by[j] = fmaf(y2.y, g[j].z, by[j]);
+                            bx[j] = fmaf(y3.x, g[j].w, bx[j]); by[j] = fmaf(y3.y, g[j].w, by[j]);
+                        }
+                    }
+                }
+            }
+            TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                const int m = m0 + j * t.nt;
+                if (m < n_dst) {
+                    S[swz(t.d + m)] = make_float2((ax[j] + bx[j]) * scale, (ay[j] - by[j]) * scale);
+                    S[swz(t.g + m)] = make_float2((ay[j] + by[j]) * scale, (bx[j] - ax[j]) * scale);
+                }
+            }
+        }
+    } else {
+        const int n_items = 1 << (t.b - 2);                    // 4 source slots per item
+        TEB_UNROLL2 for (int it = lt; it < n_items; it += t.nt) {
+            const float4 g = TEB_LDG(reinterpret_cast<const float4*>(f + 4 * it));
+            const int p = 4 * it;
+            const int q = swz(t.a + p);
+            const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
+            float2 y0, y1, y2, y3;
+            if (p >= 4) {
+                const int r = swz(t.a + mirror_slot(p) - 3);
+                y3 = S[r]; y2 = S[r + 1]; y1 = S[r + 2]; y0 = S[r + 3];
+            } else {
+                y0 = z0; y1 = z1; y2 = z3; y3 = z2;
+            }
+            // per-slot products A_j = f_j Z_j, Bc_j = f_j Z_mirror(j)
+            const float a0x = z0.x * g.x, a0y = z0.y * g.x, b0x = y0.x * g.x, b0y = y0.y * g.x;
+            const float a1x = z1.x * g.y, a1y = z1.y * g.y, b1x = y1.x * g.y, b1y = y1.y * g.y;
+            const float a2x = z2.x * g.z, a2y = z2.y * g.z, b2x = y2.x * g.z, b2y = y2.y * g.z;
+            const float a3x = z3.x * g.w, a3y = z3.y * g.w, b3x = y3.x * g.w, b3y = y3.y * g.w;
+            if (logk == 0) {
+                const int oa = swz(t.d + p), ob = swz(t.g + p);
+                S[oa] = make_float2((a0x + b0x) * scale, (a0y - b0y) * scale);
+                S[oa + 1] = make_float2((a1x + b1x) * scale, (a1y - b1y) * scale);
+                S[oa + 2] = make_float2((a2x + b2x) * scale, (a2y - b2y) * scale);
+                S[oa + 3] = make_float2((a3x + b3x) * scale, (a3y - b3y) * scale);
+                S[ob] = make_float2((a0y + b0y) * scale, (b0x - a0x) * scale);
+                S[ob + 1] = make_float2((a1y + b1y) * scale, (b1x - a1x) * scale);
+                S[ob + 2] = make_float2((a2y + b2y) * scale, (b2x - a2x) * scale);
+                S[ob + 3] = make_float2((a3y + b3y) * scale, (b3x - a3x) * scale);
+            } else {
+                const int oa = swz(t.d + 2 * it), ob = swz(t.g + 2 * it);
+                const float Ax0 = a0x + a1x, Ay0 = a0y + a1y, Bx0 = b0x + b1x, By0 = b0y + b1y;
+                const float Ax1 = a2x + a3x, Ay1 = a2y + a3y, Bx1 = b2x + b3x, By1 = b2y + b3y;
+                S[oa] = make_float2((Ax0 + Bx0) * scale, (Ay0 - By0) * scale);
+                S[oa + 1] = make_float2((Ax1 + Bx1) * scale, (Ay1 - By1) * scale);
+                S[ob] = make_float2((Ay0 + By0) * scale, (Bx0 - Ax0) * scale);
+                S[ob + 1] = make_float2((Ay1 + By1) * scale, (Bx1 - Ax1) * scale);
+            }
+        }
+    }
+}
+
 // reflect padding of torch_backend.py:50-78 (F.pad(..., mode='reflect'); pad < N)
 TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
     const int Np = 1 << c.log2_Np;
@@ -515,13 +645,17 @@ TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
 }
 
 // unpad (torch_backend.py:80-102) + concatenate (kymatio/backend/torch_backend.py:143-145)
-// for a pool of `b` finished low-pass outputs: slot s goes to channel chan[e + s].
+// for a pool of `b` finished low-pass outputs: slot s goes to channels chan[2 (e + s)] (real part)
+// and chan[2 (e + s) + 1] (imaginary part of a packed pair; -1 = none).
 TEB_D void storeb_task(const float2* S, const SignalCtx& c, const Task& t, int lt) {
     const int total = t.b * t.d;
     for (int i = lt; i < total; i += t.nt) {
         const int slot = i / t.d, n = i - slot * t.d;
-        const int ch = TEB_LDG(c.chan + t.e + slot);
-        c.out[(int64_t)ch * c.n_out + n] = S[swz(t.a + (slot << t.f) + t.c + n)].x;
+        // two channels per pool slot: the real part and, for a packed pair, the imaginary part
+        const int ch_re = TEB_LDG(c.chan + 2 * (t.e + slot)), ch_im = TEB_LDG(c.chan + 2 * (t.e + slot) + 1);
+        const float2 y = S[swz(t.a + (slot << t.f) + t.c + n)];
+        c.out[(int64_t)ch_re * c.n_out + n] = y.x;
+        if (ch_im >= 0) c.out[(int64_t)ch_im * c.n_out + n] = y.y;
     }
 }
 
@@ -550,6 +684,7 @@ TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const floa
             }
             break;
         case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
+        case OP_MULFOLD2: mulfold2_task(S, arena, t, lt); break;
         case OP_STOREB: storeb_task(S, c, t, lt); break;
         case OP_STOREZ: storez_task(S, c, t, lt); break;
         case OP_TINY: tiny_task(S, t, lt); break;

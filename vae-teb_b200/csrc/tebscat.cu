@@ -194,6 +194,10 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                 break;
             case OP_FFT: {
                 // a=region b=butterflies c=log2B d=log2R: the butterflies cover b*R slots in blocks of 2^c
+                if ((t[7] & FFT_PACK) &&
+                    (!(t[7] & FFT_FUSE_FWD) || t[9] < 0 || ((int64_t)t[9] << t[5]) > ((int64_t)t[4] << t[6]) ||
+                     (t[9] > 0 && !fits(t[8], (int64_t)t[9] << t[5]))))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad packed pass (partner region %d, %d pairs)", i, t[8], t[9]);
                 if (t[5] < 1 || t[5] > kLog2TwMax || t[6] < 1 || t[6] > 4 || t[6] > t[5] || t[4] < 1 ||
                     ((t[7] & (FFT_MOD | FFT_FUSE_FWD)) && (t[6] != 4 || !(t[7] & FFT_INV))) ||
                     (((int64_t)t[4] << t[6]) & (((int64_t)1 << t[5]) - 1)) || !fits(t[3], (int64_t)t[4] << t[6]))
@@ -220,9 +224,27 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                     return fail(TEBSCAT_EINVAL, "task %d: a first inverse pass can only be fused into a k=1 MULFOLD", i);
                 break;
             }
+            case OP_MULFOLD2: {
+                // packed source: two destinations (d, g), no fused inverse pass
+                const int64_t n_dst = (int64_t)1 << (t[4] - t[5]);
+                if (t[4] < 2 || t[4] > kLog2TwMax || t[5] < 0 || t[5] > t[4] || !fits(t[3], (int64_t)1 << t[4]) ||
+                    !fits(t[6] & ~15, (t[6] & 15) + n_dst) || !fits(t[9] & ~15, (t[9] & 15) + n_dst) || t[7] < 0 ||
+                    (t[7] & 3) || (t[5] == 0 && ((t[6] | t[9]) & 3)) || (t[5] == 1 && ((t[6] | t[9]) & 1)))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD2", i);
+                if (t[5] >= 2) {
+                    const int logcw = t[10], n_chunks = 1 << (t[5] - logcw);
+                    if (logcw < 2 || logcw > t[5] || n_chunks > 32 || (unsigned)t[8] == 0u ||
+                        (n_chunks < 32 && ((unsigned)t[8] >> n_chunks) != 0u))
+                        return fail(TEBSCAT_EINVAL, "task %d: bad MULFOLD2 chunk mask", i);
+                }
+                const size_t need = t[5] >= 2 ? (((size_t)1 << (t[4] - t[5])) << t[10]) * __builtin_popcount((unsigned)t[8])
+                                              : ((size_t)1 << t[4]);
+                if ((size_t)t[7] + need > n_floats) return fail(TEBSCAT_EINVAL, "task %d: MULFOLD2 filter outside the arena", i);
+                break;
+            }
             case OP_STOREB:
                 if (t[4] < 1 || t[6] != d.n_out || t[5] < 0 || t[8] < 0 || t[8] > kLog2TwMax || t[5] + t[6] > (1 << t[8]) ||
-                    !fits(t[3], (int64_t)t[4] << t[8]) || t[7] < 0 || (size_t)t[7] + (size_t)t[4] > n_chan)
+                    !fits(t[3], (int64_t)t[4] << t[8]) || t[7] < 0 || 2 * ((size_t)t[7] + (size_t)t[4]) > n_chan)
                     return fail(TEBSCAT_EINVAL, "task %d: bad STOREB", i);
                 break;
             case OP_TINY:
@@ -260,8 +282,10 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     if (desc->n_threads != kThreads) return fail(TEBSCAT_EUNSUPPORTED, "schedules must target 512-thread CTAs");
     if (desc->n_paths < 1 || desc->n_out < 1 || desc->n_tasks < 1 || desc->n_steps < 1 || desc->smem_complex < 1)
         return fail(TEBSCAT_EINVAL, "empty plan");
+    // channel table: (real-part channel, imaginary-part channel or -1) per pool slot
     for (size_t i = 0; i < n_chan; ++i)
-        if (chan[i] < 0 || chan[i] >= desc->n_paths) return fail(TEBSCAT_EINVAL, "channel table entry %zu out of range", i);
+        if (chan[i] >= desc->n_paths || chan[i] < ((i & 1) ? -1 : 0))
+            return fail(TEBSCAT_EINVAL, "channel table entry %zu out of range", i);
     if (int rc = validate_schedule(*desc, tasks, steps, n_floats, n_chan)) return rc;
 
     int n_dev = 0;

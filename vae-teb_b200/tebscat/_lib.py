@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TEBSCAT_LIB', os.path.join(_HERE, 'libtebscat.so'))
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 TEBSCAT_OK, TEBSCAT_EINVAL, TEBSCAT_ECUDA, TEBSCAT_EUNSUPPORTED = 0, 1, 2, 3
 

@@ -36,8 +36,8 @@ import numpy as np
 
 from . import filterbank as fbk
 
-OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY = 0, 1, 2, 3, 4, 5, 6
-FFT_INV, FFT_MOD, FFT_FUSE_FWD = 1, 2, 4
+OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY, OP_MULFOLD2 = 0, 1, 2, 3, 4, 5, 6, 7
+FFT_INV, FFT_MOD, FFT_FUSE_FWD, FFT_PACK = 1, 2, 4, 8
 TASK_INTS = 12
 
 N_THREADS = 512
@@ -46,7 +46,12 @@ SMEM_BYTES_MAX = 227 * 1024
 TW_SLOTS = 68 + 136 + 4 + 16      # padded twiddle tables + the kernel's static shared memory
 MASK_THRESHOLD = 1e-9             # relative filter magnitude below which a 4-bin chunk is skipped
 BATCH_SLOTS = 8192                # target size of one batch buffer (complex slots)
-POOL_SLOTS = 2048                 # size of one half of the leaf pool
+POOL_SLOTS = 1024                 # size of one half of the leaf pool
+
+
+def pack_enabled() -> bool:
+    """Pair packing (two real moduli per forward transform); TEBSCAT_PACK=0 builds the unpacked plan (A/B)."""
+    return os.environ.get('TEBSCAT_PACK', '1') != '0'
 
 
 def bitrev_indices(n: int) -> np.ndarray:
@@ -100,11 +105,11 @@ class TaskSpec:
     c: int = 0
     d: object = 0                  # int, (Buf, offset) or LEAF
     e: int = 0
-    f: int = 0
-    g: int = 0
+    f: object = 0                  # int, or (Buf, offset): partner region of a packed pass
+    g: object = 0                  # int, or (Buf, offset): second destination of a MULFOLD2
     h: int = 0
     sexp: int = 0
-    channel: int = -1              # output channel of a leaf MULFOLD
+    channel: object = -1           # output channel(s) of a leaf MULFOLD: int or (real-part, imaginary-part or -1)
     tpi: int = 1                   # threads per work item (32 for warp-local FFT tasks)
 
 
@@ -118,6 +123,7 @@ class Chain:
     frees_own_at_end: bool = False
     depth: int = 0
     pool_half: int = -1            # >= 0 for the flush chains of the leaf pool
+    shrink: List[Tuple[int, Buf, int]] = field(default_factory=list)   # (stage, buffer, new size): tail freed after the stage
     # scheduler state
     stage: int = 0
     issued: List[bool] = field(default_factory=list)
@@ -134,24 +140,29 @@ _FFT_INSTR = {1: 40.0, 2: 110.0, 3: 250.0, 4: 480.0}
 STEP_OVERHEAD = 450.0
 
 
-def _global_pass(ref, n: int, count: int, logB: int, r: int, flags: int) -> TaskSpec:
+def _global_pass(ref, n: int, count: int, logB: int, r: int, flags: int, partner=0, n_paired: int = 0) -> TaskSpec:
     bfly = count << (n - r)
     if r <= 2 and logB == r and not (flags & FFT_MOD) and ((count << n) & 15) == 0:
         # unit-stride remainder pass: the kernel takes 16 slots per thread and trip
         return TaskSpec(OP_FFT, (count << n) >> 4, 500.0, 300.0, a=ref, b=bfly, c=logB, d=r, e=flags)
     lat, instr = _FFT_LAT[r], _FFT_INSTR[r]
     if flags & FFT_FUSE_FWD:
-        lat, instr = 1.8 * lat, 1.8 * instr
-    return TaskSpec(OP_FFT, bfly, lat, instr, a=ref, b=bfly, c=logB, d=r, e=flags)
+        k = 1.8 + (0.9 * n_paired / count if flags & FFT_PACK else 0.0)
+        lat, instr = k * lat, k * instr
+    return TaskSpec(OP_FFT, bfly, lat, instr, a=ref, b=bfly, c=logB, d=r, e=flags, f=partner, g=n_paired)
 
 
-def _fft_stages(ref, n: int, count: int, kind: str) -> List[List[TaskSpec]]:
+def _fft_stages(ref, n: int, count: int, kind: str, hi: int = 0) -> List[List[TaskSpec]]:
     """Stages of `count` in-place length-2^n transforms stored back to back at `ref`.
 
     kind: 'fwd' (DIF), 'inv' (DIT), 'inv_mod' (DIT ending in the modulus) or 'pair'
     (inverse, modulus, forward -- core/scattering1d.py:312-318 / :350-355).  In a 'pair' the
     last inverse and the first forward pass touch the same 16 elements per thread and are
     fused into one task (one shared-memory round trip and one barrier less).
+
+    Packed 'pair' (hi > 0, n >= 4): `count + hi` transforms are inverted; block i (< hi) of the second
+    group -- stored right behind the first `count` blocks -- is the PARTNER of block i: the fused pass
+    takes both moduli as real and imaginary part, so the forward half runs on `count` blocks only.
 
     (Running the small-block passes warp-locally with __syncwarp() instead of CTA barriers was
     measured 30 % SLOWER on B200: warps executing different passes thrash the instruction cache.)"""
@@ -174,9 +185,13 @@ def _fft_stages(ref, n: int, count: int, kind: str) -> List[List[TaskSpec]]:
         return [[_global_pass(ref, n, count, b, r, FFT_INV | (mod if i == len(dit) - 1 else 0))]
                 for i, (b, r) in enumerate(dit)]
     if kind == 'pair':
-        out = [[_global_pass(ref, n, count, b, r, FFT_INV)] for b, r in dit[:-1]]
+        out = [[_global_pass(ref, n, count + hi, b, r, FFT_INV)] for b, r in dit[:-1]]
         b, r = dit[-1]
-        out.append([_global_pass(ref, n, count, b, r, FFT_INV | FFT_MOD | FFT_FUSE_FWD)])
+        if hi > 0:
+            out.append([_global_pass(ref, n, count, b, r, FFT_INV | FFT_MOD | FFT_FUSE_FWD | FFT_PACK,
+                                     partner=(ref[0], ref[1] + (count << n)), n_paired=hi)])
+        else:
+            out.append([_global_pass(ref, n, count, b, r, FFT_INV | FFT_MOD | FFT_FUSE_FWD)])
         out += [[_global_pass(ref, n, count, b2, r2, 0)] for b2, r2 in dif[1:]]
         return out
     raise ValueError(kind)
@@ -243,7 +258,7 @@ def _fuse_first_inverse_pass(mulfolds: List[TaskSpec], stages: List[List[TaskSpe
     every MULFOLD feeding it is a plain k=1 product, let the MULFOLD do that pass on the four
     slots each of its threads owns and drop the pass (core :307-312 in one round trip)."""
     r0 = radix_split(n)[-1]
-    if r0 <= 2 and len(radix_split(n)) > 1 and all(m.c == 0 for m in mulfolds):
+    if r0 <= 2 and len(radix_split(n)) > 1 and all(m.op == OP_MULFOLD and m.c == 0 for m in mulfolds):
         first = stages[0][0]
         if first.op == OP_FFT and first.c == r0 and first.d == r0 and (first.e & FFT_INV) and not (first.e & (FFT_MOD | FFT_FUSE_FWD)):
             for m in mulfolds:
@@ -269,6 +284,24 @@ def _mulfold(arena: _Arena, src, log_src: int, logk: int, dst, filt_off: int, ch
         mask -= 1 << 32                                    # the task table holds int32 fields
     return TaskSpec(OP_MULFOLD, work, lat, instr, a=src, b=log_src, c=logk, d=dst, e=filt_off, f=mask,
                     h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst, channel=channel)
+
+
+def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_off: int) -> TaskSpec:
+    """MULFOLD on a packed source (spectrum of u_a + i u_b): one task, both children (csrc: mulfold2_task)."""
+    log_dst = log_src - logk
+    if logk >= 2:
+        mask = arena.chunk_mask(filt_off, logk)
+        nch = bin(mask).count('1') << (_Arena.chunk_log2(logk) - 2)
+        filt_off = arena.compact(filt_off, logk, mask)
+        work, lat, instr = -(-(1 << log_dst) // 2), 900.0 + 250.0 * nch, 220.0 + 300.0 * nch
+    else:
+        mask = 0
+        work, lat, instr = 1 << (log_src - 2), 800.0, 220.0
+    if mask >= 1 << 31:
+        mask -= 1 << 32
+    # mean over k blocks, 1/L of the inverse transform, and the 1/2 of the pair separation
+    return TaskSpec(OP_MULFOLD2, work, lat, instr, a=src, b=log_src, c=logk, d=dst_a, e=filt_off, f=mask, g=dst_b,
+                    h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst + 1)
 
 
 # ------------------------------------------------------------------------------------
@@ -359,9 +392,35 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
     channel = {k: c for c, k in enumerate(keys)}
     chains: List[Chain] = []
 
-    def leaf(src, log_src: int, level: int, key) -> TaskSpec:
-        """phi[level] multiply + periodise down to 2^lf into a pool slot (core :287-289)."""
-        return _mulfold(arena, src, log_src, log_src - lf, LEAF, phi_off[level], channel[key])
+    def leaf(src, log_src: int, level: int, key, key_im=None) -> TaskSpec:
+        """phi[level] multiply + periodise down to 2^lf into a pool slot (core :287-289).  phi is real and
+        even, so the leaf of a PACKED spectrum U_a + i U_b is the packed pair of leaves: after the inverse
+        transform the real part is channel `key`, the imaginary part channel `key_im`."""
+        ch = (channel[key], channel[key_im] if key_im is not None else -1)
+        return _mulfold(arena, src, log_src, log_src - lf, LEAF, phi_off[level], ch)
+
+    def pack_stage(stages) -> int:
+        for si, st in enumerate(stages):
+            if any(t.op == OP_FFT and (t.e & FFT_PACK) for t in st):
+                return si
+        return -1
+
+    def paired(items, pack: bool):
+        """Adjacent filters of the same scale j share one forward transform: they carry similar energy
+        and have the same children.  Pairs first, singles last (the packed pass wants partners in front)."""
+        if not pack:
+            return [(x, None) for x in items]
+        pairs, singles, i = [], [], 0
+        while i < len(items):
+            if i + 1 < len(items) and bank.psi1[items[i]].j == bank.psi1[items[i + 1]].j:
+                pairs.append((items[i], items[i + 1]))
+                i += 2
+            else:
+                singles.append((items[i], None))
+                i += 1
+        return pairs + singles
+
+    packing = pack_enabled()
 
     # root: pad + forward transform of the signal (core/scattering1d.py:278-280)
     u0 = Buf(1 << n, 'U0')
@@ -379,46 +438,71 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
         groups.setdefault(k1, []).append(n1)
     for k1 in sorted(groups):
         l1 = n - k1
-        per_batch = max(1, batch_slots >> l1)
-        members = groups[k1]
-        for s in range(0, len(members), per_batch):
-            batch = members[s:s + per_batch]
-            nb = len(batch)
-            x1 = Buf(nb << l1, 'U1[k1=%d:%d]' % (k1, batch[0]))
-            mf = [_mulfold(arena, (u0, 0), n, k1, (x1, i << l1), psi1_off[n1]) for i, n1 in enumerate(batch)]
-            st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x1, 0), l1, nb, 'pair'), l1)   # :307-318
+        pack1 = packing and l1 >= 4
+        # entries (a, b): filters a and b share the forward transform; one batch = `per_batch` entries
+        entries_all = paired(groups[k1], pack1)
+        per_batch = max(1, (batch_slots // 2 if pack1 else batch_slots) >> l1)
+        for s in range(0, len(entries_all), per_batch):
+            batch = sorted(entries_all[s:s + per_batch], key=lambda e: e[1] is None)
+            lo = len(batch)
+            hi = sum(1 for _, b in batch if b is not None)             # pairs come first
+            x1 = Buf((lo + hi) << l1, 'U1[k1=%d:%d]' % (k1, batch[0][0]))
+            mf = [_mulfold(arena, (u0, 0), n, k1, (x1, i << l1), psi1_off[a]) for i, (a, _) in enumerate(batch)]
+            mf += [_mulfold(arena, (u0, 0), n, k1, (x1, (lo + i) << l1), psi1_off[b])
+                   for i, (_, b) in enumerate(batch) if b is not None]
+            st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x1, 0), l1, lo, 'pair', hi=hi), l1)   # :307-318
             c1 = Chain(x1.name, st, after=[root], reads=[u0], owns=[x1], depth=1)
+            if hi:
+                c1.shrink.append((pack_stage(st), x1, lo << l1))
             chains.append(c1)
             # low-pass leaves of the batch (:320-327)
-            chains.append(Chain('S1' + x1.name, [[leaf((x1, i << l1), l1, k1, (n1,)) for i, n1 in enumerate(batch)]],
+            chains.append(Chain('S1' + x1.name,
+                                [[leaf((x1, i << l1), l1, k1, (a,), (b,) if b is not None else None)
+                                  for i, (a, b) in enumerate(batch)]],
                                 after=[c1], reads=[x1], depth=2))
             if max_order != 2:
                 continue
-            # second order, grouped by child length (:337-364)
-            kids: Dict[int, List[Tuple[int, int, int]]] = {}
-            for i, n1 in enumerate(batch):
-                p1 = bank.psi1[n1]
+            # second order, grouped by child length (:337-364); the children of a packed parent are a pair again
+            kids: Dict[int, List[Tuple[int, int, Optional[int], int]]] = {}
+            for i, (a, b) in enumerate(batch):
+                p1 = bank.psi1[a]
                 for n2, p2 in enumerate(bank.psi2):
                     if p2.j > p1.j:
                         if not p2.xi < p1.xi:
                             raise AssertionError('psi2 ordering assertion of the reference violated')
                         k2 = max(min(p2.j - k1 - os_, log2_T - k1 - os_), 0)   # :344-345
-                        kids.setdefault(k2, []).append((i, n1, n2))
+                        kids.setdefault(k2, []).append((i, a, b, n2))
             for k2 in sorted(kids):
                 l2 = l1 - k2
-                fam = kids[k2]
-                per = max(1, batch_slots >> l2)
+                pack2 = packing and l2 >= 4
+                fam = sorted(kids[k2], key=lambda e: e[2] is None)            # pairs first (stable)
+                per = max(1, (batch_slots // 2 if pack2 else batch_slots // 2) >> l2)
                 for s2 in range(0, len(fam), per):
                     sub = fam[s2:s2 + per]
-                    x2 = Buf(len(sub) << l2, 'U2[%d,k2=%d]' % (batch[0], k2))
-                    mf = [_mulfold(arena, (x1, i << l1), l1, k2, (x2, c << l2), psi2_off[n2][k1])
-                          for c, (i, n1, n2) in enumerate(sub)]                         # :347-348
-                    st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x2, 0), l2, len(sub), 'pair'), l2)   # :350-355
+                    lo2 = len(sub)
+                    hi2 = sum(1 for e in sub if e[2] is not None)
+                    x2 = Buf((lo2 + hi2) << l2, 'U2[%d,k2=%d]' % (batch[0][0], k2))
+                    mf = []
+                    for c, (i, a, b, n2) in enumerate(sub):                                 # :347-348
+                        if b is not None:
+                            mf.append(_mulfold2(arena, (x1, i << l1), l1, k2, (x2, c << l2), (x2, (lo2 + c) << l2),
+                                                psi2_off[n2][k1]))
+                        else:
+                            mf.append(_mulfold(arena, (x1, i << l1), l1, k2, (x2, c << l2), psi2_off[n2][k1]))
+                    if pack2:
+                        st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x2, 0), l2, lo2, 'pair', hi=hi2), l2)   # :350-355
+                        lv = [leaf((x2, c << l2), l2, k1 + k2, (a, n2), (b, n2) if b is not None else None)
+                              for c, (i, a, b, n2) in enumerate(sub)]
+                    else:
+                        st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x2, 0), l2, lo2 + hi2, 'pair'), l2)
+                        lv = [leaf((x2, c << l2), l2, k1 + k2, (a, n2)) for c, (i, a, b, n2) in enumerate(sub)]
+                        lv += [leaf((x2, (lo2 + c) << l2), l2, k1 + k2, (b, n2))
+                               for c, (i, a, b, n2) in enumerate(sub) if b is not None]
                     c2 = Chain(x2.name, st, after=[c1], reads=[x1], owns=[x2], depth=2)
+                    if pack2 and hi2:
+                        c2.shrink.append((pack_stage(st), x2, lo2 << l2))
                     chains.append(c2)
-                    chains.append(Chain('S2' + x2.name,
-                                        [[leaf((x2, c << l2), l2, k1 + k2, (n1, n2)) for c, (i, n1, n2) in enumerate(sub)]],
-                                        after=[c2], reads=[x2], depth=3))               # :358-364
+                    chains.append(Chain('S2' + x2.name, [lv], after=[c2], reads=[x2], depth=3))   # :358-364
     return chains, keys, n_out, lf, i0
 
 
@@ -493,13 +577,14 @@ class _LeafPool:
         h = self.cur
         slot = self.fill[h]
         self.fill[h] += 1
-        self.channels[h].append(channel)
+        self.channels[h].append(channel if isinstance(channel, tuple) else (channel, -1))
         return self.bufs[h].off + (slot << self.lf)
 
     def flush_chain(self, h: int) -> Chain:
         cnt = self.fill[h]
-        table_off = len(self.chan_table)
-        self.chan_table += self.channels[h]
+        table_off = len(self.chan_table) // 2          # in slots: the table holds (real, imaginary) channel pairs
+        for pair in self.channels[h]:
+            self.chan_table += [pair[0], pair[1]]
         ref = (self.bufs[h], 0)
         st = _fft_stages(ref, self.lf, cnt, 'inv')
         st.append([TaskSpec(OP_STOREB, cnt * self.n_out, 150.0, 14.0, a=ref, b=cnt, c=self.i0, d=self.n_out,
@@ -694,7 +779,8 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
         used = 0
         for (c, ti, t), nt in zip(chosen, nts):
             dst = pool.take(t.channel) if t.d is LEAF else resolve(t.d)
-            this_step.append([t.op | (t.sexp << 8), used, nt, resolve(t.a), t.b, t.c, dst, t.e, t.f, t.g, t.h, 0])
+            this_step.append([t.op | (t.sexp << 8), used, nt, resolve(t.a), t.b, t.c, dst, t.e, resolve(t.f), resolve(t.g),
+                              t.h, 0])
             used += nt
             est_issue += (nt // 32) * math.ceil(t.work * t.tpi / nt) * t.instr
             c.issued[ti] = True
@@ -710,6 +796,12 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
                     b.readers_left -= 1
                     release_if_dead(b)
             c.stage += 1
+            for si, buf, new_size in c.shrink:
+                if si == c.stage - 1 and buf.off >= 0 and _round16(new_size) < _round16(buf.size):
+                    # the partner blocks of a packed pass are dead once the pass has run: free the tail
+                    alloc.release(buf.off + _round16(new_size), _round16(buf.size) - _round16(new_size))
+                    free_slots += _round16(buf.size) - _round16(new_size)
+                    buf.size = new_size
             if c.stage == len(c.stages):
                 c.done_step = step_idx
                 active.remove(c)
@@ -766,6 +858,9 @@ def task_accesses(t, log2_Np):
             i0 = u & ((1 << logs) - 1); blk = u >> logs
             s = (a + (blk << logB) + i0)[:, None] + (np.arange(1 << logR) << logs)[None, :]
             add(s, u % nt, False); add(s, u % nt, True)
+            if flags & FFT_PACK:
+                sel = blk < g
+                add(s[sel] - a + f, (u % nt)[sel], False)
     elif op == OP_MULFOLD:
         log_src, logk = b, c
         if logk >= 2:
@@ -779,6 +874,19 @@ def task_accesses(t, log2_Np):
                 add(d + 4 * it[:, None] + np.arange(4)[None, :], it % nt, True)
             else:
                 add(d + 2 * it[:, None] + np.arange(2)[None, :], it % nt, True)
+    elif op == OP_MULFOLD2:
+        log_src, logk = b, c
+        src = a + np.arange(1 << log_src)
+        for w in range(nt // 32):                       # mirrored reads: any slot of the source
+            add(src, np.full(src.shape, 32 * w), False)
+        if logk >= 2:
+            m = np.arange(1 << (log_src - logk))
+            add(d + m, m % nt, True); add(g + m, m % nt, True)
+        else:
+            it = np.arange(1 << (log_src - 2))
+            w_ = 4 >> logk
+            add(d + w_ * it[:, None] + np.arange(w_)[None, :], it % nt, True)
+            add(g + w_ * it[:, None] + np.arange(w_)[None, :], it % nt, True)
     elif op == OP_STOREB:
         s = a + np.arange(b << f)
         for w in range(nt // 32):
@@ -856,7 +964,8 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     # batches as large as shared memory allows: retry with smaller batches / pool when the
     # buffers of a configuration (large output-rate lengths, T << 2**J) do not fit
     last_err = None
-    for batch_slots, pool_slots in ((BATCH_SLOTS, POOL_SLOTS), (4096, 2048), (2048, 1024), (1024, 512), (512, 256)):
+    for batch_slots, pool_slots in ((BATCH_SLOTS, POOL_SLOTS), (BATCH_SLOTS, 512), (4096, 1024), (2048, 1024), (1024, 512),
+                                    (512, 256)):
         arena = _Arena()
         chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling)
         try:
