@@ -213,9 +213,20 @@ template <int LOGR> TEB_D float2 twiddle_power(const float2 (&wb)[LOGR], int q) 
     return w;
 }
 
+// Shared-memory accesses of the butterflies go through BYTE offsets (slot index * 8, computed once
+// per butterfly and reused by the stores): the address of an access is then "constant base + register"
+// and costs no instruction of its own.
+TEB_D float2 sld(const float2* S, int byte_off) {
+    return *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(S) + byte_off);
+}
+TEB_D void sst(float2* S, int byte_off, float2 v) {
+    *reinterpret_cast<float2*>(reinterpret_cast<char*>(S) + byte_off) = v;
+}
+
 // One radix-2^LOGR pass over butterfly u of a length-2^logL transform stored at `base`.
 //   forward (INV=0): decimation in frequency, block size 2^logB, natural -> bit-reversed
 //   inverse (INV=1): decimation in time, the exact adjoint of the forward pass
+// Unit-stride passes (logs == 0) have i0 == 0, so their twiddles are exactly 1: no special case.
 template <int LOGR, bool INV, bool MOD, bool FUSE = false>
 TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int base, int logB, int u,
                          int partner = 0, int n_paired = 0) {
@@ -226,33 +237,36 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
     const int p0 = base + (blk << logB) + i0;
     float2 v[R];
     float2 wb[LOGR];
-    if (logs > 0) {
+    {
         const int k1 = i0 << (kLog2TwMax - logB);
         TEB_UNROLL for (int i = 0; i < LOGR; ++i) wb[i] = twiddle(twA, twB, k1 << i);
     }
-    // element j of the butterfly lives at slot swz(p0 + j*s); for strides that are multiples of
-    // 16 the padded layout is affine in j
+    // element j of the butterfly lives at slot swz(p0) + swz(j << logs) (p0's low four bits are below
+    // the stride, so the pad terms add without carry); for strides >= 16 that is affine in j
     int slot[R];
-    if (logs >= 4) {
-        const int s0 = swz(p0), ds = (1 << logs) + (1 << (logs - 4));
-        TEB_UNROLL for (int j = 0; j < R; ++j) slot[j] = s0 + j * ds;
-    } else {
-        TEB_UNROLL for (int j = 0; j < R; ++j) slot[j] = swz(p0 + (j << logs));
+    {
+        const int s0 = swz(p0) << 3;
+        if (logs >= 4) {
+            const int ds = ((1 << logs) + (1 << (logs - 4))) << 3;
+            TEB_UNROLL for (int j = 0; j < R; ++j) slot[j] = s0 + j * ds;
+        } else {
+            TEB_UNROLL for (int j = 0; j < R; ++j) slot[j] = s0 + (swz(j << logs) << 3);
+        }
     }
 #define TEB_SLOT(j) slot[j]
     if (!INV) {
-        TEB_UNROLL for (int j = 0; j < R; ++j) v[j] = S[TEB_SLOT(j)];
+        TEB_UNROLL for (int j = 0; j < R; ++j) v[j] = sld(S, TEB_SLOT(j));
         Dft<R, -1>::run(v);
         TEB_UNROLL for (int r = 0; r < R; ++r) {
             const int q = qmap<R>(r);
             float2 y = v[r];
-            if (q != 0 && logs > 0) y = cmul(y, twiddle_power<LOGR>(wb, q));
-            S[TEB_SLOT(brev<LOGR>(q))] = y;
+            if (q != 0) y = cmul(y, twiddle_power<LOGR>(wb, q));
+            sst(S, TEB_SLOT(brev<LOGR>(q)), y);
         }
     } else {
         TEB_UNROLL for (int q = 0; q < R; ++q) {
-            float2 y = S[TEB_SLOT(brev<LOGR>(q))];
-            if (q != 0 && logs > 0) y = cmulc(y, twiddle_power<LOGR>(wb, q));
+            float2 y = sld(S, TEB_SLOT(brev<LOGR>(q)));
+            if (q != 0) y = cmulc(y, twiddle_power<LOGR>(wb, q));
             v[q] = y;
         }
         Dft<R, +1>::run(v);
@@ -260,7 +274,7 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
             TEB_UNROLL for (int r = 0; r < R; ++r) {
                 float2 y = v[r];
                 if (MOD) y = make_float2(teb_sqrt(fmaf(y.x, y.x, y.y * y.y)), 0.f);
-                S[TEB_SLOT(qmap<R>(r))] = y;
+                sst(S, TEB_SLOT(qmap<R>(r)), y);
             }
         } else {
             // The last inverse pass and the first forward pass of "ifft -> modulus -> fft" touch
@@ -273,10 +287,10 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
                 // Packed pair: the partner transform's last inverse pass; its modulus becomes the
                 // IMAGINARY part, so one forward transform serves both real signals
                 // (FFT(u_a + i u_b) = U_a + i U_b; the consumers separate or keep them packed).
-                const int delta = (partner - base) + ((partner - base) >> 4);    // both multiples of 16
+                const int delta = ((partner - base) + ((partner - base) >> 4)) << 3;    // both multiples of 16
                 TEB_UNROLL for (int q = 0; q < R; ++q) {
-                    float2 y = S[TEB_SLOT(brev<LOGR>(q)) + delta];
-                    if (q != 0 && logs > 0) y = cmulc(y, twiddle_power<LOGR>(wb, q));
+                    float2 y = sld(S, TEB_SLOT(brev<LOGR>(q)) + delta);
+                    if (q != 0) y = cmulc(y, twiddle_power<LOGR>(wb, q));
                     v[q] = y;
                 }
                 Dft<R, +1>::run(v);
@@ -287,8 +301,8 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
             TEB_UNROLL for (int r = 0; r < R; ++r) {
                 const int q = qmap<R>(r);
                 float2 y = f[r];
-                if (q != 0 && logs > 0) y = cmul(y, twiddle_power<LOGR>(wb, q));
-                S[TEB_SLOT(brev<LOGR>(q))] = y;
+                if (q != 0) y = cmul(y, twiddle_power<LOGR>(wb, q));
+                sst(S, TEB_SLOT(brev<LOGR>(q)), y);
             }
         }
     }
@@ -526,6 +540,18 @@ TEB_D int mirror_slot(int p) { return p ? (p ^ ((1 << (31 - TEB_CLZ(p))) - 1)) :
 // so with A = sum f Z[p] and Bc = sum f Z[mirror(p)] over the k slots of an output bin
 //   dst_a[m] = (A + conj Bc) / 2,       dst_b[m] = -i (A - conj Bc) / 2
 // (the 1/2 is folded into the task's power-of-two scale).  One filter load serves both children.
+// the source slots of one 4-slot group p..p+3 and of their mirrors (bins -k), as (z[4], y[4])
+TEB_D void load_group_and_mirror(const float2* S, int base, int p, float2 (&z)[4], float2 (&y)[4]) {
+    const int q = swz(base + p);
+    z[0] = S[q]; z[1] = S[q + 1]; z[2] = S[q + 2]; z[3] = S[q + 3];
+    if (p >= 4) {                                   // mirrors of p..p+3: pm, pm-1, pm-2, pm-3 (one aligned group)
+        const int r = swz(base + mirror_slot(p) - 3);
+        y[3] = S[r]; y[2] = S[r + 1]; y[1] = S[r + 2]; y[0] = S[r + 3];
+    } else {                                        // slots 0,1,2,3 <-> 0,1,3,2
+        y[0] = z[0]; y[1] = z[1]; y[2] = z[3]; y[3] = z[2];
+    }
+}
+
 TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task& t, int lt) {
     const int logk = t.c;
     const float scale = ldexpf(1.0f, -(t.op >> 8));
@@ -535,6 +561,51 @@ TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task&
         const unsigned mask = (unsigned)t.f;
         const int logcw = t.h;
         const int nch = __popc(mask) << (logcw - 2);
+        if (nch <= 2 && logcw == 2) {
+            // at most two active chunks (the usual case for the second-order bank): the filter loads of
+            // four outputs are all in flight before the first is used -- one L2 round trip per trip
+            const int i0 = (TEB_FFS(mask) - 1) << 2;
+            const unsigned m2 = mask & (mask - 1);
+            const int i1 = m2 ? ((TEB_FFS(m2) - 1) << 2) : i0;
+            for (int m0 = lt; m0 < n_dst; m0 += 4 * t.nt) {
+                float4 g0[4], g1[4];
+                TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + j * t.nt;
+                    const bool ok = m < n_dst;
+                    const float4* fm = reinterpret_cast<const float4*>(f) + m * nch;
+                    g0[j] = ok ? TEB_LDG(fm) : float4{0.f, 0.f, 0.f, 0.f};
+                    g1[j] = (ok && m2) ? TEB_LDG(fm + 1) : float4{0.f, 0.f, 0.f, 0.f};
+                }
+                TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + j * t.nt;
+                    if (m < n_dst) {
+                        float2 z[4], y[4];
+                        load_group_and_mirror(S, t.a, (m << logk) + i0, z, y);
+                        float ax = z[0].x * g0[j].x, ay = z[0].y * g0[j].x, bx = y[0].x * g0[j].x, by = y[0].y * g0[j].x;
+                        ax = fmaf(z[1].x, g0[j].y, ax); ay = fmaf(z[1].y, g0[j].y, ay);
+                        bx = fmaf(y[1].x, g0[j].y, bx); by = fmaf(y[1].y, g0[j].y, by);
+                        ax = fmaf(z[2].x, g0[j].z, ax); ay = fmaf(z[2].y, g0[j].z, ay);
+                        bx = fmaf(y[2].x, g0[j].z, bx); by = fmaf(y[2].y, g0[j].z, by);
+                        ax = fmaf(z[3].x, g0[j].w, ax); ay = fmaf(z[3].y, g0[j].w, ay);
+                        bx = fmaf(y[3].x, g0[j].w, bx); by = fmaf(y[3].y, g0[j].w, by);
+                        if (m2) {
+                            load_group_and_mirror(S, t.a, (m << logk) + i1, z, y);
+                            ax = fmaf(z[0].x, g1[j].x, ax); ay = fmaf(z[0].y, g1[j].x, ay);
+                            bx = fmaf(y[0].x, g1[j].x, bx); by = fmaf(y[0].y, g1[j].x, by);
+                            ax = fmaf(z[1].x, g1[j].y, ax); ay = fmaf(z[1].y, g1[j].y, ay);
+                            bx = fmaf(y[1].x, g1[j].y, bx); by = fmaf(y[1].y, g1[j].y, by);
+                            ax = fmaf(z[2].x, g1[j].z, ax); ay = fmaf(z[2].y, g1[j].z, ay);
+                            bx = fmaf(y[2].x, g1[j].z, bx); by = fmaf(y[2].y, g1[j].z, by);
+                            ax = fmaf(z[3].x, g1[j].w, ax); ay = fmaf(z[3].y, g1[j].w, ay);
+                            bx = fmaf(y[3].x, g1[j].w, bx); by = fmaf(y[3].y, g1[j].w, by);
+                        }
+                        S[swz(t.d + m)] = make_float2((ax + bx) * scale, (ay - by) * scale);
+                        S[swz(t.g + m)] = make_float2((ay + by) * scale, (bx - ax) * scale);
+                    }
+                }
+            }
+            return;
+        }
         for (int m0 = lt; m0 < n_dst; m0 += 2 * t.nt) {
             float ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f}, bx[2] = {0.f, 0.f}, by[2] = {0.f, 0.f};
             unsigned rest = mask;
@@ -553,24 +624,16 @@ TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task&
                     TEB_UNROLL for (int j = 0; j < 2; ++j) {
                         const int m = m0 + j * t.nt;
                         if (m < n_dst) {
-                            const int p = (m << logk) + i;                 // multiple of 4
-                            const int q = swz(t.a + p);
-                            const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
-                            float2 y0, y1, y2, y3;
-                            if (p >= 4) {                                   // mirrors of p..p+3: pm, pm-1, pm-2, pm-3
-                                const int r = swz(t.a + mirror_slot(p) - 3);
-                                y3 = S[r]; y2 = S[r + 1]; y1 = S[r + 2]; y0 = S[r + 3];
-                            } else {                                        // slots 0,1,2,3 <-> 0,1,3,2
-                                y0 = z0; y1 = z1; y2 = z3; y3 = z2;
-                            }
-                            ax[j] = fmaf(z0.x, g[j].x, ax[j]); ay[j] = fmaf(z0.y, g[j].x, ay[j]);
-                            ax[j] = fmaf(z1.x, g[j].y, ax[j]); ay[j] = fmaf(z1.y, g[j].y, ay[j]);
-                            ax[j] = fmaf(z2.x, g[j].z, ax[j]); ay[j] = fmaf(z2.y, g[j].z, ay[j]);
-                            ax[j] = fmaf(z3.x, g[j].w, ax[j]); ay[j] = fmaf(z3.y, g[j].w, ay[j]);
-                            bx[j] = fmaf(y0.x, g[j].x, bx[j]); by[j] = fmaf(y0.y, g[j].x, by[j]);
-                            bx[j] = fmaf(y1.x, g[j].y, bx[j]); by[j] = fmaf(y1.y, g[j].y, by[j]);
-                            bx[j] = fmaf(y2.x, g[j].z, bx[j]); by[j] = fmaf(y2.y, g[j].z, by[j]);
-                            bx[j] = fmaf(y3.x, g[j].w, bx[j]); by[j] = fmaf(y3.y, g[j].w, by[j]);
+                            float2 z[4], y[4];
+                            load_group_and_mirror(S, t.a, (m << logk) + i, z, y);
+                            ax[j] = fmaf(z[0].x, g[j].x, ax[j]); ay[j] = fmaf(z[0].y, g[j].x, ay[j]);
+                            ax[j] = fmaf(z[1].x, g[j].y, ax[j]); ay[j] = fmaf(z[1].y, g[j].y, ay[j]);
+                            ax[j] = fmaf(z[2].x, g[j].z, ax[j]); ay[j] = fmaf(z[2].y, g[j].z, ay[j]);
+                            ax[j] = fmaf(z[3].x, g[j].w, ax[j]); ay[j] = fmaf(z[3].y, g[j].w, ay[j]);
+                            bx[j] = fmaf(y[0].x, g[j].x, bx[j]); by[j] = fmaf(y[0].y, g[j].x, by[j]);
+                            bx[j] = fmaf(y[1].x, g[j].y, bx[j]); by[j] = fmaf(y[1].y, g[j].y, by[j]);
+                            bx[j] = fmaf(y[2].x, g[j].z, bx[j]); by[j] = fmaf(y[2].y, g[j].z, by[j]);
+                            bx[j] = fmaf(y[3].x, g[j].w, bx[j]); by[j] = fmaf(y[3].y, g[j].w, by[j]);
                         }
                     }
                 }
@@ -585,41 +648,42 @@ TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task&
         }
     } else {
         const int n_items = 1 << (t.b - 2);                    // 4 source slots per item
-        TEB_UNROLL2 for (int it = lt; it < n_items; it += t.nt) {
-            const float4 g = TEB_LDG(reinterpret_cast<const float4*>(f + 4 * it));
-            const int p = 4 * it;
-            const int q = swz(t.a + p);
-            const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
-            float2 y0, y1, y2, y3;
-            if (p >= 4) {
-                const int r = swz(t.a + mirror_slot(p) - 3);
-                y3 = S[r]; y2 = S[r + 1]; y1 = S[r + 2]; y0 = S[r + 3];
-            } else {
-                y0 = z0; y1 = z1; y2 = z3; y3 = z2;
+        for (int it0 = lt; it0 < n_items; it0 += 4 * t.nt) {
+            float4 gg[4];
+            TEB_UNROLL for (int j = 0; j < 4; ++j) {           // four filter loads in flight per thread
+                const int it = it0 + j * t.nt;
+                gg[j] = (it < n_items) ? TEB_LDG(reinterpret_cast<const float4*>(f + 4 * it)) : float4{0.f, 0.f, 0.f, 0.f};
             }
-            // per-slot products A_j = f_j Z_j, Bc_j = f_j Z_mirror(j)
-            const float a0x = z0.x * g.x, a0y = z0.y * g.x, b0x = y0.x * g.x, b0y = y0.y * g.x;
-            const float a1x = z1.x * g.y, a1y = z1.y * g.y, b1x = y1.x * g.y, b1y = y1.y * g.y;
-            const float a2x = z2.x * g.z, a2y = z2.y * g.z, b2x = y2.x * g.z, b2y = y2.y * g.z;
-            const float a3x = z3.x * g.w, a3y = z3.y * g.w, b3x = y3.x * g.w, b3y = y3.y * g.w;
-            if (logk == 0) {
-                const int oa = swz(t.d + p), ob = swz(t.g + p);
-                S[oa] = make_float2((a0x + b0x) * scale, (a0y - b0y) * scale);
-                S[oa + 1] = make_float2((a1x + b1x) * scale, (a1y - b1y) * scale);
-                S[oa + 2] = make_float2((a2x + b2x) * scale, (a2y - b2y) * scale);
-                S[oa + 3] = make_float2((a3x + b3x) * scale, (a3y - b3y) * scale);
-                S[ob] = make_float2((a0y + b0y) * scale, (b0x - a0x) * scale);
-                S[ob + 1] = make_float2((a1y + b1y) * scale, (b1x - a1x) * scale);
-                S[ob + 2] = make_float2((a2y + b2y) * scale, (b2x - a2x) * scale);
-                S[ob + 3] = make_float2((a3y + b3y) * scale, (b3x - a3x) * scale);
-            } else {
-                const int oa = swz(t.d + 2 * it), ob = swz(t.g + 2 * it);
-                const float Ax0 = a0x + a1x, Ay0 = a0y + a1y, Bx0 = b0x + b1x, By0 = b0y + b1y;
-                const float Ax1 = a2x + a3x, Ay1 = a2y + a3y, Bx1 = b2x + b3x, By1 = b2y + b3y;
-                S[oa] = make_float2((Ax0 + Bx0) * scale, (Ay0 - By0) * scale);
-                S[oa + 1] = make_float2((Ax1 + Bx1) * scale, (Ay1 - By1) * scale);
-                S[ob] = make_float2((Ay0 + By0) * scale, (Bx0 - Ax0) * scale);
-                S[ob + 1] = make_float2((Ay1 + By1) * scale, (Bx1 - Ax1) * scale);
+            TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                const int it = it0 + j * t.nt;
+                if (it >= n_items) continue;
+                const float4 g = gg[j];
+                float2 z[4], y[4];
+                load_group_and_mirror(S, t.a, 4 * it, z, y);
+                // per-slot products A_r = f_r Z_r, Bc_r = f_r Z_mirror(r)
+                const float a0x = z[0].x * g.x, a0y = z[0].y * g.x, b0x = y[0].x * g.x, b0y = y[0].y * g.x;
+                const float a1x = z[1].x * g.y, a1y = z[1].y * g.y, b1x = y[1].x * g.y, b1y = y[1].y * g.y;
+                const float a2x = z[2].x * g.z, a2y = z[2].y * g.z, b2x = y[2].x * g.z, b2y = y[2].y * g.z;
+                const float a3x = z[3].x * g.w, a3y = z[3].y * g.w, b3x = y[3].x * g.w, b3y = y[3].y * g.w;
+                if (logk == 0) {
+                    const int oa = swz(t.d + 4 * it), ob = swz(t.g + 4 * it);
+                    S[oa] = make_float2((a0x + b0x) * scale, (a0y - b0y) * scale);
+                    S[oa + 1] = make_float2((a1x + b1x) * scale, (a1y - b1y) * scale);
+                    S[oa + 2] = make_float2((a2x + b2x) * scale, (a2y - b2y) * scale);
+                    S[oa + 3] = make_float2((a3x + b3x) * scale, (a3y - b3y) * scale);
+                    S[ob] = make_float2((a0y + b0y) * scale, (b0x - a0x) * scale);
+                    S[ob + 1] = make_float2((a1y + b1y) * scale, (b1x - a1x) * scale);
+                    S[ob + 2] = make_float2((a2y + b2y) * scale, (b2x - a2x) * scale);
+                    S[ob + 3] = make_float2((a3y + b3y) * scale, (b3x - a3x) * scale);
+                } else {
+                    const int oa = swz(t.d + 2 * it), ob = swz(t.g + 2 * it);
+                    const float Ax0 = a0x + a1x, Ay0 = a0y + a1y, Bx0 = b0x + b1x, By0 = b0y + b1y;
+                    const float Ax1 = a2x + a3x, Ay1 = a2y + a3y, Bx1 = b2x + b3x, By1 = b2y + b3y;
+                    S[oa] = make_float2((Ax0 + Bx0) * scale, (Ay0 - By0) * scale);
+                    S[oa + 1] = make_float2((Ax1 + Bx1) * scale, (Ay1 - By1) * scale);
+                    S[ob] = make_float2((Ay0 + By0) * scale, (Bx0 - Ax0) * scale);
+                    S[ob + 1] = make_float2((Ay1 + By1) * scale, (Bx1 - Ax1) * scale);
+                }
             }
         }
     }

@@ -291,12 +291,16 @@ def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_of
     log_dst = log_src - logk
     if logk >= 2:
         mask = arena.chunk_mask(filt_off, logk)
-        nch = bin(mask).count('1') << (_Arena.chunk_log2(logk) - 2)
+        logcw = _Arena.chunk_log2(logk)
+        nch = bin(mask).count('1') << (logcw - 2)
         filt_off = arena.compact(filt_off, logk, mask)
-        work, lat, instr = -(-(1 << log_dst) // 2), 900.0 + 250.0 * nch, 220.0 + 300.0 * nch
+        if nch <= 2 and logcw == 2:                        # four outputs per thread and trip, loads up front
+            work, lat, instr = -(-(1 << log_dst) // 4), 1100.0 + 250.0 * nch, 150.0 + 420.0 * nch
+        else:                                              # two outputs per trip, one L2 round trip per chunk
+            work, lat, instr = -(-(1 << log_dst) // 2), 900.0 + 700.0 * nch, 100.0 + 220.0 * nch
     else:
         mask = 0
-        work, lat, instr = 1 << (log_src - 2), 800.0, 220.0
+        work, lat, instr = 1 << (log_src - 4), 1300.0, 520.0          # four 4-slot items per thread and trip
     if mask >= 1 << 31:
         mask -= 1 << 32
     # mean over k blocks, 1/L of the inverse transform, and the 1/2 of the pair separation
@@ -365,11 +369,13 @@ class _Allocator:
 
 
 def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int, arena: _Arena,
-                 batch_slots: int = BATCH_SLOTS, oversampling: int = 0):
+                 batch_slots: int = BATCH_SLOTS, oversampling: int = 0, child_slots: Optional[int] = None):
     """The cascade as a forest of chains of batched tasks, in the reference's channel order."""
     n = geo.J_pad
     log2_T = int(math.floor(math.log2(T)))
     os_ = int(oversampling)
+    if child_slots is None:
+        child_slots = batch_slots // 2
     kf = max(log2_T - os_, 0)                             # final subsampling (:285, :322, :358)
     lf = n - kf                                           # log2 of the final (output-rate) length
     if lf < 0:
@@ -476,7 +482,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
                 l2 = l1 - k2
                 pack2 = packing and l2 >= 4
                 fam = sorted(kids[k2], key=lambda e: e[2] is None)            # pairs first (stable)
-                per = max(1, (batch_slots // 2 if pack2 else batch_slots // 2) >> l2)
+                per = max(1, child_slots >> l2)
                 for s2 in range(0, len(fam), per):
                     sub = fam[s2:s2 + per]
                     lo2 = len(sub)
@@ -604,7 +610,8 @@ class _LeafPool:
 
 
 def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out: int,
-                    max_parallel: int = 64, pack_gain: float = 0.97, pool_slots: int = POOL_SLOTS):
+                    max_parallel: int = 64, pack_gain: float = 0.97, pool_slots: int = POOL_SLOTS,
+                    open_demand: float = 2.0):
     """Greedy list scheduling of chains into steps (see module docstring)."""
     children: Dict[int, List[Chain]] = {}
     for ch in chains:
@@ -731,7 +738,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
         for c in startable:
             if len(active) >= max_parallel:
                 break
-            if demand >= 2 * N_THREADS and c.depth <= 1:
+            if demand >= open_demand * N_THREADS and c.depth <= 1:
                 continue                          # enough queued work; do not open new subtrees
             if try_start(c, force=False):
                 pending.remove(c)
@@ -952,7 +959,10 @@ def emit(steps) -> Tuple[np.ndarray, np.ndarray]:
 
 
 def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int = 64,
-               oversampling: int = 0) -> ScatPlan:
+               oversampling: int = 0, tune: Optional[dict] = None) -> ScatPlan:
+    """`tune` overrides scheduler knobs (tools/sweep_sched.py): batch_slots, child_slots, pool_slots,
+    pack_gain, open_demand."""
+    tune = dict(tune or {})
     Q1 = fbk._as_Q1(Q)
     geo = fbk.build_geometry(N, J, Q1, T)
     if geo.J_pad > LOG2_NP_MAX:
@@ -964,13 +974,17 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     # batches as large as shared memory allows: retry with smaller batches / pool when the
     # buffers of a configuration (large output-rate lengths, T << 2**J) do not fit
     last_err = None
-    for batch_slots, pool_slots in ((BATCH_SLOTS, POOL_SLOTS), (BATCH_SLOTS, 512), (4096, 1024), (2048, 1024), (1024, 512),
-                                    (512, 256)):
+    ladder = [(BATCH_SLOTS, POOL_SLOTS), (BATCH_SLOTS, 512), (4096, 1024), (2048, 1024), (1024, 512), (512, 256)]
+    if 'batch_slots' in tune or 'pool_slots' in tune:
+        ladder.insert(0, (tune.get('batch_slots', BATCH_SLOTS), tune.get('pool_slots', POOL_SLOTS)))
+    for batch_slots, pool_slots in ladder:
         arena = _Arena()
-        chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling)
+        chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling,
+                                                   child_slots=tune.get('child_slots'))
         try:
             steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel,
-                                                       pool_slots=pool_slots)
+                                                       pool_slots=pool_slots, pack_gain=tune.get('pack_gain', 0.97),
+                                                       open_demand=tune.get('open_demand', 2.0))
             break
         except (RuntimeError, AssertionError) as e:
             last_err = e
