@@ -38,7 +38,9 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
             for (int ti = steps[2 * s]; ti < steps[2 * s + 1]; ++ti) {
                 Task t;
                 memcpy(&t, tasks + kTaskInts * ti, sizeof(Task));
-                for (int lt = 0; lt < t.nt; ++lt) exec_task(S.data(), tw.data(), tw.data() + kTwAP, arena, c, t, lt);
+                // multi-pass FFT tasks: pass by pass over all lanes (the kernel separates them by warp fences)
+                for (int k = 0; k < task_passes(t); ++k)
+                    for (int lt = 0; lt < t.nt; ++lt) exec_task(S.data(), tw.data(), tw.data() + kTwAP, arena, c, t, lt, k);
             }
         }
     }

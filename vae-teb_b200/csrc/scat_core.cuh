@@ -213,6 +213,10 @@ template <int LOGR> TEB_D float2 twiddle_power(const float2 (&wb)[LOGR], int q) 
     return w;
 }
 
+#ifdef TEBSCAT_PROF_BFLY
+__device__ long long g_bfly_dbg[8];
+#endif
+
 // Shared-memory accesses of the butterflies go through BYTE offsets (slot index * 8, computed once
 // per butterfly and reused by the stores): the address of an access is then "constant base + register"
 // and costs no instruction of its own.
@@ -231,6 +235,11 @@ template <int LOGR, bool INV, bool MOD, bool FUSE = false>
 TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int base, int logB, int u,
                          int partner = 0, int n_paired = 0) {
     constexpr int R = 1 << LOGR;
+#ifdef TEBSCAT_PROF_BFLY
+    const bool dbg = threadIdx.x == 0 && blockIdx.x == 0 && !INV && LOGR == 4;
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if (dbg) c0 = clock64();
+#endif
     const int logs = logB - LOGR;                  // log2 of the sub-block stride
     const int i0 = u & ((1 << logs) - 1);
     const int blk = u >> logs;
@@ -256,13 +265,22 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
 #define TEB_SLOT(j) slot[j]
     if (!INV) {
         TEB_UNROLL for (int j = 0; j < R; ++j) v[j] = sld(S, TEB_SLOT(j));
+#ifdef TEBSCAT_PROF_BFLY
+        if (dbg) { float sink = 0.f; TEB_UNROLL for (int j = 0; j < R; ++j) sink += v[j].x; if (sink == 1234.5f) g_bfly_dbg[7] = 1; c1 = clock64(); }
+#endif
         Dft<R, -1>::run(v);
+#ifdef TEBSCAT_PROF_BFLY
+        if (dbg) { float sink = 0.f; TEB_UNROLL for (int j = 0; j < R; ++j) sink += v[j].x + v[j].y; if (sink == 1234.5f) g_bfly_dbg[7] = 1; c2 = clock64(); }
+#endif
         TEB_UNROLL for (int r = 0; r < R; ++r) {
             const int q = qmap<R>(r);
             float2 y = v[r];
             if (q != 0) y = cmul(y, twiddle_power<LOGR>(wb, q));
             sst(S, TEB_SLOT(brev<LOGR>(q)), y);
         }
+#ifdef TEBSCAT_PROF_BFLY
+        if (dbg) { c3 = clock64(); g_bfly_dbg[0] += c1 - c0; g_bfly_dbg[1] += c2 - c1; g_bfly_dbg[2] += c3 - c2; g_bfly_dbg[3] += 1; }
+#endif
     } else {
         TEB_UNROLL for (int q = 0; q < R; ++q) {
             float2 y = sld(S, TEB_SLOT(brev<LOGR>(q)));
@@ -334,31 +352,75 @@ TEB_D void fft_unit_stride_group(float2* S, int first_slot) {
     TEB_UNROLL for (int j = 0; j < 16; ++j) S[q0 + j] = v[j];
 }
 
+// One pass of an FFT task over `slots` slots at t.a: radix 2^LOGR, blocks of 2^logB.
 template <int LOGR>
-TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task& t, int lt) {
-    const int n_bfly = t.b;
-    const bool inv = (t.e & FFT_INV) != 0, mod = (t.e & FFT_MOD) != 0, fuse = (t.e & FFT_FUSE_FWD) != 0;
-    if (LOGR <= 2 && t.c == LOGR && !mod && (((n_bfly << LOGR) & 15) == 0)) {
-        const int n_groups = (n_bfly << LOGR) >> 4;
+TEB_D void fft_pass(float2* S, const float2* twA, const float2* twB, const Task& t, int lt, int logB, int flags,
+                    int slots) {
+    const int n_bfly = slots >> LOGR;
+    const bool inv = (flags & FFT_INV) != 0, mod = (flags & FFT_MOD) != 0, fuse = (flags & FFT_FUSE_FWD) != 0;
+    if (LOGR <= 3 && logB == LOGR && !mod && ((slots & 15) == 0)) {
+        const int n_groups = slots >> 4;
         for (int g = lt; g < n_groups; g += t.nt) {
-            if (!inv) fft_unit_stride_group<(LOGR <= 2 ? LOGR : 1), false>(S, t.a + (g << 4));
-            else fft_unit_stride_group<(LOGR <= 2 ? LOGR : 1), true>(S, t.a + (g << 4));
+            if (!inv) fft_unit_stride_group<(LOGR <= 3 ? LOGR : 1), false>(S, t.a + (g << 4));
+            else fft_unit_stride_group<(LOGR <= 3 ? LOGR : 1), true>(S, t.a + (g << 4));
         }
         return;
     }
     // the modulus / fused passes are always radix 16 (the last inverse pass of any transform
     // of 16 samples or more): only that instantiation carries them, which keeps the kernel small
     if (!inv) {
-        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, t.c, u);
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, false, false>(S, twA, twB, t.a, logB, u);
     } else if (LOGR == 4 && fuse) {
-        const int n_paired = (t.e & FFT_PACK) ? t.g : 0;
-        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<4, true, true, true>(S, twA, twB, t.a, t.c, u, t.f, n_paired);
+        const int n_paired = (flags & FFT_PACK) ? t.g : 0;
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<4, true, true, true>(S, twA, twB, t.a, logB, u, t.f, n_paired);
     } else if (LOGR == 4 && mod) {
-        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<4, true, true>(S, twA, twB, t.a, t.c, u);
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<4, true, true>(S, twA, twB, t.a, logB, u);
     } else {
-        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, false>(S, twA, twB, t.a, t.c, u);
+        for (int u = lt; u < n_bfly; u += t.nt) fft_butterfly<LOGR, true, false>(S, twA, twB, t.a, logB, u);
     }
 }
+
+// An FFT task is a SEQUENCE of up to four passes over the same slots.  Passes after the first are
+// packed 12 bits each -- log2B | log2R << 4 | flags << 7 -- into h (two) and pad bits 4..15 (one).
+// The host only chains passes whose blocks are at most 512 slots: 32 consecutive work items (radix-16
+// butterflies, or 16-slot groups of the unit-stride pass) then cover the same 512 slots in every pass, so
+// a warp only ever reads what it wrote itself and a warp-level fence between the passes is enough --
+// no CTA barrier, no trip through the dispatcher.
+TEB_D unsigned long long fft_more_passes(const Task& t) {
+    return (unsigned long long)((unsigned)t.h & 0xffffffu) | ((unsigned long long)(((unsigned)t.pad >> 4) & 0xfffu) << 24);
+}
+TEB_D int task_passes(const Task& t) {
+    if ((t.op & 0xff) != OP_FFT) return 1;
+    unsigned long long more = fft_more_passes(t);
+    int n = 1;
+    while (more & 0xfff) { ++n; more >>= 12; }
+    return n;
+}
+TEB_D void fft_task_pass(float2* S, const float2* twA, const float2* twB, const Task& t, int lt, int logB, int logR,
+                         int flags) {
+    const int slots = t.b << t.d;
+    switch (logR) {
+        case 4: fft_pass<4>(S, twA, twB, t, lt, logB, flags, slots); break;
+        case 3: fft_pass<3>(S, twA, twB, t, lt, logB, flags, slots); break;
+        case 2: fft_pass<2>(S, twA, twB, t, lt, logB, flags, slots); break;
+        default: fft_pass<1>(S, twA, twB, t, lt, logB, flags, slots); break;
+    }
+}
+#ifndef TEBSCAT_HOST_EMU
+TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task& t, int lt) {
+    unsigned long long more = fft_more_passes(t);
+    int logB = t.c, logR = t.d, flags = t.e;
+    for (;;) {
+        fft_task_pass(S, twA, twB, t, lt, logB, logR, flags);
+        if (!(more & 0xfff)) break;
+        __syncwarp();
+        logB = (int)(more & 15);
+        logR = (int)((more >> 4) & 7);
+        flags = (int)((more >> 7) & 15);
+        more >>= 12;
+    }
+}
+#endif
 
 // Transforms of 2, 4 or 8 samples (output-rate lengths of short signals): one thread per
 // transform, direct O(L^2) DFT with the eighth roots of unity as constants.  Same conventions
@@ -735,18 +797,26 @@ TEB_D void storez_task(const float2* S, const SignalCtx& c, const Task& t, int l
     }
 }
 
+// `pass` selects the pass of a multi-pass FFT task; the kernel runs them back to back (fft_task), the host
+// emulator -- which executes the lanes of a task one after another -- runs pass by pass.
 TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const float* __restrict__ arena,
-                     const SignalCtx& c, const Task& t, int lt) {
+                     const SignalCtx& c, const Task& t, int lt, int pass = -1) {
     switch (t.op & 0xff) {
         case OP_LOAD: load_task(S, c, t, lt); break;
-        case OP_FFT:
-            switch (t.d) {
-                case 4: fft_task<4>(S, twA, twB, t, lt); break;
-                case 3: fft_task<3>(S, twA, twB, t, lt); break;
-                case 2: fft_task<2>(S, twA, twB, t, lt); break;
-                default: fft_task<1>(S, twA, twB, t, lt); break;
+        case OP_FFT: {
+#ifndef TEBSCAT_HOST_EMU
+            fft_task(S, twA, twB, t, lt);
+#else
+            unsigned long long more = fft_more_passes(t);
+            int logB = t.c, logR = t.d, flags = t.e;
+            for (int k = 0; k < pass; ++k) {
+                logB = (int)(more & 15); logR = (int)((more >> 4) & 7); flags = (int)((more >> 7) & 15);
+                more >>= 12;
             }
+            fft_task_pass(S, twA, twB, t, lt, logB, logR, flags);
+#endif
             break;
+        }
         case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
         case OP_MULFOLD2: mulfold2_task(S, arena, t, lt); break;
         case OP_STOREB: storeb_task(S, c, t, lt); break;

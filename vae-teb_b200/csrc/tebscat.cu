@@ -113,7 +113,8 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
             s_fetch = (s_fetch + 1 == n_steps) ? 0 : s_fetch + 1;
             if (prof) p.prof[s] = clock64();
             const int op = __shfl_sync(0xffffffffu, cur, 0);
-            const int warp_sync_only = __shfl_sync(0xffffffffu, cur, 11);
+            const int f11 = __shfl_sync(0xffffffffu, cur, 11);
+            const int warp_sync_only = f11 & 1;
             if ((op & 0xff) != OP_NOP) {
                 Task t;
                 t.op = op;
@@ -127,7 +128,7 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
                 t.f = __shfl_sync(0xffffffffu, cur, 8);
                 t.g = __shfl_sync(0xffffffffu, cur, 9);
                 t.h = __shfl_sync(0xffffffffu, cur, 10);
-                t.pad = 0;
+                t.pad = f11;
 #ifdef TEBSCAT_PROF_PHASES
                 if (prof) p.prof[n_steps + 1 + 3 * s] = clock64();
 #endif
@@ -198,6 +199,19 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                     (!(t[7] & FFT_FUSE_FWD) || t[9] < 0 || ((int64_t)t[9] << t[5]) > ((int64_t)t[4] << t[6]) ||
                      (t[9] > 0 && !fits(t[8], (int64_t)t[9] << t[5]))))
                     return fail(TEBSCAT_EINVAL, "task %d: bad packed pass (partner region %d, %d pairs)", i, t[8], t[9]);
+                {   // chained passes (12 bits each in h and pad): blocks of at most 512 slots, never the fused pass
+                    unsigned long long more = (unsigned long long)((unsigned)t[10] & 0xffffffu) |
+                                              ((unsigned long long)(((unsigned)t[11] >> 4) & 0xfffu) << 24);
+                    const int64_t slots = (int64_t)t[4] << t[6];
+                    if (more && (t[5] > 9 || (t[7] & FFT_FUSE_FWD) || (slots & 15)))
+                        return fail(TEBSCAT_EINVAL, "task %d: pass chain starts with a cross-warp pass", i);
+                    for (; more & 0xfff; more >>= 12) {
+                        const int lb = (int)(more & 15), lr = (int)((more >> 4) & 7), fl = (int)((more >> 7) & 15);
+                        if (lb < 1 || lb > 9 || lr < 1 || lr > 4 || lr > lb || (fl & (FFT_FUSE_FWD | FFT_PACK)) ||
+                            ((fl & FFT_MOD) && (lr != 4 || !(fl & FFT_INV))) || (slots & (((int64_t)1 << lb) - 1)))
+                            return fail(TEBSCAT_EINVAL, "task %d: bad chained pass (B=2^%d R=2^%d)", i, lb, lr);
+                    }
+                }
                 if (t[5] < 1 || t[5] > kLog2TwMax || t[6] < 1 || t[6] > 4 || t[6] > t[5] || t[4] < 1 ||
                     ((t[7] & (FFT_MOD | FFT_FUSE_FWD)) && (t[6] != 4 || !(t[7] & FFT_INV))) ||
                     (((int64_t)t[4] << t[6]) & (((int64_t)1 << t[5]) - 1)) || !fits(t[3], (int64_t)t[4] << t[6]))
@@ -328,7 +342,10 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
         int relaxed = steps[2 * st] < steps[2 * st + 1] ? 1 : 0;
         for (int ti = steps[2 * st]; ti < steps[2 * st + 1]; ++ti) relaxed &= (tasks[kTaskInts * ti + 11] & 1);
         if (st == desc->n_steps - 1) relaxed = 0;
-        for (int w = 0; w < kWarps; ++w) wt[((size_t)st * kWarps + w) * kTaskInts + 11] = relaxed;
+        for (int w = 0; w < kWarps; ++w) {
+            int32_t& f11 = wt[((size_t)st * kWarps + w) * kTaskInts + 11];
+            f11 = (f11 & ~1) | relaxed;
+        }
     }
     CU(cudaMalloc(&p->d_warp_tab, wt.size() * sizeof(int32_t)));
     CU(cudaMemcpy(p->d_warp_tab, wt.data(), wt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -436,6 +453,15 @@ extern "C" int tebscat_scat1d_profile_steps(const tebscat_plan* p, const float* 
     ++g_launches;
     return TEBSCAT_OK;
 }
+
+#ifdef TEBSCAT_PROF_BFLY
+extern "C" int tebscat_debug_bfly(long long* out8, int reset) {
+    if (reset) { long long z[8] = {0}; cudaMemcpyToSymbol(tebscat::g_bfly_dbg, z, sizeof(z)); return 0; }
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, tebscat::g_bfly_dbg, 8 * sizeof(long long));
+    return 0;
+}
+#endif
 
 extern "C" int tebscat_scat1d_forward_host(tebscat_plan* p, const float* x_host, int64_t B, float* S_host) {
     g_launches = 0;

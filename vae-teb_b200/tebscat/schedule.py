@@ -109,6 +109,7 @@ class TaskSpec:
     g: object = 0                  # int, or (Buf, offset): second destination of a MULFOLD2
     h: int = 0
     sexp: int = 0
+    pad: int = 0                   # field 11: bit 0 = relaxed barrier (post-pass), bits 4..15 = third chained FFT pass
     channel: object = -1           # output channel(s) of a leaf MULFOLD: int or (real-part, imaginary-part or -1)
     tpi: int = 1                   # threads per work item (32 for warp-local FFT tasks)
 
@@ -142,7 +143,7 @@ STEP_OVERHEAD = 450.0
 
 def _global_pass(ref, n: int, count: int, logB: int, r: int, flags: int, partner=0, n_paired: int = 0) -> TaskSpec:
     bfly = count << (n - r)
-    if r <= 2 and logB == r and not (flags & FFT_MOD) and ((count << n) & 15) == 0:
+    if r <= 3 and logB == r and not (flags & FFT_MOD) and ((count << n) & 15) == 0:
         # unit-stride remainder pass: the kernel takes 16 slots per thread and trip
         return TaskSpec(OP_FFT, (count << n) >> 4, 500.0, 300.0, a=ref, b=bfly, c=logB, d=r, e=flags)
     lat, instr = _FFT_LAT[r], _FFT_INSTR[r]
@@ -195,6 +196,53 @@ def _fft_stages(ref, n: int, count: int, kind: str, hi: int = 0) -> List[List[Ta
         out += [[_global_pass(ref, n, count, b2, r2, 0)] for b2, r2 in dif[1:]]
         return out
     raise ValueError(kind)
+
+
+MAX_CHAIN = 4                     # passes per FFT task (the first + three packed into h / pad)
+LOCAL_LOG2 = 9                    # blocks of <= 512 slots: 32 consecutive work items own them in every pass
+
+
+def chain_enabled() -> bool:
+    return os.environ.get('TEBSCAT_CHAIN', '1') != '0'
+
+
+def _merge_local_passes(stages: List[List[TaskSpec]]) -> List[List[TaskSpec]]:
+    """Chain consecutive single-task FFT stages whose blocks are at most 512 slots into ONE task: its
+    passes run back to back separated by warp fences (csrc: fft_task), not by CTA barriers and trips through
+    the dispatcher.  Valid because such passes -- radix-16 butterflies or 16-slot unit-stride groups, the same
+    number of work items in each -- map 32 consecutive work items onto the same 512 slots."""
+    if not chain_enabled():
+        return stages
+
+    def local(st) -> bool:
+        if len(st) != 1:
+            return False
+        t = st[0]
+        if t.op != OP_FFT or t.c > LOCAL_LOG2 or (t.e & (FFT_FUSE_FWD | FFT_PACK)) or t.h or t.pad:
+            return False
+        return ((t.b << t.d) & 15) == 0 and (t.d == 4 or t.c == t.d)
+
+    out: List[List[TaskSpec]] = []
+    for st in stages:
+        if out and local(st) and len(out[-1]) == 1 and getattr(out[-1][0], '_chain', 0) and \
+                out[-1][0]._chain < MAX_CHAIN and out[-1][0].a == st[0].a and \
+                (out[-1][0].b << out[-1][0].d) == (st[0].b << st[0].d):
+            head, t = out[-1][0], st[0]
+            code = t.c | (t.d << 4) | (t.e << 7)
+            if head._chain == 1:
+                head.h |= code
+            elif head._chain == 2:
+                head.h |= code << 12
+            else:
+                head.pad |= code << 4
+            head._chain += 1
+            head.lat += t.lat
+            head.instr += t.instr
+            continue
+        if local(st):
+            st[0]._chain = 1
+        out.append(st)
+    return out
 
 
 class _Arena:
@@ -431,7 +479,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
     # root: pad + forward transform of the signal (core/scattering1d.py:278-280)
     u0 = Buf(1 << n, 'U0')
     root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
-                 _fft_stages((u0, 0), n, 1, 'fwd'), owns=[u0], depth=0)
+                 _merge_local_passes(_fft_stages((u0, 0), n, 1, 'fwd')), owns=[u0], depth=0)
     chains.append(root)
     chains.append(Chain('S0', [[leaf((u0, 0), n, 0, ())]], after=[root], reads=[u0], depth=1))   # :285-292
 
@@ -456,7 +504,8 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
             mf = [_mulfold(arena, (u0, 0), n, k1, (x1, i << l1), psi1_off[a]) for i, (a, _) in enumerate(batch)]
             mf += [_mulfold(arena, (u0, 0), n, k1, (x1, (lo + i) << l1), psi1_off[b])
                    for i, (_, b) in enumerate(batch) if b is not None]
-            st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x1, 0), l1, lo, 'pair', hi=hi), l1)   # :307-318
+            st = [mf] + _merge_local_passes(
+                _fuse_first_inverse_pass(mf, _fft_stages((x1, 0), l1, lo, 'pair', hi=hi), l1))             # :307-318
             c1 = Chain(x1.name, st, after=[root], reads=[u0], owns=[x1], depth=1)
             if hi:
                 c1.shrink.append((pack_stage(st), x1, lo << l1))
@@ -496,11 +545,13 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
                         else:
                             mf.append(_mulfold(arena, (x1, i << l1), l1, k2, (x2, c << l2), psi2_off[n2][k1]))
                     if pack2:
-                        st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x2, 0), l2, lo2, 'pair', hi=hi2), l2)   # :350-355
+                        st = [mf] + _merge_local_passes(
+                            _fuse_first_inverse_pass(mf, _fft_stages((x2, 0), l2, lo2, 'pair', hi=hi2), l2))   # :350-355
                         lv = [leaf((x2, c << l2), l2, k1 + k2, (a, n2), (b, n2) if b is not None else None)
                               for c, (i, a, b, n2) in enumerate(sub)]
                     else:
-                        st = [mf] + _fuse_first_inverse_pass(mf, _fft_stages((x2, 0), l2, lo2 + hi2, 'pair'), l2)
+                        st = [mf] + _merge_local_passes(
+                            _fuse_first_inverse_pass(mf, _fft_stages((x2, 0), l2, lo2 + hi2, 'pair'), l2))
                         lv = [leaf((x2, c << l2), l2, k1 + k2, (a, n2)) for c, (i, a, b, n2) in enumerate(sub)]
                         lv += [leaf((x2, (lo2 + c) << l2), l2, k1 + k2, (b, n2))
                                for c, (i, a, b, n2) in enumerate(sub) if b is not None]
@@ -592,7 +643,7 @@ class _LeafPool:
         for pair in self.channels[h]:
             self.chan_table += [pair[0], pair[1]]
         ref = (self.bufs[h], 0)
-        st = _fft_stages(ref, self.lf, cnt, 'inv')
+        st = _merge_local_passes(_fft_stages(ref, self.lf, cnt, 'inv'))
         st.append([TaskSpec(OP_STOREB, cnt * self.n_out, 150.0, 14.0, a=ref, b=cnt, c=self.i0, d=self.n_out,
                             e=table_off, f=self.lf)])
         ch = Chain('flush%d@%d' % (h, table_off), st, depth=9, pool_half=h)
@@ -787,7 +838,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
         for (c, ti, t), nt in zip(chosen, nts):
             dst = pool.take(t.channel) if t.d is LEAF else resolve(t.d)
             this_step.append([t.op | (t.sexp << 8), used, nt, resolve(t.a), t.b, t.c, dst, t.e, resolve(t.f), resolve(t.g),
-                              t.h, 0])
+                              t.h, t.pad])
             used += nt
             est_issue += (nt // 32) * math.ceil(t.work * t.tpi / nt) * t.instr
             c.issued[ti] = True
@@ -855,7 +906,7 @@ def task_accesses(t, log2_Np):
         add(a + i, i % nt, True)
     elif op == OP_FFT:
         logB, logR, flags = c, d, e
-        if logR <= 2 and logB == logR and not (flags & FFT_MOD) and ((b << logR) & 15) == 0:
+        if logR <= 3 and logB == logR and not (flags & FFT_MOD) and ((b << logR) & 15) == 0:
             gidx = np.arange((b << logR) >> 4)
             s = a + 16 * gidx[:, None] + np.arange(16)[None, :]
             add(s, gidx % nt, False); add(s, gidx % nt, True)
@@ -868,6 +919,14 @@ def task_accesses(t, log2_Np):
             if flags & FFT_PACK:
                 sel = blk < g
                 add(s[sel] - a + f, (u % nt)[sel], False)
+        more = (h & 0xffffff) | (((int(t[11]) >> 4) & 0xfff) << 24)
+        while more & 0xfff:                             # chained passes touch the same slots, warp by warp
+            sub = t.copy()
+            sub[5], sub[6], sub[7] = more & 15, (more >> 4) & 7, (more >> 7) & 15
+            sub[4] = (b << logR) >> int(sub[6])
+            sub[10] = 0; sub[11] = 0
+            out += task_accesses(sub, log2_Np)
+            more >>= 12
     elif op == OP_MULFOLD:
         log_src, logk = b, c
         if logk >= 2:
@@ -997,7 +1056,7 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
         keep = elide_barriers(tasks, ranges, capacity, geo.J_pad)
         for st in range(ranges.shape[0]):
             if not keep[st]:
-                tasks[ranges[st, 0]:ranges[st, 1], 11] = 1
+                tasks[ranges[st, 0]:ranges[st, 1], 11] |= 1
                 n_relaxed += 1
     stats = dict(n_steps=len(steps), n_tasks=n_tasks, n_relaxed=n_relaxed, smem_logical=high,
                  mean_tasks_per_step=n_tasks / max(1, len(steps)), **sched)
