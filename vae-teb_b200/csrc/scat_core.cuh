@@ -106,22 +106,59 @@ TEB_D float teb_sqrt(float v) {
 #endif
 
 // ---- complex helpers -----------------------------------------------------------
+// On the device every complex operation is written with the PACKED fp32 forms of sm_100
+// (add/mul/fma.rn.f32x2 on a 64-bit register pair): measured on B200 (tools/micro/fp2_rate.cu) the scalar
+// forms are limited by register-operand bandwidth -- FADD 93, three-register FFMA 62 lane-ops/cycle/SM --
+// while FADD2/FMUL2 reach 124 and FFMA2 82, in half the issue slots.  ptxas folds the mov.b64 packs below
+// into operand modifiers (broadcast .F32, swap .LO_HI, per-half negation), so a complex add is ONE
+// instruction and a complex multiply TWO.  The formulas -- which product is rounded, which is fused -- are
+// the same in the scalar host versions, so the host emulator stays bit-comparable.
+#ifdef TEBSCAT_HOST_EMU
 TEB_D float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 TEB_D float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 TEB_D float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+    return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
 }
 TEB_D float2 cmulc(float2 a, float2 b) {   // a * conj(b)
-    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
-}
-// multiply by exp(SGN * i*pi/2)
-template <int SGN> TEB_D float2 rot90(float2 a) {
-    return SGN < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y)));
 }
 // multiply by the constant (c + SGN*i*s)
 template <int SGN> TEB_D float2 cmulk(float2 a, float c, float s) {
-    return SGN < 0 ? make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s))
-                   : make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.y, c, a.x * s));
+    return SGN < 0 ? make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -(a.x * s)))
+                   : make_float2(fmaf(a.x, c, -(a.y * s)), fmaf(a.y, c, a.x * s));
+}
+TEB_D float2 cmul_r(float2 z, float g) { return make_float2(z.x * g, z.y * g); }                 // z * real
+TEB_D float2 cfma_r(float2 z, float g, float2 acc) { return make_float2(fmaf(z.x, g, acc.x), fmaf(z.y, g, acc.y)); }
+#else
+typedef unsigned long long teb_u64;
+TEB_D teb_u64 pk(float x, float y) { teb_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+TEB_D teb_u64 pk(float2 a) { return pk(a.x, a.y); }
+TEB_D float2 unpk(teb_u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+TEB_D teb_u64 add2(teb_u64 a, teb_u64 b) { teb_u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+TEB_D teb_u64 mul2(teb_u64 a, teb_u64 b) { teb_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+TEB_D teb_u64 fma2(teb_u64 a, teb_u64 b, teb_u64 c) {
+    teb_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+TEB_D float2 cadd(float2 a, float2 b) { return unpk(add2(pk(a), pk(b))); }
+TEB_D float2 csub(float2 a, float2 b) { return unpk(add2(pk(a), pk(-b.x, -b.y))); }
+TEB_D float2 cmul(float2 a, float2 b) {
+    const float2 t = unpk(mul2(pk(a.y, a.y), pk(b.y, b.x)));             // (a.y b.y, a.y b.x)
+    return unpk(fma2(pk(a.x, a.x), pk(b), pk(-t.x, t.y)));
+}
+TEB_D float2 cmulc(float2 a, float2 b) {   // a * conj(b)
+    const float2 t = unpk(mul2(pk(b.y, b.y), pk(a.y, a.x)));             // (a.y b.y, a.x b.y)
+    return unpk(fma2(pk(b.x, b.x), pk(a), pk(t.x, -t.y)));
+}
+template <int SGN> TEB_D float2 cmulk(float2 a, float c, float s) {
+    const float2 t = unpk(mul2(pk(s, s), pk(a.y, a.x)));                 // (a.y s, a.x s)
+    return SGN < 0 ? unpk(fma2(pk(c, c), pk(a), pk(t.x, -t.y))) : unpk(fma2(pk(c, c), pk(a), pk(-t.x, t.y)));
+}
+TEB_D float2 cmul_r(float2 z, float g) { return unpk(mul2(pk(z), pk(g, g))); }
+TEB_D float2 cfma_r(float2 z, float g, float2 acc) { return unpk(fma2(pk(z), pk(g, g), pk(acc))); }
+#endif
+// multiply by exp(SGN * i*pi/2)
+template <int SGN> TEB_D float2 rot90(float2 a) {
+    return SGN < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
 }
 
 // shared-memory slot of logical complex index i: one pad slot after every 16.  It keeps
