@@ -108,6 +108,7 @@ class TaskSpec:
     f: object = 0                  # int, or (Buf, offset): partner region of a packed pass
     g: object = 0                  # int, or (Buf, offset): second destination of a MULFOLD2
     h: int = 0
+    trip: float = -1.0             # latency one more trip of a thread adds (default: instr)
     sexp: int = 0
     pad: int = 0                   # field 11: bit 0 = relaxed barrier (post-pass), bits 4..15 = third chained FFT pass
     channel: object = -1           # output channel(s) of a leaf MULFOLD: int or (real-part, imaginary-part or -1)
@@ -136,8 +137,8 @@ class Chain:
 # a step lasts  STEP_OVERHEAD + max_t(lat_t) + sum_t warps_t/4 * trips_t * instr_t  cycles, where lat is
 # the dependent-issue latency of one work item on an idle SM and instr the issue cycles one
 # more warp per scheduler adds (one R16 butterfly alone: 1850 cycles; 4 warps/scheduler: 3330).
-_FFT_LAT = {1: 350.0, 2: 500.0, 3: 800.0, 4: 1400.0}
-_FFT_INSTR = {1: 40.0, 2: 110.0, 3: 250.0, 4: 480.0}
+_FFT_LAT = {1: 350.0, 2: 450.0, 3: 600.0, 4: 800.0}
+_FFT_INSTR = {1: 40.0, 2: 90.0, 3: 180.0, 4: 330.0}
 STEP_OVERHEAD = 450.0
 
 
@@ -318,20 +319,28 @@ def _fuse_first_inverse_pass(mulfolds: List[TaskSpec], stages: List[List[TaskSpe
 
 def _mulfold(arena: _Arena, src, log_src: int, logk: int, dst, filt_off: int, channel: int = -1) -> TaskSpec:
     log_dst = log_src - logk
+    trip = -1.0
     if logk >= 2:
         mask = arena.chunk_mask(filt_off, logk)
-        nch = bin(mask).count('1') << (_Arena.chunk_log2(logk) - 2)     # in units of four bins
+        logcw = _Arena.chunk_log2(logk)
+        nch = bin(mask).count('1') << (logcw - 2)     # in units of four bins
         filt_off = arena.compact(filt_off, logk, mask)
-        # the kernel takes four outputs per thread and trip
-        work, lat, instr = -(-(1 << log_dst) // 4), 900.0 + 150.0 * nch, 250.0 + 200.0 * nch
+        # the kernel takes four outputs per thread and trip; every trip is one L2 round trip when at most two
+        # chunks are active, one per chunk otherwise (measured: tools/step_floor.py, tools/step_phases.py)
+        work = -(-(1 << log_dst) // 4)
+        if nch <= 2 and logcw == 2:
+            lat, instr, trip = 1300.0 + 250.0 * nch, 100.0 + 120.0 * nch, 600.0 + 150.0 * nch
+        else:
+            lat, instr, trip = 800.0 + 1000.0 * nch, 100.0 + 120.0 * nch, 300.0 + 900.0 * nch
     else:
         mask = 0
-        work, lat, instr = 1 << (log_src - 2), 700.0, 120.0
+        # four 4-slot items per thread are in flight together (one L2 round trip per group of four)
+        work, lat, instr, trip = -(-(1 << (log_src - 2)) // 4), 2300.0, 320.0, 2000.0
     # mean over k blocks (2^-logk) and the 1/L of the following inverse transform (2^-log_dst)
     if mask >= 1 << 31:
         mask -= 1 << 32                                    # the task table holds int32 fields
     return TaskSpec(OP_MULFOLD, work, lat, instr, a=src, b=log_src, c=logk, d=dst, e=filt_off, f=mask,
-                    h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst, channel=channel)
+                    h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst, channel=channel, trip=trip)
 
 
 def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_off: int) -> TaskSpec:
@@ -343,17 +352,17 @@ def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_of
         nch = bin(mask).count('1') << (logcw - 2)
         filt_off = arena.compact(filt_off, logk, mask)
         if nch <= 2 and logcw == 2:                        # four outputs per thread and trip, loads up front
-            work, lat, instr = -(-(1 << log_dst) // 4), 1100.0 + 250.0 * nch, 150.0 + 420.0 * nch
+            work, lat, instr, trip = -(-(1 << log_dst) // 4), 1700.0 + 500.0 * nch, 150.0 + 250.0 * nch, 1200.0 + 500.0 * nch
         else:                                              # two outputs per trip, one L2 round trip per chunk
-            work, lat, instr = -(-(1 << log_dst) // 2), 900.0 + 700.0 * nch, 100.0 + 220.0 * nch
+            work, lat, instr, trip = -(-(1 << log_dst) // 2), 900.0 + 1100.0 * nch, 100.0 + 150.0 * nch, 300.0 + 1000.0 * nch
     else:
         mask = 0
-        work, lat, instr = 1 << (log_src - 4), 1300.0, 520.0          # four 4-slot items per thread and trip
+        work, lat, instr, trip = 1 << (log_src - 4), 2600.0, 500.0, 2400.0       # four 4-slot items per thread and trip
     if mask >= 1 << 31:
         mask -= 1 << 32
     # mean over k blocks, 1/L of the inverse transform, and the 1/2 of the pair separation
     return TaskSpec(OP_MULFOLD2, work, lat, instr, a=src, b=log_src, c=logk, d=dst_a, e=filt_off, f=mask, g=dst_b,
-                    h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst + 1)
+                    h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst + 1, trip=trip)
 
 
 # ------------------------------------------------------------------------------------
@@ -577,7 +586,7 @@ def _step_time(items: List[Tuple[TaskSpec, int]]) -> float:
     issue = 0.0
     for t, nt in items:
         trips = math.ceil(t.work * t.tpi / nt)
-        lat = max(lat, t.lat + (trips - 1) * t.instr)
+        lat = max(lat, t.lat + (trips - 1) * (t.trip if t.trip >= 0 else t.instr))
         issue += (nt / 128.0) * trips * t.instr
     return STEP_OVERHEAD + lat + issue
 
@@ -591,7 +600,8 @@ def _split_threads(tasks: List[TaskSpec]) -> Optional[List[int]]:
     nts = [32] * n
     left = N_THREADS - 32 * n
     while left > 0:
-        times = [(math.ceil(t.work * t.tpi / nt) - 1) * t.instr + t.lat for t, nt in zip(tasks, nts)]
+        times = [(math.ceil(t.work * t.tpi / nt) - 1) * (t.trip if t.trip >= 0 else t.instr) + t.lat
+                 for t, nt in zip(tasks, nts)]
         order = sorted(range(n), key=lambda i: -times[i])
         grew = False
         for i in order:
