@@ -61,22 +61,25 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 
 // One CTA per SM, persistent over the batch: signal b, b + gridDim.x, ...
-// Every warp walks its own column of the task table.  A 12-int record is held ONE INT PER
-// LANE (lane l keeps field l), so the two records prefetched ahead of the executing one
-// cost two registers, and the fields are broadcast with shuffles when the step starts.
-// Descriptor latency (an L2 hit) therefore never sits between two barriers.
-__device__ __forceinline__ int fetch_field(const int32_t* p) {
-    // volatile: the prefetch must be ISSUED here, two steps ahead of its use; as a plain load
-    // the compiler sinks it to the consumer behind the barrier and the L2 latency is exposed
-    int v;
-    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
+// Every warp walks its own column of the task table.  The 12-int records travel global -> shared with
+// cp.async, two steps ahead of their use, into a three-deep ring per warp: no register is held across a
+// task body (the butterflies use all 128 -- a register-held prefetch gets spilled to local memory, which
+// with the whole L1 carved out as shared memory is an L2 round trip at the start of every step), and the
+// fields are read back one per lane and broadcast with shuffles when the step starts.
+constexpr int kRing = 3;
+
+__device__ __forceinline__ void fetch_record(int32_t* dst_smem, const int32_t* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src));
 }
+__device__ __forceinline__ void fetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fetch_wait_all_but_2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 
 template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ out, long long B) {
     extern __shared__ __align__(16) float2 smem[];
+    __shared__ __align__(16) int32_t ring[kRing][kWarps][kTaskInts];
     float2* S = smem;
     float2* twA = smem + p.smem_complex;
     float2* twB = twA + kTwAP;
@@ -85,12 +88,16 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int32_t* tab = reinterpret_cast<const int32_t*>(p.warp_tab) + kTaskInts * warp + (lane < kTaskInts ? lane : 0);
+    const int32_t* tab = reinterpret_cast<const int32_t*>(p.warp_tab) + kTaskInts * warp + lane;
     const int stride = kTaskInts * kWarps;
     const int n_steps = p.n_steps;
-    int cur = fetch_field(tab);
-    int nxt = fetch_field(tab + stride * (1 % n_steps));
-    int s_fetch = 2 % n_steps;
+    // records of the first two steps
+    if (lane < kTaskInts) fetch_record(&ring[0][warp][lane], tab);
+    fetch_commit();
+    if (lane < kTaskInts) fetch_record(&ring[1][warp][lane], tab + stride * (1 % n_steps));
+    fetch_commit();
+    int s_fetch = 2 % n_steps;       // step whose record is fetched next (wraps into the next signal)
+    int slot = 0;                    // ring slot of the step about to run
     __shared__ SignalCtx c;          // per-signal context lives in shared memory: nothing to keep in
                                      // registers across the (partly out-of-line) task bodies
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
@@ -109,9 +116,19 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
         __syncthreads();             // (the last step of the previous signal ended in a barrier too)
         const bool prof = PROF && blockIdx.x == 0 && b == blockIdx.x && tid == 0;
         for (int s = 0; s < n_steps; ++s) {
-            const int fut = fetch_field(tab + stride * s_fetch);       // wraps into the next signal
-            s_fetch = (s_fetch + 1 == n_steps) ? 0 : s_fetch + 1;
+            {   // prefetch the record two steps ahead into the slot the previous step has just released
+                const int fslot = slot == 0 ? kRing - 1 : slot - 1;
+                if (lane < kTaskInts) fetch_record(&ring[fslot][warp][lane], tab + stride * s_fetch);
+                fetch_commit();
+                s_fetch = (s_fetch + 1 == n_steps) ? 0 : s_fetch + 1;
+            }
             if (prof) p.prof[s] = clock64();
+            fetch_wait_all_but_2();  // this step's record has landed (issued two steps ago)
+            __syncwarp();
+            // one field per lane, broadcast with shuffles: the compiler keeps shuffle-broadcast values in
+            // UNIFORM registers, which the task bodies do not compete for
+            const int cur = ring[slot][warp][lane < kTaskInts ? lane : 0];
+            slot = slot + 1 == kRing ? 0 : slot + 1;
             const int op = __shfl_sync(0xffffffffu, cur, 0);
             const int f11 = __shfl_sync(0xffffffffu, cur, 11);
             const int warp_sync_only = f11 & 1;
@@ -143,8 +160,6 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
 #ifdef TEBSCAT_PROF_PHASES
             if (prof) p.prof[n_steps + 3 + 3 * s] = clock64();
 #endif
-            cur = nxt;
-            nxt = fut;
         }
         if (prof) p.prof[n_steps] = clock64();
     }
