@@ -30,6 +30,7 @@ def run(tasks_per_step, label):
     start = clk[:ns]; ph = clk[ns + 1:].reshape(ns, 3)
     r = np.stack([ph[:, 0] - start, ph[:, 1] - ph[:, 0], ph[:, 2] - ph[:, 1], clk[1:ns + 1] - start], 1)[4:]
     n = max(1, d[3])
+    print('   last step: decode-end -> fft_task %d -> fft_pass %d -> butterfly start %d cycles' % (d[4] - d[7], d[5] - d[4], d[6] - d[5]))
     print('%-40s step %5d = decode %4d + body %5d + bar-issue %4d + rest %4d | butterfly: setup+loads %4d dft %4d twiddle+store %4d' % (
         label, np.median(r[:, 3]), np.median(r[:, 0]), np.median(r[:, 1]), np.median(r[:, 2]),
         np.median(r[:, 3] - r[:, 0] - r[:, 1] - r[:, 2]), d[0] // n, d[1] // n, d[2] // n))

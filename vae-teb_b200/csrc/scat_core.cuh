@@ -275,7 +275,7 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
 #ifdef TEBSCAT_PROF_BFLY
     const bool dbg = threadIdx.x == 0 && blockIdx.x == 0 && !INV && LOGR == 4;
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    if (dbg) c0 = clock64();
+    if (dbg) { c0 = clock64(); g_bfly_dbg[6] = c0; }
 #endif
     const int logs = logB - LOGR;                  // log2 of the sub-block stride
     const int i0 = u & ((1 << logs) - 1);
@@ -303,11 +303,11 @@ TEB_D void fft_butterfly(float2* S, const float2* twA, const float2* twB, int ba
     if (!INV) {
         TEB_UNROLL for (int j = 0; j < R; ++j) v[j] = sld(S, TEB_SLOT(j));
 #ifdef TEBSCAT_PROF_BFLY
-        if (dbg) { float sink = 0.f; TEB_UNROLL for (int j = 0; j < R; ++j) sink += v[j].x; if (sink == 1234.5f) g_bfly_dbg[7] = 1; c1 = clock64(); }
+        if (dbg) { float sink = 0.f; TEB_UNROLL for (int j = 0; j < R; ++j) sink += v[j].x; if (sink == 1234.5f) g_bfly_dbg[3] = 1; c1 = clock64(); }
 #endif
         Dft<R, -1>::run(v);
 #ifdef TEBSCAT_PROF_BFLY
-        if (dbg) { float sink = 0.f; TEB_UNROLL for (int j = 0; j < R; ++j) sink += v[j].x + v[j].y; if (sink == 1234.5f) g_bfly_dbg[7] = 1; c2 = clock64(); }
+        if (dbg) { float sink = 0.f; TEB_UNROLL for (int j = 0; j < R; ++j) sink += v[j].x + v[j].y; if (sink == 1234.5f) g_bfly_dbg[3] = 1; c2 = clock64(); }
 #endif
         TEB_UNROLL for (int r = 0; r < R; ++r) {
             const int q = qmap<R>(r);
@@ -394,6 +394,9 @@ template <int LOGR>
 TEB_D void fft_pass(float2* S, const float2* twA, const float2* twB, const Task& t, int lt, int logB, int flags,
                     int slots) {
     const int n_bfly = slots >> LOGR;
+#ifdef TEBSCAT_PROF_BFLY
+    if (threadIdx.x == 0 && blockIdx.x == 0 && LOGR == 4) g_bfly_dbg[5] = clock64();
+#endif
     const bool inv = (flags & FFT_INV) != 0, mod = (flags & FFT_MOD) != 0, fuse = (flags & FFT_FUSE_FWD) != 0;
     if (LOGR <= 3 && logB == LOGR && !mod && ((slots & 15) == 0)) {
         const int n_groups = slots >> 4;
@@ -436,15 +439,17 @@ TEB_D int task_passes(const Task& t) {
 TEB_D void fft_task_pass(float2* S, const float2* twA, const float2* twB, const Task& t, int lt, int logB, int logR,
                          int flags) {
     const int slots = t.b << t.d;
-    switch (logR) {
-        case 4: fft_pass<4>(S, twA, twB, t, lt, logB, flags, slots); break;
-        case 3: fft_pass<3>(S, twA, twB, t, lt, logB, flags, slots); break;
-        case 2: fft_pass<2>(S, twA, twB, t, lt, logB, flags, slots); break;
-        default: fft_pass<1>(S, twA, twB, t, lt, logB, flags, slots); break;
-    }
+    // (an if-chain, radix 16 first: no jump table through the constant cache on the hot path)
+    if (logR == 4) fft_pass<4>(S, twA, twB, t, lt, logB, flags, slots);
+    else if (logR == 3) fft_pass<3>(S, twA, twB, t, lt, logB, flags, slots);
+    else if (logR == 2) fft_pass<2>(S, twA, twB, t, lt, logB, flags, slots);
+    else fft_pass<1>(S, twA, twB, t, lt, logB, flags, slots);
 }
 #ifndef TEBSCAT_HOST_EMU
 TEB_D void fft_task(float2* S, const float2* twA, const float2* twB, const Task& t, int lt) {
+#ifdef TEBSCAT_PROF_BFLY
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_bfly_dbg[4] = clock64();
+#endif
     unsigned long long more = fft_more_passes(t);
     int logB = t.c, logR = t.d, flags = t.e;
     for (;;) {
@@ -514,6 +519,7 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
     const int logk = t.c;
     const float scale = ldexpf(1.0f, -(t.op >> 8));
     const float* f = arena + t.e;
+    const float2 zero = make_float2(0.f, 0.f);
     if (logk >= 2) {
         // Filter layout for k >= 4: COMPACTED by the host to the active chunks only,
         // f[(m * nch + c) * 4 + r], so that consecutive outputs read consecutive memory
@@ -541,20 +547,18 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
                     const int m = m0 + j * t.nt;
                     if (m < n_dst) {
                         const int q = swz(t.a + (m << logk) + i0);
-                        const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
-                        float ax = z0.x * g0[j].x, ay = z0.y * g0[j].x;
-                        ax = fmaf(z1.x, g0[j].y, ax); ay = fmaf(z1.y, g0[j].y, ay);
-                        ax = fmaf(z2.x, g0[j].z, ax); ay = fmaf(z2.y, g0[j].z, ay);
-                        ax = fmaf(z3.x, g0[j].w, ax); ay = fmaf(z3.y, g0[j].w, ay);
+                        float2 acc = cmul_r(S[q], g0[j].x);
+                        acc = cfma_r(S[q + 1], g0[j].y, acc);
+                        acc = cfma_r(S[q + 2], g0[j].z, acc);
+                        acc = cfma_r(S[q + 3], g0[j].w, acc);
                         if (m2) {
                             const int r = swz(t.a + (m << logk) + i1);
-                            const float2 y0 = S[r], y1 = S[r + 1], y2 = S[r + 2], y3 = S[r + 3];
-                            ax = fmaf(y0.x, g1[j].x, ax); ay = fmaf(y0.y, g1[j].x, ay);
-                            ax = fmaf(y1.x, g1[j].y, ax); ay = fmaf(y1.y, g1[j].y, ay);
-                            ax = fmaf(y2.x, g1[j].z, ax); ay = fmaf(y2.y, g1[j].z, ay);
-                            ax = fmaf(y3.x, g1[j].w, ax); ay = fmaf(y3.y, g1[j].w, ay);
+                            acc = cfma_r(S[r], g1[j].x, acc);
+                            acc = cfma_r(S[r + 1], g1[j].y, acc);
+                            acc = cfma_r(S[r + 2], g1[j].z, acc);
+                            acc = cfma_r(S[r + 3], g1[j].w, acc);
                         }
-                        S[swz(t.d + m)] = make_float2(ax * scale, ay * scale);
+                        S[swz(t.d + m)] = cmul_r(acc, scale);
                     }
                 }
             }
@@ -563,7 +567,7 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
         // four outputs per thread and trip: the chunk loop is uniform over the task, so the
         // four 128-bit filter loads of one chunk are in flight together
         for (int m0 = lt; m0 < n_dst; m0 += 4 * t.nt) {
-            float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f};
+            float2 acc[4] = {zero, zero, zero, zero};
             unsigned rest = mask;
             int c = 0;
             while (rest) {
@@ -581,18 +585,17 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
                         const int m = m0 + j * t.nt;
                         if (m < n_dst) {
                             const int q = swz(t.a + (m << logk) + i);      // 4 slots of one 16-group: contiguous
-                            const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
-                            ax[j] = fmaf(z0.x, g[j].x, ax[j]); ay[j] = fmaf(z0.y, g[j].x, ay[j]);
-                            ax[j] = fmaf(z1.x, g[j].y, ax[j]); ay[j] = fmaf(z1.y, g[j].y, ay[j]);
-                            ax[j] = fmaf(z2.x, g[j].z, ax[j]); ay[j] = fmaf(z2.y, g[j].z, ay[j]);
-                            ax[j] = fmaf(z3.x, g[j].w, ax[j]); ay[j] = fmaf(z3.y, g[j].w, ay[j]);
+                            acc[j] = cfma_r(S[q], g[j].x, acc[j]);
+                            acc[j] = cfma_r(S[q + 1], g[j].y, acc[j]);
+                            acc[j] = cfma_r(S[q + 2], g[j].z, acc[j]);
+                            acc[j] = cfma_r(S[q + 3], g[j].w, acc[j]);
                         }
                     }
                 }
             }
             TEB_UNROLL for (int j = 0; j < 4; ++j) {
                 const int m = m0 + j * t.nt;
-                if (m < n_dst) S[swz(t.d + m)] = make_float2(ax[j] * scale, ay[j] * scale);
+                if (m < n_dst) S[swz(t.d + m)] = cmul_r(acc[j], scale);
             }
         }
     } else {
@@ -603,10 +606,10 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
             const float2 z0 = S[q], z1 = S[q + 1], z2 = S[q + 2], z3 = S[q + 3];
             if (logk == 0) {
                 const int o = swz(t.d + 4 * it);
-                float2 w0 = make_float2(z0.x * g.x * scale, z0.y * g.x * scale);
-                float2 w1 = make_float2(z1.x * g.y * scale, z1.y * g.y * scale);
-                float2 w2 = make_float2(z2.x * g.z * scale, z2.y * g.z * scale);
-                float2 w3 = make_float2(z3.x * g.w * scale, z3.y * g.w * scale);
+                float2 w0 = cmul_r(z0, g.x * scale);
+                float2 w1 = cmul_r(z1, g.y * scale);
+                float2 w2 = cmul_r(z2, g.z * scale);
+                float2 w3 = cmul_r(z3, g.w * scale);
                 // optionally the first (unit-stride, twiddle-free) inverse pass of the transform
                 // that follows, on the four slots this thread owns: one round trip less
                 if (t.g == 1) {
@@ -623,8 +626,8 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
                 S[o + 3] = w3;
             } else {
                 const int o = swz(t.d + 2 * it);
-                S[o] = make_float2(fmaf(z0.x, g.x, z1.x * g.y) * scale, fmaf(z0.y, g.x, z1.y * g.y) * scale);
-                S[o + 1] = make_float2(fmaf(z2.x, g.z, z3.x * g.w) * scale, fmaf(z2.y, g.z, z3.y * g.w) * scale);
+                S[o] = cmul_r(cfma_r(z0, g.x, cmul_r(z1, g.y)), scale);
+                S[o + 1] = cmul_r(cfma_r(z2, g.z, cmul_r(z3, g.w)), scale);
             }
         }
     }
@@ -651,10 +654,19 @@ TEB_D void load_group_and_mirror(const float2* S, int base, int p, float2 (&z)[4
     }
 }
 
+// outputs of one packed-source bin: A = sum f Z[p], Bc = sum f Z[mirror(p)]
+//   dst_a = (A + conj Bc) * scale,   dst_b = -i (A - conj Bc) * scale
+TEB_D void mulfold2_store(float2* S, int oa, int ob, float2 A, float2 Bc, float scale) {
+    const float2 cb = make_float2(Bc.x, -Bc.y);
+    S[oa] = cmul_r(cadd(A, cb), scale);
+    S[ob] = cmul_r(rot90<-1>(csub(A, cb)), scale);
+}
+
 TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task& t, int lt) {
     const int logk = t.c;
     const float scale = ldexpf(1.0f, -(t.op >> 8));
     const float* f = arena + t.e;
+    const float2 zero = make_float2(0.f, 0.f);
     if (logk >= 2) {
         const int n_dst = 1 << (t.b - logk);
         const unsigned mask = (unsigned)t.f;
@@ -680,33 +692,25 @@ TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task&
                     if (m < n_dst) {
                         float2 z[4], y[4];
                         load_group_and_mirror(S, t.a, (m << logk) + i0, z, y);
-                        float ax = z[0].x * g0[j].x, ay = z[0].y * g0[j].x, bx = y[0].x * g0[j].x, by = y[0].y * g0[j].x;
-                        ax = fmaf(z[1].x, g0[j].y, ax); ay = fmaf(z[1].y, g0[j].y, ay);
-                        bx = fmaf(y[1].x, g0[j].y, bx); by = fmaf(y[1].y, g0[j].y, by);
-                        ax = fmaf(z[2].x, g0[j].z, ax); ay = fmaf(z[2].y, g0[j].z, ay);
-                        bx = fmaf(y[2].x, g0[j].z, bx); by = fmaf(y[2].y, g0[j].z, by);
-                        ax = fmaf(z[3].x, g0[j].w, ax); ay = fmaf(z[3].y, g0[j].w, ay);
-                        bx = fmaf(y[3].x, g0[j].w, bx); by = fmaf(y[3].y, g0[j].w, by);
+                        float2 A = cmul_r(z[0], g0[j].x), Bc = cmul_r(y[0], g0[j].x);
+                        A = cfma_r(z[1], g0[j].y, A); Bc = cfma_r(y[1], g0[j].y, Bc);
+                        A = cfma_r(z[2], g0[j].z, A); Bc = cfma_r(y[2], g0[j].z, Bc);
+                        A = cfma_r(z[3], g0[j].w, A); Bc = cfma_r(y[3], g0[j].w, Bc);
                         if (m2) {
                             load_group_and_mirror(S, t.a, (m << logk) + i1, z, y);
-                            ax = fmaf(z[0].x, g1[j].x, ax); ay = fmaf(z[0].y, g1[j].x, ay);
-                            bx = fmaf(y[0].x, g1[j].x, bx); by = fmaf(y[0].y, g1[j].x, by);
-                            ax = fmaf(z[1].x, g1[j].y, ax); ay = fmaf(z[1].y, g1[j].y, ay);
-                            bx = fmaf(y[1].x, g1[j].y, bx); by = fmaf(y[1].y, g1[j].y, by);
-                            ax = fmaf(z[2].x, g1[j].z, ax); ay = fmaf(z[2].y, g1[j].z, ay);
-                            bx = fmaf(y[2].x, g1[j].z, bx); by = fmaf(y[2].y, g1[j].z, by);
-                            ax = fmaf(z[3].x, g1[j].w, ax); ay = fmaf(z[3].y, g1[j].w, ay);
-                            bx = fmaf(y[3].x, g1[j].w, bx); by = fmaf(y[3].y, g1[j].w, by);
+                            A = cfma_r(z[0], g1[j].x, A); Bc = cfma_r(y[0], g1[j].x, Bc);
+                            A = cfma_r(z[1], g1[j].y, A); Bc = cfma_r(y[1], g1[j].y, Bc);
+                            A = cfma_r(z[2], g1[j].z, A); Bc = cfma_r(y[2], g1[j].z, Bc);
+                            A = cfma_r(z[3], g1[j].w, A); Bc = cfma_r(y[3], g1[j].w, Bc);
                         }
-                        S[swz(t.d + m)] = make_float2((ax + bx) * scale, (ay - by) * scale);
-                        S[swz(t.g + m)] = make_float2((ay + by) * scale, (bx - ax) * scale);
+                        mulfold2_store(S, swz(t.d + m), swz(t.g + m), A, Bc, scale);
                     }
                 }
             }
             return;
         }
         for (int m0 = lt; m0 < n_dst; m0 += 2 * t.nt) {
-            float ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f}, bx[2] = {0.f, 0.f}, by[2] = {0.f, 0.f};
+            float2 A[2] = {zero, zero}, Bc[2] = {zero, zero};
             unsigned rest = mask;
             int c = 0;
             while (rest) {
@@ -725,24 +729,17 @@ TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task&
                         if (m < n_dst) {
                             float2 z[4], y[4];
                             load_group_and_mirror(S, t.a, (m << logk) + i, z, y);
-                            ax[j] = fmaf(z[0].x, g[j].x, ax[j]); ay[j] = fmaf(z[0].y, g[j].x, ay[j]);
-                            ax[j] = fmaf(z[1].x, g[j].y, ax[j]); ay[j] = fmaf(z[1].y, g[j].y, ay[j]);
-                            ax[j] = fmaf(z[2].x, g[j].z, ax[j]); ay[j] = fmaf(z[2].y, g[j].z, ay[j]);
-                            ax[j] = fmaf(z[3].x, g[j].w, ax[j]); ay[j] = fmaf(z[3].y, g[j].w, ay[j]);
-                            bx[j] = fmaf(y[0].x, g[j].x, bx[j]); by[j] = fmaf(y[0].y, g[j].x, by[j]);
-                            bx[j] = fmaf(y[1].x, g[j].y, bx[j]); by[j] = fmaf(y[1].y, g[j].y, by[j]);
-                            bx[j] = fmaf(y[2].x, g[j].z, bx[j]); by[j] = fmaf(y[2].y, g[j].z, by[j]);
-                            bx[j] = fmaf(y[3].x, g[j].w, bx[j]); by[j] = fmaf(y[3].y, g[j].w, by[j]);
+                            A[j] = cfma_r(z[0], g[j].x, A[j]); Bc[j] = cfma_r(y[0], g[j].x, Bc[j]);
+                            A[j] = cfma_r(z[1], g[j].y, A[j]); Bc[j] = cfma_r(y[1], g[j].y, Bc[j]);
+                            A[j] = cfma_r(z[2], g[j].z, A[j]); Bc[j] = cfma_r(y[2], g[j].z, Bc[j]);
+                            A[j] = cfma_r(z[3], g[j].w, A[j]); Bc[j] = cfma_r(y[3], g[j].w, Bc[j]);
                         }
                     }
                 }
             }
             TEB_UNROLL for (int j = 0; j < 2; ++j) {
                 const int m = m0 + j * t.nt;
-                if (m < n_dst) {
-                    S[swz(t.d + m)] = make_float2((ax[j] + bx[j]) * scale, (ay[j] - by[j]) * scale);
-                    S[swz(t.g + m)] = make_float2((ay[j] + by[j]) * scale, (bx[j] - ax[j]) * scale);
-                }
+                if (m < n_dst) mulfold2_store(S, swz(t.d + m), swz(t.g + m), A[j], Bc[j], scale);
             }
         }
     } else {
@@ -759,29 +756,17 @@ TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task&
                 const float4 g = gg[j];
                 float2 z[4], y[4];
                 load_group_and_mirror(S, t.a, 4 * it, z, y);
-                // per-slot products A_r = f_r Z_r, Bc_r = f_r Z_mirror(r)
-                const float a0x = z[0].x * g.x, a0y = z[0].y * g.x, b0x = y[0].x * g.x, b0y = y[0].y * g.x;
-                const float a1x = z[1].x * g.y, a1y = z[1].y * g.y, b1x = y[1].x * g.y, b1y = y[1].y * g.y;
-                const float a2x = z[2].x * g.z, a2y = z[2].y * g.z, b2x = y[2].x * g.z, b2y = y[2].y * g.z;
-                const float a3x = z[3].x * g.w, a3y = z[3].y * g.w, b3x = y[3].x * g.w, b3y = y[3].y * g.w;
                 if (logk == 0) {
                     const int oa = swz(t.d + 4 * it), ob = swz(t.g + 4 * it);
-                    S[oa] = make_float2((a0x + b0x) * scale, (a0y - b0y) * scale);
-                    S[oa + 1] = make_float2((a1x + b1x) * scale, (a1y - b1y) * scale);
-                    S[oa + 2] = make_float2((a2x + b2x) * scale, (a2y - b2y) * scale);
-                    S[oa + 3] = make_float2((a3x + b3x) * scale, (a3y - b3y) * scale);
-                    S[ob] = make_float2((a0y + b0y) * scale, (b0x - a0x) * scale);
-                    S[ob + 1] = make_float2((a1y + b1y) * scale, (b1x - a1x) * scale);
-                    S[ob + 2] = make_float2((a2y + b2y) * scale, (b2x - a2x) * scale);
-                    S[ob + 3] = make_float2((a3y + b3y) * scale, (b3x - a3x) * scale);
+                    mulfold2_store(S, oa, ob, cmul_r(z[0], g.x), cmul_r(y[0], g.x), scale);
+                    mulfold2_store(S, oa + 1, ob + 1, cmul_r(z[1], g.y), cmul_r(y[1], g.y), scale);
+                    mulfold2_store(S, oa + 2, ob + 2, cmul_r(z[2], g.z), cmul_r(y[2], g.z), scale);
+                    mulfold2_store(S, oa + 3, ob + 3, cmul_r(z[3], g.w), cmul_r(y[3], g.w), scale);
                 } else {
                     const int oa = swz(t.d + 2 * it), ob = swz(t.g + 2 * it);
-                    const float Ax0 = a0x + a1x, Ay0 = a0y + a1y, Bx0 = b0x + b1x, By0 = b0y + b1y;
-                    const float Ax1 = a2x + a3x, Ay1 = a2y + a3y, Bx1 = b2x + b3x, By1 = b2y + b3y;
-                    S[oa] = make_float2((Ax0 + Bx0) * scale, (Ay0 - By0) * scale);
-                    S[oa + 1] = make_float2((Ax1 + Bx1) * scale, (Ay1 - By1) * scale);
-                    S[ob] = make_float2((Ay0 + By0) * scale, (Bx0 - Ax0) * scale);
-                    S[ob + 1] = make_float2((Ay1 + By1) * scale, (Bx1 - Ax1) * scale);
+                    mulfold2_store(S, oa, ob, cfma_r(z[0], g.x, cmul_r(z[1], g.y)), cfma_r(y[0], g.x, cmul_r(y[1], g.y)), scale);
+                    mulfold2_store(S, oa + 1, ob + 1, cfma_r(z[2], g.z, cmul_r(z[3], g.w)),
+                                   cfma_r(y[2], g.z, cmul_r(y[3], g.w)), scale);
                 }
             }
         }

@@ -149,6 +149,9 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
 #ifdef TEBSCAT_PROF_PHASES
                 if (prof) p.prof[n_steps + 1 + 3 * s] = clock64();
 #endif
+#ifdef TEBSCAT_PROF_BFLY
+                if (tid == 0 && blockIdx.x == 0) tebscat::g_bfly_dbg[7] = clock64();
+#endif
                 exec_task(S, twA, twB, p.arena, c, t, tid - t.t0);
 #ifdef TEBSCAT_PROF_PHASES
                 if (prof) p.prof[n_steps + 2 + 3 * s] = clock64();
