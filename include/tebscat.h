@@ -79,6 +79,26 @@ void tebscat_plan_destroy(tebscat_plan* plan);
 int tebscat_scat1d_forward(const tebscat_plan* plan, const float* x_dev, int64_t B,
                            float* S_dev, void* stream);
 
+/* Output epilogue fused into the transform's stores: what CombinedHDF5Dataset.__getitem__ does
+ * to a stored `fhr_st` record before the model sees it --
+ *   trim `trim` decimated samples at both ends                  (hdf5_dataset/hdf5_dataset.py:733-741),
+ *   normalize_tensor_data: log(clamp(x, 0) + log_eps) or asinh(x) on the flagged channels, then
+ *   (x - mean[c]) / (std[c] + 1e-8)                             (hdf5_dataset/hdf5_dataset.py:96-135),
+ *   (channels, time) -> (time, channels)                        (hdf5_dataset/hdf5_dataset.py:758-759).
+ * All pointers are DEVICE pointers to n_paths entries; mode: 0 none, 1 log, 2 asinh. */
+typedef struct tebscat_epilogue {
+    const float* mean_dev;
+    const float* std_dev;
+    const unsigned char* mode_dev;
+    float log_eps;
+    int32_t trim;
+    int32_t time_major;    /* 1: out_dev is [B, n_out - 2 trim, n_paths]; 0: [B, n_paths, n_out - 2 trim] */
+} tebscat_epilogue;
+
+/* tebscat_scat1d_forward with the epilogue above (epilogue == NULL: identical to tebscat_scat1d_forward). */
+int tebscat_scat1d_forward_ex(const tebscat_plan* plan, const float* x_dev, int64_t B, float* out_dev,
+                              const tebscat_epilogue* epilogue, void* stream);
+
 /* Same transform with HOST buffers: pinned staging, chunked H2D / compute / D2H
  * overlap on the plan's own streams; returns when S_host is complete.  This is
  * the call the dataset builder makes per record

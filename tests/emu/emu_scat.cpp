@@ -17,7 +17,9 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
                                   int smem_complex, int n_tasks, int n_steps,
                                   const float* arena, const int32_t* tasks, const int32_t* steps,
                                   const int32_t* chan, const float* x, long long B, float* out,
-                                  float* zc, float* zp, int z_mode) {
+                                  float* zc, float* zp, int z_mode,
+                                  const float* ep_mean, const float* ep_std, const unsigned char* ep_mode,
+                                  float ep_log_eps, int ep_trim, int ep_time_major) {
     std::vector<float2> S((size_t)smem_complex);
     std::vector<float2> tw(kTwAP + kTwBP, make_float2(0.f, 0.f));
     const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
@@ -28,7 +30,9 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
         for (auto& z : S) z = make_float2(NAN, NAN);
         SignalCtx c;
         c.x = x + b * N;
-        c.out = out + b * (long long)n_paths * n_out;
+        c.out = out + b * (long long)n_paths * (ep_mean ? n_out - 2 * ep_trim : n_out);
+        c.ep_mean = ep_mean; c.ep_std = ep_std; c.ep_mode = ep_mode; c.ep_log_eps = ep_log_eps;
+        c.ep_trim = ep_trim; c.ep_time_major = ep_time_major; c.n_paths = n_paths;
         c.chan = chan;
         c.zc = reinterpret_cast<float2*>(zc) + b * (long long)n_paths * n_out;
         c.zp = reinterpret_cast<float2*>(zp) + b * (long long)n_paths * n_out;

@@ -36,13 +36,23 @@ def emu_available():
     return os.path.exists(EMU_PATH)
 
 
-def emu_forward(plan, x, stage_a=False):
+def emu_forward(plan, x, stage_a=False, epilogue=None):
     """Run the schedule of `plan` through the host emulator (tests/emu).  With stage_a=True the
     plan is a phase stage-A schedule and the (cartesian, polar) analytic signals are returned."""
     lib = ctypes.CDLL(EMU_PATH)
     x = np.ascontiguousarray(x, np.float32)
     B = x.shape[0]
-    out = np.full((B, plan.n_paths, plan.n_out) if not stage_a else (1,), np.nan, np.float32)
+    ep_mean = ep_std = ep_mode = None
+    ep_eps, ep_trim, ep_tm = 0.0, 0, 0
+    oshape = (B, plan.n_paths, plan.n_out)
+    if epilogue is not None:                      # dict(mean, std, mode, log_eps, trim, time_major): SURVEY 8f-2
+        ep_mean = np.ascontiguousarray(epilogue['mean'], np.float32)
+        ep_std = np.ascontiguousarray(epilogue['std'], np.float32)
+        ep_mode = np.ascontiguousarray(epilogue['mode'], np.uint8)
+        ep_eps, ep_trim, ep_tm = float(epilogue['log_eps']), int(epilogue['trim']), int(bool(epilogue['time_major']))
+        keep = plan.n_out - 2 * ep_trim
+        oshape = (B, keep, plan.n_paths) if ep_tm else (B, plan.n_paths, keep)
+    out = np.full(oshape if not stage_a else (1,), np.nan, np.float32)
     zshape = (B, plan.n_paths, plan.n_out, 2) if stage_a else (1,)
     zc, zp = np.full(zshape, np.nan, np.float32), np.full(zshape, np.nan, np.float32)
     fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
@@ -54,7 +64,11 @@ def emu_forward(plan, x, stage_a=False):
                                 plan.smem_complex, tasks.shape[0], steps.shape[0],
                                 arena.ctypes.data_as(fp), tasks.ctypes.data_as(ip), steps.ctypes.data_as(ip),
                                 chan.ctypes.data_as(ip), x.ctypes.data_as(fp), ctypes.c_longlong(B), out.ctypes.data_as(fp),
-                                zc.ctypes.data_as(fp), zp.ctypes.data_as(fp), 3 if stage_a else 0)
+                                zc.ctypes.data_as(fp), zp.ctypes.data_as(fp), 3 if stage_a else 0,
+                                ep_mean.ctypes.data_as(fp) if ep_mean is not None else None,
+                                ep_std.ctypes.data_as(fp) if ep_std is not None else None,
+                                ep_mode.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)) if ep_mode is not None else None,
+                                ctypes.c_float(ep_eps), ep_trim, ep_tm)
     assert rc == 0
     if stage_a:
         return zc[..., 0] + 1j * zc[..., 1], zp

@@ -83,7 +83,16 @@ struct SignalCtx {
     float2* zp;              // phase stage A: analytic signals of this job, polar (|z|, theta) [F][N]
     int32_t z_mode;          // Z_CART | Z_POLAR
     int32_t N, pad_left, log2_Np, n_out;
+    // optional output epilogue (hdf5_dataset/hdf5_dataset.py:18-137, :733-741, :758-759): per-channel
+    // log / asinh transform, (x - mean) / (std + 1e-8), trim of `trim` samples at both ends, and the
+    // (channels, time) -> (time, channels) transposition the model consumes
+    const float* ep_mean;    // [C] or null: no epilogue
+    const float* ep_std;     // [C]
+    const unsigned char* ep_mode;   // [C]: EP_NONE / EP_LOG / EP_ASINH
+    float ep_log_eps;
+    int32_t ep_trim, ep_time_major, n_paths;
 };
+enum : int32_t { EP_NONE = 0, EP_LOG = 1, EP_ASINH = 2 };
 
 constexpr int kLog2TwMax = 13;                 // twiddle tables cover lengths up to 8192
 constexpr int kTwA = 1 << (kLog2TwMax - 7);    // coarse table entries: W^(128 a)
@@ -795,6 +804,25 @@ TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
 // unpad (torch_backend.py:80-102) + concatenate (kymatio/backend/torch_backend.py:143-145)
 // for a pool of `b` finished low-pass outputs: slot s goes to channels chan[2 (e + s)] (real part)
 // and chan[2 (e + s) + 1] (imaginary part of a packed pair; -1 = none).
+// normalize_tensor_data (hdf5_dataset/hdf5_dataset.py:96-135) for one coefficient of channel ch
+TEB_D float epilogue_value(const SignalCtx& c, int ch, float v) {
+    const int mode = c.ep_mode[ch];
+    if (mode == EP_LOG) v = logf(fmaxf(v, 0.0f) + c.ep_log_eps);          // :107  log(clamp(x, min=0) + eps)
+    else if (mode == EP_ASINH) v = asinhf(v);                                // :118
+    return (v - c.ep_mean[ch]) / (c.ep_std[ch] + 1e-8f);                     // :133-135
+}
+TEB_D void store_coefficient(const SignalCtx& c, int ch, int n, float v) {
+    if (!c.ep_mean) {
+        c.out[(int64_t)ch * c.n_out + n] = v;
+        return;
+    }
+    const int n_keep = c.n_out - 2 * c.ep_trim, m = n - c.ep_trim;           // :733-741
+    if (m < 0 || m >= n_keep) return;
+    v = epilogue_value(c, ch, v);
+    if (c.ep_time_major) c.out[(int64_t)m * c.n_paths + ch] = v;             // :758-759
+    else c.out[(int64_t)ch * n_keep + m] = v;
+}
+
 TEB_D void storeb_task(const float2* S, const SignalCtx& c, const Task& t, int lt) {
     const int total = t.b * t.d;
     for (int i = lt; i < total; i += t.nt) {
@@ -802,8 +830,8 @@ TEB_D void storeb_task(const float2* S, const SignalCtx& c, const Task& t, int l
         // two channels per pool slot: the real part and, for a packed pair, the imaginary part
         const int ch_re = TEB_LDG(c.chan + 2 * (t.e + slot)), ch_im = TEB_LDG(c.chan + 2 * (t.e + slot) + 1);
         const float2 y = S[swz(t.a + (slot << t.f) + t.c + n)];
-        c.out[(int64_t)ch_re * c.n_out + n] = y.x;
-        if (ch_im >= 0) c.out[(int64_t)ch_im * c.n_out + n] = y.y;
+        store_coefficient(c, ch_re, n, y.x);
+        if (ch_im >= 0) store_coefficient(c, ch_im, n, y.y);
     }
 }
 

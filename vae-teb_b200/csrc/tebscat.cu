@@ -55,6 +55,12 @@ struct KParams {
     int32_t n_steps;
     int32_t smem_complex;
     int32_t N, pad_left, log2_Np, n_paths, n_out;
+    // output epilogue (null mean = none)
+    const float* ep_mean;
+    const float* ep_std;
+    const unsigned char* ep_mode;
+    float ep_log_eps;
+    int32_t ep_trim, ep_time_major;
 };
 
 constexpr int kThreads = 512;
@@ -103,7 +109,14 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         if (tid == 0) {
             c.x = x + b * p.x_stride;
-            c.out = out + b * (long long)p.n_paths * p.n_out;
+            c.out = out + b * (long long)p.n_paths * (p.ep_mean ? p.n_out - 2 * p.ep_trim : p.n_out);
+            c.ep_mean = p.ep_mean;
+            c.ep_std = p.ep_std;
+            c.ep_mode = p.ep_mode;
+            c.ep_log_eps = p.ep_log_eps;
+            c.ep_trim = p.ep_trim;
+            c.ep_time_major = p.ep_time_major;
+            c.n_paths = p.n_paths;
             c.chan = p.chan;
             c.zc = p.zc + b * p.z_stride;
             c.zp = p.zp + b * p.z_stride;
@@ -403,6 +416,12 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     k.log2_Np = desc->log2_Np;
     k.n_paths = desc->n_paths;
     k.n_out = desc->n_out;
+    k.ep_mean = nullptr;
+    k.ep_std = nullptr;
+    k.ep_mode = nullptr;
+    k.ep_log_eps = 0.f;
+    k.ep_trim = 0;
+    k.ep_time_major = 0;
     *out = p;
     return TEBSCAT_OK;
 }
@@ -444,6 +463,34 @@ extern "C" int tebscat_scat1d_forward(const tebscat_plan* p, const float* x_dev,
     int rc = launch_scat1d(p, x_dev, B, S_dev, (cudaStream_t)stream);
     if (cur != p->device && cur >= 0) cudaSetDevice(cur);
     return rc;
+}
+
+extern "C" int tebscat_scat1d_forward_ex(const tebscat_plan* p, const float* x_dev, int64_t B, float* out_dev,
+                                         const tebscat_epilogue* ep, void* stream) {
+    g_launches = 0;
+    if (!p || B < 0 || (B > 0 && (!x_dev || !out_dev))) return fail(TEBSCAT_EINVAL, "null argument");
+    if (!ep) return tebscat_scat1d_forward(p, x_dev, B, out_dev, stream);
+    if (!ep->mean_dev || !ep->std_dev || !ep->mode_dev) return fail(TEBSCAT_EINVAL, "epilogue: null statistics");
+    if (ep->trim < 0 || 2 * ep->trim >= p->desc.n_out)
+        return fail(TEBSCAT_EINVAL, "epilogue: trim %d leaves nothing of %d samples", ep->trim, p->desc.n_out);
+    if (B == 0) return TEBSCAT_OK;
+    int cur = -1;
+    CU(cudaGetDevice(&cur));
+    if (cur != p->device) CU(cudaSetDevice(p->device));
+    KParams kp = p->kp;
+    kp.ep_mean = ep->mean_dev;
+    kp.ep_std = ep->std_dev;
+    kp.ep_mode = ep->mode_dev;
+    kp.ep_log_eps = ep->log_eps;
+    kp.ep_trim = ep->trim;
+    kp.ep_time_major = ep->time_major ? 1 : 0;
+    const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
+    scat1d_kernel<false><<<grid, p->desc.n_threads, p->smem_bytes, (cudaStream_t)stream>>>(kp, x_dev, out_dev, (long long)B);
+    cudaError_t e = cudaGetLastError();
+    if (cur != p->device && cur >= 0) cudaSetDevice(cur);
+    if (e != cudaSuccess) return fail(TEBSCAT_ECUDA, "launch failed: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return TEBSCAT_OK;
 }
 
 extern "C" int tebscat_scat1d_profile_steps(const tebscat_plan* p, const float* x_dev, int64_t B, float* S_dev,

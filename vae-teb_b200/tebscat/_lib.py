@@ -28,6 +28,11 @@ class PhaseDesc(ctypes.Structure):
                 ('reserved', ctypes.c_int32 * 10)]
 
 
+class Epilogue(ctypes.Structure):
+    _fields_ = [('mean_dev', ctypes.c_void_p), ('std_dev', ctypes.c_void_p), ('mode_dev', ctypes.c_void_p),
+                ('log_eps', ctypes.c_float), ('trim', ctypes.c_int32), ('time_major', ctypes.c_int32)]
+
+
 _lib = None
 
 
@@ -57,6 +62,8 @@ def load():
     lib.tebscat_plan_destroy.argtypes = [vp]
     lib.tebscat_scat1d_forward.restype = ctypes.c_int
     lib.tebscat_scat1d_forward.argtypes = [vp, vp, ctypes.c_int64, vp, vp]
+    lib.tebscat_scat1d_forward_ex.restype = ctypes.c_int
+    lib.tebscat_scat1d_forward_ex.argtypes = [vp, vp, ctypes.c_int64, vp, ctypes.POINTER(Epilogue), vp]
     lib.tebscat_scat1d_forward_host.restype = ctypes.c_int
     lib.tebscat_scat1d_forward_host.argtypes = [vp, vp, ctypes.c_int64, vp]
     lib.tebscat_phase_plan_create.restype = ctypes.c_int

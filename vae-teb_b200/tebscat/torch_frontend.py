@@ -244,6 +244,64 @@ class Scattering1D(nn.Module):
             out.append({'coef': S[:, c, :].reshape(batch_shape + (n_out,)), 'j': j})
         return [out, out]
 
+    def forward_normalized(self, x, mean, variance, log_channels='all_except_0', asinh_channels=None,
+                           log_epsilon=1e-6, trim=0, time_major=True):
+        """The transform with the dataset's post-processing fused into its stores: returns
+        exactly what ``CombinedHDF5Dataset.__getitem__`` hands the model for a stored ``fhr_st`` record --
+        trimmed by `trim` decimated samples at both ends (hdf5_dataset/hdf5_dataset.py:733-741), normalised
+        like ``normalize_tensor_data`` (:18-137: ``log(clamp(x, 0) + eps)`` / ``asinh`` on the configured
+        channels, then ``(x - mean) / (sqrt(variance) + 1e-8)``) and laid out ``(time, channels)``
+        (:758-759).  `mean` / `variance` are the per-channel statistics of DatasetStatsCalculator;
+        `log_channels` / `asinh_channels` take the values of the reference's config ('all_except_0', 'all',
+        or a list of channel indices)."""
+        self._check_options()
+        if self.out_type != 'array' or not self.vectorize:
+            raise NotImplementedError('forward_normalized produces the array output only')
+        if x.shape[-1] != self.N:
+            raise ValueError('Input length {} does not match shape={}'.format(x.shape[-1], self.N))
+        if x.dtype is not torch.float32:
+            raise TypeError('Input and filter must be of the same dtype.')
+        if x.device.type != 'cuda':
+            raise TypeError('Input must be on GPU.')
+        batch_shape = x.shape[:-1]
+        x2 = x.reshape(-1, self.N)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        B = x2.shape[0]
+        plan = self._plan_for(x.device.index if x.device.index is not None else torch.cuda.current_device())
+        sched = self._sched[1]
+        C, n_out = sched.n_paths, sched.n_out
+        trim = int(trim)
+        if trim < 0 or 2 * trim >= n_out:
+            raise ValueError('trim={} leaves nothing of {} samples'.format(trim, n_out))
+        mean_t = torch.as_tensor(np.asarray(mean, np.float32)).reshape(-1)
+        std_t = torch.as_tensor(np.asarray(np.sqrt(np.asarray(variance)), np.float32)).reshape(-1)   # :62-66
+        if mean_t.numel() != C or std_t.numel() != C:
+            raise ValueError('statistics must have one entry per channel ({})'.format(C))
+        mode = np.zeros(C, np.uint8)
+        if log_channels == 'all_except_0':                                        # :86-91
+            mode[1:] = 1
+        elif isinstance(log_channels, (list, tuple)):
+            mode[list(log_channels)] = 1
+        if asinh_channels == 'all':                                               # :94-99 (applied after the log)
+            if mode.any():
+                raise NotImplementedError('a channel with both log and asinh normalisation is not supported')
+            mode[:] = 2
+        elif isinstance(asinh_channels, (list, tuple)) and len(asinh_channels):
+            if mode[list(asinh_channels)].any():
+                raise NotImplementedError('a channel with both log and asinh normalisation is not supported')
+            mode[list(asinh_channels)] = 2
+        dev = x.device
+        mean_d, std_d, mode_d = mean_t.to(dev), std_t.to(dev), torch.from_numpy(mode).to(dev)
+        keep = n_out - 2 * trim
+        out = torch.empty((B, keep, C) if time_major else (B, C, keep), dtype=torch.float32, device=dev)
+        ep = _lib.Epilogue(mean_d.data_ptr(), std_d.data_ptr(), mode_d.data_ptr(), float(log_epsilon), trim,
+                           1 if time_major else 0)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = _lib.load().tebscat_scat1d_forward_ex(plan.handle, x2.data_ptr(), B, out.data_ptr(), ctypes.byref(ep), stream)
+        _lib.check(rc)
+        return out.reshape(batch_shape + tuple(out.shape[1:]))
+
     def scattering_host(self, x, out=None, device=0):
         """End-to-end path on HOST tensors: pinned staging, chunked H2D / kernel / D2H
         overlap inside the library (tebscat_scat1d_forward_host).  Returns S on the host."""
