@@ -148,6 +148,12 @@ int tebscat_phase_forward(tebscat_phase_plan* plan, const float* x_dev, int64_t 
                           int ch_i, int ch_j, const int32_t* pair_subset_host, int n_subset,
                           int apply_low_pass, float* out_dev, void* stream);
 
+/* Optional: run stage B (the low-pass of every (sample, pair) product, _apply_phi_filter :233-273) as
+ * transforms on the step interpreter instead of the dense operator.  `pair_plan` is a plan created with
+ * tebscat_plan_create whose schedule starts with LOADPAIR tasks (tebscat/phase.py builds it); the phase
+ * plan takes ownership.  Requires a power-of-two decimation factor. */
+int tebscat_phase_plan_attach_pair_plan(tebscat_phase_plan* plan, tebscat_plan* pair_plan);
+
 /* Single-pass dataset entry: within-channel correlations of channel ch_i for the
  * pairs `within_subset` and cross-channel correlations ch_i x ch_j for `cross_subset`, sharing the
  * analytic signals of ch_i.  Replaces the two st_model(...) calls and the 903 -> 44 / 130 masking

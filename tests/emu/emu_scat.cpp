@@ -33,6 +33,15 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
         c.out = out + b * (long long)n_paths * (ep_mean ? n_out - 2 * ep_trim : n_out);
         c.ep_mean = ep_mean; c.ep_std = ep_std; c.ep_mode = ep_mode; c.ep_log_eps = ep_log_eps;
         c.ep_trim = ep_trim; c.ep_time_major = ep_time_major; c.n_paths = n_paths;
+        c.ch_limit = n_paths;
+        // phase stage B (OP_LOADPAIR): job b covers rows b*n_paths + q; zc/zp are then [rows][N] INPUTS
+        if (z_mode == 4) {
+            for (int q = 0; q < 2 && q < n_paths; ++q) {
+                c.pr_zp[q] = reinterpret_cast<const float2*>(zp) + (b * n_paths + q) * (long long)N;
+                c.pr_zc[q] = reinterpret_cast<const float2*>(zc) + (b * n_paths + q) * (long long)N;
+                c.pr_pw[q] = x[b * n_paths + q];           // the rows' powers travel in `x`
+            }
+        }
         c.chan = chan;
         c.zc = reinterpret_cast<float2*>(zc) + b * (long long)n_paths * n_out;
         c.zp = reinterpret_cast<float2*>(zp) + b * (long long)n_paths * n_out;

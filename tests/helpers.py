@@ -73,3 +73,31 @@ def emu_forward(plan, x, stage_a=False, epilogue=None):
     if stage_a:
         return zc[..., 0] + 1j * zc[..., 1], zp
     return out
+
+
+def emu_pair_stage(pair_plan, zp_rows, zc_rows, powers):
+    """Phase stage B in its transform form through the host emulator: rows of (|z_i|, theta_i) and
+    (re, im) of z_j, one power per row -> (rows, n_out) low-passed real parts."""
+    lib = ctypes.CDLL(EMU_PATH)
+    rows, N = zp_rows.shape[0], zp_rows.shape[1]
+    rpj = pair_plan.n_paths
+    jobs = -(-rows // rpj)
+    pad = jobs * rpj - rows
+
+    def padded(a):
+        a = np.ascontiguousarray(a, np.float32)
+        return np.ascontiguousarray(np.concatenate([a, np.repeat(a[-1:], pad, axis=0)]) if pad else a)
+    zp, zc, pw = padded(zp_rows), padded(zc_rows), padded(np.asarray(powers, np.float32))
+    out = np.full((jobs, rpj, pair_plan.n_out), np.nan, np.float32)
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    tasks = np.ascontiguousarray(pair_plan.tasks, np.int32)
+    steps = np.ascontiguousarray(pair_plan.steps, np.int32)
+    arena = np.ascontiguousarray(pair_plan.arena, np.float32)
+    chan = np.ascontiguousarray(pair_plan.chan, np.int32)
+    rc = lib.emu_scat1d_forward(pair_plan.N, pair_plan.geo.J_pad, pair_plan.geo.pad_left, rpj, pair_plan.n_out,
+                                pair_plan.smem_complex, tasks.shape[0], steps.shape[0],
+                                arena.ctypes.data_as(fp), tasks.ctypes.data_as(ip), steps.ctypes.data_as(ip),
+                                chan.ctypes.data_as(ip), pw.ctypes.data_as(fp), ctypes.c_longlong(jobs), out.ctypes.data_as(fp),
+                                zc.ctypes.data_as(fp), zp.ctypes.data_as(fp), 4, None, None, None, ctypes.c_float(0.0), 0, 0)
+    assert rc == 0
+    return out.reshape(jobs * rpj, pair_plan.n_out)[:rows]

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, emu_available, emu_forward
+from helpers import GOLDEN, emu_available, emu_forward, emu_pair_stage
 from oracle.phase_oracle import PhaseOracle
 from tebscat.phase import PhasePlan
 
@@ -63,3 +63,29 @@ def test_stage_a_emulated_matches_oracle(name):
     assert err.max() < 1e-5, err.max()
     assert np.allclose(zp[..., 0], np.abs(z), rtol=1e-6, atol=1e-9)
     assert np.allclose(zp[..., 1], np.angle(z), atol=1e-6)
+
+
+@pytest.mark.skipif(not emu_available(), reason='host emulator not built')
+@pytest.mark.parametrize('name', ['H', 'P'])
+def test_pair_stage_transform_form_matches_oracle(name):
+    """Stage B as transforms on the interpreter (power-of-two decimation): LOADPAIR -> FFT -> phi on the kept
+    bins -> reduced iFFT -> unpad must equal the oracle's _smooth of the same products."""
+    d = np.load(os.path.join(GOLDEN, 'phase_%s.npz' % name))
+    J, Q, T, N = CFG[name]
+    p = plan_of(name, d['scattering'].shape[-1])
+    assert p.pair_plan is not None and p.pair_plan.n_out == p.n_out
+    o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1])
+    rng = np.random.RandomState(9)
+    rows = 5                                                  # odd: the last job repeats its row
+    zi = (rng.randn(rows, N) + 1j * rng.randn(rows, N)).astype(np.complex64)
+    zj = (rng.randn(rows, N) + 1j * rng.randn(rows, N)).astype(np.complex64)
+    pw = np.array([1.0, 1.5, 2.0, 3.25, 7.0], np.float32)
+    zp = np.stack([np.abs(zi), np.angle(zi)], -1).astype(np.float32)
+    zc = np.stack([zj.real, zj.imag], -1).astype(np.float32)
+    out = emu_pair_stage(p.pair_plan, zp, zc, pw)
+    assert out.shape == (rows, p.n_out) and not np.isnan(out).any()
+    theta = zp[..., 1].astype(np.float32) * pw[:, None]       # fp32 product like the reference (:215)
+    c = zp[..., 0].astype(np.float64) * np.exp(1j * theta.astype(np.float64)) * np.conj(zj.astype(np.complex128))
+    ref = o._smooth(c).real
+    err = np.linalg.norm(out - ref, axis=-1) / np.linalg.norm(ref, axis=-1)
+    assert err.max() < 1e-5, err

@@ -59,6 +59,8 @@ enum : int32_t {
     OP_STOREB = 4,   // a=pool base b=slots c=first index d=count e=channel-table offset f=log2 slot length
     OP_STOREZ = 5,   // a=src b=row (filter index) c=first index d=count: complex crop -> global (phase stage A)
     OP_TINY = 6,     // a=region b=transforms c=log2L (1..3) e=flags: whole transforms of 2, 4 or 8 samples
+    OP_LOADPAIR = 8, // phase stage B on the interpreter: a=dst b=row of the job; c(t) = |z_i| e^{i p theta_i} conj(z_j)
+                     // of the row's pair, reflect-padded (kymatio_phase_scattering.py:211-218, :283/:339, :162-209)
     OP_MULFOLD2 = 7  // like MULFOLD with k >= 1 on a PACKED source (spectrum of u_a + i u_b): a=src b=log2Lsrc c=log2k
                      // d=dst of the a-child e=filter offset f=chunk mask g=dst of the b-child h=log2 chunk width
 };
@@ -91,6 +93,11 @@ struct SignalCtx {
     const unsigned char* ep_mode;   // [C]: EP_NONE / EP_LOG / EP_ASINH
     float ep_log_eps;
     int32_t ep_trim, ep_time_major, n_paths;
+    // phase stage B (OP_LOADPAIR): the rows (sample, pair) of this job; ch_limit = rows that exist
+    const float2* pr_zp[2];  // (|z_i|, theta_i)[N] of the row's 'i' filter
+    const float2* pr_zc[2];  // (re, im)[N] of the row's 'j' filter
+    float pr_pw[2];
+    int32_t ch_limit;        // channels >= ch_limit are not stored (n_paths for the scattering transform)
 };
 enum : int32_t { EP_NONE = 0, EP_LOG = 1, EP_ASINH = 2 };
 
@@ -801,6 +808,50 @@ TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
     }
 }
 
+// Phase stage B: the phase-accelerated product of one (sample, pair) row, computed where it is consumed.
+//   theta * p in fp32 like the reference (:215), an exact-enough two-constant reduction to [-pi, pi],
+//   c = |z_i| (cos + i sin)(p theta_i) * conj(z_j)                         (:216-218, :283 / :339)
+// and the reflect padding of _pad_signal (:162-209; pad < N): every sample is written to its own slot and
+// to the slots of its mirror images, so the transcendental work is done once per sample.
+TEB_D float2 accelerated_product(float2 pz, float2 zj, float power) {
+    const float ph = pz.y * power;
+    const float k = rintf(ph * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, ph);
+    r = fmaf(-k, -1.7484555314695172e-7f, r);
+    float sn, cs;
+#ifdef TEBSCAT_HOST_EMU
+    sn = sinf(r); cs = cosf(r);
+#else
+    __sincosf(r, &sn, &cs);
+#endif
+    const float ar = pz.x * cs, ai = pz.x * sn;
+    return make_float2(fmaf(ar, zj.x, ai * zj.y), fmaf(ai, zj.x, -ar * zj.y));     // (ar + i ai) * conj(zj)
+}
+
+TEB_D void loadpair_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
+    const int Np = 1 << c.log2_Np;
+    const int pad_right = Np - c.N - c.pad_left;
+    const float2* zp = c.pr_zp[t.b];
+    const float2* zc = c.pr_zc[t.b];
+    const float pw = c.pr_pw[t.b];
+    for (int t0 = lt; t0 < c.N; t0 += 4 * t.nt) {
+        float2 a[4], b[4];
+        TEB_UNROLL for (int j = 0; j < 4; ++j) {
+            const int tt = t0 + j * t.nt;
+            a[j] = tt < c.N ? TEB_LDG(zp + tt) : make_float2(0.f, 0.f);
+            b[j] = tt < c.N ? TEB_LDG(zc + tt) : make_float2(0.f, 0.f);
+        }
+        TEB_UNROLL for (int j = 0; j < 4; ++j) {
+            const int tt = t0 + j * t.nt;
+            if (tt >= c.N) continue;
+            const float2 v = accelerated_product(a[j], b[j], pw);
+            S[swz(t.a + c.pad_left + tt)] = v;
+            if (tt >= 1 && tt <= c.pad_left) S[swz(t.a + c.pad_left - tt)] = v;                       // left mirror
+            if (tt <= c.N - 2 && tt >= c.N - 1 - pad_right) S[swz(t.a + c.pad_left + 2 * (c.N - 1) - tt)] = v;   // right mirror
+        }
+    }
+}
+
 // unpad (torch_backend.py:80-102) + concatenate (kymatio/backend/torch_backend.py:143-145)
 // for a pool of `b` finished low-pass outputs: slot s goes to channels chan[2 (e + s)] (real part)
 // and chan[2 (e + s) + 1] (imaginary part of a packed pair; -1 = none).
@@ -812,6 +863,7 @@ TEB_D float epilogue_value(const SignalCtx& c, int ch, float v) {
     return (v - c.ep_mean[ch]) / (c.ep_std[ch] + 1e-8f);                     // :133-135
 }
 TEB_D void store_coefficient(const SignalCtx& c, int ch, int n, float v) {
+    if (ch >= c.ch_limit) return;
     if (!c.ep_mean) {
         c.out[(int64_t)ch * c.n_out + n] = v;
         return;
@@ -869,6 +921,7 @@ TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const floa
         }
         case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
         case OP_MULFOLD2: mulfold2_task(S, arena, t, lt); break;
+        case OP_LOADPAIR: loadpair_task(S, c, t, lt); break;
         case OP_STOREB: storeb_task(S, c, t, lt); break;
         case OP_STOREZ: storez_task(S, c, t, lt); break;
         case OP_TINY: tiny_task(S, t, lt); break;

@@ -61,6 +61,15 @@ struct KParams {
     const unsigned char* ep_mode;
     float ep_log_eps;
     int32_t ep_trim, ep_time_major;
+    // phase stage B on the interpreter (pair_rows > 0): a job is n_paths consecutive (sample, pair) rows
+    const float2* pair_zp;   // [Bc][F][N] (|z|, theta) of the 'i' channel
+    const float2* pair_zc;   // [Bc][F][N] (re, im) of the 'j' channel
+    const int32_t* pair_i;
+    const int32_t* pair_j;
+    const float* pair_pw;
+    const int32_t* pair_subset;
+    long long pair_rows;
+    int32_t pair_n_sel, pair_F;
 };
 
 constexpr int kThreads = 512;
@@ -117,6 +126,20 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
             c.ep_trim = p.ep_trim;
             c.ep_time_major = p.ep_time_major;
             c.n_paths = p.n_paths;
+            c.ch_limit = p.n_paths;
+            if (p.pair_rows > 0) {
+                const long long r0 = b * p.n_paths;
+                c.ch_limit = (int)(p.pair_rows - r0 < p.n_paths ? p.pair_rows - r0 : p.n_paths);
+                for (int q = 0; q < 2 && q < p.n_paths; ++q) {
+                    const long long r = r0 + q < p.pair_rows ? r0 + q : p.pair_rows - 1;    // a missing row repeats the last
+                    const long long smp = r / p.pair_n_sel;
+                    const int sel = (int)(r - smp * p.pair_n_sel);
+                    const int pair = p.pair_subset ? p.pair_subset[sel] : sel;
+                    c.pr_zp[q] = p.pair_zp + (smp * p.pair_F + p.pair_i[pair]) * (long long)p.N;
+                    c.pr_zc[q] = p.pair_zc + (smp * p.pair_F + p.pair_j[pair]) * (long long)p.N;
+                    c.pr_pw[q] = p.pair_pw[pair];
+                }
+            }
             c.chan = p.chan;
             c.zc = p.zc + b * p.z_stride;
             c.zp = p.zp + b * p.z_stride;
@@ -300,6 +323,10 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                 if (t[4] < 0 || t[4] >= d.n_paths || t[6] != d.n_out || t[5] < 0 || !fits(t[3], (int64_t)t[5] + t[6]))
                     return fail(TEBSCAT_EINVAL, "task %d: bad STOREZ", i);
                 break;
+            case OP_LOADPAIR:
+                if (t[4] < 0 || t[4] > 1 || t[4] >= d.n_paths || !fits(t[3], (int64_t)1 << d.log2_Np))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad LOADPAIR", i);
+                break;
             case OP_NOP:
                 break;
             default:
@@ -422,6 +449,15 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     k.ep_log_eps = 0.f;
     k.ep_trim = 0;
     k.ep_time_major = 0;
+    k.pair_zp = nullptr;
+    k.pair_zc = nullptr;
+    k.pair_i = nullptr;
+    k.pair_j = nullptr;
+    k.pair_pw = nullptr;
+    k.pair_subset = nullptr;
+    k.pair_rows = 0;
+    k.pair_n_sel = 0;
+    k.pair_F = 0;
     *out = p;
     return TEBSCAT_OK;
 }
@@ -596,18 +632,7 @@ struct PairParams {
     int32_t n_sel, F, N, n_out, n_cols_pad;
 };
 
-__device__ __forceinline__ float2 accelerated_product(float2 pz, float2 zj, float power) {
-    // theta * p in fp32 like the reference (:215), then an exact-enough reduction to [-pi, pi]
-    const float ph = pz.y * power;
-    const float k = rintf(ph * 0.15915494309189535f);
-    float r = fmaf(-k, 6.2831854820251465f, ph);
-    r = fmaf(-k, -1.7484555314695172e-7f, r);
-    float sn, cs;
-    __sincosf(r, &sn, &cs);
-    const float ar = pz.x * cs, ai = pz.x * sn;
-    // (ar + i ai) * conj(zj)
-    return make_float2(fmaf(ar, zj.x, ai * zj.y), fmaf(ai, zj.x, -ar * zj.y));
-}
+// (accelerated_product: scat_core.cuh -- shared with the interpreter's OP_LOADPAIR)
 
 // ---- tensor-core contraction ------------------------------------------------------------
 // out = A' B' with A' = [Re c, -Im c] (rows x 2N) and B' = [Re G; Im G] (2N x n_out) is a real
@@ -785,6 +810,7 @@ struct tebscat_phase_plan {
     float2* d_zc2 = nullptr;       // second cartesian workspace of the dataset entry point
     int64_t ws_samples = 0;
     int64_t ws2_samples = 0;
+    tebscat_plan* pair_plan = nullptr;   // optional: stage B as FFTs on the interpreter (owned)
     std::mutex mu;
 };
 
@@ -834,7 +860,45 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
     cudaFree(p->d_zp);
     cudaFree(p->d_zc2);
     tebscat_plan_destroy(p->stage_a);
+    tebscat_plan_destroy(p->pair_plan);
     delete p;
+}
+
+// Stage B as transforms on the step interpreter: `pair_plan` is a schedule whose jobs are n_paths (1 or 2)
+// consecutive (sample, pair) rows -- LOADPAIR, forward transform, phi on the kept bins, reduced inverse
+// transform, unpad (the literal cascade of _apply_phi_filter :233-273).  5 N log N instead of the dense
+// operator's 4 N n_out flops per row: it wins when the output is long (production config: n_out = 360).
+// Only for power-of-two decimation; the dense tensor-core kernel stays the general path.
+extern "C" int tebscat_phase_plan_attach_pair_plan(tebscat_phase_plan* p, tebscat_plan* pair_plan) {
+    if (!p || !pair_plan) return fail(TEBSCAT_EINVAL, "null argument");
+    if (pair_plan->device != p->device || pair_plan->desc.N != p->desc.N || pair_plan->desc.n_out != p->desc.n_out ||
+        pair_plan->desc.n_paths < 1 || pair_plan->desc.n_paths > 2)
+        return fail(TEBSCAT_EINVAL, "pair plan does not match the phase description");
+    std::lock_guard<std::mutex> lock(p->mu);
+    tebscat_plan_destroy(p->pair_plan);
+    p->pair_plan = pair_plan;
+    return TEBSCAT_OK;
+}
+
+static int launch_pairs_fft(const tebscat_phase_plan* p, const float2* zp, const float2* zc, const int32_t* subset_dev,
+                            int n_sel, int64_t nb, float* out, cudaStream_t st) {
+    const tebscat_plan* a = p->pair_plan;
+    KParams kp = a->kp;
+    kp.pair_zp = zp;
+    kp.pair_zc = zc;
+    kp.pair_i = p->d_i;
+    kp.pair_j = p->d_j;
+    kp.pair_pw = p->d_pw;
+    kp.pair_subset = subset_dev;
+    kp.pair_rows = (long long)nb * n_sel;
+    kp.pair_n_sel = n_sel;
+    kp.pair_F = p->desc.n_filters;
+    const long long jobs = (kp.pair_rows + a->desc.n_paths - 1) / a->desc.n_paths;
+    const int grid = (int)(jobs < (long long)a->n_sms ? jobs : (long long)a->n_sms);
+    scat1d_kernel<false><<<grid, a->desc.n_threads, a->smem_bytes, st>>>(kp, nullptr, out, jobs);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
 }
 
 static int launch_stage_a(const tebscat_plan* a, const float* x, long long x_stride, int64_t jobs,
@@ -908,7 +972,10 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
         pp.N = d.N;
         pp.n_out = d.n_out;
         pp.n_cols_pad = d.n_cols_pad;
-        if (apply_low_pass) {
+        if (apply_low_pass && p->pair_plan) {
+            if (int rc = launch_pairs_fft(p, p->d_zp, p->d_zc, pp.subset, n_sel, nb, pp.out, st)) return rc;
+            continue;
+        } else if (apply_low_pass) {
             dim3 grid((unsigned)((pp.rows + kPR - 1) / kPR), (unsigned)(d.n_cols_pad / kPC));
             phase_pair_kernel<<<grid, kPThreads, kPairSmem, st>>>(pp);
         } else {
@@ -922,6 +989,7 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
 
 static int launch_pairs(const tebscat_phase_plan* p, const float2* zp, const float2* zc, const int32_t* subset_dev,
                         int n_sel, int64_t nb, float* out, cudaStream_t st) {
+    if (p->pair_plan) return launch_pairs_fft(p, zp, zc, subset_dev, n_sel, nb, out, st);
     const tebscat_phase_desc& d = p->desc;
     PairParams pp;
     pp.zp = zp;

@@ -68,6 +68,8 @@ def load():
     lib.tebscat_scat1d_forward_host.argtypes = [vp, vp, ctypes.c_int64, vp]
     lib.tebscat_phase_plan_create.restype = ctypes.c_int
     lib.tebscat_phase_plan_create.argtypes = [ctypes.POINTER(PhaseDesc), vp, fp, i32p, i32p, fp, ctypes.POINTER(vp)]
+    lib.tebscat_phase_plan_attach_pair_plan.restype = ctypes.c_int
+    lib.tebscat_phase_plan_attach_pair_plan.argtypes = [vp, vp]
     lib.tebscat_phase_plan_destroy.restype = None
     lib.tebscat_phase_plan_destroy.argtypes = [vp]
     lib.tebscat_phase_forward.restype = ctypes.c_int

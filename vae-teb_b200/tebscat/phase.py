@@ -12,6 +12,7 @@ truncation operator) as one fused kernel.  Host code here only builds the plan.
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -49,6 +50,9 @@ def smoothing_operator(phi0_f32, N, J_pad, pad_left, dec):
         E2 = np.exp(-2j * np.pi * np.outer(tp[lo:hi], k) / Np)               # (chunk, M)
         np.add.at(G, src[lo:hi], E2 @ E1)
     return G
+
+
+PAIR_FFT_MIN_OUT = 160      # outputs per row from which the transform form of stage B beats the dense operator
 
 
 class PhasePlan:
@@ -89,6 +93,50 @@ class PhasePlan:
         Gp[:, :self.n_out, 1] = G.imag
         self.G = Gp
         self._build_stage_a()
+        self.pair_plan = None
+        if self.dec & (self.dec - 1) == 0 and (1 << self.geo.J_pad) // self.dec >= 16:
+            self._build_pair_plan(phi0)
+
+    def _build_pair_plan(self, phi0, rows_per_job=2):
+        """Stage B as transforms (power-of-two decimation): per (sample, pair) row the literal cascade of
+        _apply_phi_filter (:233-273) on the step interpreter --
+            LOADPAIR (product + reflect pad) -> FFT(Np) -> phi on bins [0, Np/dec) -> iFFT(Np/dec) -> unpad.
+        Keeping bins [0, M) and multiplying by phi IS a 'filter multiply + periodise by dec' with the filter
+        phi * 1[k < M] (the periodisation sums bins m + i M, of which only i = 0 survives), times dec to undo
+        the periodisation's mean: the transform's leaf machinery does the rest.  Two rows share a job so
+        that every step has work for all 512 threads."""
+        n = self.geo.J_pad
+        Np, dec = 1 << n, self.dec
+        M = Np // dec
+        lf = int(math.log2(M))
+        start = self.geo.pad_left // dec
+        arena = sch._Arena()
+        f = np.zeros(Np, np.float64)
+        f[:M] = phi0.astype(np.float64)[:M] * dec                       # :239-250 (float32 phi, exact power-of-two scale)
+        off = arena.add(f)
+        chains = []
+        for q in range(rows_per_job):
+            xq = sch.Buf(Np, 'C[%d]' % q)
+            st = [[sch.TaskSpec(sch.OP_LOADPAIR, -(-self.N // 4), 1500.0, 120.0, a=(xq, 0), b=q, trip=900.0)]]
+            st += sch._merge_local_passes(sch._fft_stages((xq, 0), n, 1, 'fwd'))
+            c = sch.Chain(xq.name, st, owns=[xq], depth=1)
+            chains.append(c)
+            leaf = sch._mulfold(arena, (xq, 0), n, n - lf, sch.LEAF, off, (q, -1))
+            chains.append(sch.Chain('Y[%d]' % q, [[leaf]], after=[c], reads=[xq], depth=2))
+        steps, high, chan, stats = sch.schedule_chains(chains, sch.smem_capacity(), lf, start, self.n_out,
+                                                       pool_slots=max(rows_per_job << lf, 256))
+        tasks, ranges = sch.emit(steps)
+        logical = sch._round16(high)
+
+        class _P:
+            pass
+        a = _P()
+        a.N, a.geo, a.n_paths, a.n_out = self.N, self.geo, rows_per_job, self.n_out
+        a.n_threads, a.smem_complex = sch.N_THREADS, logical + logical // 16
+        a.tasks, a.steps, a.arena = tasks, ranges, arena.finish()
+        a.chan = np.asarray(chan, np.int32)
+        a.stats = stats
+        self.pair_plan = a
 
     def _build_stage_a(self):
         """Schedule of stage A: root transform, then per filter psi multiply -> iFFT -> STOREZ."""
@@ -141,6 +189,14 @@ class _DevicePhasePlan:
         stage_a.handle = None                       # ownership moved into the phase plan
         self.handle = handle
         self._lib = lib
+        # stage B as transforms where that is the cheaper form (long outputs); TEBSCAT_PHASE_FFT=0/1 overrides
+        mode = os.environ.get('TEBSCAT_PHASE_FFT', 'auto')
+        use_fft = plan.pair_plan is not None and (mode == '1' or (mode == 'auto' and plan.n_out >= PAIR_FFT_MIN_OUT))
+        self.uses_fft_pairs = bool(use_fft)
+        if use_fft:
+            pp = _DevicePlan(plan.pair_plan, device_index)
+            _lib.check(lib.tebscat_phase_plan_attach_pair_plan(handle, pp.handle))
+            pp.handle = None
 
     def __del__(self):
         try:

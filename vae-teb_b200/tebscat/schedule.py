@@ -36,14 +36,14 @@ import numpy as np
 
 from . import filterbank as fbk
 
-OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY, OP_MULFOLD2 = 0, 1, 2, 3, 4, 5, 6, 7
+OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY, OP_MULFOLD2, OP_LOADPAIR = 0, 1, 2, 3, 4, 5, 6, 7, 8
 FFT_INV, FFT_MOD, FFT_FUSE_FWD, FFT_PACK = 1, 2, 4, 8
 TASK_INTS = 12
 
 N_THREADS = 512
 LOG2_NP_MAX = 13                  # single-CTA limit of the kernel (kLog2TwMax)
 SMEM_BYTES_MAX = 227 * 1024
-TW_SLOTS = 68 + 136 + 4 + 16 + 288   # padded twiddle tables + the kernel's static shared memory (context, record ring)
+TW_SLOTS = 68 + 136 + 4 + 24 + 288   # padded twiddle tables + the kernel's static shared memory (context, record ring)
 MASK_THRESHOLD = 1e-9             # relative filter magnitude below which a 4-bin chunk is skipped
 BATCH_SLOTS = 8192                # target size of one batch buffer (complex slots)
 POOL_SLOTS = 1024                 # size of one half of the leaf pool
@@ -950,6 +950,10 @@ def task_accesses(t, log2_Np):
                 add(d + 4 * it[:, None] + np.arange(4)[None, :], it % nt, True)
             else:
                 add(d + 2 * it[:, None] + np.arange(2)[None, :], it % nt, True)
+    elif op == OP_LOADPAIR:
+        s_ = a + np.arange(1 << log2_Np)
+        for w in range(nt // 32):
+            add(s_, np.full(s_.shape, 32 * w), True)
     elif op == OP_MULFOLD2:
         log_src, logk = b, c
         src = a + np.arange(1 << log_src)
