@@ -36,7 +36,7 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
         c.ch_limit = n_paths;
         // phase stage B (OP_LOADPAIR): job b covers rows b*n_paths + q; zc/zp are then [rows][N] INPUTS
         if (z_mode == 4) {
-            for (int q = 0; q < 2 && q < n_paths; ++q) {
+            for (int q = 0; q < kMaxPairRows && q < n_paths; ++q) {
                 c.pr_zp[q] = reinterpret_cast<const float2*>(zp) + (b * n_paths + q) * (long long)N;
                 c.pr_zc[q] = reinterpret_cast<const float2*>(zc) + (b * n_paths + q) * (long long)N;
                 c.pr_pw[q] = x[b * n_paths + q];           // the rows' powers travel in `x`

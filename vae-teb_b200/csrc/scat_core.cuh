@@ -77,6 +77,8 @@ struct Task {
     int32_t a, b, c, d, e, f, g, h, pad;
 };
 
+constexpr int kMaxPairRows = 8;    // (sample, pair) rows of one phase stage-B job
+
 struct SignalCtx {
     const float* x;          // this signal's N input samples
     float* out;              // this signal's [n_paths, n_out] block
@@ -94,9 +96,9 @@ struct SignalCtx {
     float ep_log_eps;
     int32_t ep_trim, ep_time_major, n_paths;
     // phase stage B (OP_LOADPAIR): the rows (sample, pair) of this job; ch_limit = rows that exist
-    const float2* pr_zp[2];  // (|z_i|, theta_i)[N] of the row's 'i' filter
-    const float2* pr_zc[2];  // (re, im)[N] of the row's 'j' filter
-    float pr_pw[2];
+    const float2* pr_zp[kMaxPairRows];  // (|z_i|, theta_i)[N] of the row's 'i' filter
+    const float2* pr_zc[kMaxPairRows];  // (re, im)[N] of the row's 'j' filter
+    float pr_pw[kMaxPairRows];
     int32_t ch_limit;        // channels >= ch_limit are not stored (n_paths for the scattering transform)
 };
 enum : int32_t { EP_NONE = 0, EP_LOG = 1, EP_ASINH = 2 };

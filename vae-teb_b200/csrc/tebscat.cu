@@ -130,7 +130,7 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
             if (p.pair_rows > 0) {
                 const long long r0 = b * p.n_paths;
                 c.ch_limit = (int)(p.pair_rows - r0 < p.n_paths ? p.pair_rows - r0 : p.n_paths);
-                for (int q = 0; q < 2 && q < p.n_paths; ++q) {
+                for (int q = 0; q < kMaxPairRows && q < p.n_paths; ++q) {
                     const long long r = r0 + q < p.pair_rows ? r0 + q : p.pair_rows - 1;    // a missing row repeats the last
                     const long long smp = r / p.pair_n_sel;
                     const int sel = (int)(r - smp * p.pair_n_sel);
@@ -324,7 +324,7 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                     return fail(TEBSCAT_EINVAL, "task %d: bad STOREZ", i);
                 break;
             case OP_LOADPAIR:
-                if (t[4] < 0 || t[4] > 1 || t[4] >= d.n_paths || !fits(t[3], (int64_t)1 << d.log2_Np))
+                if (t[4] < 0 || t[4] >= kMaxPairRows || t[4] >= d.n_paths || !fits(t[3], (int64_t)1 << d.log2_Np))
                     return fail(TEBSCAT_EINVAL, "task %d: bad LOADPAIR", i);
                 break;
             case OP_NOP:
@@ -864,7 +864,7 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
     delete p;
 }
 
-// Stage B as transforms on the step interpreter: `pair_plan` is a schedule whose jobs are n_paths (1 or 2)
+// Stage B as transforms on the step interpreter: `pair_plan` is a schedule whose jobs are n_paths (up to 8)
 // consecutive (sample, pair) rows -- LOADPAIR, forward transform, phi on the kept bins, reduced inverse
 // transform, unpad (the literal cascade of _apply_phi_filter :233-273).  5 N log N instead of the dense
 // operator's 4 N n_out flops per row: it wins when the output is long (production config: n_out = 360).
@@ -872,7 +872,7 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
 extern "C" int tebscat_phase_plan_attach_pair_plan(tebscat_phase_plan* p, tebscat_plan* pair_plan) {
     if (!p || !pair_plan) return fail(TEBSCAT_EINVAL, "null argument");
     if (pair_plan->device != p->device || pair_plan->desc.N != p->desc.N || pair_plan->desc.n_out != p->desc.n_out ||
-        pair_plan->desc.n_paths < 1 || pair_plan->desc.n_paths > 2)
+        pair_plan->desc.n_paths < 1 || pair_plan->desc.n_paths > kMaxPairRows)
         return fail(TEBSCAT_EINVAL, "pair plan does not match the phase description");
     std::lock_guard<std::mutex> lock(p->mu);
     tebscat_plan_destroy(p->pair_plan);

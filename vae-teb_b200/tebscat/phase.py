@@ -97,14 +97,18 @@ class PhasePlan:
         if self.dec & (self.dec - 1) == 0 and (1 << self.geo.J_pad) // self.dec >= 16:
             self._build_pair_plan(phi0)
 
-    def _build_pair_plan(self, phi0, rows_per_job=2):
+    def _build_pair_plan(self, phi0, rows_per_job=None):
         """Stage B as transforms (power-of-two decimation): per (sample, pair) row the literal cascade of
         _apply_phi_filter (:233-273) on the step interpreter --
             LOADPAIR (product + reflect pad) -> FFT(Np) -> phi on bins [0, Np/dec) -> iFFT(Np/dec) -> unpad.
         Keeping bins [0, M) and multiplying by phi IS a 'filter multiply + periodise by dec' with the filter
         phi * 1[k < M] (the periodisation sums bins m + i M, of which only i = 0 survives), times dec to undo
-        the periodisation's mean: the transform's leaf machinery does the rest.  Two rows share a job so
-        that every step has work for all 512 threads."""
+        the periodisation's mean: the transform's leaf machinery does the rest.  Several rows share a job:
+        as many as fit run side by side, and while the short tail of one wave (reduced iFFT, store) runs, the
+        next wave's LOADPAIR already uses the buffers the first has released -- the list scheduler overlaps
+        them."""
+        if rows_per_job is None:
+            rows_per_job = int(os.environ.get('TEBSCAT_PAIR_ROWS', '8'))
         n = self.geo.J_pad
         Np, dec = 1 << n, self.dec
         M = Np // dec

@@ -43,7 +43,7 @@ TASK_INTS = 12
 N_THREADS = 512
 LOG2_NP_MAX = 13                  # single-CTA limit of the kernel (kLog2TwMax)
 SMEM_BYTES_MAX = 227 * 1024
-TW_SLOTS = 68 + 136 + 4 + 24 + 288   # padded twiddle tables + the kernel's static shared memory (context, record ring)
+TW_SLOTS = 68 + 136 + 4 + 48 + 288   # padded twiddle tables + the kernel's static shared memory (context, record ring)
 MASK_THRESHOLD = 1e-9             # relative filter magnitude below which a 4-bin chunk is skipped
 BATCH_SLOTS = 8192                # target size of one batch buffer (complex slots)
 POOL_SLOTS = 1024                 # size of one half of the leaf pool
