@@ -7,6 +7,10 @@ followed by one barrier.  This module turns the cascade of
 
 Design (what makes the steps full):
 
+* PAIR PACKING: every forward transform acts on a real signal (a modulus), so two of them share one
+  complex transform (FFT_PACK); phi leaves of a packed spectrum need no separation, psi2 children are
+  separated on the fly by MULFOLD2 (mirrored bins).
+
 * Same-length transforms are BATCHED: first-order filters that share the
   subsampling 2^k1 are processed ``8192 / L1`` at a time in one contiguous buffer,
   their children (second order) are grouped by length the same way, and every FFT
@@ -166,8 +170,8 @@ def _fft_stages(ref, n: int, count: int, kind: str, hi: int = 0) -> List[List[Ta
     group -- stored right behind the first `count` blocks -- is the PARTNER of block i: the fused pass
     takes both moduli as real and imaginary part, so the forward half runs on `count` blocks only.
 
-    (Running the small-block passes warp-locally with __syncwarp() instead of CTA barriers was
-    measured 30 % SLOWER on B200: warps executing different passes thrash the instruction cache.)"""
+    Consecutive passes over blocks of <= 512 slots are chained into one task afterwards
+    (_merge_local_passes)."""
     if n < 1:
         raise NotImplementedError('length-1 transforms are not supported')
     if n < 4:
