@@ -220,6 +220,23 @@ def run_gpu(args):
                  'achieved_fp32_tflops': 512 * 2 * 741 * 4800 * 80 * 2 / (pms * 1e-3) / 1e12,
                  'note': 'includes the scattering transform of the FHR channel and stage A of both channels'}
         del pm
+        # production dataset step (create_hdf5_dataset.py:360-441): S + 44 within + 130 cross pairs in one pass
+        from tebscat.synth import ctg_batch as _ctg
+        pmp = KymatioPhaseScattering1D(J=11, Q=4, T=16, shape=5760, device=dev, max_order=1)
+        sel = pmp.get_optimal_coefficients_for_fhr(11, 4, 16)['recommendations']
+        xp = _ctg(512, 5760, seed=99).to(dev)
+        pmp.forward_dataset(xp, sel['use_phase_mask'], sel['use_cross_mask'])
+        torch.cuda.synchronize()
+        p0.record()
+        for _ in range(3):
+            pmp.forward_dataset(xp, sel['use_phase_mask'], sel['use_cross_mask'])
+        p1.record()
+        torch.cuda.synchronize()
+        dms = p0.elapsed_time(p1) / 3
+        phase['dataset_step'] = {'metric': 'production dataset step segments/s (J=11,Q=4,T=16,N=5760: S + 44 within + 130 cross pairs)',
+                                 'value': 512 / (dms * 1e-3), 'unit': 'segments/s', 'batch': 512, 'ms': dms,
+                                 'stage_b': 'transform form' if pmp._dev_plan(local).uses_fft_pairs else 'dense operator'}
+        del pmp
 
     if rank == 0:
         hbm_peak, peak_src = peaks()

@@ -190,3 +190,24 @@ def test_output_conventions_list_and_dict():
     assert list(dct.keys()) == meta['key']
     for c, k in enumerate(meta['key']):
         assert dct[k].shape == (3, 2, 1, arr.shape[-1]) and torch.equal(dct[k][..., 0, :], arr[..., c, :])
+
+
+@pytest.mark.gpu
+def test_relaxed_and_chained_schedule_is_bitwise_equal_to_fully_barriered(monkeypatch):
+    """Race check without a sanitizer: warp-fenced chained passes and relaxed barriers change WHEN a butterfly
+    runs, never its arithmetic, so the product schedule must reproduce -- bit for bit, run after run -- the
+    output of the same cascade scheduled with one CTA barrier after every single pass."""
+    import torch
+    from tebscat import Scattering1D
+    from tebscat.synth import ctg_batch
+    J, N, Q, T = 6, 4800, 8, 64
+    x = ctg_batch(148 * 2, N, seed=11).reshape(-1, N)[:148 * 3].cuda()
+    fast = Scattering1D(J, N, Q, T=T).cuda()
+    ref = fast(x)[0].clone()
+    for _ in range(4):                                      # run-to-run determinism
+        assert torch.equal(fast(x)[0], ref)
+    monkeypatch.setenv('TEBSCAT_RELAX', '0')
+    monkeypatch.setenv('TEBSCAT_CHAIN', '0')
+    safe = Scattering1D(J, N, Q, T=T).cuda()
+    assert safe._schedule().stats['n_relaxed'] == 0 and safe._schedule().stats['n_steps'] > fast._schedule().stats['n_steps']
+    assert torch.equal(safe(x)[0], ref)
