@@ -98,3 +98,31 @@ class ScatteringOracle:
         out.extend(order2)                                                     # :372-375
         S = np.stack(out, axis=1)                                              # :378 (dim 2 of (B,1,C,T))
         return S.reshape(batch_shape + S.shape[-2:]).astype(self.rdtype)       # torch_frontend.py:231-235
+
+    def unaveraged(self, x):
+        """average=False, out_type='list' (core :293-294, :329-330, :366-367): [(key, coef (..., len))] in the
+        reference's order -- the input itself, then the unpadded moduli U1 and U2 at their own rates."""
+        x = np.asarray(x)
+        batch_shape = x.shape[:-1]
+        x = x.reshape(-1, x.shape[-1]).astype(self.rdtype)
+        g = self.geo
+        log2_T = math.floor(math.log2(self.T))
+        os_ = self.oversampling
+        i0, i1 = g['ind_start'], g['ind_end']
+        out = [((), x)]                                                         # :294
+        order2 = []
+        U0_f = self._fft(reflect_pad(x, g['pad_left'], g['pad_right']))
+        for n1, p1 in enumerate(self.psi1):
+            j1 = p1['j']
+            k1 = max(min(j1 - os_, log2_T - os_), 0)
+            U1 = np.abs(self._ifft(subsample_fourier(U0_f * p1['levels'][0], 2 ** k1)))
+            out.append(((n1,), U1[:, i0[k1]:i1[k1]]))                          # :330
+            if self.max_order == 2:
+                U1_f = self._fft(U1)
+                for n2, p2 in enumerate(self.psi2):
+                    if p2['j'] > j1:
+                        k2 = max(min(p2['j'] - k1 - os_, log2_T - k1 - os_), 0)
+                        U2 = np.abs(self._ifft(subsample_fourier(U1_f * p2['levels'][k1], 2 ** k2)))
+                        order2.append(((n1, n2), U2[:, i0[k1 + k2]:i1[k1 + k2]]))   # :367
+        out.extend(order2)
+        return [(k, v.reshape(batch_shape + v.shape[-1:]).astype(self.rdtype)) for k, v in out]

@@ -61,6 +61,7 @@ enum : int32_t {
     OP_TINY = 6,     // a=region b=transforms c=log2L (1..3) e=flags: whole transforms of 2, 4 or 8 samples
     OP_LOADPAIR = 8, // phase stage B on the interpreter: a=dst b=row of the job; c(t) = |z_i| e^{i p theta_i} conj(z_j)
                      // of the row's pair, reflect-padded (kymatio_phase_scattering.py:211-218, :283/:339, :162-209)
+    OP_STOREU = 9,   // average=False: a=src c=first index d=count e=offset in the output row: the modulus itself
     OP_MULFOLD2 = 7  // like MULFOLD with k >= 1 on a PACKED source (spectrum of u_a + i u_b): a=src b=log2Lsrc c=log2k
                      // d=dst of the a-child e=filter offset f=chunk mask g=dst of the b-child h=log2 chunk width
 };
@@ -889,6 +890,11 @@ TEB_D void storeb_task(const float2* S, const SignalCtx& c, const Task& t, int l
     }
 }
 
+// average=False (core/scattering1d.py:329-330, :366-367): the unpadded modulus U1 / U2 at its own rate
+TEB_D void storeu_task(const float2* S, const SignalCtx& c, const Task& t, int lt) {
+    for (int n = lt; n < t.d; n += t.nt) c.out[(int64_t)t.e + n] = S[swz(t.a + t.c + n)].x;
+}
+
 // Phase stage A (hdf5_dataset/kymatio_phase_scattering.py:220-231): the unpadded analytic
 // signal z = ifft(fft(pad(x)) psi1_f)[pad_left : pad_left + N], stored for the pair stage as
 // (re, im) and/or as (|z|, atan2(im, re)) -- the polar form of _accelerate_phase (:214-215).
@@ -924,6 +930,7 @@ TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const floa
         case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
         case OP_MULFOLD2: mulfold2_task(S, arena, t, lt); break;
         case OP_LOADPAIR: loadpair_task(S, c, t, lt); break;
+        case OP_STOREU: storeu_task(S, c, t, lt); break;
         case OP_STOREB: storeb_task(S, c, t, lt); break;
         case OP_STOREZ: storez_task(S, c, t, lt); break;
         case OP_TINY: tiny_task(S, t, lt); break;

@@ -323,6 +323,11 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                 if (t[4] < 0 || t[4] >= d.n_paths || t[6] != d.n_out || t[5] < 0 || !fits(t[3], (int64_t)t[5] + t[6]))
                     return fail(TEBSCAT_EINVAL, "task %d: bad STOREZ", i);
                 break;
+            case OP_STOREU:
+                if (t[5] < 0 || t[6] < 1 || t[7] < 0 || (int64_t)t[7] + t[6] > (int64_t)d.n_paths * d.n_out ||
+                    !fits(t[3] & ~15, (t[3] & 15) + (int64_t)t[5] + t[6]))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad STOREU", i);
+                break;
             case OP_LOADPAIR:
                 if (t[4] < 0 || t[4] >= kMaxPairRows || t[4] >= d.n_paths || !fits(t[3], (int64_t)1 << d.log2_Np))
                     return fail(TEBSCAT_EINVAL, "task %d: bad LOADPAIR", i);

@@ -40,7 +40,7 @@ import numpy as np
 
 from . import filterbank as fbk
 
-OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY, OP_MULFOLD2, OP_LOADPAIR = 0, 1, 2, 3, 4, 5, 6, 7, 8
+OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY, OP_MULFOLD2, OP_LOADPAIR, OP_STOREU = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 FFT_INV, FFT_MOD, FFT_FUSE_FWD, FFT_PACK = 1, 2, 4, 8
 TASK_INTS = 12
 
@@ -978,6 +978,9 @@ def task_accesses(t, log2_Np):
     elif op == OP_STOREZ:
         i = np.arange(d)
         add(a + c + i, i % nt, False)
+    elif op == OP_STOREU:
+        i = np.arange(d)
+        add(a + c + i, i % nt, False)
     elif op == OP_TINY:
         u = np.arange(b)
         s = a + (u[:, None] << c) + np.arange(1 << c)[None, :]
@@ -1019,6 +1022,130 @@ def elide_barriers(tasks, steps, capacity, log2_Np):
         record(acc)
     keep[n_steps - 1] = True
     return keep
+
+
+def build_chains_unaveraged(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int, arena: _Arena,
+                            batch_slots: int = BATCH_SLOTS, oversampling: int = 0):
+    """average=False (core/scattering1d.py:293-294, :329-330, :366-367): no phi low-pass; every path is the
+    unpadded modulus at its own rate.  Returns the chains and the segments [(key, offset, length)] of the
+    output row (order 0 is the input itself and is not produced here)."""
+    n = geo.J_pad
+    log2_T = int(math.floor(math.log2(T)))
+    os_ = int(oversampling)
+    keys: List[Tuple[int, ...]] = [(i,) for i in range(len(bank.psi1))]
+    if max_order == 2:
+        for n1, p1 in enumerate(bank.psi1):
+            for n2, p2 in enumerate(bank.psi2):
+                if p2.j > p1.j:
+                    keys.append((n1, n2))
+    seg_len: Dict[Tuple[int, ...], Tuple[int, int]] = {}                 # key -> (first index, length)
+    k_of: Dict[Tuple[int, ...], int] = {}
+    for n1, p1 in enumerate(bank.psi1):
+        k1 = max(min(p1.j - os_, log2_T - os_), 0)
+        k_of[(n1,)] = k1
+        if max_order == 2:
+            for n2, p2 in enumerate(bank.psi2):
+                if p2.j > p1.j:
+                    k_of[(n1, n2)] = k1 + max(min(p2.j - k1 - os_, log2_T - k1 - os_), 0)
+    offsets: Dict[Tuple[int, ...], int] = {}
+    total = 0
+    for key in keys:
+        k = k_of[key]
+        i0, i1 = geo.ind_start[k], geo.ind_end[k]
+        seg_len[key] = (i0, i1 - i0)
+        offsets[key] = total
+        total += i1 - i0
+
+    def store(ref, key) -> TaskSpec:
+        i0, ln = seg_len[key]
+        return TaskSpec(OP_STOREU, ln, 200.0, 12.0, a=ref, c=i0, d=ln, e=offsets[key])
+
+    psi1_off = [arena.add(p.levels[0]) for p in bank.psi1]
+    psi2_off = [[arena.add(a) for a in p.levels] for p in bank.psi2]
+    chains: List[Chain] = []
+    u0 = Buf(1 << n, 'U0')
+    root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
+                 _merge_local_passes(_fft_stages((u0, 0), n, 1, 'fwd')), owns=[u0], depth=0)
+    chains.append(root)
+    groups: Dict[int, List[int]] = {}
+    for n1, p1 in enumerate(bank.psi1):
+        groups.setdefault(k_of[(n1,)], []).append(n1)
+    for k1 in sorted(groups):
+        l1 = n - k1
+        per_batch = max(1, batch_slots >> l1)
+        members = groups[k1]
+        for s0 in range(0, len(members), per_batch):
+            batch = members[s0:s0 + per_batch]
+            nb = len(batch)
+            x1 = Buf(nb << l1, 'U1[k1=%d:%d]' % (k1, batch[0]))
+            mf = [_mulfold(arena, (u0, 0), n, k1, (x1, i << l1), psi1_off[n1]) for i, n1 in enumerate(batch)]
+            st = [mf] + _merge_local_passes(_fuse_first_inverse_pass(mf, _fft_stages((x1, 0), l1, nb, 'inv_mod'), l1))   # :307-315
+            st.append([store((x1, i << l1), (n1,)) for i, n1 in enumerate(batch)])                                   # :329-330
+            kids: Dict[int, List[Tuple[int, int, int]]] = {}
+            if max_order == 2:
+                for i, n1 in enumerate(batch):
+                    for n2, p2 in enumerate(bank.psi2):
+                        if p2.j > bank.psi1[n1].j:
+                            kids.setdefault(k_of[(n1, n2)] - k1, []).append((i, n1, n2))
+            if kids:
+                st += _merge_local_passes(_fft_stages((x1, 0), l1, nb, 'fwd'))                                       # :317-318
+            c1 = Chain(x1.name, st, after=[root], reads=[u0], owns=[x1], depth=1)
+            chains.append(c1)
+            for k2 in sorted(kids):
+                l2 = l1 - k2
+                fam = kids[k2]
+                per = max(1, (batch_slots // 2) >> l2)
+                for s2 in range(0, len(fam), per):
+                    sub = fam[s2:s2 + per]
+                    x2 = Buf(len(sub) << l2, 'U2[%d,k2=%d]' % (batch[0], k2))
+                    mf2 = [_mulfold(arena, (x1, i << l1), l1, k2, (x2, c << l2), psi2_off[n2][k1])
+                           for c, (i, n1, n2) in enumerate(sub)]                                               # :347-348
+                    st2 = [mf2] + _merge_local_passes(
+                        _fuse_first_inverse_pass(mf2, _fft_stages((x2, 0), l2, len(sub), 'inv_mod'), l2))           # :350-353
+                    st2.append([store((x2, c << l2), (n1, n2)) for c, (i, n1, n2) in enumerate(sub)])             # :366-367
+                    chains.append(Chain(x2.name, st2, after=[c1], reads=[x1], owns=[x2], frees_own_at_end=True, depth=2))
+    segments = [(key, offsets[key], seg_len[key][1]) for key in keys]
+    return chains, segments, total
+
+
+def build_plan_unaveraged(J: int, N: int, Q, T: int, max_order: int = 2, oversampling: int = 0):
+    """Plan of the average=False transform: one output row of `n_out` floats per signal holding the paths
+    back to back (`segments`); order 0 (the input itself, core :293-294) is added by the frontend."""
+    Q1 = fbk._as_Q1(Q)
+    geo = fbk.build_geometry(N, J, Q1, T)
+    if geo.J_pad > LOG2_NP_MAX:
+        raise NotImplementedError('padded length 2**%d exceeds the single-CTA shared-memory design' % geo.J_pad)
+    bank = fbk.build_filter_bank(geo.J_pad, J, Q1, T)
+    capacity = smem_capacity()
+    last_err = None
+    for batch_slots in (BATCH_SLOTS, 4096, 2048, 1024, 512):
+        arena = _Arena()
+        chains, segments, total = build_chains_unaveraged(bank, geo, T, max_order, arena, batch_slots, oversampling)
+        try:
+            steps, high, chan, sched = schedule_chains(chains, capacity, 1, 0, 1)
+            break
+        except (RuntimeError, AssertionError) as e:
+            last_err = e
+    else:
+        raise NotImplementedError('no schedule fits shared memory for this configuration: %s' % last_err)
+    tasks, ranges = emit(steps)
+    if os.environ.get('TEBSCAT_RELAX', '1') != '0':
+        keep = elide_barriers(tasks, ranges, capacity, geo.J_pad)
+        for st in range(ranges.shape[0]):
+            if not keep[st]:
+                tasks[ranges[st, 0]:ranges[st, 1], 11] |= 1
+    logical = _round16(high)
+
+    class _U:
+        pass
+    u = _U()
+    u.J, u.Q, u.T, u.N, u.max_order, u.geo, u.bank = J, Q1, T, N, max_order, geo, bank
+    u.n_paths, u.n_out, u.segments = 1, total, segments
+    u.arena, u.tasks, u.steps = arena.finish(), tasks, ranges
+    u.chan = np.zeros(2, np.int32)
+    u.smem_complex, u.n_threads = logical + logical // 16, N_THREADS
+    u.stats = dict(n_steps=len(steps), n_tasks=tasks.shape[0], smem_logical=high, **sched)
+    return u
 
 
 def smem_capacity() -> int:

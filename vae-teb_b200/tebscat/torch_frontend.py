@@ -12,7 +12,7 @@ behind it.
 Differences from the fork, all on the lenient side:
  * ``T=None`` means ``2**J`` (the fork crashes, SURVEY.md item 2);
  * ``Q`` may be an int or a ``(Q1, 1)`` tuple (the fork takes ints only);
- * ``average=False`` (un-averaged U1/U2 outputs) raises ``NotImplementedError``; ``oversampling``,
+ * ``average=False`` (un-averaged U1/U2 outputs, ``out_type='list'`` or ``vectorize=False``) is one launch too; ``oversampling``,
    ``out_type='list'`` and ``vectorize=False`` are supported (the latter two are views of the
    fused array result).
 """
@@ -28,7 +28,7 @@ import torch.nn as nn
 from . import _lib
 from . import filterbank as fbk
 from .meta import compute_meta, output_size
-from .schedule import build_plan
+from .schedule import build_plan, build_plan_unaveraged
 
 
 class _DevicePlan:
@@ -192,9 +192,6 @@ class Scattering1D(nn.Module):
             warnings.warn("The vectorize option is deprecated and will be "
                           "removed in version 0.3. Please set "
                           "out_type='list' for equivalent functionality.", DeprecationWarning)
-        if not self.average:
-            raise NotImplementedError('the fused CUDA path implements average=True only '
-                                      '(un-averaged U1/U2 outputs are not built); there is no fallback path')
         if int(self.oversampling) < 0:
             raise ValueError('oversampling must be >= 0')
 
@@ -221,6 +218,8 @@ class Scattering1D(nn.Module):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         B = x2.shape[0]
+        if not self.average:
+            return self._scattering_unaveraged(x2, batch_shape)
         plan = self._plan_for(x.device.index if x.device.index is not None else torch.cuda.current_device())
         sched = self._sched[1]
         C, n_out = sched.n_paths, sched.n_out
@@ -242,6 +241,34 @@ class Scattering1D(nn.Module):
             key = meta['key'][c]
             j = tuple(int(v) for v in meta['j'][c][:len(key)])
             out.append({'coef': S[:, c, :].reshape(batch_shape + (n_out,)), 'j': j})
+        return [out, out]
+
+    def _scattering_unaveraged(self, x2, batch_shape):
+        """average=False (core/scattering1d.py:293-294, :329-330, :366-367): the input itself, then the unpadded
+        moduli U1 / U2 at their own rates.  One launch writes all paths back to back into one row per signal;
+        the coefficients returned are views of it."""
+        key = (self.J, self.N, self._Q1, self.T, self.max_order, int(self.oversampling))
+        if getattr(self, '_usched', None) is None or self._usched[0] != key:
+            self._usched = (key, build_plan_unaveraged(self.J, self.N, self._Q1, self.T, self.max_order,
+                                                       oversampling=int(self.oversampling)))
+            self._uplans = {}
+        sched = self._usched[1]
+        dev = x2.device
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        if index not in self._uplans:
+            self._uplans[index] = _DevicePlan(sched, index)
+        B = x2.shape[0]
+        row = torch.empty((B, sched.n_out), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().tebscat_scat1d_forward(self._uplans[index].handle, x2.data_ptr(), B, row.data_ptr(), stream))
+        meta = self.meta()
+        j_of = {tuple(meta['key'][c]): tuple(int(v) for v in meta['j'][c][:len(meta['key'][c])]) for c in range(len(meta['key']))}
+        coefs = [((), x2.reshape(batch_shape + (self.N,)))]                       # :294  S_0 = x
+        coefs += [(k, row[:, off:off + ln].reshape(batch_shape + (ln,))) for k, off, ln in sched.segments]
+        if self.out_type == 'array':                     # vectorize=False: dict keyed by the filter indices (:380-381)
+            out = {k: v for k, v in coefs}
+            return [out, out]
+        out = [{'coef': v, 'j': j_of[k]} for k, v in coefs]                      # :382-385
         return [out, out]
 
     def forward_normalized(self, x, mean, variance, log_channels='all_except_0', asinh_channels=None,
