@@ -160,3 +160,27 @@ def test_single_pass_dataset_entry_matches_two_calls():
     assert torch.equal(one['scattering'], a['scattering'])
     assert torch.equal(one['phase_corr'], a['phase_corr'][:, pm])
     assert torch.equal(one['cross_phase_corr'], b['cross_phase_corr'][:, cm])
+
+
+def test_transform_and_dense_forms_of_stage_b_agree(monkeypatch):
+    """Stage B exists in two forms: transforms on the interpreter (power-of-two decimation) and the dense
+    operator on the tensor cores.  Same products, same low-pass: they must agree to fp32 accuracy -- on the
+    production configuration (where the transform form is the default) and on the headline one (where it is not)."""
+    from tebscat import KymatioPhaseScattering1D
+    from tebscat.synth import ctg_batch
+    for (J, Q, T, N, mo, subset) in ((11, 4, 16, 5760, 1, 60), (6, 8, 64, 4800, 2, 41)):
+        x = ctg_batch(3, N, seed=17).cuda()
+        outs = {}
+        for mode in ('0', '1'):
+            monkeypatch.setenv('TEBSCAT_PHASE_FFT', mode)
+            m = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), max_order=mo)
+            assert m._dev_plan(0).uses_fft_pairs == (mode == '1')
+            pairs = torch.zeros(len(m.i_idx), dtype=torch.bool)
+            pairs[::max(1, len(m.i_idx) // subset)] = True                   # an odd number of rows per sample
+            outs[mode] = m(x, compute_phase=False, compute_cross_phase=True, phase_pairs=pairs)['cross_phase_corr'].cpu().numpy()
+        a, b = outs['0'], outs['1']
+        assert a.shape == b.shape
+        err = np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(a, axis=-1), 1e-30)
+        # rows whose energy is rounding noise of a strong product are excluded like in the oracle comparison
+        strong = np.linalg.norm(a, axis=-1) > 1e-4 * np.linalg.norm(a, axis=-1).max()
+        assert err[strong].max() < 2e-5, err[strong].max()
