@@ -167,6 +167,29 @@ int tebscat_phase_forward_dual(tebscat_phase_plan* plan, const float* x_dev, int
 /* Number of kernels the last forward call on this thread launched. */
 int tebscat_last_launch_count(void);
 
+/* ---- large-support level: padded lengths 2^14 .. 2^17 ----------------------
+ * At these lengths a spectrum no longer fits one SM.  The cascade keeps the reference's op order
+ * (core/scattering1d.py:269-370) with every op one launch over the batch on GLOBAL buffers of complex64
+ * (bit-reversed spectra); the transforms run as tile jobs of the step interpreter.  tebscat/large.py drives it. */
+typedef struct tebscat_large tebscat_large;
+int tebscat_large_create(int device, tebscat_large** out);
+void tebscat_large_destroy(tebscat_large* ctx);
+/* tile plan (tebscat.schedule.build_tile_plan) for in-place transforms of 2^log2_len <= 8192 samples; ownership moves */
+int tebscat_large_set_tile_plan(tebscat_large* ctx, int log2_len, int inverse, tebscat_plan* plan);
+/* pad (torch_backend.py:50-78) + real -> complex: x_dev [B, N] -> u_dev [B, 2^log2_Np] complex64 */
+int tebscat_large_pad_load(tebscat_large* ctx, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,
+                           float* u_dev, void* stream);
+/* fft / ifft (torch_backend.py:106-128, unnormalised), in place, forward natural -> bit-reversed, inverse back */
+int tebscat_large_fft(tebscat_large* ctx, float* buf_dev, int64_t n_transforms, int log2_len, int inverse, void* stream);
+/* cdgmm + subsample_fourier (kymatio/backend/torch_backend.py:147-219, torch_backend.py:18-48), times 2^-scale_exp */
+int tebscat_large_mulfold(tebscat_large* ctx, const float* src_dev, const float* filt_dev, float* dst_dev, int64_t B,
+                          int log_src, int logk, uint32_t chunk_mask, int log_chunk, int scale_exp, void* stream);
+/* modulus (kymatio/backend/torch_backend.py:137-141), in place */
+int tebscat_large_modulus(tebscat_large* ctx, float* buf_dev, int64_t n_complex, void* stream);
+/* unpad + concatenate (torch_backend.py:80-102, kymatio/backend/torch_backend.py:143-145) */
+int tebscat_large_store(tebscat_large* ctx, const float* buf_dev, int64_t B, int log_len, int i0, int n_out, int n_paths,
+                        int channel, float* out_dev, void* stream);
+
 /* Measured FP32 FMA peak of `device` in TFLOP/s (bench.py's FP32 roofline denominator;
  * MEASURED_PEAKS.json has no FP32 figure). */
 int tebscat_bench_fp32_peak(int device, double* tflops_out);

@@ -34,6 +34,11 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
         c.ep_mean = ep_mean; c.ep_std = ep_std; c.ep_mode = ep_mode; c.ep_log_eps = ep_log_eps;
         c.ep_trim = ep_trim; c.ep_time_major = ep_time_major; c.n_paths = n_paths;
         c.ch_limit = n_paths;
+        c.gbuf = nullptr; c.g_valid = 0;
+        if (z_mode == 8) {                          // tile jobs: `zc` is the global complex buffer, n_out = slots per job
+            c.gbuf = reinterpret_cast<float2*>(zc) + b * (long long)n_out;
+            c.g_valid = n_out;
+        }
         // phase stage B (OP_LOADPAIR): job b covers rows b*n_paths + q; zc/zp are then [rows][N] INPUTS
         if (z_mode == 4) {
             for (int q = 0; q < kMaxPairRows && q < n_paths; ++q) {

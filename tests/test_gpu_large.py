@@ -1,0 +1,62 @@
+"""Large-support level: padded lengths above 2^13 against the float64 oracle, and the pieces of the
+level on their own (transforms of every length on global buffers against numpy)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.scattering1d_oracle import ScatteringOracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('log_len', [3, 7, 10, 13, 14, 15, 16, 17])
+def test_global_transforms_match_numpy(log_len):
+    from tebscat import _lib
+    from tebscat.large import LargeDevicePlan, LargePlan
+    from tebscat.schedule import bitrev_indices
+    dp = _get_ctx()
+    L, n_tr = 1 << log_len, 5 if log_len > 10 else 37            # 37 transforms: the last tile is partial
+    rng = np.random.RandomState(log_len)
+    z = (rng.randn(n_tr, L) + 1j * rng.randn(n_tr, L)).astype(np.complex64)
+    br = bitrev_indices(L)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    buf = torch.view_as_real(torch.from_numpy(z).cuda()).contiguous()
+    _lib.check(_lib.load().tebscat_large_fft(dp.handle, ctypes.c_void_p(buf.data_ptr()), n_tr, log_len, 0, st))
+    got = torch.view_as_complex(buf).cpu().numpy()
+    ref = np.fft.fft(z.astype(np.complex128), axis=-1)[:, br]
+    assert np.abs(got - ref).max() < 2e-6 * np.abs(ref).max()
+    _lib.check(_lib.load().tebscat_large_fft(dp.handle, ctypes.c_void_p(buf.data_ptr()), n_tr, log_len, 1, st))
+    back = torch.view_as_complex(buf).cpu().numpy() / L
+    assert np.abs(back - z).max() < 2e-6 * np.abs(z).max()
+
+
+_ctx = {}
+
+
+def _get_ctx():
+    from tebscat.large import LargeDevicePlan, LargePlan
+    if 'dp' not in _ctx:
+        class _P:                                            # every tile length, no cascade
+            tile_lengths = list(range(1, 14))
+            arena = np.zeros(4, np.float32)
+        _ctx['dp'] = LargeDevicePlan(_P(), 0)
+    return _ctx['dp']
+
+
+@pytest.mark.parametrize('cfg', [(8, 8, 2 ** 13, 256, 2), (6, 4, 12000, 64, 2), (9, 2, 2 ** 14, 512, 1)])
+def test_large_support_matches_oracle(cfg):
+    from tebscat import Scattering1D
+    J, Q, N, T, mo = cfg
+    S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    assert S.J_pad > 13
+    x = torch.randn(3, N, generator=torch.Generator().manual_seed(J))
+    out, P = S(x.cuda())
+    torch.cuda.synchronize()
+    out = out.cpu().numpy().astype(np.float64)
+    ref = ScatteringOracle(J, N, Q, T, mo)(x.numpy())
+    assert out.shape == ref.shape and P.shape == (3, 1) + ref.shape[1:]
+    nr = np.linalg.norm(ref, axis=-1)
+    err = np.linalg.norm(out - ref, axis=-1)
+    assert np.all(err <= 1e-5 * nr + 1e-10 * nr.max()), float((err / nr).max())

@@ -61,6 +61,8 @@ enum : int32_t {
     OP_TINY = 6,     // a=region b=transforms c=log2L (1..3) e=flags: whole transforms of 2, 4 or 8 samples
     OP_LOADPAIR = 8, // phase stage B on the interpreter: a=dst b=row of the job; c(t) = |z_i| e^{i p theta_i} conj(z_j)
                      // of the row's pair, reflect-padded (kymatio_phase_scattering.py:211-218, :283/:339, :162-209)
+    OP_LOADC = 10,   // large-support level: a=dst b=slots: complex tile of the job's global buffer -> shared memory
+    OP_STOREC = 11,  //                      a=src b=slots: and back
     OP_STOREU = 9,   // average=False: a=src c=first index d=count e=offset in the output row: the modulus itself
     OP_MULFOLD2 = 7  // like MULFOLD with k >= 1 on a PACKED source (spectrum of u_a + i u_b): a=src b=log2Lsrc c=log2k
                      // d=dst of the a-child e=filter offset f=chunk mask g=dst of the b-child h=log2 chunk width
@@ -101,6 +103,9 @@ struct SignalCtx {
     const float2* pr_zc[kMaxPairRows];  // (re, im)[N] of the row's 'j' filter
     float pr_pw[kMaxPairRows];
     int32_t ch_limit;        // channels >= ch_limit are not stored (n_paths for the scattering transform)
+    // large-support level (OP_LOADC / OP_STOREC): this job's tile of a global complex buffer
+    float2* gbuf;
+    int32_t g_valid;         // complex elements of the tile that exist (the last job may be partial)
 };
 enum : int32_t { EP_NONE = 0, EP_LOG = 1, EP_ASINH = 2 };
 
@@ -890,6 +895,25 @@ TEB_D void storeb_task(const float2* S, const SignalCtx& c, const Task& t, int l
     }
 }
 
+// Large-support level: transforms of more than 8192 samples live in global memory; their
+// 8192-sample blocks -- and every shorter transform of that level -- pass through shared memory as tiles.
+TEB_D void loadc_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
+    for (int i0 = lt; i0 < t.b; i0 += 4 * t.nt) {
+        float2 v[4];
+        TEB_UNROLL for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * t.nt;
+            v[j] = (i < t.b && i < c.g_valid) ? c.gbuf[i] : make_float2(0.f, 0.f);
+        }
+        TEB_UNROLL for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * t.nt;
+            if (i < t.b) S[swz(t.a + i)] = v[j];
+        }
+    }
+}
+TEB_D void storec_task(const float2* S, const SignalCtx& c, const Task& t, int lt) {
+    for (int i = lt; i < t.b && i < c.g_valid; i += t.nt) c.gbuf[i] = S[swz(t.a + i)];
+}
+
 // average=False (core/scattering1d.py:329-330, :366-367): the unpadded modulus U1 / U2 at its own rate
 TEB_D void storeu_task(const float2* S, const SignalCtx& c, const Task& t, int lt) {
     for (int n = lt; n < t.d; n += t.nt) c.out[(int64_t)t.e + n] = S[swz(t.a + t.c + n)].x;
@@ -931,6 +955,8 @@ TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const floa
         case OP_MULFOLD2: mulfold2_task(S, arena, t, lt); break;
         case OP_LOADPAIR: loadpair_task(S, c, t, lt); break;
         case OP_STOREU: storeu_task(S, c, t, lt); break;
+        case OP_LOADC: loadc_task(S, c, t, lt); break;
+        case OP_STOREC: storec_task(S, c, t, lt); break;
         case OP_STOREB: storeb_task(S, c, t, lt); break;
         case OP_STOREZ: storez_task(S, c, t, lt); break;
         case OP_TINY: tiny_task(S, t, lt); break;

@@ -70,6 +70,10 @@ struct KParams {
     const int32_t* pair_subset;
     long long pair_rows;
     int32_t pair_n_sel, pair_F;
+    // large-support level: job b works on the tile [b * g_slots, +g_slots) of a global complex buffer
+    float2* gbuf;
+    long long g_total;
+    int32_t g_slots;
 };
 
 constexpr int kThreads = 512;
@@ -127,6 +131,13 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
             c.ep_time_major = p.ep_time_major;
             c.n_paths = p.n_paths;
             c.ch_limit = p.n_paths;
+            c.gbuf = nullptr;
+            c.g_valid = 0;
+            if (p.gbuf) {
+                const long long e0 = b * (long long)p.g_slots;
+                c.gbuf = p.gbuf + e0;
+                c.g_valid = (int)(p.g_total - e0 < p.g_slots ? p.g_total - e0 : p.g_slots);
+            }
             if (p.pair_rows > 0) {
                 const long long r0 = b * p.n_paths;
                 c.ch_limit = (int)(p.pair_rows - r0 < p.n_paths ? p.pair_rows - r0 : p.n_paths);
@@ -323,6 +334,10 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                 if (t[4] < 0 || t[4] >= d.n_paths || t[6] != d.n_out || t[5] < 0 || !fits(t[3], (int64_t)t[5] + t[6]))
                     return fail(TEBSCAT_EINVAL, "task %d: bad STOREZ", i);
                 break;
+            case OP_LOADC:
+            case OP_STOREC:
+                if (t[4] < 1 || !fits(t[3], t[4])) return fail(TEBSCAT_EINVAL, "task %d: bad tile transfer", i);
+                break;
             case OP_STOREU:
                 if (t[5] < 0 || t[6] < 1 || t[7] < 0 || (int64_t)t[7] + t[6] > (int64_t)d.n_paths * d.n_out ||
                     !fits(t[3] & ~15, (t[3] & 15) + (int64_t)t[5] + t[6]))
@@ -463,6 +478,9 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     k.pair_rows = 0;
     k.pair_n_sel = 0;
     k.pair_F = 0;
+    k.gbuf = nullptr;
+    k.g_total = 0;
+    k.g_slots = 0;
     *out = p;
     return TEBSCAT_OK;
 }
@@ -1077,5 +1095,290 @@ extern "C" int tebscat_phase_forward_dual(tebscat_phase_plan* p, const float* x_
         if (int rc = launch_pairs(p, p->d_zp, p->d_zc, sub_w, n_within, nb, out_within_dev + (size_t)b0 * n_within * d.n_out, st)) return rc;
         if (int rc = launch_pairs(p, p->d_zp, p->d_zc2, sub_c, n_cross, nb, out_cross_dev + (size_t)b0 * n_cross * d.n_out, st)) return rc;
     }
+    return TEBSCAT_OK;
+}
+
+
+// =================================================================================
+// Large-support level: padded lengths above 2^13
+// =================================================================================
+// Spectra of more than 8192 samples live in global memory (L2/HBM).  The cascade keeps the reference's op order
+// (core/scattering1d.py:269-370); every op is one launch over the whole batch:
+//   pad+load, transform (tile jobs of the step interpreter; above 8192 samples one global radix pass plus
+//   tile jobs), filter multiply + periodisation, modulus, unpad + store.
+// Spectra are in bit-reversed order like everywhere else, so the periodisation is a sum of adjacent elements.
+
+constexpr int kLargeMaxLog2 = 17;
+
+struct tebscat_large {
+    int device = 0;
+    int n_sms = 0;
+    tebscat_plan* tile[kLog2TwMax + 1][2] = {};     // [log2 length][inverse]: owned
+    float2* d_tw[kLargeMaxLog2 + 1] = {};           // W_L^m, m < L, for L = 2^14 .. 2^17
+};
+
+extern "C" int tebscat_large_create(int device, tebscat_large** out) {
+    if (!out) return fail(TEBSCAT_EINVAL, "null argument");
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(TEBSCAT_EINVAL, "device %d not in [0,%d)", device, n_dev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    tebscat_large* g = new tebscat_large();
+    g->device = device;
+    g->n_sms = prop.multiProcessorCount;
+    for (int n = kLog2TwMax + 1; n <= kLargeMaxLog2; ++n) {
+        const size_t L = (size_t)1 << n;
+        std::vector<float2> tw(L);
+        const double w0 = -2.0 * M_PI / (double)L;
+        for (size_t m = 0; m < L; ++m) tw[m] = make_float2((float)cos(w0 * (double)m), (float)sin(w0 * (double)m));
+        CU(cudaMalloc(&g->d_tw[n], L * sizeof(float2)));
+        CU(cudaMemcpy(g->d_tw[n], tw.data(), L * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    *out = g;
+    return TEBSCAT_OK;
+}
+
+extern "C" void tebscat_large_destroy(tebscat_large* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    for (int n = 0; n <= kLog2TwMax; ++n)
+        for (int d = 0; d < 2; ++d) tebscat_plan_destroy(g->tile[n][d]);
+    for (int n = 0; n <= kLargeMaxLog2; ++n) cudaFree(g->d_tw[n]);
+    delete g;
+}
+
+/* Hand a tile plan (schedule.build_tile_plan) for transforms of 2^log2_len samples to the context (it takes ownership). */
+extern "C" int tebscat_large_set_tile_plan(tebscat_large* g, int log2_len, int inverse, tebscat_plan* plan) {
+    if (!g || !plan || log2_len < 1 || log2_len > kLog2TwMax) return fail(TEBSCAT_EINVAL, "bad tile plan");
+    if (plan->device != g->device) return fail(TEBSCAT_EINVAL, "tile plan lives on another device");
+    tebscat_plan_destroy(g->tile[log2_len][inverse ? 1 : 0]);
+    g->tile[log2_len][inverse ? 1 : 0] = plan;
+    return TEBSCAT_OK;
+}
+
+// reflect padding (torch_backend.py:50-78) + real -> complex, natural order
+__global__ void g_pad_load_kernel(const float* __restrict__ x, float2* __restrict__ u, long long B, int N, int pad_left, int log2_Np) {
+    const long long total = B << log2_Np;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e >> log2_Np;
+        int r = (int)(e - (b << log2_Np)) - pad_left;
+        if (r < 0) r = -r;
+        if (r >= N) r = 2 * (N - 1) - r;
+        u[e] = make_float2(__ldg(x + b * N + r), 0.f);
+    }
+}
+
+// One radix-R pass (R = 2^logr <= 16) across the R blocks of 8192 samples of every length-2^n transform:
+// forward = first decimation-in-frequency pass (natural -> R blocks, twiddled), inverse = last decimation-in-time pass.
+template <int LOGR>
+__global__ void g_radix_kernel(float2* __restrict__ buf, long long n_transforms, int n, int inverse, const float2* __restrict__ tw) {
+    constexpr int R = 1 << LOGR;
+    const int logm = n - LOGR;                               // block length 2^logm (= 8192)
+    const long long total = n_transforms << logm;
+    const long long L = (long long)1 << n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long s = e >> logm;
+        const int i0 = (int)(e - (s << logm));
+        float2* base = buf + s * L;
+        float2 v[R], y[R];
+        if (!inverse) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) v[j] = base[i0 + ((long long)j << logm)];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {                    // X_q = sum_j v_j W_R^(j q); y_q = X_q W_L^(i0 q)
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const float2 w = __ldg(tw + ((((long long)j * q) & (R - 1)) << logm));      // W_R^(jq) = W_L^(jq L/R)
+                    acc.x += v[j].x * w.x - v[j].y * w.y;
+                    acc.y += v[j].x * w.y + v[j].y * w.x;
+                }
+                const float2 t = __ldg(tw + (long long)i0 * q);
+                y[q] = make_float2(acc.x * t.x - acc.y * t.y, acc.x * t.y + acc.y * t.x);
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                int rq = 0;
+#pragma unroll
+                for (int bb = 0; bb < LOGR; ++bb) rq |= ((q >> bb) & 1) << (LOGR - 1 - bb);
+                base[i0 + ((long long)rq << logm)] = y[q];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                int rq = 0;
+#pragma unroll
+                for (int bb = 0; bb < LOGR; ++bb) rq |= ((q >> bb) & 1) << (LOGR - 1 - bb);
+                const float2 z = base[i0 + ((long long)rq << logm)];
+                const float2 t = __ldg(tw + (long long)i0 * q);                               // times conj(W_L^(i0 q))
+                v[q] = make_float2(z.x * t.x + z.y * t.y, z.y * t.x - z.x * t.y);
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j) {                    // x_j = sum_q v_q conj(W_R^(j q))
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const float2 w = __ldg(tw + ((((long long)j * q) & (R - 1)) << logm));
+                    acc.x += v[q].x * w.x + v[q].y * w.y;
+                    acc.y += v[q].y * w.x - v[q].x * w.y;
+                }
+                y[j] = acc;
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j) base[i0 + ((long long)j << logm)] = y[j];
+        }
+    }
+}
+
+static int launch_tile_jobs(const tebscat_large* g, float2* buf, long long total_elems, int log2_len, int inverse, cudaStream_t st) {
+    const tebscat_plan* a = g->tile[log2_len][inverse ? 1 : 0];
+    if (!a) return fail(TEBSCAT_EINVAL, "no tile plan for transforms of 2^%d samples", log2_len);
+    KParams kp = a->kp;
+    kp.gbuf = buf;
+    kp.g_total = total_elems;
+    kp.g_slots = 8192;
+    const long long jobs = (total_elems + 8191) / 8192;
+    const int grid = (int)(jobs < (long long)a->n_sms ? jobs : (long long)a->n_sms);
+    scat1d_kernel<false><<<grid, a->desc.n_threads, a->smem_bytes, st>>>(kp, nullptr, nullptr, jobs);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+/* In-place transforms of `n_transforms` contiguous sequences of 2^log2_len complex samples (2 <= len <= 2^17).
+ * Forward: natural -> bit-reversed order; inverse: bit-reversed -> natural, unnormalised. */
+extern "C" int tebscat_large_fft(tebscat_large* g, float* buf_dev, int64_t n_transforms, int log2_len, int inverse, void* stream) {
+    if (!g || !buf_dev || n_transforms < 1 || log2_len < 1 || log2_len > kLargeMaxLog2) return fail(TEBSCAT_EINVAL, "bad transform request");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* buf = reinterpret_cast<float2*>(buf_dev);
+    const long long total = (long long)n_transforms << log2_len;
+    if (log2_len <= kLog2TwMax) return launch_tile_jobs(g, buf, total, log2_len, inverse, st);
+    const int logr = log2_len - kLog2TwMax;
+    const int blocks = g->n_sms * 8;
+    auto radix = [&]() {
+        switch (logr) {
+            case 1: g_radix_kernel<1><<<blocks, 256, 0, st>>>(buf, n_transforms, log2_len, inverse, g->d_tw[log2_len]); break;
+            case 2: g_radix_kernel<2><<<blocks, 256, 0, st>>>(buf, n_transforms, log2_len, inverse, g->d_tw[log2_len]); break;
+            case 3: g_radix_kernel<3><<<blocks, 256, 0, st>>>(buf, n_transforms, log2_len, inverse, g->d_tw[log2_len]); break;
+            default: g_radix_kernel<4><<<blocks, 256, 0, st>>>(buf, n_transforms, log2_len, inverse, g->d_tw[log2_len]); break;
+        }
+        ++g_launches;
+    };
+    if (!inverse) {
+        radix();
+        CU(cudaGetLastError());
+        return launch_tile_jobs(g, buf, total, kLog2TwMax, 0, st);
+    }
+    if (int rc = launch_tile_jobs(g, buf, total, kLog2TwMax, 1, st)) return rc;
+    radix();
+    CU(cudaGetLastError());
+    return TEBSCAT_OK;
+}
+
+extern "C" int tebscat_large_pad_load(tebscat_large* g, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,
+                                      float* u_dev, void* stream) {
+    if (!g || !x_dev || !u_dev || B < 1 || N < 2 || pad_left < 0 || pad_left >= N || ((1LL << log2_Np) - N - pad_left) >= N)
+        return fail(TEBSCAT_EINVAL, "Indefinite padding size (larger than tensor).");
+    CU(cudaSetDevice(g->device));
+    g_pad_load_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(x_dev, reinterpret_cast<float2*>(u_dev), B, N, pad_left, log2_Np);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+// dst[b, m] = 2^-sexp * sum_{t<k} src[b, m k + t] * f[m k + t]  (bit-reversed order; 4-bin chunks of the k-block that
+// the host found negligible for every output are skipped: `mask` over up to 32 chunks of 2^logcw bins)
+__global__ void g_mulfold_kernel(const float2* __restrict__ src, const float* __restrict__ f, float2* __restrict__ dst,
+                                 long long B, int log_src, int logk, unsigned mask, int logcw, float scale) {
+    const int log_dst = log_src - logk;
+    const long long total = B << log_dst;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e >> log_dst;
+        const long long m = e - (b << log_dst);
+        const float2* s = src + (b << log_src) + (m << logk);
+        const float* ff = f + (m << logk);
+        float ax = 0.f, ay = 0.f;
+        if (logk < 2) {
+            for (int t = 0; t < (1 << logk); ++t) {
+                const float2 z = s[t];
+                const float w = __ldg(ff + t);
+                ax = fmaf(z.x, w, ax);
+                ay = fmaf(z.y, w, ay);
+            }
+        } else {
+            unsigned rest = mask;
+            while (rest) {
+                const int i_chunk = (__ffs(rest) - 1) << logcw;
+                rest &= rest - 1;
+                for (int t = i_chunk; t < i_chunk + (1 << logcw); t += 4) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(ff + t));
+                    const float2 z0 = s[t], z1 = s[t + 1], z2 = s[t + 2], z3 = s[t + 3];
+                    ax = fmaf(z0.x, w.x, ax); ay = fmaf(z0.y, w.x, ay);
+                    ax = fmaf(z1.x, w.y, ax); ay = fmaf(z1.y, w.y, ay);
+                    ax = fmaf(z2.x, w.z, ax); ay = fmaf(z2.y, w.z, ay);
+                    ax = fmaf(z3.x, w.w, ax); ay = fmaf(z3.y, w.w, ay);
+                }
+            }
+        }
+        dst[e] = make_float2(ax * scale, ay * scale);
+    }
+}
+
+/* cdgmm + subsample_fourier (kymatio/backend/torch_backend.py:147-219, torch_backend.py:18-48) on global spectra. */
+extern "C" int tebscat_large_mulfold(tebscat_large* g, const float* src_dev, const float* filt_dev, float* dst_dev, int64_t B,
+                                     int log_src, int logk, uint32_t chunk_mask, int log_chunk, int scale_exp, void* stream) {
+    if (!g || !src_dev || !filt_dev || !dst_dev || B < 1 || log_src < 1 || log_src > kLargeMaxLog2 || logk < 0 || logk > log_src ||
+        (logk >= 2 && (chunk_mask == 0 || log_chunk < 2 || log_chunk > logk || (logk - log_chunk) > 5)))
+        return fail(TEBSCAT_EINVAL, "bad filter multiply request");
+    CU(cudaSetDevice(g->device));
+    g_mulfold_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(src_dev), filt_dev,
+                                                                      reinterpret_cast<float2*>(dst_dev), B, log_src, logk, chunk_mask,
+                                                                      log_chunk, ldexpf(1.0f, -scale_exp));
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+__global__ void g_modulus_kernel(float2* __restrict__ buf, long long total) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const float2 z = buf[e];
+        buf[e] = make_float2(sqrtf(fmaf(z.x, z.x, z.y * z.y)), 0.f);
+    }
+}
+
+/* modulus (kymatio/backend/torch_backend.py:137-141), in place, imaginary part zeroed */
+extern "C" int tebscat_large_modulus(tebscat_large* g, float* buf_dev, int64_t n_complex, void* stream) {
+    if (!g || !buf_dev || n_complex < 1) return fail(TEBSCAT_EINVAL, "null argument");
+    CU(cudaSetDevice(g->device));
+    g_modulus_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(buf_dev), n_complex);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+__global__ void g_store_kernel(const float2* __restrict__ buf, float* __restrict__ out, long long B, int log_len, int i0, int n_out,
+                               int n_paths, int channel) {
+    const long long total = B * n_out;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / n_out;
+        const int n = (int)(e - b * n_out);
+        out[(b * n_paths + channel) * n_out + n] = buf[(b << log_len) + i0 + n].x;
+    }
+}
+
+/* unpad + concatenate (torch_backend.py:80-102, kymatio/backend/torch_backend.py:143-145): real part of samples
+ * [i0, i0 + n_out) of every length-2^log_len signal -> channel `channel` of out [B, n_paths, n_out] */
+extern "C" int tebscat_large_store(tebscat_large* g, const float* buf_dev, int64_t B, int log_len, int i0, int n_out, int n_paths,
+                                   int channel, float* out_dev, void* stream) {
+    if (!g || !buf_dev || !out_dev || B < 1 || i0 < 0 || n_out < 1 || i0 + n_out > (1 << log_len) || channel < 0 || channel >= n_paths)
+        return fail(TEBSCAT_EINVAL, "bad store request");
+    CU(cudaSetDevice(g->device));
+    g_store_kernel<<<g->n_sms * 4, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(buf_dev), out_dev, B, log_len, i0,
+                                                                    n_out, n_paths, channel);
+    CU(cudaGetLastError());
+    ++g_launches;
     return TEBSCAT_OK;
 }

@@ -78,6 +78,25 @@ def load():
     lib.tebscat_phase_forward_dual.restype = ctypes.c_int
     lib.tebscat_phase_forward_dual.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                i32p, ctypes.c_int, i32p, ctypes.c_int, vp, vp, vp]
+    u32 = ctypes.c_uint32
+    lib.tebscat_large_create.restype = ctypes.c_int
+    lib.tebscat_large_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    lib.tebscat_large_destroy.restype = None
+    lib.tebscat_large_destroy.argtypes = [vp]
+    lib.tebscat_large_set_tile_plan.restype = ctypes.c_int
+    lib.tebscat_large_set_tile_plan.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.tebscat_large_pad_load.restype = ctypes.c_int
+    lib.tebscat_large_pad_load.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.tebscat_large_fft.restype = ctypes.c_int
+    lib.tebscat_large_fft.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, vp]
+    lib.tebscat_large_mulfold.restype = ctypes.c_int
+    lib.tebscat_large_mulfold.argtypes = [vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, u32, ctypes.c_int,
+                                          ctypes.c_int, vp]
+    lib.tebscat_large_modulus.restype = ctypes.c_int
+    lib.tebscat_large_modulus.argtypes = [vp, vp, ctypes.c_int64, vp]
+    lib.tebscat_large_store.restype = ctypes.c_int
+    lib.tebscat_large_store.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, vp, vp]
     lib.tebscat_scat1d_profile_steps.restype = ctypes.c_int
     lib.tebscat_scat1d_profile_steps.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp]
     lib.tebscat_bench_fp32_peak.restype = ctypes.c_int

@@ -1,0 +1,172 @@
+"""Large-support level: padded lengths 2^14 .. 2^17.
+
+At these lengths a spectrum (128 KB .. 1 MB) no longer fits one SM, so the fused single-kernel cascade of
+``schedule.py`` does not apply.  This driver keeps the reference's op order
+(``kymatio/scattering1d/core/scattering1d.py:269-370``) with every op ONE launch over the whole batch on global
+(L2/HBM-resident) complex buffers -- pad + load, transform, filter multiply + periodisation, modulus, unpad + store
+-- all hand-written CUDA behind the C ABI (``tebscat_large_*``).  Transforms run as tile jobs of the step
+interpreter (``schedule.build_tile_plan``); above 8192 samples one global radix pass precedes / follows them.
+Spectra are kept in bit-reversed order, so the periodisation is a sum of adjacent elements here too.
+
+There is no CPU or torch fallback in here: torch only owns the buffers.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import filterbank as fbk
+from . import schedule as sch
+
+LOG2_MAX = 17
+
+
+class _TilePlanOwner:
+    """Creates the device plan of a tile schedule and hands it to the large-support context."""
+
+    def __init__(self, ctx, n, inverse, device_index):
+        from .torch_frontend import _DevicePlan
+        dp = _DevicePlan(sch.build_tile_plan(n, inverse), device_index)
+        _lib.check(_lib.load().tebscat_large_set_tile_plan(ctx, n, 1 if inverse else 0, dp.handle))
+        dp.handle = None
+
+
+class LargePlan:
+    """Host description: geometry, filter arena (bit-reversed, fp32 like register_filters) and the op list."""
+
+    def __init__(self, J, N, Q, T, max_order=2, oversampling=0):
+        Q1 = fbk._as_Q1(Q)
+        self.J, self.N, self.Q, self.T, self.max_order = J, N, Q1, T, max_order
+        self.geo = geo = fbk.build_geometry(N, J, Q1, T)
+        n = geo.J_pad
+        if n > LOG2_MAX:
+            raise NotImplementedError('padded length 2**%d exceeds the large-support level (max 2**%d)' % (n, LOG2_MAX))
+        bank = fbk.build_filter_bank(n, J, Q1, T)
+        log2_T = int(math.floor(math.log2(T)))
+        os_ = int(oversampling)
+        kf = max(log2_T - os_, 0)
+        self.lf = lf = n - kf
+        if lf < 1:
+            raise NotImplementedError('output-rate length below 2 samples is not supported')
+        self.i0, i1 = geo.ind_start[kf], geo.ind_end[kf]
+        self.n_out = i1 - self.i0
+        arena = sch._Arena()
+        phi_off = [arena.add(a) for a in bank.phi.levels]
+        psi1_off = [arena.add(p.levels[0]) for p in bank.psi1]
+        psi2_off = [[arena.add(a) for a in p.levels] for p in bank.psi2]
+
+        def mf(off, log_src, logk):
+            """(filter offset, log_src, logk, chunk mask, log2 chunk width, scale exponent)"""
+            if logk >= 2:
+                mask, logcw = arena.chunk_mask(off, logk), sch._Arena.chunk_log2(logk)
+            else:
+                mask, logcw = 0, 0
+            return (off, log_src, logk, mask & 0xffffffff, logcw, logk + (log_src - logk))   # mean over k, 1/L of the iFFT
+
+        keys = [()] + [(i,) for i in range(len(bank.psi1))]
+        if max_order == 2:
+            for n1, p1 in enumerate(bank.psi1):
+                for n2, p2 in enumerate(bank.psi2):
+                    if p2.j > p1.j:
+                        keys.append((n1, n2))
+        self.keys = keys
+        channel = {k: c for c, k in enumerate(keys)}
+        # the cascade as a list of paths: (channel, [first-order op], [second-order ops])
+        self.s0 = mf(phi_off[0], n, n - lf)                                       # core :285-292
+        self.first = []
+        for n1, p1 in enumerate(bank.psi1):
+            k1 = max(min(p1.j - os_, log2_T - os_), 0)                            # :304
+            if not p1.xi < 0.5 / (2 ** k1):
+                raise AssertionError('psi1 aliasing assertion of the reference violated')
+            l1 = n - k1
+            entry = dict(ch=channel[(n1,)], l1=l1, mul=mf(psi1_off[n1], n, k1), leaf=mf(phi_off[k1], l1, l1 - lf), kids=[])
+            if max_order == 2:
+                for n2, p2 in enumerate(bank.psi2):
+                    if p2.j > p1.j:
+                        k2 = max(min(p2.j - k1 - os_, log2_T - k1 - os_), 0)      # :344-345
+                        l2 = l1 - k2
+                        entry['kids'].append(dict(ch=channel[(n1, n2)], l2=l2, mul=mf(psi2_off[n2][k1], l1, k2),
+                                                  leaf=mf(phi_off[k1 + k2], l2, l2 - lf)))
+            self.first.append(entry)
+        self.arena = arena.finish()
+        self.n_paths = len(keys)
+        lens = {n, lf} | {e['l1'] for e in self.first} | {k['l2'] for e in self.first for k in e['kids']}
+        self.tile_lengths = sorted(min(v, sch.LOG2_NP_MAX) for v in lens)
+
+
+class LargeDevicePlan:
+    def __init__(self, plan: LargePlan, device_index: int):
+        lib = _lib.load()
+        self._lib = lib
+        self.plan = plan
+        self.device_index = device_index
+        handle = ctypes.c_void_p()
+        _lib.check(lib.tebscat_large_create(int(device_index), ctypes.byref(handle)))
+        self.handle = handle
+        for nlen in sorted(set(plan.tile_lengths)):
+            for inv in (False, True):
+                _TilePlanOwner(handle, nlen, inv, device_index)
+        self.arena = torch.from_numpy(np.ascontiguousarray(plan.arena, np.float32)).to(torch.device('cuda', device_index))
+        self._ws = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self._lib.tebscat_large_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _workspace(self, B, dev):
+        key = (B, dev.index)
+        if key not in self._ws:
+            Np = 1 << self.plan.geo.J_pad
+            self._ws = {key: (torch.empty(B * Np * 2, dtype=torch.float32, device=dev),          # U0
+                              torch.empty(B * Np * 2, dtype=torch.float32, device=dev),          # first-order work
+                              torch.empty(B * Np, dtype=torch.float32, device=dev),              # second-order work (<= Np/2)
+                              torch.empty(B * (2 << self.plan.lf), dtype=torch.float32, device=dev))}   # leaf
+        return self._ws[key]
+
+    def forward(self, x2, out):
+        """x2: (B, N) float32 CUDA contiguous; out: (B, C, n_out) float32 CUDA."""
+        p, lib, g = self.plan, self._lib, self.handle
+        B = x2.shape[0]
+        dev = x2.device
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        U0, W1, W2, WL = self._workspace(B, dev)
+        n, lf = p.geo.J_pad, p.lf
+        fa = self.arena.data_ptr()
+
+        def mulfold(src, spec, dst):
+            off, log_src, logk, mask, logcw, sexp = spec
+            _lib.check(lib.tebscat_large_mulfold(g, ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(fa + 4 * off),
+                                                 ctypes.c_void_p(dst.data_ptr()), B, log_src, logk, mask, logcw, sexp, st))
+
+        def fft(buf, log_len, inverse):
+            _lib.check(lib.tebscat_large_fft(g, ctypes.c_void_p(buf.data_ptr()), B, log_len, 1 if inverse else 0, st))
+
+        def leaf(src, spec, ch):                              # phi multiply + periodise -> iFFT -> unpad -> channel (:287-292)
+            mulfold(src, spec, WL)
+            fft(WL, lf, True)
+            _lib.check(lib.tebscat_large_store(g, ctypes.c_void_p(WL.data_ptr()), B, lf, p.i0, p.n_out, p.n_paths, ch,
+                                               ctypes.c_void_p(out.data_ptr()), st))
+
+        _lib.check(lib.tebscat_large_pad_load(g, ctypes.c_void_p(x2.data_ptr()), B, p.N, p.geo.pad_left, n,
+                                              ctypes.c_void_p(U0.data_ptr()), st))                    # :278
+        fft(U0, n, False)                                                                             # :280
+        leaf(U0, p.s0, 0)
+        for e in p.first:
+            mulfold(U0, e['mul'], W1)                                                                 # :307-310
+            fft(W1, e['l1'], True)                                                                    # :312
+            _lib.check(lib.tebscat_large_modulus(g, ctypes.c_void_p(W1.data_ptr()), B << e['l1'], st))   # :315
+            fft(W1, e['l1'], False)                                                                   # :318
+            leaf(W1, e['leaf'], e['ch'])                                                              # :320-327
+            for k in e['kids']:
+                mulfold(W1, k['mul'], W2)                                                             # :347-348
+                fft(W2, k['l2'], True)                                                                # :350
+                _lib.check(lib.tebscat_large_modulus(g, ctypes.c_void_p(W2.data_ptr()), B << k['l2'], st))   # :352
+                fft(W2, k['l2'], False)                                                               # :355
+                leaf(W2, k['leaf'], k['ch'])                                                          # :358-364
+        return out

@@ -41,6 +41,7 @@ import numpy as np
 from . import filterbank as fbk
 
 OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY, OP_MULFOLD2, OP_LOADPAIR, OP_STOREU = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+OP_LOADC, OP_STOREC = 10, 11
 FFT_INV, FFT_MOD, FFT_FUSE_FWD, FFT_PACK = 1, 2, 4, 8
 TASK_INTS = 12
 
@@ -981,6 +982,12 @@ def task_accesses(t, log2_Np):
     elif op == OP_STOREU:
         i = np.arange(d)
         add(a + c + i, i % nt, False)
+    elif op == OP_LOADC:
+        i = np.arange(b)
+        add(a + i, i % nt, True)
+    elif op == OP_STOREC:
+        i = np.arange(b)
+        add(a + i, i % nt, False)
     elif op == OP_TINY:
         u = np.arange(b)
         s = a + (u[:, None] << c) + np.arange(1 << c)[None, :]
@@ -1146,6 +1153,35 @@ def build_plan_unaveraged(J: int, N: int, Q, T: int, max_order: int = 2, oversam
     u.smem_complex, u.n_threads = logical + logical // 16, N_THREADS
     u.stats = dict(n_steps=len(steps), n_tasks=tasks.shape[0], smem_logical=high, **sched)
     return u
+
+
+TILE_SLOTS = 8192                 # complex elements one tile job moves through shared memory
+
+
+def build_tile_plan(n: int, inverse: bool):
+    """Large-support level: in-place transforms of length 2^n (n <= 13) on a GLOBAL buffer, one
+    job = one tile of 8192 elements = 8192 >> n transforms: LOADC -> chained passes -> STOREC.
+    Forward: natural -> bit-reversed; inverse: bit-reversed -> natural, unnormalised (like the cascade's own)."""
+    if not 1 <= n <= LOG2_NP_MAX:
+        raise ValueError('tile transforms have 2 .. 8192 samples')
+    count = max(1, TILE_SLOTS >> n)
+    slots = count << n
+    buf = Buf(slots, 'tile')
+    st = [[TaskSpec(OP_LOADC, -(-slots // 4), 900.0, 30.0, a=(buf, 0), b=slots)]]
+    st += _merge_local_passes(_fft_stages((buf, 0), n, count, 'inv' if inverse else 'fwd'))
+    st.append([TaskSpec(OP_STOREC, slots, 300.0, 12.0, a=(buf, 0), b=slots)])
+    steps, high, chan, sched = schedule_chains([Chain('tile', st, owns=[buf], depth=0)], smem_capacity(), 1, 0, 1)
+    tasks, ranges = emit(steps)
+    logical = _round16(high)
+
+    class _T:
+        pass
+    t = _T()
+    t.N, t.n_paths, t.n_out, t.slots = 1 << LOG2_NP_MAX, 1, 1, slots
+    t.geo = type('G', (), dict(J_pad=LOG2_NP_MAX, pad_left=0))()
+    t.arena, t.tasks, t.steps, t.chan = np.zeros(4, np.float32), tasks, ranges, np.zeros(2, np.int32)
+    t.smem_complex, t.n_threads = logical + logical // 16, N_THREADS
+    return t
 
 
 def smem_capacity() -> int:

@@ -28,7 +28,7 @@ import torch.nn as nn
 from . import _lib
 from . import filterbank as fbk
 from .meta import compute_meta, output_size
-from .schedule import build_plan, build_plan_unaveraged
+from .schedule import LOG2_NP_MAX, build_plan, build_plan_unaveraged
 
 
 class _DevicePlan:
@@ -220,6 +220,8 @@ class Scattering1D(nn.Module):
         B = x2.shape[0]
         if not self.average:
             return self._scattering_unaveraged(x2, batch_shape)
+        if self.J_pad > LOG2_NP_MAX:
+            return self._scattering_large(x2, batch_shape)
         plan = self._plan_for(x.device.index if x.device.index is not None else torch.cuda.current_device())
         sched = self._sched[1]
         C, n_out = sched.n_paths, sched.n_out
@@ -242,6 +244,28 @@ class Scattering1D(nn.Module):
             j = tuple(int(v) for v in meta['j'][c][:len(key)])
             out.append({'coef': S[:, c, :].reshape(batch_shape + (n_out,)), 'j': j})
         return [out, out]
+
+    def _scattering_large(self, x2, batch_shape):
+        """Padded lengths 2^14 .. 2^17: the large-support level of tebscat/large.py -- the reference's
+        op order on global spectra, transforms as tile jobs of the interpreter.  Array output only."""
+        from .large import LargeDevicePlan, LargePlan
+        if self.out_type != 'array' or not self.vectorize:
+            raise NotImplementedError('the large-support level produces the array output only')
+        key = (self.J, self.N, self._Q1, self.T, self.max_order, int(self.oversampling))
+        if getattr(self, '_lsched', None) is None or self._lsched[0] != key:
+            self._lsched = (key, LargePlan(self.J, self.N, self._Q1, self.T, self.max_order, int(self.oversampling)))
+            self._lplans = {}
+        lp = self._lsched[1]
+        dev = x2.device
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        if index not in self._lplans:
+            self._lplans[index] = LargeDevicePlan(lp, index)
+        B = x2.shape[0]
+        S = torch.empty((B, lp.n_paths, lp.n_out), dtype=torch.float32, device=dev)
+        chunk = max(1, (1 << 28) >> self.J_pad)              # <= 2.7 GB of workspace per chunk
+        for b0 in range(0, B, chunk):
+            self._lplans[index].forward(x2[b0:b0 + chunk], S[b0:b0 + chunk])
+        return [S.reshape(batch_shape + (lp.n_paths, lp.n_out)), S.view(B, 1, lp.n_paths, lp.n_out)]
 
     def _scattering_unaveraged(self, x2, batch_shape):
         """average=False (core/scattering1d.py:293-294, :329-330, :366-367): the input itself, then the unpadded
