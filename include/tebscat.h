@@ -174,13 +174,16 @@ int tebscat_last_launch_count(void);
 typedef struct tebscat_large tebscat_large;
 int tebscat_large_create(int device, tebscat_large** out);
 void tebscat_large_destroy(tebscat_large* ctx);
-/* tile plan (tebscat.schedule.build_tile_plan) for in-place transforms of 2^log2_len <= 8192 samples; ownership moves */
-int tebscat_large_set_tile_plan(tebscat_large* ctx, int log2_len, int inverse, tebscat_plan* plan);
+/* tile plan (tebscat.schedule.build_tile_plan) for in-place transforms of 2^log2_len <= 8192 samples;
+ * kind: 0 forward, 1 inverse, 2 inverse -> modulus -> forward; ownership moves */
+int tebscat_large_set_tile_plan(tebscat_large* ctx, int log2_len, int kind, tebscat_plan* plan);
 /* pad (torch_backend.py:50-78) + real -> complex: x_dev [B, N] -> u_dev [B, 2^log2_Np] complex64 */
 int tebscat_large_pad_load(tebscat_large* ctx, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,
                            float* u_dev, void* stream);
 /* fft / ifft (torch_backend.py:106-128, unnormalised), in place, forward natural -> bit-reversed, inverse back */
 int tebscat_large_fft(tebscat_large* ctx, float* buf_dev, int64_t n_transforms, int log2_len, int inverse, void* stream);
+/* ifft -> modulus -> fft (core/scattering1d.py:312-318) in place on bit-reversed spectra, unnormalised */
+int tebscat_large_pair(tebscat_large* ctx, float* buf_dev, int64_t n_transforms, int log2_len, void* stream);
 /* cdgmm + subsample_fourier (kymatio/backend/torch_backend.py:147-219, torch_backend.py:18-48), times 2^-scale_exp */
 int tebscat_large_mulfold(tebscat_large* ctx, const float* src_dev, const float* filt_dev, float* dst_dev, int64_t B,
                           int log_src, int logk, uint32_t chunk_mask, int log_chunk, int scale_exp, void* stream);

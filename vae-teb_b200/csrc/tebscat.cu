@@ -1113,7 +1113,7 @@ constexpr int kLargeMaxLog2 = 17;
 struct tebscat_large {
     int device = 0;
     int n_sms = 0;
-    tebscat_plan* tile[kLog2TwMax + 1][2] = {};     // [log2 length][inverse]: owned
+    tebscat_plan* tile[kLog2TwMax + 1][3] = {};     // [log2 length][forward / inverse / inverse-modulus-forward]: owned
     float2* d_tw[kLargeMaxLog2 + 1] = {};           // W_L^m, m < L, for L = 2^14 .. 2^17
 };
 
@@ -1144,17 +1144,17 @@ extern "C" void tebscat_large_destroy(tebscat_large* g) {
     if (!g) return;
     cudaSetDevice(g->device);
     for (int n = 0; n <= kLog2TwMax; ++n)
-        for (int d = 0; d < 2; ++d) tebscat_plan_destroy(g->tile[n][d]);
+        for (int d = 0; d < 3; ++d) tebscat_plan_destroy(g->tile[n][d]);
     for (int n = 0; n <= kLargeMaxLog2; ++n) cudaFree(g->d_tw[n]);
     delete g;
 }
 
 /* Hand a tile plan (schedule.build_tile_plan) for transforms of 2^log2_len samples to the context (it takes ownership). */
-extern "C" int tebscat_large_set_tile_plan(tebscat_large* g, int log2_len, int inverse, tebscat_plan* plan) {
-    if (!g || !plan || log2_len < 1 || log2_len > kLog2TwMax) return fail(TEBSCAT_EINVAL, "bad tile plan");
+extern "C" int tebscat_large_set_tile_plan(tebscat_large* g, int log2_len, int kind, tebscat_plan* plan) {
+    if (!g || !plan || log2_len < 1 || log2_len > kLog2TwMax || kind < 0 || kind > 2) return fail(TEBSCAT_EINVAL, "bad tile plan");
     if (plan->device != g->device) return fail(TEBSCAT_EINVAL, "tile plan lives on another device");
-    tebscat_plan_destroy(g->tile[log2_len][inverse ? 1 : 0]);
-    g->tile[log2_len][inverse ? 1 : 0] = plan;
+    tebscat_plan_destroy(g->tile[log2_len][kind]);
+    g->tile[log2_len][kind] = plan;
     return TEBSCAT_OK;
 }
 
@@ -1232,8 +1232,8 @@ __global__ void g_radix_kernel(float2* __restrict__ buf, long long n_transforms,
     }
 }
 
-static int launch_tile_jobs(const tebscat_large* g, float2* buf, long long total_elems, int log2_len, int inverse, cudaStream_t st) {
-    const tebscat_plan* a = g->tile[log2_len][inverse ? 1 : 0];
+static int launch_tile_jobs(const tebscat_large* g, float2* buf, long long total_elems, int log2_len, int kind, cudaStream_t st) {
+    const tebscat_plan* a = g->tile[log2_len][kind];
     if (!a) return fail(TEBSCAT_EINVAL, "no tile plan for transforms of 2^%d samples", log2_len);
     KParams kp = a->kp;
     kp.gbuf = buf;
@@ -1276,6 +1276,79 @@ extern "C" int tebscat_large_fft(tebscat_large* g, float* buf_dev, int64_t n_tra
     radix();
     CU(cudaGetLastError());
     return TEBSCAT_OK;
+}
+
+// Middle of a long "iFFT -> modulus -> FFT" (core/scattering1d.py:312-318): last inverse radix pass, modulus and
+// first forward radix pass on the R values each thread owns -- one trip through memory instead of three.
+template <int LOGR>
+__global__ void g_radix_pair_kernel(float2* __restrict__ buf, long long n_transforms, int n, const float2* __restrict__ tw) {
+    constexpr int R = 1 << LOGR;
+    const int logm = n - LOGR;
+    const long long total = n_transforms << logm;
+    const long long L = (long long)1 << n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long s = e >> logm;
+        const int i0 = (int)(e - (s << logm));
+        float2* base = buf + s * L;
+        float2 v[R], tq[R];
+        float m[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            int rq = 0;
+#pragma unroll
+            for (int bb = 0; bb < LOGR; ++bb) rq |= ((q >> bb) & 1) << (LOGR - 1 - bb);
+            const float2 z = base[i0 + ((long long)rq << logm)];
+            tq[q] = __ldg(tw + (long long)i0 * q);
+            v[q] = make_float2(z.x * tq[q].x + z.y * tq[q].y, z.y * tq[q].x - z.x * tq[q].y);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            float ax = 0.f, ay = 0.f;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const float2 w = __ldg(tw + ((((long long)j * q) & (R - 1)) << logm));
+                ax += v[q].x * w.x + v[q].y * w.y;
+                ay += v[q].y * w.x - v[q].x * w.y;
+            }
+            m[j] = sqrtf(fmaf(ax, ax, ay * ay));
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            float ax = 0.f, ay = 0.f;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const float2 w = __ldg(tw + ((((long long)j * q) & (R - 1)) << logm));
+                ax += m[j] * w.x;
+                ay += m[j] * w.y;
+            }
+            int rq = 0;
+#pragma unroll
+            for (int bb = 0; bb < LOGR; ++bb) rq |= ((q >> bb) & 1) << (LOGR - 1 - bb);
+            base[i0 + ((long long)rq << logm)] = make_float2(ax * tq[q].x - ay * tq[q].y, ax * tq[q].y + ay * tq[q].x);
+        }
+    }
+}
+
+/* ifft -> modulus -> fft (core/scattering1d.py:312-318) in place on `n_transforms` bit-reversed spectra of 2^log2_len
+ * samples: the result is the bit-reversed spectrum of |ifft(.)| (unnormalised inverse). */
+extern "C" int tebscat_large_pair(tebscat_large* g, float* buf_dev, int64_t n_transforms, int log2_len, void* stream) {
+    if (!g || !buf_dev || n_transforms < 1 || log2_len < 1 || log2_len > kLargeMaxLog2) return fail(TEBSCAT_EINVAL, "bad transform request");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* buf = reinterpret_cast<float2*>(buf_dev);
+    const long long total = (long long)n_transforms << log2_len;
+    if (log2_len <= kLog2TwMax) return launch_tile_jobs(g, buf, total, log2_len, 2, st);
+    if (int rc = launch_tile_jobs(g, buf, total, kLog2TwMax, 1, st)) return rc;
+    const int blocks = g->n_sms * 8;
+    switch (log2_len - kLog2TwMax) {
+        case 1: g_radix_pair_kernel<1><<<blocks, 256, 0, st>>>(buf, n_transforms, log2_len, g->d_tw[log2_len]); break;
+        case 2: g_radix_pair_kernel<2><<<blocks, 256, 0, st>>>(buf, n_transforms, log2_len, g->d_tw[log2_len]); break;
+        case 3: g_radix_pair_kernel<3><<<blocks, 256, 0, st>>>(buf, n_transforms, log2_len, g->d_tw[log2_len]); break;
+        default: g_radix_pair_kernel<4><<<blocks, 256, 0, st>>>(buf, n_transforms, log2_len, g->d_tw[log2_len]); break;
+    }
+    CU(cudaGetLastError());
+    ++g_launches;
+    return launch_tile_jobs(g, buf, total, kLog2TwMax, 0, st);
 }
 
 extern "C" int tebscat_large_pad_load(tebscat_large* g, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,

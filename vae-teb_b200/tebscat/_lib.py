@@ -89,6 +89,8 @@ def load():
     lib.tebscat_large_pad_load.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.tebscat_large_fft.restype = ctypes.c_int
     lib.tebscat_large_fft.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, vp]
+    lib.tebscat_large_pair.restype = ctypes.c_int
+    lib.tebscat_large_pair.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, vp]
     lib.tebscat_large_mulfold.restype = ctypes.c_int
     lib.tebscat_large_mulfold.argtypes = [vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, u32, ctypes.c_int,
                                           ctypes.c_int, vp]

@@ -26,10 +26,11 @@ LOG2_MAX = 17
 class _TilePlanOwner:
     """Creates the device plan of a tile schedule and hands it to the large-support context."""
 
-    def __init__(self, ctx, n, inverse, device_index):
+    def __init__(self, ctx, n, kind, device_index):
         from .torch_frontend import _DevicePlan
-        dp = _DevicePlan(sch.build_tile_plan(n, inverse), device_index)
-        _lib.check(_lib.load().tebscat_large_set_tile_plan(ctx, n, 1 if inverse else 0, dp.handle))
+        plan = sch.build_tile_plan(n, kind == 1, kind='pair' if kind == 2 else None)
+        dp = _DevicePlan(plan, device_index)
+        _lib.check(_lib.load().tebscat_large_set_tile_plan(ctx, n, kind, dp.handle))
         dp.handle = None
 
 
@@ -106,8 +107,8 @@ class LargeDevicePlan:
         _lib.check(lib.tebscat_large_create(int(device_index), ctypes.byref(handle)))
         self.handle = handle
         for nlen in sorted(set(plan.tile_lengths)):
-            for inv in (False, True):
-                _TilePlanOwner(handle, nlen, inv, device_index)
+            for kind in (0, 1, 2):                   # forward, inverse, inverse -> modulus -> forward
+                _TilePlanOwner(handle, nlen, kind, device_index)
         self.arena = torch.from_numpy(np.ascontiguousarray(plan.arena, np.float32)).to(torch.device('cuda', device_index))
         self._ws = {}
 
@@ -147,6 +148,9 @@ class LargeDevicePlan:
         def fft(buf, log_len, inverse):
             _lib.check(lib.tebscat_large_fft(g, ctypes.c_void_p(buf.data_ptr()), B, log_len, 1 if inverse else 0, st))
 
+        def pair(buf, log_len):                               # ifft -> modulus -> fft, one trip per level
+            _lib.check(lib.tebscat_large_pair(g, ctypes.c_void_p(buf.data_ptr()), B, log_len, st))
+
         def leaf(src, spec, ch):                              # phi multiply + periodise -> iFFT -> unpad -> channel (:287-292)
             mulfold(src, spec, WL)
             fft(WL, lf, True)
@@ -159,14 +163,10 @@ class LargeDevicePlan:
         leaf(U0, p.s0, 0)
         for e in p.first:
             mulfold(U0, e['mul'], W1)                                                                 # :307-310
-            fft(W1, e['l1'], True)                                                                    # :312
-            _lib.check(lib.tebscat_large_modulus(g, ctypes.c_void_p(W1.data_ptr()), B << e['l1'], st))   # :315
-            fft(W1, e['l1'], False)                                                                   # :318
+            pair(W1, e['l1'])                                                                         # :312-318
             leaf(W1, e['leaf'], e['ch'])                                                              # :320-327
             for k in e['kids']:
                 mulfold(W1, k['mul'], W2)                                                             # :347-348
-                fft(W2, k['l2'], True)                                                                # :350
-                _lib.check(lib.tebscat_large_modulus(g, ctypes.c_void_p(W2.data_ptr()), B << k['l2'], st))   # :352
-                fft(W2, k['l2'], False)                                                               # :355
+                pair(W2, k['l2'])                                                                     # :350-355
                 leaf(W2, k['leaf'], k['ch'])                                                          # :358-364
         return out

@@ -1158,17 +1158,18 @@ def build_plan_unaveraged(J: int, N: int, Q, T: int, max_order: int = 2, oversam
 TILE_SLOTS = 8192                 # complex elements one tile job moves through shared memory
 
 
-def build_tile_plan(n: int, inverse: bool):
+def build_tile_plan(n: int, inverse, kind: Optional[str] = None):
     """Large-support level: in-place transforms of length 2^n (n <= 13) on a GLOBAL buffer, one
     job = one tile of 8192 elements = 8192 >> n transforms: LOADC -> chained passes -> STOREC.
-    Forward: natural -> bit-reversed; inverse: bit-reversed -> natural, unnormalised (like the cascade's own)."""
+    Forward: natural -> bit-reversed; inverse: bit-reversed -> natural, unnormalised (like the cascade's own);
+    kind='pair': inverse -> modulus -> forward in one job (core/scattering1d.py:312-318)."""
     if not 1 <= n <= LOG2_NP_MAX:
         raise ValueError('tile transforms have 2 .. 8192 samples')
     count = max(1, TILE_SLOTS >> n)
     slots = count << n
     buf = Buf(slots, 'tile')
     st = [[TaskSpec(OP_LOADC, -(-slots // 4), 900.0, 30.0, a=(buf, 0), b=slots)]]
-    st += _merge_local_passes(_fft_stages((buf, 0), n, count, 'inv' if inverse else 'fwd'))
+    st += _merge_local_passes(_fft_stages((buf, 0), n, count, kind or ('inv' if inverse else 'fwd')))
     st.append([TaskSpec(OP_STOREC, slots, 300.0, 12.0, a=(buf, 0), b=slots)])
     steps, high, chan, sched = schedule_chains([Chain('tile', st, owns=[buf], depth=0)], smem_capacity(), 1, 0, 1)
     tasks, ranges = emit(steps)
