@@ -175,8 +175,9 @@ typedef struct tebscat_large tebscat_large;
 int tebscat_large_create(int device, tebscat_large** out);
 void tebscat_large_destroy(tebscat_large* ctx);
 /* tile plan (tebscat.schedule.build_tile_plan) for in-place transforms of 2^log2_len <= 8192 samples;
- * kind: 0 forward, 1 inverse, 2 inverse -> modulus -> forward; ownership moves */
-int tebscat_large_set_tile_plan(tebscat_large* ctx, int log2_len, int kind, tebscat_plan* plan);
+ * kind: 0 forward, 1 inverse, 2 inverse -> modulus -> forward; one job covers slots_per_job consecutive complex
+ * elements (a multiple of the length); ownership moves */
+int tebscat_large_set_tile_plan(tebscat_large* ctx, int log2_len, int kind, int slots_per_job, tebscat_plan* plan);
 /* pad (torch_backend.py:50-78) + real -> complex: x_dev [B, N] -> u_dev [B, 2^log2_Np] complex64 */
 int tebscat_large_pad_load(tebscat_large* ctx, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,
                            float* u_dev, void* stream);

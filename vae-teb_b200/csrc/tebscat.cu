@@ -1113,7 +1113,10 @@ constexpr int kLargeMaxLog2 = 17;
 struct tebscat_large {
     int device = 0;
     int n_sms = 0;
-    tebscat_plan* tile[kLog2TwMax + 1][3] = {};     // [log2 length][forward / inverse / inverse-modulus-forward]: owned
+    // [log2 length][forward / inverse / inverse-modulus-forward][small / large job]: owned.  Large jobs (three
+    // 8192-blocks) amortise the per-step latency of the interpreter, small ones keep every SM busy on short buffers.
+    tebscat_plan* tile[kLog2TwMax + 1][3][2] = {};
+    int tile_slots[kLog2TwMax + 1][3][2] = {};      // complex elements one job of the plan covers
     float2* d_tw[kLargeMaxLog2 + 1] = {};           // W_L^m, m < L, for L = 2^14 .. 2^17
 };
 
@@ -1144,17 +1147,22 @@ extern "C" void tebscat_large_destroy(tebscat_large* g) {
     if (!g) return;
     cudaSetDevice(g->device);
     for (int n = 0; n <= kLog2TwMax; ++n)
-        for (int d = 0; d < 3; ++d) tebscat_plan_destroy(g->tile[n][d]);
+        for (int d = 0; d < 3; ++d)
+            for (int z = 0; z < 2; ++z) tebscat_plan_destroy(g->tile[n][d][z]);
     for (int n = 0; n <= kLargeMaxLog2; ++n) cudaFree(g->d_tw[n]);
     delete g;
 }
 
 /* Hand a tile plan (schedule.build_tile_plan) for transforms of 2^log2_len samples to the context (it takes ownership). */
-extern "C" int tebscat_large_set_tile_plan(tebscat_large* g, int log2_len, int kind, tebscat_plan* plan) {
-    if (!g || !plan || log2_len < 1 || log2_len > kLog2TwMax || kind < 0 || kind > 2) return fail(TEBSCAT_EINVAL, "bad tile plan");
+extern "C" int tebscat_large_set_tile_plan(tebscat_large* g, int log2_len, int kind, int slots, tebscat_plan* plan) {
+    if (!g || !plan || log2_len < 1 || log2_len > kLog2TwMax || kind < 0 || kind > 2 || slots < (1 << log2_len) ||
+        (slots & ((1 << log2_len) - 1)))
+        return fail(TEBSCAT_EINVAL, "bad tile plan");
     if (plan->device != g->device) return fail(TEBSCAT_EINVAL, "tile plan lives on another device");
-    tebscat_plan_destroy(g->tile[log2_len][kind]);
-    g->tile[log2_len][kind] = plan;
+    const int z = slots > 8192 ? 1 : 0;
+    tebscat_plan_destroy(g->tile[log2_len][kind][z]);
+    g->tile[log2_len][kind][z] = plan;
+    g->tile_slots[log2_len][kind][z] = slots;
     return TEBSCAT_OK;
 }
 
@@ -1233,13 +1241,16 @@ __global__ void g_radix_kernel(float2* __restrict__ buf, long long n_transforms,
 }
 
 static int launch_tile_jobs(const tebscat_large* g, float2* buf, long long total_elems, int log2_len, int kind, cudaStream_t st) {
-    const tebscat_plan* a = g->tile[log2_len][kind];
+    // large jobs only when there are enough of them for two waves over the SMs
+    int z = (g->tile[log2_len][kind][1] && total_elems / g->tile_slots[log2_len][kind][1] >= 2LL * g->n_sms) ? 1 : 0;
+    if (!g->tile[log2_len][kind][z]) z ^= 1;
+    const tebscat_plan* a = g->tile[log2_len][kind][z];
     if (!a) return fail(TEBSCAT_EINVAL, "no tile plan for transforms of 2^%d samples", log2_len);
     KParams kp = a->kp;
     kp.gbuf = buf;
     kp.g_total = total_elems;
-    kp.g_slots = 8192;
-    const long long jobs = (total_elems + 8191) / 8192;
+    kp.g_slots = g->tile_slots[log2_len][kind][z];
+    const long long jobs = (total_elems + kp.g_slots - 1) / kp.g_slots;
     const int grid = (int)(jobs < (long long)a->n_sms ? jobs : (long long)a->n_sms);
     scat1d_kernel<false><<<grid, a->desc.n_threads, a->smem_bytes, st>>>(kp, nullptr, nullptr, jobs);
     CU(cudaGetLastError());

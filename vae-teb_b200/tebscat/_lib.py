@@ -84,7 +84,7 @@ def load():
     lib.tebscat_large_destroy.restype = None
     lib.tebscat_large_destroy.argtypes = [vp]
     lib.tebscat_large_set_tile_plan.restype = ctypes.c_int
-    lib.tebscat_large_set_tile_plan.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.tebscat_large_set_tile_plan.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.tebscat_large_pad_load.restype = ctypes.c_int
     lib.tebscat_large_pad_load.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.tebscat_large_fft.restype = ctypes.c_int

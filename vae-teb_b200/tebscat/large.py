@@ -26,11 +26,11 @@ LOG2_MAX = 17
 class _TilePlanOwner:
     """Creates the device plan of a tile schedule and hands it to the large-support context."""
 
-    def __init__(self, ctx, n, kind, device_index):
+    def __init__(self, ctx, n, kind, device_index, tile_slots):
         from .torch_frontend import _DevicePlan
-        plan = sch.build_tile_plan(n, kind == 1, kind='pair' if kind == 2 else None)
+        plan = sch.build_tile_plan(n, kind == 1, kind='pair' if kind == 2 else None, tile_slots=tile_slots)
         dp = _DevicePlan(plan, device_index)
-        _lib.check(_lib.load().tebscat_large_set_tile_plan(ctx, n, kind, dp.handle))
+        _lib.check(_lib.load().tebscat_large_set_tile_plan(ctx, n, kind, plan.slots, dp.handle))
         dp.handle = None
 
 
@@ -108,7 +108,8 @@ class LargeDevicePlan:
         self.handle = handle
         for nlen in sorted(set(plan.tile_lengths)):
             for kind in (0, 1, 2):                   # forward, inverse, inverse -> modulus -> forward
-                _TilePlanOwner(handle, nlen, kind, device_index)
+                for slots in sch.TILE_SLOTS:
+                    _TilePlanOwner(handle, nlen, kind, device_index, slots)
         self.arena = torch.from_numpy(np.ascontiguousarray(plan.arena, np.float32)).to(torch.device('cuda', device_index))
         self._ws = {}
 

@@ -1155,17 +1155,19 @@ def build_plan_unaveraged(J: int, N: int, Q, T: int, max_order: int = 2, oversam
     return u
 
 
-TILE_SLOTS = 8192                 # complex elements one tile job moves through shared memory
+TILE_SLOTS = (8192, 3 * 8192)     # complex elements one tile job moves through shared memory: small jobs keep every
+                                  # SM busy on short buffers; with three 8192-blocks every task has three trips per
+                                  # thread, which amortises the per-step latency of the interpreter
 
 
-def build_tile_plan(n: int, inverse, kind: Optional[str] = None):
+def build_tile_plan(n: int, inverse, kind: Optional[str] = None, tile_slots: int = TILE_SLOTS[0]):
     """Large-support level: in-place transforms of length 2^n (n <= 13) on a GLOBAL buffer, one
     job = one tile of 8192 elements = 8192 >> n transforms: LOADC -> chained passes -> STOREC.
     Forward: natural -> bit-reversed; inverse: bit-reversed -> natural, unnormalised (like the cascade's own);
     kind='pair': inverse -> modulus -> forward in one job (core/scattering1d.py:312-318)."""
     if not 1 <= n <= LOG2_NP_MAX:
         raise ValueError('tile transforms have 2 .. 8192 samples')
-    count = max(1, TILE_SLOTS >> n)
+    count = max(1, tile_slots >> n)
     slots = count << n
     buf = Buf(slots, 'tile')
     st = [[TaskSpec(OP_LOADC, -(-slots // 4), 900.0, 30.0, a=(buf, 0), b=slots)]]
