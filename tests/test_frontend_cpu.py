@@ -124,10 +124,29 @@ def test_constructor_errors_and_options():
     assert 'GPU' in ve.value.args[0]
 
 
-def test_large_support_is_refused_loudly():
+def test_large_support_goes_to_the_large_level():
+    """Padded lengths above 2^13 do not fit the single-CTA schedule (which must say so) and are served by the
+    large-support level (tebscat/large.py): same channel order as meta(), same output geometry."""
+    from tebscat.large import LargePlan
     S = Scattering1D(10, 2 ** 16, 8)
+    assert S.J_pad == 17
     with pytest.raises(NotImplementedError):
         S._schedule()
+    lp = LargePlan(8, 2 ** 13, 8, 256)
+    S8 = Scattering1D(8, 2 ** 13, 8, T=256)
+    assert lp.geo.J_pad == 14 and lp.n_paths == S8.output_size() == len(S8.meta()['key'])
+    assert [tuple(k) for k in S8.meta()['key']] == lp.keys
+    assert lp.n_out == 2 ** 13 // 256 and lp.lf == 14 - 8
+    assert [e['ch'] for e in lp.first] == list(range(1, len(lp.first) + 1))
+    chans = [0] + [e['ch'] for e in lp.first] + [k['ch'] for e in lp.first for k in e['kids']]
+    assert sorted(chans) == list(range(lp.n_paths))                       # every channel produced exactly once
+    for e in lp.first:
+        off, log_src, logk, mask, logcw, sexp = e['mul']
+        assert log_src == 14 and log_src - logk == e['l1'] and sexp == log_src
+        for k in e['kids']:
+            assert k['mul'][1] == e['l1'] and k['mul'][1] - k['mul'][2] == k['l2']
+    with pytest.raises(NotImplementedError):
+        LargePlan(12, 2 ** 18, 8, 4096)
 
 
 def test_c_abi_exports_every_declared_symbol():
