@@ -56,7 +56,10 @@ typedef struct tebscat_plan_desc {
     int32_t smem_complex;  /* complex64 slots of shared memory the schedule addresses  */
     int32_t n_tasks;       /* entries of `tasks` (12 x int32 each)                     */
     int32_t n_steps;       /* entries of `steps` (2 x int32 each: [task_begin, task_end)) */
-    int32_t reserved[6];
+    int32_t border_mode;   /* padding rule of the plan's loads: 0 reflect (the scattering transform, always),
+                              1 constant (zeros), 2 circular -- KymatioPhaseScattering1D(border_mode=...),
+                              hdf5_dataset/kymatio_phase_scattering.py:162-173                          */
+    int32_t reserved[5];
 } tebscat_plan_desc;
 
 typedef struct tebscat_plan tebscat_plan;

@@ -111,12 +111,41 @@ def phase_fixture(name, B):
     print(name, 'phase', within.shape, cross.shape, 'masks', pm.sum(), cm.sum())
 
 
+def phase_option_fixture(tag, name, B, **opts):
+    """Non-default options of the phase module: border_mode 'constant' / 'circular'
+    (:162-173) and oversampling (target length of the scattering output, :445)."""
+    J, Q, T, N, max_order, _ = CONFIGS[name][:6]
+    m = kps.KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cpu'),
+                                     max_order=max_order, **opts)
+    x = torch.cat([ctg_batch(B, N, seed=177), randn_batch(B, N, 2, seed=178)], 0)
+    with torch.no_grad():
+        rw = m(x, compute_phase=True, phase_channels=[0])
+        rc = m(x, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1])
+    np.savez_compressed(
+        os.path.join(OUT, 'phase_%s.npz' % tag),
+        J=J, Q=Q, T=T, N=N, max_order=max_order, x=x.numpy(),
+        border_mode=opts.get('border_mode', 'reflect'), oversampling=opts.get('oversampling', 0),
+        scattering=rw['scattering'].numpy(), within=rw['phase_corr'].numpy(), cross=rc['cross_phase_corr'].numpy(),
+    )
+    print(tag, 'phase', rw['phase_corr'].shape, rc['cross_phase_corr'].shape)
+
+
+def phase_option_fixtures():
+    phase_option_fixture('S_constant', 'S', 1, border_mode='constant')
+    phase_option_fixture('S_circular', 'S', 1, border_mode='circular')
+    phase_option_fixture('S_over1', 'S', 1, oversampling=1)
+
+
 if __name__ == '__main__':
+    if sys.argv[1:] == ['phase-options']:
+        phase_option_fixtures()
+        sys.exit(0)
     for n in CONFIGS:
         scat_fixture(n)
     phase_fixture('H', 1)
     phase_fixture('P', 1)
     phase_fixture('S', 2)
+    phase_option_fixtures()
     kat = np.load(os.path.join(REF, 'kymatio/tests/scattering1d/test_data_1d.npz'))
     np.savez_compressed(os.path.join(OUT, 'kat_test_data_1d.npz'), **{k: kat[k] for k in kat})
     print('done')

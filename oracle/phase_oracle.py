@@ -30,10 +30,23 @@ from . import filters_oracle as fo
 from .scattering1d_oracle import reflect_pad
 
 
+def pad_signal(x, pad_left, pad_right, border_mode='reflect'):
+    """:162-173 -- _pad_signal: 'reflect' (single fold, pad < N), 'constant' (zeros) or 'circular'."""
+    if border_mode == 'reflect':
+        return reflect_pad(x, pad_left, pad_right)
+    widths = [(0, 0)] * (x.ndim - 1) + [(pad_left, pad_right)]
+    if border_mode == 'constant':
+        return np.pad(x, widths, mode='constant')
+    if border_mode == 'circular':
+        return np.pad(x, widths, mode='wrap')
+    raise ValueError(f"Unsupported border_mode: {border_mode}")
+
+
 class PhaseOracle:
-    def __init__(self, J, Q, T, N, n_out):
+    def __init__(self, J, Q, T, N, n_out, border_mode='reflect'):
         """n_out: temporal length of the scattering output (target_length, :445)."""
         self.J, self.Q, self.T, self.N, self.n_out = J, Q, T, N, n_out
+        self.border_mode = border_mode
         self.geo = fo.geometry(N, J, Q, T, clamp=True)                      # :100-113
         bank = fo.filter_factory(self.geo['J_pad'], J, Q, T)                 # :117-120
         # complex64 cast keeps the fp32 value of the real float64 filters  (:123-125)
@@ -54,7 +67,7 @@ class PhaseOracle:
     def analytic(self, x):
         """x: (B, N) -> z (B, F, N) complex128."""
         g = self.geo
-        xf = scipy.fft.fft(reflect_pad(np.asarray(x, np.float64), g['pad_left'], g['pad_right']), axis=-1)
+        xf = scipy.fft.fft(pad_signal(np.asarray(x, np.float64), g['pad_left'], g['pad_right'], self.border_mode), axis=-1)
         z = scipy.fft.ifft(xf[:, None, :] * self.psi1[None], axis=-1)
         return z[..., g['ind_start'][0]:g['ind_end'][0]]
 
@@ -63,7 +76,7 @@ class PhaseOracle:
         g = self.geo
         Np = 2 ** g['J_pad']
         dec = self.N // self.n_out if (self.n_out > 0 and self.N > self.n_out) else 1   # :287-291
-        cf = scipy.fft.fft(reflect_pad(c, g['pad_left'], g['pad_right']), axis=-1) * self.phi
+        cf = scipy.fft.fft(pad_signal(c, g['pad_left'], g['pad_right'], self.border_mode), axis=-1) * self.phi
         if dec > 1:
             y = scipy.fft.ifft(cf[..., :max(Np // dec, 1)], axis=-1)          # :242-252
             s = g['pad_left'] // dec                                          # :258

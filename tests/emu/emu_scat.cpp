@@ -19,7 +19,7 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
                                   const int32_t* chan, const float* x, long long B, float* out,
                                   float* zc, float* zp, int z_mode,
                                   const float* ep_mean, const float* ep_std, const unsigned char* ep_mode,
-                                  float ep_log_eps, int ep_trim, int ep_time_major) {
+                                  float ep_log_eps, int ep_trim, int ep_time_major, int border) {
     std::vector<float2> S((size_t)smem_complex);
     std::vector<float2> tw(kTwAP + kTwBP, make_float2(0.f, 0.f));
     const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
@@ -51,7 +51,7 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
         c.zc = reinterpret_cast<float2*>(zc) + b * (long long)n_paths * n_out;
         c.zp = reinterpret_cast<float2*>(zp) + b * (long long)n_paths * n_out;
         c.z_mode = z_mode;
-        c.N = N; c.pad_left = pad_left; c.log2_Np = log2_Np; c.n_out = n_out;
+        c.N = N; c.pad_left = pad_left; c.log2_Np = log2_Np; c.n_out = n_out; c.border = border;
         for (int s = 0; s < n_steps; ++s) {
             for (int ti = steps[2 * s]; ti < steps[2 * s + 1]; ++ti) {
                 Task t;

@@ -184,3 +184,51 @@ def test_transform_and_dense_forms_of_stage_b_agree(monkeypatch):
         # rows whose energy is rounding noise of a strong product are excluded like in the oracle comparison
         strong = np.linalg.norm(a, axis=-1) > 1e-4 * np.linalg.norm(a, axis=-1).max()
         assert err[strong].max() < 2e-5, err[strong].max()
+
+
+@pytest.mark.parametrize('tag', ['S_constant', 'S_circular', 'S_over1'])
+@pytest.mark.parametrize('form', ['0', '1'])
+def test_phase_options_match_oracle_and_reference(tag, form, monkeypatch):
+    """border_mode 'constant' / 'circular' (kymatio_phase_scattering.py:162-173) and oversampling (:445), in the
+    dense form of stage B and -- where the decimation factor is a power of two -- the transform form."""
+    from tebscat import KymatioPhaseScattering1D
+    d = np.load(os.path.join(GOLDEN, 'phase_%s.npz' % tag))
+    J, Q, T, N, mo = CFG['S']
+    border, over = str(d['border_mode']), int(d['oversampling'])
+    monkeypatch.setenv('TEBSCAT_PHASE_FFT', form)
+    m = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), max_order=mo,
+                                 border_mode=border, oversampling=over)
+    if form == '1' and m._plan.pair_plan is None:
+        pytest.skip('decimation factor %d is not a power of two' % m._plan.dec)
+    assert m._dev_plan(0).uses_fft_pairs == (form == '1')
+    x = torch.from_numpy(d['x']).cuda()
+    o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1], border_mode=border)
+    rw = m(x, compute_phase=True, phase_channels=[0])
+    rc = m(x, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1])
+    assert rel_l2(rw['scattering'].cpu().numpy(), d['scattering']) < 2e-6
+    xin = d['x']
+    for ours, ref, mode in ((rw['phase_corr'], d['within'], 'within'), (rc['cross_phase_corr'], d['cross'], 'cross')):
+        ours = ours.cpu().numpy().astype(np.float64)
+        assert ours.shape == ref.shape
+        xm = xin[:, 0] if mode == 'within' else xin
+        check(ours, o.align_branches(xm, ours, mode=mode), tag + '/' + mode)
+        diff = (ours - o.align_branches(xm, ours, mode=mode)) - (ref - o.align_branches(xm, ref, mode=mode))
+        assert np.linalg.norm(diff) / np.linalg.norm(ref) < 1e-4, mode
+
+
+@pytest.mark.parametrize('border', ['constant', 'circular'])
+def test_border_modes_in_transform_form(border, monkeypatch):
+    """LOADPAIR's zero / circular padding on the device (oversampling = 1 gives the S config a decimation of 8)."""
+    from tebscat import KymatioPhaseScattering1D
+    from tebscat.synth import ctg_batch
+    J, Q, T, N, mo = CFG['S']
+    monkeypatch.setenv('TEBSCAT_PHASE_FFT', '1')
+    m = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), max_order=mo,
+                                 border_mode=border, oversampling=1)
+    assert m._dev_plan(0).uses_fft_pairs
+    x = ctg_batch(3, N, seed=5)
+    ours = m(x.cuda(), compute_phase=False, compute_cross_phase=True)['cross_phase_corr'].cpu().numpy().astype(np.float64)
+    o = PhaseOracle(J, Q, T, N, 125, border_mode=border)
+    check(ours, o.align_branches(x.numpy(), ours, mode='cross'), border)
+    other = PhaseOracle(J, Q, T, N, 125)(x.numpy(), mode='cross')
+    assert rel_l2(ours, other) > 1e-3                                     # and it is not the reflect result

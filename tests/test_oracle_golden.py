@@ -110,3 +110,20 @@ def test_phase_vs_reference(golden_dir, name):
         # fp32 reference vs fp64 oracle: p*theta is rounded in fp32 with p up to ~100
         assert overall < 5e-5, (mode, overall, rel_l2(plain, ref))
         assert np.median(per_path) < 5e-5 and per_path.max() < 2e-3, (mode, per_path.max())
+
+
+@pytest.mark.parametrize('tag', ['S_constant', 'S_circular', 'S_over1'])
+def test_phase_options_vs_reference(golden_dir, tag):
+    """border_mode 'constant' / 'circular' (kymatio_phase_scattering.py:162-173) and oversampling (the
+    target length follows the scattering output, :445) against outputs of the live reference."""
+    d = load(golden_dir, 'phase_%s.npz' % tag)
+    J, Q, T, N = int(d['J']), int(d['Q']), int(d['T']), int(d['N'])
+    o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1], border_mode=str(d['border_mode']))
+    x = d['x']
+    for mode, ref in (('within', d['within']), ('cross', d['cross'])):
+        xin = x[:, 0] if mode == 'within' else x
+        assert o(xin, mode=mode).shape == ref.shape
+        aligned = o.align_branches(xin, ref, mode=mode)
+        per_path = rel_l2(aligned, ref, axis=-1)
+        assert rel_l2(aligned, ref) < 5e-5, (mode, rel_l2(aligned, ref))
+        assert np.median(per_path) < 5e-5 and per_path.max() < 2e-3, (mode, per_path.max())

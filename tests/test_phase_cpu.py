@@ -89,3 +89,50 @@ def test_pair_stage_transform_form_matches_oracle(name):
     ref = o._smooth(c).real
     err = np.linalg.norm(out - ref, axis=-1) / np.linalg.norm(ref, axis=-1)
     assert err.max() < 1e-5, err
+
+
+# ---- non-default options: border_mode (:162-173) and a power-of-two decimation on the ragged config ------------
+@pytest.mark.parametrize('border', ['constant', 'circular'])
+def test_smoothing_operator_border_modes(border):
+    J, Q, T, N = CFG['S']
+    p = PhasePlan(J, Q, T, N, 66, border_mode=border)
+    o = PhaseOracle(J, Q, T, N, 66, border_mode=border)
+    rng = np.random.RandomState(3)
+    c = rng.randn(4, N) + 1j * rng.randn(4, N)
+    G = p.G[:, :p.n_out, 0].astype(np.float64) + 1j * p.G[:, :p.n_out, 1]
+    ref = o._smooth(c)
+    assert np.abs(c @ G - ref).max() < 1e-6 * np.abs(ref).max()
+
+
+@pytest.mark.skipif(not emu_available(), reason='host emulator not built')
+@pytest.mark.parametrize('border', ['constant', 'circular'])
+def test_stage_a_and_pair_stage_border_modes_emulated(border):
+    """LOAD and LOADPAIR with zero / circular padding through the host emulator, against the oracle.
+    Target length 125 (oversampling = 1 of the S config) gives the power-of-two decimation 8 the
+    transform form of stage B needs."""
+    J, Q, T, N = CFG['S']
+    p = PhasePlan(J, Q, T, N, 125, border_mode=border)
+    o = PhaseOracle(J, Q, T, N, 125, border_mode=border)
+    assert p.dec == 8 and p.pair_plan is not None and p.stage_a.border == p.pair_plan.border != 0
+    x = np.random.RandomState(5).randn(2, N).astype(np.float32) + 3.0      # an offset makes the padding rule visible
+    z, zp = emu_forward(p.stage_a, x, stage_a=True)
+    ref = o.analytic(x)
+    err = np.linalg.norm(z - ref, axis=-1) / np.linalg.norm(ref, axis=-1)
+    assert not np.isnan(z).any() and err.max() < 1e-5, err.max()
+    # and it is not the reflect result
+    assert np.abs(z - PhaseOracle(J, Q, T, N, 125).analytic(x)).max() > 1e-3
+
+    rng = np.random.RandomState(9)
+    rows = 3
+    zi = (rng.randn(rows, N) + 1j * rng.randn(rows, N)).astype(np.complex64)
+    zj = (rng.randn(rows, N) + 1j * rng.randn(rows, N)).astype(np.complex64)
+    pw = np.array([1.0, 1.5, 3.25], np.float32)
+    zpol = np.stack([np.abs(zi), np.angle(zi)], -1).astype(np.float32)
+    zc = np.stack([zj.real, zj.imag], -1).astype(np.float32)
+    out = emu_pair_stage(p.pair_plan, zpol, zc, pw)
+    theta = zpol[..., 1].astype(np.float32) * pw[:, None]
+    c = zpol[..., 0].astype(np.float64) * np.exp(1j * theta.astype(np.float64)) * np.conj(zj.astype(np.complex128))
+    ref = o._smooth(c).real
+    assert out.shape == ref.shape and not np.isnan(out).any()
+    err = np.linalg.norm(out - ref, axis=-1) / np.linalg.norm(ref, axis=-1)
+    assert err.max() < 1e-5, err

@@ -106,8 +106,12 @@ struct SignalCtx {
     // large-support level (OP_LOADC / OP_STOREC): this job's tile of a global complex buffer
     float2* gbuf;
     int32_t g_valid;         // complex elements of the tile that exist (the last job may be partial)
+    // padding rule of OP_LOAD / OP_LOADPAIR: the scattering transform always reflects (torch_backend.py:50-78);
+    // the phase module's _pad_signal (kymatio_phase_scattering.py:162-173) also offers 'constant' and 'circular'
+    int32_t border;
 };
 enum : int32_t { EP_NONE = 0, EP_LOG = 1, EP_ASINH = 2 };
+enum : int32_t { BORDER_REFLECT = 0, BORDER_CONSTANT = 1, BORDER_CIRCULAR = 2 };
 
 constexpr int kLog2TwMax = 13;                 // twiddle tables cover lengths up to 8192
 constexpr int kTwA = 1 << (kLog2TwMax - 7);    // coarse table entries: W^(128 a)
@@ -797,7 +801,8 @@ TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task&
     }
 }
 
-// reflect padding of torch_backend.py:50-78 (F.pad(..., mode='reflect'); pad < N)
+// reflect padding of torch_backend.py:50-78 (F.pad(..., mode='reflect'); pad < N); for the phase module's
+// stage A also F.pad(..., 'constant', 0) and F.pad(..., 'circular') (kymatio_phase_scattering.py:162-173)
 TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
     const int Np = 1 << c.log2_Np;
     for (int i0 = lt; i0 < Np; i0 += 8 * t.nt) {
@@ -805,9 +810,17 @@ TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
         TEB_UNROLL for (int j = 0; j < 8; ++j) {
             const int i = i0 + j * t.nt;
             int r = i - c.pad_left;
-            if (r < 0) r = -r;
-            if (r >= c.N) r = 2 * (c.N - 1) - r;
-            v[j] = (i < Np) ? TEB_LDG(c.x + r) : 0.f;
+            bool inside = i < Np;
+            if (c.border == BORDER_REFLECT) {
+                if (r < 0) r = -r;
+                if (r >= c.N) r = 2 * (c.N - 1) - r;
+            } else if (c.border == BORDER_CIRCULAR) {
+                if (r < 0) r += c.N;
+                if (r >= c.N) r -= c.N;
+            } else {
+                inside = inside && r >= 0 && r < c.N;
+            }
+            v[j] = inside ? TEB_LDG(c.x + r) : 0.f;
         }
         TEB_UNROLL for (int j = 0; j < 8; ++j) {
             const int i = i0 + j * t.nt;
@@ -854,9 +867,19 @@ TEB_D void loadpair_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
             if (tt >= c.N) continue;
             const float2 v = accelerated_product(a[j], b[j], pw);
             S[swz(t.a + c.pad_left + tt)] = v;
-            if (tt >= 1 && tt <= c.pad_left) S[swz(t.a + c.pad_left - tt)] = v;                       // left mirror
-            if (tt <= c.N - 2 && tt >= c.N - 1 - pad_right) S[swz(t.a + c.pad_left + 2 * (c.N - 1) - tt)] = v;   // right mirror
+            if (c.border == BORDER_REFLECT) {
+                if (tt >= 1 && tt <= c.pad_left) S[swz(t.a + c.pad_left - tt)] = v;                       // left mirror
+                if (tt <= c.N - 2 && tt >= c.N - 1 - pad_right) S[swz(t.a + c.pad_left + 2 * (c.N - 1) - tt)] = v;   // right mirror
+            } else if (c.border == BORDER_CIRCULAR) {                       // padded[i] = c[(i - pad_left) mod N], pad <= N
+                if (tt >= c.N - c.pad_left) S[swz(t.a + c.pad_left + tt - c.N)] = v;
+                if (tt < pad_right) S[swz(t.a + c.pad_left + tt + c.N)] = v;
+            }
         }
+    }
+    if (c.border == BORDER_CONSTANT) {                                      // zeros on both sides
+        const float2 z = make_float2(0.f, 0.f);
+        for (int i = lt; i < c.pad_left; i += t.nt) S[swz(t.a + i)] = z;
+        for (int i = lt; i < pad_right; i += t.nt) S[swz(t.a + c.pad_left + c.N + i)] = z;
     }
 }
 

@@ -55,6 +55,7 @@ struct KParams {
     int32_t n_steps;
     int32_t smem_complex;
     int32_t N, pad_left, log2_Np, n_paths, n_out;
+    int32_t border;          // BORDER_* of OP_LOAD / OP_LOADPAIR
     // output epilogue (null mean = none)
     const float* ep_mean;
     const float* ep_std;
@@ -158,6 +159,7 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
             c.N = p.N;
             c.pad_left = p.pad_left;
             c.log2_Np = p.log2_Np;
+            c.border = p.border;
             c.n_out = p.n_out;
         }
         __syncthreads();             // (the last step of the previous signal ended in a barrier too)
@@ -461,6 +463,7 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     k.N = desc->N;
     k.pad_left = desc->pad_left;
     k.log2_Np = desc->log2_Np;
+    k.border = desc->border_mode;
     k.n_paths = desc->n_paths;
     k.n_out = desc->n_out;
     k.ep_mean = nullptr;

@@ -19,7 +19,7 @@ class PlanDesc(ctypes.Structure):
                 ('pad_left', ctypes.c_int32), ('n_paths', ctypes.c_int32), ('n_out', ctypes.c_int32),
                 ('n_threads', ctypes.c_int32), ('smem_complex', ctypes.c_int32),
                 ('n_tasks', ctypes.c_int32), ('n_steps', ctypes.c_int32),
-                ('reserved', ctypes.c_int32 * 6)]
+                ('border_mode', ctypes.c_int32), ('reserved', ctypes.c_int32 * 5)]
 
 
 class PhaseDesc(ctypes.Structure):

@@ -26,10 +26,13 @@ from .torch_frontend import Scattering1D, _DevicePlan
 COL_TILE = 80            # kPC of the pair kernel
 
 
-def smoothing_operator(phi0_f32, N, J_pad, pad_left, dec):
+BORDER_MODES = {'reflect': 0, 'constant': 1, 'circular': 2}        # _pad_signal (:162-173)
+
+
+def smoothing_operator(phi0_f32, N, J_pad, pad_left, dec, border_mode='reflect'):
     """The linear map of ``_apply_phi_filter`` (:233-273) with decimation, as a dense matrix.
 
-    c (N complex) -> reflect-pad (Np) -> FFT -> * phi -> bins [0, Np//dec) -> iFFT of that
+    c (N complex) -> pad (Np; reflect, zeros or circular) -> FFT -> * phi -> bins [0, Np//dec) -> iFFT of that
     length -> samples [pad_left//dec, pad_left//dec + N//dec).  Returns G (N, n_out) complex128
     with out = c @ G."""
     Np = 1 << J_pad
@@ -42,13 +45,20 @@ def smoothing_operator(phi0_f32, N, J_pad, pad_left, dec):
     E1 = (phi / M)[:, None] * np.exp(2j * np.pi * np.outer(k, n_abs) / M)    # (M, n_out)
     G = np.zeros((N, n_abs.size), np.complex128)
     tp = np.arange(Np)
-    src = tp - pad_left                                                      # reflect (single fold: pad < N)
-    src = np.where(src < 0, -src, src)
-    src = np.where(src >= N, 2 * (N - 1) - src, src)
+    src = tp - pad_left
+    live = np.ones(Np, bool)
+    if border_mode == 'reflect':                                             # single fold: pad < N
+        src = np.where(src < 0, -src, src)
+        src = np.where(src >= N, 2 * (N - 1) - src, src)
+    elif border_mode == 'circular':                                          # pad <= N
+        src = np.mod(src, N)
+    else:                                                                    # 'constant': padded samples are zero
+        live = (src >= 0) & (src < N)
     for lo in range(0, Np, 1024):                                            # bounded temporaries
         hi = min(lo + 1024, Np)
-        E2 = np.exp(-2j * np.pi * np.outer(tp[lo:hi], k) / Np)               # (chunk, M)
-        np.add.at(G, src[lo:hi], E2 @ E1)
+        sel = live[lo:hi]
+        E2 = np.exp(-2j * np.pi * np.outer(tp[lo:hi][sel], k) / Np)          # (chunk, M)
+        np.add.at(G, src[lo:hi][sel], E2 @ E1)
     return G
 
 
@@ -58,9 +68,10 @@ PAIR_FFT_MIN_OUT = 160      # outputs per row from which the transform form of s
 class PhasePlan:
     """Host description of the phase path of one (J, Q, T, N) configuration."""
 
-    def __init__(self, J, Q, T, N, n_out_scattering):
+    def __init__(self, J, Q, T, N, n_out_scattering, border_mode='reflect'):
         Q1 = fbk._as_Q1(Q)
         self.J, self.Q, self.T, self.N = J, Q1, T, N
+        self.border_mode, self.border = border_mode, BORDER_MODES[border_mode]
         self.geo = fbk.build_geometry(N, J, Q1, T, clamp_to_signal=True)     # :100-113
         if self.geo.J_pad > sch.LOG2_NP_MAX:
             raise NotImplementedError('padded length 2**%d exceeds the single-CTA design' % self.geo.J_pad)
@@ -83,7 +94,7 @@ class PhasePlan:
         if self.dec <= 1:
             raise NotImplementedError('phase path without decimation (target length >= N) is not built')
         phi0 = bank.phi.levels[0].astype(np.float32)
-        G = smoothing_operator(phi0, N, self.geo.J_pad, self.geo.pad_left, self.dec)
+        G = smoothing_operator(phi0, N, self.geo.J_pad, self.geo.pad_left, self.dec, border_mode)
         self.n_out = G.shape[1]
         if self.n_out == 0:
             raise NotImplementedError('zero-length decimated output (reference falls back to no decimation)')
@@ -136,6 +147,7 @@ class PhasePlan:
             pass
         a = _P()
         a.N, a.geo, a.n_paths, a.n_out = self.N, self.geo, rows_per_job, self.n_out
+        a.border = self.border
         a.n_threads, a.smem_complex = sch.N_THREADS, logical + logical // 16
         a.tasks, a.steps, a.arena = tasks, ranges, arena.finish()
         a.chan = np.asarray(chan, np.int32)
@@ -165,6 +177,7 @@ class PhasePlan:
             pass
         a = _A()
         a.N, a.geo, a.n_paths, a.n_out = self.N, self.geo, len(self.bank.psi1), self.N
+        a.border = self.border
         a.n_threads, a.smem_complex = sch.N_THREADS, logical + logical // 16
         a.tasks, a.steps, a.arena = tasks, ranges, arena.finish()
         a.chan = np.zeros(1, np.int32)
@@ -233,16 +246,12 @@ class KymatioPhaseScattering1D(nn.Module):
         self.N = int(shape) if isinstance(shape, (int, float)) else int(shape[0])
         if border_mode not in ('reflect', 'constant', 'circular'):
             raise ValueError(f"Unsupported border_mode: {border_mode}")
-        if border_mode != 'reflect':
-            raise NotImplementedError("the fused CUDA path implements border_mode='reflect' only")
-        if oversampling != 0:
-            raise NotImplementedError('the fused CUDA path implements oversampling=0 only')
 
         self.scattering = Scattering1D(J=J, shape=shape, Q=self.Q_scattering, max_order=max_order, average=True,
                                        oversampling=oversampling, vectorize=True, out_type='array', T=T).to(self.device)
-        n_out_scat = self.scattering.ind_end[int(math.floor(math.log2(T)))] - \
-            self.scattering.ind_start[int(math.floor(math.log2(T)))]
-        self._plan = PhasePlan(J, self.Q, T, self.N, n_out_scat)
+        k_out = max(int(math.floor(math.log2(T))) - oversampling, 0)       # core/scattering1d.py:260-261; target_length (:445)
+        n_out_scat = self.scattering.ind_end[k_out] - self.scattering.ind_start[k_out]
+        self._plan = PhasePlan(J, self.Q, T, self.N, n_out_scat, border_mode)
         g = self._plan.geo
         self.J_pad, self.pad_left, self.pad_right = g.J_pad, g.pad_left, g.pad_right
         self.ind_start, self.ind_end = g.ind_start, g.ind_end

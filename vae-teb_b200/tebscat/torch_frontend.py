@@ -47,6 +47,7 @@ class _DevicePlan:
         desc.smem_complex = plan.smem_complex
         desc.n_tasks = plan.tasks.shape[0]
         desc.n_steps = plan.steps.shape[0]
+        desc.border_mode = int(getattr(plan, 'border', 0))     # phase plans only; the transform always reflects
         arena = np.ascontiguousarray(plan.arena, np.float32)
         tasks = np.ascontiguousarray(plan.tasks, np.int32)
         steps = np.ascontiguousarray(plan.steps, np.int32)
