@@ -197,6 +197,22 @@ int tebscat_large_modulus(tebscat_large* ctx, float* buf_dev, int64_t n_complex,
 int tebscat_large_store(tebscat_large* ctx, const float* buf_dev, int64_t B, int log_len, int i0, int n_out, int n_paths,
                         int channel, float* out_dev, void* stream);
 
+/* ---- backward pass: the reference is differentiable through torch autograd with ModulusStable
+ * (kymatio/backend/torch_backend.py:5-96).  Adjoints of the ops above; tebscat/large.py walks the cascade backwards. */
+/* dst = (|src|, 0), out of place (the pre-modulus signal stays available for the backward of the modulus) */
+int tebscat_large_modulus_to(tebscat_large* ctx, const float* src_dev, float* dst_dev, int64_t n_complex, void* stream);
+/* ModulusStable.backward (:59-96): grad <- Re(grad) * u / |u|, 0 where |u| = 0 */
+int tebscat_large_modulus_backward(tebscat_large* ctx, const float* u_dev, float* grad_dev, int64_t n_complex, void* stream);
+/* adjoint of tebscat_large_mulfold: gsrc[b, p] (+)= 2^-scale_exp f[p] gdst[b, p >> logk] (bit-reversed order) */
+int tebscat_large_unfold(tebscat_large* ctx, const float* gdst_dev, const float* filt_dev, float* gsrc_dev, int64_t B,
+                         int log_src, int logk, uint32_t chunk_mask, int log_chunk, int scale_exp, int accumulate, void* stream);
+/* adjoint of tebscat_large_store: zero signal with gout[b, channel, :] in the real part of samples [i0, i0 + n_out) */
+int tebscat_large_unstore(tebscat_large* ctx, const float* gout_dev, int64_t B, int log_len, int i0, int n_out, int n_paths,
+                          int channel, float* buf_dev, void* stream);
+/* adjoint of tebscat_large_pad_load: real part of the padded gradient folded back onto the N samples */
+int tebscat_large_pad_adjoint(tebscat_large* ctx, const float* gu_dev, int64_t B, int N, int pad_left, int log2_Np,
+                              float* gx_dev, void* stream);
+
 /* Measured FP32 FMA peak of `device` in TFLOP/s (bench.py's FP32 roofline denominator;
  * MEASURED_PEAKS.json has no FP32 figure). */
 int tebscat_bench_fp32_peak(int device, double* tflops_out);

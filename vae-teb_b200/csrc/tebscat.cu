@@ -1469,3 +1469,139 @@ extern "C" int tebscat_large_store(tebscat_large* g, const float* buf_dev, int64
     ++g_launches;
     return TEBSCAT_OK;
 }
+
+// ---- backward pass: adjoints of the ops above ----------------------------------------------------------
+// The reference is differentiable through torch autograd with ModulusStable (kymatio/backend/torch_backend.py:5-96;
+// test_differentiability_scattering, tests/scattering1d/test_torch_scattering1d.py:292-315).  Here the gradient is the
+// transposed cascade on the same global buffers: recompute a first-order node, walk its subtree backwards.
+
+// dst = (|src|, 0) out of place: the pre-modulus signal is kept for the backward of the modulus
+__global__ void g_modulus_to_kernel(const float2* __restrict__ src, float2* __restrict__ dst, long long total) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const float2 z = src[e];
+        dst[e] = make_float2(sqrtf(fmaf(z.x, z.x, z.y * z.y)), 0.f);
+    }
+}
+
+extern "C" int tebscat_large_modulus_to(tebscat_large* g, const float* src_dev, float* dst_dev, int64_t n_complex, void* stream) {
+    if (!g || !src_dev || !dst_dev || n_complex < 1) return fail(TEBSCAT_EINVAL, "null argument");
+    CU(cudaSetDevice(g->device));
+    g_modulus_to_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(src_dev),
+                                                                         reinterpret_cast<float2*>(dst_dev), n_complex);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+// ModulusStable.backward (kymatio/backend/torch_backend.py:59-96): grad_u = grad_|u| * u / |u|, 0 where |u| = 0.
+// `grad` holds the gradient with respect to the (real) modulus in its real part; it is overwritten by grad_u.
+__global__ void g_modulus_backward_kernel(const float2* __restrict__ u, float2* __restrict__ grad, long long total) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const float2 z = u[e];
+        const float m = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+        const float q = m == 0.f ? 0.f : grad[e].x / m;
+        grad[e] = make_float2(z.x * q, z.y * q);
+    }
+}
+
+extern "C" int tebscat_large_modulus_backward(tebscat_large* g, const float* u_dev, float* grad_dev, int64_t n_complex, void* stream) {
+    if (!g || !u_dev || !grad_dev || n_complex < 1) return fail(TEBSCAT_EINVAL, "null argument");
+    CU(cudaSetDevice(g->device));
+    g_modulus_backward_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(u_dev),
+                                                                               reinterpret_cast<float2*>(grad_dev), n_complex);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+// adjoint of g_mulfold_kernel: gsrc[b, p] (+)= 2^-sexp * f[p] * gdst[b, p >> logk]; the chunks the forward skips get 0
+__global__ void g_unfold_kernel(const float2* __restrict__ gdst, const float* __restrict__ f, float2* __restrict__ gsrc,
+                                long long B, int log_src, int logk, unsigned mask, int logcw, float scale, int accumulate) {
+    const long long total = B << log_src;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e >> log_src;
+        const int p = (int)(e - (b << log_src));
+        const int t = p & ((1 << logk) - 1);
+        const bool live = logk < 2 || ((mask >> (t >> logcw)) & 1u);
+        float2 v = make_float2(0.f, 0.f);
+        if (live) {
+            const float w = __ldg(f + p) * scale;
+            const float2 z = gdst[(b << (log_src - logk)) + (p >> logk)];
+            v = make_float2(z.x * w, z.y * w);
+        }
+        if (accumulate) {
+            if (live) {
+                const float2 o = gsrc[e];
+                gsrc[e] = make_float2(o.x + v.x, o.y + v.y);
+            }
+        } else {
+            gsrc[e] = v;
+        }
+    }
+}
+
+extern "C" int tebscat_large_unfold(tebscat_large* g, const float* gdst_dev, const float* filt_dev, float* gsrc_dev, int64_t B,
+                                    int log_src, int logk, uint32_t chunk_mask, int log_chunk, int scale_exp, int accumulate,
+                                    void* stream) {
+    if (!g || !gdst_dev || !filt_dev || !gsrc_dev || B < 1 || log_src < 1 || log_src > kLargeMaxLog2 || logk < 0 || logk > log_src ||
+        (logk >= 2 && (chunk_mask == 0 || log_chunk < 2 || log_chunk > logk || (logk - log_chunk) > 5)))
+        return fail(TEBSCAT_EINVAL, "bad filter multiply request");
+    CU(cudaSetDevice(g->device));
+    g_unfold_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(gdst_dev), filt_dev,
+                                                                     reinterpret_cast<float2*>(gsrc_dev), B, log_src, logk, chunk_mask,
+                                                                     log_chunk, ldexpf(1.0f, -scale_exp), accumulate);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+// adjoint of g_store_kernel: buf[b, :] = 0 except Re buf[b, i0 + n] = gout[b, channel, n]
+__global__ void g_unstore_kernel(const float* __restrict__ gout, float2* __restrict__ buf, long long B, int log_len, int i0, int n_out,
+                                 int n_paths, int channel) {
+    const long long total = B << log_len;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e >> log_len;
+        const int n = (int)(e - (b << log_len)) - i0;
+        const float v = (n >= 0 && n < n_out) ? __ldg(gout + (b * n_paths + channel) * n_out + n) : 0.f;
+        buf[e] = make_float2(v, 0.f);
+    }
+}
+
+extern "C" int tebscat_large_unstore(tebscat_large* g, const float* gout_dev, int64_t B, int log_len, int i0, int n_out, int n_paths,
+                                     int channel, float* buf_dev, void* stream) {
+    if (!g || !buf_dev || !gout_dev || B < 1 || i0 < 0 || n_out < 1 || i0 + n_out > (1 << log_len) || channel < 0 || channel >= n_paths)
+        return fail(TEBSCAT_EINVAL, "bad store request");
+    CU(cudaSetDevice(g->device));
+    g_unstore_kernel<<<g->n_sms * 4, 256, 0, (cudaStream_t)stream>>>(gout_dev, reinterpret_cast<float2*>(buf_dev), B, log_len, i0,
+                                                                      n_out, n_paths, channel);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+// adjoint of g_pad_load_kernel: gx[b, r] = Re gu[b, pad_left + r] + its left and right mirror images (pad < N: one fold)
+__global__ void g_pad_adjoint_kernel(const float2* __restrict__ gu, float* __restrict__ gx, long long B, int N, int pad_left, int log2_Np) {
+    const long long total = B * N;
+    const int pad_right = (1 << log2_Np) - N - pad_left;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / N;
+        const int r = (int)(e - b * N);
+        const float2* row = gu + (b << log2_Np);
+        float v = row[pad_left + r].x;
+        if (r >= 1 && r <= pad_left) v += row[pad_left - r].x;
+        if (r <= N - 2 && r >= N - 1 - pad_right) v += row[pad_left + 2 * (N - 1) - r].x;
+        gx[e] = v;
+    }
+}
+
+extern "C" int tebscat_large_pad_adjoint(tebscat_large* g, const float* gu_dev, int64_t B, int N, int pad_left, int log2_Np,
+                                         float* gx_dev, void* stream) {
+    if (!g || !gx_dev || !gu_dev || B < 1 || N < 2 || pad_left < 0 || pad_left >= N || ((1LL << log2_Np) - N - pad_left) >= N)
+        return fail(TEBSCAT_EINVAL, "Indefinite padding size (larger than tensor).");
+    CU(cudaSetDevice(g->device));
+    g_pad_adjoint_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(gu_dev), gx_dev, B, N, pad_left,
+                                                                          log2_Np);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}

@@ -99,6 +99,18 @@ def load():
     lib.tebscat_large_store.restype = ctypes.c_int
     lib.tebscat_large_store.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, vp, vp]
+    lib.tebscat_large_modulus_to.restype = ctypes.c_int
+    lib.tebscat_large_modulus_to.argtypes = [vp, vp, vp, ctypes.c_int64, vp]
+    lib.tebscat_large_modulus_backward.restype = ctypes.c_int
+    lib.tebscat_large_modulus_backward.argtypes = [vp, vp, vp, ctypes.c_int64, vp]
+    lib.tebscat_large_unfold.restype = ctypes.c_int
+    lib.tebscat_large_unfold.argtypes = [vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, u32, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, vp]
+    lib.tebscat_large_unstore.restype = ctypes.c_int
+    lib.tebscat_large_unstore.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, vp, vp]
+    lib.tebscat_large_pad_adjoint.restype = ctypes.c_int
+    lib.tebscat_large_pad_adjoint.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.tebscat_scat1d_profile_steps.restype = ctypes.c_int
     lib.tebscat_scat1d_profile_steps.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp]
     lib.tebscat_bench_fp32_peak.restype = ctypes.c_int

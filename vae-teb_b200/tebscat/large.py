@@ -198,3 +198,84 @@ class LargeDevicePlan:
                 pair(W2, k['l2'])                                                                     # :350-355
                 leaf(W2, k['leaf'], k['ch'])                                                          # :358-364
         return out
+
+    # ---- backward pass --------------------------------------------------------------------------------
+    def _bwd_workspace(self, B, dev):
+        key = ('bwd', B, dev.index)
+        if getattr(self, '_bws_key', None) != key:
+            Np = 1 << self.plan.geo.J_pad
+            self._bws = tuple(torch.empty(B * Np * 2, dtype=torch.float32, device=dev) for _ in range(8)) + \
+                (torch.empty(B * (2 << self.plan.lf), dtype=torch.float32, device=dev),)
+            self._bws_key = key
+        return self._bws
+
+    def backward(self, x2, gout, gx):
+        """gx = (dS/dx)^T gout for x2 (B, N), gout (B, C, n_out), gx (B, N), all float32 CUDA contiguous.
+
+        The reference differentiates the cascade with torch autograd (ModulusStable,
+        kymatio/backend/torch_backend.py:5-96).  Here the transposed cascade runs on the same global buffers: the
+        spectrum U0 is recomputed once, every first-order node is recomputed when its turn comes (the pre-modulus
+        signals u1, u2 are what the modulus' backward needs) and its subtree is walked backwards --
+            store^T (zero signal carrying the output gradient) -> iFFT^T = FFT -> (phi multiply + periodise)^T
+            -> FFT^T = iFFT, real part -> modulus backward -> iFFT^T = FFT -> (psi multiply + periodise)^T, accumulated.
+        With spectra in bit-reversed order the adjoint of the forward transform (natural -> bit-reversed) IS the
+        unnormalised inverse transform (bit-reversed -> natural) and vice versa, so no new transform is needed."""
+        p, lib, g = self.plan, self._lib, self.handle
+        B, dev = x2.shape[0], x2.device
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        U0, gU0, W1, H1, gH1, W2, gW2, gA, WL = self._bwd_workspace(B, dev)
+        n, lf = p.geo.J_pad, p.lf
+        fa = self.arena.data_ptr()
+        vp = ctypes.c_void_p
+
+        def mulfold(src, spec, dst):
+            off, log_src, logk, mask, logcw, sexp = spec
+            _lib.check(lib.tebscat_large_mulfold(g, vp(src.data_ptr()), vp(fa + 4 * off), vp(dst.data_ptr()), B, log_src, logk,
+                                                 mask, logcw, sexp, st))
+
+        def unfold(gdst, spec, gsrc, accumulate):
+            off, log_src, logk, mask, logcw, sexp = spec
+            _lib.check(lib.tebscat_large_unfold(g, vp(gdst.data_ptr()), vp(fa + 4 * off), vp(gsrc.data_ptr()), B, log_src, logk,
+                                                mask, logcw, sexp, 1 if accumulate else 0, st))
+
+        def fft(buf, log_len, inverse):
+            _lib.check(lib.tebscat_large_fft(g, vp(buf.data_ptr()), B, log_len, 1 if inverse else 0, st))
+
+        def leaf_adjoint(spec, ch, gsrc, accumulate):
+            """(phi multiply + periodise -> iFFT -> unpad -> channel)^T, core :287-292 / :320-327 / :358-364"""
+            _lib.check(lib.tebscat_large_unstore(g, vp(gout.data_ptr()), B, lf, p.i0, p.n_out, p.n_paths, ch, vp(WL.data_ptr()), st))
+            fft(WL, lf, False)
+            unfold(WL, spec, gsrc, accumulate)
+
+        def modulus_node(y, log_len, mod_out):
+            """y: periodised spectrum -> u = ifft(y) (kept in y) -> mod_out = fft(|u|)"""
+            fft(y, log_len, True)
+            _lib.check(lib.tebscat_large_modulus_to(g, vp(y.data_ptr()), vp(mod_out.data_ptr()), B << log_len, st))
+            fft(mod_out, log_len, False)
+
+        def modulus_adjoint(gspec, u, log_len):
+            """gspec: gradient w.r.t. fft(|u|) (bit-reversed) -> gradient w.r.t. the periodised spectrum ifft's input"""
+            fft(gspec, log_len, True)                          # FFT^T; the modulus is real: only the real part matters
+            _lib.check(lib.tebscat_large_modulus_backward(g, vp(u.data_ptr()), vp(gspec.data_ptr()), B << log_len, st))
+            fft(gspec, log_len, False)                         # iFFT^T (its 1/L lives in the multiply's scale)
+
+        _lib.check(lib.tebscat_large_pad_load(g, vp(x2.data_ptr()), B, p.N, p.geo.pad_left, n, vp(U0.data_ptr()), st))
+        fft(U0, n, False)
+        leaf_adjoint(p.s0, 0, gU0, False)                      # initialises gU0
+        for e in p.first:
+            l1 = e['l1']
+            mulfold(U0, e['mul'], W1)
+            modulus_node(W1, l1, H1)                     # W1 = u1, H1 = fft(|u1|)
+            leaf_adjoint(e['leaf'], e['ch'], gH1, False)       # initialises gH1
+            for k in e['kids']:
+                l2 = k['l2']
+                mulfold(H1, k['mul'], W2)
+                fft(W2, l2, True)                              # W2 = u2
+                leaf_adjoint(k['leaf'], k['ch'], gW2, False)   # gradient w.r.t. fft(|u2|)
+                modulus_adjoint(gW2, W2, l2)
+                unfold(gW2, k['mul'], gH1, True)
+            modulus_adjoint(gH1, W1, l1)
+            unfold(gH1, e['mul'], gU0, True)
+        fft(gU0, n, True)                                      # FFT^T of the real padded signal
+        _lib.check(lib.tebscat_large_pad_adjoint(g, vp(gU0.data_ptr()), B, p.N, p.geo.pad_left, n, vp(gx.data_ptr()), st))
+        return gx

@@ -71,6 +71,22 @@ class _DevicePlan:
             pass
 
 
+class _ScatteringFunction(torch.autograd.Function):
+    """Autograd node of the array-output transform: forward = the product path, backward = the transposed
+    cascade in CUDA (no torch ops on either)."""
+
+    @staticmethod
+    def forward(ctx, x2, module):
+        ctx.module = module
+        ctx.save_for_backward(x2)
+        return module._forward_array(x2)
+
+    @staticmethod
+    def backward(ctx, gS):
+        (x2,) = ctx.saved_tensors
+        return ctx.module._backward_array(x2, gS), None
+
+
 class Scattering1D(nn.Module):
     def __init__(self, J, shape, Q=1, max_order=2, average=True, oversampling=0, vectorize=True,
                  out_type='array', backend='torch', T=None):
@@ -219,17 +235,17 @@ class Scattering1D(nn.Module):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         B = x2.shape[0]
+        needs_grad = torch.is_grad_enabled() and x.requires_grad
         if not self.average:
+            if needs_grad:
+                raise NotImplementedError('the backward pass is built for average=True')
             return self._scattering_unaveraged(x2, batch_shape)
-        if self.J_pad > LOG2_NP_MAX:
-            return self._scattering_large(x2, batch_shape)
-        plan = self._plan_for(x.device.index if x.device.index is not None else torch.cuda.current_device())
-        sched = self._sched[1]
-        C, n_out = sched.n_paths, sched.n_out
-        S = torch.empty((B, C, n_out), dtype=torch.float32, device=x.device)
-        stream = torch.cuda.current_stream(x.device).cuda_stream
-        rc = _lib.load().tebscat_scat1d_forward(plan.handle, x2.data_ptr(), B, S.data_ptr(), stream)
-        _lib.check(rc)
+        if self.J_pad > LOG2_NP_MAX and (self.out_type != 'array' or not self.vectorize):
+            raise NotImplementedError('the large-support level produces the array output only')
+        # differentiable like the reference's torch backend (ModulusStable, kymatio/backend/torch_backend.py:5-96):
+        # the forward is the same fused launch, the backward the transposed cascade of tebscat/large.py
+        S = _ScatteringFunction.apply(x2, self) if needs_grad else self._forward_array(x2)
+        C, n_out = S.shape[1], S.shape[2]
         P = S.view(B, 1, C, n_out)                       # core/scattering1d.py:395-397: P is S before the reshape
         if self.out_type == 'array' and self.vectorize:
             return [S.reshape(batch_shape + (C, n_out)), P]
@@ -246,27 +262,50 @@ class Scattering1D(nn.Module):
             out.append({'coef': S[:, c, :].reshape(batch_shape + (n_out,)), 'j': j})
         return [out, out]
 
-    def _scattering_large(self, x2, batch_shape):
-        """Padded lengths 2^14 .. 2^17: the large-support level of tebscat/large.py -- the reference's
-        op order on global spectra, transforms as tile jobs of the interpreter.  Array output only."""
+    def _forward_array(self, x2):
+        """S (B, C, n_out) of x2 (B, N): the fused single-launch cascade up to padded lengths of 2^13, the
+        large-support level of tebscat/large.py above."""
+        dev = x2.device
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        B = x2.shape[0]
+        if self.J_pad > LOG2_NP_MAX:
+            lp, ldp = self._large_plan_for(index)
+            S = torch.empty((B, lp.n_paths, lp.n_out), dtype=torch.float32, device=dev)
+            chunk = max(1, (1 << 28) >> self.J_pad)              # <= 2.7 GB of workspace per chunk
+            for b0 in range(0, B, chunk):
+                ldp.forward(x2[b0:b0 + chunk], S[b0:b0 + chunk])
+            return S
+        plan = self._plan_for(index)
+        sched = self._sched[1]
+        S = torch.empty((B, sched.n_paths, sched.n_out), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().tebscat_scat1d_forward(plan.handle, x2.data_ptr(), B, S.data_ptr(), stream))
+        return S
+
+    def _large_plan_for(self, index):
+        """Op-list plan of the large-support level: the forward above 2^13 and the backward pass at any length."""
         from .large import LargeDevicePlan, LargePlan
-        if self.out_type != 'array' or not self.vectorize:
-            raise NotImplementedError('the large-support level produces the array output only')
         key = (self.J, self.N, self._Q1, self.T, self.max_order, int(self.oversampling))
         if getattr(self, '_lsched', None) is None or self._lsched[0] != key:
             self._lsched = (key, LargePlan(self.J, self.N, self._Q1, self.T, self.max_order, int(self.oversampling)))
             self._lplans = {}
-        lp = self._lsched[1]
+        if index not in self._lplans:
+            self._lplans[index] = LargeDevicePlan(self._lsched[1], index)
+        return self._lsched[1], self._lplans[index]
+
+    def _backward_array(self, x2, gS):
+        """(dS/dx)^T gS -- see LargeDevicePlan.backward."""
         dev = x2.device
         index = dev.index if dev.index is not None else torch.cuda.current_device()
-        if index not in self._lplans:
-            self._lplans[index] = LargeDevicePlan(lp, index)
-        B = x2.shape[0]
-        S = torch.empty((B, lp.n_paths, lp.n_out), dtype=torch.float32, device=dev)
-        chunk = max(1, (1 << 28) >> self.J_pad)              # <= 2.7 GB of workspace per chunk
-        for b0 in range(0, B, chunk):
-            self._lplans[index].forward(x2[b0:b0 + chunk], S[b0:b0 + chunk])
-        return [S.reshape(batch_shape + (lp.n_paths, lp.n_out)), S.view(B, 1, lp.n_paths, lp.n_out)]
+        lp, ldp = self._large_plan_for(index)
+        gS = gS.contiguous()
+        if gS.dtype is not torch.float32:
+            raise TypeError('Input and filter must be of the same dtype.')
+        gx = torch.empty_like(x2)
+        chunk = max(1, (1 << 25) >> self.J_pad)                  # <= 2.4 GB of workspace per chunk
+        for b0 in range(0, x2.shape[0], chunk):
+            ldp.backward(x2[b0:b0 + chunk], gS[b0:b0 + chunk], gx[b0:b0 + chunk])
+        return gx
 
     def _scattering_unaveraged(self, x2, batch_shape):
         """average=False (core/scattering1d.py:293-294, :329-330, :366-367): the input itself, then the unpadded
