@@ -803,6 +803,8 @@ __global__ void __launch_bounds__(kPThreads, 2) phase_pair_kernel(const PairPara
     }
 }
 
+#include "phase_tc.cuh"
+
 // cross_phase_low_pass=False (:356-360): the full-rate real part of the product
 __global__ void phase_product_kernel(const PairParams p) {
     const long long total = p.rows * p.N;
@@ -826,6 +828,8 @@ struct tebscat_phase_plan {
     tebscat_plan* stage_a = nullptr;
     int device = 0;
     float2* d_G = nullptr;
+    float* d_Bs = nullptr;          // tcgen05 form: [2][n_cols_pad][k_pad] TF32 head / tail of B' (phase_tc.cuh)
+    int32_t n_slabs = 0, k_pad = 0;
     int32_t* d_i = nullptr;
     int32_t* d_j = nullptr;
     float* d_pw = nullptr;
@@ -861,6 +865,31 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
     const size_t g_elems = (size_t)d->N * d->n_cols_pad;
     CU(cudaMalloc(&p->d_G, g_elems * sizeof(float2)));
     CU(cudaMemcpy(p->d_G, G_host, g_elems * sizeof(float2), cudaMemcpyHostToDevice));
+    {   // B'[n][2t + c] = G[t][n][c], split into TF32 head and tail (round to nearest, ties away, like cvt.rna.tf32.f32)
+        p->n_slabs = (d->N + kTcSlabT - 1) / kTcSlabT;
+        p->k_pad = p->n_slabs * kTcK;
+        const size_t per = (size_t)d->n_cols_pad * p->k_pad;
+        std::vector<float> bs(2 * per, 0.f);
+        auto rna = [](float v) {
+            uint32_t u;
+            memcpy(&u, &v, 4);
+            u = (u + 0x1000u) & 0xffffe000u;
+            float r;
+            memcpy(&r, &u, 4);
+            return r;
+        };
+        for (int t = 0; t < d->N; ++t)
+            for (int n = 0; n < d->n_cols_pad; ++n)
+                for (int c = 0; c < 2; ++c) {
+                    const float v = G_host[((size_t)t * d->n_cols_pad + n) * 2 + c];
+                    const float hi = rna(v);
+                    bs[(size_t)n * p->k_pad + 2 * t + c] = hi;
+                    bs[per + (size_t)n * p->k_pad + 2 * t + c] = rna(v - hi);
+                }
+        CU(cudaMalloc(&p->d_Bs, bs.size() * sizeof(float)));
+        CU(cudaMemcpy(p->d_Bs, bs.data(), bs.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaFuncSetAttribute(phase_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+    }
     CU(cudaMalloc(&p->d_i, d->n_pairs * sizeof(int32_t)));
     CU(cudaMalloc(&p->d_j, d->n_pairs * sizeof(int32_t)));
     CU(cudaMalloc(&p->d_pw, d->n_pairs * sizeof(float)));
@@ -877,6 +906,7 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaFree(p->d_G);
+    cudaFree(p->d_Bs);
     cudaFree(p->d_i);
     cudaFree(p->d_j);
     cudaFree(p->d_pw);
@@ -888,6 +918,29 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
     tebscat_plan_destroy(p->stage_a);
     tebscat_plan_destroy(p->pair_plan);
     delete p;
+}
+
+// The dense form of stage B: tcgen05 + TMEM (phase_tc.cuh) unless TEBSCAT_PHASE_MMA=sync asks for the mma.sync kernel.
+static bool use_tcgen05_pairs() {
+    static const int v = [] {
+        const char* e = getenv("TEBSCAT_PHASE_MMA");
+        return (e && strcmp(e, "sync") == 0) ? 0 : 1;
+    }();
+    return v != 0;
+}
+static void launch_pair_gemm(const tebscat_phase_plan* p, const PairParams& pp, cudaStream_t st) {
+    const tebscat_phase_desc& d = p->desc;
+    if (use_tcgen05_pairs()) {
+        PairTcParams q;
+        q.zp = pp.zp; q.zc = pp.zc; q.Bs = p->d_Bs; q.i_idx = pp.i_idx; q.j_idx = pp.j_idx; q.powers = pp.powers;
+        q.subset = pp.subset; q.out = pp.out; q.rows = pp.rows; q.n_sel = pp.n_sel; q.F = pp.F; q.N = pp.N;
+        q.n_out = pp.n_out; q.n_cols_pad = pp.n_cols_pad; q.n_slabs = p->n_slabs; q.k_pad = p->k_pad;
+        dim3 grid((unsigned)((pp.rows + kTcRows - 1) / kTcRows), (unsigned)(d.n_cols_pad / kTcCols));
+        phase_pair_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(q);
+    } else {
+        dim3 grid((unsigned)((pp.rows + kPR - 1) / kPR), (unsigned)(d.n_cols_pad / kPC));
+        phase_pair_kernel<<<grid, kPThreads, kPairSmem, st>>>(pp);
+    }
 }
 
 // Stage B as transforms on the step interpreter: `pair_plan` is a schedule whose jobs are n_paths (up to 8)
@@ -1002,8 +1055,7 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
             if (int rc = launch_pairs_fft(p, p->d_zp, p->d_zc, pp.subset, n_sel, nb, pp.out, st)) return rc;
             continue;
         } else if (apply_low_pass) {
-            dim3 grid((unsigned)((pp.rows + kPR - 1) / kPR), (unsigned)(d.n_cols_pad / kPC));
-            phase_pair_kernel<<<grid, kPThreads, kPairSmem, st>>>(pp);
+            launch_pair_gemm(p, pp, st);
         } else {
             phase_product_kernel<<<1184, 256, 0, st>>>(pp);
         }
@@ -1032,8 +1084,7 @@ static int launch_pairs(const tebscat_phase_plan* p, const float2* zp, const flo
     pp.N = d.N;
     pp.n_out = d.n_out;
     pp.n_cols_pad = d.n_cols_pad;
-    dim3 grid((unsigned)((pp.rows + kPR - 1) / kPR), (unsigned)(d.n_cols_pad / kPC));
-    phase_pair_kernel<<<grid, kPThreads, kPairSmem, st>>>(pp);
+    launch_pair_gemm(p, pp, st);
     CU(cudaGetLastError());
     ++g_launches;
     return TEBSCAT_OK;
