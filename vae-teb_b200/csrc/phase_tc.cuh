@@ -8,15 +8,15 @@
 // B'[2t, n] = Re G[t, n], B'[2t+1, n] = Im G[t, n], in 3xTF32 (fp32-class accuracy): A' = Ah + Al, B' = Bh + Bl,
 // out ~= Ah Bh + Al Bh + Ah Bl.
 //
-// One CTA = 128 rows x 80 columns, one CTA per SM, 25 warps:
-//   * 16 PRODUCER warps compute the rows' products where they are consumed -- a thread owns one row (= one TMEM
-//     lane) and four time samples of a slab of 16 -- split them into TF32 head and tail and write them straight into
-//     TENSOR MEMORY with tcgen05.st: the A' operand never touches shared memory (tcgen05.mma with A from TMEM).
-//     They also copy the slab of B' (pre-split on the host side of the plan, K-major, 128-byte swizzle) into shared
-//     memory;
+// One CTA = 128 rows x 80 columns, one CTA per SM, 21 warps:
+//   * 16 PRODUCER warps in four groups compute the rows' products where they are consumed -- group j owns the slabs
+//     i = j (mod 4), a thread one row (= one TMEM lane) of such a slab of 16 samples -- split them into TF32 head and
+//     tail and write them straight into TENSOR MEMORY with tcgen05.st: the A' operand never touches shared memory
+//     (tcgen05.mma with A from TMEM).  The group also copies its slab of B' (pre-split on the host side of the plan,
+//     K-major, 128-byte swizzle) into shared memory with cp.async;
 //   * ONE thread of the MMA warp issues tcgen05.mma.kind::tf32 (M = 128, N = 80, K = 8): 12 per slab, accumulating in
 //     TMEM; tcgen05.commit releases the slab's stage and hands finished accumulators to
-//   * 8 EPILOGUE warps, which drain an accumulator every kTcDrain slabs with tcgen05.ld and add it to running sums
+//   * 4 EPILOGUE warps, which drain an accumulator every kTcDrain slabs with tcgen05.ld and add it to running sums
 //     in fp32 registers (a tensor-core accumulator that runs over all K = 2N = 9600 would carry its truncation bias,
 //     see the mma.sync kernel), double-buffered so the drain overlaps the next group's MMAs.
 // mbarriers: full[s] (producers -> MMA), empty[s] (MMA -> producers), acc_full[a] (MMA -> epilogue),
@@ -33,12 +33,14 @@ constexpr int kTcSlabT = 16;          // time samples per slab
 constexpr int kTcK = 2 * kTcSlabT;    // K per slab (Re, -Im interleaved)
 constexpr int kTcStages = 4;
 constexpr int kTcDrain = 2;           // slabs per accumulator drain
-constexpr int kTcEpiWarps = 8, kTcProdWarps = 16;
-constexpr int kTcMmaWarp = kTcEpiWarps;                          // warp 8
-constexpr int kTcThreads = 32 * (kTcEpiWarps + 1 + kTcProdWarps);   // 800
+constexpr int kTcEpiWarps = 4, kTcProdWarps = 16, kTcGroups = 4;   // producer groups of four warps (one per TMEM lane quarter)
+constexpr int kTcMmaWarp = kTcEpiWarps;                          // warp 4
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 1 + kTcProdWarps);   // 672: 96 registers per thread
 constexpr int kTcBTile = kTcCols * 128;                         // bytes of one B' tile (80 rows x 32 tf32)
 constexpr int kTcStageBytes = 2 * kTcBTile;                      // head + tail
-constexpr size_t kTcSmem = 1024 + (size_t)kTcStages * kTcStageBytes + 256;
+constexpr int kTcInBytes = 2 * kTcRows * 128;                    // one group's input slab: 128 lines of (|z|, theta) + 128 of (re, im)
+constexpr int kTcOffBars = kTcStages * kTcStageBytes + kTcGroups * kTcInBytes;
+constexpr size_t kTcSmem = 1024 + (size_t)kTcOffBars + 256 + 2 * kTcRows * sizeof(long long);
 constexpr uint32_t kTcAcc0 = 0, kTcAcc1 = 128, kTcA0 = 256;      // TMEM columns; A' stage s: head at kTcA0 + 64 s, tail + 32
 
 struct PairTcParams {
@@ -74,6 +76,24 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (!done && spin > (1u << 24)) __trap();
+    }
+}
+// the same for warps that wait long (epilogue, producers ahead of the tensor core): back off between polls so that
+// the polling does not take issue slots from the producers
+__device__ __forceinline__ void tc_mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done) {
+            __nanosleep(ns);
+            if (spin > (1u << 22)) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -119,10 +139,13 @@ __device__ __forceinline__ uint64_t tc_b_desc(uint32_t smem_addr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 80
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcCols >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
 
+// TF32 head and tail of v.  cvt.rna.tf32.f32 (round to nearest, ties away) is "add half an ulp of the 13 dropped bits to
+// the magnitude, truncate"; as two integer instructions it runs on the ALU pipe instead of the 16-lane conversion unit,
+// which the sine and cosine of every product already occupy.
 __device__ __forceinline__ void tc_split(float v, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
     const float r = v - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const PairTcParams p) {
@@ -131,8 +154,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     const uint32_t raw = tc_smem_u32(tc_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = tc_raw + (base - raw);
-    const uint32_t bars = base + kTcStages * kTcStageBytes;          // full[4], empty[4], acc_full[2], acc_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kTcStages * kTcStageBytes + 128);
+    const uint32_t bars = base + kTcOffBars;                         // full[4], empty[4], acc_full[2], acc_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kTcOffBars + 128);
+    long long* s_off = reinterpret_cast<long long*>(sm + kTcOffBars + 256);   // [2][128]: first sample of the rows' inputs, -1 = no row
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (kTcStages + s); };
     auto acc_full = [&](int a) { return bars + 8u * (2 * kTcStages + a); };
@@ -141,7 +165,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < kTcStages; ++s) {
-            tc_mbar_init(full(s), kTcProdWarps);
+            tc_mbar_init(full(s), kTcProdWarps / kTcGroups);
             tc_mbar_init(empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -149,6 +173,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
             tc_mbar_init(acc_empty(a), kTcEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < kTcRows) {
+        const long long row = (long long)blockIdx.x * kTcRows + tid;
+        long long zp_off = -1, zc_off = -1;
+        if (row < p.rows) {
+            const long long b = row / p.n_sel;
+            const int sidx = (int)(row - b * p.n_sel);
+            const int pair = p.subset ? p.subset[sidx] : sidx;
+            zp_off = (b * p.F + p.i_idx[pair]) * (long long)p.N;
+            zc_off = (b * p.F + p.j_idx[pair]) * (long long)p.N;
+        }
+        s_off[tid] = zp_off;
+        s_off[kTcRows + tid] = zc_off;
     }
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem_u32(tmem_slot)) : "memory");
@@ -165,18 +202,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     const int n_groups = (n_slabs + kTcDrain - 1) / kTcDrain;
 
     if (warp < kTcEpiWarps) {
-        // ===== epilogue: lanes 32 q .. 32 q + 31, columns 40 h .. 40 h + 39 =====
-        const int q = warp & 3, h = warp >> 2;
-        float total[40];
+        // ===== epilogue: warp q drains lanes 32 q .. 32 q + 31, all 80 columns =====
+        const int q = warp & 3;
+        float total[kTcCols];
 #pragma unroll
-        for (int i = 0; i < 40; ++i) total[i] = 0.f;
+        for (int i = 0; i < kTcCols; ++i) total[i] = 0.f;
         for (int g = 0; g < n_groups; ++g) {
             const int a = g & 1;
-            tc_mbar_wait(acc_full(a), (g >> 1) & 1);
+            tc_mbar_wait_relaxed(acc_full(a), (g >> 1) & 1, 128);
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (a ? kTcAcc1 : kTcAcc0) + 40 * h;
+            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (a ? kTcAcc1 : kTcAcc0);
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
+            for (int j = 0; j < kTcCols / 8; ++j) {
                 float v[8];
                 tc_ld8(taddr + 8 * j, v);
 #pragma unroll
@@ -189,8 +226,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         const long long row = row0 + 32 * q + lane;
         if (row < p.rows) {
 #pragma unroll
-            for (int i = 0; i < 40; ++i) {
-                const int col = col0 + 40 * h + i;
+            for (int i = 0; i < kTcCols; ++i) {
+                const int col = col0 + i;
                 if (col < p.n_out) p.out[row * p.n_out + col] = total[i];
             }
         }
@@ -222,77 +259,107 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         }
         __syncwarp();
     } else {
-        // ===== producers: row 32 q + lane, samples 4 sub .. 4 sub + 3 of every slab; B' tiles =====
+        // ===== producers: four groups of four warps; group j owns the slabs i = j (mod 4), a thread the 16 samples of
+        // row 32 q + lane in such a slab.  The slab's inputs -- one 128-byte line of (|z|, theta) and one of (re, im) per
+        // row -- come through shared memory: the group copies them with COALESCED cp.async (eight lanes per line; a lane
+        // reading its own row straight from global memory costs one L1 wavefront per lane, and the L1 data pipe was
+        // the limit), swizzled so that the per-row 128-bit reads are conflict free.  While one group waits (its copies,
+        // its stage, the tensor-memory stores), the other three compute. =====
         const int pw_ = warp - (kTcMmaWarp + 1);
-        const int q = warp & 3, sub = pw_ >> 2;
-        const int ptid = pw_ * 32 + lane;
-        const long long row = row0 + 32 * q + lane;
-        long long zp_off = -1, zc_off = 0;
+        const int q = warp & 3, grp = pw_ >> 2;
+        const int gtid = q * 32 + lane;                         // 0..127 inside the group = the thread's row
+        const long long row = row0 + gtid;
         float pw = 1.f;
         if (row < p.rows) {
-            const long long b = row / p.n_sel;
-            const int sidx = (int)(row - b * p.n_sel);
-            const int pair = p.subset ? p.subset[sidx] : sidx;
-            zp_off = (b * p.F + p.i_idx[pair]) * (long long)p.N;
-            zc_off = (b * p.F + p.j_idx[pair]) * (long long)p.N;
-            pw = p.powers[pair];
+            const int sidx = (int)(row % p.n_sel);
+            pw = p.powers[p.subset ? p.subset[sidx] : sidx];
         }
-        float2 rzp[4], rzc[4];
-        auto fetch = [&](int i) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int t = i * kTcSlabT + 4 * sub + j;
-                const bool in = zp_off >= 0 && t < p.N;
-                rzp[j] = in ? __ldg(p.zp + zp_off + t) : make_float2(0.f, 0.f);
-                rzc[j] = in ? __ldg(p.zc + zc_off + t) : make_float2(0.f, 0.f);
+        const uint32_t sin_base = base + kTcStages * kTcStageBytes + grp * kTcInBytes;
+        const uint8_t* sin_ptr = sm + kTcStages * kTcStageBytes + grp * kTcInBytes;
+        const bool wide = (p.N & 1) == 0;                       // rows start on 16-byte boundaries
+        auto copy_inputs = [&](int i) {
+            const int t_slab = i * kTcSlabT;
+            if (wide) {
+#pragma unroll 4
+                for (int k = 0; k < 16; ++k) {
+                    const int idx = gtid + 128 * k;
+                    const int arr = idx >> 10, r = (idx >> 3) & 127, c = idx & 7;          // 16-byte chunk c of row r
+                    const long long off = s_off[arr * kTcRows + r];
+                    const int t = t_slab + 2 * c;
+                    const int bytes = off < 0 ? 0 : max(0, min(16, (p.N - t) * 8));
+                    const float2* src = (arr ? p.zc : p.zp) + (bytes ? off + t : 0);
+                    const uint32_t dst = sin_base + arr * (kTcRows * 128) + r * 128 + ((c ^ (r & 7)) << 4);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+                }
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < 32; ++k) {
+                    const int idx = gtid + 128 * k;
+                    const int arr = idx >> 11, r = (idx >> 4) & 127, c8 = idx & 15;        // 8-byte sample c8 of row r
+                    const long long off = s_off[arr * kTcRows + r];
+                    const int t = t_slab + c8;
+                    const int bytes = (off < 0 || t >= p.N) ? 0 : 8;
+                    const float2* src = (arr ? p.zc : p.zp) + (bytes ? off + t : 0);
+                    const uint32_t dst = sin_base + arr * (kTcRows * 128) + r * 128 + (((c8 >> 1) ^ (r & 7)) << 4) + (c8 & 1) * 8;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+                }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        fetch(0);
         const float* Bh = p.Bs + (size_t)col0 * p.k_pad;
         const float* Bl = p.Bs + ((size_t)p.n_cols_pad + col0) * p.k_pad;
-        for (int i = 0; i < n_slabs; ++i) {
+        if (grp < n_slabs) copy_inputs(grp);
+        for (int i = grp; i < n_slabs; i += kTcGroups) {
             const int s = i % kTcStages;
-            tc_mbar_wait(empty(s), ((i / kTcStages) & 1) ^ 1);
+            tc_mbar_wait_relaxed(empty(s), ((i / kTcStages) & 1) ^ 1, 32);
             tc_fence_after();
-            // B' slab: 2 x 80 rows x 8 chunks of 16 bytes, swizzled
-            float4 bv[3];
+            // B' slab: 2 x 80 rows x 8 chunks of 16 bytes, global -> swizzled shared memory, asynchronously
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int idx = ptid + 512 * j;
-                if (idx < 2 * kTcCols * 8) {
-                    const int part = idx >= kTcCols * 8, rem = idx - part * kTcCols * 8;
-                    const int n = rem >> 3, c = rem & 7;
-                    bv[j] = __ldg(reinterpret_cast<const float4*>((part ? Bl : Bh) + (size_t)n * p.k_pad + i * kTcK + 4 * c));
+            for (int j = 0; j < 10; ++j) {
+                const int idx = gtid + 128 * j;
+                const int part = idx >= kTcCols * 8, rem = idx - part * kTcCols * 8;
+                const int n = rem >> 3, c = rem & 7;
+                const float* src = (part ? Bl : Bh) + (size_t)n * p.k_pad + i * kTcK + 4 * c;
+                const uint32_t dst = base + s * kTcStageBytes + part * kTcBTile + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");               // this slab's inputs (not yet B')
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // ... of every thread of the group
+            // A': the products of this thread's samples, split, straight into tensor memory
+            const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + kTcA0 + 64 * s;
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) {
+                float4 zp2[2], zc2[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int off = gtid * 128 + (((2 * ss + h) ^ (gtid & 7)) << 4);
+                    zp2[h] = *reinterpret_cast<const float4*>(sin_ptr + off);
+                    zc2[h] = *reinterpret_cast<const float4*>(sin_ptr + kTcRows * 128 + off);
                 }
-            }
-            // A': the products of this thread's four samples, split, straight into tensor memory
-            uint32_t hi[8], lo[8];
+                uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 c = accelerated_product(rzp[j], rzc[j], pw);
-                tc_split(c.x, hi[2 * j], lo[2 * j]);
-                tc_split(-c.y, hi[2 * j + 1], lo[2 * j + 1]);
-            }
-            if (i + 1 < n_slabs) fetch(i + 1);
-            const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + kTcA0 + 64 * s + 8 * sub;
-            tc_st8(ta, hi);
-            tc_st8(ta + 32, lo);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int idx = ptid + 512 * j;
-                if (idx < 2 * kTcCols * 8) {
-                    const int part = idx >= kTcCols * 8, rem = idx - part * kTcCols * 8;
-                    const int n = rem >> 3, c = rem & 7;
-                    uint8_t* dst = sm + s * kTcStageBytes + part * kTcBTile + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4);
-                    *reinterpret_cast<float4*>(dst) = bv[j];
+                for (int j = 0; j < 4; ++j) {
+                    const float4 a = zp2[j >> 1], b = zc2[j >> 1];
+                    const float2 c = (j & 1) ? accelerated_product(make_float2(a.z, a.w), make_float2(b.z, b.w), pw)
+                                             : accelerated_product(make_float2(a.x, a.y), make_float2(b.x, b.y), pw);
+                    tc_split(c.x, hi[2 * j], lo[2 * j]);
+                    tc_split(-c.y, hi[2 * j + 1], lo[2 * j + 1]);
                 }
+                tc_st8(ta + 8 * ss, hi);
+                tc_st8(ta + 32 + 8 * ss, lo);
             }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // everyone has read the inputs: refill
+            if (i + kTcGroups < n_slabs) copy_inputs(i + kTcGroups);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");               // B' has landed (the refill may be in flight)
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of B' -> the MMA's async proxy
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(full(s));
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
