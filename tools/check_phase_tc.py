@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'vae-teb_b200'))
 import numpy as np
 
-CFGS = {'S': (4, 4, 16, 1000, 2, 3), 'H': (6, 8, 64, 4800, 2, 4)}
+CFGS = {'S': (4, 4, 16, 1000, 2, 3), 'odd': (4, 4, 16, 999, 2, 3), 'H': (6, 8, 64, 4800, 2, 4)}
 
 def child(tag, out):
     import torch

@@ -139,13 +139,14 @@ __device__ __forceinline__ uint64_t tc_b_desc(uint32_t smem_addr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 80
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcCols >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
 
-// TF32 head and tail of v.  cvt.rna.tf32.f32 (round to nearest, ties away) is "add half an ulp of the 13 dropped bits to
-// the magnitude, truncate"; as two integer instructions it runs on the ALU pipe instead of the 16-lane conversion unit,
-// which the sine and cosine of every product already occupy.
+// TF32 head and tail of v by truncation: head = the top 19 bits, tail = v - head (exact), of which the tensor core
+// again reads the top 19 bits.  v = head + tail holds exactly, the dropped tail bits are below 2^-20 |v| and the
+// product of the two tails (the term 3xTF32 leaves out) below 2^-21 |v b| -- fp32 class, in two instructions per
+// value on the ALU / FMA pipes (cvt.rna.tf32.f32 would occupy the 16-lane conversion unit that the sine and cosine
+// of every product already use).  B' is split with rounding on the host.
 __device__ __forceinline__ void tc_split(float v, uint32_t& hi, uint32_t& lo) {
-    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
-    const float r = v - __uint_as_float(hi);
-    lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const PairTcParams p) {
@@ -277,27 +278,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         const uint32_t sin_base = base + kTcStages * kTcStageBytes + grp * kTcInBytes;
         const uint8_t* sin_ptr = sm + kTcStages * kTcStageBytes + grp * kTcInBytes;
         const bool wide = (p.N & 1) == 0;                       // rows start on 16-byte boundaries
+        // thread (rb, c) of the group copies chunk c (16 bytes = 2 samples; 8 lanes cover a 128-byte line) of the rows
+        // rb, rb + 16, ..., rb + 112 of both arrays: the swizzle term (r & 7) = (rb & 7) and the sample offset are the
+        // thread's own constants
+        const int cc = gtid & 7, rb = gtid >> 3;
+        const uint32_t dst0 = sin_base + rb * 128 + ((cc ^ (rb & 7)) << 4);
         auto copy_inputs = [&](int i) {
-            const int t_slab = i * kTcSlabT;
             if (wide) {
-#pragma unroll 4
+                const int t = i * kTcSlabT + 2 * cc;
+                const int bytes_t = max(0, min(16, (p.N - t) * 8));
+#pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    const int idx = gtid + 128 * k;
-                    const int arr = idx >> 10, r = (idx >> 3) & 127, c = idx & 7;          // 16-byte chunk c of row r
-                    const long long off = s_off[arr * kTcRows + r];
-                    const int t = t_slab + 2 * c;
-                    const int bytes = off < 0 ? 0 : max(0, min(16, (p.N - t) * 8));
-                    const float2* src = (arr ? p.zc : p.zp) + (bytes ? off + t : 0);
-                    const uint32_t dst = sin_base + arr * (kTcRows * 128) + r * 128 + ((c ^ (r & 7)) << 4);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+                    const long long off = s_off[(k >> 3) * kTcRows + rb + 16 * (k & 7)];
+                    const int bytes = off < 0 ? 0 : bytes_t;
+                    const float2* src = ((k >> 3) ? p.zc : p.zp) + (bytes ? off + t : 0);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (k >> 3) * (kTcRows * 128) + (k & 7) * 2048),
+                                 "l"(src), "r"(bytes) : "memory");
                 }
             } else {
+                // odd N: rows start on 8-byte boundaries only; sample by sample (thread (rb16, c8): 16 lanes per line)
+                const int c8 = gtid & 15, r16 = gtid >> 4;
+                const int t = i * kTcSlabT + c8;
 #pragma unroll 4
                 for (int k = 0; k < 32; ++k) {
-                    const int idx = gtid + 128 * k;
-                    const int arr = idx >> 11, r = (idx >> 4) & 127, c8 = idx & 15;        // 8-byte sample c8 of row r
+                    const int arr = k >> 4, r = r16 + 8 * (k & 15);
                     const long long off = s_off[arr * kTcRows + r];
-                    const int t = t_slab + c8;
                     const int bytes = (off < 0 || t >= p.N) ? 0 : 8;
                     const float2* src = (arr ? p.zc : p.zp) + (bytes ? off + t : 0);
                     const uint32_t dst = sin_base + arr * (kTcRows * 128) + r * 128 + (((c8 >> 1) ^ (r & 7)) << 4) + (c8 & 1) * 8;
