@@ -32,7 +32,8 @@ constexpr int kTcCols = 80;           // output columns per CTA (UMMA N)
 constexpr int kTcSlabT = 16;          // time samples per slab
 constexpr int kTcK = 2 * kTcSlabT;    // K per slab (Re, -Im interleaved)
 constexpr int kTcStages = 4;
-constexpr int kTcDrain = 2;           // slabs per accumulator drain
+constexpr int kTcDrain = 2;           // slabs per accumulator drain: 24 tensor-core accumulations between fp32 adds (the TMEM
+                                      // accumulator truncates like the register one: with 4 the error against the mma.sync kernel doubles)
 constexpr int kTcEpiWarps = 4, kTcProdWarps = 16, kTcGroups = 4;   // producer groups of four warps (one per TMEM lane quarter)
 constexpr int kTcMmaWarp = kTcEpiWarps;                          // warp 4
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 1 + kTcProdWarps);   // 672: 96 registers per thread
@@ -40,7 +41,7 @@ constexpr int kTcBTile = kTcCols * 128;                         // bytes of one 
 constexpr int kTcStageBytes = 2 * kTcBTile;                      // head + tail
 constexpr int kTcInBytes = 2 * kTcRows * 128;                    // one group's input slab: 128 lines of (|z|, theta) + 128 of (re, im)
 constexpr int kTcOffBars = kTcStages * kTcStageBytes + kTcGroups * kTcInBytes;
-constexpr size_t kTcSmem = 1024 + (size_t)kTcOffBars + 256 + 2 * kTcRows * sizeof(long long);
+constexpr size_t kTcSmem = 1024 + (size_t)kTcOffBars + 256 + 2 * kTcRows * sizeof(int32_t);
 constexpr uint32_t kTcAcc0 = 0, kTcAcc1 = 128, kTcA0 = 256;      // TMEM columns; A' stage s: head at kTcA0 + 64 s, tail + 32
 
 struct PairTcParams {
@@ -85,15 +86,12 @@ __device__ __forceinline__ void tc_mbar_wait_relaxed(uint32_t bar, uint32_t pari
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"      // suspends up to the time hint
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(ns)
             : "memory");
-        if (!done) {
-            __nanosleep(ns);
-            if (spin > (1u << 22)) __trap();
-        }
+        if (!done && spin > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -157,7 +155,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     uint8_t* sm = tc_raw + (base - raw);
     const uint32_t bars = base + kTcOffBars;                         // full[4], empty[4], acc_full[2], acc_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kTcOffBars + 128);
-    long long* s_off = reinterpret_cast<long long*>(sm + kTcOffBars + 256);   // [2][128]: first sample of the rows' inputs, -1 = no row
+    int32_t* s_off = reinterpret_cast<int32_t*>(sm + kTcOffBars + 256);       // [2][128]: first sample of the rows' inputs (float2 units)
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (kTcStages + s); };
     auto acc_full = [&](int a) { return bars + 8u * (2 * kTcStages + a); };
@@ -177,13 +175,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     }
     if (tid < kTcRows) {
         const long long row = (long long)blockIdx.x * kTcRows + tid;
-        long long zp_off = -1, zc_off = -1;
+        // rows beyond the batch (last CTA) read the first row: their products are computed and never stored
+        int32_t zp_off = 0, zc_off = 0;
         if (row < p.rows) {
             const long long b = row / p.n_sel;
             const int sidx = (int)(row - b * p.n_sel);
             const int pair = p.subset ? p.subset[sidx] : sidx;
-            zp_off = (b * p.F + p.i_idx[pair]) * (long long)p.N;
-            zc_off = (b * p.F + p.j_idx[pair]) * (long long)p.N;
+            zp_off = (int32_t)((b * p.F + p.i_idx[pair]) * (long long)p.N);       // < 2^31: the workspace chunk is bounded
+            zc_off = (int32_t)((b * p.F + p.j_idx[pair]) * (long long)p.N);
         }
         s_off[tid] = zp_off;
         s_off[kTcRows + tid] = zc_off;
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         for (int i = 0; i < kTcCols; ++i) total[i] = 0.f;
         for (int g = 0; g < n_groups; ++g) {
             const int a = g & 1;
-            tc_mbar_wait_relaxed(acc_full(a), (g >> 1) & 1, 128);
+            tc_mbar_wait_relaxed(acc_full(a), (g >> 1) & 1, 4000);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (a ? kTcAcc1 : kTcAcc0);
 #pragma unroll
@@ -289,11 +288,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 const int bytes_t = max(0, min(16, (p.N - t) * 8));
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    const long long off = s_off[(k >> 3) * kTcRows + rb + 16 * (k & 7)];
-                    const int bytes = off < 0 ? 0 : bytes_t;
-                    const float2* src = ((k >> 3) ? p.zc : p.zp) + (bytes ? off + t : 0);
+                    const int off = s_off[(k >> 3) * kTcRows + rb + 16 * (k & 7)];
+                    const float2* src = ((k >> 3) ? p.zc : p.zp) + (bytes_t ? off + t : 0);
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (k >> 3) * (kTcRows * 128) + (k & 7) * 2048),
-                                 "l"(src), "r"(bytes) : "memory");
+                                 "l"(src), "r"(bytes_t) : "memory");
                 }
             } else {
                 // odd N: rows start on 8-byte boundaries only; sample by sample (thread (rb16, c8): 16 lanes per line)
@@ -302,8 +300,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
 #pragma unroll 4
                 for (int k = 0; k < 32; ++k) {
                     const int arr = k >> 4, r = r16 + 8 * (k & 15);
-                    const long long off = s_off[arr * kTcRows + r];
-                    const int bytes = (off < 0 || t >= p.N) ? 0 : 8;
+                    const int off = s_off[arr * kTcRows + r];
+                    const int bytes = t >= p.N ? 0 : 8;
                     const float2* src = (arr ? p.zc : p.zp) + (bytes ? off + t : 0);
                     const uint32_t dst = sin_base + arr * (kTcRows * 128) + r * 128 + (((c8 >> 1) ^ (r & 7)) << 4) + (c8 & 1) * 8;
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
@@ -316,7 +314,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         if (grp < n_slabs) copy_inputs(grp);
         for (int i = grp; i < n_slabs; i += kTcGroups) {
             const int s = i % kTcStages;
-            tc_mbar_wait_relaxed(empty(s), ((i / kTcStages) & 1) ^ 1, 32);
+            tc_mbar_wait_relaxed(empty(s), ((i / kTcStages) & 1) ^ 1, 1000);
             tc_fence_after();
             // B' slab: 2 x 80 rows x 8 chunks of 16 bytes, global -> swizzled shared memory, asynchronously
 #pragma unroll

@@ -930,7 +930,9 @@ static bool use_tcgen05_pairs() {
 }
 static void launch_pair_gemm(const tebscat_phase_plan* p, const PairParams& pp, cudaStream_t st) {
     const tebscat_phase_desc& d = p->desc;
-    if (use_tcgen05_pairs()) {
+    // (the tcgen05 kernel keeps 32-bit sample offsets into the workspace chunk)
+    const long long ws_elems = (pp.rows / pp.n_sel + 1) * (long long)pp.F * pp.N;
+    if (use_tcgen05_pairs() && ws_elems < (1LL << 31)) {
         PairTcParams q;
         q.zp = pp.zp; q.zc = pp.zc; q.Bs = p->d_Bs; q.i_idx = pp.i_idx; q.j_idx = pp.j_idx; q.powers = pp.powers;
         q.subset = pp.subset; q.out = pp.out; q.rows = pp.rows; q.n_sel = pp.n_sel; q.F = pp.F; q.N = pp.N;
