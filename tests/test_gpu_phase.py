@@ -232,3 +232,30 @@ def test_border_modes_in_transform_form(border, monkeypatch):
     check(ours, o.align_branches(x.numpy(), ours, mode='cross'), border)
     other = PhaseOracle(J, Q, T, N, 125)(x.numpy(), mode='cross')
     assert rel_l2(ours, other) > 1e-3                                     # and it is not the reflect result
+
+
+def test_tcgen05_and_mma_sync_kernels_of_the_dense_form_agree(monkeypatch):
+    """The dense form of stage B has two kernels: tcgen05 + TMEM (default; A' operand generated straight
+    into tensor memory, truncation split) and mma.sync (TEBSCAT_PHASE_MMA=sync; rounding split).  Same products, same
+    operator, both 3xTF32 with fp32 accumulation across slabs: fp32-class agreement.  Covers an odd length (the
+    8-byte input copy path), a ragged last CTA and a pair subset."""
+    from tebscat import KymatioPhaseScattering1D
+    from tebscat.synth import ctg_batch
+    monkeypatch.setenv('TEBSCAT_PHASE_FFT', '0')
+    for (J, Q, T, N, mo, B, sub) in ((6, 8, 64, 4800, 2, 3, None), (4, 4, 16, 999, 2, 5, None), (11, 4, 16, 5760, 1, 2, 7)):
+        m = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), max_order=mo)
+        x = ctg_batch(B, N, seed=23).cuda()
+        pairs = None
+        if sub:
+            pairs = torch.zeros(len(m.i_idx), dtype=torch.bool)
+            pairs[::sub] = True
+        outs = {}
+        for kern in ('tc', 'sync'):
+            monkeypatch.setenv('TEBSCAT_PHASE_MMA', kern)
+            outs[kern] = m(x, compute_phase=False, compute_cross_phase=True, phase_pairs=pairs)['cross_phase_corr'].cpu().numpy().astype(np.float64)
+        a, b = outs['sync'], outs['tc']
+        assert a.shape == b.shape and np.isfinite(b).all()
+        assert np.linalg.norm(a - b) / np.linalg.norm(a) < 5e-6
+        rows = np.linalg.norm(a, axis=-1)
+        strong = rows > 1e-4 * rows.max()
+        assert (np.linalg.norm(a - b, axis=-1)[strong] / rows[strong]).max() < 5e-5

@@ -922,11 +922,8 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
 
 // The dense form of stage B: tcgen05 + TMEM (phase_tc.cuh) unless TEBSCAT_PHASE_MMA=sync asks for the mma.sync kernel.
 static bool use_tcgen05_pairs() {
-    static const int v = [] {
-        const char* e = getenv("TEBSCAT_PHASE_MMA");
-        return (e && strcmp(e, "sync") == 0) ? 0 : 1;
-    }();
-    return v != 0;
+    const char* e = getenv("TEBSCAT_PHASE_MMA");          // read per call: the tests switch it
+    return !(e && strcmp(e, "sync") == 0);
 }
 static void launch_pair_gemm(const tebscat_phase_plan* p, const PairParams& pp, cudaStream_t st) {
     const tebscat_phase_desc& d = p->desc;
