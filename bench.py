@@ -141,7 +141,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from tebscat import Scattering1D, _lib
     from tebscat.synth import ctg_batch
-    from tebscat.sharding import max_over_ranks
+    from tebscat.sharding import bind_host_to_device, max_over_ranks
     import ctypes
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -152,6 +152,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
+    # host side of the end-to-end path: this rank's pinned buffers live on the GPU's own NUMA node
+    prev_affinity = bind_host_to_device(local) if world > 1 else None
     S = Scattering1D(J, N, Q, T=T).to(dev)
     n_sig = 2 * SAMPLES_PER_GPU
     # a few hundred distinct synthetic records tiled up to the batch (generation is host-side and slow)
@@ -199,6 +201,9 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_value = world * n_sig * args.steps / max_over_ranks(e2e_s, dev)
+    local_cpus = len(os.sched_getaffinity(0))
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)                       # the CPU baseline below uses every host core
 
     # ---- secondary: cross-channel phase scattering (BASELINE configs[2]) on a bounded batch ----
     phase = None
@@ -254,7 +259,8 @@ def run_gpu(args):
             'config': {'workload': 'Scattering1D J=6 Q=8 T=64 N=4800 orders 0-2, batch 8192 two-channel '
                                    'signals (16384 signals) per GPU -- BASELINE configs[1]',
                        'signals_per_gpu': n_sig, 'l2': 'inputs+outputs 934 MB per step, larger than L2',
-                       'parallelism': 'batch-sharded x%d, no collective' % world},
+                       'parallelism': 'batch-sharded x%d, no collective' % world,
+                       'host_binding': ('NUMA-local, %d CPUs per rank' % local_cpus) if prev_affinity is not None else 'none'},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': n_sig * N * 4,
                     'd2h_bytes_per_step': n_sig * C * n_out * 4},

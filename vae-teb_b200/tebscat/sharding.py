@@ -2,8 +2,28 @@
 (core/scattering1d.py:269-399 has no cross-batch op), so each rank transforms a contiguous
 slice of the batch with its own plan replica and there is no collective on the transform.
 ``torch.distributed`` is used only for barriers and for reducing timings."""
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def bind_host_to_device(device_index: int):
+    """Restrict the calling process to the CPUs NVML reports as local to the GPU (its NUMA node), so that the pinned
+    staging buffers allocated afterwards are node-local: with one rank per GPU every rank streams ~30 GB/s of host
+    memory through its own root complex instead of across the socket interconnect.  Returns the previous affinity
+    (to restore with os.sched_setaffinity) or None when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return before
+    except Exception:
+        return None
 
 
 def shard_range(n_items: int, rank: int, world: int):
