@@ -243,6 +243,28 @@ def run_gpu(args):
                                  'stage_b': 'transform form' if pmp._dev_plan(local).uses_fft_pairs else 'dense operator'}
         del pmp
 
+    # ---- secondary: backward pass on a bounded batch ---------------------------------
+    backward = None
+    if rank == 0 and not args.no_phase:
+        xg = x_dev[:1024].reshape(2048, N).clone().requires_grad_(True)
+        og, _ = S(xg)
+        wg = torch.ones_like(og)
+        og.backward(wg)                                               # builds the op-list plan, warms up
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(3):
+            xg.grad = None
+            og, _ = S(xg)
+            og.backward(wg)
+        b1.record()
+        torch.cuda.synchronize()
+        bms = b0.elapsed_time(b1) / 3
+        backward = {'metric': 'Scattering1D forward + backward signals/s (J=6,Q=8,N=4800)', 'value': 2048 / (bms * 1e-3),
+                    'unit': 'signals/s', 'batch': 2048, 'ms': bms,
+                    'note': 'forward = the fused launch, backward = recompute + transposed cascade (tebscat/large.py)'}
+        del xg, og, wg
+
     if rank == 0:
         hbm_peak, peak_src = peaks()
         kernel_ms = sum(per_launch_ms) / len(per_launch_ms)
@@ -281,6 +303,7 @@ def run_gpu(args):
             'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': '1024 CTG signals in batches of 64, %.1f s, torch-CPU port of the reference (oracle/scattering1d_torch_port.py)' % cpu_dt},
             'phase': phase,
+            'backward': backward,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

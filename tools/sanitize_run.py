@@ -16,6 +16,22 @@ if what == 'scat':
         f = S.forward_normalized(x, np.zeros(C), np.ones(C), trim=1)
         torch.cuda.synchronize()
         print('scat', J, N, Q, T, tuple(out.shape), tuple(f.shape), float(out.abs().sum()))
+elif what == 'backward':
+    for (J, N, Q, T, mo) in ((5, 700, 2, 8, 2), (4, 1000, 4, 16, 2)):
+        S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+        x = ctg_batch(2, N, seed=1).reshape(-1, N)[:3].cuda().requires_grad_(True)
+        out, _ = S(x)
+        out.sum().backward()
+        torch.cuda.synchronize()
+        print('backward', J, N, float(x.grad.abs().sum()))
+elif what == 'phase_tc':
+    os.environ['TEBSCAT_PHASE_FFT'] = '0'
+    for (J, Q, T, N) in ((4, 4, 16, 1000), (4, 4, 16, 999)):
+        m = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'))
+        x = ctg_batch(2, N, seed=2).cuda()
+        r = m(x, compute_phase=False, compute_cross_phase=True)
+        torch.cuda.synchronize()
+        print(what, N, float(r['cross_phase_corr'].abs().sum()))
 else:
     os.environ['TEBSCAT_PHASE_FFT'] = '1' if what == 'phase_fft' else '0'
     m = KymatioPhaseScattering1D(J=11, Q=4, T=16, shape=5760, device=torch.device('cuda'), max_order=1)
