@@ -82,6 +82,7 @@ class _ScatteringFunction(torch.autograd.Function):
         return module._forward_array(x2)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gS):
         (x2,) = ctx.saved_tensors
         return ctx.module._backward_array(x2, gS), None
