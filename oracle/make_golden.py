@@ -44,6 +44,7 @@ CONFIGS = {
     'S': (4, 4, 16, 1000, 2, 4),        # small ragged-length config
     'T': (5, 2, 8, 700, 2, 3),          # T < 2**J
     'O': (5, 4, 32, 1200, 2, 2, 1),     # oversampling = 1
+    'L': (6, 4, 64, 9000, 2, 1),        # padded length 2**14: the large-support level
 }
 
 
@@ -139,6 +140,9 @@ def phase_option_fixtures():
 if __name__ == '__main__':
     if sys.argv[1:] == ['phase-options']:
         phase_option_fixtures()
+        sys.exit(0)
+    if len(sys.argv) == 3 and sys.argv[1] == 'scat':
+        scat_fixture(sys.argv[2])
         sys.exit(0)
     for n in CONFIGS:
         scat_fixture(n)

@@ -10,7 +10,7 @@ from oracle import filters_oracle as fo
 from oracle.scattering1d_oracle import ScatteringOracle
 from oracle.phase_oracle import PhaseOracle
 
-SCAT = ['H', 'P', 'S', 'T', 'O']
+SCAT = ['H', 'P', 'S', 'T', 'O', 'L']
 
 
 def rel_l2(a, b, axis=None):
