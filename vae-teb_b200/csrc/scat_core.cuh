@@ -805,22 +805,24 @@ TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task&
 // stage A also F.pad(..., 'constant', 0) and F.pad(..., 'circular') (kymatio_phase_scattering.py:162-173)
 TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
     const int Np = 1 << c.log2_Np;
+    const int N = c.N, pad_left = c.pad_left, border = c.border;
+    const float* x = c.x;
     for (int i0 = lt; i0 < Np; i0 += 8 * t.nt) {
         float v[8];
         TEB_UNROLL for (int j = 0; j < 8; ++j) {
             const int i = i0 + j * t.nt;
-            int r = i - c.pad_left;
+            int r = i - pad_left;
             bool inside = i < Np;
-            if (c.border == BORDER_REFLECT) {
+            if (border == BORDER_REFLECT) {
                 if (r < 0) r = -r;
-                if (r >= c.N) r = 2 * (c.N - 1) - r;
-            } else if (c.border == BORDER_CIRCULAR) {
-                if (r < 0) r += c.N;
-                if (r >= c.N) r -= c.N;
+                if (r >= N) r = 2 * (N - 1) - r;
+            } else if (border == BORDER_CIRCULAR) {
+                if (r < 0) r += N;
+                if (r >= N) r -= N;
             } else {
-                inside = inside && r >= 0 && r < c.N;
+                inside = inside && r >= 0 && r < N;
             }
-            v[j] = inside ? TEB_LDG(c.x + r) : 0.f;
+            v[j] = inside ? TEB_LDG(x + r) : 0.f;
         }
         TEB_UNROLL for (int j = 0; j < 8; ++j) {
             const int i = i0 + j * t.nt;
@@ -850,36 +852,38 @@ TEB_D float2 accelerated_product(float2 pz, float2 zj, float power) {
 }
 
 TEB_D void loadpair_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
+    // (the context lives in shared memory like S: read its fields once, the stores below would force reloads)
+    const int N = c.N, pad_left = c.pad_left, border = c.border;
     const int Np = 1 << c.log2_Np;
-    const int pad_right = Np - c.N - c.pad_left;
+    const int pad_right = Np - N - pad_left;
     const float2* zp = c.pr_zp[t.b];
     const float2* zc = c.pr_zc[t.b];
     const float pw = c.pr_pw[t.b];
-    for (int t0 = lt; t0 < c.N; t0 += 4 * t.nt) {
+    for (int t0 = lt; t0 < N; t0 += 4 * t.nt) {
         float2 a[4], b[4];
         TEB_UNROLL for (int j = 0; j < 4; ++j) {
             const int tt = t0 + j * t.nt;
-            a[j] = tt < c.N ? TEB_LDG(zp + tt) : make_float2(0.f, 0.f);
-            b[j] = tt < c.N ? TEB_LDG(zc + tt) : make_float2(0.f, 0.f);
+            a[j] = tt < N ? TEB_LDG(zp + tt) : make_float2(0.f, 0.f);
+            b[j] = tt < N ? TEB_LDG(zc + tt) : make_float2(0.f, 0.f);
         }
         TEB_UNROLL for (int j = 0; j < 4; ++j) {
             const int tt = t0 + j * t.nt;
-            if (tt >= c.N) continue;
+            if (tt >= N) continue;
             const float2 v = accelerated_product(a[j], b[j], pw);
-            S[swz(t.a + c.pad_left + tt)] = v;
-            if (c.border == BORDER_REFLECT) {
-                if (tt >= 1 && tt <= c.pad_left) S[swz(t.a + c.pad_left - tt)] = v;                       // left mirror
-                if (tt <= c.N - 2 && tt >= c.N - 1 - pad_right) S[swz(t.a + c.pad_left + 2 * (c.N - 1) - tt)] = v;   // right mirror
-            } else if (c.border == BORDER_CIRCULAR) {                       // padded[i] = c[(i - pad_left) mod N], pad <= N
-                if (tt >= c.N - c.pad_left) S[swz(t.a + c.pad_left + tt - c.N)] = v;
-                if (tt < pad_right) S[swz(t.a + c.pad_left + tt + c.N)] = v;
+            S[swz(t.a + pad_left + tt)] = v;
+            if (border == BORDER_REFLECT) {
+                if (tt >= 1 && tt <= pad_left) S[swz(t.a + pad_left - tt)] = v;                       // left mirror
+                if (tt <= N - 2 && tt >= N - 1 - pad_right) S[swz(t.a + pad_left + 2 * (N - 1) - tt)] = v;   // right mirror
+            } else if (border == BORDER_CIRCULAR) {                         // padded[i] = c[(i - pad_left) mod N], pad <= N
+                if (tt >= N - pad_left) S[swz(t.a + pad_left + tt - N)] = v;
+                if (tt < pad_right) S[swz(t.a + pad_left + tt + N)] = v;
             }
         }
     }
-    if (c.border == BORDER_CONSTANT) {                                      // zeros on both sides
+    if (border == BORDER_CONSTANT) {                                        // zeros on both sides
         const float2 z = make_float2(0.f, 0.f);
-        for (int i = lt; i < c.pad_left; i += t.nt) S[swz(t.a + i)] = z;
-        for (int i = lt; i < pad_right; i += t.nt) S[swz(t.a + c.pad_left + c.N + i)] = z;
+        for (int i = lt; i < pad_left; i += t.nt) S[swz(t.a + i)] = z;
+        for (int i = lt; i < pad_right; i += t.nt) S[swz(t.a + pad_left + N + i)] = z;
     }
 }
 
