@@ -352,15 +352,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 tc_st8(ta + 8 * ss, hi);
                 tc_st8(ta + 32 + 8 * ss, lo);
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // everyone has read the inputs: refill
-            if (i + kTcGroups < n_slabs) copy_inputs(i + kTcGroups);
-            else asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");               // B' has landed (the refill may be in flight)
+            // hand the slab to the tensor core first ...
+            asm volatile("cp.async.wait_group 0;" ::: "memory");               // B' has landed
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of B' -> the MMA's async proxy
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(full(s));
+            // ... then refill the inputs (off the producer -> MMA critical path): everyone has read them
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            if (i + kTcGroups < n_slabs) copy_inputs(i + kTcGroups);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
