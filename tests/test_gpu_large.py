@@ -77,3 +77,19 @@ def test_large_support_matches_the_live_reference(golden_dir):
     err = np.linalg.norm(out - ref, axis=-1) / np.linalg.norm(ref, axis=-1)
     assert err[1].max() < 1e-5, err[1].max()
     assert np.linalg.norm(out[0] - ref[0]) / np.linalg.norm(ref[0]) < 2e-6
+
+
+def test_large_support_output_conventions():
+    """out_type='list' and vectorize=False at a padded length of 2^14: views of the same array (core :379-385)."""
+    import warnings
+    from tebscat import Scattering1D
+    N = 9000
+    x = torch.randn(2, N, generator=torch.Generator().manual_seed(3)).cuda()
+    ref, _ = Scattering1D(6, N, 4, T=64).cuda()(x)
+    lst, _ = Scattering1D(6, N, 4, T=64, out_type='list').cuda()(x)
+    assert len(lst) == ref.shape[1]
+    assert all(torch.equal(c['coef'], ref[:, i]) for i, c in enumerate(lst))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', DeprecationWarning)
+        dct, _ = Scattering1D(6, N, 4, T=64, vectorize=False).cuda()(x)
+    assert dct[()].shape == (2, 1, ref.shape[-1]) and torch.equal(dct[()][:, 0], ref[:, 0])

@@ -241,8 +241,6 @@ class Scattering1D(nn.Module):
             if needs_grad:
                 raise NotImplementedError('the backward pass is built for average=True')
             return self._scattering_unaveraged(x2, batch_shape)
-        if self.J_pad > LOG2_NP_MAX and (self.out_type != 'array' or not self.vectorize):
-            raise NotImplementedError('the large-support level produces the array output only')
         # differentiable like the reference's torch backend (ModulusStable, kymatio/backend/torch_backend.py:5-96):
         # the forward is the same fused launch, the backward the transposed cascade of tebscat/large.py
         S = _ScatteringFunction.apply(x2, self) if needs_grad else self._forward_array(x2)
