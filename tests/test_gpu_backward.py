@@ -106,3 +106,24 @@ def test_unaveraged_backward_is_refused_loudly():
     S = Scattering1D(4, 1000, 4, T=16, average=False, out_type='list').cuda()
     with pytest.raises(NotImplementedError):
         S(torch.randn(1, 1000, device='cuda', requires_grad=True))
+
+
+def test_adjoint_entry_points_reject_bad_requests():
+    """Status codes, never exceptions or crashes, across the C ABI (include/tebscat.h conventions)."""
+    import ctypes
+    from tebscat import _lib
+    lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    assert lib.tebscat_large_create(0, ctypes.byref(ctx)) == 0
+    buf = torch.zeros(1 << 12, device='cuda')
+    vp, st = ctypes.c_void_p, ctypes.c_void_p(0)
+    ptr = vp(buf.data_ptr())
+    assert lib.tebscat_large_unfold(ctx, ptr, ptr, ptr, 1, 8, 9, 0, 0, 0, 0, st) == _lib.TEBSCAT_EINVAL         # logk > log_src
+    assert lib.tebscat_large_unfold(ctx, ptr, ptr, ptr, 1, 8, 4, 0, 2, 0, 0, st) == _lib.TEBSCAT_EINVAL         # empty chunk mask
+    assert lib.tebscat_large_unstore(ctx, ptr, 1, 6, 60, 10, 3, 0, ptr, st) == _lib.TEBSCAT_EINVAL              # crop beyond the signal
+    assert lib.tebscat_large_unstore(ctx, ptr, 1, 6, 0, 10, 3, 3, ptr, st) == _lib.TEBSCAT_EINVAL               # channel out of range
+    assert lib.tebscat_large_pad_adjoint(ctx, ptr, 1, 100, 100, 8, ptr, st) == _lib.TEBSCAT_EINVAL              # pad >= N
+    assert lib.tebscat_large_modulus_backward(ctx, None, ptr, 16, st) == _lib.TEBSCAT_EINVAL
+    assert lib.tebscat_large_modulus_to(ctx, ptr, ptr, 0, st) == _lib.TEBSCAT_EINVAL
+    assert b'padding' in lib.tebscat_last_error() or len(lib.tebscat_last_error()) > 0
+    lib.tebscat_large_destroy(ctx)

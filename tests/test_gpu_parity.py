@@ -211,3 +211,27 @@ def test_relaxed_and_chained_schedule_is_bitwise_equal_to_fully_barriered(monkey
     safe = Scattering1D(J, N, Q, T=T).cuda()
     assert safe._schedule().stats['n_relaxed'] == 0 and safe._schedule().stats['n_steps'] > fast._schedule().stats['n_steps']
     assert torch.equal(safe(x)[0], ref)
+
+
+def test_forward_is_reentrant_across_host_threads_and_streams():
+    """SURVEY 8b 'Threading': a plan is immutable after creation, so forward calls from several host threads on
+    different streams must not interfere."""
+    import threading
+    from tebscat import Scattering1D
+    S = Scattering1D(6, 4800, 8, T=64).cuda()
+    xs = [torch.randn(300 + 50 * i, 4800, generator=torch.Generator().manual_seed(i)).cuda() for i in range(4)]
+    serial = [S(x)[0].clone() for x in xs]
+    torch.cuda.synchronize()
+    out = [None] * 4
+
+    def work(i):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            for _ in range(3):
+                out[i] = S(xs[i])[0]
+        st.synchronize()
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for a, b in zip(serial, out):
+        assert torch.equal(a, b)

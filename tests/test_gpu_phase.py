@@ -259,3 +259,22 @@ def test_tcgen05_and_mma_sync_kernels_of_the_dense_form_agree(monkeypatch):
         rows = np.linalg.norm(a, axis=-1)
         strong = rows > 1e-4 * rows.max()
         assert (np.linalg.norm(a - b, axis=-1)[strong] / rows[strong]).max() < 5e-5
+
+
+def test_large_batch_phase_properties():
+    """BASELINE configs[2] shape at a bounded batch (2048 x 741 pairs x 75 = 455 MB of output, seven workspace chunks):
+    every sample of the big batch equals the same sample computed on its own (rows are independent, chunk and CTA
+    boundaries do not matter), auto-correlations (i == j, power 1) are non-negative up to rounding, all finite."""
+    m = module_of('H')
+    from tebscat.synth import ctg_batch
+    B = 2048
+    x = ctg_batch(64, 4800, seed=31).repeat(B // 64, 1, 1)
+    x = (x + 0.01 * torch.randn(x.shape, generator=torch.Generator().manual_seed(32))).cuda().contiguous()
+    big = m(x, compute_phase=False, compute_cross_phase=True)['cross_phase_corr']
+    assert big.shape == (B, 741, 75) and bool(torch.isfinite(big).all())
+    for k in (0, 295, 296, 1023, 2047):                       # both sides of a workspace-chunk boundary, the last sample
+        one = m(x[k:k + 1], compute_phase=False, compute_cross_phase=True)['cross_phase_corr']
+        assert torch.equal(one[0], big[k]), k
+    within = m(x[:512], compute_phase=True, phase_channels=[0])['phase_corr']
+    auto = within[:, m.autoc_idx.to(within.device)]
+    assert float(auto.min()) > -1e-4 * float(auto.abs().max())
