@@ -395,9 +395,10 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     p->n_sms = prop.multiProcessorCount;
     p->smem_bytes = ((size_t)desc->smem_complex + kTwAP + kTwBP) * sizeof(float2);
     if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+        const size_t wanted = p->smem_bytes;
         delete p;
         return fail(TEBSCAT_EUNSUPPORTED, "schedule needs %zu B of shared memory, device offers %zu",
-                    p->smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
+                    wanted, (size_t)prop.sharedMemPerBlockOptin);
     }
     std::vector<float2> tw(kTwAP + kTwBP, make_float2(0.f, 0.f));
     const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
