@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -389,14 +390,15 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
 
-    tebscat_plan* p = new tebscat_plan();
+    // (owned by a guard until the plan is complete: a failing CUDA call below must not leak it)
+    std::unique_ptr<tebscat_plan, void (*)(tebscat_plan*)> guard(new tebscat_plan(), tebscat_plan_destroy);
+    tebscat_plan* p = guard.get();
     p->desc = *desc;
     p->device = device;
     p->n_sms = prop.multiProcessorCount;
     p->smem_bytes = ((size_t)desc->smem_complex + kTwAP + kTwBP) * sizeof(float2);
     if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
         const size_t wanted = p->smem_bytes;
-        delete p;
         return fail(TEBSCAT_EUNSUPPORTED, "schedule needs %zu B of shared memory, device offers %zu",
                     wanted, (size_t)prop.sharedMemPerBlockOptin);
     }
@@ -485,7 +487,7 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     k.gbuf = nullptr;
     k.g_total = 0;
     k.g_slots = 0;
-    *out = p;
+    *out = guard.release();
     return TEBSCAT_OK;
 }
 
@@ -859,7 +861,11 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
             return fail(TEBSCAT_EINVAL, "pair %d references a filter outside [0,%d)", k, d->n_filters);
     CU(cudaSetDevice(stage_a->device));
     CU(cudaFuncSetAttribute(phase_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
-    tebscat_phase_plan* p = new tebscat_phase_plan();
+    std::unique_ptr<tebscat_phase_plan, void (*)(tebscat_phase_plan*)> guard(new tebscat_phase_plan(), [](tebscat_phase_plan* q) {
+        q->stage_a = nullptr;                    // on failure the caller keeps the stage-A plan
+        tebscat_phase_plan_destroy(q);
+    });
+    tebscat_phase_plan* p = guard.get();
     p->desc = *d;
     p->stage_a = stage_a;
     p->device = stage_a->device;
@@ -899,7 +905,7 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
     CU(cudaMemcpy(p->d_i, i_idx, d->n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_j, j_idx, d->n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_pw, powers, d->n_pairs * sizeof(float), cudaMemcpyHostToDevice));
-    *out = p;
+    *out = guard.release();
     return TEBSCAT_OK;
 }
 
@@ -1182,7 +1188,8 @@ extern "C" int tebscat_large_create(int device, tebscat_large** out) {
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    tebscat_large* g = new tebscat_large();
+    std::unique_ptr<tebscat_large, void (*)(tebscat_large*)> guard(new tebscat_large(), tebscat_large_destroy);
+    tebscat_large* g = guard.get();
     g->device = device;
     g->n_sms = prop.multiProcessorCount;
     for (int n = kLog2TwMax + 1; n <= kLargeMaxLog2; ++n) {
@@ -1193,7 +1200,7 @@ extern "C" int tebscat_large_create(int device, tebscat_large** out) {
         CU(cudaMalloc(&g->d_tw[n], L * sizeof(float2)));
         CU(cudaMemcpy(g->d_tw[n], tw.data(), L * sizeof(float2), cudaMemcpyHostToDevice));
     }
-    *out = g;
+    *out = guard.release();
     return TEBSCAT_OK;
 }
 
