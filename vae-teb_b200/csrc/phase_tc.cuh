@@ -8,19 +8,18 @@
 // B'[2t, n] = Re G[t, n], B'[2t+1, n] = Im G[t, n], in 3xTF32 (fp32-class accuracy): A' = Ah + Al, B' = Bh + Bl,
 // out ~= Ah Bh + Al Bh + Ah Bl.
 //
-// One CTA = 128 rows x 80 columns, one CTA per SM, 22 warps:
+// One CTA = 128 rows x 80 columns, one CTA per SM, 21 warps:
 //   * 16 PRODUCER warps in four groups compute the rows' products where they are consumed -- group j owns the slabs
 //     i = j (mod 4), a thread one row (= one TMEM lane) of such a slab of 16 samples -- split them into TF32 head and
 //     tail and write them straight into TENSOR MEMORY with tcgen05.st: the A' operand never touches shared memory
-//     (tcgen05.mma with A from TMEM);
-//   * ONE thread of the LOADER warp brings the slab of B' (pre-split and pre-swizzled on the host side of the plan:
-//     K-major, 128-byte swizzle, stored in tile order) with one bulk copy (cp.async.bulk, mbarrier complete_tx);
+//     (tcgen05.mma with A from TMEM).  The group also copies its slab of B' (pre-split on the host side of the plan,
+//     K-major, 128-byte swizzle) into shared memory with cp.async;
 //   * ONE thread of the MMA warp issues tcgen05.mma.kind::tf32 (M = 128, N = 80, K = 8): 12 per slab, accumulating in
 //     TMEM; tcgen05.commit releases the slab's stage and hands finished accumulators to
 //   * 4 EPILOGUE warps, which drain an accumulator every kTcDrain slabs with tcgen05.ld and add it to running sums
 //     in fp32 registers (a tensor-core accumulator that runs over all K = 2N = 9600 would carry its truncation bias,
 //     see the mma.sync kernel), double-buffered so the drain overlaps the next group's MMAs.
-// mbarriers: full[s] (producers -> MMA), full_b[s] (bulk copy -> MMA), empty[s] (MMA -> producers, loader), acc_full[a] (MMA -> epilogue),
+// mbarriers: full[s] (producers -> MMA), empty[s] (MMA -> producers), acc_full[a] (MMA -> epilogue),
 // acc_empty[a] (epilogue -> MMA).  TMEM (512 columns): accumulators at 0 and 128, A' stages from 256.
 #pragma once
 #include <cuda_runtime.h>
@@ -37,8 +36,7 @@ constexpr int kTcDrain = 2;           // slabs per accumulator drain: 24 tensor-
                                       // accumulator truncates like the register one: with 4 the error against the mma.sync kernel doubles)
 constexpr int kTcEpiWarps = 4, kTcProdWarps = 16, kTcGroups = 4;   // producer groups of four warps (one per TMEM lane quarter)
 constexpr int kTcMmaWarp = kTcEpiWarps;                          // warp 4
-constexpr int kTcLoadWarp = kTcEpiWarps + 1;                     // warp 5: bulk copies of B'
-constexpr int kTcThreads = 32 * (kTcEpiWarps + 2 + kTcProdWarps);   // 704
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 1 + kTcProdWarps);   // 672: 96 registers per thread
 constexpr int kTcBTile = kTcCols * 128;                         // bytes of one B' tile (80 rows x 32 tf32)
 constexpr int kTcStageBytes = 2 * kTcBTile;                      // head + tail
 constexpr int kTcInBytes = 2 * kTcRows * 128;                    // one group's input slab: 128 lines of (|z|, theta) + 128 of (re, im)
@@ -49,8 +47,7 @@ constexpr uint32_t kTcAcc0 = 0, kTcAcc1 = 128, kTcA0 = 256;      // TMEM columns
 struct PairTcParams {
     const float2* zp;
     const float2* zc;
-    const float* Bs;            // [column tile][slab][head, tail] x one shared-memory tile (80 rows x 128 bytes, swizzled) of TF32
-                                // values in fp32 containers: each tile is one bulk copy
+    const float* Bs;            // [2 (head, tail)][n_cols_pad][k_pad] TF32 values in fp32 containers, k_pad = 32 n_slabs
     const int32_t* i_idx;
     const int32_t* j_idx;
     const float* powers;
@@ -157,20 +154,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = tc_raw + (base - raw);
     const uint32_t bars = base + kTcOffBars;                         // full[4], empty[4], acc_full[2], acc_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kTcOffBars + 192);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kTcOffBars + 128);
     int32_t* s_off = reinterpret_cast<int32_t*>(sm + kTcOffBars + 256);       // [2][128]: first sample of the rows' inputs (float2 units)
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (kTcStages + s); };
     auto acc_full = [&](int a) { return bars + 8u * (2 * kTcStages + a); };
     auto acc_empty = [&](int a) { return bars + 8u * (2 * kTcStages + 2 + a); };
-    auto full_b = [&](int s) { return bars + 8u * (2 * kTcStages + 4 + s); };      // B' tiles landed (bulk copy, complete_tx)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < kTcStages; ++s) {
             tc_mbar_init(full(s), kTcProdWarps / kTcGroups);
             tc_mbar_init(empty(s), 1);
-            tc_mbar_init(full_b(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             tc_mbar_init(acc_full(a), 1);
@@ -246,7 +241,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                     tc_mbar_wait(acc_empty(a), ((g >> 1) & 1) ^ 1);          // passes at once for the first two groups
                     tc_fence_after();
                 }
-                tc_mbar_wait(full_b(s), (i / kTcStages) & 1);
                 tc_mbar_wait(full(s), (i / kTcStages) & 1);
                 tc_fence_after();
                 const uint32_t d = tmem + (a ? kTcAcc1 : kTcAcc0);
@@ -264,20 +258,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
             }
         }
         __syncwarp();
-    } else if (warp == kTcLoadWarp) {
-        // ===== B' loader: one thread, two bulk copies per slab (the host stores B' in tile order) =====
-        if (lane == 0) {
-            const float* tiles = p.Bs + (size_t)blockIdx.y * p.n_slabs * 2 * (kTcBTile / 4);
-            for (int i = 0; i < n_slabs; ++i) {
-                const int s = i % kTcStages;
-                tc_mbar_wait_relaxed(empty(s), ((i / kTcStages) & 1) ^ 1, 1000);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_b(s)), "r"(kTcStageBytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(base + s * kTcStageBytes), "l"(tiles + (size_t)i * 2 * (kTcBTile / 4)), "r"(kTcStageBytes), "r"(full_b(s))
-                             : "memory");
-            }
-        }
-        __syncwarp();
     } else {
         // ===== producers: four groups of four warps; group j owns the slabs i = j (mod 4), a thread the 16 samples of
         // row 32 q + lane in such a slab.  The slab's inputs -- one 128-byte line of (|z|, theta) and one of (re, im) per
@@ -285,7 +265,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         // reading its own row straight from global memory costs one L1 wavefront per lane, and the L1 data pipe was
         // the limit), swizzled so that the per-row 128-bit reads are conflict free.  While one group waits (its copies,
         // its stage, the tensor-memory stores), the other three compute. =====
-        const int pw_ = warp - (kTcLoadWarp + 1);
+        const int pw_ = warp - (kTcMmaWarp + 1);
         const int q = warp & 3, grp = pw_ >> 2;
         const int gtid = q * 32 + lane;                         // 0..127 inside the group = the thread's row
         const long long row = row0 + gtid;
@@ -329,12 +309,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        const float* Bh = p.Bs + (size_t)col0 * p.k_pad;
+        const float* Bl = p.Bs + ((size_t)p.n_cols_pad + col0) * p.k_pad;
         if (grp < n_slabs) copy_inputs(grp);
         for (int i = grp; i < n_slabs; i += kTcGroups) {
             const int s = i % kTcStages;
             tc_mbar_wait_relaxed(empty(s), ((i / kTcStages) & 1) ^ 1, 1000);
             tc_fence_after();
-            asm volatile("cp.async.wait_group 0;" ::: "memory");               // this slab's inputs
+            // B' slab: 2 x 80 rows x 8 chunks of 16 bytes, global -> swizzled shared memory, asynchronously
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                const int idx = gtid + 128 * j;
+                const int part = idx >= kTcCols * 8, rem = idx - part * kTcCols * 8;
+                const int n = rem >> 3, c = rem & 7;
+                const float* src = (part ? Bl : Bh) + (size_t)n * p.k_pad + i * kTcK + 4 * c;
+                const uint32_t dst = base + s * kTcStageBytes + part * kTcBTile + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");               // this slab's inputs (not yet B')
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // ... of every thread of the group
             // A': the products of this thread's samples, split, straight into tensor memory
             const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + kTcA0 + 64 * s;
@@ -360,8 +353,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 tc_st8(ta + 32 + 8 * ss, lo);
             }
             // hand the slab to the tensor core first ...
+            asm volatile("cp.async.wait_group 0;" ::: "memory");               // B' has landed
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of B' -> the MMA's async proxy
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(full(s));
             // ... then refill the inputs (off the producer -> MMA critical path): everyone has read them

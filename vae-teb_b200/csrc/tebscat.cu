@@ -875,11 +875,8 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
     {   // B'[n][2t + c] = G[t][n][c], split into TF32 head and tail (round to nearest, ties away, like cvt.rna.tf32.f32)
         p->n_slabs = (d->N + kTcSlabT - 1) / kTcSlabT;
         p->k_pad = p->n_slabs * kTcK;
-        // Laid out as the kernel's shared-memory tiles, ready for one bulk copy each: [column tile][slab][head, tail]
-        // x (80 rows x 128 bytes, K-major, 16-byte chunk c of row n at (n/8) 1024 + (n%8) 128 + ((c ^ n%8) 16))
-        const int n_tiles = d->n_cols_pad / kTcCols;
-        const size_t tile_f = (size_t)kTcBTile / sizeof(float);
-        std::vector<float> bs((size_t)n_tiles * p->n_slabs * 2 * tile_f, 0.f);
+        const size_t per = (size_t)d->n_cols_pad * p->k_pad;
+        std::vector<float> bs(2 * per, 0.f);
         auto rna = [](float v) {
             uint32_t u;
             memcpy(&u, &v, 4);
@@ -893,11 +890,8 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
                 for (int c = 0; c < 2; ++c) {
                     const float v = G_host[((size_t)t * d->n_cols_pad + n) * 2 + c];
                     const float hi = rna(v);
-                    const int tile = n / kTcCols, nn = n % kTcCols, slab = t / kTcSlabT, k = 2 * (t % kTcSlabT) + c;
-                    const size_t in_tile = (size_t)(nn >> 3) * 256 + (size_t)(nn & 7) * 32 + (size_t)(((k >> 2) ^ (nn & 7)) << 2) + (k & 3);
-                    const size_t base = ((size_t)tile * p->n_slabs + slab) * 2 * tile_f;
-                    bs[base + in_tile] = hi;
-                    bs[base + tile_f + in_tile] = rna(v - hi);
+                    bs[(size_t)n * p->k_pad + 2 * t + c] = hi;
+                    bs[per + (size_t)n * p->k_pad + 2 * t + c] = rna(v - hi);
                 }
         CU(cudaMalloc(&p->d_Bs, bs.size() * sizeof(float)));
         CU(cudaMemcpy(p->d_Bs, bs.data(), bs.size() * sizeof(float), cudaMemcpyHostToDevice));
