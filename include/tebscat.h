@@ -197,6 +197,16 @@ int tebscat_large_modulus(tebscat_large* ctx, float* buf_dev, int64_t n_complex,
 int tebscat_large_store(tebscat_large* ctx, const float* buf_dev, int64_t B, int log_len, int i0, int n_out, int n_paths,
                         int channel, float* out_dev, void* stream);
 
+/* A whole leaf in one launch: phi multiply + periodise (as tebscat_large_mulfold) down to 2^lf = 2^(log_src - logk)
+ * <= 1024 bins -> inverse transform -> samples [i0, i0 + n_out) -> channel (core/scattering1d.py:287-292, :320-327,
+ * :358-364), and its adjoint for the backward pass (gsrc (+)= ...). */
+int tebscat_large_leaf(tebscat_large* ctx, const float* src_dev, const float* filt_dev, int64_t B, int log_src, int logk,
+                       uint32_t chunk_mask, int log_chunk, int scale_exp, int i0, int n_out, int n_paths, int channel,
+                       float* out_dev, void* stream);
+int tebscat_large_leaf_adjoint(tebscat_large* ctx, const float* gout_dev, const float* filt_dev, int64_t B, int log_src, int logk,
+                               uint32_t chunk_mask, int log_chunk, int scale_exp, int i0, int n_out, int n_paths, int channel,
+                               float* gsrc_dev, int accumulate, void* stream);
+
 /* ---- backward pass: the reference is differentiable through torch autograd with ModulusStable
  * (kymatio/backend/torch_backend.py:5-96).  Adjoints of the ops above; tebscat/large.py walks the cascade backwards. */
 /* dst = (|src|, 0), out of place (the pre-modulus signal stays available for the backward of the modulus) */

@@ -1528,6 +1528,151 @@ extern "C" int tebscat_large_store(tebscat_large* g, const float* buf_dev, int64
     return TEBSCAT_OK;
 }
 
+// ---- fused leaves ---------------------------------------------------------------------------------------------------
+// A leaf of the cascade (core/scattering1d.py:287-292 / :320-327 / :358-364) is "phi multiply + periodise down to
+// 2^lf bins -> inverse transform of 2^lf samples -> unpad -> channel": three launches and two round trips of a tiny
+// buffer in the op-by-op form.  Here one block does it per signal: the periodised spectrum (<= 1024 bins) lives in
+// shared memory, the transform is a radix-2 decimation-in-time pass sequence (bit-reversed in, natural out, twiddles
+// from sincospif), and the adjoint kernel runs the same steps transposed (decimation in frequency, natural in,
+// bit-reversed out) for the backward pass.
+constexpr int kLeafMaxLog2 = 10;
+
+__global__ void __launch_bounds__(256) g_leaf_kernel(const float2* __restrict__ src, const float* __restrict__ f, float* __restrict__ out,
+                                                     long long B, int log_src, int logk, unsigned mask, int logcw, float scale, int lf,
+                                                     int i0, int n_out, int n_paths, int channel) {
+    __shared__ float2 buf[1 << kLeafMaxLog2];
+    const int M = 1 << lf;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        const float2* sb = src + (b << log_src);
+        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+            const float2* s = sb + ((long long)m << logk);
+            const float* ff = f + ((long long)m << logk);
+            float ax = 0.f, ay = 0.f;
+            if (logk < 2) {
+                for (int t = 0; t < (1 << logk); ++t) {
+                    const float2 z = s[t];
+                    const float w = __ldg(ff + t);
+                    ax = fmaf(z.x, w, ax);
+                    ay = fmaf(z.y, w, ay);
+                }
+            } else {
+                unsigned rest = mask;
+                while (rest) {
+                    const int i_chunk = (__ffs(rest) - 1) << logcw;
+                    rest &= rest - 1;
+                    for (int t = i_chunk; t < i_chunk + (1 << logcw); t += 4) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(ff + t));
+                        const float2 z0 = s[t], z1 = s[t + 1], z2 = s[t + 2], z3 = s[t + 3];
+                        ax = fmaf(z0.x, w.x, ax); ay = fmaf(z0.y, w.x, ay);
+                        ax = fmaf(z1.x, w.y, ax); ay = fmaf(z1.y, w.y, ay);
+                        ax = fmaf(z2.x, w.z, ax); ay = fmaf(z2.y, w.z, ay);
+                        ax = fmaf(z3.x, w.w, ax); ay = fmaf(z3.y, w.w, ay);
+                    }
+                }
+            }
+            buf[m] = make_float2(ax * scale, ay * scale);
+        }
+        __syncthreads();
+        for (int st = 0; st < lf; ++st) {                      // decimation in time: bit-reversed -> natural, e^{+i...}
+            const int half = 1 << st;
+            for (int j = threadIdx.x; j < (M >> 1); j += blockDim.x) {
+                const int pos = j & (half - 1), lo = ((j >> st) << (st + 1)) + pos, hi = lo + half;
+                float sn, cs;
+                sincospif((float)pos / (float)half, &sn, &cs);
+                const float2 a = buf[lo], z = buf[hi];
+                const float2 w = make_float2(fmaf(z.x, cs, -z.y * sn), fmaf(z.x, sn, z.y * cs));
+                buf[lo] = make_float2(a.x + w.x, a.y + w.y);
+                buf[hi] = make_float2(a.x - w.x, a.y - w.y);
+            }
+            __syncthreads();
+        }
+        for (int n = threadIdx.x; n < n_out; n += blockDim.x) out[(b * n_paths + channel) * n_out + n] = buf[i0 + n].x;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) g_leaf_adjoint_kernel(const float* __restrict__ gout, const float* __restrict__ f,
+                                                             float2* __restrict__ gsrc, long long B, int log_src, int logk, unsigned mask,
+                                                             int logcw, float scale, int lf, int i0, int n_out, int n_paths, int channel,
+                                                             int accumulate) {
+    __shared__ float2 buf[1 << kLeafMaxLog2];
+    const int M = 1 << lf;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int n = threadIdx.x; n < M; n += blockDim.x) {
+            const int k = n - i0;
+            buf[n] = make_float2((k >= 0 && k < n_out) ? __ldg(gout + (b * n_paths + channel) * n_out + k) : 0.f, 0.f);
+        }
+        __syncthreads();
+        for (int st = lf - 1; st >= 0; --st) {                 // the transposed passes: natural -> bit-reversed, e^{-i...}
+            const int half = 1 << st;
+            for (int j = threadIdx.x; j < (M >> 1); j += blockDim.x) {
+                const int pos = j & (half - 1), lo = ((j >> st) << (st + 1)) + pos, hi = lo + half;
+                float sn, cs;
+                sincospif((float)pos / (float)half, &sn, &cs);
+                const float2 a = buf[lo], z = buf[hi];
+                const float2 d = make_float2(a.x - z.x, a.y - z.y);
+                buf[lo] = make_float2(a.x + z.x, a.y + z.y);
+                buf[hi] = make_float2(fmaf(d.x, cs, d.y * sn), fmaf(d.y, cs, -d.x * sn));
+            }
+            __syncthreads();
+        }
+        float2* gb = gsrc + (b << log_src);
+        for (int p = threadIdx.x; p < (1 << log_src); p += blockDim.x) {
+            const int t = p & ((1 << logk) - 1);
+            const bool live = logk < 2 || ((mask >> (t >> logcw)) & 1u);
+            float2 v = make_float2(0.f, 0.f);
+            if (live) {
+                const float w = __ldg(f + p) * scale;
+                const float2 z = buf[p >> logk];
+                v = make_float2(z.x * w, z.y * w);
+            }
+            if (!accumulate) gb[p] = v;
+            else if (live) {
+                const float2 o = gb[p];
+                gb[p] = make_float2(o.x + v.x, o.y + v.y);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static bool leaf_args_ok(int log_src, int logk, uint32_t chunk_mask, int log_chunk, int lf, int i0, int n_out, int n_paths, int channel) {
+    return log_src >= 1 && log_src <= kLargeMaxLog2 && logk >= 0 && logk <= log_src && lf == log_src - logk && lf >= 1 &&
+           lf <= kLeafMaxLog2 && !(logk >= 2 && (chunk_mask == 0 || log_chunk < 2 || log_chunk > logk || (logk - log_chunk) > 5)) &&
+           i0 >= 0 && n_out >= 1 && i0 + n_out <= (1 << lf) && channel >= 0 && channel < n_paths;
+}
+
+extern "C" int tebscat_large_leaf(tebscat_large* g, const float* src_dev, const float* filt_dev, int64_t B, int log_src, int logk,
+                                  uint32_t chunk_mask, int log_chunk, int scale_exp, int i0, int n_out, int n_paths, int channel,
+                                  float* out_dev, void* stream) {
+    const int lf = log_src - logk;
+    if (!g || !src_dev || !filt_dev || !out_dev || B < 1 || !leaf_args_ok(log_src, logk, chunk_mask, log_chunk, lf, i0, n_out, n_paths, channel))
+        return fail(TEBSCAT_EINVAL, "bad leaf request");
+    CU(cudaSetDevice(g->device));
+    const int grid = (int)(B < (int64_t)g->n_sms * 8 ? B : (int64_t)g->n_sms * 8);
+    g_leaf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(src_dev), filt_dev, out_dev, B, log_src, logk,
+                                                          chunk_mask, log_chunk, ldexpf(1.0f, -scale_exp), lf, i0, n_out, n_paths, channel);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+extern "C" int tebscat_large_leaf_adjoint(tebscat_large* g, const float* gout_dev, const float* filt_dev, int64_t B, int log_src, int logk,
+                                          uint32_t chunk_mask, int log_chunk, int scale_exp, int i0, int n_out, int n_paths, int channel,
+                                          float* gsrc_dev, int accumulate, void* stream) {
+    const int lf = log_src - logk;
+    if (!g || !gout_dev || !filt_dev || !gsrc_dev || B < 1 || !leaf_args_ok(log_src, logk, chunk_mask, log_chunk, lf, i0, n_out, n_paths, channel))
+        return fail(TEBSCAT_EINVAL, "bad leaf request");
+    CU(cudaSetDevice(g->device));
+    const int grid = (int)(B < (int64_t)g->n_sms * 8 ? B : (int64_t)g->n_sms * 8);
+    g_leaf_adjoint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout_dev, filt_dev, reinterpret_cast<float2*>(gsrc_dev), B, log_src, logk,
+                                                                  chunk_mask, log_chunk, ldexpf(1.0f, -scale_exp), lf, i0, n_out, n_paths,
+                                                                  channel, accumulate);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
 // ---- backward pass: adjoints of the ops above ----------------------------------------------------------
 // The reference is differentiable through torch autograd with ModulusStable (kymatio/backend/torch_backend.py:5-96;
 // test_differentiability_scattering, tests/scattering1d/test_torch_scattering1d.py:292-315).  Here the gradient is the

@@ -99,6 +99,12 @@ def load():
     lib.tebscat_large_store.restype = ctypes.c_int
     lib.tebscat_large_store.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, vp, vp]
+    lib.tebscat_large_leaf.restype = ctypes.c_int
+    lib.tebscat_large_leaf.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, u32, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.tebscat_large_leaf_adjoint.restype = ctypes.c_int
+    lib.tebscat_large_leaf_adjoint.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, u32, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp]
     lib.tebscat_large_modulus_to.restype = ctypes.c_int
     lib.tebscat_large_modulus_to.argtypes = [vp, vp, vp, ctypes.c_int64, vp]
     lib.tebscat_large_modulus_backward.restype = ctypes.c_int

@@ -21,6 +21,8 @@ from . import filterbank as fbk
 from . import schedule as sch
 
 LOG2_MAX = 17
+LEAF_FUSED_MAX_LOG2 = 10          # leaves of up to 1024 output-rate samples run as one launch (tebscat_large_leaf)
+FUSED_LEAVES = __import__('os').environ.get('TEBSCAT_FUSED_LEAVES', '0') != '0'
 
 
 class _TilePlanOwner:
@@ -180,6 +182,11 @@ class LargeDevicePlan:
             _lib.check(lib.tebscat_large_pair(g, ctypes.c_void_p(buf.data_ptr()), B, log_len, st))
 
         def leaf(src, spec, ch):                              # phi multiply + periodise -> iFFT -> unpad -> channel (:287-292)
+            if lf <= LEAF_FUSED_MAX_LOG2 and FUSED_LEAVES:       # one launch, the 2^lf bins never leave shared memory
+                off, log_src, logk, mask, logcw, sexp = spec
+                _lib.check(lib.tebscat_large_leaf(g, ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(fa + 4 * off), B, log_src, logk,
+                                                  mask, logcw, sexp, p.i0, p.n_out, p.n_paths, ch, ctypes.c_void_p(out.data_ptr()), st))
+                return
             mulfold(src, spec, WL)
             fft(WL, lf, True)
             _lib.check(lib.tebscat_large_store(g, ctypes.c_void_p(WL.data_ptr()), B, lf, p.i0, p.n_out, p.n_paths, ch,
@@ -243,6 +250,11 @@ class LargeDevicePlan:
 
         def leaf_adjoint(spec, ch, gsrc, accumulate):
             """(phi multiply + periodise -> iFFT -> unpad -> channel)^T, core :287-292 / :320-327 / :358-364"""
+            if lf <= LEAF_FUSED_MAX_LOG2 and FUSED_LEAVES:
+                off, log_src, logk, mask, logcw, sexp = spec
+                _lib.check(lib.tebscat_large_leaf_adjoint(g, vp(gout.data_ptr()), vp(fa + 4 * off), B, log_src, logk, mask, logcw, sexp,
+                                                          p.i0, p.n_out, p.n_paths, ch, vp(gsrc.data_ptr()), 1 if accumulate else 0, st))
+                return
             _lib.check(lib.tebscat_large_unstore(g, vp(gout.data_ptr()), B, lf, p.i0, p.n_out, p.n_paths, ch, vp(WL.data_ptr()), st))
             fft(WL, lf, False)
             unfold(WL, spec, gsrc, accumulate)
