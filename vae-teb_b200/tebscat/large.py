@@ -22,7 +22,7 @@ from . import schedule as sch
 
 LOG2_MAX = 17
 LEAF_FUSED_MAX_LOG2 = 10          # leaves of up to 1024 output-rate samples run as one launch (tebscat_large_leaf)
-FUSED_LEAVES = __import__('os').environ.get('TEBSCAT_FUSED_LEAVES', '0') != '0'
+FUSED_LEAVES = __import__('os').environ.get('TEBSCAT_FUSED_LEAVES', '1') != '0'
 
 
 class _TilePlanOwner:
