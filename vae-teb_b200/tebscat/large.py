@@ -153,7 +153,7 @@ class LargeDevicePlan:
                 self._run(xs, os_)                                   # warm-up outside the capture (workspace allocation)
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # other threads (e.g. DDP's reducer) keep working
                 self._run(xs, os_)
             self._graph_key, self._graph, self._gx, self._gout = key, graph, xs, os_
         self._gx.copy_(x2)
@@ -236,7 +236,7 @@ class LargeDevicePlan:
                 self._run_backward(xs, gs, gxs)                      # warm-up outside the capture (workspace allocation)
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # other threads (e.g. DDP's reducer) keep working
                 self._run_backward(xs, gs, gxs)
             self._bgraph_key, self._bgraph, self._bgx, self._bgs, self._bgxs = key, graph, xs, gs, gxs
         self._bgx.copy_(x2)
