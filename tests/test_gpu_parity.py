@@ -235,3 +235,29 @@ def test_forward_is_reentrant_across_host_threads_and_streams():
     [t.join() for t in threads]
     for a, b in zip(serial, out):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('cfg', [(4, 4827, 8, 4, 2), (3, 4223, 1, 4, 1), (2, 4085, 1, 2, 2)])
+def test_configurations_beyond_the_fused_schedule(cfg):
+    """Output-rate lengths of 2048 samples and more (T <= 4 at a padded length of 8192) do not fit the fused
+    single-kernel schedule (build_plan says so); the frontend then serves them on the op-by-op CUDA level of
+    tebscat/large.py -- same parity bar, forward and backward."""
+    from tebscat import Scattering1D
+    from tebscat.schedule import build_plan
+    from oracle.scattering1d_grad_oracle import GradOracle
+    J, N, Q, T, mo = cfg
+    with pytest.raises(NotImplementedError):
+        build_plan(J, N, Q, T, mo)
+    S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    x = torch.randn(3, N, generator=torch.Generator().manual_seed(J)).cuda().requires_grad_(True)
+    out, _ = S(x)
+    assert S._op_by_op
+    ref = ScatteringOracle(J, N, Q, T, mo)(x.detach().cpu().numpy())
+    got = out.detach().cpu().numpy().astype(np.float64)
+    assert got.shape == ref.shape
+    nr = np.linalg.norm(ref, axis=-1)
+    assert np.all(np.linalg.norm(got - ref, axis=-1) <= 1e-5 * nr + 1e-10 * nr.max())
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(9))
+    (out * w.cuda()).sum().backward()
+    _, g64 = GradOracle(J, N, Q, T, mo).vjp(x.detach().cpu().numpy(), w.numpy())
+    assert rel_l2(x.grad.cpu().numpy(), g64, axis=-1).max() < 1e-5

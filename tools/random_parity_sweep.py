@@ -1,0 +1,69 @@
+"""One-off robustness sweep on the GPU: random (J, Q, T, N, max_order, oversampling) configurations -- forward against the
+float64 oracle, gradients against the autograd oracle, the dense (tcgen05) phase path against the phase oracle."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'vae-teb_b200'))
+import numpy as np, torch
+from tebscat import Scattering1D, KymatioPhaseScattering1D
+from oracle.scattering1d_oracle import ScatteringOracle
+from oracle.scattering1d_grad_oracle import GradOracle
+from oracle.phase_oracle import PhaseOracle
+
+rng = np.random.RandomState(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+n_fwd, n_bwd, n_ph = (int(v) for v in (sys.argv[2:5] if len(sys.argv) > 4 else (30, 8, 8)))
+bad = 0
+
+def config():
+    while True:
+        J = int(rng.randint(2, 9)); Q = int(rng.choice([1, 2, 4, 8, 12])); N = int(rng.randint(200, 7000))
+        T = int(2 ** rng.randint(1, J + 1)); mo = int(rng.choice([1, 2])); os_ = int(rng.choice([0, 0, 0, 1]))
+        try:
+            S = Scattering1D(J, N, Q, max_order=mo, T=T, oversampling=os_)
+            if S.J_pad <= 13:
+                S._schedule()
+            return J, Q, T, N, mo, os_, S
+        except (ValueError, NotImplementedError, AssertionError):
+            continue
+
+t0 = time.time()
+for k in range(n_fwd):
+    J, Q, T, N, mo, os_, S = config()
+    S = S.cuda()
+    x = torch.randn(3, N, generator=torch.Generator().manual_seed(k))
+    out = S(x.cuda())[0].cpu().numpy().astype(np.float64)
+    ref = ScatteringOracle(J, N, Q, T, mo, oversampling=os_)(x.numpy())
+    nr = np.linalg.norm(ref, axis=-1); err = np.linalg.norm(out - ref, axis=-1)
+    ok = out.shape == ref.shape and np.all(err <= 1e-5 * nr + 1e-10 * nr.max())
+    bad += not ok
+    print('fwd', (J, Q, T, N, mo, os_), 'J_pad', S.J_pad, 'C', out.shape[1], 'worst %.2e' % float((err / np.maximum(nr, 1e-30)).max()), 'OK' if ok else 'FAIL', flush=True)
+for k in range(n_bwd):
+    J, Q, T, N, mo, os_, S = config()
+    S = S.cuda()
+    x = torch.randn(2, N, generator=torch.Generator().manual_seed(100 + k)).cuda().requires_grad_(True)
+    out, _ = S(x)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(200 + k))
+    (out * w.cuda()).sum().backward()
+    _, g64 = GradOracle(J, N, Q, T, mo, os_).vjp(x.detach().cpu().numpy(), w.numpy())
+    e = np.linalg.norm(x.grad.cpu().numpy() - g64, axis=-1) / np.linalg.norm(g64, axis=-1)
+    ok = e.max() < 1e-5
+    bad += not ok
+    print('bwd', (J, Q, T, N, mo, os_), 'J_pad', S.J_pad, 'worst %.2e' % e.max(), 'OK' if ok else 'FAIL', flush=True)
+os.environ['TEBSCAT_PHASE_FFT'] = '0'
+for k in range(n_ph):
+    while True:
+        J = int(rng.randint(3, 8)); Q = int(rng.choice([2, 4, 8])); N = int(rng.randint(400, 5000)); T = int(2 ** rng.randint(2, J + 1))
+        border = str(rng.choice(['reflect', 'reflect', 'constant', 'circular']))
+        try:
+            m = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), border_mode=border)
+            break
+        except (ValueError, NotImplementedError, AssertionError):
+            continue
+    x = torch.randn(2, 2, N, generator=torch.Generator().manual_seed(300 + k))
+    ours = m(x.cuda(), compute_phase=False, compute_cross_phase=True)['cross_phase_corr'].cpu().numpy().astype(np.float64)
+    o = PhaseOracle(J, Q, T, N, m.scattering(x[:, 0].cuda().contiguous())[0].shape[-1], border_mode=border)
+    ref = o.align_branches(x.numpy(), ours, mode='cross')
+    rel = np.linalg.norm(ours - ref) / np.linalg.norm(ref)
+    ok = ours.shape == ref.shape and rel < 5e-5
+    bad += not ok
+    print('phase', (J, Q, T, N, border), 'pairs', ours.shape[1], 'n_out', ours.shape[2], 'rel %.2e' % rel, 'OK' if ok else 'FAIL', flush=True)
+print('done in %.0f s, failures: %d' % (time.time() - t0, bad))

@@ -112,6 +112,7 @@ class Scattering1D(nn.Module):
         self._plans = {}
         self._host_plan = None
         self._sched = None
+        self._op_by_op = False            # True once the fused schedule turned out not to fit (see _forward_array)
 
     # ---- base_frontend.py:27-77 ------------------------------------------------
     def build(self):
@@ -267,7 +268,15 @@ class Scattering1D(nn.Module):
         dev = x2.device
         index = dev.index if dev.index is not None else torch.cuda.current_device()
         B = x2.shape[0]
-        if self.J_pad > LOG2_NP_MAX:
+        if self.J_pad <= LOG2_NP_MAX and not self._op_by_op:
+            try:
+                self._schedule()
+            except NotImplementedError:
+                # a valid configuration the fused single-kernel schedule cannot hold in shared memory (output-rate
+                # lengths of 2048 samples and more, i.e. T <= 4 at a padded length of 8192): the op-by-op level of
+                # tebscat/large.py serves it -- the same CUDA ops, one launch each
+                self._op_by_op = True
+        if self.J_pad > LOG2_NP_MAX or self._op_by_op:
             lp, ldp = self._large_plan_for(index)
             S = torch.empty((B, lp.n_paths, lp.n_out), dtype=torch.float32, device=dev)
             chunk = max(1, (1 << 28) >> self.J_pad)              # <= 2.7 GB of workspace per chunk
