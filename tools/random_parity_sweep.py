@@ -19,8 +19,6 @@ def config():
         T = int(2 ** rng.randint(1, J + 1)); mo = int(rng.choice([1, 2])); os_ = int(rng.choice([0, 0, 0, 1]))
         try:
             S = Scattering1D(J, N, Q, max_order=mo, T=T, oversampling=os_)
-            if S.J_pad <= 13:
-                S._schedule()
             return J, Q, T, N, mo, os_, S
         except (ValueError, NotImplementedError, AssertionError):
             continue
@@ -35,7 +33,7 @@ for k in range(n_fwd):
     nr = np.linalg.norm(ref, axis=-1); err = np.linalg.norm(out - ref, axis=-1)
     ok = out.shape == ref.shape and np.all(err <= 1e-5 * nr + 1e-10 * nr.max())
     bad += not ok
-    print('fwd', (J, Q, T, N, mo, os_), 'J_pad', S.J_pad, 'C', out.shape[1], 'worst %.2e' % float((err / np.maximum(nr, 1e-30)).max()), 'OK' if ok else 'FAIL', flush=True)
+    print('fwd', (J, Q, T, N, mo, os_), 'op-by-op' if S._op_by_op else 'fused', 'J_pad', S.J_pad, 'C', out.shape[1], 'worst %.2e' % float((err / np.maximum(nr, 1e-30)).max()), 'OK' if ok else 'FAIL', flush=True)
 for k in range(n_bwd):
     J, Q, T, N, mo, os_, S = config()
     S = S.cuda()
