@@ -93,3 +93,20 @@ def test_large_support_output_conventions():
         warnings.simplefilter('ignore', DeprecationWarning)
         dct, _ = Scattering1D(6, N, 4, T=64, vectorize=False).cuda()(x)
     assert dct[()].shape == (2, 1, ref.shape[-1]) and torch.equal(dct[()][:, 0], ref[:, 0])
+
+
+@pytest.mark.parametrize('graph', ['1', '0'])
+def test_children_as_long_as_their_parent(graph, monkeypatch):
+    """With oversampling a second-order path may not be subsampled at all (core/scattering1d.py:344-345): its
+    transform is as long as its parent's, and the second-order workspace must hold it (regression: it was sized for
+    half the padded length, and signals beyond the first half of the batch were overwritten)."""
+    from tebscat import Scattering1D
+    monkeypatch.setenv('TEBSCAT_LARGE_GRAPH', graph)
+    J, Q, T, N, mo, os_ = 4, 1, 2, 5980, 2, 1
+    S = Scattering1D(J, N, Q, max_order=mo, T=T, oversampling=os_).cuda()
+    x = torch.randn(5, N, generator=torch.Generator().manual_seed(4))
+    out = S(x.cuda())[0].cpu().numpy().astype(np.float64)
+    assert S._op_by_op
+    ref = ScatteringOracle(J, N, Q, T, mo, oversampling=os_)(x.numpy())
+    assert out.shape == ref.shape
+    assert (np.linalg.norm(out - ref, axis=-1) / np.linalg.norm(ref, axis=-1)).max() < 1e-5

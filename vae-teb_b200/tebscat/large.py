@@ -97,6 +97,9 @@ class LargePlan:
         self.n_paths = len(keys)
         lens = {n, lf} | {e['l1'] for e in self.first} | {k['l2'] for e in self.first for k in e['kids']}
         self.tile_lengths = sorted(min(v, sch.LOG2_NP_MAX) for v in lens)
+        # longest second-order transform: Np/2 without oversampling, but a child is not subsampled at all when
+        # oversampling >= its j2 - k1 (core :344-345), and then it is as long as its parent
+        self.max_l2 = max([k['l2'] for e in self.first for k in e['kids']], default=1)
 
 
 class LargeDevicePlan:
@@ -129,7 +132,7 @@ class LargeDevicePlan:
             Np = 1 << self.plan.geo.J_pad
             self._ws = {key: (torch.empty(B * Np * 2, dtype=torch.float32, device=dev),          # U0
                               torch.empty(B * Np * 2, dtype=torch.float32, device=dev),          # first-order work
-                              torch.empty(B * Np, dtype=torch.float32, device=dev),              # second-order work (<= Np/2)
+                              torch.empty(B * (2 << self.plan.max_l2), dtype=torch.float32, device=dev),   # second-order work
                               torch.empty(B * (2 << self.plan.lf), dtype=torch.float32, device=dev))}   # leaf
         return self._ws[key]
 
