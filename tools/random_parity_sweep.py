@@ -15,8 +15,8 @@ bad = 0
 
 def config():
     while True:
-        J = int(rng.randint(2, 9)); Q = int(rng.choice([1, 2, 4, 8, 12])); N = int(rng.randint(200, 7000))
-        T = int(2 ** rng.randint(1, J + 1)); mo = int(rng.choice([1, 2])); os_ = int(rng.choice([0, 0, 0, 1]))
+        J = int(rng.randint(2, 9)); Q = int(rng.choice([1, 2, 4, 8, 12])); N = int(rng.randint(200, 7000 if rng.rand() < 0.8 else 20000))
+        T = int(2 ** rng.randint(1, J + 1)); mo = int(rng.choice([1, 2])); os_ = int(rng.choice([0, 0, 0, 1, 2]))
         try:
             S = Scattering1D(J, N, Q, max_order=mo, T=T, oversampling=os_)
             return J, Q, T, N, mo, os_, S
