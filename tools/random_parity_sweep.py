@@ -46,6 +46,31 @@ for k in range(n_bwd):
     ok = e.max() < 1e-5
     bad += not ok
     print('bwd', (J, Q, T, N, mo, os_), 'J_pad', S.J_pad, 'worst %.2e' % e.max(), 'OK' if ok else 'FAIL', flush=True)
+n_un = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+for k in range(n_un):                                   # average=False (un-averaged moduli) where the fused schedule exists
+    while True:
+        J, Q, T, N, mo, os_, S = config()
+        try:
+            if S.J_pad > 13:
+                continue
+            Su = Scattering1D(J, N, Q, max_order=mo, T=T, oversampling=os_, average=False, out_type='list').cuda()
+            x = torch.randn(2, N, generator=torch.Generator().manual_seed(400 + k))
+            out = Su(x.cuda())[0]
+            break
+        except NotImplementedError:
+            continue
+    ref = ScatteringOracle(J, N, Q, T, mo, oversampling=os_).unaveraged(x.numpy())
+    worst, ok = 0.0, len(out) == len(ref)
+    for o, (key, v) in zip(out, ref):
+        got = o['coef'].cpu().numpy().astype(np.float64)
+        if got.shape != v.shape:
+            ok = False
+            break
+        e = (np.linalg.norm(got - v, axis=-1) / np.maximum(np.linalg.norm(v, axis=-1), 1e-30)).max()
+        worst = max(worst, float(e))
+    ok = ok and worst < 1e-5
+    bad += not ok
+    print('unaveraged', (J, Q, T, N, mo, os_), 'paths', len(out), 'worst %.2e' % worst, 'OK' if ok else 'FAIL', flush=True)
 os.environ['TEBSCAT_PHASE_FFT'] = '0'
 for k in range(n_ph):
     while True:
@@ -63,5 +88,11 @@ for k in range(n_ph):
     rel = np.linalg.norm(ours - ref) / np.linalg.norm(ref)
     ok = ours.shape == ref.shape and rel < 5e-5
     bad += not ok
+    wi = m(x.cuda(), compute_phase=True, phase_channels=[1])['phase_corr'].cpu().numpy().astype(np.float64)
+    rw = o.align_branches(x.numpy()[:, 1], wi, mode='within')
+    full = m(x.cuda(), compute_phase=False, compute_cross_phase=True, cross_phase_low_pass=False, cross_phase_same_pairs_only=True)['cross_phase_corr'].cpu().numpy()
+    rf = o(x.numpy(), mode='cross', pair_subset=o.autoc_idx, low_pass=False)
+    ok = ok and np.linalg.norm(wi - rw) / np.linalg.norm(rw) < 5e-5 and full.shape == rf.shape
+    bad += (not ok) and rel < 5e-5
     print('phase', (J, Q, T, N, border), 'pairs', ours.shape[1], 'n_out', ours.shape[2], 'rel %.2e' % rel, 'OK' if ok else 'FAIL', flush=True)
 print('done in %.0f s, failures: %d' % (time.time() - t0, bad))
