@@ -27,7 +27,7 @@ t0 = time.time()
 for k in range(n_fwd):
     J, Q, T, N, mo, os_, S = config()
     S = S.cuda()
-    x = torch.randn(3, N, generator=torch.Generator().manual_seed(k))
+    x = torch.randn(int(rng.randint(1, 10)), N, generator=torch.Generator().manual_seed(k))
     out = S(x.cuda())[0].cpu().numpy().astype(np.float64)
     ref = ScatteringOracle(J, N, Q, T, mo, oversampling=os_)(x.numpy())
     nr = np.linalg.norm(ref, axis=-1); err = np.linalg.norm(out - ref, axis=-1)
@@ -37,7 +37,7 @@ for k in range(n_fwd):
 for k in range(n_bwd):
     J, Q, T, N, mo, os_, S = config()
     S = S.cuda()
-    x = torch.randn(2, N, generator=torch.Generator().manual_seed(100 + k)).cuda().requires_grad_(True)
+    x = torch.randn(int(rng.randint(1, 8)), N, generator=torch.Generator().manual_seed(100 + k)).cuda().requires_grad_(True)
     out, _ = S(x)
     w = torch.randn(out.shape, generator=torch.Generator().manual_seed(200 + k))
     (out * w.cuda()).sum().backward()
@@ -81,7 +81,7 @@ for k in range(n_ph):
             break
         except (ValueError, NotImplementedError, AssertionError):
             continue
-    x = torch.randn(2, 2, N, generator=torch.Generator().manual_seed(300 + k))
+    x = torch.randn(int(rng.randint(1, 6)), 2, N, generator=torch.Generator().manual_seed(300 + k))
     ours = m(x.cuda(), compute_phase=False, compute_cross_phase=True)['cross_phase_corr'].cpu().numpy().astype(np.float64)
     o = PhaseOracle(J, Q, T, N, m.scattering(x[:, 0].cuda().contiguous())[0].shape[-1], border_mode=border)
     ref = o.align_branches(x.numpy(), ours, mode='cross')
