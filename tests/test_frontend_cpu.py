@@ -168,3 +168,19 @@ def test_missing_library_fails_loudly(monkeypatch):
     with pytest.raises(_lib.TebscatError) as ve:
         _lib.load()
     assert 'no CPU fallback' in str(ve.value)
+
+
+def test_op_by_op_plan_workspace_geometry():
+    """Host logic of the op-by-op level: the second-order workspace follows the longest child -- half the padded length
+    normally, the full length when oversampling leaves a child un-subsampled (core/scattering1d.py:344-345) -- and the
+    configurations the fused schedule cannot hold are exactly the ones with output-rate lengths of 2048 and more."""
+    from tebscat.large import LargePlan
+    from tebscat.schedule import build_plan
+    assert LargePlan(6, 9000, 4, 64, 2).max_l2 == 13                      # Np = 2^14: children at most Np / 2
+    lp = LargePlan(4, 5980, 1, 2, 2, oversampling=1)                      # T = 2, oversampling = 1: nothing is subsampled
+    assert lp.geo.J_pad == 13 and lp.lf == 13 and lp.max_l2 == 13
+    assert all(k['mul'][2] == 0 for e in lp.first for k in e['kids'])     # logk = 0 for every child
+    assert LargePlan(6, 4800, 8, 64, 1).max_l2 == 1                       # first order only: no children
+    with pytest.raises(NotImplementedError):
+        build_plan(4, 4827, 8, 4, 2)                                      # lf = 11
+    build_plan(4, 4827, 8, 8, 2)                                          # lf = 10 fits
