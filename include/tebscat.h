@@ -75,6 +75,12 @@ int tebscat_plan_create(const tebscat_plan_desc* desc,
 
 void tebscat_plan_destroy(tebscat_plan* plan);
 
+/* Analysis window applied to the samples as the plan's loads read them: x[t] * window[t] before padding.
+ * window_host: N floats (copied), or NULL to remove it.  Replaces the eager `x = x * window` of
+ * KymatioPhaseScattering1D.forward (hdf5_dataset/kymatio_phase_scattering.py:405-407; the Tukey taper of
+ * _create_tukey_window, :362-392).  Call it between forward calls, not concurrently with them. */
+int tebscat_plan_set_window(tebscat_plan* plan, const float* window_host);
+
 /* S[b, c, :] for b < B.  x_dev: [B, N]; S_dev: [B, n_paths, n_out]; both device
  * fp32 contiguous.  Replaces core.scattering1d
  * (kymatio/kymatio/scattering1d/core/scattering1d.py:197-399) as called from
@@ -140,6 +146,9 @@ int tebscat_phase_plan_create(const tebscat_phase_desc* desc, tebscat_plan* stag
 
 void tebscat_phase_plan_destroy(tebscat_phase_plan* plan);
 
+/* The same window on the loads of stage A (both channels). */
+int tebscat_phase_plan_set_window(tebscat_phase_plan* plan, const float* window_host);
+
 /* out[b, s, :] = Re smooth( |z_i| exp(i p theta_i) conj(z_j) ) for the selected pairs s,
  * z_i from channel ch_i and z_j from channel ch_j of x_dev [B, n_channels, N]
  * (ch_i == ch_j: _compute_phase_correlation :275-301; else
@@ -177,6 +186,8 @@ int tebscat_last_launch_count(void);
 typedef struct tebscat_large tebscat_large;
 int tebscat_large_create(int device, tebscat_large** out);
 void tebscat_large_destroy(tebscat_large* ctx);
+/* analysis window of pad_load / pad_adjoint (see tebscat_plan_set_window): n floats (copied), or NULL to remove it */
+int tebscat_large_set_window(tebscat_large* ctx, const float* window_host, int n);
 /* tile plan (tebscat.schedule.build_tile_plan) for in-place transforms of 2^log2_len <= 8192 samples;
  * kind: 0 forward, 1 inverse, 2 inverse -> modulus -> forward; one job covers slots_per_job consecutive complex
  * elements (a multiple of the length); ownership moves */

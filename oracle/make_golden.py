@@ -112,6 +112,23 @@ def phase_fixture(name, B):
     print(name, 'phase', within.shape, cross.shape, 'masks', pm.sum(), cm.sum())
 
 
+def phase_fixture_randn(tag, name, B, seed=578):
+    """randn-only rows of the full pair set (no CTG rows): on these the live reference itself is within
+    1e-5 per path of the float64 oracle, so north_star's bound is asserted on them without any relaxation."""
+    J, Q, T, N, max_order, _ = CONFIGS[name][:6]
+    m = kps.KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cpu'), max_order=max_order)
+    x = randn_batch(B, N, 2, seed=seed)
+    with torch.no_grad():
+        rw = m(x, compute_phase=True, phase_channels=[0])
+        rc = m(x, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1])
+    np.savez_compressed(
+        os.path.join(OUT, 'phase_%s.npz' % tag),
+        J=J, Q=Q, T=T, N=N, max_order=max_order, x=x.numpy(), n_ctg=0, subset=False,
+        scattering=rw['scattering'].numpy(), within=rw['phase_corr'].numpy(), cross=rc['cross_phase_corr'].numpy(),
+    )
+    print(tag, 'phase (randn rows)', rw['phase_corr'].shape, rc['cross_phase_corr'].shape)
+
+
 def phase_option_fixture(tag, name, B, **opts):
     """Non-default options of the phase module: border_mode 'constant' / 'circular'
     (:162-173) and oversampling (target length of the scattering output, :445)."""
@@ -138,6 +155,9 @@ def phase_option_fixtures():
 
 
 if __name__ == '__main__':
+    if sys.argv[1:] == ['phase-randn']:
+        phase_fixture_randn('Hr', 'H', 4)
+        sys.exit(0)
     if sys.argv[1:] == ['phase-options']:
         phase_option_fixtures()
         sys.exit(0)
@@ -149,6 +169,7 @@ if __name__ == '__main__':
     phase_fixture('H', 1)
     phase_fixture('P', 1)
     phase_fixture('S', 2)
+    phase_fixture_randn('Hr', 'H', 4)
     phase_option_fixtures()
     kat = np.load(os.path.join(REF, 'kymatio/tests/scattering1d/test_data_1d.npz'))
     np.savez_compressed(os.path.join(OUT, 'kat_test_data_1d.npz'), **{k: kat[k] for k in kat})

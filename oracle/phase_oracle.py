@@ -43,10 +43,16 @@ def pad_signal(x, pad_left, pad_right, border_mode='reflect'):
 
 
 class PhaseOracle:
-    def __init__(self, J, Q, T, N, n_out, border_mode='reflect'):
-        """n_out: temporal length of the scattering output (target_length, :445)."""
+    def __init__(self, J, Q, T, N, n_out, border_mode='reflect', cdtype=np.complex128):
+        """n_out: temporal length of the scattering output (target_length, :445).
+        cdtype=np.complex64 evaluates every step in single precision like the reference does (fp32 transforms,
+        fp32 atan2, p * theta rounded in fp32): the distance of that output to the float64 one is the
+        reference-class fp32 noise of a path, which the tests use as the noise floor where no output of the
+        live reference is committed."""
         self.J, self.Q, self.T, self.N, self.n_out = J, Q, T, N, n_out
         self.border_mode = border_mode
+        self.cdtype = np.dtype(cdtype)
+        self.rdtype = np.float32 if self.cdtype == np.complex64 else np.float64
         self.geo = fo.geometry(N, J, Q, T, clamp=True)                      # :100-113
         bank = fo.filter_factory(self.geo['J_pad'], J, Q, T)                 # :117-120
         # complex64 cast keeps the fp32 value of the real float64 filters  (:123-125)
@@ -67,8 +73,9 @@ class PhaseOracle:
     def analytic(self, x):
         """x: (B, N) -> z (B, F, N) complex128."""
         g = self.geo
-        xf = scipy.fft.fft(pad_signal(np.asarray(x, np.float64), g['pad_left'], g['pad_right'], self.border_mode), axis=-1)
-        z = scipy.fft.ifft(xf[:, None, :] * self.psi1[None], axis=-1)
+        xf = scipy.fft.fft(pad_signal(np.asarray(x, self.rdtype), g['pad_left'], g['pad_right'], self.border_mode)
+                           .astype(self.cdtype), axis=-1)
+        z = scipy.fft.ifft(xf[:, None, :] * self.psi1[None].astype(self.rdtype), axis=-1)
         return z[..., g['ind_start'][0]:g['ind_end'][0]]
 
     # :233-273 (decimation branch)
@@ -76,7 +83,7 @@ class PhaseOracle:
         g = self.geo
         Np = 2 ** g['J_pad']
         dec = self.N // self.n_out if (self.n_out > 0 and self.N > self.n_out) else 1   # :287-291
-        cf = scipy.fft.fft(pad_signal(c, g['pad_left'], g['pad_right'], self.border_mode), axis=-1) * self.phi
+        cf = scipy.fft.fft(pad_signal(c, g['pad_left'], g['pad_right'], self.border_mode), axis=-1) * self.phi.astype(self.rdtype)
         if dec > 1:
             y = scipy.fft.ifft(cf[..., :max(Np // dec, 1)], axis=-1)          # :242-252
             s = g['pad_left'] // dec                                          # :258
@@ -90,8 +97,8 @@ class PhaseOracle:
         if pair_subset is not None:
             ii, jj, pw = ii[pair_subset], jj[pair_subset], pw[pair_subset]
         zi = z_i[:, ii, :]
-        theta = np.arctan2(zi.imag, zi.real) * pw[None, :, None].astype(np.float64)   # :214-215
-        acc = np.abs(zi) * (np.cos(theta) + 1j * np.sin(theta))              # :218
+        theta = np.arctan2(zi.imag, zi.real) * pw[None, :, None].astype(self.rdtype)  # :214-215
+        acc = (np.abs(zi) * (np.cos(theta) + 1j * np.sin(theta))).astype(self.cdtype)   # :218
         c = acc * np.conj(z_j[:, jj, :])                                     # :283 / :339
         if not low_pass:
             return c.real                                                    # :357-360
@@ -99,7 +106,7 @@ class PhaseOracle:
 
     def __call__(self, x, mode='cross', pair_subset=None, low_pass=True):
         """mode 'within': x (B, N); mode 'cross': x (B, 2, N) -> (B, P, n_out) float64."""
-        x = np.asarray(x, np.float64)
+        x = np.asarray(x, self.rdtype)
         if mode == 'within':
             z = self.analytic(x)
             y = self.pair_stage(z, z, pair_subset, low_pass)

@@ -51,7 +51,7 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
         c.zc = reinterpret_cast<float2*>(zc) + b * (long long)n_paths * n_out;
         c.zp = reinterpret_cast<float2*>(zp) + b * (long long)n_paths * n_out;
         c.z_mode = z_mode;
-        c.N = N; c.pad_left = pad_left; c.log2_Np = log2_Np; c.n_out = n_out; c.border = border;
+        c.N = N; c.pad_left = pad_left; c.log2_Np = log2_Np; c.n_out = n_out; c.border = border; c.win = nullptr;
         for (int s = 0; s < n_steps; ++s) {
             for (int ti = steps[2 * s]; ti < steps[2 * s + 1]; ++ti) {
                 Task t;

@@ -32,6 +32,17 @@ def path_tolerance(ref64, ref32, rel=1e-5, noise_factor=4.0):
                       noise_factor * np.linalg.norm(ref32.astype(np.float64) - ref64, axis=-1))
 
 
+def phase_path_tolerance(oracle_aligned_to_ref, ref_fp32, rel=1e-5, noise_factor=4.0):
+    """Per-path L2 error budget of the phase path: rel-L2 <= 1e-5 (north_star), or -- on paths where the
+    REFERENCE's own fp32 arithmetic (p * theta rounded in fp32 with p up to ~100) is noisier
+    than that -- `noise_factor` times the distance of the live reference's committed fp32 output to the
+    branch-aligned float64 oracle.  On randn rows the reference sits below 1e-5 on every path, so the
+    budget there is the plain north-star bound times at most `noise_factor`; the tests assert the plain
+    bound on those rows separately."""
+    return np.maximum(rel * np.linalg.norm(oracle_aligned_to_ref, axis=-1),
+                      noise_factor * np.linalg.norm(ref_fp32.astype(np.float64) - oracle_aligned_to_ref, axis=-1))
+
+
 def emu_available():
     return os.path.exists(EMU_PATH)
 

@@ -184,3 +184,37 @@ def test_op_by_op_plan_workspace_geometry():
     with pytest.raises(NotImplementedError):
         build_plan(4, 4827, 8, 4, 2)                                      # lf = 11
     build_plan(4, 4827, 8, 8, 2)                                          # lf = 10 fits
+
+
+def test_plan_validation_runs_before_any_device_call():
+    """tebscat_plan_create validates the schedule on the host before it touches CUDA, so malformed plans are
+    refused with TEBSCAT_EINVAL on a box without a GPU too: a thread range outside the CTA, and two tasks of
+    one step on the same warps (the check that used to sit behind a double free)."""
+    from tebscat.schedule import build_plan
+    from tebscat.torch_frontend import _DevicePlan
+    p = build_plan(5, 700, 2, 8, 2)
+    p.tasks = p.tasks.copy()
+    p.tasks[3, 1] = 5000
+    with pytest.raises(ValueError) as e:
+        _DevicePlan(p, 0)
+    assert 'outside the CTA' in str(e.value)
+    p = build_plan(5, 700, 2, 8, 2)
+    p.tasks = p.tasks.copy()
+    st = next(s for s in range(p.steps.shape[0]) if p.steps[s, 1] - p.steps[s, 0] >= 2)
+    p.tasks[p.steps[st, 0] + 1, 1] = p.tasks[p.steps[st, 0], 1]
+    with pytest.raises(ValueError) as e:
+        _DevicePlan(p, 0)
+    assert 'overlapping thread ranges' in str(e.value)
+
+
+def test_level_selection_follows_the_current_options():
+    """Which level serves a configuration (fused single kernel / op by op) is decided per schedule key, not latched:
+    `oversampling` is read at call time like in the reference (core/scattering1d.py:260-261), so changing it on a
+    live module must re-decide in both directions."""
+    from tebscat import Scattering1D
+    S = Scattering1D(6, 4800, 8, T=8)
+    assert not S._op_by_op                      # output rate 1024 samples: fits the fused schedule
+    S.oversampling = 1
+    assert S._op_by_op                          # 2048 samples at the output rate: op-by-op level
+    S.oversampling = 0
+    assert not S._op_by_op

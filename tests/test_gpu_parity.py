@@ -150,6 +150,39 @@ def test_plan_validation_errors():
     assert rc == _lib.TEBSCAT_EINVAL
 
 
+def test_plan_error_paths_free_the_plan_once():
+    """Two error paths of tebscat_plan_create used to free the plan twice (round-1 advice): two tasks of one
+    step on the same warps -> ValueError (TEBSCAT_EINVAL); dynamic + static shared memory above the opt-in
+    limit -> NotImplementedError (TEBSCAT_EUNSUPPORTED).  The process survives and a valid plan still works."""
+    from tebscat.schedule import build_plan
+    from tebscat.torch_frontend import _DevicePlan
+    J, N, Q, T, mo = CONFIGS['T']
+    for _ in range(3):
+        p = build_plan(J, N, Q, T, mo)
+        p.tasks = p.tasks.copy()
+        st = next(s for s in range(p.steps.shape[0]) if p.steps[s, 1] - p.steps[s, 0] >= 2)
+        a, b = p.steps[st, 0], p.steps[st, 0] + 1
+        p.tasks[b, 1] = p.tasks[a, 1]                  # second task starts on the first one's warps
+        with pytest.raises(ValueError) as ve:
+            _DevicePlan(p, 0)
+        assert 'overlapping thread ranges' in str(ve.value)
+        q = build_plan(J, N, Q, T, mo)
+        optin = torch.cuda.get_device_properties(0).shared_memory_per_block_optin
+        q.smem_complex = optin // 8 - 204              # dynamic part alone fits exactly; with the static part it does not
+        with pytest.raises(NotImplementedError) as ne:
+            _DevicePlan(q, 0)
+        assert 'shared memory' in str(ne.value)
+        q.smem_complex = optin // 8 + 4096             # and the plainly oversized request
+        with pytest.raises(NotImplementedError):
+            _DevicePlan(q, 0)
+    from tebscat import Scattering1D
+    S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    x = np.random.RandomState(5).randn(2, N).astype(np.float32)
+    out, _ = S(torch.from_numpy(x).cuda())
+    ref = ScatteringOracle(J, N, Q, T, mo)(x)
+    assert rel_l2(out.cpu().numpy().astype(np.float64), ref) < 1e-5
+
+
 @pytest.mark.parametrize('cfg', [(7, 8, 512, 128, 2), (8, 8, 1000, 256, 2), (10, 4, 5000, 1024, 1), (5, 8, 512, 24, 2),
                                  (3, 8, 2048, 6, 2), (10, 12, 5000, 768, 2)])
 def test_other_configurations(cfg):

@@ -1,60 +1,102 @@
 """GPU parity of the phase-harmonic correlation path (KymatioPhaseScattering1D) against the
 float64 oracle and the committed outputs of the live reference.
 
-PARITY UNPINNED by the reference's own tests (it has none for this module).  Tolerances: the
-reference rounds p*theta in fp32 with p up to ~100 and its theta flips sign at the two
-reflect-symmetry samples, so comparisons go through the oracle's branch
-alignment and use: overall rel-L2 <= 5e-5, per-path median <= 5e-5, per-path max <= 2e-3 --
-the same numbers the oracle itself is pinned with against the reference (test_oracle_golden)."""
+PARITY UNPINNED by the reference's own tests (it has none for this module); pinned against outputs of the
+live reference (tests/golden/phase_*.npz, oracle/make_golden.py) through the branch-aligned protocol of
+SURVEY.md 8c.  Bound, per coefficient path and for every form of stage B (dense on tcgen05, dense on mma.sync,
+transforms on the interpreter):
+
+    || ours - oracle64 ||  <=  max( 1e-5 || path || ,  4 || reference_fp32 - oracle64 || )
+
+i.e. north_star's 1e-5, relaxed only where the REFERENCE's own fp32 arithmetic is noisier than a quarter of
+that (it rounds p * theta in fp32 with p up to 108: on randn rows the live reference is within 1e-5 of the
+float64 oracle on every path with p < 32 but up to 2.1e-5 away on the 24 paths with p >= 32 -- fixture
+phase_Hr.npz --, on CTG rows, mean 140 bpm, up to 2.9e-4).  On randn rows every path with p < 32 is also held
+to the plain 1e-5.  Where no reference output is committed, the noise floor is the single-precision oracle's
+distance to the float64 one (same statistics: median ratio 1.0 to the live reference's, tools/phase_parity_report.py).
+The worst ratio err / bound of every comparison is printed (pytest -s)."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, rel_l2
+from helpers import GOLDEN, phase_path_tolerance, rel_l2
 from oracle.phase_oracle import PhaseOracle
 
 pytestmark = pytest.mark.gpu
 
-CFG = {'H': (6, 8, 64, 4800, 2), 'P': (11, 4, 16, 5760, 1), 'S': (4, 4, 16, 1000, 2)}
+CFG = {'H': (6, 8, 64, 4800, 2), 'Hr': (6, 8, 64, 4800, 2), 'P': (11, 4, 16, 5760, 1), 'S': (4, 4, 16, 1000, 2)}
+FORMS = {'tcgen05': ('0', 'tc'), 'mma.sync': ('0', 'sync'), 'transform': ('1', 'tc')}
 _mods = {}
 
 
-def module_of(name):
+def module_of(name, form=None, monkeypatch=None, **opts):
+    """Module of configuration `name`; `form` selects the form of stage B (the switches are read when the device
+    plan is built / per call, so the environment stays set for the duration of the test)."""
     from tebscat import KymatioPhaseScattering1D
-    if name not in _mods:
+    if form is not None:
+        monkeypatch.setenv('TEBSCAT_PHASE_FFT', FORMS[form][0])
+        monkeypatch.setenv('TEBSCAT_PHASE_MMA', FORMS[form][1])
+    key = (name, form if form is None else FORMS[form][0], tuple(sorted(opts.items())))
+    if key not in _mods:
         J, Q, T, N, mo = CFG[name]
-        _mods[name] = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), max_order=mo)
-    return _mods[name]
+        _mods[key] = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), max_order=mo, **opts)
+    return _mods[key]
 
 
-def check(ours, oracle_aligned, tag):
-    overall = rel_l2(ours, oracle_aligned)
-    per_path = rel_l2(ours, oracle_aligned, axis=-1)
-    assert overall < 5e-5, (tag, overall)
-    assert np.median(per_path) < 5e-5 and per_path.max() < 2e-3, (tag, np.median(per_path), per_path.max())
+def check(ours, o, xin, mode, tag, sub=None, ref=None, randn_rows=()):
+    """The bound of the module docstring.  `ref`: committed fp32 output of the live reference (else the
+    single-precision oracle supplies the noise floor).  Returns the worst err / bound."""
+    ours = np.asarray(ours, np.float64)
+    al_us = o.align_branches(xin, ours, mode=mode, pair_subset=sub)
+    if ref is None:
+        o32 = PhaseOracle(o.J, o.Q, o.T, o.N, o.n_out, border_mode=o.border_mode, cdtype=np.complex64)
+        ref = o32(xin, mode=mode, pair_subset=sub).astype(np.float64)
+    al_ref = o.align_branches(xin, ref, mode=mode, pair_subset=sub)
+    tol = phase_path_tolerance(al_ref, ref)
+    err = np.linalg.norm(ours - al_us, axis=-1)
+    ratio = err / tol
+    rel = err / np.linalg.norm(al_us, axis=-1)
+    pw = o.powers if sub is None else o.powers[sub]
+    low_p = pw < 32
+    for b in randn_rows:
+        assert rel[b][low_p].max() <= 1e-5, (tag, 'randn row %d' % b, rel[b][low_p].max())
+    print('%s: worst err/bound %.3f, worst per-path rel-L2 %.2e (randn rows, p < 32: %.2e), overall %.2e' % (
+        tag, ratio.max(), rel.max(), max([rel[b][low_p].max() for b in randn_rows], default=float('nan')),
+        rel_l2(ours, al_us)))
+    assert ratio.max() <= 1.0, (tag, ratio.max(), np.unravel_index(ratio.argmax(), ratio.shape))
+    return ratio.max()
 
 
-@pytest.mark.parametrize('name', ['H', 'S', 'P'])
-def test_phase_matches_oracle_and_reference(name):
+@pytest.mark.parametrize('form', ['tcgen05', 'mma.sync', 'transform'])
+@pytest.mark.parametrize('name', ['H', 'Hr', 'S', 'P'])
+def test_phase_matches_oracle_and_reference(name, form, monkeypatch):
     d = np.load(os.path.join(GOLDEN, 'phase_%s.npz' % name))
     J, Q, T, N, mo = CFG[name]
-    m = module_of(name)
+    m = module_of(name, form, monkeypatch)
+    if form == 'transform' and m._plan.pair_plan is None:
+        pytest.skip('decimation factor %d is not a power of two' % m._plan.dec)
+    assert m._dev_plan(0).uses_fft_pairs == (form == 'transform')
     x = torch.from_numpy(d['x']).cuda()
     n_out = d['scattering'].shape[-1]
     o = PhaseOracle(J, Q, T, N, n_out)
     subset = bool(d['subset'])
-    sel = m.get_optimal_coefficients_for_fhr(J, Q, T)
-    pm = sel['recommendations']['use_phase_mask'].cpu().numpy()
-    cm = sel['recommendations']['use_cross_mask'].cpu().numpy()
-    assert np.array_equal(pm, d['phase_mask']) and np.array_equal(cm, d['cross_mask'])     # identical masks
+    B = d['x'].shape[0]
+    n_ctg = int(d['n_ctg']) if 'n_ctg' in d.files else B // 2        # make_golden: CTG rows first, randn rows behind
+    randn_rows = range(n_ctg, B)
+    pm = cm = None
+    if 'phase_mask' in d.files:
+        sel = m.get_optimal_coefficients_for_fhr(J, Q, T)
+        pm = sel['recommendations']['use_phase_mask'].cpu().numpy()
+        cm = sel['recommendations']['use_cross_mask'].cpu().numpy()
+        assert np.array_equal(pm, d['phase_mask']) and np.array_equal(cm, d['cross_mask'])     # identical masks
 
     rw = m(x, compute_phase=True, phase_channels=[0], phase_pairs=pm if subset else None)
     rc = m(x, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1], phase_pairs=cm if subset else None)
     assert set(rw) == {'scattering', 'phase_corr', 'autoc_idx'}
     assert set(rc) == {'scattering', 'cross_phase_corr', 'autoc_idx'}
-    assert torch.equal(rw['autoc_idx'].cpu(), torch.from_numpy(d['autoc_idx']))
+    assert np.array_equal(rw['autoc_idx'].cpu().numpy(), o.autoc_idx)
     within = rw['phase_corr'].cpu().numpy().astype(np.float64)
     cross = rc['cross_phase_corr'].cpu().numpy().astype(np.float64)
     assert within.shape == d['within'].shape and cross.shape == d['cross'].shape
@@ -64,15 +106,16 @@ def test_phase_matches_oracle_and_reference(name):
     sub_w = np.nonzero(pm)[0] if subset else None
     sub_c = np.nonzero(cm)[0] if subset else None
     xin = d['x']
-    check(within, o.align_branches(xin[:, 0], within, mode='within', pair_subset=sub_w), 'within/oracle')
-    check(cross, o.align_branches(xin, cross, mode='cross', pair_subset=sub_c), 'cross/oracle')
+    tag = '%s/%s/' % (name, form)
+    check(within, o, xin[:, 0], 'within', tag + 'within', sub_w, d['within'], randn_rows)
+    check(cross, o, xin, 'cross', tag + 'cross', sub_c, d['cross'], randn_rows)
     # against the live reference's fp32 outputs: both sides carry fp32 noise of p*theta
     for ours, ref, mode, sub in ((within, d['within'], 'within', sub_w), (cross, d['cross'], 'cross', sub_c)):
         aligned_to_ref = o.align_branches(xin[:, 0] if mode == 'within' else xin, ref, mode=mode, pair_subset=sub)
         aligned_to_us = o.align_branches(xin[:, 0] if mode == 'within' else xin, ours, mode=mode, pair_subset=sub)
         # distance to the reference after removing each side's branch choice
         diff = (ours - aligned_to_us) - (ref - aligned_to_ref)
-        assert np.linalg.norm(diff) / np.linalg.norm(ref) < 1e-4, mode
+        assert np.linalg.norm(diff) / np.linalg.norm(ref) < 5e-5, mode
 
 
 def test_full_rate_product_and_same_pairs():
@@ -90,9 +133,8 @@ def test_full_rate_product_and_same_pairs():
     assert rel_l2(full[..., inner], ref[..., inner]) < 5e-5
     r2 = m(x, compute_phase=False, compute_cross_phase=True, cross_phase_same_pairs_only=True)
     same = r2['cross_phase_corr'].cpu().numpy().astype(np.float64)
-    ref2 = o.align_branches(d['x'][:2], same, mode='cross', pair_subset=o.autoc_idx)
-    assert same.shape == ref2.shape
-    check(same, ref2, 'same-pairs')
+    assert same.shape == (2, len(o.autoc_idx), d['cross'].shape[-1])
+    check(same, o, d['x'][:2], 'cross', 'same-pairs', o.autoc_idx, d['cross'][:2][:, o.autoc_idx])
 
 
 def test_within_autocorrelation_is_nonnegative_and_2d_input():
@@ -187,20 +229,17 @@ def test_transform_and_dense_forms_of_stage_b_agree(monkeypatch):
 
 
 @pytest.mark.parametrize('tag', ['S_constant', 'S_circular', 'S_over1'])
-@pytest.mark.parametrize('form', ['0', '1'])
+@pytest.mark.parametrize('form', ['tcgen05', 'mma.sync', 'transform'])
 def test_phase_options_match_oracle_and_reference(tag, form, monkeypatch):
     """border_mode 'constant' / 'circular' (kymatio_phase_scattering.py:162-173) and oversampling (:445), in the
-    dense form of stage B and -- where the decimation factor is a power of two -- the transform form."""
-    from tebscat import KymatioPhaseScattering1D
+    dense forms of stage B and -- where the decimation factor is a power of two -- the transform form."""
     d = np.load(os.path.join(GOLDEN, 'phase_%s.npz' % tag))
     J, Q, T, N, mo = CFG['S']
     border, over = str(d['border_mode']), int(d['oversampling'])
-    monkeypatch.setenv('TEBSCAT_PHASE_FFT', form)
-    m = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), max_order=mo,
-                                 border_mode=border, oversampling=over)
-    if form == '1' and m._plan.pair_plan is None:
+    m = module_of('S', form, monkeypatch, border_mode=border, oversampling=over)
+    if form == 'transform' and m._plan.pair_plan is None:
         pytest.skip('decimation factor %d is not a power of two' % m._plan.dec)
-    assert m._dev_plan(0).uses_fft_pairs == (form == '1')
+    assert m._dev_plan(0).uses_fft_pairs == (form == 'transform')
     x = torch.from_numpy(d['x']).cuda()
     o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1], border_mode=border)
     rw = m(x, compute_phase=True, phase_channels=[0])
@@ -211,9 +250,9 @@ def test_phase_options_match_oracle_and_reference(tag, form, monkeypatch):
         ours = ours.cpu().numpy().astype(np.float64)
         assert ours.shape == ref.shape
         xm = xin[:, 0] if mode == 'within' else xin
-        check(ours, o.align_branches(xm, ours, mode=mode), tag + '/' + mode)
+        check(ours, o, xm, mode, '%s/%s/%s' % (tag, form, mode), None, ref, randn_rows=range(xin.shape[0] // 2, xin.shape[0]))
         diff = (ours - o.align_branches(xm, ours, mode=mode)) - (ref - o.align_branches(xm, ref, mode=mode))
-        assert np.linalg.norm(diff) / np.linalg.norm(ref) < 1e-4, mode
+        assert np.linalg.norm(diff) / np.linalg.norm(ref) < 5e-5, mode
 
 
 @pytest.mark.parametrize('border', ['constant', 'circular'])
@@ -229,7 +268,7 @@ def test_border_modes_in_transform_form(border, monkeypatch):
     x = ctg_batch(3, N, seed=5)
     ours = m(x.cuda(), compute_phase=False, compute_cross_phase=True)['cross_phase_corr'].cpu().numpy().astype(np.float64)
     o = PhaseOracle(J, Q, T, N, 125, border_mode=border)
-    check(ours, o.align_branches(x.numpy(), ours, mode='cross'), border)
+    check(ours, o, x.numpy(), 'cross', 'transform form, border ' + border)      # noise floor: the single-precision oracle
     other = PhaseOracle(J, Q, T, N, 125)(x.numpy(), mode='cross')
     assert rel_l2(ours, other) > 1e-3                                     # and it is not the reflect result
 

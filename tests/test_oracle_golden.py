@@ -9,6 +9,7 @@ import pytest
 from oracle import filters_oracle as fo
 from oracle.scattering1d_oracle import ScatteringOracle
 from oracle.phase_oracle import PhaseOracle
+from helpers import phase_path_tolerance
 
 SCAT = ['H', 'P', 'S', 'T', 'O', 'L']
 
@@ -87,29 +88,45 @@ def test_torch_port_vs_reference(golden_dir, name):
     assert rel_l2(S, d['S'], axis=-1).max() < 2e-6
 
 
-@pytest.mark.parametrize('name', ['H', 'P', 'S'])
+def _pin_phase_oracle(o, x, ref, mode, sub, randn_rows, tag):
+    """float64 oracle vs the live reference's fp32 output, per path: within 1e-5 wherever single-precision
+    arithmetic allows it, and never further than 4x the distance between the single-precision and the float64
+    evaluation of the oracle itself (the reference rounds p * theta in fp32 with p up to 108)."""
+    xin = x[:, 0] if mode == 'within' else x
+    assert o(xin, mode=mode, pair_subset=sub).shape == ref.shape
+    aligned = o.align_branches(xin, ref, mode=mode, pair_subset=sub)
+    o32 = PhaseOracle(o.J, o.Q, o.T, o.N, o.n_out, border_mode=o.border_mode, cdtype=np.complex64)
+    y32 = o32(xin, mode=mode, pair_subset=sub).astype(np.float64)
+    tol = phase_path_tolerance(o.align_branches(xin, y32, mode=mode, pair_subset=sub), y32)
+    err = np.linalg.norm(aligned - ref, axis=-1)
+    rel = err / np.linalg.norm(aligned, axis=-1)
+    pw = o.powers if sub is None else o.powers[sub]
+    for b in randn_rows:
+        assert rel[b][pw < 32].max() <= 1e-5 and rel[b].max() <= 2.5e-5, (tag, mode, b, rel[b].max())
+    assert (err / tol).max() <= 1.0, (tag, mode, (err / tol).max())
+    assert rel_l2(aligned, ref) < 5e-5, (tag, mode, rel_l2(aligned, ref))
+
+
+@pytest.mark.parametrize('name', ['H', 'Hr', 'P', 'S'])
 def test_phase_vs_reference(golden_dir, name):
     d = load(golden_dir, 'phase_%s.npz' % name)
     J, Q, T, N = int(d['J']), int(d['Q']), int(d['T']), int(d['N'])
     n_out = d['scattering'].shape[-1]
     o = PhaseOracle(J, Q, T, N, n_out)
-    assert np.array_equal(o.center_freqs, d['center_freqs'])
-    assert np.array_equal(o.i_idx, d['i_idx']) and np.array_equal(o.j_idx, d['j_idx'])
-    assert np.array_equal(o.powers, d['powers'])
-    assert np.array_equal(o.autoc_idx, d['autoc_idx'])
-    x = d['x'][:2]
+    if 'powers' in d.files:
+        assert np.array_equal(o.center_freqs, d['center_freqs'])
+        assert np.array_equal(o.i_idx, d['i_idx']) and np.array_equal(o.j_idx, d['j_idx'])
+        assert np.array_equal(o.powers, d['powers'])
+        assert np.array_equal(o.autoc_idx, d['autoc_idx'])
+    B = d['x'].shape[0]
+    n_ctg = int(d['n_ctg']) if 'n_ctg' in d.files else B // 2          # make_golden: CTG rows first, randn rows behind
+    rows = [0, B - 1] if n_ctg else [0, 1]                              # one CTG and one randn row (bounded CPU time)
+    x = d['x'][rows]
     sub_w = np.nonzero(d['phase_mask'])[0] if bool(d['subset']) else None
     sub_c = np.nonzero(d['cross_mask'])[0] if bool(d['subset']) else None
-    for mode, ref, sub in (('within', d['within'][:2], sub_w), ('cross', d['cross'][:2], sub_c)):
-        xin = x[:, 0] if mode == 'within' else x
-        plain = o(xin, mode=mode, pair_subset=sub)
-        assert plain.shape == ref.shape
-        aligned = o.align_branches(xin, ref, mode=mode, pair_subset=sub)
-        overall = rel_l2(aligned, ref)
-        per_path = rel_l2(aligned, ref, axis=-1)
-        # fp32 reference vs fp64 oracle: p*theta is rounded in fp32 with p up to ~100
-        assert overall < 5e-5, (mode, overall, rel_l2(plain, ref))
-        assert np.median(per_path) < 5e-5 and per_path.max() < 2e-3, (mode, per_path.max())
+    randn_rows = [1] if n_ctg else [0, 1]
+    _pin_phase_oracle(o, x, d['within'][rows], 'within', sub_w, randn_rows, name)
+    _pin_phase_oracle(o, x, d['cross'][rows], 'cross', sub_c, randn_rows, name)
 
 
 @pytest.mark.parametrize('tag', ['S_constant', 'S_circular', 'S_over1'])
@@ -120,13 +137,8 @@ def test_phase_options_vs_reference(golden_dir, tag):
     J, Q, T, N = int(d['J']), int(d['Q']), int(d['T']), int(d['N'])
     o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1], border_mode=str(d['border_mode']))
     x = d['x']
-    for mode, ref in (('within', d['within']), ('cross', d['cross'])):
-        xin = x[:, 0] if mode == 'within' else x
-        assert o(xin, mode=mode).shape == ref.shape
-        aligned = o.align_branches(xin, ref, mode=mode)
-        per_path = rel_l2(aligned, ref, axis=-1)
-        assert rel_l2(aligned, ref) < 5e-5, (mode, rel_l2(aligned, ref))
-        assert np.median(per_path) < 5e-5 and per_path.max() < 2e-3, (mode, per_path.max())
+    _pin_phase_oracle(o, x, d['within'], 'within', None, [1], tag)
+    _pin_phase_oracle(o, x, d['cross'], 'cross', None, [1], tag)
 
 
 @pytest.mark.parametrize('name', ['T', 'S', 'P1', 'O', 'H'])

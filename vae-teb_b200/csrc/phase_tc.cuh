@@ -16,11 +16,15 @@
 //     K-major, 128-byte swizzle) into shared memory with cp.async;
 //   * ONE thread of the MMA warp issues tcgen05.mma.kind::tf32 (M = 128, N = 80, K = 8): 12 per slab, accumulating in
 //     TMEM; tcgen05.commit releases the slab's stage and hands finished accumulators to
-//   * 4 EPILOGUE warps, which drain an accumulator every kTcDrain slabs with tcgen05.ld and add it to running sums
-//     in fp32 registers (a tensor-core accumulator that runs over all K = 2N = 9600 would carry its truncation bias,
-//     see the mma.sync kernel), double-buffered so the drain overlaps the next group's MMAs.
+//   * 4 EPILOGUE warps, which drain the head-product accumulator every kTcDrain slabs with tcgen05.ld and add it to
+//     running sums in fp32 registers (a tensor-core accumulator that runs over all K = 2N = 9600 would carry its
+//     truncation bias, see the mma.sync kernel), double-buffered so the drain overlaps the next group's MMAs.  The
+//     correction products Al Bh + Ah Bl go to an accumulator of their own that is read once at the end: they are
+//     2^-11 of the result, so their own truncation error is irrelevant, and keeping them out of the head accumulator
+//     cuts the accumulations between two fp32 adds from 24 to 8 (measured: round-2 parity report in profiles/).
 // mbarriers: full[s] (producers -> MMA), empty[s] (MMA -> producers), acc_full[a] (MMA -> epilogue),
-// acc_empty[a] (epilogue -> MMA).  TMEM (512 columns): accumulators at 0 and 128, A' stages from 256.
+// acc_empty[a] (epilogue -> MMA).  TMEM (512 columns): head-product accumulators at 0 and 80, the accumulator of the
+// correction products at 160, A' stages from 256.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,8 +36,9 @@ constexpr int kTcCols = 80;           // output columns per CTA (UMMA N)
 constexpr int kTcSlabT = 16;          // time samples per slab
 constexpr int kTcK = 2 * kTcSlabT;    // K per slab (Re, -Im interleaved)
 constexpr int kTcStages = 4;
-constexpr int kTcDrain = 2;           // slabs per accumulator drain: 24 tensor-core accumulations between fp32 adds (the TMEM
-                                      // accumulator truncates like the register one: with 4 the error against the mma.sync kernel doubles)
+constexpr int kTcDrain = 2;           // slabs per drain of the head-product accumulator: 8 tensor-core accumulations between
+                                      // fp32 adds (the TMEM accumulator truncates like the register one: the error grows with
+                                      // the number of accumulations into one running sum)
 constexpr int kTcEpiWarps = 4, kTcProdWarps = 16, kTcGroups = 4;   // producer groups of four warps (one per TMEM lane quarter)
 constexpr int kTcMmaWarp = kTcEpiWarps;                          // warp 4
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 1 + kTcProdWarps);   // 672: 96 registers per thread
@@ -42,7 +47,10 @@ constexpr int kTcStageBytes = 2 * kTcBTile;                      // head + tail
 constexpr int kTcInBytes = 2 * kTcRows * 128;                    // one group's input slab: 128 lines of (|z|, theta) + 128 of (re, im)
 constexpr int kTcOffBars = kTcStages * kTcStageBytes + kTcGroups * kTcInBytes;
 constexpr size_t kTcSmem = 1024 + (size_t)kTcOffBars + 256 + 2 * kTcRows * sizeof(int32_t);
-constexpr uint32_t kTcAcc0 = 0, kTcAcc1 = 128, kTcA0 = 256;      // TMEM columns; A' stage s: head at kTcA0 + 64 s, tail + 32
+// TMEM columns: the two head-product accumulators (Ah Bh, drained every kTcDrain slabs), ONE accumulator of the
+// correction products (Al Bh + Ah Bl: 2^-11 of the head products, so its truncation error stays below 1e-7 of the
+// result even over the whole contraction -- it is read once, at the end), and the A' stages (head at kTcA0 + 64 s, tail + 32)
+constexpr uint32_t kTcAcc0 = 0, kTcAcc1 = 80, kTcAccS = 160, kTcA0 = 256;
 
 struct PairTcParams {
     const float2* zp;
@@ -137,13 +145,13 @@ __device__ __forceinline__ uint64_t tc_b_desc(uint32_t smem_addr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 80
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcCols >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
 
-// TF32 head and tail of v by truncation: head = the top 19 bits, tail = v - head (exact), of which the tensor core
-// again reads the top 19 bits.  v = head + tail holds exactly, the dropped tail bits are below 2^-20 |v| and the
-// product of the two tails (the term 3xTF32 leaves out) below 2^-21 |v b| -- fp32 class, in two instructions per
-// value on the ALU / FMA pipes (cvt.rna.tf32.f32 would occupy the 16-lane conversion unit that the sine and cosine
-// of every product already use).  B' is split with rounding on the host.
+// TF32 head and tail of v: head = v rounded to the top 19 bits (round half away from zero, as an integer add on the
+// bit pattern), tail = v - head (exact, |tail| <= 2^-12 |v|), of which the tensor core reads the top 19 bits: the
+// dropped tail bits are below 2^-23 |v| and the product of the two tails (the term 3xTF32 leaves out) below
+// 2^-24 |v b| -- three instructions per value on the ALU / FMA pipes (cvt.rna.tf32.f32 would occupy the 16-lane
+// conversion unit that the sine and cosine of every product already use).  B' is split with rounding on the host.
 __device__ __forceinline__ void tc_split(float v, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(v) & 0xffffe000u;
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
     lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
@@ -223,6 +231,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(acc_empty(a));
         }
+        {   // the correction products: complete with the last group's commit (a commit covers every earlier MMA)
+            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + kTcAccS;
+#pragma unroll
+            for (int j = 0; j < kTcCols / 8; ++j) {
+                float v[8];
+                tc_ld8(taddr + 8 * j, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) total[8 * j + i] += v[i];
+            }
+            tc_fence_before();
+        }
         const long long row = row0 + 32 * q + lane;
         if (row < p.rows) {
 #pragma unroll
@@ -243,15 +262,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 }
                 tc_mbar_wait(full(s), (i / kTcStages) & 1);
                 tc_fence_after();
-                const uint32_t d = tmem + (a ? kTcAcc1 : kTcAcc0);
+                const uint32_t d = tmem + (a ? kTcAcc1 : kTcAcc0), dc = tmem + kTcAccS;
                 const uint32_t a_hi = tmem + kTcA0 + 64 * s, a_lo = a_hi + 32;
                 const uint32_t b_hi = base + s * kTcStageBytes, b_lo = b_hi + kTcBTile;
 #pragma unroll
                 for (int k = 0; k < kTcK / 8; ++k) {
                     const uint64_t dh = tc_b_desc(b_hi + 32 * k), dl = tc_b_desc(b_lo + 32 * k);
                     tc_mma_ts(d, a_hi + 8 * k, dh, kTcIdesc, (first && k == 0) ? 0u : 1u);
-                    tc_mma_ts(d, a_lo + 8 * k, dh, kTcIdesc, 1u);
-                    tc_mma_ts(d, a_hi + 8 * k, dl, kTcIdesc, 1u);
+                    tc_mma_ts(dc, a_lo + 8 * k, dh, kTcIdesc, (i == 0 && k == 0) ? 0u : 1u);
+                    tc_mma_ts(dc, a_hi + 8 * k, dl, kTcIdesc, 1u);
                 }
                 tc_commit(empty(s));                                          // the stage is free once these MMAs retire
                 if ((i % kTcDrain) == kTcDrain - 1 || i == n_slabs - 1) tc_commit(acc_full(a));

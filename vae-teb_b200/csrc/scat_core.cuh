@@ -84,6 +84,8 @@ constexpr int kMaxPairRows = 8;    // (sample, pair) rows of one phase stage-B j
 
 struct SignalCtx {
     const float* x;          // this signal's N input samples
+    const float* win;        // optional analysis window applied to the samples as they are loaded ([N] or null): the
+                             // Tukey taper of KymatioPhaseScattering1D(tukey_alpha=...) (kymatio_phase_scattering.py:362-392, :405-407)
     float* out;              // this signal's [n_paths, n_out] block
     const int32_t* chan;     // channel table of the batched stores
     float2* zc;              // phase stage A: analytic signals of this job, cartesian [F][N]
@@ -807,6 +809,7 @@ TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
     const int Np = 1 << c.log2_Np;
     const int N = c.N, pad_left = c.pad_left, border = c.border;
     const float* x = c.x;
+    const float* win = c.win;
     for (int i0 = lt; i0 < Np; i0 += 8 * t.nt) {
         float v[8];
         TEB_UNROLL for (int j = 0; j < 8; ++j) {
@@ -823,6 +826,7 @@ TEB_D void load_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
                 inside = inside && r >= 0 && r < N;
             }
             v[j] = inside ? TEB_LDG(x + r) : 0.f;
+            if (win && inside) v[j] *= TEB_LDG(win + r);
         }
         TEB_UNROLL for (int j = 0; j < 8; ++j) {
             const int i = i0 + j * t.nt;

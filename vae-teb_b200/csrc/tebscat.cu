@@ -44,6 +44,7 @@ static int fail(int code, const char* fmt, ...) {
 // ---------------------------------------------------------------------------------
 struct KParams {
     const float* arena;      // filters, fp32, bit-reversed bin order
+    const float* win;        // optional analysis window of OP_LOAD ([N] or null)
     const float2* tw;        // kTwA coarse + kTwB fine twiddles
     const int4* warp_tab;    // [n_steps][kWarps] x 3 int4: the task of every warp in every step
     const int32_t* chan;     // channel table of the batched stores
@@ -124,6 +125,7 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         if (tid == 0) {
             c.x = x + b * p.x_stride;
+            c.win = p.win;
             c.out = out + b * (long long)p.n_paths * (p.ep_mean ? p.n_out - 2 * p.ep_trim : p.n_out);
             c.ep_mean = p.ep_mean;
             c.ep_std = p.ep_std;
@@ -239,6 +241,7 @@ struct tebscat_plan {
     float2* d_tw = nullptr;
     int32_t* d_warp_tab = nullptr;
     int32_t* d_chan = nullptr;
+    float* d_win = nullptr;
     KParams kp;
     HostPipe pipe;
     std::mutex pipe_mu;
@@ -250,6 +253,15 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
     for (int s = 0; s < d.n_steps; ++s) {
         const int b = steps[2 * s], e = steps[2 * s + 1];
         if (b < 0 || e < b || e > d.n_tasks) return fail(TEBSCAT_EINVAL, "step %d: bad task range [%d,%d)", s, b, e);
+        // the tasks of a step own disjoint warps (a warp executes ONE task per step)
+        unsigned busy = 0;
+        for (int i = b; i < e; ++i) {
+            const int32_t* t = tasks + kTaskInts * i;
+            if ((t[0] & 0xff) == OP_NOP || t[1] < 0 || t[2] <= 0 || t[1] + t[2] > kThreads || ((t[1] | t[2]) & 31)) continue;
+            const unsigned m = (t[2] >= 32 * 32 ? ~0u : ((1u << (t[2] / 32)) - 1u)) << (t[1] / 32);
+            if (busy & m) return fail(TEBSCAT_EINVAL, "step %d: overlapping thread ranges", s);
+            busy |= m;
+        }
     }
     auto fits = [&](int64_t off, int64_t len) { return off >= 0 && (off & 15) == 0 && ((off + len + 15) & ~(int64_t)15) <= cap; };
     for (int i = 0; i < d.n_tasks; ++i) {
@@ -416,7 +428,8 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
             const int32_t* t = tasks + kTaskInts * ti;
             for (int w = t[1] / 32; w < (t[1] + t[2]) / 32; ++w) {
                 int32_t* rec = wt.data() + ((size_t)st * kWarps + w) * kTaskInts;
-                if ((rec[0] & 0xff) != OP_NOP) { delete p; return fail(TEBSCAT_EINVAL, "step %d: overlapping thread ranges", st); }
+                // (validate_schedule has rejected overlapping ranges; the guard owns the plan on every error path)
+                if ((rec[0] & 0xff) != OP_NOP) return fail(TEBSCAT_EINVAL, "step %d: overlapping thread ranges", st);
                 memcpy(rec, t, kTaskInts * sizeof(int32_t));
             }
         }
@@ -445,13 +458,12 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     CU(cudaFuncSetAttribute(scat1d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(prop.sharedMemPerBlockOptin - fa1.sharedSizeBytes)));
     if (p->smem_bytes + fa0.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin ||
-        p->smem_bytes + fa1.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) {
-        tebscat_plan_destroy(p);
-        return fail(TEBSCAT_EUNSUPPORTED, "schedule needs more shared memory than the device offers");
-    }
+        p->smem_bytes + fa1.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(TEBSCAT_EUNSUPPORTED, "schedule needs more shared memory than the device offers");   // guard frees the plan
 
     KParams& k = p->kp;
     k.arena = p->d_arena;
+    k.win = nullptr;
     k.tw = p->d_tw;
     k.warp_tab = reinterpret_cast<const int4*>(p->d_warp_tab);
     k.chan = p->d_chan;
@@ -506,7 +518,33 @@ extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
     cudaFree(p->d_tw);
     cudaFree(p->d_warp_tab);
     cudaFree(p->d_chan);
+    cudaFree(p->d_win);
     delete p;
+}
+
+// Analysis window of the plan's loads: x[t] * w[t] before padding (the Tukey taper of
+// KymatioPhaseScattering1D, hdf5_dataset/kymatio_phase_scattering.py:362-392, applied at :405-407).
+// window_host: N floats, or NULL to remove it.  Not re-entrant with forward calls on the same plan.
+extern "C" int tebscat_plan_set_window(tebscat_plan* p, const float* window_host) {
+    if (!p) return fail(TEBSCAT_EINVAL, "null plan");
+    int prev = 0;
+    CU(cudaGetDevice(&prev));
+    CU(cudaSetDevice(p->device));
+    int rc = TEBSCAT_OK;
+    do {
+        if (!window_host) { p->kp.win = nullptr; break; }
+        if (!p->d_win && cudaMalloc(&p->d_win, (size_t)p->desc.N * sizeof(float)) != cudaSuccess) {
+            rc = fail(TEBSCAT_ECUDA, "cudaMalloc of the window failed");
+            break;
+        }
+        if (cudaMemcpy(p->d_win, window_host, (size_t)p->desc.N * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            rc = fail(TEBSCAT_ECUDA, "upload of the window failed");
+            break;
+        }
+        p->kp.win = p->d_win;
+    } while (0);
+    cudaSetDevice(prev);
+    return rc;
 }
 
 static int launch_scat1d(const tebscat_plan* p, const float* x, int64_t B, float* S, cudaStream_t st) {
@@ -927,6 +965,13 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
     delete p;
 }
 
+// the window acts where the samples enter: stage A's loads (both channels go through the same stage-A plan)
+extern "C" int tebscat_phase_plan_set_window(tebscat_phase_plan* p, const float* window_host) {
+    if (!p) return fail(TEBSCAT_EINVAL, "null plan");
+    std::lock_guard<std::mutex> lock(p->mu);
+    return tebscat_plan_set_window(p->stage_a, window_host);
+}
+
 // The dense form of stage B: tcgen05 + TMEM (phase_tc.cuh) unless TEBSCAT_PHASE_MMA=sync asks for the mma.sync kernel.
 static bool use_tcgen05_pairs() {
     const char* e = getenv("TEBSCAT_PHASE_MMA");          // read per call: the tests switch it
@@ -1178,6 +1223,8 @@ struct tebscat_large {
     tebscat_plan* tile[kLog2TwMax + 1][3][2] = {};
     int tile_slots[kLog2TwMax + 1][3][2] = {};      // complex elements one job of the plan covers
     float2* d_tw[kLargeMaxLog2 + 1] = {};           // W_L^m, m < L, for L = 2^14 .. 2^17
+    float* d_win = nullptr;                         // optional analysis window of pad_load / pad_adjoint
+    int win_n = 0;
 };
 
 extern "C" int tebscat_large_create(int device, tebscat_large** out) {
@@ -1211,7 +1258,22 @@ extern "C" void tebscat_large_destroy(tebscat_large* g) {
         for (int d = 0; d < 3; ++d)
             for (int z = 0; z < 2; ++z) tebscat_plan_destroy(g->tile[n][d][z]);
     for (int n = 0; n <= kLargeMaxLog2; ++n) cudaFree(g->d_tw[n]);
+    cudaFree(g->d_win);
     delete g;
+}
+
+// analysis window of pad_load / pad_adjoint (see tebscat_plan_set_window): n floats, or NULL to remove it
+extern "C" int tebscat_large_set_window(tebscat_large* g, const float* window_host, int n) {
+    if (!g || (window_host && n < 1)) return fail(TEBSCAT_EINVAL, "bad window");
+    CU(cudaSetDevice(g->device));
+    cudaFree(g->d_win);
+    g->d_win = nullptr;
+    g->win_n = 0;
+    if (!window_host) return TEBSCAT_OK;
+    CU(cudaMalloc(&g->d_win, (size_t)n * sizeof(float)));
+    CU(cudaMemcpy(g->d_win, window_host, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    g->win_n = n;
+    return TEBSCAT_OK;
 }
 
 /* Hand a tile plan (schedule.build_tile_plan) for transforms of 2^log2_len samples to the context (it takes ownership). */
@@ -1228,14 +1290,17 @@ extern "C" int tebscat_large_set_tile_plan(tebscat_large* g, int log2_len, int k
 }
 
 // reflect padding (torch_backend.py:50-78) + real -> complex, natural order
-__global__ void g_pad_load_kernel(const float* __restrict__ x, float2* __restrict__ u, long long B, int N, int pad_left, int log2_Np) {
+__global__ void g_pad_load_kernel(const float* __restrict__ x, float2* __restrict__ u, long long B, int N, int pad_left, int log2_Np,
+                                  const float* __restrict__ win) {
     const long long total = B << log2_Np;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long b = e >> log2_Np;
         int r = (int)(e - (b << log2_Np)) - pad_left;
         if (r < 0) r = -r;
         if (r >= N) r = 2 * (N - 1) - r;
-        u[e] = make_float2(__ldg(x + b * N + r), 0.f);
+        float v = __ldg(x + b * N + r);
+        if (win) v *= __ldg(win + r);
+        u[e] = make_float2(v, 0.f);
     }
 }
 
@@ -1428,7 +1493,9 @@ extern "C" int tebscat_large_pad_load(tebscat_large* g, const float* x_dev, int6
     if (!g || !x_dev || !u_dev || B < 1 || N < 2 || pad_left < 0 || pad_left >= N || ((1LL << log2_Np) - N - pad_left) >= N)
         return fail(TEBSCAT_EINVAL, "Indefinite padding size (larger than tensor).");
     CU(cudaSetDevice(g->device));
-    g_pad_load_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(x_dev, reinterpret_cast<float2*>(u_dev), B, N, pad_left, log2_Np);
+    if (g->d_win && g->win_n != N) return fail(TEBSCAT_EINVAL, "window of %d samples on signals of %d", g->win_n, N);
+    g_pad_load_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(x_dev, reinterpret_cast<float2*>(u_dev), B, N, pad_left, log2_Np,
+                                                                       g->d_win);
     CU(cudaGetLastError());
     ++g_launches;
     return TEBSCAT_OK;
@@ -1783,7 +1850,8 @@ extern "C" int tebscat_large_unstore(tebscat_large* g, const float* gout_dev, in
 }
 
 // adjoint of g_pad_load_kernel: gx[b, r] = Re gu[b, pad_left + r] + its left and right mirror images (pad < N: one fold)
-__global__ void g_pad_adjoint_kernel(const float2* __restrict__ gu, float* __restrict__ gx, long long B, int N, int pad_left, int log2_Np) {
+__global__ void g_pad_adjoint_kernel(const float2* __restrict__ gu, float* __restrict__ gx, long long B, int N, int pad_left, int log2_Np,
+                                     const float* __restrict__ win) {
     const long long total = B * N;
     const int pad_right = (1 << log2_Np) - N - pad_left;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -1793,6 +1861,7 @@ __global__ void g_pad_adjoint_kernel(const float2* __restrict__ gu, float* __res
         float v = row[pad_left + r].x;
         if (r >= 1 && r <= pad_left) v += row[pad_left - r].x;
         if (r <= N - 2 && r >= N - 1 - pad_right) v += row[pad_left + 2 * (N - 1) - r].x;
+        if (win) v *= __ldg(win + r);
         gx[e] = v;
     }
 }
@@ -1802,8 +1871,9 @@ extern "C" int tebscat_large_pad_adjoint(tebscat_large* g, const float* gu_dev, 
     if (!g || !gx_dev || !gu_dev || B < 1 || N < 2 || pad_left < 0 || pad_left >= N || ((1LL << log2_Np) - N - pad_left) >= N)
         return fail(TEBSCAT_EINVAL, "Indefinite padding size (larger than tensor).");
     CU(cudaSetDevice(g->device));
+    if (g->d_win && g->win_n != N) return fail(TEBSCAT_EINVAL, "window of %d samples on signals of %d", g->win_n, N);
     g_pad_adjoint_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(gu_dev), gx_dev, B, N, pad_left,
-                                                                          log2_Np);
+                                                                          log2_Np, g->d_win);
     CU(cudaGetLastError());
     ++g_launches;
     return TEBSCAT_OK;

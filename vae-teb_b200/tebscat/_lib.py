@@ -58,6 +58,12 @@ def load():
     lib.tebscat_plan_create.restype = ctypes.c_int
     lib.tebscat_plan_create.argtypes = [ctypes.POINTER(PlanDesc), fp, ctypes.c_size_t, i32p, i32p,
                                         i32p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.tebscat_plan_set_window.restype = ctypes.c_int
+    lib.tebscat_plan_set_window.argtypes = [vp, fp]
+    lib.tebscat_phase_plan_set_window.restype = ctypes.c_int
+    lib.tebscat_phase_plan_set_window.argtypes = [vp, fp]
+    lib.tebscat_large_set_window.restype = ctypes.c_int
+    lib.tebscat_large_set_window.argtypes = [vp, fp, ctypes.c_int]
     lib.tebscat_plan_destroy.restype = None
     lib.tebscat_plan_destroy.argtypes = [vp]
     lib.tebscat_scat1d_forward.restype = ctypes.c_int

@@ -112,7 +112,6 @@ class Scattering1D(nn.Module):
         self._plans = {}
         self._host_plan = None
         self._sched = None
-        self._op_by_op = False            # True once the fused schedule turned out not to fit (see _forward_array)
 
     # ---- base_frontend.py:27-77 ------------------------------------------------
     def build(self):
@@ -186,12 +185,33 @@ class Scattering1D(nn.Module):
 
     # ---- plan handling -------------------------------------------------------------
     def _schedule(self):
+        """Fused schedule of the current (J, N, Q, T, max_order, oversampling); raises NotImplementedError when the
+        configuration does not fit the single-kernel design.  Both outcomes are cached under that key, so mutating
+        `T` / `oversampling` afterwards re-decides (the reference re-reads its attributes on every call too)."""
         key = (self.J, self.N, self._Q1, self.T, self.max_order, int(self.oversampling))
         if self._sched is None or self._sched[0] != key:
-            self._sched = (key, build_plan(self.J, self.N, self._Q1, self.T, self.max_order,
-                                           oversampling=int(self.oversampling)))
+            try:
+                plan = build_plan(self.J, self.N, self._Q1, self.T, self.max_order, oversampling=int(self.oversampling))
+            except NotImplementedError as e:
+                plan = e
+            self._sched = (key, plan)
             self._plans = {}
+        if isinstance(self._sched[1], NotImplementedError):
+            raise NotImplementedError(str(self._sched[1]))
         return self._sched[1]
+
+    @property
+    def _op_by_op(self):
+        """True when the fused single-kernel schedule cannot hold the current configuration in shared memory (output-rate
+        lengths of 2048 samples and more, i.e. T <= 4 at a padded length of 8192): the op-by-op level of tebscat/large.py
+        serves it -- the same CUDA ops, one launch each.  Part of the schedule key, not a sticky flag."""
+        if self.J_pad > LOG2_NP_MAX:
+            return False
+        try:
+            self._schedule()
+            return False
+        except NotImplementedError:
+            return True
 
     def _plan_for(self, device_index):
         sched = self._schedule()
@@ -268,14 +288,6 @@ class Scattering1D(nn.Module):
         dev = x2.device
         index = dev.index if dev.index is not None else torch.cuda.current_device()
         B = x2.shape[0]
-        if self.J_pad <= LOG2_NP_MAX and not self._op_by_op:
-            try:
-                self._schedule()
-            except NotImplementedError:
-                # a valid configuration the fused single-kernel schedule cannot hold in shared memory (output-rate
-                # lengths of 2048 samples and more, i.e. T <= 4 at a padded length of 8192): the op-by-op level of
-                # tebscat/large.py serves it -- the same CUDA ops, one launch each
-                self._op_by_op = True
         if self.J_pad > LOG2_NP_MAX or self._op_by_op:
             lp, ldp = self._large_plan_for(index)
             S = torch.empty((B, lp.n_paths, lp.n_out), dtype=torch.float32, device=dev)
