@@ -143,6 +143,10 @@ def phase_option_fixture(tag, name, B, **opts):
         os.path.join(OUT, 'phase_%s.npz' % tag),
         J=J, Q=Q, T=T, N=N, max_order=max_order, x=x.numpy(),
         border_mode=opts.get('border_mode', 'reflect'), oversampling=opts.get('oversampling', 0),
+        tukey_alpha=float(opts.get('tukey_alpha') or 0.0),
+        window=m._create_tukey_window(N, opts.get('tukey_alpha'), torch.device('cpu')).numpy(),
+        window_odd=m._create_tukey_window(777, 0.5, torch.device('cpu')).numpy(),
+        window_hann=m._create_tukey_window(64, 1.0, torch.device('cpu')).numpy(),
         scattering=rw['scattering'].numpy(), within=rw['phase_corr'].numpy(), cross=rc['cross_phase_corr'].numpy(),
     )
     print(tag, 'phase', rw['phase_corr'].shape, rc['cross_phase_corr'].shape)
@@ -152,11 +156,15 @@ def phase_option_fixtures():
     phase_option_fixture('S_constant', 'S', 1, border_mode='constant')
     phase_option_fixture('S_circular', 'S', 1, border_mode='circular')
     phase_option_fixture('S_over1', 'S', 1, oversampling=1)
+    phase_option_fixture('S_tukey', 'S', 1, tukey_alpha=0.25)
 
 
 if __name__ == '__main__':
     if sys.argv[1:] == ['phase-randn']:
         phase_fixture_randn('Hr', 'H', 4)
+        sys.exit(0)
+    if sys.argv[1:] == ['phase-tukey']:
+        phase_option_fixture('S_tukey', 'S', 1, tukey_alpha=0.25)
         sys.exit(0)
     if sys.argv[1:] == ['phase-options']:
         phase_option_fixtures()

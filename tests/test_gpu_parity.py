@@ -294,3 +294,40 @@ def test_configurations_beyond_the_fused_schedule(cfg):
     (out * w.cuda()).sum().backward()
     _, g64 = GradOracle(J, N, Q, T, mo).vjp(x.detach().cpu().numpy(), w.numpy())
     assert rel_l2(x.grad.cpu().numpy(), g64, axis=-1).max() < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cfg', [('T', None), ('T', 1), ('L', None)])
+def test_analysis_window_on_every_level(cfg):
+    """Scattering1D.set_window: the taper the kernels' loads apply (the Tukey option of the phase module,
+    kymatio_phase_scattering.py:405-407) equals tapering the input first -- on the fused level, the op-by-op level
+    (forced through a configuration the fused schedule cannot hold) and the large-support level, forward and
+    backward (gradient of a windowed transform = window * gradient)."""
+    from tebscat import Scattering1D
+    name, force_T = cfg
+    if name == 'L':
+        J, N, Q, T, mo = 6, 9000, 4, 64, 2
+    else:
+        J, N, Q, T, mo = CONFIGS[name]
+    if force_T is not None:
+        J, N, Q, T, mo = 6, 4800, 8, 4, 1                 # output rate 2048 at Np = 8192: op-by-op level
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, N, generator=g).cuda()
+    w = torch.linspace(0.2, 1.0, N).cuda() * torch.cos(torch.linspace(0, 3.0, N)).cuda().abs()
+    plain = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    tapered = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    tapered.set_window(w.cpu().numpy())
+    assert tapered._op_by_op == (force_T is not None)
+    ref, _ = plain((x * w).contiguous())
+    out, _ = tapered(x)
+    assert torch.equal(out, ref)
+    out2, _ = tapered(x)                                   # graph replay on the large levels
+    assert torch.equal(out2, ref)
+    xg = x.clone().requires_grad_(True)
+    wgt = torch.randn(ref.shape, generator=torch.Generator().manual_seed(12)).cuda()
+    (tapered(xg)[0] * wgt).sum().backward()
+    xr = (x * w).contiguous().requires_grad_(True)
+    (plain(xr)[0] * wgt).sum().backward()
+    assert torch.allclose(xg.grad, xr.grad * w, rtol=1e-6, atol=1e-6 * float(xr.grad.abs().max()))
+    tapered.set_window(None)
+    assert torch.equal(tapered(x)[0], plain(x)[0])

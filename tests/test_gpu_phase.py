@@ -228,15 +228,20 @@ def test_transform_and_dense_forms_of_stage_b_agree(monkeypatch):
         assert err[strong].max() < 2e-5, err[strong].max()
 
 
-@pytest.mark.parametrize('tag', ['S_constant', 'S_circular', 'S_over1'])
+@pytest.mark.parametrize('tag', ['S_constant', 'S_circular', 'S_over1', 'S_tukey'])
 @pytest.mark.parametrize('form', ['tcgen05', 'mma.sync', 'transform'])
 def test_phase_options_match_oracle_and_reference(tag, form, monkeypatch):
-    """border_mode 'constant' / 'circular' (kymatio_phase_scattering.py:162-173) and oversampling (:445), in the
-    dense forms of stage B and -- where the decimation factor is a power of two -- the transform form."""
+    """border_mode 'constant' / 'circular' (kymatio_phase_scattering.py:162-173), oversampling (:445) and the Tukey
+    taper (:362-392, :405-407 -- applied by the kernels' loads here), in the dense forms of stage B and -- where
+    the decimation factor is a power of two -- the transform form."""
     d = np.load(os.path.join(GOLDEN, 'phase_%s.npz' % tag))
     J, Q, T, N, mo = CFG['S']
     border, over = str(d['border_mode']), int(d['oversampling'])
-    m = module_of('S', form, monkeypatch, border_mode=border, oversampling=over)
+    alpha = float(d['tukey_alpha']) if 'tukey_alpha' in d.files and float(d['tukey_alpha']) > 0 else None
+    opts = dict(border_mode=border, oversampling=over)
+    if alpha is not None:
+        opts['tukey_alpha'] = alpha
+    m = module_of('S', form, monkeypatch, **opts)
     if form == 'transform' and m._plan.pair_plan is None:
         pytest.skip('decimation factor %d is not a power of two' % m._plan.dec)
     assert m._dev_plan(0).uses_fft_pairs == (form == 'transform')
@@ -246,6 +251,8 @@ def test_phase_options_match_oracle_and_reference(tag, form, monkeypatch):
     rc = m(x, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1])
     assert rel_l2(rw['scattering'].cpu().numpy(), d['scattering']) < 2e-6
     xin = d['x']
+    if alpha is not None:                       # the oracle sees the tapered signal (the reference tapers in fp32)
+        xin = xin * d['window']
     for ours, ref, mode in ((rw['phase_corr'], d['within'], 'within'), (rc['cross_phase_corr'], d['cross'], 'cross')):
         ours = ours.cpu().numpy().astype(np.float64)
         assert ours.shape == ref.shape

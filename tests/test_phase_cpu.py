@@ -136,3 +136,16 @@ def test_stage_a_and_pair_stage_border_modes_emulated(border):
     assert out.shape == ref.shape and not np.isnan(out).any()
     err = np.linalg.norm(out - ref, axis=-1) / np.linalg.norm(ref, axis=-1)
     assert err.max() < 1e-5, err
+
+
+def test_tukey_window_matches_reference():
+    """_create_tukey_window (kymatio_phase_scattering.py:362-392) of the live reference, stored by
+    oracle/make_golden.py: interior taper, odd length, and the alpha >= 1 (Hann) branch; degenerate alphas."""
+    from tebscat.phase import tukey_window
+    d = np.load(os.path.join(GOLDEN, 'phase_S_tukey.npz'))
+    for key, n, alpha in (('window', 1000, 0.25), ('window_odd', 777, 0.5), ('window_hann', 64, 1.0)):
+        w = tukey_window(n, alpha)
+        assert w.shape == d[key].shape and np.abs(w - d[key]).max() < 5e-7, key
+    assert np.array_equal(tukey_window(50, None), np.ones(50)) and np.array_equal(tukey_window(50, 0.0), np.ones(50))
+    assert np.array_equal(tukey_window(50, 1.5), np.ones(50))        # outside (0, 1]: rectangular, like the reference
+    assert np.array_equal(tukey_window(5, 0.2), np.ones(5))          # taper shorter than one sample

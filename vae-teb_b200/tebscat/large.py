@@ -116,7 +116,7 @@ class LargeDevicePlan:
                 for slots in sch.TILE_SLOTS:
                     _TilePlanOwner(handle, nlen, kind, device_index, slots)
         self.arena = torch.from_numpy(np.ascontiguousarray(plan.arena, np.float32)).to(torch.device('cuda', device_index))
-        self._ws = {}
+        self._ws, self._bws, self._graphs, self._seen = {}, {}, {}, {}
 
     def __del__(self):
         try:
@@ -126,43 +126,94 @@ class LargeDevicePlan:
         except Exception:
             pass
 
+    # ---- workspaces and CUDA graphs ------------------------------------------------------------------------------
+    # One grow-only workspace per direction, sized for the largest batch seen (a smaller batch uses a prefix): a
+    # loader whose last batch is short, or a batch chunked with a remainder, does not reallocate anything.  Graphs
+    # are cached per (batch size, buffers) in a small LRU; growing a workspace drops the graphs that captured it.
+    GRAPH_SLOTS = 6
+
     def _workspace(self, B, dev):
-        key = (B, dev.index)
-        if key not in self._ws:
+        if B > self._ws.get('cap', 0) or self._ws.get('dev') != dev.index:
             Np = 1 << self.plan.geo.J_pad
-            self._ws = {key: (torch.empty(B * Np * 2, dtype=torch.float32, device=dev),          # U0
-                              torch.empty(B * Np * 2, dtype=torch.float32, device=dev),          # first-order work
-                              torch.empty(B * (2 << self.plan.max_l2), dtype=torch.float32, device=dev),   # second-order work
-                              torch.empty(B * (2 << self.plan.lf), dtype=torch.float32, device=dev))}   # leaf
-        return self._ws[key]
+            self._ws = dict(cap=B, dev=dev.index, bufs=(
+                torch.empty(B * Np * 2, dtype=torch.float32, device=dev),                       # U0
+                torch.empty(B * Np * 2, dtype=torch.float32, device=dev),                       # first-order work
+                torch.empty(B * (2 << self.plan.max_l2), dtype=torch.float32, device=dev),      # second-order work
+                torch.empty(B * (2 << self.plan.lf), dtype=torch.float32, device=dev)))         # leaf
+            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != 'fwd'}
+        return self._ws['bufs']
+
+    def invalidate_graphs(self):
+        """Forget every captured graph (a plan-level setting the kernels read through the context has changed)."""
+        self._graphs = {}
+        self._seen = {}
+
+    def _graphed(self, kind, run, args, ins, outs):
+        """Run `run(*args)` through a CUDA graph.  `ins` / `outs`: the caller-owned tensors among `args`.
+
+        A forward is a few thousand short launches (a backward ~1200 at the headline configuration): below ~1000
+        signals they, not the arithmetic, set the time, so the op list of a batch size is captured once and replayed.
+        When a call comes with buffers that were seen before (steady-state loops reuse addresses), the graph is
+        captured ON those buffers and replays with no staging copy at all; a first sighting goes through a graph on
+        static buffers (one copy in, one copy out)."""
+        import os
+        if os.environ.get('TEBSCAT_LARGE_GRAPH', '1') == '0':
+            return run(*args)
+        dev = args[0].device
+        B = args[0].shape[0]
+        ptrs = tuple(t.data_ptr() for t in args)
+        direct_key = (kind, B, dev.index) + ptrs
+        staged_key = (kind, B, dev.index)
+        entry = self._graphs.get(direct_key)
+        if entry is None and self._seen.get(direct_key, 0) >= 1:
+            entry = self._capture(run, args, dev)
+            self._remember(direct_key, entry)
+        if entry is not None:
+            self._graphs[direct_key] = self._graphs.pop(direct_key)      # most recently used last
+            entry['graph'].replay()
+            return args[-1]
+        if len(self._seen) > 64:
+            self._seen = {}
+        self._seen[direct_key] = self._seen.get(direct_key, 0) + 1
+        entry = self._graphs.get(staged_key)
+        if entry is None:
+            static = tuple(torch.empty_like(t) for t in args)
+            for t, sbuf in zip(args, static):
+                if any(t is i for i in ins):
+                    sbuf.copy_(t)
+            entry = self._capture(run, static, dev)
+            entry['static'] = static
+            self._remember(staged_key, entry)
+        else:
+            self._graphs[staged_key] = self._graphs.pop(staged_key)
+        for t, sbuf in zip(args, entry['static']):
+            if any(t is i for i in ins):
+                sbuf.copy_(t)
+        entry['graph'].replay()
+        for t, sbuf in zip(args, entry['static']):
+            if any(t is o for o in outs):
+                t.copy_(sbuf)
+        return args[-1]
+
+    def _capture(self, run, args, dev):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            run(*args)                                               # warm-up outside the capture (workspace allocation)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # other threads (e.g. DDP's reducer) keep working
+            run(*args)
+        return dict(graph=graph, static=None)
+
+    def _remember(self, key, entry):
+        self._graphs[key] = entry
+        while len(self._graphs) > self.GRAPH_SLOTS:
+            self._graphs.pop(next(iter(self._graphs)))
 
     def forward(self, x2, out):
-        """x2: (B, N) float32 CUDA contiguous; out: (B, C, n_out) float32 CUDA.  The op list of one batch size is
-        captured once into a CUDA graph and replayed: a forward is a few thousand short launches, and without the
-        graph a third of the time at Np = 2^14 is launch overhead."""
-        import os
-        B, dev = x2.shape[0], x2.device
-        if os.environ.get('TEBSCAT_LARGE_GRAPH', '1') == '0':
-            return self._run(x2, out)
-        key = (B, dev.index)
-        if getattr(self, '_graph_key', None) != key:
-            self._graph_key, self._graph = None, None
-            xs = torch.empty_like(x2)
-            os_ = torch.empty_like(out)
-            xs.copy_(x2)
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                self._run(xs, os_)                                   # warm-up outside the capture (workspace allocation)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # other threads (e.g. DDP's reducer) keep working
-                self._run(xs, os_)
-            self._graph_key, self._graph, self._gx, self._gout = key, graph, xs, os_
-        self._gx.copy_(x2)
-        self._graph.replay()
-        out.copy_(self._gout)
-        return out
+        """x2: (B, N) float32 CUDA contiguous; out: (B, C, n_out) float32 CUDA."""
+        return self._graphed('fwd', self._run, (x2, out), ins=(x2,), outs=(out,))
 
     def _run(self, x2, out):
         p, lib, g = self.plan, self._lib, self.handle
@@ -211,42 +262,17 @@ class LargeDevicePlan:
 
     # ---- backward pass --------------------------------------------------------------------------------
     def _bwd_workspace(self, B, dev):
-        key = ('bwd', B, dev.index)
-        if getattr(self, '_bws_key', None) != key:
+        if B > self._bws.get('cap', 0) or self._bws.get('dev') != dev.index:
             Np = 1 << self.plan.geo.J_pad
-            self._bws = tuple(torch.empty(B * Np * 2, dtype=torch.float32, device=dev) for _ in range(8)) + \
-                (torch.empty(B * (2 << self.plan.lf), dtype=torch.float32, device=dev),)
-            self._bws_key = key
-        return self._bws
+            self._bws = dict(cap=B, dev=dev.index, bufs=tuple(
+                torch.empty(B * Np * 2, dtype=torch.float32, device=dev) for _ in range(8)) +
+                (torch.empty(B * (2 << self.plan.lf), dtype=torch.float32, device=dev),))
+            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != 'bwd'}
+        return self._bws['bufs']
 
     def backward(self, x2, gout, gx):
-        """gx = (dS/dx)^T gout.  Like the forward of this level, the op list of one batch size (about 1200 short
-        launches at the headline configuration: below ~1000 signals they, not the arithmetic, set the time) is
-        captured once into a CUDA graph and replayed."""
-        import os
-        B, dev = x2.shape[0], x2.device
-        if os.environ.get('TEBSCAT_LARGE_GRAPH', '1') == '0':
-            return self._run_backward(x2, gout, gx)
-        key = (B, dev.index)
-        if getattr(self, '_bgraph_key', None) != key:
-            self._bgraph_key, self._bgraph = None, None
-            xs, gs, gxs = torch.empty_like(x2), torch.empty_like(gout), torch.empty_like(gx)
-            xs.copy_(x2)
-            gs.copy_(gout)
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                self._run_backward(xs, gs, gxs)                      # warm-up outside the capture (workspace allocation)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # other threads (e.g. DDP's reducer) keep working
-                self._run_backward(xs, gs, gxs)
-            self._bgraph_key, self._bgraph, self._bgx, self._bgs, self._bgxs = key, graph, xs, gs, gxs
-        self._bgx.copy_(x2)
-        self._bgs.copy_(gout)
-        self._bgraph.replay()
-        gx.copy_(self._bgxs)
-        return gx
+        """gx = (dS/dx)^T gout, through the graph cache of `_graphed`."""
+        return self._graphed('bwd', self._run_backward, (x2, gout, gx), ins=(x2, gout), outs=(gx,))
 
     def _run_backward(self, x2, gout, gx):
         """gx = (dS/dx)^T gout for x2 (B, N), gout (B, C, n_out), gx (B, N), all float32 CUDA contiguous.

@@ -62,6 +62,26 @@ def smoothing_operator(phi0_f32, N, J_pad, pad_left, dec, border_mode='reflect')
     return G
 
 
+def tukey_window(n, alpha):
+    """Tukey (tapered cosine) window with the reference's conventions (kymatio_phase_scattering.py:362-392): alpha
+    outside (0, 1] -> rectangular; alpha >= 1 -> symmetric Hann of n points; otherwise each edge of
+    L = int(alpha (n - 1) / 2) samples is one half of a symmetric Hann window of 2 L points.  float64."""
+    w = np.ones(int(n), np.float64)
+    if alpha is None or not 0 < alpha <= 1:
+        return w
+
+    def hann(m):                                        # 0.5 - 0.5 cos(2 pi k / (m - 1)), k < m
+        return 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(m) / max(m - 1, 1))
+
+    if alpha >= 1.0:
+        return hann(int(n))
+    edge = int(alpha * (n - 1) / 2.0)
+    if edge > 0:
+        h = hann(2 * edge)
+        w[:edge], w[n - edge:] = h[:edge], h[edge:]
+    return w
+
+
 PAIR_FFT_MIN_OUT = 160      # outputs per row from which the transform form of stage B beats the dense operator
 
 
@@ -266,6 +286,7 @@ class KymatioPhaseScattering1D(nn.Module):
         self.register_buffer('powers', torch.from_numpy(self._plan.powers).to(self.device))
         self.register_buffer('autoc_idx', torch.from_numpy(self._plan.autoc_idx).to(self.device))
         self._dev_plans = {}
+        self._windowed = set()
 
     # ---- plumbing -------------------------------------------------------------------------
     def _dev_plan(self, index):
@@ -300,20 +321,23 @@ class KymatioPhaseScattering1D(nn.Module):
         _lib.check(rc)
         return out
 
-    # ---- Tukey window (:362-392) -----------------------------------------------------------
-    def _create_tukey_window(self, n, alpha, device):
-        if alpha is None or not (0 < alpha <= 1):
-            return torch.ones(n, device=device)
-        if alpha >= 1.0:
-            return torch.hann_window(n, periodic=False, device=device)
-        taper_len = int(alpha * (n - 1) / 2.0)
-        if taper_len == 0:
-            return torch.ones(n, device=device)
-        taper = torch.hann_window(2 * taper_len, periodic=False, device=device)
-        window = torch.ones(n, device=device)
-        window[:taper_len] = taper[:taper_len]
-        window[n - taper_len:] = taper[taper_len:]
-        return window
+    # ---- Tukey window (:362-392, applied at :405-407) ---------------------------------------
+    def _window(self, n):
+        """The reference multiplies the input by a Tukey taper before anything else.  Here the taper is a table the
+        kernels' loads apply (OP_LOAD / pad_load: tebscat_plan_set_window): no elementwise pass over the batch."""
+        if self.tukey_alpha is None:
+            return None
+        return tukey_window(n, self.tukey_alpha)
+
+    def _install_window(self, index):
+        """Hand the taper to the device plans of the scattering transform and of stage A (once per device)."""
+        if self.tukey_alpha is None or index in self._windowed:
+            return
+        w = np.ascontiguousarray(self._window(self.N), np.float32)
+        self.scattering.set_window(w)
+        plan = self._dev_plan(index)
+        _lib.check(_lib.load().tebscat_phase_plan_set_window(plan.handle, w.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+        self._windowed.add(index)
 
     # ---- forward (:394-473) -------------------------------------------------------------------
     def forward(self, x, compute_phase=True, compute_cross_phase=False, cross_phase_same_pairs_only=False,
@@ -322,8 +346,10 @@ class KymatioPhaseScattering1D(nn.Module):
         """Same contract as the reference.  ``phase_pairs`` (extension) restricts the phase
         output to the given pair indices, e.g. the masks of get_optimal_coefficients_for_fhr."""
         x = x.to(self.device)
-        if self.tukey_alpha is not None:
-            x = x * self._create_tukey_window(x.shape[-1], self.tukey_alpha, x.device)
+        if self.tukey_alpha is not None and x.device.type == 'cuda':
+            if x.shape[-1] != self.N:
+                raise ValueError('Input length {} does not match shape={}'.format(x.shape[-1], self.N))
+            self._install_window(x.device.index if x.device.index is not None else torch.cuda.current_device())
         ch = None
         if x.dim() == 3:
             B, n_channels, N = x.shape
@@ -390,8 +416,8 @@ class KymatioPhaseScattering1D(nn.Module):
         and only the selected pairs contracted.  `phase_pairs` / `cross_pairs`: boolean masks over
         the P pairs (e.g. get_optimal_coefficients_for_fhr()['recommendations']) or index arrays."""
         x = x.to(self.device)
-        if self.tukey_alpha is not None:
-            x = x * self._create_tukey_window(x.shape[-1], self.tukey_alpha, x.device)
+        if self.tukey_alpha is not None and x.device.type == 'cuda' and x.shape[-1] == self.N:
+            self._install_window(x.device.index if x.device.index is not None else torch.cuda.current_device())
         if x.dim() != 3 or x.shape[1] < 2:
             raise ValueError("Cross-channel correlation requires at least 2 channels")
         B, C, N = x.shape
@@ -523,4 +549,4 @@ class KymatioPhaseScattering1D(nn.Module):
         return results
 
 
-__all__ = ['KymatioPhaseScattering1D', 'PhasePlan', 'smoothing_operator']
+__all__ = ['KymatioPhaseScattering1D', 'PhasePlan', 'smoothing_operator', 'tukey_window']

@@ -217,7 +217,33 @@ class Scattering1D(nn.Module):
         sched = self._schedule()
         if device_index not in self._plans:
             self._plans[device_index] = _DevicePlan(sched, device_index)
+            self._apply_window(self._plans[device_index])
         return self._plans[device_index]
+
+    def set_window(self, window):
+        """Extension: analysis window w[t] applied to the samples as the kernels load them (x[t] * w[t] before
+        padding), e.g. the Tukey taper of KymatioPhaseScattering1D (hdf5_dataset/kymatio_phase_scattering.py:405-407).
+        `window`: N values or None.  Acts on every level (fused, op-by-op, large support) and on the backward pass."""
+        if window is not None:
+            window = np.ascontiguousarray(np.asarray(window, dtype=np.float32).reshape(-1))
+            if window.shape[0] != self.N:
+                raise ValueError('window of {} samples on a transform of shape={}'.format(window.shape[0], self.N))
+        self._window = window
+        for p in self._plans.values():
+            self._apply_window(p)
+        for p in getattr(self, '_lplans', {}).values():
+            self._apply_window_large(p)
+
+    def _apply_window(self, dev_plan):
+        w = getattr(self, '_window', None)
+        ptr = w.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if w is not None else None
+        _lib.check(_lib.load().tebscat_plan_set_window(dev_plan.handle, ptr))
+
+    def _apply_window_large(self, ldp):
+        w = getattr(self, '_window', None)
+        ptr = w.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if w is not None else None
+        _lib.check(_lib.load().tebscat_large_set_window(ldp.handle, ptr, int(self.N)))
+        ldp.invalidate_graphs()
 
     def _check_options(self):
         if self.out_type not in ('array', 'list'):
@@ -291,7 +317,7 @@ class Scattering1D(nn.Module):
         if self.J_pad > LOG2_NP_MAX or self._op_by_op:
             lp, ldp = self._large_plan_for(index)
             S = torch.empty((B, lp.n_paths, lp.n_out), dtype=torch.float32, device=dev)
-            chunk = max(1, (1 << 28) >> self.J_pad)              # <= 2.7 GB of workspace per chunk
+            chunk = max(1, (1 << 28) >> self.J_pad)              # B * Np <= 2^28: U0 and W1 2 GB each, W2 <= 2 GB, leaves: <= 6.2 GB
             for b0 in range(0, B, chunk):
                 ldp.forward(x2[b0:b0 + chunk], S[b0:b0 + chunk])
             return S
@@ -311,6 +337,8 @@ class Scattering1D(nn.Module):
             self._lplans = {}
         if index not in self._lplans:
             self._lplans[index] = LargeDevicePlan(self._lsched[1], index)
+            if getattr(self, '_window', None) is not None:
+                self._apply_window_large(self._lplans[index])
         return self._lsched[1], self._lplans[index]
 
     def _backward_array(self, x2, gS):
@@ -322,7 +350,7 @@ class Scattering1D(nn.Module):
         if gS.dtype is not torch.float32:
             raise TypeError('Input and filter must be of the same dtype.')
         gx = torch.empty_like(x2)
-        chunk = max(1, (1 << 25) >> self.J_pad)                  # <= 2.4 GB of workspace per chunk
+        chunk = max(1, (1 << 25) >> self.J_pad)                  # B * Np <= 2^25: eight buffers of 256 MB + leaves, <= 2.1 GB
         for b0 in range(0, x2.shape[0], chunk):
             ldp.backward(x2[b0:b0 + chunk], gS[b0:b0 + chunk], gx[b0:b0 + chunk])
         return gx
@@ -415,7 +443,9 @@ class Scattering1D(nn.Module):
 
     def scattering_host(self, x, out=None, device=0):
         """End-to-end path on HOST tensors: pinned staging, chunked H2D / kernel / D2H
-        overlap inside the library (tebscat_scat1d_forward_host).  Returns S on the host."""
+        overlap inside the library (tebscat_scat1d_forward_host).  Returns S on the host.
+        Served by the fused single-kernel level only (padded lengths up to 2^13 that fit its schedule); other
+        configurations raise NotImplementedError -- use forward() on device tensors for them."""
         self._check_options()
         if x.device.type != 'cpu' or x.dtype is not torch.float32:
             raise TypeError('scattering_host expects a float32 CPU tensor')
@@ -429,6 +459,10 @@ class Scattering1D(nn.Module):
         C, n_out = sched.n_paths, sched.n_out
         if out is None:
             out = torch.empty((B, C, n_out), dtype=torch.float32, pin_memory=True)
+        elif (not torch.is_tensor(out) or out.device.type != 'cpu' or out.dtype is not torch.float32 or
+              not out.is_contiguous() or out.numel() != B * C * n_out):
+            # the library writes B * C * n_out floats through this pointer
+            raise ValueError('out must be a contiguous float32 CPU tensor of {} elements'.format(B * C * n_out))
         rc = _lib.load().tebscat_scat1d_forward_host(plan.handle, x2.data_ptr(), B, out.data_ptr())
         _lib.check(rc)
         return out.reshape(batch_shape + (C, n_out))
