@@ -54,6 +54,15 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def bf16_sustained_peak():
+    """Measured dense bf16 TFLOP/s of this pool's B200 inside a long step (MEASURED_PEAKS.json), 0.0 if absent."""
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f).get('bf16_tflops_sustained', 0.0))
+    return 0.0
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons of one GPU while the timed region runs."""
 
@@ -203,6 +212,16 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_value = world * n_sig * args.steps / max_over_ranks(e2e_s, dev)
+    # the same pipeline without its kernel: what this box's host <-> device path can move for exactly this traffic,
+    # with all ranks copying at once (tools/host_copy_ceiling.py sweeps it on its own)
+    plan_h = S._plan_for(local).handle
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _lib.check(_lib.load().tebscat_scat1d_host_copies_only(plan_h, x_host.data_ptr(), n_sig, out_host.data_ptr()))
+    torch.cuda.synchronize()
+    copy_s = max_over_ranks(time.perf_counter() - t0, dev)
+    copy_value = world * n_sig * args.steps / copy_s
     local_cpus = len(os.sched_getaffinity(0))
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)                       # the CPU baseline below uses every host core
@@ -212,19 +231,51 @@ def run_gpu(args):
     if rank == 0 and not args.no_phase:
         from tebscat import KymatioPhaseScattering1D
         pm = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=dev)
-        xb = x_dev[:512]
-        pm(xb, compute_phase=False, compute_cross_phase=True)
+        PB = args.phase_batch                                          # BASELINE configs[2]: 8192 FHR x UP pairs
+        xb = x_dev[:PB]
+        pm(xb[:512], compute_phase=False, compute_cross_phase=True)    # builds the plans, warms up
         torch.cuda.synchronize()
+        ph = pm._dev_plan(local).handle
+        lib = _lib.load()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 2
+        _lib.check(lib.tebscat_phase_plan_profile(ph, 1))
         p0.record()
-        for _ in range(3):
-            pm(xb, compute_phase=False, compute_cross_phase=True)
+        for _ in range(reps):
+            po = pm(xb, compute_phase=False, compute_cross_phase=True)['cross_phase_corr']
         p1.record()
         torch.cuda.synchronize()
-        pms = p0.elapsed_time(p1) / 3
+        pms = p0.elapsed_time(p1) / reps
+        a_ms, b_ms, n_chunks = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
+        _lib.check(lib.tebscat_phase_plan_profile_read(ph, ctypes.byref(a_ms), ctypes.byref(b_ms), ctypes.byref(n_chunks)))
+        _lib.check(lib.tebscat_phase_plan_profile(ph, 0))
+        n_pairs, n_po = int(po.shape[1]), int(po.shape[2])
+        del po
+        stage_b_s = b_ms.value * 1e-3 / reps
+        # dominant kernel: the dense contraction on tcgen05 -- rows x (2 N) x 80 columns, three TF32 products each
+        tensor_flops = PB * n_pairs * (2 * N) * 80 * 2 * 3
+        bf16_sustained = bf16_sustained_peak()
+        tf32_peak = bf16_sustained / 2 if bf16_sustained else 1125.0
+        ach = tensor_flops / stage_b_s / 1e12
         phase = {'metric': 'cross-channel phase scattering FHR x UP pairs/s (J=6,Q=8,N=4800, 741 pairs)',
-                 'value': 512 / (pms * 1e-3), 'unit': 'signal-pairs/s', 'batch': 512, 'ms': pms,
-                 'achieved_fp32_tflops': 512 * 2 * 741 * 4800 * 80 * 2 / (pms * 1e-3) / 1e12,
+                 'value': PB / (pms * 1e-3), 'unit': 'signal-pairs/s', 'batch': PB, 'ms': pms,
+                 'config': 'BASELINE configs[2]: batch %d two-channel signals, N=4800, all 741 pairs; output %.2f GB per pass' % (
+                     PB, PB * n_pairs * n_po * 4 / 1e9),
+                 'stage_ms': {'stage_a': a_ms.value / reps, 'stage_b': b_ms.value / reps, 'chunks': n_chunks.value // reps,
+                              'how': 'CUDA events on the launch stream around the stages of every workspace chunk '
+                                     '(tebscat_phase_plan_profile)'},
+                 'roofline': {'bound': 'tensor', 'kernel': 'phase_pair_tc_kernel (stage B, dense form)',
+                              'achieved': ach, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak,
+                              'peak_source': 'dense TF32 = half of MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
+                                             if bf16_sustained else 'fallback: half of the nominal 2250 TFLOP/s bf16',
+                              'executed': 'rows x 2N x 80 x 2 x 3 (3xTF32: Ah Bh + Al Bh + Ah Bl) / stage-B time',
+                              'fp32_equivalent_tflops': ach / 3,
+                              'reference_equivalent_tflops': PB / (pms * 1e-3) * 440e6 / 1e12,
+                              'reference_equivalent_note': 'SURVEY 8d: 440 MFLOP per pair of the reference\'s FFT formulation, whole call',
+                              'hbm': {'algorithmic_bytes_per_pair': 260700,
+                                      'achieved_gbs': PB / (pms * 1e-3) * 260700 / 1e9, 'peak_gbs': peaks()[0],
+                                      'frac': PB / (pms * 1e-3) * 260700 / 1e9 / peaks()[0]},
+                              'traffic': None},
                  'note': 'includes the scattering transform of the FHR channel and stage A of both channels'}
         del pm
         # production dataset step (create_hdf5_dataset.py:360-441): S + 44 within + 130 cross pairs in one pass
@@ -232,6 +283,7 @@ def run_gpu(args):
         pmp = KymatioPhaseScattering1D(J=11, Q=4, T=16, shape=5760, device=dev, max_order=1)
         sel = pmp.get_optimal_coefficients_for_fhr(11, 4, 16)['recommendations']
         xp = _ctg(512, 5760, seed=99).to(dev)
+        torch.cuda.empty_cache()
         pmp.forward_dataset(xp, sel['use_phase_mask'], sel['use_cross_mask'])
         torch.cuda.synchronize()
         p0.record()
@@ -287,7 +339,13 @@ def run_gpu(args):
                        'host_binding': ('NUMA-local, %d CPUs per rank' % local_cpus) if prev_affinity is not None else 'none'},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': n_sig * N * 4,
-                    'd2h_bytes_per_step': n_sig * C * n_out * 4},
+                    'd2h_bytes_per_step': n_sig * C * n_out * 4,
+                    'host_copy_ceiling': {'value': copy_value, 'unit': UNIT,
+                                          'gbs': copy_value * BYTES_PER_SIGNAL / 1e9,
+                                          'note': 'the same pinned H2D + D2H chunks on the same streams with the kernel '
+                                                  'left out, all ranks at once (tebscat_scat1d_host_copies_only)'},
+                    'frac_of_copy_ceiling': e2e_value / copy_value,
+                    'pipeline': '3 slots of 1184 signals: H2D, kernel and D2H on separate streams'},
             'gpu_launches': launches,
             # 554 flop/B -- the cascade is bound by the FP32 pipe (with shared-memory bandwidth as the
             # co-limit), not by HBM; the HBM figures are reported beside it
@@ -319,6 +377,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='tebscat', choices=['tebscat', 'reference'])
     ap.add_argument('--no-phase', action='store_true', help='skip the secondary phase-scattering measurement')
+    ap.add_argument('--phase-batch', type=int, default=8192, help='two-channel samples of the phase secondary (BASELINE configs[2]: 8192)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'tebscat' else args.warmup
     if args.impl == 'reference':

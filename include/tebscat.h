@@ -115,6 +115,10 @@ int tebscat_scat1d_forward_ex(const tebscat_plan* plan, const float* x_dev, int6
 int tebscat_scat1d_forward_host(tebscat_plan* plan, const float* x_host, int64_t B,
                                 float* S_host);
 
+/* Diagnostic: the host <-> device copies of tebscat_scat1d_forward_host (same chunks, streams and buffers) without
+ * its kernel -- the copy ceiling the end-to-end rate is reported against (bench.py `e2e.host_copy_ceiling`). */
+int tebscat_scat1d_host_copies_only(tebscat_plan* plan, const float* x_host, int64_t B, float* S_host);
+
 /* Diagnostic: run the transform once and return clock64() of CTA 0 at every step
  * boundary of its first signal (n_steps + 1 values).  Used to calibrate the host
  * scheduler's cost model; not on the product path. */
@@ -159,6 +163,11 @@ int tebscat_phase_plan_set_window(tebscat_phase_plan* plan, const float* window_
 int tebscat_phase_forward(tebscat_phase_plan* plan, const float* x_dev, int64_t B, int n_channels,
                           int ch_i, int ch_j, const int32_t* pair_subset_host, int n_subset,
                           int apply_low_pass, float* out_dev, void* stream);
+
+/* Diagnostic (bench.py): time the two stages of tebscat_phase_forward with CUDA events on the caller's stream.
+ * _profile(plan, 1) starts recording, _profile_read returns the summed stage times (ms) and clears the record. */
+int tebscat_phase_plan_profile(tebscat_phase_plan* plan, int enable);
+int tebscat_phase_plan_profile_read(tebscat_phase_plan* plan, double* stage_a_ms, double* stage_b_ms, int* n_chunks);
 
 /* Optional: run stage B (the low-pass of every (sample, pair) product, _apply_phi_filter :233-273) as
  * transforms on the step interpreter instead of the dense operator.  `pair_plan` is a plan created with

@@ -224,12 +224,15 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
 // plan
 // ---------------------------------------------------------------------------------
 struct HostPipe {            // resources of the host-buffer entry point, created lazily
+    // Three-stage pipeline over chunks of the batch: H2D on one stream, the kernel on a second, D2H on a third
+    // (each direction has its own copy engine), kSlots chunks in flight, ordered by events.
+    static constexpr int kSlots = 3;
     bool ready = false;
     int64_t chunk = 0;
-    cudaStream_t stream[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
-    float* d_x[2] = {nullptr, nullptr};
-    float* d_S[2] = {nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t loaded[kSlots] = {}, computed[kSlots] = {}, drained[kSlots] = {};
+    float* d_x[kSlots] = {};
+    float* d_S[kSlots] = {};
 };
 
 struct tebscat_plan {
@@ -506,12 +509,17 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
 extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    if (p->pipe.ready) {
-        for (int i = 0; i < 2; ++i) {
-            cudaStreamDestroy(p->pipe.stream[i]);
-            cudaEventDestroy(p->pipe.done[i]);
-            cudaFree(p->pipe.d_x[i]);
-            cudaFree(p->pipe.d_S[i]);
+    {
+        HostPipe& hp = p->pipe;
+        if (hp.s_in) cudaStreamDestroy(hp.s_in);
+        if (hp.s_run) cudaStreamDestroy(hp.s_run);
+        if (hp.s_out) cudaStreamDestroy(hp.s_out);
+        for (int i = 0; i < HostPipe::kSlots; ++i) {
+            if (hp.loaded[i]) cudaEventDestroy(hp.loaded[i]);
+            if (hp.computed[i]) cudaEventDestroy(hp.computed[i]);
+            if (hp.drained[i]) cudaEventDestroy(hp.drained[i]);
+            cudaFree(hp.d_x[i]);
+            cudaFree(hp.d_S[i]);
         }
     }
     cudaFree(p->d_arena);
@@ -631,36 +639,69 @@ extern "C" int tebscat_debug_bfly(long long* out8, int reset) {
 }
 #endif
 
-extern "C" int tebscat_scat1d_forward_host(tebscat_plan* p, const float* x_host, int64_t B, float* S_host) {
+static int host_pipe_prepare(tebscat_plan* p) {
+    HostPipe& hp = p->pipe;
+    if (hp.ready) return TEBSCAT_OK;
+    const size_t in_f = (size_t)p->desc.N, out_f = (size_t)p->desc.n_paths * p->desc.n_out;
+    hp.chunk = (int64_t)p->n_sms * 8;              // 8 signals per SM per chunk (H: 22.7 MB in, 44.8 MB out)
+    CU(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        CU(cudaEventCreateWithFlags(&hp.loaded[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&hp.computed[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&hp.drained[i], cudaEventDisableTiming));
+        CU(cudaMalloc(&hp.d_x[i], hp.chunk * in_f * sizeof(float)));
+        CU(cudaMalloc(&hp.d_S[i], hp.chunk * out_f * sizeof(float)));
+    }
+    hp.ready = true;
+    return TEBSCAT_OK;
+}
+
+// `copies_only` != 0 runs the same pipeline without the kernel: the host <-> device copy ceiling of this rank for
+// exactly the traffic of the real call (bench.py reports the end-to-end rate as a fraction of it).
+static int forward_host_impl(tebscat_plan* p, const float* x_host, int64_t B, float* S_host, int copies_only) {
     g_launches = 0;
     if (!p || B < 0 || (B > 0 && (!x_host || !S_host))) return fail(TEBSCAT_EINVAL, "null argument");
     if (B == 0) return TEBSCAT_OK;
     std::lock_guard<std::mutex> lock(p->pipe_mu);
+    int prev = 0;
+    CU(cudaGetDevice(&prev));
     CU(cudaSetDevice(p->device));
+    struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+    if (int rc = host_pipe_prepare(p)) return rc;
     HostPipe& hp = p->pipe;
     const size_t in_f = (size_t)p->desc.N, out_f = (size_t)p->desc.n_paths * p->desc.n_out;
-    if (!hp.ready) {
-        hp.chunk = (int64_t)p->n_sms * 8;          // 8 signals per SM per chunk
-        for (int i = 0; i < 2; ++i) {
-            CU(cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
-            CU(cudaMalloc(&hp.d_x[i], hp.chunk * in_f * sizeof(float)));
-            CU(cudaMalloc(&hp.d_S[i], hp.chunk * out_f * sizeof(float)));
-        }
-        hp.ready = true;
-    }
-    int slot = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += hp.chunk, slot ^= 1) {
+    int64_t n = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += hp.chunk, ++n) {
+        const int slot = (int)(n % HostPipe::kSlots);
         const int64_t nb = (B - b0 < hp.chunk) ? (B - b0) : hp.chunk;
-        cudaStream_t st = hp.stream[slot];
-        // the slot's previous D2H is ordered before this H2D by stream order
-        CU(cudaMemcpyAsync(hp.d_x[slot], x_host + b0 * in_f, nb * in_f * sizeof(float), cudaMemcpyHostToDevice, st));
-        if (int rc = launch_scat1d(p, hp.d_x[slot], nb, hp.d_S[slot], st)) return rc;
-        CU(cudaMemcpyAsync(S_host + b0 * out_f, hp.d_S[slot], nb * out_f * sizeof(float), cudaMemcpyDeviceToHost, st));
+        // the slot's input buffer is free once its previous kernel has run, its output buffer once drained
+        if (n >= HostPipe::kSlots) CU(cudaStreamWaitEvent(hp.s_in, hp.computed[slot], 0));
+        CU(cudaMemcpyAsync(hp.d_x[slot], x_host + b0 * in_f, nb * in_f * sizeof(float), cudaMemcpyHostToDevice, hp.s_in));
+        CU(cudaEventRecord(hp.loaded[slot], hp.s_in));
+        CU(cudaStreamWaitEvent(hp.s_run, hp.loaded[slot], 0));
+        if (n >= HostPipe::kSlots) CU(cudaStreamWaitEvent(hp.s_run, hp.drained[slot], 0));
+        if (!copies_only)
+            if (int rc = launch_scat1d(p, hp.d_x[slot], nb, hp.d_S[slot], hp.s_run)) return rc;
+        CU(cudaEventRecord(hp.computed[slot], hp.s_run));
+        CU(cudaStreamWaitEvent(hp.s_out, hp.computed[slot], 0));
+        CU(cudaMemcpyAsync(S_host + b0 * out_f, hp.d_S[slot], nb * out_f * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
+        CU(cudaEventRecord(hp.drained[slot], hp.s_out));
     }
-    CU(cudaStreamSynchronize(hp.stream[0]));
-    CU(cudaStreamSynchronize(hp.stream[1]));
+    CU(cudaStreamSynchronize(hp.s_out));
+    CU(cudaStreamSynchronize(hp.s_run));
+    CU(cudaStreamSynchronize(hp.s_in));
     return TEBSCAT_OK;
+}
+
+extern "C" int tebscat_scat1d_forward_host(tebscat_plan* p, const float* x_host, int64_t B, float* S_host) {
+    return forward_host_impl(p, x_host, B, S_host, 0);
+}
+
+// Diagnostic (bench.py, tools/host_copy_ceiling.py): the copies of tebscat_scat1d_forward_host without its kernel.
+extern "C" int tebscat_scat1d_host_copies_only(tebscat_plan* p, const float* x_host, int64_t B, float* S_host) {
+    return forward_host_impl(p, x_host, B, S_host, 1);
 }
 
 // =================================================================================
@@ -883,6 +924,9 @@ struct tebscat_phase_plan {
     int64_t ws2_samples = 0;
     tebscat_plan* pair_plan = nullptr;   // optional: stage B as FFTs on the interpreter (owned)
     std::mutex mu;
+    // optional stage timing (tebscat_phase_plan_profile): events around stage A and stage B of every chunk
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;    // triples (before A, between, after B)
 };
 
 extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_plan* stage_a, const float* G_host,
@@ -960,6 +1004,7 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
     cudaFree(p->d_zc);
     cudaFree(p->d_zp);
     cudaFree(p->d_zc2);
+    for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
     tebscat_plan_destroy(p->stage_a);
     tebscat_plan_destroy(p->pair_plan);
     delete p;
@@ -1078,15 +1123,24 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
     if (pair_subset_host) CU(cudaMemcpyAsync(p->d_subset, pair_subset_host, n_sel * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     const long long x_stride = (long long)n_channels * d.N;
     const size_t out_per_sample = (size_t)n_sel * (apply_low_pass ? d.n_out : d.N);
+    auto mark = [&]() {                          // stage timing, when asked for
+        if (!p->prof) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        p->prof_ev.push_back(e);
+    };
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
         const float* xb = x_dev + b0 * x_stride;
+        mark();
         if (ch_i == ch_j) {
             if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_i * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_CART | Z_POLAR, st)) return rc;
         } else {
             if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_i * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_POLAR, st)) return rc;
             if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_j * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_CART, st)) return rc;
         }
+        mark();
         PairParams pp;
         pp.zp = p->d_zp;
         pp.zc = p->d_zc;
@@ -1104,6 +1158,7 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
         pp.n_cols_pad = d.n_cols_pad;
         if (apply_low_pass && p->pair_plan) {
             if (int rc = launch_pairs_fft(p, p->d_zp, p->d_zc, pp.subset, n_sel, nb, pp.out, st)) return rc;
+            mark();
             continue;
         } else if (apply_low_pass) {
             launch_pair_gemm(p, pp, st);
@@ -1112,7 +1167,37 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
         }
         CU(cudaGetLastError());
         ++g_launches;
+        mark();
     }
+    return TEBSCAT_OK;
+}
+
+// Stage timing of tebscat_phase_forward (bench.py's roofline of the phase metric): while enabled, every chunk records
+// CUDA events before stage A, between the stages and after stage B on the caller's stream.
+extern "C" int tebscat_phase_plan_profile(tebscat_phase_plan* p, int enable) {
+    if (!p) return fail(TEBSCAT_EINVAL, "null plan");
+    std::lock_guard<std::mutex> lock(p->mu);
+    for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
+    p->prof_ev.clear();
+    p->prof = enable != 0;
+    return TEBSCAT_OK;
+}
+// Sum of the recorded stage times in milliseconds since profiling was enabled (waits for the last event); clears them.
+extern "C" int tebscat_phase_plan_profile_read(tebscat_phase_plan* p, double* stage_a_ms, double* stage_b_ms, int* n_chunks) {
+    if (!p || !stage_a_ms || !stage_b_ms || !n_chunks) return fail(TEBSCAT_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lock(p->mu);
+    *stage_a_ms = *stage_b_ms = 0.0;
+    *n_chunks = (int)(p->prof_ev.size() / 3);
+    if (!p->prof_ev.empty()) CU(cudaEventSynchronize(p->prof_ev.back()));
+    for (size_t k = 0; k + 2 < p->prof_ev.size(); k += 3) {
+        float a = 0.f, b = 0.f;
+        CU(cudaEventElapsedTime(&a, p->prof_ev[k], p->prof_ev[k + 1]));
+        CU(cudaEventElapsedTime(&b, p->prof_ev[k + 1], p->prof_ev[k + 2]));
+        *stage_a_ms += a;
+        *stage_b_ms += b;
+    }
+    for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
+    p->prof_ev.clear();
     return TEBSCAT_OK;
 }
 

@@ -72,8 +72,15 @@ def load():
     lib.tebscat_scat1d_forward_ex.argtypes = [vp, vp, ctypes.c_int64, vp, ctypes.POINTER(Epilogue), vp]
     lib.tebscat_scat1d_forward_host.restype = ctypes.c_int
     lib.tebscat_scat1d_forward_host.argtypes = [vp, vp, ctypes.c_int64, vp]
+    lib.tebscat_scat1d_host_copies_only.restype = ctypes.c_int
+    lib.tebscat_scat1d_host_copies_only.argtypes = [vp, vp, ctypes.c_int64, vp]
     lib.tebscat_phase_plan_create.restype = ctypes.c_int
     lib.tebscat_phase_plan_create.argtypes = [ctypes.POINTER(PhaseDesc), vp, fp, i32p, i32p, fp, ctypes.POINTER(vp)]
+    lib.tebscat_phase_plan_profile.restype = ctypes.c_int
+    lib.tebscat_phase_plan_profile.argtypes = [vp, ctypes.c_int]
+    lib.tebscat_phase_plan_profile_read.restype = ctypes.c_int
+    lib.tebscat_phase_plan_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                                    ctypes.POINTER(ctypes.c_int)]
     lib.tebscat_phase_plan_attach_pair_plan.restype = ctypes.c_int
     lib.tebscat_phase_plan_attach_pair_plan.argtypes = [vp, vp]
     lib.tebscat_phase_plan_destroy.restype = None
