@@ -157,11 +157,15 @@ def phase_option_fixtures():
     phase_option_fixture('S_circular', 'S', 1, border_mode='circular')
     phase_option_fixture('S_over1', 'S', 1, oversampling=1)
     phase_option_fixture('S_tukey', 'S', 1, tukey_alpha=0.25)
+    phase_option_fixture('S_nodec', 'S', 1, oversampling=4)        # target length = N: no decimation (:268-273)
 
 
 if __name__ == '__main__':
     if sys.argv[1:] == ['phase-randn']:
         phase_fixture_randn('Hr', 'H', 4)
+        sys.exit(0)
+    if sys.argv[1:] == ['phase-nodec']:
+        phase_option_fixture('S_nodec', 'S', 1, oversampling=4)
         sys.exit(0)
     if sys.argv[1:] == ['phase-tukey']:
         phase_option_fixture('S_tukey', 'S', 1, tukey_alpha=0.25)

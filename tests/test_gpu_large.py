@@ -45,12 +45,15 @@ def _get_ctx():
     return _ctx['dp']
 
 
-@pytest.mark.parametrize('cfg', [(8, 8, 2 ** 13, 256, 2), (6, 4, 12000, 64, 2), (9, 2, 2 ** 14, 512, 1)])
+@pytest.mark.parametrize('cfg', [(8, 8, 2 ** 13, 256, 2, 14), (6, 4, 12000, 64, 2, 15), (9, 2, 2 ** 14, 512, 1, 15),
+                                 # the top of BASELINE configs[3] (J=10, Q=8, N = 2^15 and 2^16) and ragged lengths
+                                 (10, 8, 2 ** 15, 1024, 2, 16), (10, 8, 2 ** 16, 1024, 2, 17),
+                                 (8, 4, 50000, 256, 2, 16), (10, 2, 100000, 512, 2, 17)])
 def test_large_support_matches_oracle(cfg):
     from tebscat import Scattering1D
-    J, Q, N, T, mo = cfg
+    J, Q, N, T, mo, j_pad = cfg
     S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
-    assert S.J_pad > 13
+    assert S.J_pad == j_pad > 13
     x = torch.randn(3, N, generator=torch.Generator().manual_seed(J))
     out, P = S(x.cuda())
     torch.cuda.synchronize()

@@ -324,3 +324,28 @@ def test_large_batch_phase_properties():
     within = m(x[:512], compute_phase=True, phase_channels=[0])['phase_corr']
     auto = within[:, m.autoc_idx.to(within.device)]
     assert float(auto.min()) > -1e-4 * float(auto.abs().max())
+
+
+def test_phase_without_decimation_matches_oracle_and_reference():
+    """Target length >= N (here oversampling = 4 >= log2 T): no decimation, the full-length low-pass of
+    kymatio_phase_scattering.py:268-273.  Served by the transform form (one row per job); pinned against the live
+    reference's output (fixture phase_S_nodec.npz) with the bound of the module docstring."""
+    d = np.load(os.path.join(GOLDEN, 'phase_S_nodec.npz'))
+    J, Q, T, N, mo = CFG['S']
+    over = int(d['oversampling'])
+    m = module_of('S', None, None, oversampling=over)
+    assert m._plan.dec == 1 and m._plan.n_out == N and m._dev_plan(0).uses_fft_pairs
+    x = torch.from_numpy(d['x']).cuda()
+    o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1])
+    rw = m(x, compute_phase=True, phase_channels=[0])
+    rc = m(x, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1])
+    assert rel_l2(rw['scattering'].cpu().numpy(), d['scattering']) < 2e-6
+    for ours, ref, mode in ((rw['phase_corr'], d['within'], 'within'), (rc['cross_phase_corr'], d['cross'], 'cross')):
+        ours = ours.cpu().numpy().astype(np.float64)
+        assert ours.shape == ref.shape == (2, len(o.i_idx), N)
+        xm = d['x'][:, 0] if mode == 'within' else d['x']
+        check(ours, o, xm, mode, 'no decimation/' + mode, None, ref, randn_rows=[1])
+    # a pair subset and the single-pass dataset entry go through the same plan
+    sub = np.arange(0, len(o.i_idx), 7)
+    part = m(x, compute_phase=False, compute_cross_phase=True, phase_pairs=sub)['cross_phase_corr']
+    assert torch.equal(part, rc['cross_phase_corr'][:, torch.from_numpy(sub).cuda()])

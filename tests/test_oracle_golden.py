@@ -129,7 +129,7 @@ def test_phase_vs_reference(golden_dir, name):
     _pin_phase_oracle(o, x, d['cross'][rows], 'cross', sub_c, randn_rows, name)
 
 
-@pytest.mark.parametrize('tag', ['S_constant', 'S_circular', 'S_over1'])
+@pytest.mark.parametrize('tag', ['S_constant', 'S_circular', 'S_over1', 'S_tukey', 'S_nodec'])
 def test_phase_options_vs_reference(golden_dir, tag):
     """border_mode 'constant' / 'circular' (kymatio_phase_scattering.py:162-173) and oversampling (the
     target length follows the scattering output, :445) against outputs of the live reference."""
@@ -137,6 +137,8 @@ def test_phase_options_vs_reference(golden_dir, tag):
     J, Q, T, N = int(d['J']), int(d['Q']), int(d['T']), int(d['N'])
     o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1], border_mode=str(d['border_mode']))
     x = d['x']
+    if 'tukey_alpha' in d.files and float(d['tukey_alpha']) > 0:       # the reference tapers its input first (:405-407)
+        x = x * d['window']
     _pin_phase_oracle(o, x, d['within'], 'within', None, [1], tag)
     _pin_phase_oracle(o, x, d['cross'], 'cross', None, [1], tag)
 

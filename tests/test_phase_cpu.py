@@ -149,3 +149,29 @@ def test_tukey_window_matches_reference():
     assert np.array_equal(tukey_window(50, None), np.ones(50)) and np.array_equal(tukey_window(50, 0.0), np.ones(50))
     assert np.array_equal(tukey_window(50, 1.5), np.ones(50))        # outside (0, 1]: rectangular, like the reference
     assert np.array_equal(tukey_window(5, 0.2), np.ones(5))          # taper shorter than one sample
+
+
+@pytest.mark.skipif(not emu_available(), reason='host emulator not built')
+def test_pair_stage_without_decimation_emulated():
+    """Target length >= N (oversampling >= log2 T, or T = 1): the reference low-passes at full length,
+    ifft(fft(pad(c)) phi)[pad_left : pad_left + N] (kymatio_phase_scattering.py:268-273).  Here: the transform form
+    with one row per job (the dense operator would be N x N), through the host emulator against the oracle."""
+    J, Q, T, N = CFG['S']
+    p = PhasePlan(J, Q, T, N, N)                                # scattering output as long as the input
+    assert p.dec == 1 and p.n_out == N and p.G is None and p.pair_plan is not None and p.pair_plan.n_paths == 1
+    o = PhaseOracle(J, Q, T, N, N)
+    rng = np.random.RandomState(19)
+    rows = 3
+    zi = (rng.randn(rows, N) + 1j * rng.randn(rows, N)).astype(np.complex64)
+    zj = (rng.randn(rows, N) + 1j * rng.randn(rows, N)).astype(np.complex64)
+    pw = np.array([1.0, 2.0, 4.5], np.float32)
+    zp = np.stack([np.abs(zi), np.angle(zi)], -1).astype(np.float32)
+    zc = np.stack([zj.real, zj.imag], -1).astype(np.float32)
+    out = emu_pair_stage(p.pair_plan, zp, zc, pw)
+    assert out.shape == (rows, N) and not np.isnan(out).any()
+    theta = zp[..., 1].astype(np.float32) * pw[:, None]
+    c = zp[..., 0].astype(np.float64) * np.exp(1j * theta.astype(np.float64)) * np.conj(zj.astype(np.complex128))
+    ref = o._smooth(c).real
+    assert ref.shape == out.shape
+    err = np.linalg.norm(out - ref, axis=-1) / np.linalg.norm(ref, axis=-1)
+    assert err.max() < 1e-5, err

@@ -932,11 +932,13 @@ struct tebscat_phase_plan {
 extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_plan* stage_a, const float* G_host,
                                          const int32_t* i_idx, const int32_t* j_idx, const float* powers,
                                          tebscat_phase_plan** out) {
-    if (!d || !stage_a || !G_host || !i_idx || !j_idx || !powers || !out) return fail(TEBSCAT_EINVAL, "null argument");
+    // G_host may be NULL: the plan then has no dense form of stage B and needs an attached pair plan
+    // (configurations without decimation, where the dense operator would be N x N)
+    if (!d || !stage_a || !i_idx || !j_idx || !powers || !out) return fail(TEBSCAT_EINVAL, "null argument");
     if (d->abi_version != TEBSCAT_ABI_VERSION) return fail(TEBSCAT_EINVAL, "ABI version mismatch");
     if (d->N != stage_a->desc.N || d->n_filters != stage_a->desc.n_paths || stage_a->desc.n_out != d->N)
         return fail(TEBSCAT_EINVAL, "stage-A plan does not match the phase description");
-    if (d->n_pairs < 1 || d->n_out < 1 || d->n_cols_pad < d->n_out || d->n_cols_pad % kPC != 0)
+    if (d->n_pairs < 1 || d->n_out < 1 || (G_host && (d->n_cols_pad < d->n_out || d->n_cols_pad % kPC != 0)))
         return fail(TEBSCAT_EINVAL, "bad phase description");
     for (int k = 0; k < d->n_pairs; ++k)
         if (i_idx[k] < 0 || i_idx[k] >= d->n_filters || j_idx[k] < 0 || j_idx[k] >= d->n_filters)
@@ -952,9 +954,11 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
     p->stage_a = stage_a;
     p->device = stage_a->device;
     const size_t g_elems = (size_t)d->N * d->n_cols_pad;
-    CU(cudaMalloc(&p->d_G, g_elems * sizeof(float2)));
-    CU(cudaMemcpy(p->d_G, G_host, g_elems * sizeof(float2), cudaMemcpyHostToDevice));
-    {   // B'[n][2t + c] = G[t][n][c], split into TF32 head and tail (round to nearest, ties away, like cvt.rna.tf32.f32)
+    if (G_host) {
+        CU(cudaMalloc(&p->d_G, g_elems * sizeof(float2)));
+        CU(cudaMemcpy(p->d_G, G_host, g_elems * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    if (G_host) {   // B'[n][2t + c] = G[t][n][c], split into TF32 head and tail (round to nearest, ties away, like cvt.rna.tf32.f32)
         p->n_slabs = (d->N + kTcSlabT - 1) / kTcSlabT;
         p->k_pad = p->n_slabs * kTcK;
         const size_t per = (size_t)d->n_cols_pad * p->k_pad;
@@ -1160,6 +1164,8 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
             if (int rc = launch_pairs_fft(p, p->d_zp, p->d_zc, pp.subset, n_sel, nb, pp.out, st)) return rc;
             mark();
             continue;
+        } else if (apply_low_pass && !p->d_G) {
+            return fail(TEBSCAT_EUNSUPPORTED, "this phase plan has no dense operator and no pair plan attached");
         } else if (apply_low_pass) {
             launch_pair_gemm(p, pp, st);
         } else {
@@ -1204,6 +1210,7 @@ extern "C" int tebscat_phase_plan_profile_read(tebscat_phase_plan* p, double* st
 static int launch_pairs(const tebscat_phase_plan* p, const float2* zp, const float2* zc, const int32_t* subset_dev,
                         int n_sel, int64_t nb, float* out, cudaStream_t st) {
     if (p->pair_plan) return launch_pairs_fft(p, zp, zc, subset_dev, n_sel, nb, out, st);
+    if (!p->d_G) return fail(TEBSCAT_EUNSUPPORTED, "this phase plan has no dense operator and no pair plan attached");
     const tebscat_phase_desc& d = p->desc;
     PairParams pp;
     pp.zp = zp;

@@ -111,20 +111,27 @@ class PhasePlan:
             self.dec = max(1, min(N, N // n_out_scattering))
         else:
             self.dec = 1
-        if self.dec <= 1:
-            raise NotImplementedError('phase path without decimation (target length >= N) is not built')
         phi0 = bank.phi.levels[0].astype(np.float32)
+        if self.dec > 1:
+            Np, start = 1 << self.geo.J_pad, self.geo.pad_left // self.dec
+            if min(start + N // self.dec, max(Np // self.dec, 1)) - start <= 0:
+                self.dec = 1                          # zero-length decimated output: the reference falls back (:296-299)
+        self._build_stage_a()
+        self.pair_plan = None
+        if self.dec == 1:
+            # no decimation (target length >= N, e.g. T = 1 or oversampling >= log2 T): the full-length low-pass
+            # ifft(fft(pad(c)) phi)[pad_left : pad_left + N] (:268-273).  The dense operator would be N x N, so
+            # stage B exists in the transform form only: one (sample, pair) row per job.
+            self.n_out, self.n_cols_pad, self.G = N, 0, None
+            self._build_pair_plan(phi0, rows_per_job=1)
+            return
         G = smoothing_operator(phi0, N, self.geo.J_pad, self.geo.pad_left, self.dec, border_mode)
         self.n_out = G.shape[1]
-        if self.n_out == 0:
-            raise NotImplementedError('zero-length decimated output (reference falls back to no decimation)')
         self.n_cols_pad = -(-self.n_out // COL_TILE) * COL_TILE
         Gp = np.zeros((N, self.n_cols_pad, 2), np.float32)
         Gp[:, :self.n_out, 0] = G.real
         Gp[:, :self.n_out, 1] = G.imag
         self.G = Gp
-        self._build_stage_a()
-        self.pair_plan = None
         if self.dec & (self.dec - 1) == 0 and (1 << self.geo.J_pad) // self.dec >= 16:
             self._build_pair_plan(phi0)
 
@@ -213,13 +220,13 @@ class _DevicePhasePlan:
         d.abi_version = _lib.ABI_VERSION
         d.N, d.n_filters, d.n_pairs = plan.N, len(plan.bank.psi1), len(plan.i_idx)
         d.n_out, d.n_cols_pad = plan.n_out, plan.n_cols_pad
-        G = np.ascontiguousarray(plan.G, np.float32)
+        G = np.ascontiguousarray(plan.G, np.float32) if plan.G is not None else None
         ii = np.ascontiguousarray(plan.i_idx, np.int32)
         jj = np.ascontiguousarray(plan.j_idx, np.int32)
         pw = np.ascontiguousarray(plan.powers, np.float32)
         handle = ctypes.c_void_p()
         i32p, fp = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)
-        rc = lib.tebscat_phase_plan_create(ctypes.byref(d), stage_a.handle, G.ctypes.data_as(fp),
+        rc = lib.tebscat_phase_plan_create(ctypes.byref(d), stage_a.handle, G.ctypes.data_as(fp) if G is not None else None,
                                            ii.ctypes.data_as(i32p), jj.ctypes.data_as(i32p),
                                            pw.ctypes.data_as(fp), ctypes.byref(handle))
         _lib.check(rc)
@@ -228,7 +235,8 @@ class _DevicePhasePlan:
         self._lib = lib
         # stage B as transforms where that is the cheaper form (long outputs); TEBSCAT_PHASE_FFT=0/1 overrides
         mode = os.environ.get('TEBSCAT_PHASE_FFT', 'auto')
-        use_fft = plan.pair_plan is not None and (mode == '1' or (mode == 'auto' and plan.n_out >= PAIR_FFT_MIN_OUT))
+        use_fft = plan.pair_plan is not None and (mode == '1' or (mode == 'auto' and plan.n_out >= PAIR_FFT_MIN_OUT)
+                                                  or plan.G is None)
         self.uses_fft_pairs = bool(use_fft)
         if use_fft:
             pp = _DevicePlan(plan.pair_plan, device_index)
