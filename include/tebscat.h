@@ -239,6 +239,11 @@ int tebscat_large_unfold(tebscat_large* ctx, const float* gdst_dev, const float*
 /* adjoint of tebscat_large_store: zero signal with gout[b, channel, :] in the real part of samples [i0, i0 + n_out) */
 int tebscat_large_unstore(tebscat_large* ctx, const float* gout_dev, int64_t B, int log_len, int i0, int n_out, int n_paths,
                           int channel, float* buf_dev, void* stream);
+/* adjoint of the un-averaged store (average=False: the unpadded modulus itself is the output, core/scattering1d.py:329-330,
+ * :366-367): grow[b, offset : offset + len] (rows of row_stride floats) -> real part of samples [i0, i0 + len) of the
+ * length-2^log_len buffer; accumulate == 0 writes the whole buffer (zero elsewhere), != 0 adds inside the window */
+int tebscat_large_unstore_row(tebscat_large* ctx, const float* grow_dev, int64_t B, int64_t row_stride, int64_t offset,
+                              int log_len, int i0, int len, int accumulate, float* buf_dev, void* stream);
 /* adjoint of tebscat_large_pad_load: real part of the padded gradient folded back onto the N samples */
 int tebscat_large_pad_adjoint(tebscat_large* ctx, const float* gu_dev, int64_t B, int N, int pad_left, int log2_Np,
                               float* gx_dev, void* stream);

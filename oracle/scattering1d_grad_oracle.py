@@ -60,6 +60,39 @@ class GradOracle:
                         order2.append(S2[:, i0[k1 + k2 + k2_J]:i1[k1 + k2 + k2_J]])
         return torch.stack(out + order2, dim=1)
 
+    def forward_unaveraged(self, x):
+        """average=False (core/scattering1d.py:329-330, :366-367): the unpadded moduli U1 / U2 at their own rates,
+        back to back in the reference's path order (all first-order paths, then all second-order ones) -> (B, total).
+        Order 0 is the input itself and is left out."""
+        o, g = self.o, self.o.geo
+        t = lambda a: torch.from_numpy(np.asarray(a, np.float64))
+        log2_T = math.floor(math.log2(o.T))
+        os_ = o.oversampling
+        i0, i1 = g['ind_start'], g['ind_end']
+        xp = torch.nn.functional.pad(x[:, None, :], (g['pad_left'], g['pad_right']), mode='reflect')[:, 0]
+        U0_f = torch.fft.fft(xp.to(torch.complex128))
+        first, second = [], []
+        for p1 in o.psi1:
+            j1 = p1['j']
+            k1 = max(min(j1 - os_, log2_T - os_), 0)
+            U1 = torch.abs(torch.fft.ifft(self._periodise(U0_f * t(p1['levels'][0]), 2 ** k1)))
+            first.append(U1[:, i0[k1]:i1[k1]])
+            if o.max_order == 2:
+                U1_f = torch.fft.fft(U1.to(torch.complex128))
+                for p2 in o.psi2:
+                    if p2['j'] > j1:
+                        k2 = max(min(p2['j'] - k1 - os_, log2_T - k1 - os_), 0)
+                        U2 = torch.abs(torch.fft.ifft(self._periodise(U1_f * t(p2['levels'][k1]), 2 ** k2)))
+                        second.append(U2[:, i0[k1 + k2]:i1[k1 + k2]])
+        return torch.cat(first + second, dim=1)
+
+    def vjp_unaveraged(self, x, w):
+        """x (B, N), w (B, total) -> (row float64, d sum(row w) / dx float64)."""
+        xt = torch.from_numpy(np.asarray(x, np.float64)).clone().requires_grad_(True)
+        row = self.forward_unaveraged(xt)
+        (row * torch.from_numpy(np.asarray(w, np.float64))).sum().backward()
+        return row.detach().numpy(), xt.grad.numpy()
+
     def vjp(self, x, w):
         """x (B, N), w (B, C, n_out) arrays -> (S float64, d sum(S w) / dx float64) as numpy arrays."""
         xt = torch.from_numpy(np.asarray(x, np.float64)).clone().requires_grad_(True)

@@ -101,11 +101,28 @@ def test_gradient_through_views_batch_shapes_and_large_level():
     assert rel_l2(xl.grad.cpu().numpy(), g64, axis=-1).max() < 1e-5
 
 
-def test_unaveraged_backward_is_refused_loudly():
+def test_unaveraged_backward_adjoint_identity():
+    """average=False through the dict output (vectorize=False): <J v, w> = <v, J^T w> with J^T from the CUDA backward
+    and J v from central differences of the CUDA forward (the map is piecewise smooth: |u| away from 0)."""
     from tebscat import Scattering1D
-    S = Scattering1D(4, 1000, 4, T=16, average=False, out_type='list').cuda()
-    with pytest.raises(NotImplementedError):
-        S(torch.randn(1, 1000, device='cuda', requires_grad=True))
+    S = Scattering1D(4, 1000, 4, T=16, average=False, vectorize=False).cuda()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 1000, generator=g).cuda()
+    v = torch.randn(2, 1000, generator=g).cuda()
+    with pytest.warns(DeprecationWarning):
+        out, _ = S(x.clone().requires_grad_(True))
+    keys = list(out.keys())
+    ws = {k: torch.randn(out[k].shape, generator=g).cuda() for k in keys}
+    xg = x.clone().requires_grad_(True)
+    with pytest.warns(DeprecationWarning):
+        o = S(xg)[0]
+    sum((o[k] * ws[k]).sum() for k in keys).backward()
+    lhs = float((xg.grad.double() * v.double()).sum())
+    eps = 1e-2
+    with torch.no_grad(), pytest.warns(DeprecationWarning):
+        op, om = S(x + eps * v)[0], S(x - eps * v)[0]
+    rhs = float(sum((((op[k] - om[k]) / (2 * eps)).double() * ws[k].double()).sum() for k in keys))
+    assert abs(lhs - rhs) < 2e-3 * max(abs(lhs), abs(rhs)), (lhs, rhs)
 
 
 def test_adjoint_entry_points_reject_bad_requests():
@@ -127,3 +144,35 @@ def test_adjoint_entry_points_reject_bad_requests():
     assert lib.tebscat_large_modulus_to(ctx, ptr, ptr, 0, st) == _lib.TEBSCAT_EINVAL
     assert b'padding' in lib.tebscat_last_error() or len(lib.tebscat_last_error()) > 0
     lib.tebscat_large_destroy(ctx)
+
+
+@pytest.mark.parametrize('name', ['Tu', 'P1u'])
+def test_unaveraged_backward_matches_reference_and_oracle(name):
+    """average=False is differentiable like in the reference (its outputs are the moduli themselves): gradient of
+    sum(coef_c * w_c) over the whole list output against the live reference's autograd (fixture) and the float64
+    autograd oracle."""
+    import os
+    from helpers import GOLDEN
+    from oracle.scattering1d_grad_oracle import GradOracle
+    from tebscat import Scattering1D
+    d = np.load(os.path.join(GOLDEN, 'backward_%s.npz' % name))
+    J, N, Q, T, mo = int(d['J']), int(d['N']), int(d['Q']), int(d['T']), int(d['max_order'])
+    S = Scattering1D(J, N, Q, max_order=mo, T=T, average=False, out_type='list').cuda()
+    x = torch.from_numpy(d['x']).cuda().requires_grad_(True)
+    out, _ = S(x)
+    lengths = [int(v) for v in d['lengths']]
+    assert [o['coef'].shape[-1] for o in out] == lengths
+    ws = [torch.from_numpy(d['w0']).cuda()] + list(torch.split(torch.from_numpy(d['w']).cuda(), lengths[1:], dim=-1))
+    sum((o['coef'] * w).sum() for o, w in zip(out, ws)).backward()
+    gx = x.grad.cpu().numpy().astype(np.float64)
+    _, g64 = GradOracle(J, N, Q, T, mo).vjp_unaveraged(d['x'], d['w'])
+    g64 = g64 + d['w0']
+    err = np.linalg.norm(gx - g64, axis=-1) / np.linalg.norm(g64, axis=-1)
+    assert err[1] < 1e-5 and err[0] < 5e-5, err              # row 0 CTG-shaped, row 1 randn (as for average=True)
+    ref = np.linalg.norm(gx - d['gx'], axis=-1) / np.linalg.norm(d['gx'], axis=-1)
+    assert ref.max() < 5e-5, ref
+    # second call: graph replay, fresh cotangents
+    x2 = torch.from_numpy(d['x']).cuda().requires_grad_(True)
+    out2, _ = S(x2)
+    sum((o['coef'] * (2 * w)).sum() for o, w in zip(out2, ws)).backward()
+    assert torch.allclose(x2.grad, 2 * x.grad, rtol=1e-5, atol=1e-6 * float(x.grad.abs().max()))

@@ -45,7 +45,7 @@ def _get_ctx():
     return _ctx['dp']
 
 
-@pytest.mark.parametrize('cfg', [(8, 8, 2 ** 13, 256, 2, 14), (6, 4, 12000, 64, 2, 15), (9, 2, 2 ** 14, 512, 1, 15),
+@pytest.mark.parametrize('cfg', [(8, 8, 2 ** 13, 256, 2, 14), (6, 4, 12000, 64, 2, 14), (9, 2, 2 ** 14, 512, 1, 15),
                                  # the top of BASELINE configs[3] (J=10, Q=8, N = 2^15 and 2^16) and ragged lengths
                                  (10, 8, 2 ** 15, 1024, 2, 16), (10, 8, 2 ** 16, 1024, 2, 17),
                                  (8, 4, 50000, 256, 2, 16), (10, 2, 100000, 512, 2, 17)])

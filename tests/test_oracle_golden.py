@@ -156,3 +156,18 @@ def test_gradient_oracle_vs_reference(golden_dir, name):
     # (as for the forward); signal 1 is randn
     err = rel_l2(gx, d['gx'], axis=-1)
     assert err[1] < 1e-5 and err[0] < 5e-5, err
+
+
+@pytest.mark.parametrize('name', ['Tu', 'P1u'])
+def test_unaveraged_gradient_oracle_vs_reference(golden_dir, name):
+    """average=False: gradient of the un-averaged outputs (order 0 = the input itself included) against the live
+    reference's own autograd graph (oracle/make_golden_backward.py)."""
+    from oracle.scattering1d_grad_oracle import GradOracle
+    d = load(golden_dir, 'backward_%s.npz' % name)
+    o = GradOracle(int(d['J']), int(d['N']), int(d['Q']), int(d['T']), int(d['max_order']), int(d['oversampling']))
+    row, g = o.vjp_unaveraged(d['x'], d['w'])
+    gx = g + d['w0']                                      # order 0: d sum(x w0) / dx = w0
+    e_row = rel_l2(row, d['row'], axis=-1)                # row 0 is CTG-shaped (mean 140 bpm): the reference's fp32 moduli carry ~1e-5
+    assert row.shape == d['row'].shape and e_row[1] < 2e-6 and e_row[0] < 2e-5, e_row
+    err = rel_l2(gx, d['gx'], axis=-1)
+    assert err[1] < 1e-5 and err[0] < 5e-5, err

@@ -1941,6 +1941,42 @@ extern "C" int tebscat_large_unstore(tebscat_large* g, const float* gout_dev, in
     return TEBSCAT_OK;
 }
 
+// adjoint of the un-averaged store (OP_STOREU / core/scattering1d.py:329-330, :366-367): the output gradient of one path,
+// grow[b, offset : offset + len], enters the real part of samples [i0, i0 + len) of the length-2^log_len signal --
+// either as the whole signal (everything else zero) or added to what the buffer already holds there
+__global__ void g_unstore_row_kernel(const float* __restrict__ grow, float2* __restrict__ buf, long long B, long long row_stride,
+                                     long long offset, int log_len, int i0, int len, int accumulate) {
+    if (accumulate) {
+        const long long total = B * len;
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+            const long long b = e / len;
+            const int n = (int)(e - b * len);
+            buf[(b << log_len) + i0 + n].x += __ldg(grow + b * row_stride + offset + n);
+        }
+        return;
+    }
+    const long long total = B << log_len;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e >> log_len;
+        const int n = (int)(e - (b << log_len)) - i0;
+        const float v = (n >= 0 && n < len) ? __ldg(grow + b * row_stride + offset + n) : 0.f;
+        buf[e] = make_float2(v, 0.f);
+    }
+}
+
+extern "C" int tebscat_large_unstore_row(tebscat_large* g, const float* grow_dev, int64_t B, int64_t row_stride, int64_t offset,
+                                         int log_len, int i0, int len, int accumulate, float* buf_dev, void* stream) {
+    if (!g || !buf_dev || !grow_dev || B < 1 || i0 < 0 || len < 1 || log_len < 0 || log_len > kLargeMaxLog2 ||
+        i0 + len > (1 << log_len) || offset < 0 || offset + len > row_stride)
+        return fail(TEBSCAT_EINVAL, "bad un-averaged store request");
+    CU(cudaSetDevice(g->device));
+    g_unstore_row_kernel<<<g->n_sms * 4, 256, 0, (cudaStream_t)stream>>>(grow_dev, reinterpret_cast<float2*>(buf_dev), B, row_stride,
+                                                                          offset, log_len, i0, len, accumulate);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
 // adjoint of g_pad_load_kernel: gx[b, r] = Re gu[b, pad_left + r] + its left and right mirror images (pad < N: one fold)
 __global__ void g_pad_adjoint_kernel(const float2* __restrict__ gu, float* __restrict__ gx, long long B, int N, int pad_left, int log2_Np,
                                      const float* __restrict__ win) {

@@ -118,6 +118,9 @@ def load():
     lib.tebscat_large_leaf_adjoint.restype = ctypes.c_int
     lib.tebscat_large_leaf_adjoint.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, u32, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp]
+    lib.tebscat_large_unstore_row.restype = ctypes.c_int
+    lib.tebscat_large_unstore_row.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int, vp, vp]
     lib.tebscat_large_modulus_to.restype = ctypes.c_int
     lib.tebscat_large_modulus_to.argtypes = [vp, vp, vp, ctypes.c_int64, vp]
     lib.tebscat_large_modulus_backward.restype = ctypes.c_int

@@ -349,3 +349,75 @@ class LargeDevicePlan:
         fft(gU0, n, True)                                      # FFT^T of the real padded signal
         _lib.check(lib.tebscat_large_pad_adjoint(g, vp(gU0.data_ptr()), B, p.N, p.geo.pad_left, n, vp(gx.data_ptr()), st))
         return gx
+
+    # ---- backward of average=False (the un-averaged moduli are the outputs) ----------------------------------------
+    def backward_unaveraged(self, x2, grow, gx, segments):
+        """gx = (d row / dx)^T grow for the average=False transform: `row` holds the unpadded moduli U1 / U2 back to back
+        (`segments` = [(key, offset, length)] of schedule.build_plan_unaveraged; order 0 -- the input itself -- is the
+        frontend's business).  Same graph cache as the other directions."""
+        self._useg = {tuple(k): (int(off), int(ln)) for k, off, ln in segments}
+        self._urow = int(grow.shape[-1])
+        return self._graphed('bwdu', self._run_backward_unaveraged, (x2, grow, gx), ins=(x2, grow), outs=(gx,))
+
+    def _run_backward_unaveraged(self, x2, grow, gx):
+        """The transposed cascade of core/scattering1d.py:300-367 with average=False: a path's output is |u| itself
+        (unpadded, at its own rate), so its cotangent enters the modulus' backward directly in the time domain --
+        for a first-order path on top of what its second-order children send back through fft(|u1|)."""
+        p, lib, g = self.plan, self._lib, self.handle
+        B, dev = x2.shape[0], x2.device
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        U0, gU0, W1, H1, gH1, W2, gW2, gA, WL = self._bwd_workspace(B, dev)
+        n = p.geo.J_pad
+        fa = self.arena.data_ptr()
+        vp = ctypes.c_void_p
+        seg, row = self._useg, self._urow
+
+        def mulfold(src, spec, dst):
+            off, log_src, logk, mask, logcw, sexp = spec
+            _lib.check(lib.tebscat_large_mulfold(g, vp(src.data_ptr()), vp(fa + 4 * off), vp(dst.data_ptr()), B, log_src, logk,
+                                                 mask, logcw, sexp, st))
+
+        def unfold(gdst, spec, gsrc, accumulate):
+            off, log_src, logk, mask, logcw, sexp = spec
+            _lib.check(lib.tebscat_large_unfold(g, vp(gdst.data_ptr()), vp(fa + 4 * off), vp(gsrc.data_ptr()), B, log_src, logk,
+                                                mask, logcw, sexp, 1 if accumulate else 0, st))
+
+        def fft(buf, log_len, inverse):
+            _lib.check(lib.tebscat_large_fft(g, vp(buf.data_ptr()), B, log_len, 1 if inverse else 0, st))
+
+        def cotangent(key, log_len, buf, accumulate):
+            """+= / = the path's output gradient in the real part of samples [ind_start, ind_start + len)"""
+            off, ln = seg[key]
+            _lib.check(lib.tebscat_large_unstore_row(g, vp(grow.data_ptr()), B, row, off, log_len, p.geo.ind_start[n - log_len], ln,
+                                                     1 if accumulate else 0, vp(buf.data_ptr()), st))
+
+        def through_modulus(grad, u, log_len):
+            """time-domain gradient w.r.t. |u| -> gradient w.r.t. the periodised spectrum the inverse transform read"""
+            _lib.check(lib.tebscat_large_modulus_backward(g, vp(u.data_ptr()), vp(grad.data_ptr()), B << log_len, st))
+            fft(grad, log_len, False)                          # iFFT^T (its 1/L lives in the multiply's scale)
+
+        _lib.check(lib.tebscat_large_pad_load(g, vp(x2.data_ptr()), B, p.N, p.geo.pad_left, n, vp(U0.data_ptr()), st))
+        fft(U0, n, False)
+        for idx, e in enumerate(p.first):
+            l1, key1 = e['l1'], p.keys[e['ch']]
+            mulfold(U0, e['mul'], W1)
+            fft(W1, l1, True)                                  # W1 = u1
+            if e['kids']:
+                _lib.check(lib.tebscat_large_modulus_to(g, vp(W1.data_ptr()), vp(H1.data_ptr()), B << l1, st))
+                fft(H1, l1, False)                             # H1 = fft(|u1|)
+                for c, k in enumerate(e['kids']):
+                    l2 = k['l2']
+                    mulfold(H1, k['mul'], W2)
+                    fft(W2, l2, True)                          # W2 = u2
+                    cotangent(p.keys[k['ch']], l2, gW2, False)
+                    through_modulus(gW2, W2, l2)
+                    unfold(gW2, k['mul'], gH1, c > 0)
+                fft(gH1, l1, True)                             # FFT^T: what the children send back to |u1|
+                cotangent(key1, l1, gH1, True)
+            else:
+                cotangent(key1, l1, gH1, False)
+            through_modulus(gH1, W1, l1)
+            unfold(gH1, e['mul'], gU0, idx > 0)
+        fft(gU0, n, True)                                      # FFT^T of the real padded signal
+        _lib.check(lib.tebscat_large_pad_adjoint(g, vp(gU0.data_ptr()), B, p.N, p.geo.pad_left, n, vp(gx.data_ptr()), st))
+        return gx

@@ -88,6 +88,23 @@ class _ScatteringFunction(torch.autograd.Function):
         return ctx.module._backward_array(x2, gS), None
 
 
+class _UnaveragedFunction(torch.autograd.Function):
+    """Autograd node of the average=False transform: the row of un-averaged moduli; backward = the transposed cascade
+    with the cotangents entering at the moduli (LargeDevicePlan.backward_unaveraged)."""
+
+    @staticmethod
+    def forward(ctx, x2, module):
+        ctx.module = module
+        ctx.save_for_backward(x2)
+        return module._unaveraged_row(x2)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grow):
+        (x2,) = ctx.saved_tensors
+        return ctx.module._backward_unaveraged(x2, grow), None
+
+
 class Scattering1D(nn.Module):
     def __init__(self, J, shape, Q=1, max_order=2, average=True, oversampling=0, vectorize=True,
                  out_type='array', backend='torch', T=None):
@@ -229,7 +246,7 @@ class Scattering1D(nn.Module):
             if window.shape[0] != self.N:
                 raise ValueError('window of {} samples on a transform of shape={}'.format(window.shape[0], self.N))
         self._window = window
-        for p in self._plans.values():
+        for p in list(self._plans.values()) + list(getattr(self, '_uplans', {}).values()):
             self._apply_window(p)
         for p in getattr(self, '_lplans', {}).values():
             self._apply_window_large(p)
@@ -285,9 +302,7 @@ class Scattering1D(nn.Module):
         B = x2.shape[0]
         needs_grad = torch.is_grad_enabled() and x.requires_grad
         if not self.average:
-            if needs_grad:
-                raise NotImplementedError('the backward pass is built for average=True')
-            return self._scattering_unaveraged(x2, batch_shape)
+            return self._scattering_unaveraged(x2, batch_shape, needs_grad)
         # differentiable like the reference's torch backend (ModulusStable, kymatio/backend/torch_backend.py:5-96):
         # the forward is the same fused launch, the backward the transposed cascade of tebscat/large.py
         S = _ScatteringFunction.apply(x2, self) if needs_grad else self._forward_array(x2)
@@ -355,10 +370,37 @@ class Scattering1D(nn.Module):
             ldp.backward(x2[b0:b0 + chunk], gS[b0:b0 + chunk], gx[b0:b0 + chunk])
         return gx
 
-    def _scattering_unaveraged(self, x2, batch_shape):
+    def _backward_unaveraged(self, x2, grow):
+        """(d row / dx)^T grow of the average=False transform, see LargeDevicePlan.backward_unaveraged."""
+        dev = x2.device
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        lp, ldp = self._large_plan_for(index)
+        sched = self._usched[1]
+        grow = grow.contiguous()
+        gx = torch.empty_like(x2)
+        chunk = max(1, (1 << 25) >> self.J_pad)
+        for b0 in range(0, x2.shape[0], chunk):
+            ldp.backward_unaveraged(x2[b0:b0 + chunk], grow[b0:b0 + chunk], gx[b0:b0 + chunk], sched.segments)
+        return gx
+
+    def _scattering_unaveraged(self, x2, batch_shape, needs_grad=False):
         """average=False (core/scattering1d.py:293-294, :329-330, :366-367): the input itself, then the unpadded
         moduli U1 / U2 at their own rates.  One launch writes all paths back to back into one row per signal;
-        the coefficients returned are views of it."""
+        the coefficients returned are views of it.  Differentiable like the reference (the order-0 coefficient IS
+        the input; the row's backward is the transposed cascade in CUDA)."""
+        row = _UnaveragedFunction.apply(x2, self) if needs_grad else self._unaveraged_row(x2)
+        sched = self._usched[1]
+        meta = self.meta()
+        j_of = {tuple(meta['key'][c]): tuple(int(v) for v in meta['j'][c][:len(meta['key'][c])]) for c in range(len(meta['key']))}
+        coefs = [((), x2.reshape(batch_shape + (self.N,)))]                       # :294  S_0 = x
+        coefs += [(k, row[:, off:off + ln].reshape(batch_shape + (ln,))) for k, off, ln in sched.segments]
+        if self.out_type == 'array':                     # vectorize=False: dict keyed by the filter indices (:380-381)
+            out = {k: v for k, v in coefs}
+            return [out, out]
+        out = [{'coef': v, 'j': j_of[k]} for k, v in coefs]                      # :382-385
+        return [out, out]
+
+    def _unaveraged_row(self, x2):
         key = (self.J, self.N, self._Q1, self.T, self.max_order, int(self.oversampling))
         if getattr(self, '_usched', None) is None or self._usched[0] != key:
             self._usched = (key, build_plan_unaveraged(self.J, self.N, self._Q1, self.T, self.max_order,
@@ -369,19 +411,12 @@ class Scattering1D(nn.Module):
         index = dev.index if dev.index is not None else torch.cuda.current_device()
         if index not in self._uplans:
             self._uplans[index] = _DevicePlan(sched, index)
+            self._apply_window(self._uplans[index])
         B = x2.shape[0]
         row = torch.empty((B, sched.n_out), dtype=torch.float32, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(_lib.load().tebscat_scat1d_forward(self._uplans[index].handle, x2.data_ptr(), B, row.data_ptr(), stream))
-        meta = self.meta()
-        j_of = {tuple(meta['key'][c]): tuple(int(v) for v in meta['j'][c][:len(meta['key'][c])]) for c in range(len(meta['key']))}
-        coefs = [((), x2.reshape(batch_shape + (self.N,)))]                       # :294  S_0 = x
-        coefs += [(k, row[:, off:off + ln].reshape(batch_shape + (ln,))) for k, off, ln in sched.segments]
-        if self.out_type == 'array':                     # vectorize=False: dict keyed by the filter indices (:380-381)
-            out = {k: v for k, v in coefs}
-            return [out, out]
-        out = [{'coef': v, 'j': j_of[k]} for k, v in coefs]                      # :382-385
-        return [out, out]
+        return row
 
     def forward_normalized(self, x, mean, variance, log_channels='all_except_0', asinh_channels=None,
                            log_epsilon=1e-6, trim=0, time_major=True):
