@@ -148,14 +148,15 @@ class LargeDevicePlan:
         self._graphs = {}
         self._seen = {}
 
-    def _graphed(self, kind, run, args, ins, outs):
+    def _graphed(self, kind, run, args, ins, outs, direct=True):
         """Run `run(*args)` through a CUDA graph.  `ins` / `outs`: the caller-owned tensors among `args`.
 
         A forward is a few thousand short launches (a backward ~1200 at the headline configuration): below ~1000
         signals they, not the arithmetic, set the time, so the op list of a batch size is captured once and replayed.
         When a call comes with buffers that were seen before (steady-state loops reuse addresses), the graph is
         captured ON those buffers and replays with no staging copy at all; a first sighting goes through a graph on
-        static buffers (one copy in, one copy out)."""
+        static buffers (one copy in, one copy out).  `direct=False` (the chunks of a long batch: many buffer
+        addresses, one batch size) always takes the static-buffer graph."""
         import os
         if os.environ.get('TEBSCAT_LARGE_GRAPH', '1') == '0':
             return run(*args)
@@ -164,17 +165,18 @@ class LargeDevicePlan:
         ptrs = tuple(t.data_ptr() for t in args)
         direct_key = (kind, B, dev.index) + ptrs
         staged_key = (kind, B, dev.index)
-        entry = self._graphs.get(direct_key)
-        if entry is None and self._seen.get(direct_key, 0) >= 1:
+        entry = self._graphs.get(direct_key) if direct else None
+        if direct and entry is None and self._seen.get(direct_key, 0) >= 1:
             entry = self._capture(run, args, dev)
             self._remember(direct_key, entry)
         if entry is not None:
             self._graphs[direct_key] = self._graphs.pop(direct_key)      # most recently used last
             entry['graph'].replay()
             return args[-1]
-        if len(self._seen) > 64:
-            self._seen = {}
-        self._seen[direct_key] = self._seen.get(direct_key, 0) + 1
+        if direct:
+            if len(self._seen) > 64:
+                self._seen = {}
+            self._seen[direct_key] = self._seen.get(direct_key, 0) + 1
         entry = self._graphs.get(staged_key)
         if entry is None:
             static = tuple(torch.empty_like(t) for t in args)
@@ -211,9 +213,17 @@ class LargeDevicePlan:
         while len(self._graphs) > self.GRAPH_SLOTS:
             self._graphs.pop(next(iter(self._graphs)))
 
-    def forward(self, x2, out):
+    def forward(self, x2, out, direct=True):
         """x2: (B, N) float32 CUDA contiguous; out: (B, C, n_out) float32 CUDA."""
-        return self._graphed('fwd', self._run, (x2, out), ins=(x2,), outs=(out,))
+        return self._graphed('fwd', self._run, (x2, out), ins=(x2,), outs=(out,), direct=direct)
+
+    def bytes_per_signal(self, backward=False):
+        """Workspace bytes one signal occupies on this level (what has to stay in L2 for the ops of a chunk to find
+        their operands there instead of in HBM)."""
+        Np = 1 << self.plan.geo.J_pad
+        if backward:
+            return 8 * Np * 8 + (2 << self.plan.lf) * 4
+        return 2 * Np * 8 + (2 << self.plan.max_l2) * 4 + (2 << self.plan.lf) * 4
 
     def _run(self, x2, out):
         p, lib, g = self.plan, self._lib, self.handle
@@ -270,9 +280,9 @@ class LargeDevicePlan:
             self._graphs = {k: v for k, v in self._graphs.items() if k[0] != 'bwd'}
         return self._bws['bufs']
 
-    def backward(self, x2, gout, gx):
+    def backward(self, x2, gout, gx, direct=True):
         """gx = (dS/dx)^T gout, through the graph cache of `_graphed`."""
-        return self._graphed('bwd', self._run_backward, (x2, gout, gx), ins=(x2, gout), outs=(gx,))
+        return self._graphed('bwd', self._run_backward, (x2, gout, gx), ins=(x2, gout), outs=(gx,), direct=direct)
 
     def _run_backward(self, x2, gout, gx):
         """gx = (dS/dx)^T gout for x2 (B, N), gout (B, C, n_out), gx (B, N), all float32 CUDA contiguous.
@@ -351,13 +361,13 @@ class LargeDevicePlan:
         return gx
 
     # ---- backward of average=False (the un-averaged moduli are the outputs) ----------------------------------------
-    def backward_unaveraged(self, x2, grow, gx, segments):
+    def backward_unaveraged(self, x2, grow, gx, segments, direct=True):
         """gx = (d row / dx)^T grow for the average=False transform: `row` holds the unpadded moduli U1 / U2 back to back
         (`segments` = [(key, offset, length)] of schedule.build_plan_unaveraged; order 0 -- the input itself -- is the
         frontend's business).  Same graph cache as the other directions."""
         self._useg = {tuple(k): (int(off), int(ln)) for k, off, ln in segments}
         self._urow = int(grow.shape[-1])
-        return self._graphed('bwdu', self._run_backward_unaveraged, (x2, grow, gx), ins=(x2, grow), outs=(gx,))
+        return self._graphed('bwdu', self._run_backward_unaveraged, (x2, grow, gx), ins=(x2, grow), outs=(gx,), direct=direct)
 
     def _run_backward_unaveraged(self, x2, grow, gx):
         """The transposed cascade of core/scattering1d.py:300-367 with average=False: a path's output is |u| itself

@@ -332,9 +332,9 @@ class Scattering1D(nn.Module):
         if self.J_pad > LOG2_NP_MAX or self._op_by_op:
             lp, ldp = self._large_plan_for(index)
             S = torch.empty((B, lp.n_paths, lp.n_out), dtype=torch.float32, device=dev)
-            chunk = max(1, (1 << 28) >> self.J_pad)              # B * Np <= 2^28: U0 and W1 2 GB each, W2 <= 2 GB, leaves: <= 6.2 GB
+            chunk = self._large_chunk(ldp, backward=False)
             for b0 in range(0, B, chunk):
-                ldp.forward(x2[b0:b0 + chunk], S[b0:b0 + chunk])
+                ldp.forward(x2[b0:b0 + chunk], S[b0:b0 + chunk], direct=B <= chunk)
             return S
         plan = self._plan_for(index)
         sched = self._sched[1]
@@ -342,6 +342,19 @@ class Scattering1D(nn.Module):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(_lib.load().tebscat_scat1d_forward(plan.handle, x2.data_ptr(), B, S.data_ptr(), stream))
         return S
+
+    def _large_chunk(self, ldp, backward):
+        """Signals per chunk of the op-by-op levels, bounded by workspace memory: B * Np <= 2^28 forward (U0 and W1 2 GB
+        each, W2 <= 2 GB, leaves: <= 6.2 GB), 2^25 backward (eight buffers of 256 MB + leaves).  As large as memory
+        allows on purpose: every op is one launch over the chunk and its tile jobs run at the interpreter's per-step
+        latency, so the level is launch/latency-bound, not HBM-bound -- measured (tools/l2_chunk_sweep.sh,
+        profiles/r02_l2_chunk_sweep.txt): chunks sized for their workspace to stay in L2 (64 MB) run at 2.4 instead of
+        5.7 TFLOP/s at a padded length of 2^14, and the backward at 19 k instead of 42 k signals/s."""
+        import os
+        if os.environ.get('TEBSCAT_LARGE_L2_MB'):              # experiment switch of the sweep tool
+            budget = int(float(os.environ['TEBSCAT_LARGE_L2_MB']) * (1 << 20))
+            return int(max(16, min(1 << 16, budget // ldp.bytes_per_signal(backward))))
+        return max(1, ((1 << 25) if backward else (1 << 28)) >> self.J_pad)
 
     def _large_plan_for(self, index):
         """Op-list plan of the large-support level: the forward above 2^13 and the backward pass at any length."""
@@ -365,9 +378,9 @@ class Scattering1D(nn.Module):
         if gS.dtype is not torch.float32:
             raise TypeError('Input and filter must be of the same dtype.')
         gx = torch.empty_like(x2)
-        chunk = max(1, (1 << 25) >> self.J_pad)                  # B * Np <= 2^25: eight buffers of 256 MB + leaves, <= 2.1 GB
+        chunk = self._large_chunk(ldp, backward=True)
         for b0 in range(0, x2.shape[0], chunk):
-            ldp.backward(x2[b0:b0 + chunk], gS[b0:b0 + chunk], gx[b0:b0 + chunk])
+            ldp.backward(x2[b0:b0 + chunk], gS[b0:b0 + chunk], gx[b0:b0 + chunk], direct=x2.shape[0] <= chunk)
         return gx
 
     def _backward_unaveraged(self, x2, grow):
@@ -378,9 +391,10 @@ class Scattering1D(nn.Module):
         sched = self._usched[1]
         grow = grow.contiguous()
         gx = torch.empty_like(x2)
-        chunk = max(1, (1 << 25) >> self.J_pad)
+        chunk = self._large_chunk(ldp, backward=True)
         for b0 in range(0, x2.shape[0], chunk):
-            ldp.backward_unaveraged(x2[b0:b0 + chunk], grow[b0:b0 + chunk], gx[b0:b0 + chunk], sched.segments)
+            ldp.backward_unaveraged(x2[b0:b0 + chunk], grow[b0:b0 + chunk], gx[b0:b0 + chunk], sched.segments,
+                                    direct=x2.shape[0] <= chunk)
         return gx
 
     def _scattering_unaveraged(self, x2, batch_shape, needs_grad=False):
