@@ -75,6 +75,18 @@ int tebscat_plan_create(const tebscat_plan_desc* desc,
 
 void tebscat_plan_destroy(tebscat_plan* plan);
 
+/* Plan files.  The schedule of a configuration is built by tebscat/schedule.py (host Python, like the reference's own
+ * filter factory); _save writes everything tebscat_plan_create takes into one self-describing, checksummed file
+ * (`python -m tebscat.export_plan` does it from the command line) and _load creates the plan from it, so that a consumer
+ * without Python (C, C++, or any FFI) can run the transform: tebscat_plan_load + tebscat_scat1d_forward.  The file is
+ * validated like a direct call (schedule checks, ABI version, sizes, checksum): a malformed file is TEBSCAT_EINVAL. */
+int tebscat_plan_save(const char* path, const tebscat_plan_desc* desc, const float* filter_arena_host, size_t n_floats,
+                      const int32_t* tasks_host, const int32_t* steps_host,
+                      const int32_t* channel_table_host, size_t n_channel_entries);
+int tebscat_plan_load(const char* path, int device, tebscat_plan** out);
+/* The description a plan was created with (input length N, output geometry n_paths x n_out, ...). */
+int tebscat_plan_get_desc(const tebscat_plan* plan, tebscat_plan_desc* out);
+
 /* Analysis window applied to the samples as the plan's loads read them: x[t] * window[t] before padding.
  * window_host: N floats (copied), or NULL to remove it.  Replaces the eager `x = x * window` of
  * KymatioPhaseScattering1D.forward (hdf5_dataset/kymatio_phase_scattering.py:405-407; the Tukey taper of
@@ -169,6 +181,16 @@ int tebscat_phase_forward(tebscat_phase_plan* plan, const float* x_dev, int64_t 
 int tebscat_phase_plan_profile(tebscat_phase_plan* plan, int enable);
 int tebscat_phase_plan_profile_read(tebscat_phase_plan* plan, double* stage_a_ms, double* stage_b_ms, int* n_chunks);
 
+/* Padded lengths above 2^13: no stage-A plan exists (the analytic signals come from tebscat_large_* ops, see
+ * tebscat_large_storez); the plan holds the pair tables and the dense operator only, and stage B runs on workspaces the
+ * caller owns: zp_dev [nb][F][N] (|z|, theta) of the 'i' channel, zc_dev [nb][F][N] (re, im) of the 'j' channel
+ * (kymatio_phase_scattering.py:275-360).  nb * F * N < 2^31. */
+int tebscat_phase_plan_create_pairs_only(const tebscat_phase_desc* desc, int device, const float* G_host,
+                                         const int32_t* i_idx, const int32_t* j_idx, const float* powers,
+                                         tebscat_phase_plan** out);
+int tebscat_phase_pairs(tebscat_phase_plan* plan, const float* zp_dev, const float* zc_dev, int64_t nb,
+                        const int32_t* pair_subset_host, int n_subset, int apply_low_pass, float* out_dev, void* stream);
+
 /* Optional: run stage B (the low-pass of every (sample, pair) product, _apply_phi_filter :233-273) as
  * transforms on the step interpreter instead of the dense operator.  `pair_plan` is a plan created with
  * tebscat_plan_create whose schedule starts with LOADPAIR tasks (tebscat/phase.py builds it); the phase
@@ -216,6 +238,11 @@ int tebscat_large_modulus(tebscat_large* ctx, float* buf_dev, int64_t n_complex,
 /* unpad + concatenate (torch_backend.py:80-102, kymatio/backend/torch_backend.py:143-145) */
 int tebscat_large_store(tebscat_large* ctx, const float* buf_dev, int64_t B, int log_len, int i0, int n_out, int n_paths,
                         int channel, float* out_dev, void* stream);
+
+/* phase stage A on this level (hdf5_dataset/kymatio_phase_scattering.py:220-231): buf_dev[b, i0 : i0 + N] of filter f ->
+ * zc_dev [B][F][N] (re, im) if mode & 1, zp_dev [B][F][N] (|z|, atan2) if mode & 2 */
+int tebscat_large_storez(tebscat_large* ctx, const float* buf_dev, int64_t B, int log_len, int i0, int N, int F, int f,
+                         int mode, float* zc_dev, float* zp_dev, void* stream);
 
 /* A whole leaf in one launch: phi multiply + periodise (as tebscat_large_mulfold) down to 2^lf = 2^(log_src - logk)
  * <= 1024 bins -> inverse transform -> samples [i0, i0 + n_out) -> channel (core/scattering1d.py:287-292, :320-327,

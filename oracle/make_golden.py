@@ -164,6 +164,9 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['phase-randn']:
         phase_fixture_randn('Hr', 'H', 4)
         sys.exit(0)
+    if sys.argv[1:] == ['phase-large']:
+        phase_fixture('L', 1)
+        sys.exit(0)
     if sys.argv[1:] == ['phase-nodec']:
         phase_option_fixture('S_nodec', 'S', 1, oversampling=4)
         sys.exit(0)
@@ -181,6 +184,7 @@ if __name__ == '__main__':
     phase_fixture('H', 1)
     phase_fixture('P', 1)
     phase_fixture('S', 2)
+    phase_fixture('L', 1)                       # padded length 2**14: stage A on the large-support level
     phase_fixture_randn('Hr', 'H', 4)
     phase_option_fixtures()
     kat = np.load(os.path.join(REF, 'kymatio/tests/scattering1d/test_data_1d.npz'))

@@ -218,3 +218,45 @@ def test_level_selection_follows_the_current_options():
     assert S._op_by_op                          # 2048 samples at the output rate: op-by-op level
     S.oversampling = 0
     assert not S._op_by_op
+
+
+def test_plan_files_are_validated(tmp_path):
+    """tebscat_plan_save / tebscat_plan_load (the ABI without the Python scheduler at run time): a saved plan reaches
+    plan creation (on a box without a GPU that is the first CUDA call: RuntimeError), anything else is refused on the
+    host with TEBSCAT_EINVAL -- wrong magic, truncation, trailing bytes, a flipped payload bit (checksum), and a
+    schedule that does not validate is not even written."""
+    import ctypes
+    from tebscat import _lib
+    from tebscat.export_plan import main as export_main, save_plan
+    from tebscat.schedule import build_plan
+    lib = _lib.load()
+    path = str(tmp_path / 'T.tebplan')
+    export_main(['--J', '5', '--shape', '700', '--Q', '2', '--T', '8', path])
+    blob = open(path, 'rb').read()
+    assert blob[:8] == b'TEBSCATP'
+
+    def load(p):
+        h = ctypes.c_void_p()
+        rc = lib.tebscat_plan_load(p.encode(), 0, ctypes.byref(h))
+        if rc == 0:
+            lib.tebscat_plan_destroy(h)
+        return rc, lib.tebscat_last_error().decode()
+
+    rc, msg = load(path)
+    assert rc in (_lib.TEBSCAT_OK, _lib.TEBSCAT_ECUDA), (rc, msg)       # valid file: only the device can object
+    for name, data, word in (('magic', b'X' + blob[1:], 'not a tebscat plan file'),
+                             ('short', blob[:-100], 'truncated'),
+                             ('long', blob + b'\0', 'trailing'),
+                             ('flip', blob[:5000] + bytes([blob[5000] ^ 1]) + blob[5001:], 'checksum')):
+        bad = str(tmp_path / (name + '.tebplan'))
+        open(bad, 'wb').write(data)
+        rc, msg = load(bad)
+        assert rc == _lib.TEBSCAT_EINVAL and word in msg, (name, rc, msg)
+    rc, msg = load(str(tmp_path / 'missing.tebplan'))
+    assert rc == _lib.TEBSCAT_EINVAL and 'cannot open' in msg
+    p = build_plan(5, 700, 2, 8, 2)
+    p.tasks = p.tasks.copy()
+    p.tasks[3, 1] = 5000                                               # thread range outside the CTA
+    with pytest.raises(ValueError):
+        save_plan(p, str(tmp_path / 'bad.tebplan'))
+    assert not (tmp_path / 'bad.tebplan').exists()

@@ -331,3 +331,31 @@ def test_analysis_window_on_every_level(cfg):
     assert torch.allclose(xg.grad, xr.grad * w, rtol=1e-6, atol=1e-6 * float(xr.grad.abs().max()))
     tapered.set_window(None)
     assert torch.equal(tapered(x)[0], plain(x)[0])
+
+
+@pytest.mark.gpu
+def test_c_consumer_without_python_at_run_time(tmp_path):
+    """The ABI is self-sufficient for a non-Python consumer: examples/c_consumer.c, plain C compiled with
+    gcc against include/tebscat.h, loads a plan FILE and transforms host signals; same numbers as the torch frontend,
+    bit for bit."""
+    import subprocess
+    from tebscat import Scattering1D
+    from tebscat.export_plan import main as export_main
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, 'vae-teb_b200', 'tebscat')
+    exe = str(tmp_path / 'c_consumer')
+    subprocess.run(['gcc', '-O2', '-I', os.path.join(root, 'include'), os.path.join(root, 'examples', 'c_consumer.c'), '-o', exe,
+                    '-L', libdir, '-ltebscat', '-Wl,-rpath,' + libdir, '-lm'], check=True)
+    J, N, Q, T, mo = CONFIGS['S']
+    plan_path, x_path, s_path = (str(tmp_path / n) for n in ('S.tebplan', 'x.f32', 'S.f32'))
+    export_main(['--J', str(J), '--shape', str(N), '--Q', str(Q), '--T', str(T), '--max-order', str(mo), plan_path])
+    x = np.random.RandomState(8).randn(37, N).astype(np.float32)
+    x.tofile(x_path)
+    r = subprocess.run([exe, plan_path, x_path, s_path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    ref = S(torch.from_numpy(x).cuda())[0].cpu().numpy()
+    got = np.fromfile(s_path, np.float32).reshape(ref.shape)
+    assert np.array_equal(got, ref)
+    bad = subprocess.run([exe, x_path, x_path, s_path], capture_output=True, text=True)      # not a plan file
+    assert bad.returncode == 1 and 'not a tebscat plan file' in bad.stderr

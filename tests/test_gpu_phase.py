@@ -26,7 +26,8 @@ from oracle.phase_oracle import PhaseOracle
 
 pytestmark = pytest.mark.gpu
 
-CFG = {'H': (6, 8, 64, 4800, 2), 'Hr': (6, 8, 64, 4800, 2), 'P': (11, 4, 16, 5760, 1), 'S': (4, 4, 16, 1000, 2)}
+CFG = {'H': (6, 8, 64, 4800, 2), 'Hr': (6, 8, 64, 4800, 2), 'P': (11, 4, 16, 5760, 1), 'S': (4, 4, 16, 1000, 2),
+       'L': (6, 4, 64, 9000, 2)}
 FORMS = {'tcgen05': ('0', 'tc'), 'mma.sync': ('0', 'sync'), 'transform': ('1', 'tc')}
 _mods = {}
 
@@ -349,3 +350,37 @@ def test_phase_without_decimation_matches_oracle_and_reference():
     sub = np.arange(0, len(o.i_idx), 7)
     part = m(x, compute_phase=False, compute_cross_phase=True, phase_pairs=sub)['cross_phase_corr']
     assert torch.equal(part, rc['cross_phase_corr'][:, torch.from_numpy(sub).cuda()])
+
+
+@pytest.mark.parametrize('kernel', ['tc', 'sync'])
+def test_phase_at_a_padded_length_of_2_14(kernel, monkeypatch):
+    """N = 9000 -> padded length 2^14: no spectrum fits one SM.  Stage A runs on the ops of the large-support level
+    (tebscat_large_*, one launch per op over a chunk of samples), stage B in its dense form (decimation factor 63: not
+    a power of two) on either tensor-core kernel.  Pinned against the live reference (fixture phase_L.npz)."""
+    d = np.load(os.path.join(GOLDEN, 'phase_L.npz'))
+    J, Q, T, N, mo = CFG['L']
+    monkeypatch.setenv('TEBSCAT_PHASE_MMA', kernel)
+    m = module_of('L')
+    assert m.J_pad == 14 and m._plan.large and m._plan.dec == 63
+    x = torch.from_numpy(d['x']).cuda()
+    o = PhaseOracle(J, Q, T, N, d['scattering'].shape[-1])
+    assert np.array_equal(o.powers, d['powers']) and np.array_equal(m.powers.cpu().numpy(), d['powers'])
+    rw = m(x, compute_phase=True, phase_channels=[0])
+    rc = m(x, compute_phase=False, compute_cross_phase=True, phase_channels=[0, 1])
+    # (the scattering part at this length: large-support level; row 0 is CTG-shaped, see test_gpu_large)
+    assert rel_l2(rw['scattering'].cpu().numpy(), d['scattering']) < 5e-6
+    for ours, ref, mode in ((rw['phase_corr'], d['within'], 'within'), (rc['cross_phase_corr'], d['cross'], 'cross')):
+        ours = ours.cpu().numpy().astype(np.float64)
+        assert ours.shape == ref.shape
+        xm = d['x'][:, 0] if mode == 'within' else d['x']
+        check(ours, o, xm, mode, 'Np=2^14/%s/%s' % (kernel, mode), None, ref, randn_rows=[1])
+    sub = np.arange(3, len(o.i_idx), 11)
+    part = m(x, compute_phase=False, compute_cross_phase=True, phase_pairs=sub)['cross_phase_corr']
+    assert torch.equal(part, rc['cross_phase_corr'][:, torch.from_numpy(sub).cuda()])
+    full = m(x[1:], compute_phase=False, compute_cross_phase=True, cross_phase_low_pass=False)['cross_phase_corr']   # the randn row
+    ref_full = o(d['x'][1:], mode='cross', low_pass=False)
+    assert full.shape == ref_full.shape and rel_l2(full.cpu().numpy()[..., 2:-2], ref_full[..., 2:-2]) < 5e-5
+    sel = m.get_optimal_coefficients_for_fhr(J, Q, T)['recommendations']
+    one = m.forward_dataset(x, sel['use_phase_mask'], sel['use_cross_mask'])
+    assert torch.equal(one['phase_corr'], rw['phase_corr'][:, sel['use_phase_mask']])
+    assert torch.equal(one['cross_phase_corr'], rc['cross_phase_corr'][:, sel['use_cross_mask']])

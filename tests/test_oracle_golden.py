@@ -107,7 +107,7 @@ def _pin_phase_oracle(o, x, ref, mode, sub, randn_rows, tag):
     assert rel_l2(aligned, ref) < 5e-5, (tag, mode, rel_l2(aligned, ref))
 
 
-@pytest.mark.parametrize('name', ['H', 'Hr', 'P', 'S'])
+@pytest.mark.parametrize('name', ['H', 'Hr', 'P', 'S', 'L'])
 def test_phase_vs_reference(golden_dir, name):
     d = load(golden_dir, 'phase_%s.npz' % name)
     J, Q, T, N = int(d['J']), int(d['Q']), int(d['T']), int(d['N'])

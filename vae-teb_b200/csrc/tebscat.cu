@@ -506,6 +506,99 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     return TEBSCAT_OK;
 }
 
+extern "C" int tebscat_plan_get_desc(const tebscat_plan* p, tebscat_plan_desc* out) {
+    if (!p || !out) return fail(TEBSCAT_EINVAL, "null argument");
+    *out = p->desc;
+    return TEBSCAT_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// plan files: everything tebscat_plan_create takes, in one self-describing file, so that a consumer without the
+// Python scheduler (tebscat/schedule.py builds the schedule) can create plans at run time
+// ---------------------------------------------------------------------------------
+namespace {
+struct PlanFileHeader {
+    char magic[8];            // "TEBSCATP"
+    int32_t abi_version;
+    int32_t header_bytes;
+    uint64_t n_floats, n_chan;
+    uint64_t checksum;        // FNV-1a over desc + payload
+    tebscat_plan_desc desc;
+};
+uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+}  // namespace
+
+extern "C" int tebscat_plan_save(const char* path, const tebscat_plan_desc* desc, const float* arena, size_t n_floats,
+                                 const int32_t* tasks, const int32_t* steps, const int32_t* chan, size_t n_chan) {
+    if (!path || !desc || !arena || !tasks || !steps || !chan) return fail(TEBSCAT_EINVAL, "null argument");
+    if (desc->abi_version != TEBSCAT_ABI_VERSION) return fail(TEBSCAT_EINVAL, "ABI version %d != %d", desc->abi_version, TEBSCAT_ABI_VERSION);
+    if (desc->n_tasks < 1 || desc->n_steps < 1) return fail(TEBSCAT_EINVAL, "empty plan");
+    if (int rc = validate_schedule(*desc, tasks, steps, n_floats, n_chan)) return rc;
+    PlanFileHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "TEBSCATP", 8);
+    h.abi_version = TEBSCAT_ABI_VERSION;
+    h.header_bytes = (int32_t)sizeof(h);
+    h.n_floats = n_floats;
+    h.n_chan = n_chan;
+    h.desc = *desc;
+    uint64_t c = fnv1a(1469598103934665603ull, desc, sizeof(*desc));
+    c = fnv1a(c, arena, n_floats * sizeof(float));
+    c = fnv1a(c, tasks, (size_t)desc->n_tasks * kTaskInts * sizeof(int32_t));
+    c = fnv1a(c, steps, (size_t)desc->n_steps * 2 * sizeof(int32_t));
+    c = fnv1a(c, chan, n_chan * sizeof(int32_t));
+    h.checksum = c;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(TEBSCAT_EINVAL, "cannot open %s for writing", path);
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(arena, sizeof(float), n_floats, f) == n_floats &&
+              fwrite(tasks, sizeof(int32_t), (size_t)desc->n_tasks * kTaskInts, f) == (size_t)desc->n_tasks * kTaskInts &&
+              fwrite(steps, sizeof(int32_t), (size_t)desc->n_steps * 2, f) == (size_t)desc->n_steps * 2 &&
+              (n_chan == 0 || fwrite(chan, sizeof(int32_t), n_chan, f) == n_chan);
+    ok = (fclose(f) == 0) && ok;
+    return ok ? TEBSCAT_OK : fail(TEBSCAT_EINVAL, "short write to %s", path);
+}
+
+extern "C" int tebscat_plan_load(const char* path, int device, tebscat_plan** out) {
+    if (!path || !out) return fail(TEBSCAT_EINVAL, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(TEBSCAT_EINVAL, "cannot open %s", path);
+    PlanFileHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "TEBSCATP", 8) != 0 || h.header_bytes != (int32_t)sizeof(h)) {
+        fclose(f);
+        return fail(TEBSCAT_EINVAL, "%s is not a tebscat plan file", path);
+    }
+    if (h.abi_version != TEBSCAT_ABI_VERSION || h.desc.abi_version != TEBSCAT_ABI_VERSION) {
+        fclose(f);
+        return fail(TEBSCAT_EINVAL, "plan file of ABI version %d, library has %d", h.abi_version, TEBSCAT_ABI_VERSION);
+    }
+    if (h.desc.n_tasks < 1 || h.desc.n_steps < 1 || h.desc.n_tasks > (1 << 24) || h.desc.n_steps > (1 << 24) ||
+        h.n_floats < 1 || h.n_floats > ((uint64_t)1 << 32) || h.n_chan > ((uint64_t)1 << 28)) {
+        fclose(f);
+        return fail(TEBSCAT_EINVAL, "plan file with implausible sizes");
+    }
+    std::vector<float> arena(h.n_floats);
+    std::vector<int32_t> tasks((size_t)h.desc.n_tasks * kTaskInts), steps((size_t)h.desc.n_steps * 2), chan(h.n_chan ? h.n_chan : 1);
+    bool ok = fread(arena.data(), sizeof(float), arena.size(), f) == arena.size() &&
+              fread(tasks.data(), sizeof(int32_t), tasks.size(), f) == tasks.size() &&
+              fread(steps.data(), sizeof(int32_t), steps.size(), f) == steps.size() &&
+              (h.n_chan == 0 || fread(chan.data(), sizeof(int32_t), h.n_chan, f) == h.n_chan);
+    char extra;
+    ok = ok && fread(&extra, 1, 1, f) == 0;          // nothing may follow the payload
+    fclose(f);
+    if (!ok) return fail(TEBSCAT_EINVAL, "plan file %s is truncated or has trailing bytes", path);
+    uint64_t c = fnv1a(1469598103934665603ull, &h.desc, sizeof(h.desc));
+    c = fnv1a(c, arena.data(), arena.size() * sizeof(float));
+    c = fnv1a(c, tasks.data(), tasks.size() * sizeof(int32_t));
+    c = fnv1a(c, steps.data(), steps.size() * sizeof(int32_t));
+    c = fnv1a(c, chan.data(), h.n_chan * sizeof(int32_t));
+    if (c != h.checksum) return fail(TEBSCAT_EINVAL, "plan file %s fails its checksum", path);
+    return tebscat_plan_create(&h.desc, arena.data(), arena.size(), tasks.data(), steps.data(), chan.data(), h.n_chan, device, out);
+}
+
 extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
@@ -929,21 +1022,44 @@ struct tebscat_phase_plan {
     std::vector<cudaEvent_t> prof_ev;    // triples (before A, between, after B)
 };
 
+static int phase_plan_create_impl(const tebscat_phase_desc* d, tebscat_plan* stage_a, int device, const float* G_host,
+                                  const int32_t* i_idx, const int32_t* j_idx, const float* powers, tebscat_phase_plan** out);
+
 extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_plan* stage_a, const float* G_host,
                                          const int32_t* i_idx, const int32_t* j_idx, const float* powers,
                                          tebscat_phase_plan** out) {
+    if (!stage_a) return fail(TEBSCAT_EINVAL, "null argument");
+    return phase_plan_create_impl(d, stage_a, stage_a->device, G_host, i_idx, j_idx, powers, out);
+}
+
+// A phase plan WITHOUT a stage-A plan: for padded lengths above 2^13 the analytic signals come from the ops of the
+// large-support level (tebscat_large_*, driven by tebscat/phase.py) and stage B runs on the workspaces the caller
+// hands to tebscat_phase_pairs.
+extern "C" int tebscat_phase_plan_create_pairs_only(const tebscat_phase_desc* d, int device, const float* G_host,
+                                                    const int32_t* i_idx, const int32_t* j_idx, const float* powers,
+                                                    tebscat_phase_plan** out) {
+    if (!G_host) return fail(TEBSCAT_EINVAL, "a pairs-only plan needs the dense operator");
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(TEBSCAT_EINVAL, "device %d not in [0,%d)", device, n_dev);
+    return phase_plan_create_impl(d, nullptr, device, G_host, i_idx, j_idx, powers, out);
+}
+
+static int phase_plan_create_impl(const tebscat_phase_desc* d, tebscat_plan* stage_a, int device, const float* G_host,
+                                  const int32_t* i_idx, const int32_t* j_idx, const float* powers, tebscat_phase_plan** out) {
     // G_host may be NULL: the plan then has no dense form of stage B and needs an attached pair plan
     // (configurations without decimation, where the dense operator would be N x N)
-    if (!d || !stage_a || !i_idx || !j_idx || !powers || !out) return fail(TEBSCAT_EINVAL, "null argument");
+    if (!d || !i_idx || !j_idx || !powers || !out) return fail(TEBSCAT_EINVAL, "null argument");
     if (d->abi_version != TEBSCAT_ABI_VERSION) return fail(TEBSCAT_EINVAL, "ABI version mismatch");
-    if (d->N != stage_a->desc.N || d->n_filters != stage_a->desc.n_paths || stage_a->desc.n_out != d->N)
+    if (d->N < 2 || d->n_filters < 1) return fail(TEBSCAT_EINVAL, "bad phase description");
+    if (stage_a && (d->N != stage_a->desc.N || d->n_filters != stage_a->desc.n_paths || stage_a->desc.n_out != d->N))
         return fail(TEBSCAT_EINVAL, "stage-A plan does not match the phase description");
     if (d->n_pairs < 1 || d->n_out < 1 || (G_host && (d->n_cols_pad < d->n_out || d->n_cols_pad % kPC != 0)))
         return fail(TEBSCAT_EINVAL, "bad phase description");
     for (int k = 0; k < d->n_pairs; ++k)
         if (i_idx[k] < 0 || i_idx[k] >= d->n_filters || j_idx[k] < 0 || j_idx[k] >= d->n_filters)
             return fail(TEBSCAT_EINVAL, "pair %d references a filter outside [0,%d)", k, d->n_filters);
-    CU(cudaSetDevice(stage_a->device));
+    CU(cudaSetDevice(device));
     CU(cudaFuncSetAttribute(phase_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
     std::unique_ptr<tebscat_phase_plan, void (*)(tebscat_phase_plan*)> guard(new tebscat_phase_plan(), [](tebscat_phase_plan* q) {
         q->stage_a = nullptr;                    // on failure the caller keeps the stage-A plan
@@ -952,7 +1068,7 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
     tebscat_phase_plan* p = guard.get();
     p->desc = *d;
     p->stage_a = stage_a;
-    p->device = stage_a->device;
+    p->device = device;
     const size_t g_elems = (size_t)d->N * d->n_cols_pad;
     if (G_host) {
         CU(cudaMalloc(&p->d_G, g_elems * sizeof(float2)));
@@ -1017,6 +1133,7 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
 // the window acts where the samples enter: stage A's loads (both channels go through the same stage-A plan)
 extern "C" int tebscat_phase_plan_set_window(tebscat_phase_plan* p, const float* window_host) {
     if (!p) return fail(TEBSCAT_EINVAL, "null plan");
+    if (!p->stage_a) return fail(TEBSCAT_EUNSUPPORTED, "this phase plan has no stage A (its loads belong to a tebscat_large context)");
     std::lock_guard<std::mutex> lock(p->mu);
     return tebscat_plan_set_window(p->stage_a, window_host);
 }
@@ -1108,6 +1225,7 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
             if (pair_subset_host[k] < 0 || pair_subset_host[k] >= p->desc.n_pairs)
                 return fail(TEBSCAT_EINVAL, "pair subset entry %d outside [0,%d)", k, p->desc.n_pairs);
     if (B == 0) return TEBSCAT_OK;
+    if (!p->stage_a) return fail(TEBSCAT_EUNSUPPORTED, "this phase plan has no stage A: use tebscat_phase_pairs on analytic signals");
     std::lock_guard<std::mutex> lock(p->mu);
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(p->device));
@@ -1233,6 +1351,49 @@ static int launch_pairs(const tebscat_phase_plan* p, const float2* zp, const flo
     return TEBSCAT_OK;
 }
 
+// Stage B alone, on analytic signals the caller has produced (padded lengths above 2^13: stage A runs on the ops of the
+// large-support level): zp_dev [nb][F][N] (|z|, theta) of the 'i' channel, zc_dev [nb][F][N] (re, im) of the 'j' channel.
+extern "C" int tebscat_phase_pairs(tebscat_phase_plan* p, const float* zp_dev, const float* zc_dev, int64_t nb,
+                                   const int32_t* pair_subset_host, int n_subset, int apply_low_pass, float* out_dev, void* stream) {
+    g_launches = 0;
+    if (!p || nb < 0 || (nb > 0 && (!zp_dev || !zc_dev || !out_dev))) return fail(TEBSCAT_EINVAL, "null argument");
+    if (pair_subset_host && (n_subset < 1 || n_subset > p->desc.n_pairs)) return fail(TEBSCAT_EINVAL, "bad pair subset size");
+    if (pair_subset_host)
+        for (int k = 0; k < n_subset; ++k)
+            if (pair_subset_host[k] < 0 || pair_subset_host[k] >= p->desc.n_pairs)
+                return fail(TEBSCAT_EINVAL, "pair subset entry %d outside [0,%d)", k, p->desc.n_pairs);
+    if (nb == 0) return TEBSCAT_OK;
+    if ((long long)nb * p->desc.n_filters * p->desc.N >= (1LL << 31))
+        return fail(TEBSCAT_EINVAL, "workspace of %lld samples: chunk the batch (32-bit sample offsets)", (long long)nb);
+    std::lock_guard<std::mutex> lock(p->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(p->device));
+    const int n_sel = pair_subset_host ? n_subset : p->desc.n_pairs;
+    if (pair_subset_host) CU(cudaMemcpyAsync(p->d_subset, pair_subset_host, n_sel * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const int32_t* sub = pair_subset_host ? p->d_subset : nullptr;
+    if (apply_low_pass)
+        return launch_pairs(p, reinterpret_cast<const float2*>(zp_dev), reinterpret_cast<const float2*>(zc_dev), sub, n_sel, nb, out_dev, st);
+    PairParams pp;
+    pp.zp = reinterpret_cast<const float2*>(zp_dev);
+    pp.zc = reinterpret_cast<const float2*>(zc_dev);
+    pp.G = p->d_G;
+    pp.i_idx = p->d_i;
+    pp.j_idx = p->d_j;
+    pp.powers = p->d_pw;
+    pp.subset = sub;
+    pp.out = out_dev;
+    pp.rows = (long long)nb * n_sel;
+    pp.n_sel = n_sel;
+    pp.F = p->desc.n_filters;
+    pp.N = p->desc.N;
+    pp.n_out = p->desc.n_out;
+    pp.n_cols_pad = p->desc.n_cols_pad;
+    phase_product_kernel<<<1184, 256, 0, st>>>(pp);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
 // Single-pass dataset entry: within-channel correlations of channel ch_i for the
 // pairs `within_subset` AND cross-channel correlations ch_i x ch_j for `cross_subset`, with the
 // analytic signals of ch_i computed once.  Replaces the two st_model(...) calls and the masking
@@ -1245,6 +1406,7 @@ extern "C" int tebscat_phase_forward_dual(tebscat_phase_plan* p, const float* x_
     if (!p || B < 0 || (B > 0 && (!x_dev || !out_within_dev || !out_cross_dev))) return fail(TEBSCAT_EINVAL, "null argument");
     if (n_channels < 2 || ch_i < 0 || ch_i >= n_channels || ch_j < 0 || ch_j >= n_channels || ch_i == ch_j)
         return fail(TEBSCAT_EINVAL, "the dataset entry point needs two distinct channels in [0,%d)", n_channels);
+    if (!p->stage_a) return fail(TEBSCAT_EUNSUPPORTED, "this phase plan has no stage A: use tebscat_phase_pairs on analytic signals");
     if (!within_subset_host || !cross_subset_host || n_within < 1 || n_cross < 1 ||
         n_within + n_cross > 2 * p->desc.n_pairs)
         return fail(TEBSCAT_EINVAL, "bad pair subsets");
@@ -1936,6 +2098,34 @@ extern "C" int tebscat_large_unstore(tebscat_large* g, const float* gout_dev, in
     CU(cudaSetDevice(g->device));
     g_unstore_kernel<<<g->n_sms * 4, 256, 0, (cudaStream_t)stream>>>(gout_dev, reinterpret_cast<float2*>(buf_dev), B, log_len, i0,
                                                                       n_out, n_paths, channel);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
+// Phase stage A on the large-support level (kymatio_phase_scattering.py:220-231): the unpadded analytic signal of
+// filter f, buf[b, i0 : i0 + N], into the workspaces of the pair stage -- cartesian and / or polar like STOREZ
+__global__ void g_storez_kernel(const float2* __restrict__ buf, long long B, int log_len, int i0, int N, int F, int f, int mode,
+                                float2* __restrict__ zc, float2* __restrict__ zp) {
+    const long long total = B * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / N;
+        const int t = (int)(e - b * N);
+        const float2 z = buf[(b << log_len) + i0 + t];
+        const long long o = (b * F + f) * (long long)N + t;
+        if (mode & Z_CART) zc[o] = z;
+        if (mode & Z_POLAR) zp[o] = make_float2(sqrtf(fmaf(z.x, z.x, z.y * z.y)), atan2f(z.y, z.x));
+    }
+}
+
+extern "C" int tebscat_large_storez(tebscat_large* g, const float* buf_dev, int64_t B, int log_len, int i0, int N, int F, int f,
+                                    int mode, float* zc_dev, float* zp_dev, void* stream) {
+    if (!g || !buf_dev || B < 1 || log_len < 1 || log_len > kLargeMaxLog2 || i0 < 0 || N < 1 || i0 + N > (1 << log_len) ||
+        F < 1 || f < 0 || f >= F || !(mode & (Z_CART | Z_POLAR)) || ((mode & Z_CART) && !zc_dev) || ((mode & Z_POLAR) && !zp_dev))
+        return fail(TEBSCAT_EINVAL, "bad analytic-signal store request");
+    CU(cudaSetDevice(g->device));
+    g_storez_kernel<<<g->n_sms * 4, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(buf_dev), B, log_len, i0, N, F, f, mode,
+                                                                     reinterpret_cast<float2*>(zc_dev), reinterpret_cast<float2*>(zp_dev));
     CU(cudaGetLastError());
     ++g_launches;
     return TEBSCAT_OK;

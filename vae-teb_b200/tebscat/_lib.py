@@ -58,6 +58,13 @@ def load():
     lib.tebscat_plan_create.restype = ctypes.c_int
     lib.tebscat_plan_create.argtypes = [ctypes.POINTER(PlanDesc), fp, ctypes.c_size_t, i32p, i32p,
                                         i32p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.tebscat_plan_save.restype = ctypes.c_int
+    lib.tebscat_plan_save.argtypes = [ctypes.c_char_p, ctypes.POINTER(PlanDesc), fp, ctypes.c_size_t, i32p, i32p, i32p,
+                                      ctypes.c_size_t]
+    lib.tebscat_plan_get_desc.restype = ctypes.c_int
+    lib.tebscat_plan_get_desc.argtypes = [vp, ctypes.POINTER(PlanDesc)]
+    lib.tebscat_plan_load.restype = ctypes.c_int
+    lib.tebscat_plan_load.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]
     lib.tebscat_plan_set_window.restype = ctypes.c_int
     lib.tebscat_plan_set_window.argtypes = [vp, fp]
     lib.tebscat_phase_plan_set_window.restype = ctypes.c_int
@@ -76,6 +83,13 @@ def load():
     lib.tebscat_scat1d_host_copies_only.argtypes = [vp, vp, ctypes.c_int64, vp]
     lib.tebscat_phase_plan_create.restype = ctypes.c_int
     lib.tebscat_phase_plan_create.argtypes = [ctypes.POINTER(PhaseDesc), vp, fp, i32p, i32p, fp, ctypes.POINTER(vp)]
+    lib.tebscat_phase_plan_create_pairs_only.restype = ctypes.c_int
+    lib.tebscat_phase_plan_create_pairs_only.argtypes = [ctypes.POINTER(PhaseDesc), ctypes.c_int, fp, i32p, i32p, fp, ctypes.POINTER(vp)]
+    lib.tebscat_phase_pairs.restype = ctypes.c_int
+    lib.tebscat_phase_pairs.argtypes = [vp, vp, vp, ctypes.c_int64, i32p, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.tebscat_large_storez.restype = ctypes.c_int
+    lib.tebscat_large_storez.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, vp, vp, vp]
     lib.tebscat_phase_plan_profile.restype = ctypes.c_int
     lib.tebscat_phase_plan_profile.argtypes = [vp, ctypes.c_int]
     lib.tebscat_phase_plan_profile_read.restype = ctypes.c_int

@@ -116,7 +116,7 @@ class LargeDevicePlan:
                 for slots in sch.TILE_SLOTS:
                     _TilePlanOwner(handle, nlen, kind, device_index, slots)
         self.arena = torch.from_numpy(np.ascontiguousarray(plan.arena, np.float32)).to(torch.device('cuda', device_index))
-        self._ws, self._bws, self._graphs, self._seen = {}, {}, {}, {}
+        self._ws, self._bws, self._graphs = {}, {}, {}
 
     def __del__(self):
         try:
@@ -129,7 +129,7 @@ class LargeDevicePlan:
     # ---- workspaces and CUDA graphs ------------------------------------------------------------------------------
     # One grow-only workspace per direction, sized for the largest batch seen (a smaller batch uses a prefix): a
     # loader whose last batch is short, or a batch chunked with a remainder, does not reallocate anything.  Graphs
-    # are cached per (batch size, buffers) in a small LRU; growing a workspace drops the graphs that captured it.
+    # are cached per (direction, batch size) in a small LRU; growing a workspace drops the graphs that captured it.
     GRAPH_SLOTS = 6
 
     def _workspace(self, B, dev):
@@ -146,38 +146,23 @@ class LargeDevicePlan:
     def invalidate_graphs(self):
         """Forget every captured graph (a plan-level setting the kernels read through the context has changed)."""
         self._graphs = {}
-        self._seen = {}
 
     def _graphed(self, kind, run, args, ins, outs, direct=True):
         """Run `run(*args)` through a CUDA graph.  `ins` / `outs`: the caller-owned tensors among `args`.
 
         A forward is a few thousand short launches (a backward ~1200 at the headline configuration): below ~1000
-        signals they, not the arithmetic, set the time, so the op list of a batch size is captured once and replayed.
-        When a call comes with buffers that were seen before (steady-state loops reuse addresses), the graph is
-        captured ON those buffers and replays with no staging copy at all; a first sighting goes through a graph on
-        static buffers (one copy in, one copy out).  `direct=False` (the chunks of a long batch: many buffer
-        addresses, one batch size) always takes the static-buffer graph."""
+        signals they, not the arithmetic, set the time, so the op list of a batch size is captured once -- on static
+        buffers of that batch size -- and replayed between one copy in and one copy out (0.4 % of a forward at a
+        padded length of 2^14).  Capturing on the caller's own buffers instead (keyed by their addresses, measured:
+        +5 % on a loop that reuses its buffers) was dropped: a training loop's gradient buffers alternate between a
+        few addresses, every new combination costs a capture, and short runs never amortise them (`direct` is kept
+        in the signature for the callers and ignored)."""
         import os
         if os.environ.get('TEBSCAT_LARGE_GRAPH', '1') == '0':
             return run(*args)
         dev = args[0].device
-        B = args[0].shape[0]
-        ptrs = tuple(t.data_ptr() for t in args)
-        direct_key = (kind, B, dev.index) + ptrs
-        staged_key = (kind, B, dev.index)
-        entry = self._graphs.get(direct_key) if direct else None
-        if direct and entry is None and self._seen.get(direct_key, 0) >= 1:
-            entry = self._capture(run, args, dev)
-            self._remember(direct_key, entry)
-        if entry is not None:
-            self._graphs[direct_key] = self._graphs.pop(direct_key)      # most recently used last
-            entry['graph'].replay()
-            return args[-1]
-        if direct:
-            if len(self._seen) > 64:
-                self._seen = {}
-            self._seen[direct_key] = self._seen.get(direct_key, 0) + 1
-        entry = self._graphs.get(staged_key)
+        key = (kind, args[0].shape[0], dev.index)
+        entry = self._graphs.get(key)
         if entry is None:
             static = tuple(torch.empty_like(t) for t in args)
             for t, sbuf in zip(args, static):
@@ -185,9 +170,9 @@ class LargeDevicePlan:
                     sbuf.copy_(t)
             entry = self._capture(run, static, dev)
             entry['static'] = static
-            self._remember(staged_key, entry)
+            self._remember(key, entry)
         else:
-            self._graphs[staged_key] = self._graphs.pop(staged_key)
+            self._graphs[key] = self._graphs.pop(key)          # most recently used last
         for t, sbuf in zip(args, entry['static']):
             if any(t is i for i in ins):
                 sbuf.copy_(t)

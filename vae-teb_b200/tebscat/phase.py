@@ -93,8 +93,10 @@ class PhasePlan:
         self.J, self.Q, self.T, self.N = J, Q1, T, N
         self.border_mode, self.border = border_mode, BORDER_MODES[border_mode]
         self.geo = fbk.build_geometry(N, J, Q1, T, clamp_to_signal=True)     # :100-113
-        if self.geo.J_pad > sch.LOG2_NP_MAX:
-            raise NotImplementedError('padded length 2**%d exceeds the single-CTA design' % self.geo.J_pad)
+        # padded lengths above 2^13: stage A on the ops of the large-support level, stage B in its dense form
+        self.large = self.geo.J_pad > sch.LOG2_NP_MAX
+        if self.geo.J_pad > 17:
+            raise NotImplementedError('padded length 2**%d exceeds the large-support level (max 2**17)' % self.geo.J_pad)
         bank = fbk.build_filter_bank(self.geo.J_pad, J, Q1, T)               # :117-120
         self.bank = bank
         self.center_freqs = np.array([p.xi for p in bank.psi1], dtype=np.float32)       # :128
@@ -116,8 +118,18 @@ class PhasePlan:
             Np, start = 1 << self.geo.J_pad, self.geo.pad_left // self.dec
             if min(start + N // self.dec, max(Np // self.dec, 1)) - start <= 0:
                 self.dec = 1                          # zero-length decimated output: the reference falls back (:296-299)
-        self._build_stage_a()
         self.pair_plan = None
+        if self.large:
+            if self.dec == 1:
+                raise NotImplementedError('phase path without decimation at a padded length of 2**%d (the transform '
+                                          'form of stage B needs one spectrum per SM: <= 2**13)' % self.geo.J_pad)
+            arena = sch._Arena()
+            self.psi1_off = [arena.add(p.levels[0]) for p in bank.psi1]
+            self.arena = arena.finish()
+            self.tile_lengths = [sch.LOG2_NP_MAX]             # the long transforms run as 8192-sample tiles + one global pass
+            self.stage_a = None
+        else:
+            self._build_stage_a()
         if self.dec == 1:
             # no decimation (target length >= N, e.g. T = 1 or oversampling >= log2 T): the full-length low-pass
             # ifft(fft(pad(c)) phi)[pad_left : pad_left + N] (:268-273).  The dense operator would be N x N, so
@@ -132,7 +144,7 @@ class PhasePlan:
         Gp[:, :self.n_out, 0] = G.real
         Gp[:, :self.n_out, 1] = G.imag
         self.G = Gp
-        if self.dec & (self.dec - 1) == 0 and (1 << self.geo.J_pad) // self.dec >= 16:
+        if not self.large and self.dec & (self.dec - 1) == 0 and (1 << self.geo.J_pad) // self.dec >= 16:
             self._build_pair_plan(phi0)
 
     def _build_pair_plan(self, phi0, rows_per_job=None):
@@ -215,7 +227,9 @@ class PhasePlan:
 class _DevicePhasePlan:
     def __init__(self, plan: PhasePlan, device_index: int):
         lib = _lib.load()
-        stage_a = _DevicePlan(plan.stage_a, device_index)
+        self.plan = plan
+        self.large = None
+        stage_a = _DevicePlan(plan.stage_a, device_index) if not plan.large else None
         d = _lib.PhaseDesc()
         d.abi_version = _lib.ABI_VERSION
         d.N, d.n_filters, d.n_pairs = plan.N, len(plan.bank.psi1), len(plan.i_idx)
@@ -226,13 +240,22 @@ class _DevicePhasePlan:
         pw = np.ascontiguousarray(plan.powers, np.float32)
         handle = ctypes.c_void_p()
         i32p, fp = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)
-        rc = lib.tebscat_phase_plan_create(ctypes.byref(d), stage_a.handle, G.ctypes.data_as(fp) if G is not None else None,
-                                           ii.ctypes.data_as(i32p), jj.ctypes.data_as(i32p),
-                                           pw.ctypes.data_as(fp), ctypes.byref(handle))
-        _lib.check(rc)
-        stage_a.handle = None                       # ownership moved into the phase plan
+        if plan.large:
+            rc = lib.tebscat_phase_plan_create_pairs_only(ctypes.byref(d), int(device_index), G.ctypes.data_as(fp),
+                                                          ii.ctypes.data_as(i32p), jj.ctypes.data_as(i32p),
+                                                          pw.ctypes.data_as(fp), ctypes.byref(handle))
+            _lib.check(rc)
+            from .large import LargeDevicePlan
+            self.large = LargeDevicePlan(plan, device_index)   # context + tile plans + the psi1 arena on the device
+        else:
+            rc = lib.tebscat_phase_plan_create(ctypes.byref(d), stage_a.handle, G.ctypes.data_as(fp) if G is not None else None,
+                                               ii.ctypes.data_as(i32p), jj.ctypes.data_as(i32p),
+                                               pw.ctypes.data_as(fp), ctypes.byref(handle))
+            _lib.check(rc)
+            stage_a.handle = None                       # ownership moved into the phase plan
         self.handle = handle
         self._lib = lib
+        self._ws = None
         # stage B as transforms where that is the cheaper form (long outputs); TEBSCAT_PHASE_FFT=0/1 overrides
         mode = os.environ.get('TEBSCAT_PHASE_FFT', 'auto')
         use_fft = plan.pair_plan is not None and (mode == '1' or (mode == 'auto' and plan.n_out >= PAIR_FFT_MIN_OUT)
@@ -250,6 +273,54 @@ class _DevicePhasePlan:
                 self.handle = None
         except Exception:
             pass
+
+    # ---- padded lengths above 2^13 ---------------------------------------------------------------------------------
+    LARGE_CHUNK_BYTES = 1 << 30                  # workspace of analytic signals per chunk (two arrays of this size)
+
+    def forward_large(self, x3, ch_i, ch_j, sub_ptr, n_sel, low_pass, out):
+        """Stage A on the large-support level -- pad + load, FFT, and per filter psi multiply -> iFFT -> crop
+        (kymatio_phase_scattering.py:220-231) as one launch each over a chunk of samples -- into workspaces of
+        (|z|, theta) / (re, im), then stage B (tebscat_phase_pairs) on them."""
+        lib, p, g = self._lib, self.plan, self.large.handle
+        B, C, N = x3.shape
+        dev = x3.device
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        F, n, Np = len(p.bank.psi1), p.geo.J_pad, 1 << p.geo.J_pad
+        chunk = int(max(1, min(B, self.LARGE_CHUNK_BYTES // (F * N * 8), ((1 << 31) - 1) // (F * N))))
+        if self._ws is None or self._ws[0] < chunk or self._ws[1].device != dev:
+            self._ws = (chunk, torch.empty(chunk * F * N * 2, dtype=torch.float32, device=dev),      # zc
+                        torch.empty(chunk * F * N * 2, dtype=torch.float32, device=dev),              # zp
+                        torch.empty(chunk * Np * 2, dtype=torch.float32, device=dev),                 # spectrum of the channel
+                        torch.empty(chunk * Np * 2, dtype=torch.float32, device=dev),                 # one filtered signal
+                        torch.empty(chunk * N, dtype=torch.float32, device=dev))                      # the channel, contiguous
+        _, zc, zp, U0, W, xc = self._ws
+        vp = ctypes.c_void_p
+        fa = self.large.arena.data_ptr()
+        width = p.n_out if low_pass else N
+
+        def stage_a(xb, ch, mode):
+            nb = xb.shape[0]
+            xcv = xc[:nb * N].view(nb, N)
+            xcv.copy_(xb[:, ch, :])
+            _lib.check(lib.tebscat_large_pad_load(g, vp(xcv.data_ptr()), nb, N, p.geo.pad_left, n, vp(U0.data_ptr()), st))
+            _lib.check(lib.tebscat_large_fft(g, vp(U0.data_ptr()), nb, n, 0, st))
+            for f, off in enumerate(p.psi1_off):
+                _lib.check(lib.tebscat_large_mulfold(g, vp(U0.data_ptr()), vp(fa + 4 * off), vp(W.data_ptr()), nb, n, 0, 0, 0, n, st))
+                _lib.check(lib.tebscat_large_fft(g, vp(W.data_ptr()), nb, n, 1, st))
+                _lib.check(lib.tebscat_large_storez(g, vp(W.data_ptr()), nb, n, p.geo.pad_left, N, F, f, mode,
+                                                    vp(zc.data_ptr()), vp(zp.data_ptr()), st))
+
+        for b0 in range(0, B, chunk):
+            xb = x3[b0:b0 + chunk]
+            nb = xb.shape[0]
+            if ch_i == ch_j:
+                stage_a(xb, ch_i, 3)
+            else:
+                stage_a(xb, ch_i, 2)
+                stage_a(xb, ch_j, 1)
+            _lib.check(lib.tebscat_phase_pairs(self.handle, vp(zp.data_ptr()), vp(zc.data_ptr()), nb, sub_ptr, n_sel,
+                                               1 if low_pass else 0, vp(out[b0:b0 + nb].data_ptr()), st))
+        return out
 
 
 class KymatioPhaseScattering1D(nn.Module):
@@ -323,6 +394,8 @@ class KymatioPhaseScattering1D(nn.Module):
         out = torch.empty((B, n_sel, width), dtype=torch.float32, device=x3.device)
         if n_sel == 0 or B == 0:
             return out
+        if self._plan.large:
+            return plan.forward_large(x3, int(ch_i), int(ch_j), sub_ptr, n_sel, low_pass, out)
         rc = _lib.load().tebscat_phase_forward(plan.handle, x3.data_ptr(), B, C, int(ch_i), int(ch_j), sub_ptr, n_sel,
                                                1 if low_pass else 0, out.data_ptr(),
                                                torch.cuda.current_stream(x3.device).cuda_stream)
@@ -344,7 +417,11 @@ class KymatioPhaseScattering1D(nn.Module):
         w = np.ascontiguousarray(self._window(self.N), np.float32)
         self.scattering.set_window(w)
         plan = self._dev_plan(index)
-        _lib.check(_lib.load().tebscat_phase_plan_set_window(plan.handle, w.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+        wp = w.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        if self._plan.large:
+            _lib.check(_lib.load().tebscat_large_set_window(plan.large.handle, wp, int(self.N)))
+        else:
+            _lib.check(_lib.load().tebscat_phase_plan_set_window(plan.handle, wp))
         self._windowed.add(index)
 
     # ---- forward (:394-473) -------------------------------------------------------------------
@@ -451,6 +528,9 @@ class KymatioPhaseScattering1D(nn.Module):
         index = x.device.index if x.device.index is not None else torch.cuda.current_device()
         plan = self._dev_plan(index)
         n_out = self._plan.n_out
+        if self._plan.large:                          # above 2^13 the two correlations are two passes of the same driver
+            return {'scattering': S, 'phase_corr': self._phase(x, ch_i, ch_i, sub_w), 'cross_phase_corr': self._phase(x, ch_i, ch_j, sub_c),
+                    'autoc_idx': self.autoc_idx}
         within = torch.empty((B, sub_w.size, n_out), dtype=torch.float32, device=x.device)
         cross = torch.empty((B, sub_c.size, n_out), dtype=torch.float32, device=x.device)
         i32p = ctypes.POINTER(ctypes.c_int32)
