@@ -171,7 +171,8 @@ int tebscat_phase_plan_set_window(tebscat_phase_plan* plan, const float* window_
  * _compute_cross_channel_phase_correlation :303-360).  pair_subset_host (nullable) selects
  * pairs like `same_pairs_only` / the dataset masks (create_hdf5_dataset.py:440-441).
  * apply_low_pass == 0 returns the full-rate real part, out [B, n_sel, N] (:356-360).
- * Calls on one phase plan are serialised (it owns an L2-sized workspace). */
+ * Calls on one phase plan are serialised (it owns an L2-sized workspace): the enqueue under a lock, and a call on another
+ * stream than the previous one waits (on the device) for that call to finish. */
 int tebscat_phase_forward(tebscat_phase_plan* plan, const float* x_dev, int64_t B, int n_channels,
                           int ch_i, int ch_j, const int32_t* pair_subset_host, int n_subset,
                           int apply_low_pass, float* out_dev, void* stream);

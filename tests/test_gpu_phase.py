@@ -384,3 +384,25 @@ def test_phase_at_a_padded_length_of_2_14(kernel, monkeypatch):
     one = m.forward_dataset(x, sel['use_phase_mask'], sel['use_cross_mask'])
     assert torch.equal(one['phase_corr'], rw['phase_corr'][:, sel['use_phase_mask']])
     assert torch.equal(one['cross_phase_corr'], rc['cross_phase_corr'][:, sel['use_cross_mask']])
+
+
+def test_calls_on_different_streams_do_not_race_on_the_workspaces():
+    """A phase plan owns its workspaces (analytic signals, subset tables).  Calls enqueued back to back on two
+    streams, with different inputs and no host synchronisation in between, must give what the same calls give
+    one after another (the library orders a call on a new stream behind the previous call's work)."""
+    m = module_of('S')
+    g = torch.Generator().manual_seed(77)
+    xs = [torch.randn(40, 2, 1000, generator=g).cuda() for _ in range(4)]
+    ref = [m(x, compute_phase=False, compute_cross_phase=True)['cross_phase_corr'].clone() for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for s in streams:
+        s.wait_stream(torch.cuda.current_stream())
+    outs = []
+    for rep in range(3):
+        for k, x in enumerate(xs):
+            with torch.cuda.stream(streams[k % 2]):
+                outs.append((k, m(x, compute_phase=False, compute_cross_phase=True)['cross_phase_corr']))
+    torch.cuda.synchronize()
+    for k, o in outs:
+        assert torch.equal(o, ref[k]), k

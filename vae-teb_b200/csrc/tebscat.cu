@@ -39,6 +39,27 @@ static int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                  \
     } while (0)
 
+// Every entry point runs on its plan's device and leaves the caller's current device as it found it (a
+// single-process multi-GPU caller must not be moved to another device behind its back).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;              // already there: nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(dev)                                                                                     \
+    DeviceGuard device_guard_(dev);                                                                        \
+    if (device_guard_.err != cudaSuccess)                                                                  \
+        return fail(TEBSCAT_ECUDA, "cudaSetDevice(%d) failed: %s", (int)(dev), cudaGetErrorString(device_guard_.err))
+
 // ---------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------
@@ -401,7 +422,7 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     int n_dev = 0;
     CU(cudaGetDeviceCount(&n_dev));
     if (device < 0 || device >= n_dev) return fail(TEBSCAT_EINVAL, "device %d not in [0,%d)", device, n_dev);
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
 
@@ -601,7 +622,7 @@ extern "C" int tebscat_plan_load(const char* path, int device, tebscat_plan** ou
 
 extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceGuard device_guard_(p->device);
     {
         HostPipe& hp = p->pipe;
         if (hp.s_in) cudaStreamDestroy(hp.s_in);
@@ -628,9 +649,7 @@ extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
 // window_host: N floats, or NULL to remove it.  Not re-entrant with forward calls on the same plan.
 extern "C" int tebscat_plan_set_window(tebscat_plan* p, const float* window_host) {
     if (!p) return fail(TEBSCAT_EINVAL, "null plan");
-    int prev = 0;
-    CU(cudaGetDevice(&prev));
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     int rc = TEBSCAT_OK;
     do {
         if (!window_host) { p->kp.win = nullptr; break; }
@@ -644,7 +663,6 @@ extern "C" int tebscat_plan_set_window(tebscat_plan* p, const float* window_host
         }
         p->kp.win = p->d_win;
     } while (0);
-    cudaSetDevice(prev);
     return rc;
 }
 
@@ -661,12 +679,8 @@ extern "C" int tebscat_scat1d_forward(const tebscat_plan* p, const float* x_dev,
                                       void* stream) {
     g_launches = 0;
     if (!p || B < 0 || (B > 0 && (!x_dev || !S_dev))) return fail(TEBSCAT_EINVAL, "null argument");
-    int cur = -1;
-    CU(cudaGetDevice(&cur));
-    if (cur != p->device) CU(cudaSetDevice(p->device));
-    int rc = launch_scat1d(p, x_dev, B, S_dev, (cudaStream_t)stream);
-    if (cur != p->device && cur >= 0) cudaSetDevice(cur);
-    return rc;
+    ON_DEVICE(p->device);
+    return launch_scat1d(p, x_dev, B, S_dev, (cudaStream_t)stream);
 }
 
 extern "C" int tebscat_scat1d_forward_ex(const tebscat_plan* p, const float* x_dev, int64_t B, float* out_dev,
@@ -678,9 +692,7 @@ extern "C" int tebscat_scat1d_forward_ex(const tebscat_plan* p, const float* x_d
     if (ep->trim < 0 || 2 * ep->trim >= p->desc.n_out)
         return fail(TEBSCAT_EINVAL, "epilogue: trim %d leaves nothing of %d samples", ep->trim, p->desc.n_out);
     if (B == 0) return TEBSCAT_OK;
-    int cur = -1;
-    CU(cudaGetDevice(&cur));
-    if (cur != p->device) CU(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     KParams kp = p->kp;
     kp.ep_mean = ep->mean_dev;
     kp.ep_std = ep->std_dev;
@@ -691,7 +703,6 @@ extern "C" int tebscat_scat1d_forward_ex(const tebscat_plan* p, const float* x_d
     const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
     scat1d_kernel<false><<<grid, p->desc.n_threads, p->smem_bytes, (cudaStream_t)stream>>>(kp, x_dev, out_dev, (long long)B);
     cudaError_t e = cudaGetLastError();
-    if (cur != p->device && cur >= 0) cudaSetDevice(cur);
     if (e != cudaSuccess) return fail(TEBSCAT_ECUDA, "launch failed: %s", cudaGetErrorString(e));
     ++g_launches;
     return TEBSCAT_OK;
@@ -701,7 +712,7 @@ extern "C" int tebscat_scat1d_profile_steps(const tebscat_plan* p, const float* 
                                             long long* step_clocks_host, void* stream) {
     g_launches = 0;
     if (!p || !x_dev || !S_dev || !step_clocks_host || B < 1) return fail(TEBSCAT_EINVAL, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     long long* d_prof = nullptr;
 #ifdef TEBSCAT_PROF_PHASES
     const size_t n = 4 * (size_t)p->desc.n_steps + 1;     // + (decode, exec, barrier) stamps of every step
@@ -758,10 +769,7 @@ static int forward_host_impl(tebscat_plan* p, const float* x_host, int64_t B, fl
     if (!p || B < 0 || (B > 0 && (!x_host || !S_host))) return fail(TEBSCAT_EINVAL, "null argument");
     if (B == 0) return TEBSCAT_OK;
     std::lock_guard<std::mutex> lock(p->pipe_mu);
-    int prev = 0;
-    CU(cudaGetDevice(&prev));
-    CU(cudaSetDevice(p->device));
-    struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+    ON_DEVICE(p->device);
     if (int rc = host_pipe_prepare(p)) return rc;
     HostPipe& hp = p->pipe;
     const size_t in_f = (size_t)p->desc.N, out_f = (size_t)p->desc.n_paths * p->desc.n_out;
@@ -1017,6 +1025,11 @@ struct tebscat_phase_plan {
     int64_t ws2_samples = 0;
     tebscat_plan* pair_plan = nullptr;   // optional: stage B as FFTs on the interpreter (owned)
     std::mutex mu;
+    // The workspaces (analytic signals, subset tables) belong to the plan: a call on another stream than the previous
+    // one waits for that call's work first (calls on one stream are ordered by the stream itself).
+    cudaEvent_t last_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
     // optional stage timing (tebscat_phase_plan_profile): events around stage A and stage B of every chunk
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;    // triples (before A, between, after B)
@@ -1059,7 +1072,7 @@ static int phase_plan_create_impl(const tebscat_phase_desc* d, tebscat_plan* sta
     for (int k = 0; k < d->n_pairs; ++k)
         if (i_idx[k] < 0 || i_idx[k] >= d->n_filters || j_idx[k] < 0 || j_idx[k] >= d->n_filters)
             return fail(TEBSCAT_EINVAL, "pair %d references a filter outside [0,%d)", k, d->n_filters);
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     CU(cudaFuncSetAttribute(phase_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
     std::unique_ptr<tebscat_phase_plan, void (*)(tebscat_phase_plan*)> guard(new tebscat_phase_plan(), [](tebscat_phase_plan* q) {
         q->stage_a = nullptr;                    // on failure the caller keeps the stage-A plan
@@ -1113,7 +1126,7 @@ static int phase_plan_create_impl(const tebscat_phase_desc* d, tebscat_plan* sta
 
 extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceGuard device_guard_(p->device);
     cudaFree(p->d_G);
     cudaFree(p->d_Bs);
     cudaFree(p->d_i);
@@ -1125,6 +1138,7 @@ extern "C" void tebscat_phase_plan_destroy(tebscat_phase_plan* p) {
     cudaFree(p->d_zp);
     cudaFree(p->d_zc2);
     for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
+    if (p->last_done) cudaEventDestroy(p->last_done);
     tebscat_plan_destroy(p->stage_a);
     tebscat_plan_destroy(p->pair_plan);
     delete p;
@@ -1197,6 +1211,23 @@ static int launch_pairs_fft(const tebscat_phase_plan* p, const float2* zp, const
     return TEBSCAT_OK;
 }
 
+// order a call on `st` behind the plan's previous call if that ran on another stream; `phase_call_done` marks the end
+static int phase_call_begin(tebscat_phase_plan* p, cudaStream_t st) {
+    if (!p->last_done) CU(cudaEventCreateWithFlags(&p->last_done, cudaEventDisableTiming));
+    if (p->used && p->last_stream != st) CU(cudaStreamWaitEvent(st, p->last_done, 0));
+    return TEBSCAT_OK;
+}
+struct PhaseCallScope {                       // declared after the plan's lock: records the end of the call on every exit path
+    tebscat_phase_plan* p;
+    cudaStream_t st;
+    ~PhaseCallScope() {
+        if (p->last_done && cudaEventRecord(p->last_done, st) == cudaSuccess) {
+            p->last_stream = st;
+            p->used = true;
+        }
+    }
+};
+
 static int launch_stage_a(const tebscat_plan* a, const float* x, long long x_stride, int64_t jobs,
                           float2* zc, float2* zp, int z_mode, cudaStream_t st) {
     KParams kp = a->kp;
@@ -1228,7 +1259,9 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
     if (!p->stage_a) return fail(TEBSCAT_EUNSUPPORTED, "this phase plan has no stage A: use tebscat_phase_pairs on analytic signals");
     std::lock_guard<std::mutex> lock(p->mu);
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
+    if (int rc = phase_call_begin(p, st)) return rc;
+    PhaseCallScope call_scope{p, st};
     const tebscat_phase_desc& d = p->desc;
     const int n_sel = pair_subset_host ? n_subset : d.n_pairs;
     const size_t per_sample = (size_t)d.n_filters * d.N;
@@ -1367,7 +1400,9 @@ extern "C" int tebscat_phase_pairs(tebscat_phase_plan* p, const float* zp_dev, c
         return fail(TEBSCAT_EINVAL, "workspace of %lld samples: chunk the batch (32-bit sample offsets)", (long long)nb);
     std::lock_guard<std::mutex> lock(p->mu);
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
+    if (int rc = phase_call_begin(p, st)) return rc;
+    PhaseCallScope call_scope{p, st};
     const int n_sel = pair_subset_host ? n_subset : p->desc.n_pairs;
     if (pair_subset_host) CU(cudaMemcpyAsync(p->d_subset, pair_subset_host, n_sel * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     const int32_t* sub = pair_subset_host ? p->d_subset : nullptr;
@@ -1418,7 +1453,9 @@ extern "C" int tebscat_phase_forward_dual(tebscat_phase_plan* p, const float* x_
     if (B == 0) return TEBSCAT_OK;
     std::lock_guard<std::mutex> lock(p->mu);
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
+    if (int rc = phase_call_begin(p, st)) return rc;
+    PhaseCallScope call_scope{p, st};
     const tebscat_phase_desc& d = p->desc;
     const size_t per_sample = (size_t)d.n_filters * d.N;
     const int64_t chunk = B < kPhaseChunk ? B : kPhaseChunk;
@@ -1486,7 +1523,7 @@ extern "C" int tebscat_large_create(int device, tebscat_large** out) {
     int n_dev = 0;
     CU(cudaGetDeviceCount(&n_dev));
     if (device < 0 || device >= n_dev) return fail(TEBSCAT_EINVAL, "device %d not in [0,%d)", device, n_dev);
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     std::unique_ptr<tebscat_large, void (*)(tebscat_large*)> guard(new tebscat_large(), tebscat_large_destroy);
@@ -1507,7 +1544,7 @@ extern "C" int tebscat_large_create(int device, tebscat_large** out) {
 
 extern "C" void tebscat_large_destroy(tebscat_large* g) {
     if (!g) return;
-    cudaSetDevice(g->device);
+    DeviceGuard device_guard_(g->device);
     for (int n = 0; n <= kLog2TwMax; ++n)
         for (int d = 0; d < 3; ++d)
             for (int z = 0; z < 2; ++z) tebscat_plan_destroy(g->tile[n][d][z]);
@@ -1519,7 +1556,7 @@ extern "C" void tebscat_large_destroy(tebscat_large* g) {
 // analysis window of pad_load / pad_adjoint (see tebscat_plan_set_window): n floats, or NULL to remove it
 extern "C" int tebscat_large_set_window(tebscat_large* g, const float* window_host, int n) {
     if (!g || (window_host && n < 1)) return fail(TEBSCAT_EINVAL, "bad window");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     cudaFree(g->d_win);
     g->d_win = nullptr;
     g->win_n = 0;
@@ -1642,7 +1679,7 @@ static int launch_tile_jobs(const tebscat_large* g, float2* buf, long long total
  * Forward: natural -> bit-reversed order; inverse: bit-reversed -> natural, unnormalised. */
 extern "C" int tebscat_large_fft(tebscat_large* g, float* buf_dev, int64_t n_transforms, int log2_len, int inverse, void* stream) {
     if (!g || !buf_dev || n_transforms < 1 || log2_len < 1 || log2_len > kLargeMaxLog2) return fail(TEBSCAT_EINVAL, "bad transform request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     cudaStream_t st = (cudaStream_t)stream;
     float2* buf = reinterpret_cast<float2*>(buf_dev);
     const long long total = (long long)n_transforms << log2_len;
@@ -1724,7 +1761,7 @@ __global__ void g_radix_pair_kernel(float2* __restrict__ buf, long long n_transf
  * samples: the result is the bit-reversed spectrum of |ifft(.)| (unnormalised inverse). */
 extern "C" int tebscat_large_pair(tebscat_large* g, float* buf_dev, int64_t n_transforms, int log2_len, void* stream) {
     if (!g || !buf_dev || n_transforms < 1 || log2_len < 1 || log2_len > kLargeMaxLog2) return fail(TEBSCAT_EINVAL, "bad transform request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     cudaStream_t st = (cudaStream_t)stream;
     float2* buf = reinterpret_cast<float2*>(buf_dev);
     const long long total = (long long)n_transforms << log2_len;
@@ -1746,7 +1783,7 @@ extern "C" int tebscat_large_pad_load(tebscat_large* g, const float* x_dev, int6
                                       float* u_dev, void* stream) {
     if (!g || !x_dev || !u_dev || B < 1 || N < 2 || pad_left < 0 || pad_left >= N || ((1LL << log2_Np) - N - pad_left) >= N)
         return fail(TEBSCAT_EINVAL, "Indefinite padding size (larger than tensor).");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     if (g->d_win && g->win_n != N) return fail(TEBSCAT_EINVAL, "window of %d samples on signals of %d", g->win_n, N);
     g_pad_load_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(x_dev, reinterpret_cast<float2*>(u_dev), B, N, pad_left, log2_Np,
                                                                        g->d_win);
@@ -1799,7 +1836,7 @@ extern "C" int tebscat_large_mulfold(tebscat_large* g, const float* src_dev, con
     if (!g || !src_dev || !filt_dev || !dst_dev || B < 1 || log_src < 1 || log_src > kLargeMaxLog2 || logk < 0 || logk > log_src ||
         (logk >= 2 && (chunk_mask == 0 || log_chunk < 2 || log_chunk > logk || (logk - log_chunk) > 5)))
         return fail(TEBSCAT_EINVAL, "bad filter multiply request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     g_mulfold_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(src_dev), filt_dev,
                                                                       reinterpret_cast<float2*>(dst_dev), B, log_src, logk, chunk_mask,
                                                                       log_chunk, ldexpf(1.0f, -scale_exp));
@@ -1818,7 +1855,7 @@ __global__ void g_modulus_kernel(float2* __restrict__ buf, long long total) {
 /* modulus (kymatio/backend/torch_backend.py:137-141), in place, imaginary part zeroed */
 extern "C" int tebscat_large_modulus(tebscat_large* g, float* buf_dev, int64_t n_complex, void* stream) {
     if (!g || !buf_dev || n_complex < 1) return fail(TEBSCAT_EINVAL, "null argument");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     g_modulus_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(buf_dev), n_complex);
     CU(cudaGetLastError());
     ++g_launches;
@@ -1841,7 +1878,7 @@ extern "C" int tebscat_large_store(tebscat_large* g, const float* buf_dev, int64
                                    int channel, float* out_dev, void* stream) {
     if (!g || !buf_dev || !out_dev || B < 1 || i0 < 0 || n_out < 1 || i0 + n_out > (1 << log_len) || channel < 0 || channel >= n_paths)
         return fail(TEBSCAT_EINVAL, "bad store request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     g_store_kernel<<<g->n_sms * 4, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(buf_dev), out_dev, B, log_len, i0,
                                                                     n_out, n_paths, channel);
     CU(cudaGetLastError());
@@ -1969,7 +2006,7 @@ extern "C" int tebscat_large_leaf(tebscat_large* g, const float* src_dev, const 
     const int lf = log_src - logk;
     if (!g || !src_dev || !filt_dev || !out_dev || B < 1 || !leaf_args_ok(log_src, logk, chunk_mask, log_chunk, lf, i0, n_out, n_paths, channel))
         return fail(TEBSCAT_EINVAL, "bad leaf request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     const int grid = (int)(B < (int64_t)g->n_sms * 8 ? B : (int64_t)g->n_sms * 8);
     g_leaf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(src_dev), filt_dev, out_dev, B, log_src, logk,
                                                           chunk_mask, log_chunk, ldexpf(1.0f, -scale_exp), lf, i0, n_out, n_paths, channel);
@@ -1984,7 +2021,7 @@ extern "C" int tebscat_large_leaf_adjoint(tebscat_large* g, const float* gout_de
     const int lf = log_src - logk;
     if (!g || !gout_dev || !filt_dev || !gsrc_dev || B < 1 || !leaf_args_ok(log_src, logk, chunk_mask, log_chunk, lf, i0, n_out, n_paths, channel))
         return fail(TEBSCAT_EINVAL, "bad leaf request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     const int grid = (int)(B < (int64_t)g->n_sms * 8 ? B : (int64_t)g->n_sms * 8);
     g_leaf_adjoint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout_dev, filt_dev, reinterpret_cast<float2*>(gsrc_dev), B, log_src, logk,
                                                                   chunk_mask, log_chunk, ldexpf(1.0f, -scale_exp), lf, i0, n_out, n_paths,
@@ -2009,7 +2046,7 @@ __global__ void g_modulus_to_kernel(const float2* __restrict__ src, float2* __re
 
 extern "C" int tebscat_large_modulus_to(tebscat_large* g, const float* src_dev, float* dst_dev, int64_t n_complex, void* stream) {
     if (!g || !src_dev || !dst_dev || n_complex < 1) return fail(TEBSCAT_EINVAL, "null argument");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     g_modulus_to_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(src_dev),
                                                                          reinterpret_cast<float2*>(dst_dev), n_complex);
     CU(cudaGetLastError());
@@ -2030,7 +2067,7 @@ __global__ void g_modulus_backward_kernel(const float2* __restrict__ u, float2* 
 
 extern "C" int tebscat_large_modulus_backward(tebscat_large* g, const float* u_dev, float* grad_dev, int64_t n_complex, void* stream) {
     if (!g || !u_dev || !grad_dev || n_complex < 1) return fail(TEBSCAT_EINVAL, "null argument");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     g_modulus_backward_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(u_dev),
                                                                                reinterpret_cast<float2*>(grad_dev), n_complex);
     CU(cudaGetLastError());
@@ -2070,7 +2107,7 @@ extern "C" int tebscat_large_unfold(tebscat_large* g, const float* gdst_dev, con
     if (!g || !gdst_dev || !filt_dev || !gsrc_dev || B < 1 || log_src < 1 || log_src > kLargeMaxLog2 || logk < 0 || logk > log_src ||
         (logk >= 2 && (chunk_mask == 0 || log_chunk < 2 || log_chunk > logk || (logk - log_chunk) > 5)))
         return fail(TEBSCAT_EINVAL, "bad filter multiply request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     g_unfold_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(gdst_dev), filt_dev,
                                                                      reinterpret_cast<float2*>(gsrc_dev), B, log_src, logk, chunk_mask,
                                                                      log_chunk, ldexpf(1.0f, -scale_exp), accumulate);
@@ -2095,7 +2132,7 @@ extern "C" int tebscat_large_unstore(tebscat_large* g, const float* gout_dev, in
                                      int channel, float* buf_dev, void* stream) {
     if (!g || !buf_dev || !gout_dev || B < 1 || i0 < 0 || n_out < 1 || i0 + n_out > (1 << log_len) || channel < 0 || channel >= n_paths)
         return fail(TEBSCAT_EINVAL, "bad store request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     g_unstore_kernel<<<g->n_sms * 4, 256, 0, (cudaStream_t)stream>>>(gout_dev, reinterpret_cast<float2*>(buf_dev), B, log_len, i0,
                                                                       n_out, n_paths, channel);
     CU(cudaGetLastError());
@@ -2123,7 +2160,7 @@ extern "C" int tebscat_large_storez(tebscat_large* g, const float* buf_dev, int6
     if (!g || !buf_dev || B < 1 || log_len < 1 || log_len > kLargeMaxLog2 || i0 < 0 || N < 1 || i0 + N > (1 << log_len) ||
         F < 1 || f < 0 || f >= F || !(mode & (Z_CART | Z_POLAR)) || ((mode & Z_CART) && !zc_dev) || ((mode & Z_POLAR) && !zp_dev))
         return fail(TEBSCAT_EINVAL, "bad analytic-signal store request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     g_storez_kernel<<<g->n_sms * 4, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(buf_dev), B, log_len, i0, N, F, f, mode,
                                                                      reinterpret_cast<float2*>(zc_dev), reinterpret_cast<float2*>(zp_dev));
     CU(cudaGetLastError());
@@ -2159,7 +2196,7 @@ extern "C" int tebscat_large_unstore_row(tebscat_large* g, const float* grow_dev
     if (!g || !buf_dev || !grow_dev || B < 1 || i0 < 0 || len < 1 || log_len < 0 || log_len > kLargeMaxLog2 ||
         i0 + len > (1 << log_len) || offset < 0 || offset + len > row_stride)
         return fail(TEBSCAT_EINVAL, "bad un-averaged store request");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     g_unstore_row_kernel<<<g->n_sms * 4, 256, 0, (cudaStream_t)stream>>>(grow_dev, reinterpret_cast<float2*>(buf_dev), B, row_stride,
                                                                           offset, log_len, i0, len, accumulate);
     CU(cudaGetLastError());
@@ -2188,7 +2225,7 @@ extern "C" int tebscat_large_pad_adjoint(tebscat_large* g, const float* gu_dev, 
                                          float* gx_dev, void* stream) {
     if (!g || !gx_dev || !gu_dev || B < 1 || N < 2 || pad_left < 0 || pad_left >= N || ((1LL << log2_Np) - N - pad_left) >= N)
         return fail(TEBSCAT_EINVAL, "Indefinite padding size (larger than tensor).");
-    CU(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     if (g->d_win && g->win_n != N) return fail(TEBSCAT_EINVAL, "window of %d samples on signals of %d", g->win_n, N);
     g_pad_adjoint_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(gu_dev), gx_dev, B, N, pad_left,
                                                                           log2_Np, g->d_win);
