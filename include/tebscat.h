@@ -227,6 +227,10 @@ int tebscat_large_set_tile_plan(tebscat_large* ctx, int log2_len, int kind, int 
 /* pad (torch_backend.py:50-78) + real -> complex: x_dev [B, N] -> u_dev [B, 2^log2_Np] complex64 */
 int tebscat_large_pad_load(tebscat_large* ctx, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,
                            float* u_dev, void* stream);
+/* the same with the phase module's padding rules (kymatio_phase_scattering.py:162-173): border_mode 0 reflect, 1 constant
+ * (zeros), 2 circular -- stage A of the phase path at padded lengths above 2^13 */
+int tebscat_large_pad_load_mode(tebscat_large* ctx, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,
+                                int border_mode, float* u_dev, void* stream);
 /* fft / ifft (torch_backend.py:106-128, unnormalised), in place, forward natural -> bit-reversed, inverse back */
 int tebscat_large_fft(tebscat_large* ctx, float* buf_dev, int64_t n_transforms, int log2_len, int inverse, void* stream);
 /* ifft -> modulus -> fft (core/scattering1d.py:312-318) in place on bit-reversed spectra, unnormalised */

@@ -406,3 +406,20 @@ def test_calls_on_different_streams_do_not_race_on_the_workspaces():
     torch.cuda.synchronize()
     for k, o in outs:
         assert torch.equal(o, ref[k]), k
+
+
+@pytest.mark.parametrize('border', ['constant', 'circular'])
+def test_border_modes_at_a_padded_length_of_2_14(border):
+    """Regression (found by tools/random_parity_sweep.py): above 2^13 stage A runs on the large-support level, whose
+    pad + load kernel only knew the scattering transform's reflect padding; the phase module's 'constant' and
+    'circular' modes (kymatio_phase_scattering.py:162-173) apply to stage A too."""
+    from tebscat import KymatioPhaseScattering1D
+    J, Q, T, N = 6, 4, 16, 8361
+    m = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=torch.device('cuda'), border_mode=border)
+    assert m._plan.large
+    x = torch.randn(2, 2, N, generator=torch.Generator().manual_seed(5))
+    o = PhaseOracle(J, Q, T, N, m.scattering(x[:, 0].cuda().contiguous())[0].shape[-1], border_mode=border)
+    cross = m(x.cuda(), compute_phase=False, compute_cross_phase=True)['cross_phase_corr'].cpu().numpy()
+    check(cross, o, x.numpy(), 'cross', 'Np=2^14, border ' + border, randn_rows=[0, 1])
+    within = m(x.cuda(), compute_phase=True, phase_channels=[1])['phase_corr'].cpu().numpy()
+    check(within, o, x.numpy()[:, 1], 'within', 'Np=2^14, border ' + border, randn_rows=[0, 1])

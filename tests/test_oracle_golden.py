@@ -171,3 +171,29 @@ def test_unaveraged_gradient_oracle_vs_reference(golden_dir, name):
     assert row.shape == d['row'].shape and e_row[1] < 2e-6 and e_row[0] < 2e-5, e_row
     err = rel_l2(gx, d['gx'], axis=-1)
     assert err[1] < 1e-5 and err[0] < 5e-5, err
+
+
+def test_branch_alignment_covers_an_interior_sample_on_the_negative_real_axis():
+    """The input the random sweep met (seed 32, tools/random_parity_sweep.py): analytic sample (row 0, filter 3,
+    t = 2169) = -0.119 + 2.3e-8j, i.e. on the negative real axis to 2e-7 -- three ulps of |z| in float32.  Whichever
+    sign an fp32 transform gives Im z there is legitimate; without decimation the other branch costs ~1e-3 on the
+    paths of that filter.  align_branches picks the branch of the output under test, and only there."""
+    import torch
+    J, Q, T, N = 5, 8, 8, 3080
+    x = torch.randn(3, 2, N, generator=torch.Generator().manual_seed(319)).numpy()[:1]
+    o = PhaseOracle(J, Q, T, N, N)
+    zi, zj = o.analytic(x[:, 0]), o.analytic(x[:, 1])
+    z = zi[0, 3, 2169]
+    assert z.real < 0 and abs(z.imag) < 2e-6 * abs(z.real)
+    plain = o(x)
+    zi[0, 3, 2169] = np.conj(z)                                            # the other branch at that one sample
+    flipped = np.real(o.pair_stage(zi, zj))
+    cost = np.linalg.norm(flipped - plain) / np.linalg.norm(plain)
+    assert cost > 1e-4
+    assert np.linalg.norm(flipped - o.align_branches(x, flipped, interior_rel_im=0)) / np.linalg.norm(plain) > 1e-4
+    assert np.linalg.norm(flipped - o.align_branches(x, flipped)) / np.linalg.norm(plain) < 1e-12
+    assert np.array_equal(o.align_branches(x, plain), plain)               # nothing to align: the plain oracle
+    # an error anywhere else is NOT absorbed: perturb one unrelated sample of the output
+    wrong = plain.copy()
+    wrong[0, 100, 500] += 1e-2 * np.abs(plain[0, 100]).max()
+    assert np.array_equal(o.align_branches(x, wrong), plain)

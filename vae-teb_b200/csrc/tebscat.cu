@@ -1582,15 +1582,23 @@ extern "C" int tebscat_large_set_tile_plan(tebscat_large* g, int log2_len, int k
 
 // reflect padding (torch_backend.py:50-78) + real -> complex, natural order
 __global__ void g_pad_load_kernel(const float* __restrict__ x, float2* __restrict__ u, long long B, int N, int pad_left, int log2_Np,
-                                  const float* __restrict__ win) {
+                                  const float* __restrict__ win, int border) {
     const long long total = B << log2_Np;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long b = e >> log2_Np;
         int r = (int)(e - (b << log2_Np)) - pad_left;
-        if (r < 0) r = -r;
-        if (r >= N) r = 2 * (N - 1) - r;
-        float v = __ldg(x + b * N + r);
-        if (win) v *= __ldg(win + r);
+        bool inside = true;
+        if (border == BORDER_REFLECT) {                      // torch_backend.py:50-78; _pad_signal 'reflect' (pad < N)
+            if (r < 0) r = -r;
+            if (r >= N) r = 2 * (N - 1) - r;
+        } else if (border == BORDER_CIRCULAR) {              // kymatio_phase_scattering.py:162-173 (pad <= N)
+            if (r < 0) r += N;
+            if (r >= N) r -= N;
+        } else {                                             // 'constant': zeros
+            inside = r >= 0 && r < N;
+        }
+        float v = inside ? __ldg(x + b * N + r) : 0.f;
+        if (win && inside) v *= __ldg(win + r);
         u[e] = make_float2(v, 0.f);
     }
 }
@@ -1779,17 +1787,25 @@ extern "C" int tebscat_large_pair(tebscat_large* g, float* buf_dev, int64_t n_tr
     return launch_tile_jobs(g, buf, total, kLog2TwMax, 0, st);
 }
 
-extern "C" int tebscat_large_pad_load(tebscat_large* g, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,
-                                      float* u_dev, void* stream) {
-    if (!g || !x_dev || !u_dev || B < 1 || N < 2 || pad_left < 0 || pad_left >= N || ((1LL << log2_Np) - N - pad_left) >= N)
+extern "C" int tebscat_large_pad_load_mode(tebscat_large* g, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,
+                                           int border_mode, float* u_dev, void* stream) {
+    if (!g || !x_dev || !u_dev || B < 1 || N < 2 || pad_left < 0 || pad_left >= N || ((1LL << log2_Np) - N - pad_left) >= N ||
+        log2_Np < 1 || log2_Np > kLargeMaxLog2)
         return fail(TEBSCAT_EINVAL, "Indefinite padding size (larger than tensor).");
+    if (border_mode != BORDER_REFLECT && border_mode != BORDER_CONSTANT && border_mode != BORDER_CIRCULAR)
+        return fail(TEBSCAT_EINVAL, "unknown border mode %d", border_mode);
     ON_DEVICE(g->device);
     if (g->d_win && g->win_n != N) return fail(TEBSCAT_EINVAL, "window of %d samples on signals of %d", g->win_n, N);
     g_pad_load_kernel<<<g->n_sms * 8, 256, 0, (cudaStream_t)stream>>>(x_dev, reinterpret_cast<float2*>(u_dev), B, N, pad_left, log2_Np,
-                                                                       g->d_win);
+                                                                       g->d_win, border_mode);
     CU(cudaGetLastError());
     ++g_launches;
     return TEBSCAT_OK;
+}
+
+extern "C" int tebscat_large_pad_load(tebscat_large* g, const float* x_dev, int64_t B, int N, int pad_left, int log2_Np,
+                                      float* u_dev, void* stream) {
+    return tebscat_large_pad_load_mode(g, x_dev, B, N, pad_left, log2_Np, BORDER_REFLECT, u_dev, stream);
 }
 
 // dst[b, m] = 2^-sexp * sum_{t<k} src[b, m k + t] * f[m k + t]  (bit-reversed order; 4-bin chunks of the k-block that

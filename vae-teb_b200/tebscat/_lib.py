@@ -114,6 +114,8 @@ def load():
     lib.tebscat_large_set_tile_plan.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.tebscat_large_pad_load.restype = ctypes.c_int
     lib.tebscat_large_pad_load.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.tebscat_large_pad_load_mode.restype = ctypes.c_int
+    lib.tebscat_large_pad_load_mode.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.tebscat_large_fft.restype = ctypes.c_int
     lib.tebscat_large_fft.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, vp]
     lib.tebscat_large_pair.restype = ctypes.c_int

@@ -302,7 +302,8 @@ class _DevicePhasePlan:
             nb = xb.shape[0]
             xcv = xc[:nb * N].view(nb, N)
             xcv.copy_(xb[:, ch, :])
-            _lib.check(lib.tebscat_large_pad_load(g, vp(xcv.data_ptr()), nb, N, p.geo.pad_left, n, vp(U0.data_ptr()), st))
+            _lib.check(lib.tebscat_large_pad_load_mode(g, vp(xcv.data_ptr()), nb, N, p.geo.pad_left, n, p.border,
+                                                       vp(U0.data_ptr()), st))
             _lib.check(lib.tebscat_large_fft(g, vp(U0.data_ptr()), nb, n, 0, st))
             for f, off in enumerate(p.psi1_off):
                 _lib.check(lib.tebscat_large_mulfold(g, vp(U0.data_ptr()), vp(fa + 4 * off), vp(W.data_ptr()), nb, n, 0, 0, 0, n, st))
