@@ -29,7 +29,7 @@ class P:
 dp._lib = P()
 g = torch.empty_like(x)
 w = torch.randn(B, dp.plan.n_paths, dp.plan.n_out, device='cuda')
-dp.backward(x.detach(), w, g); torch.cuda.synchronize()
+dp._run_backward(x.detach().contiguous(), w, g); torch.cuda.synchronize()
 tot = sum(acc.values())
 for k, v in sorted(acc.items(), key=lambda kv: -kv[1])[:30]:
     print('%-40s %4d calls %8.2f ms  %5.1f%%' % (k, cnt[k], v, 100 * v / tot))

@@ -46,7 +46,7 @@ constexpr int kTcBTile = kTcCols * 128;                         // bytes of one 
 constexpr int kTcStageBytes = 2 * kTcBTile;                      // head + tail
 constexpr int kTcInBytes = 2 * kTcRows * 128;                    // one group's input slab: 128 lines of (|z|, theta) + 128 of (re, im)
 constexpr int kTcOffBars = kTcStages * kTcStageBytes + kTcGroups * kTcInBytes;
-constexpr size_t kTcSmem = 1024 + (size_t)kTcOffBars + 256 + 2 * kTcRows * sizeof(int32_t);
+constexpr size_t kTcSmem = 1024 + (size_t)kTcOffBars + 256 + 4 * kTcRows * sizeof(int32_t) + 64;
 // TMEM columns: the two head-product accumulators (Ah Bh, drained every kTcDrain slabs), ONE accumulator of the
 // correction products (Al Bh + Ah Bl: 2^-11 of the head products, so its truncation error stays below 1e-7 of the
 // result even over the whole contraction -- it is read once, at the end), and the A' stages (head at kTcA0 + 64 s, tail + 32)
@@ -181,19 +181,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // Input lines.  A row (pair) reads the (|z|, theta) line of its 'i' filter and the (re, im) line of its 'j' filter;
+    // the 128 rows of a tile are consecutive pairs of one or two samples, so they share a handful of 'i' lines and at
+    // most F 'j' lines per sample.  Each DISTINCT line is copied once per slab (s_line: its first sample in the
+    // workspace, float2 units, or -1), and a row remembers the slot of its two lines (s_slot):
+    //   side 0 ('i'): run-length slots -- the pair list is sorted by i, so equal keys are adjacent;
+    //   side 1 ('j'): slot = (sample - first sample of the tile) * F + j while that fits 128 slots, else one per row.
+    // At the headline configuration (741 pairs, F = 38) that is 4-10 + 38-76 lines instead of 256.
+    int32_t* s_slot = s_off + 2 * kTcRows;                                      // [2][128]
+    int32_t* s_cnt = s_off + 4 * kTcRows;                                       // [0..1] lines per side, [2..5] scratch
+    const long long tile_row0 = (long long)blockIdx.x * kTcRows;
+    const long long tile_last = (tile_row0 + kTcRows - 1 < p.rows ? tile_row0 + kTcRows - 1 : p.rows - 1);
+    const long long b_first = tile_row0 / p.n_sel;
+    const int nb_tile = (int)(tile_last / p.n_sel - b_first) + 1;
+    const bool direct_j = nb_tile * p.F <= kTcRows;
+    int32_t key_i = 0, key_j = 0, slot_j = 0;
     if (tid < kTcRows) {
-        const long long row = (long long)blockIdx.x * kTcRows + tid;
-        // rows beyond the batch (last CTA) read the first row: their products are computed and never stored
-        int32_t zp_off = 0, zc_off = 0;
-        if (row < p.rows) {
-            const long long b = row / p.n_sel;
-            const int sidx = (int)(row - b * p.n_sel);
-            const int pair = p.subset ? p.subset[sidx] : sidx;
-            zp_off = (int32_t)((b * p.F + p.i_idx[pair]) * (long long)p.N);       // < 2^31: the workspace chunk is bounded
-            zc_off = (int32_t)((b * p.F + p.j_idx[pair]) * (long long)p.N);
+        // rows beyond the batch (last CTA) read the lines of the tile's first row: their products are computed and never stored
+        const long long row = tile_row0 + tid < p.rows ? tile_row0 + tid : tile_row0;
+        const long long b = row / p.n_sel;
+        const int sidx = (int)(row - b * p.n_sel);
+        const int pair = p.subset ? p.subset[sidx] : sidx;
+        key_i = (int32_t)(b * p.F + p.i_idx[pair]);                             // (key * N) < 2^31: the workspace chunk is bounded
+        key_j = (int32_t)(b * p.F + p.j_idx[pair]);
+        slot_j = direct_j ? (int32_t)((b - b_first) * p.F + p.j_idx[pair]) : tid;
+        s_off[tid] = key_i;                                                     // neighbours compare keys
+        s_off[kTcRows + tid] = -1;
+    }
+    __syncthreads();
+    if (tid < kTcRows) {
+        const bool head = tid == 0 || s_off[tid - 1] != key_i;
+        const unsigned m = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_cnt[2 + warp] = __popc(m);
+        s_slot[kTcRows + tid] = slot_j;
+        s_slot[tid] = __popc(m & (0xffffffffu >> (31 - lane))) - 1;             // rank inside the warp, completed below
+    }
+    __syncthreads();
+    if (tid < kTcRows) {
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += s_cnt[2 + w];
+        const int slot_i = s_slot[tid] + before;
+        const bool head = tid == 0 || s_off[tid - 1] != key_i;
+        s_slot[tid] = slot_i;
+        if (tid == kTcRows - 1) {
+            s_cnt[0] = slot_i + 1;
+            s_cnt[1] = direct_j ? nb_tile * p.F : kTcRows;
         }
-        s_off[tid] = zp_off;
-        s_off[kTcRows + tid] = zc_off;
+        __syncwarp();
+        // (the keys in s_off[0..127] are overwritten by line offsets only after every thread has compared: next barrier)
+        key_i = head ? key_i : -1;
+    }
+    __syncthreads();
+    if (tid < kTcRows) {
+        if (key_i >= 0) s_off[s_slot[tid]] = key_i * p.N;
+        s_off[kTcRows + slot_j] = key_j * p.N;                                  // same value from every row that shares the line
     }
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem_u32(tmem_slot)) : "memory");
@@ -296,38 +337,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         const uint32_t sin_base = base + kTcStages * kTcStageBytes + grp * kTcInBytes;
         const uint8_t* sin_ptr = sm + kTcStages * kTcStageBytes + grp * kTcInBytes;
         const bool wide = (p.N & 1) == 0;                       // rows start on 16-byte boundaries
-        // thread (rb, c) of the group copies chunk c (16 bytes = 2 samples; 8 lanes cover a 128-byte line) of the rows
-        // rb, rb + 16, ..., rb + 112 of both arrays: the swizzle term (r & 7) = (rb & 7) and the sample offset are the
+        // thread (rb, c) of the group copies chunk c (16 bytes = 2 samples; 8 lanes cover a 128-byte line) of the line
+        // slots rb, rb + 16, ... of both sides: the swizzle term (slot & 7) = (rb & 7) and the sample offset are the
         // thread's own constants
         const int cc = gtid & 7, rb = gtid >> 3;
         const uint32_t dst0 = sin_base + rb * 128 + ((cc ^ (rb & 7)) << 4);
+        const int n_lines_i = s_cnt[0], n_lines_j = s_cnt[1];
         auto copy_inputs = [&](int i) {
             if (wide) {
                 const int t = i * kTcSlabT + 2 * cc;
                 const int bytes_t = max(0, min(16, (p.N - t) * 8));
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int off = s_off[(k >> 3) * kTcRows + rb + 16 * (k & 7)];
-                    const float2* src = ((k >> 3) ? p.zc : p.zp) + (bytes_t ? off + t : 0);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (k >> 3) * (kTcRows * 128) + (k & 7) * 2048),
-                                 "l"(src), "r"(bytes_t) : "memory");
+                for (int side = 0; side < 2; ++side) {
+                    const int n_lines = side ? n_lines_j : n_lines_i;
+                    const float2* arr = side ? p.zc : p.zp;
+                    for (int slot = rb; slot < n_lines; slot += 16) {
+                        const int off = s_off[side * kTcRows + slot];
+                        if (off < 0) continue;                              // a 'j' filter no row of this tile pairs with
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + side * (kTcRows * 128) + (slot - rb) * 128),
+                                     "l"(arr + (bytes_t ? off + t : 0)), "r"(bytes_t) : "memory");
+                    }
                 }
             } else {
-                // odd N: rows start on 8-byte boundaries only; sample by sample (thread (rb16, c8): 16 lanes per line)
+                // odd N: rows start on 8-byte boundaries only; sample by sample (thread (r8, c16): 16 lanes per line)
                 const int c8 = gtid & 15, r16 = gtid >> 4;
                 const int t = i * kTcSlabT + c8;
-#pragma unroll 4
-                for (int k = 0; k < 32; ++k) {
-                    const int arr = k >> 4, r = r16 + 8 * (k & 15);
-                    const int off = s_off[arr * kTcRows + r];
-                    const int bytes = t >= p.N ? 0 : 8;
-                    const float2* src = (arr ? p.zc : p.zp) + (bytes ? off + t : 0);
-                    const uint32_t dst = sin_base + arr * (kTcRows * 128) + r * 128 + (((c8 >> 1) ^ (r & 7)) << 4) + (c8 & 1) * 8;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+                const int bytes = t >= p.N ? 0 : 8;
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    const int n_lines = side ? n_lines_j : n_lines_i;
+                    const float2* arr = side ? p.zc : p.zp;
+                    for (int slot = r16; slot < n_lines; slot += 8) {
+                        const int off = s_off[side * kTcRows + slot];
+                        if (off < 0) continue;
+                        const uint32_t dst = sin_base + side * (kTcRows * 128) + slot * 128 + (((c8 >> 1) ^ (slot & 7)) << 4) + (c8 & 1) * 8;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(arr + (bytes ? off + t : 0)), "r"(bytes) : "memory");
+                    }
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        // this thread's row reads line slots li ('i' side) and lj ('j' side)
+        const int li = s_slot[gtid], lj = s_slot[kTcRows + gtid];
+        const uint8_t* line_i = sin_ptr + li * 128;
+        const uint8_t* line_j = sin_ptr + kTcRows * 128 + lj * 128;
+        const int swz_i = li & 7, swz_j = lj & 7;
         const float* Bh = p.Bs + (size_t)col0 * p.k_pad;
         const float* Bl = p.Bs + ((size_t)p.n_cols_pad + col0) * p.k_pad;
         if (grp < n_slabs) copy_inputs(grp);
@@ -355,9 +409,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 float4 zp2[2], zc2[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int off = gtid * 128 + (((2 * ss + h) ^ (gtid & 7)) << 4);
-                    zp2[h] = *reinterpret_cast<const float4*>(sin_ptr + off);
-                    zc2[h] = *reinterpret_cast<const float4*>(sin_ptr + kTcRows * 128 + off);
+                    zp2[h] = *reinterpret_cast<const float4*>(line_i + (((2 * ss + h) ^ swz_i) << 4));
+                    zc2[h] = *reinterpret_cast<const float4*>(line_j + (((2 * ss + h) ^ swz_j) << 4));
                 }
                 uint32_t hi[8], lo[8];
 #pragma unroll
