@@ -35,13 +35,14 @@ constexpr int kTcRows = 128;          // rows per CTA = TMEM lanes
 constexpr int kTcCols = 80;           // output columns per CTA (UMMA N)
 constexpr int kTcSlabT = 16;          // time samples per slab
 constexpr int kTcK = 2 * kTcSlabT;    // K per slab (Re, -Im interleaved)
-constexpr int kTcStages = 4;
+constexpr int kTcStages = 4;           // one per producer group (a group that shared stages with others could run two barrier phases ahead)
 constexpr int kTcDrain = 2;           // slabs per drain of the head-product accumulator: 8 tensor-core accumulations between
                                       // fp32 adds (the TMEM accumulator truncates like the register one: the error grows with
                                       // the number of accumulations into one running sum)
-constexpr int kTcEpiWarps = 4, kTcProdWarps = 16, kTcGroups = 4;   // producer groups of four warps (one per TMEM lane quarter)
-constexpr int kTcMmaWarp = kTcEpiWarps;                          // warp 4
-constexpr int kTcThreads = 32 * (kTcEpiWarps + 1 + kTcProdWarps);   // 672: 96 registers per thread
+constexpr int kTcEpiWarps = 8, kTcProdWarps = 16, kTcGroups = 4;   // producer groups of four warps (one per TMEM lane quarter)
+constexpr int kTcEpiCols = kTcCols / (kTcEpiWarps / 4);            // columns per epilogue warp
+constexpr int kTcMmaWarp = kTcEpiWarps, kTcMmaWarps = 3;         // warps 8..10: one issuing thread each
+constexpr int kTcThreads = 32 * (kTcEpiWarps + kTcMmaWarps + kTcProdWarps);   // 864: 72 registers per thread
 constexpr int kTcBTile = kTcCols * 128;                         // bytes of one B' tile (80 rows x 32 tf32)
 constexpr int kTcStageBytes = 2 * kTcBTile;                      // head + tail
 constexpr int kTcInBytes = 2 * kTcRows * 128;                    // one group's input slab: 128 lines of (|z|, theta) + 128 of (re, im)
@@ -50,7 +51,18 @@ constexpr size_t kTcSmem = 1024 + (size_t)kTcOffBars + 256 + 4 * kTcRows * sizeo
 // TMEM columns: the two head-product accumulators (Ah Bh, drained every kTcDrain slabs), ONE accumulator of the
 // correction products (Al Bh + Ah Bl: 2^-11 of the head products, so its truncation error stays below 1e-7 of the
 // result even over the whole contraction -- it is read once, at the end), and the A' stages (head at kTcA0 + 64 s, tail + 32)
-constexpr uint32_t kTcAcc0 = 0, kTcAcc1 = 80, kTcAccS = 160, kTcA0 = 256;
+constexpr uint32_t kTcAcc0 = 0, kTcAccS = 80, kTcAcc1 = 160, kTcA0 = 256;
+
+#ifdef TEBSCAT_TC_TRACE
+// timeline of one CTA (the last of the first wave: SM-resident alone with its wave), first kTcTraceSlabs slabs:
+// [role 0..3 producer group g | 4 MMA | 5 epilogue][slab or group][event]
+constexpr int kTcTraceSlabs = 64, kTcTraceEv = 6;
+__device__ long long g_tc_trace[6 * kTcTraceSlabs * kTcTraceEv];
+#define TC_TRACE(role, idx, ev) do { if (blockIdx.x == 1 && lane == 0 && (idx) < kTcTraceSlabs) \
+    g_tc_trace[((role) * kTcTraceSlabs + (idx)) * kTcTraceEv + (ev)] = clock64(); } while (0)
+#else
+#define TC_TRACE(role, idx, ev) do {} while (0)
+#endif
 
 struct PairTcParams {
     const float2* zp;
@@ -121,6 +133,12 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
+__device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, float (&v)[8]) {     // the caller issues tcgen05.wait::ld
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -168,17 +186,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     auto empty = [&](int s) { return bars + 8u * (kTcStages + s); };
     auto acc_full = [&](int a) { return bars + 8u * (2 * kTcStages + a); };
     auto acc_empty = [&](int a) { return bars + 8u * (2 * kTcStages + 2 + a); };
+    const uint32_t tail_done = bars + 8u * (2 * kTcStages + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < kTcStages; ++s) {
             tc_mbar_init(full(s), kTcProdWarps / kTcGroups);
-            tc_mbar_init(empty(s), 1);
+            tc_mbar_init(empty(s), 2);                                  // one issuer of each kind
         }
         for (int a = 0; a < 2; ++a) {
             tc_mbar_init(acc_full(a), 1);
             tc_mbar_init(acc_empty(a), kTcEpiWarps);
         }
+        tc_mbar_init(tail_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // Input lines.  A row (pair) reads the (|z|, theta) line of its 'i' filter and the (re, im) line of its 'j' filter;
@@ -244,6 +264,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // every MMA accumulates (one instruction covers a head accumulator AND the correction accumulator, see below):
+    // the three accumulators start at zero, and the epilogue zeroes a head accumulator again after draining it
+    if (warp < kTcEpiWarps) {
+        const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const uint32_t t0 = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (warp >> 2) * (3 * kTcCols / 2);
+#pragma unroll
+        for (int j = 0; j < 3 * kTcCols / 16; ++j) tc_st8(t0 + 8 * j, zero);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     const long long row0 = (long long)blockIdx.x * kTcRows;
     const int col0 = blockIdx.y * kTcCols;
@@ -251,71 +283,106 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     const int n_groups = (n_slabs + kTcDrain - 1) / kTcDrain;
 
     if (warp < kTcEpiWarps) {
-        // ===== epilogue: warp q drains lanes 32 q .. 32 q + 31, all 80 columns =====
-        const int q = warp & 3;
-        float total[kTcCols];
+        // ===== epilogue: warp (q, half) drains lanes 32 q .. 32 q + 31, columns 40 half .. 40 half + 39 (80 running sums
+        // per thread do not fit the registers a CTA of this size leaves per thread: they were spilled) =====
+        const int q = warp & 3, c0 = (warp >> 2) * kTcEpiCols;
+        float total[kTcEpiCols];
 #pragma unroll
-        for (int i = 0; i < kTcCols; ++i) total[i] = 0.f;
+        for (int i = 0; i < kTcEpiCols; ++i) total[i] = 0.f;
         for (int g = 0; g < n_groups; ++g) {
             const int a = g & 1;
+            if (warp == 0) TC_TRACE(5, g, 0);
             tc_mbar_wait_relaxed(acc_full(a), (g >> 1) & 1, 4000);
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (a ? kTcAcc1 : kTcAcc0);
+            if (warp == 0) TC_TRACE(5, g, 1);
+            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (a ? kTcAcc1 : kTcAcc0) + c0;
+            float v[kTcEpiCols];
 #pragma unroll
-            for (int j = 0; j < kTcCols / 8; ++j) {
-                float v[8];
-                tc_ld8(taddr + 8 * j, v);
+            for (int j = 0; j < kTcEpiCols / 8; ++j) tc_ld8_nowait(taddr + 8 * j, *reinterpret_cast<float (*)[8]>(&v[8 * j]));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            {
+                const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) total[8 * j + i] += v[i];
+                for (int j = 0; j < kTcEpiCols / 8; ++j) tc_st8(taddr + 8 * j, zero);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc_mbar_arrive(acc_empty(a));
-        }
-        {   // the correction products: complete with the last group's commit (a commit covers every earlier MMA)
-            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + kTcAccS;
+            if (lane == 0) tc_mbar_arrive(acc_empty(a));                     // the accumulator is free (and zero) before the adds
+            if (warp == 0) TC_TRACE(5, g, 2);
 #pragma unroll
-            for (int j = 0; j < kTcCols / 8; ++j) {
-                float v[8];
-                tc_ld8(taddr + 8 * j, v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) total[8 * j + i] += v[i];
-            }
-            tc_fence_before();
+            for (int i = 0; i < kTcEpiCols; ++i) total[i] += v[i];
         }
+        // the correction products: head(A') tail(B') is complete with the last group's commit (a commit covers every
+        // earlier MMA of its thread), tail(A') head(B') when the second issuing thread says so
+        tc_mbar_wait_relaxed(tail_done, 0, 1000);
+        tc_fence_after();
+        {
+            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + kTcAccS + c0;
+            float v[kTcEpiCols];
+#pragma unroll
+            for (int j = 0; j < kTcEpiCols / 8; ++j) tc_ld8_nowait(taddr + 8 * j, *reinterpret_cast<float (*)[8]>(&v[8 * j]));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < kTcEpiCols; ++i) total[i] += v[i];
+        }
+        tc_fence_before();
         const long long row = row0 + 32 * q + lane;
         if (row < p.rows) {
 #pragma unroll
-            for (int i = 0; i < kTcCols; ++i) {
-                const int col = col0 + i;
+            for (int i = 0; i < kTcEpiCols; ++i) {
+                const int col = col0 + c0 + i;
                 if (col < p.n_out) p.out[row * p.n_out + col] = total[i];
             }
         }
-    } else if (warp == kTcMmaWarp) {
-        // ===== MMA issuer: one thread =====
-        if (lane == 0) {
-            for (int i = 0; i < n_slabs; ++i) {
-                const int s = i % kTcStages, g = i / kTcDrain, a = g & 1;
-                const bool first = (i % kTcDrain) == 0;
-                if (first) {
-                    tc_mbar_wait(acc_empty(a), ((g >> 1) & 1) ^ 1);          // passes at once for the first two groups
+    } else if (warp < kTcMmaWarp + kTcMmaWarps) {
+        // ===== MMA issuers: one thread of each of three warps.  TMEM columns [head a | corrections | head b].
+        // Issuers 0 and 1 take the drain groups of their parity: head(A') head(B') into their own head accumulator.
+        // Issuer 2 takes every slab: head(A') tail(B') + tail(A') head(B') into the correction accumulator.
+        // Why three threads: an MMA of this size costs its issuing thread ~98 cycles whatever N <= 160 is, a wait on an
+        // mbarrier that is already complete ~250, and threads issue independently (tools/micro/umma_rate.cu: one
+        // thread 839, three threads 1833 of 1934 MAC/cycle/SM at N = 80); one thread issuing all twelve MMAs of a slab
+        // was the limit of the whole kernel (tools/tc_trace.py).  Every accumulator has ONE writer, so the order of
+        // its additions -- and the result, bit for bit -- does not depend on how the threads interleave. =====
+        const int m = warp - kTcMmaWarp;
+        if (lane == 0 && m < 2) {
+            const int a = m;
+            for (int g = a; g < n_groups; g += 2) {
+                if (a == 0) TC_TRACE(4, g, 0);
+                tc_mbar_wait(acc_empty(a), ((g >> 1) & 1) ^ 1);              // passes at once for the first group
+                tc_fence_after();
+                if (a == 0) TC_TRACE(4, g, 1);
+                const int i_end = min((g + 1) * kTcDrain, n_slabs);
+                for (int i = g * kTcDrain; i < i_end; ++i) {
+                    const int s = i % kTcStages;
+                    tc_mbar_wait(full(s), (i / kTcStages) & 1);
                     tc_fence_after();
+                    if (m == 0) TC_TRACE(4, g, 2 + 2 * (i - g * kTcDrain));
+                    const uint32_t d = tmem + (a ? kTcAcc1 : kTcAcc0);
+                    const uint32_t a_hi = tmem + kTcA0 + 64 * s;
+                    const uint32_t b_hi = base + s * kTcStageBytes;
+#pragma unroll
+                    for (int k = 0; k < kTcK / 8; ++k) tc_mma_ts(d, a_hi + 8 * k, tc_b_desc(b_hi + 32 * k), kTcIdesc, 1u);
+                    tc_commit(empty(s));                                      // the stage is free once the MMAs of both kinds retire
+                    if (m == 0) TC_TRACE(4, g, 3 + 2 * (i - g * kTcDrain));
                 }
+                tc_commit(acc_full(a));
+            }
+        } else if (lane == 0 && m == 2) {
+            for (int i = 0; i < n_slabs; ++i) {
+                const int s = i % kTcStages;
                 tc_mbar_wait(full(s), (i / kTcStages) & 1);
                 tc_fence_after();
-                const uint32_t d = tmem + (a ? kTcAcc1 : kTcAcc0), dc = tmem + kTcAccS;
                 const uint32_t a_hi = tmem + kTcA0 + 64 * s, a_lo = a_hi + 32;
                 const uint32_t b_hi = base + s * kTcStageBytes, b_lo = b_hi + kTcBTile;
 #pragma unroll
                 for (int k = 0; k < kTcK / 8; ++k) {
-                    const uint64_t dh = tc_b_desc(b_hi + 32 * k), dl = tc_b_desc(b_lo + 32 * k);
-                    tc_mma_ts(d, a_hi + 8 * k, dh, kTcIdesc, (first && k == 0) ? 0u : 1u);
-                    tc_mma_ts(dc, a_lo + 8 * k, dh, kTcIdesc, (i == 0 && k == 0) ? 0u : 1u);
-                    tc_mma_ts(dc, a_hi + 8 * k, dl, kTcIdesc, 1u);
+                    tc_mma_ts(tmem + kTcAccS, a_lo + 8 * k, tc_b_desc(b_hi + 32 * k), kTcIdesc, 1u);
+                    tc_mma_ts(tmem + kTcAccS, a_hi + 8 * k, tc_b_desc(b_lo + 32 * k), kTcIdesc, 1u);
                 }
-                tc_commit(empty(s));                                          // the stage is free once these MMAs retire
-                if ((i % kTcDrain) == kTcDrain - 1 || i == n_slabs - 1) tc_commit(acc_full(a));
+                tc_commit(empty(s));
             }
+            tc_commit(tail_done);
         }
         __syncwarp();
     } else {
@@ -325,7 +392,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         // reading its own row straight from global memory costs one L1 wavefront per lane, and the L1 data pipe was
         // the limit), swizzled so that the per-row 128-bit reads are conflict free.  While one group waits (its copies,
         // its stage, the tensor-memory stores), the other three compute. =====
-        const int pw_ = warp - (kTcMmaWarp + 1);
+        const int pw_ = warp - (kTcMmaWarp + kTcMmaWarps);
         const int q = warp & 3, grp = pw_ >> 2;
         const int gtid = q * 32 + lane;                         // 0..127 inside the group = the thread's row
         const long long row = row0 + gtid;
@@ -387,8 +454,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         if (grp < n_slabs) copy_inputs(grp);
         for (int i = grp; i < n_slabs; i += kTcGroups) {
             const int s = i % kTcStages;
+            if (q == 0) TC_TRACE(grp, i, 0);
             tc_mbar_wait_relaxed(empty(s), ((i / kTcStages) & 1) ^ 1, 1000);
             tc_fence_after();
+            if (q == 0) TC_TRACE(grp, i, 1);
             // B' slab: 2 x 80 rows x 8 chunks of 16 bytes, global -> swizzled shared memory, asynchronously
 #pragma unroll
             for (int j = 0; j < 10; ++j) {
@@ -402,6 +471,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 1;" ::: "memory");               // this slab's inputs (not yet B')
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // ... of every thread of the group
+            if (q == 0) TC_TRACE(grp, i, 2);
             // A': the products of this thread's samples, split, straight into tensor memory
             const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + kTcA0 + 64 * s;
 #pragma unroll
@@ -425,12 +495,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 tc_st8(ta + 32 + 8 * ss, lo);
             }
             // hand the slab to the tensor core first ...
+            if (q == 0) TC_TRACE(grp, i, 3);
             asm volatile("cp.async.wait_group 0;" ::: "memory");               // B' has landed
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of B' -> the MMA's async proxy
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(full(s));
+            if (q == 0) TC_TRACE(grp, i, 4);
             // ... then refill the inputs (off the producer -> MMA critical path): everyone has read them
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
             if (i + kTcGroups < n_slabs) copy_inputs(i + kTcGroups);

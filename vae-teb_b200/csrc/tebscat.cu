@@ -2249,3 +2249,11 @@ extern "C" int tebscat_large_pad_adjoint(tebscat_large* g, const float* gu_dev, 
     ++g_launches;
     return TEBSCAT_OK;
 }
+
+#ifdef TEBSCAT_TC_TRACE
+extern "C" int tebscat_debug_tc_trace(long long* out, int n) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tebscat::g_tc_trace, (size_t)n * sizeof(long long));
+    return 0;
+}
+#endif
