@@ -22,8 +22,9 @@ r = lambda v: int(v - t0) if v > 0 else -1
 print('producer groups: slab | wait-start, stage free, inputs landed, products stored, handed over  (cycles since the first event)')
 for i in range(16, 40):
     g = i % 4
-    print('  slab %2d group %d: %s   | wait %5d  inputs %5d  compute %5d  B+st-wait %5d' % (
-        i, g, ' '.join('%7d' % r(v) for v in t[g, i, :5]), t[g, i, 1] - t[g, i, 0], t[g, i, 2] - t[g, i, 1], t[g, i, 3] - t[g, i, 2], t[g, i, 4] - t[g, i, 3]))
+    print('  slab %2d group %d: %s   | wait %5d  inputs %5d  compute %5d  B+st-wait %5d  group barrier %5d  next copies issued %5d' % (
+        i, g, ' '.join('%7d' % r(v) for v in t[g, i, :5]), t[g, i, 1] - t[g, i, 0], t[g, i, 2] - t[g, i, 1], t[g, i, 3] - t[g, i, 2], t[g, i, 4] - t[g, i, 3],
+        t[g, i, 5] - t[g, i, 4], t[g, i + 4, 0] - t[g, i, 5]))
 print('MMA issuer (kind 0, parity 0): drain group | start, accumulator free, slab 0 full, slab 0 issued, slab 1 full, slab 1 issued')
 for g in range(8, 24, 2):
     print('  group %2d: %s   | acc wait %5d  full wait %5d  issue %5d  full wait %5d  issue %5d' % (g, ' '.join('%7d' % r(v) for v in t[4, g, :6]),

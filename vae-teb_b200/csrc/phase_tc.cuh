@@ -67,7 +67,8 @@ __device__ long long g_tc_trace[6 * kTcTraceSlabs * kTcTraceEv];
 struct PairTcParams {
     const float2* zp;
     const float2* zc;
-    const float* Bs;            // [2 (head, tail)][n_cols_pad][k_pad] TF32 values in fp32 containers, k_pad = 32 n_slabs
+    const float* Bimg;          // [column tile][slab][kTcStageBytes]: the shared-memory image of the slab's B' stage (head, tail;
+                                // TF32 values in fp32 containers, K-major, 128-byte swizzle), copied with one bulk copy
     const int32_t* i_idx;
     const int32_t* j_idx;
     const float* powers;
@@ -98,6 +99,19 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
         if (!done && spin > (1u << 24)) __trap();
     }
+}
+// one poll, no loop: the MMA issuers ask for the NEXT slab before they issue the current one, so that the ~250 cycles a
+// poll takes (even of a barrier that is complete) pass behind the MMAs instead of in front of them
+__device__ __forceinline__ uint32_t tc_mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
 }
 // the same for warps that wait long (epilogue, producers ahead of the tensor core): back off between polls so that
 // the polling does not take issue slots from the producers
@@ -227,6 +241,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         slot_j = direct_j ? (int32_t)((b - b_first) * p.F + p.j_idx[pair]) : tid;
         s_off[tid] = key_i;                                                     // neighbours compare keys
         s_off[kTcRows + tid] = -1;
+        if (tid == 0) { s_cnt[6] = kTcRows; s_cnt[7] = 0; }
     }
     __syncthreads();
     if (tid < kTcRows) {
@@ -234,6 +249,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         const unsigned m = __ballot_sync(0xffffffffu, head);
         if (lane == 0) s_cnt[2 + warp] = __popc(m);
         s_slot[kTcRows + tid] = slot_j;
+        atomicMin(&s_cnt[6], slot_j);                                           // the used 'j' slots are one range
+        atomicMax(&s_cnt[7], slot_j + 1);
         s_slot[tid] = __popc(m & (0xffffffffu >> (31 - lane))) - 1;             // rank inside the warp, completed below
     }
     __syncthreads();
@@ -353,11 +370,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 tc_fence_after();
                 if (a == 0) TC_TRACE(4, g, 1);
                 const int i_end = min((g + 1) * kTcDrain, n_slabs);
+                uint32_t ready = 0;
                 for (int i = g * kTcDrain; i < i_end; ++i) {
                     const int s = i % kTcStages;
-                    tc_mbar_wait(full(s), (i / kTcStages) & 1);
+                    if (!ready) tc_mbar_wait(full(s), (i / kTcStages) & 1);
                     tc_fence_after();
                     if (m == 0) TC_TRACE(4, g, 2 + 2 * (i - g * kTcDrain));
+                    ready = i + 1 < i_end ? tc_mbar_test(full((i + 1) % kTcStages), ((i + 1) / kTcStages) & 1) : 0u;
                     const uint32_t d = tmem + (a ? kTcAcc1 : kTcAcc0);
                     const uint32_t a_hi = tmem + kTcA0 + 64 * s;
                     const uint32_t b_hi = base + s * kTcStageBytes;
@@ -369,10 +388,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 tc_commit(acc_full(a));
             }
         } else if (lane == 0 && m == 2) {
+            uint32_t ready = 0;
             for (int i = 0; i < n_slabs; ++i) {
                 const int s = i % kTcStages;
-                tc_mbar_wait(full(s), (i / kTcStages) & 1);
+                if (!ready) tc_mbar_wait(full(s), (i / kTcStages) & 1);
                 tc_fence_after();
+                ready = i + 1 < n_slabs ? tc_mbar_test(full((i + 1) % kTcStages), ((i + 1) / kTcStages) & 1) : 0u;
                 const uint32_t a_hi = tmem + kTcA0 + 64 * s, a_lo = a_hi + 32;
                 const uint32_t b_hi = base + s * kTcStageBytes, b_lo = b_hi + kTcBTile;
 #pragma unroll
@@ -410,19 +431,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         const int cc = gtid & 7, rb = gtid >> 3;
         const uint32_t dst0 = sin_base + rb * 128 + ((cc ^ (rb & 7)) << 4);
         const int n_lines_i = s_cnt[0], n_lines_j = s_cnt[1];
+        // 'j' side with the direct slot map: line slot -> (first sample of the tile * F + slot) * N, no table; only the
+        // range of slots some row uses is copied
+        const int j_lo = s_cnt[6] & ~15, j_hi = s_cnt[7];
+        const long long j_base = b_first * p.F;
         auto copy_inputs = [&](int i) {
             if (wide) {
                 const int t = i * kTcSlabT + 2 * cc;
                 const int bytes_t = max(0, min(16, (p.N - t) * 8));
-#pragma unroll
-                for (int side = 0; side < 2; ++side) {
-                    const int n_lines = side ? n_lines_j : n_lines_i;
-                    const float2* arr = side ? p.zc : p.zp;
-                    for (int slot = rb; slot < n_lines; slot += 16) {
-                        const int off = s_off[side * kTcRows + slot];
-                        if (off < 0) continue;                              // a 'j' filter no row of this tile pairs with
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + side * (kTcRows * 128) + (slot - rb) * 128),
-                                     "l"(arr + (bytes_t ? off + t : 0)), "r"(bytes_t) : "memory");
+                for (int slot = rb; slot < n_lines_i; slot += 16) {
+                    const int off = s_off[slot];
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (slot - rb) * 128),
+                                 "l"(p.zp + (bytes_t ? off + t : 0)), "r"(bytes_t) : "memory");
+                }
+                if (direct_j) {
+                    for (int slot = j_lo + rb; slot < j_hi; slot += 16)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + kTcRows * 128 + (slot - rb) * 128),
+                                     "l"(p.zc + (bytes_t ? (j_base + slot) * p.N + t : 0)), "r"(bytes_t) : "memory");
+                } else {
+                    for (int slot = rb; slot < n_lines_j; slot += 16) {
+                        const int off = s_off[kTcRows + slot];
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + kTcRows * 128 + (slot - rb) * 128),
+                                     "l"(p.zc + (bytes_t ? off + t : 0)), "r"(bytes_t) : "memory");
                     }
                 }
             } else {
@@ -436,7 +466,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                     const float2* arr = side ? p.zc : p.zp;
                     for (int slot = r16; slot < n_lines; slot += 8) {
                         const int off = s_off[side * kTcRows + slot];
-                        if (off < 0) continue;
+                        if (off < 0) continue;                          // a 'j' filter no row of this tile pairs with
                         const uint32_t dst = sin_base + side * (kTcRows * 128) + slot * 128 + (((c8 >> 1) ^ (slot & 7)) << 4) + (c8 & 1) * 8;
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(arr + (bytes ? off + t : 0)), "r"(bytes) : "memory");
                     }
@@ -449,8 +479,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
         const uint8_t* line_i = sin_ptr + li * 128;
         const uint8_t* line_j = sin_ptr + kTcRows * 128 + lj * 128;
         const int swz_i = li & 7, swz_j = lj & 7;
-        const float* Bh = p.Bs + (size_t)col0 * p.k_pad;
-        const float* Bl = p.Bs + ((size_t)p.n_cols_pad + col0) * p.k_pad;
+        const uint8_t* Bimg = reinterpret_cast<const uint8_t*>(p.Bimg) + (size_t)blockIdx.y * p.n_slabs * kTcStageBytes;
         if (grp < n_slabs) copy_inputs(grp);
         for (int i = grp; i < n_slabs; i += kTcGroups) {
             const int s = i % kTcStages;
@@ -458,18 +487,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
             tc_mbar_wait_relaxed(empty(s), ((i / kTcStages) & 1) ^ 1, 1000);
             tc_fence_after();
             if (q == 0) TC_TRACE(grp, i, 1);
-            // B' slab: 2 x 80 rows x 8 chunks of 16 bytes, global -> swizzled shared memory, asynchronously
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const int idx = gtid + 128 * j;
-                const int part = idx >= kTcCols * 8, rem = idx - part * kTcCols * 8;
-                const int n = rem >> 3, c = rem & 7;
-                const float* src = (part ? Bl : Bh) + (size_t)n * p.k_pad + i * kTcK + 4 * c;
-                const uint32_t dst = base + s * kTcStageBytes + part * kTcBTile + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            // B' slab: its shared-memory image (head and tail, 2 x 80 rows of 128 bytes, swizzled) is one contiguous block
+            // in global memory: ONE bulk copy by one thread, accounted on the slab's `full` barrier as transaction bytes
+            // (the MMA issuers see the slab when the four warps have arrived AND the bytes have landed)
+            if (gtid == 0) {
+                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full(s)), "r"((uint32_t)kTcStageBytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(base + s * kTcStageBytes), "l"(Bimg + (size_t)i * kTcStageBytes), "r"((uint32_t)kTcStageBytes), "r"(full(s)) : "memory");
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");               // this slab's inputs (not yet B')
+            asm volatile("cp.async.wait_group 0;" ::: "memory");               // this slab's inputs
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // ... of every thread of the group
             if (q == 0) TC_TRACE(grp, i, 2);
             // A': the products of this thread's samples, split, straight into tensor memory
@@ -496,15 +522,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
             }
             // hand the slab to the tensor core first ...
             if (q == 0) TC_TRACE(grp, i, 3);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");               // B' has landed
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of B' -> the MMA's async proxy
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(full(s));
             if (q == 0) TC_TRACE(grp, i, 4);
             // ... then refill the inputs (off the producer -> MMA critical path): everyone has read them
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            if (q == 0) TC_TRACE(grp, i, 5);
             if (i + kTcGroups < n_slabs) copy_inputs(i + kTcGroups);
             else asm volatile("cp.async.commit_group;" ::: "memory");
         }

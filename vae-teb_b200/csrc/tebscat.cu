@@ -1011,7 +1011,7 @@ struct tebscat_phase_plan {
     tebscat_plan* stage_a = nullptr;
     int device = 0;
     float2* d_G = nullptr;
-    float* d_Bs = nullptr;          // tcgen05 form: [2][n_cols_pad][k_pad] TF32 head / tail of B' (phase_tc.cuh)
+    float* d_Bs = nullptr;          // tcgen05 form: shared-memory images of the slabs of B' (TF32 head / tail, phase_tc.cuh)
     int32_t n_slabs = 0, k_pad = 0;
     int32_t* d_i = nullptr;
     int32_t* d_j = nullptr;
@@ -1108,8 +1108,22 @@ static int phase_plan_create_impl(const tebscat_phase_desc* d, tebscat_plan* sta
                     bs[(size_t)n * p->k_pad + 2 * t + c] = hi;
                     bs[per + (size_t)n * p->k_pad + 2 * t + c] = rna(v - hi);
                 }
-        CU(cudaMalloc(&p->d_Bs, bs.size() * sizeof(float)));
-        CU(cudaMemcpy(p->d_Bs, bs.data(), bs.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // the kernel copies a slab of B' into shared memory with ONE bulk copy: lay the slabs out as their shared-memory
+        // image -- [column tile][slab][head, tail][80 rows x 128 bytes, 16-byte chunk c of row n at c ^ (n & 7)]
+        const int n_tiles = d->n_cols_pad / kTcCols, stage_f = kTcStageBytes / 4, tile_f = kTcBTile / 4;
+        std::vector<float> img((size_t)n_tiles * p->n_slabs * stage_f, 0.f);
+        for (int ct = 0; ct < n_tiles; ++ct)
+            for (int i = 0; i < p->n_slabs; ++i) {
+                float* dst = img.data() + ((size_t)ct * p->n_slabs + i) * stage_f;
+                for (int part = 0; part < 2; ++part)
+                    for (int n = 0; n < kTcCols; ++n)
+                        for (int c = 0; c < 8; ++c)
+                            for (int e = 0; e < 4; ++e)
+                                dst[part * tile_f + (n >> 3) * 256 + (n & 7) * 32 + ((c ^ (n & 7)) << 2) + e] =
+                                    bs[part * per + (size_t)(ct * kTcCols + n) * p->k_pad + i * kTcK + 4 * c + e];
+            }
+        CU(cudaMalloc(&p->d_Bs, img.size() * sizeof(float)));
+        CU(cudaMemcpy(p->d_Bs, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaFuncSetAttribute(phase_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
     }
     CU(cudaMalloc(&p->d_i, d->n_pairs * sizeof(int32_t)));
@@ -1163,7 +1177,7 @@ static void launch_pair_gemm(const tebscat_phase_plan* p, const PairParams& pp, 
     const long long ws_elems = (pp.rows / pp.n_sel + 1) * (long long)pp.F * pp.N;
     if (use_tcgen05_pairs() && ws_elems < (1LL << 31)) {
         PairTcParams q;
-        q.zp = pp.zp; q.zc = pp.zc; q.Bs = p->d_Bs; q.i_idx = pp.i_idx; q.j_idx = pp.j_idx; q.powers = pp.powers;
+        q.zp = pp.zp; q.zc = pp.zc; q.Bimg = p->d_Bs; q.i_idx = pp.i_idx; q.j_idx = pp.j_idx; q.powers = pp.powers;
         q.subset = pp.subset; q.out = pp.out; q.rows = pp.rows; q.n_sel = pp.n_sel; q.F = pp.F; q.N = pp.N;
         q.n_out = pp.n_out; q.n_cols_pad = pp.n_cols_pad; q.n_slabs = p->n_slabs; q.k_pad = p->k_pad;
         dim3 grid((unsigned)((pp.rows + kTcRows - 1) / kTcRows), (unsigned)(d.n_cols_pad / kTcCols));
