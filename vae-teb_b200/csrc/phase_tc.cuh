@@ -441,17 +441,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 const int bytes_t = max(0, min(16, (p.N - t) * 8));
                 for (int slot = rb; slot < n_lines_i; slot += 16) {
                     const int off = s_off[slot];
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (slot - rb) * 128),
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (slot - rb) * 128),
                                  "l"(p.zp + (bytes_t ? off + t : 0)), "r"(bytes_t) : "memory");
                 }
                 if (direct_j) {
                     for (int slot = j_lo + rb; slot < j_hi; slot += 16)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + kTcRows * 128 + (slot - rb) * 128),
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + kTcRows * 128 + (slot - rb) * 128),
                                      "l"(p.zc + (bytes_t ? (j_base + slot) * p.N + t : 0)), "r"(bytes_t) : "memory");
                 } else {
                     for (int slot = rb; slot < n_lines_j; slot += 16) {
                         const int off = s_off[kTcRows + slot];
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + kTcRows * 128 + (slot - rb) * 128),
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + kTcRows * 128 + (slot - rb) * 128),
                                      "l"(p.zc + (bytes_t ? off + t : 0)), "r"(bytes_t) : "memory");
                     }
                 }
