@@ -1279,7 +1279,10 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
     const tebscat_phase_desc& d = p->desc;
     const int n_sel = pair_subset_host ? n_subset : d.n_pairs;
     const size_t per_sample = (size_t)d.n_filters * d.N;
-    const int64_t chunk = B < kPhaseChunk ? B : kPhaseChunk;
+    // the dense form of stage B runs over three stage-A chunks at once: 888 samples x 741 pairs are 34.7 waves of row tiles
+    // on 148 SMs (99 % of the last wave used) where 296 samples are 11.6 (the twelfth wave 58 % full)
+    const int64_t span = (apply_low_pass && !p->pair_plan && p->d_G) ? 3 * kPhaseChunk : kPhaseChunk;
+    const int64_t chunk = B < span ? B : span;
     if (p->ws_samples < chunk) {
         CU(cudaStreamSynchronize(st));
         cudaFree(p->d_zc);
@@ -1303,11 +1306,17 @@ extern "C" int tebscat_phase_forward(tebscat_phase_plan* p, const float* x_dev, 
         const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
         const float* xb = x_dev + b0 * x_stride;
         mark();
-        if (ch_i == ch_j) {
-            if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_i * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_CART | Z_POLAR, st)) return rc;
-        } else {
-            if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_i * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_POLAR, st)) return rc;
-            if (int rc = launch_stage_a(p->stage_a, xb + (size_t)ch_j * d.N, x_stride, nb, p->d_zc, p->d_zp, Z_CART, st)) return rc;
+        for (int64_t a0 = 0; a0 < nb; a0 += kPhaseChunk) {            // stage A: two jobs per SM and launch
+            const int64_t na = (nb - a0 < kPhaseChunk) ? (nb - a0) : kPhaseChunk;
+            const float* xa = xb + a0 * x_stride;
+            float2* zc = p->d_zc + (size_t)a0 * per_sample;
+            float2* zp = p->d_zp + (size_t)a0 * per_sample;
+            if (ch_i == ch_j) {
+                if (int rc = launch_stage_a(p->stage_a, xa + (size_t)ch_i * d.N, x_stride, na, zc, zp, Z_CART | Z_POLAR, st)) return rc;
+            } else {
+                if (int rc = launch_stage_a(p->stage_a, xa + (size_t)ch_i * d.N, x_stride, na, zc, zp, Z_POLAR, st)) return rc;
+                if (int rc = launch_stage_a(p->stage_a, xa + (size_t)ch_j * d.N, x_stride, na, zc, zp, Z_CART, st)) return rc;
+            }
         }
         mark();
         PairParams pp;
