@@ -23,3 +23,9 @@ torch.cuda.synchronize()
 PY
 ncu --set full --clock-control none --import-source on -k regex:phase_pair_tc_kernel -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_phase_tc python /tmp/ncu_phase.py > gpurun_out/ncu_${TAG}_phase.log 2>&1
 tail -2 gpurun_out/ncu_${TAG}_phase.log
+# the evidence behind the phase kernel's structure: issue rate of tcgen05.mma per issuing thread, MMAs of several
+# threads into one accumulator, and the timeline of one CTA (library variant built with -DTEBSCAT_TC_TRACE)
+[ -x build/umma_rate ] && ./build/umma_rate > gpurun_out/${TAG}_umma_rate.txt 2>&1
+[ -x build/umma_shared_acc ] && ./build/umma_shared_acc > gpurun_out/${TAG}_umma_shared_acc.txt 2>&1
+[ -f build/variants/lib_trace.so ] && TEBSCAT_LIB=$PWD/build/variants/lib_trace.so python tools/tc_trace.py > gpurun_out/${TAG}_phase_tc_timeline.txt 2>&1
+python tools/time_phase_stages.py 8192 > gpurun_out/${TAG}_phase_stages.txt 2>&1

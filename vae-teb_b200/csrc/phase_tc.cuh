@@ -8,23 +8,26 @@
 // B'[2t, n] = Re G[t, n], B'[2t+1, n] = Im G[t, n], in 3xTF32 (fp32-class accuracy): A' = Ah + Al, B' = Bh + Bl,
 // out ~= Ah Bh + Al Bh + Ah Bl.
 //
-// One CTA = 128 rows x 80 columns, one CTA per SM, 21 warps:
+// One CTA = 128 rows x 80 columns, one CTA per SM, 27 warps:
 //   * 16 PRODUCER warps in four groups compute the rows' products where they are consumed -- group j owns the slabs
-//     i = j (mod 4), a thread one row (= one TMEM lane) of such a slab of 16 samples -- split them into TF32 head and
-//     tail and write them straight into TENSOR MEMORY with tcgen05.st: the A' operand never touches shared memory
-//     (tcgen05.mma with A from TMEM).  The group also copies its slab of B' (pre-split on the host side of the plan,
-//     K-major, 128-byte swizzle) into shared memory with cp.async;
-//   * ONE thread of the MMA warp issues tcgen05.mma.kind::tf32 (M = 128, N = 80, K = 8): 12 per slab, accumulating in
-//     TMEM; tcgen05.commit releases the slab's stage and hands finished accumulators to
-//   * 4 EPILOGUE warps, which drain the head-product accumulator every kTcDrain slabs with tcgen05.ld and add it to
-//     running sums in fp32 registers (a tensor-core accumulator that runs over all K = 2N = 9600 would carry its
-//     truncation bias, see the mma.sync kernel), double-buffered so the drain overlaps the next group's MMAs.  The
-//     correction products Al Bh + Ah Bl go to an accumulator of their own that is read once at the end: they are
-//     2^-11 of the result, so their own truncation error is irrelevant, and keeping them out of the head accumulator
-//     cuts the accumulations between two fp32 adds from 24 to 8 (measured: round-2 parity report in profiles/).
-// mbarriers: full[s] (producers -> MMA), empty[s] (MMA -> producers), acc_full[a] (MMA -> epilogue),
-// acc_empty[a] (epilogue -> MMA).  TMEM (512 columns): head-product accumulators at 0 and 80, the accumulator of the
-// correction products at 160, A' stages from 256.
+//     i = j (mod 4) and the stage j, a thread one row (= one TMEM lane) of such a slab of 16 samples -- split them
+//     into TF32 head and tail and write them straight into TENSOR MEMORY with tcgen05.st: the A' operand never touches
+//     shared memory (tcgen05.mma with A from TMEM).  The slab's inputs come through shared memory, every DISTINCT
+//     128-byte line once (cp.async); its slab of B' (pre-split on the host side of the plan and stored as the
+//     shared-memory image of the stage: K-major, 128-byte swizzle) with ONE bulk copy on the slab's barrier;
+//   * THREE MMA-issuing threads (tcgen05.mma.kind::tf32, M = 128, N = 80, K = 8): one thread issues an MMA of this
+//     size every ~98 cycles whatever N <= 160 is, threads issue independently (tools/micro/umma_rate.cu), and a
+//     single issuer was the limit of the whole kernel (tools/tc_trace.py).  Issuers 0 / 1: Ah Bh of the drain
+//     groups of their parity into their own head accumulator; issuer 2: Al Bh + Ah Bl of every slab into the
+//     correction accumulator.  One writer per accumulator: the output does not depend on how the threads interleave;
+//   * 8 EPILOGUE warps (two per TMEM lane quarter, 40 columns each), which drain a head accumulator every kTcDrain
+//     slabs with tcgen05.ld, add it to running sums in fp32 registers (a tensor-core accumulator that runs over all
+//     K = 2N = 9600 would carry its truncation bias, see the mma.sync kernel) and zero it again, double-buffered so
+//     the drain overlaps the next group's MMAs.  The correction products are 2^-11 of the result, so their own
+//     truncation error is irrelevant: their accumulator is read once at the end.
+// mbarriers: full[s] (producers + bulk copy -> issuers), empty[s] (issuers -> producers), acc_full[a] (issuer a ->
+// epilogue), acc_empty[a] (epilogue -> issuer a), tail_done (issuer 2 -> epilogue).  TMEM (512 columns, all in use):
+// head accumulators at 0 and 160, the correction accumulator at 80, A' stages (head 32 + tail 32 columns) from 256.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -48,9 +51,9 @@ constexpr int kTcStageBytes = 2 * kTcBTile;                      // head + tail
 constexpr int kTcInBytes = 2 * kTcRows * 128;                    // one group's input slab: 128 lines of (|z|, theta) + 128 of (re, im)
 constexpr int kTcOffBars = kTcStages * kTcStageBytes + kTcGroups * kTcInBytes;
 constexpr size_t kTcSmem = 1024 + (size_t)kTcOffBars + 256 + 4 * kTcRows * sizeof(int32_t) + 64;
-// TMEM columns: the two head-product accumulators (Ah Bh, drained every kTcDrain slabs), ONE accumulator of the
-// correction products (Al Bh + Ah Bl: 2^-11 of the head products, so its truncation error stays below 1e-7 of the
-// result even over the whole contraction -- it is read once, at the end), and the A' stages (head at kTcA0 + 64 s, tail + 32)
+// TMEM columns: head accumulator 0, the accumulator of the correction products (Al Bh + Ah Bl: 2^-11 of the head
+// products, so its truncation error stays below 1e-7 of the result even over the whole contraction -- it is read
+// once, at the end), head accumulator 1, and the A' stages (head at kTcA0 + 64 s, tail + 32)
 constexpr uint32_t kTcAcc0 = 0, kTcAccS = 80, kTcAcc1 = 160, kTcA0 = 256;
 
 #ifdef TEBSCAT_TC_TRACE
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     const uint32_t raw = tc_smem_u32(tc_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = tc_raw + (base - raw);
-    const uint32_t bars = base + kTcOffBars;                         // full[4], empty[4], acc_full[2], acc_empty[2]
+    const uint32_t bars = base + kTcOffBars;                         // full[4], empty[4], acc_full[2], acc_empty[2], tail_done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kTcOffBars + 128);
     int32_t* s_off = reinterpret_cast<int32_t*>(sm + kTcOffBars + 256);       // [2][128]: first sample of the rows' inputs (float2 units)
     auto full = [&](int s) { return bars + 8u * s; };
