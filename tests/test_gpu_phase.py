@@ -27,7 +27,7 @@ from oracle.phase_oracle import PhaseOracle
 pytestmark = pytest.mark.gpu
 
 CFG = {'H': (6, 8, 64, 4800, 2), 'Hr': (6, 8, 64, 4800, 2), 'P': (11, 4, 16, 5760, 1), 'S': (4, 4, 16, 1000, 2),
-       'L': (6, 4, 64, 9000, 2)}
+       'L': (6, 4, 64, 9000, 2), 'F70': (6, 12, 64, 2000, 2), 'Sodd': (4, 4, 16, 999, 2)}
 FORMS = {'tcgen05': ('0', 'tc'), 'mma.sync': ('0', 'sync'), 'transform': ('1', 'tc')}
 _mods = {}
 
@@ -423,3 +423,27 @@ def test_border_modes_at_a_padded_length_of_2_14(border):
     check(cross, o, x.numpy(), 'cross', 'Np=2^14, border ' + border, randn_rows=[0, 1])
     within = m(x.cuda(), compute_phase=True, phase_channels=[1])['phase_corr'].cpu().numpy()
     check(within, o, x.numpy()[:, 1], 'within', 'Np=2^14, border ' + border, randn_rows=[0, 1])
+
+
+@pytest.mark.parametrize('name', ['S', 'Sodd', 'F70'])
+def test_rows_do_not_depend_on_the_tile_they_land_in(name, monkeypatch):
+    """The tcgen05 kernel copies every distinct input line of a 128-row tile once and lets the rows point at their
+    lines (run-length slots on the 'i' side; on the 'j' side a direct sample x filter map while two samples' filters fit
+    128 slots -- F70 has 70 filters, so tiles that straddle samples take the per-row map; Sodd has rows that start on
+    8-byte boundaries only).  Pair subsets, the auto-correlation pairs and a longer batch move every row to another
+    tile, another slot and another neighbourhood: the results must be the same bits (one writer per accumulator)."""
+    m = module_of(name, 'tcgen05', monkeypatch)
+    N = CFG[name][3]
+    x = torch.randn(7, 2, N, device='cuda', generator=torch.Generator(device='cuda').manual_seed(31))
+    full = m(x, compute_phase=False, compute_cross_phase=True)['cross_phase_corr']
+    P = full.shape[1]
+    same = m(x, compute_phase=False, compute_cross_phase=True, cross_phase_same_pairs_only=True)['cross_phase_corr']
+    assert torch.equal(same, full[:, m.autoc_idx.to(full.device)])
+    rng = np.random.RandomState(5)
+    for k in (1, 7, 44, min(200, P)):
+        mask = np.zeros(P, bool)
+        mask[rng.choice(P, k, replace=False)] = True
+        part = m(x, compute_phase=False, compute_cross_phase=True, phase_pairs=torch.from_numpy(mask))['cross_phase_corr']
+        assert torch.equal(part, full[:, torch.from_numpy(mask).to(full.device)]), k
+    again = m(x.repeat(3, 1, 1)[2:], compute_phase=False, compute_cross_phase=True)['cross_phase_corr']
+    assert torch.equal(again[5:12], full)
