@@ -22,7 +22,7 @@
 //     correction accumulator.  One writer per accumulator: the output does not depend on how the threads interleave;
 //   * 8 EPILOGUE warps (two per TMEM lane quarter, 40 columns each), which drain a head accumulator every kTcDrain
 //     slabs with tcgen05.ld, add it to running sums in fp32 registers (a tensor-core accumulator that runs over all
-//     K = 2N = 9600 would carry its truncation bias, see the mma.sync kernel) and zero it again, double-buffered so
+//     K = 2N = 9600 would carry its truncation bias, see the mma.sync kernel), double-buffered so
 //     the drain overlaps the next group's MMAs.  The correction products are 2^-11 of the result, so their own
 //     truncation error is irrelevant: their accumulator is read once at the end.
 // mbarriers: full[s] (producers + bulk copy -> issuers), empty[s] (issuers -> producers), acc_full[a] (issuer a ->
@@ -156,17 +156,6 @@ __device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, float (&v)[8]) {  
                  : "r"(taddr)
                  : "memory");
 }
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // K-major, 128-byte swizzle: rows of 128 bytes, groups of 8 rows 1024 bytes apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t tc_b_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -284,19 +273,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // every MMA accumulates (one instruction covers a head accumulator AND the correction accumulator, see below):
-    // the three accumulators start at zero, and the epilogue zeroes a head accumulator again after draining it
-    if (warp < kTcEpiWarps) {
-        const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const uint32_t t0 = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (warp >> 2) * (3 * kTcCols / 2);
-#pragma unroll
-        for (int j = 0; j < 3 * kTcCols / 16; ++j) tc_st8(t0 + 8 * j, zero);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
     const long long row0 = (long long)blockIdx.x * kTcRows;
     const int col0 = blockIdx.y * kTcCols;
     const int n_slabs = p.n_slabs;
@@ -320,21 +296,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
 #pragma unroll
             for (int j = 0; j < kTcEpiCols / 8; ++j) tc_ld8_nowait(taddr + 8 * j, *reinterpret_cast<float (*)[8]>(&v[8 * j]));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            {
-                const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-                for (int j = 0; j < kTcEpiCols / 8; ++j) tc_st8(taddr + 8 * j, zero);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc_mbar_arrive(acc_empty(a));                     // the accumulator is free (and zero) before the adds
+            if (lane == 0) tc_mbar_arrive(acc_empty(a));                     // the accumulator is free before the adds
             if (warp == 0) TC_TRACE(5, g, 2);
 #pragma unroll
             for (int i = 0; i < kTcEpiCols; ++i) total[i] += v[i];
         }
-        // the correction products: head(A') tail(B') is complete with the last group's commit (a commit covers every
-        // earlier MMA of its thread), tail(A') head(B') when the second issuing thread says so
+        // the correction products are complete when the third issuing thread says so
         tc_mbar_wait_relaxed(tail_done, 0, 1000);
         tc_fence_after();
         {
@@ -384,7 +353,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                     const uint32_t a_hi = tmem + kTcA0 + 64 * s;
                     const uint32_t b_hi = base + s * kTcStageBytes;
 #pragma unroll
-                    for (int k = 0; k < kTcK / 8; ++k) tc_mma_ts(d, a_hi + 8 * k, tc_b_desc(b_hi + 32 * k), kTcIdesc, 1u);
+                    for (int k = 0; k < kTcK / 8; ++k)                   // the first MMA of a drain group overwrites
+                        tc_mma_ts(d, a_hi + 8 * k, tc_b_desc(b_hi + 32 * k), kTcIdesc, (i == g * kTcDrain && k == 0) ? 0u : 1u);
                     tc_commit(empty(s));                                      // the stage is free once the MMAs of both kinds retire
                     if (m == 0) TC_TRACE(4, g, 3 + 2 * (i - g * kTcDrain));
                 }
@@ -401,7 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                 const uint32_t b_hi = base + s * kTcStageBytes, b_lo = b_hi + kTcBTile;
 #pragma unroll
                 for (int k = 0; k < kTcK / 8; ++k) {
-                    tc_mma_ts(tmem + kTcAccS, a_lo + 8 * k, tc_b_desc(b_hi + 32 * k), kTcIdesc, 1u);
+                    tc_mma_ts(tmem + kTcAccS, a_lo + 8 * k, tc_b_desc(b_hi + 32 * k), kTcIdesc, (i == 0 && k == 0) ? 0u : 1u);
                     tc_mma_ts(tmem + kTcAccS, a_hi + 8 * k, tc_b_desc(b_lo + 32 * k), kTcIdesc, 1u);
                 }
                 tc_commit(empty(s));
