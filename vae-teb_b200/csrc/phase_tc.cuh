@@ -169,13 +169,15 @@ __device__ __forceinline__ uint64_t tc_b_desc(uint32_t smem_addr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 80
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcCols >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
 
-// TF32 head and tail of v: head = v rounded to the top 19 bits (round half away from zero, as an integer add on the
-// bit pattern), tail = v - head (exact, |tail| <= 2^-12 |v|), of which the tensor core reads the top 19 bits: the
-// dropped tail bits are below 2^-23 |v| and the product of the two tails (the term 3xTF32 leaves out) below
-// 2^-24 |v b| -- three instructions per value on the ALU / FMA pipes (cvt.rna.tf32.f32 would occupy the 16-lane
-// conversion unit that the sine and cosine of every product already use).  B' is split with rounding on the host.
+// TF32 head and tail of v: head = the top 19 bits of v (what the tensor core reads of an fp32 container anyway), tail =
+// v - head (exact, |tail| < 2^-10 |v|), of which the tensor core again reads the top 19 bits: the dropped tail bits are
+// below 2^-23 |v| and the product of the two tails (the term 3xTF32 leaves out) below 2^-21 |v b| -- two instructions
+// per value on the ALU / FMA pipes (cvt.rna.tf32.f32 would occupy the 16-lane conversion unit that the sine and cosine
+// of every product already use).  Rounding the head instead (one more integer add) was tried with the separate
+// correction accumulator in place: same error (worst err / bound 0.69 both ways), 3 % slower.  B' is split with
+// rounding on the host.
 __device__ __forceinline__ void tc_split(float v, uint32_t& hi, uint32_t& lo) {
-    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+    hi = __float_as_uint(v) & 0xffffe000u;
     lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
