@@ -180,6 +180,14 @@ __device__ __forceinline__ void tc_split(float v, uint32_t& hi, uint32_t& lo) {
     hi = __float_as_uint(v) & 0xffffe000u;
     lo = __float_as_uint(v - __uint_as_float(hi));
 }
+// the same for the two halves of a product (re, -im): one packed subtraction for both tails
+__device__ __forceinline__ void tc_split2(float2 c, uint32_t& hi0, uint32_t& hi1, uint32_t& lo0, uint32_t& lo1) {
+    hi0 = __float_as_uint(c.x) & 0xffffe000u;
+    hi1 = (__float_as_uint(c.y) & 0xffffe000u) ^ 0x80000000u;               // head of -c.y
+    const float2 t = csub(make_float2(c.x, -c.y), make_float2(__uint_as_float(hi0), __uint_as_float(hi1)));
+    lo0 = __float_as_uint(t.x);
+    lo1 = __float_as_uint(t.y);
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const PairTcParams p) {
     extern __shared__ uint8_t tc_raw[];
@@ -489,8 +497,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phase_pair_tc_kernel(const Pair
                     const float4 a = zp2[j >> 1], b = zc2[j >> 1];
                     const float2 c = (j & 1) ? accelerated_product(make_float2(a.z, a.w), make_float2(b.z, b.w), pw)
                                              : accelerated_product(make_float2(a.x, a.y), make_float2(b.x, b.y), pw);
-                    tc_split(c.x, hi[2 * j], lo[2 * j]);
-                    tc_split(-c.y, hi[2 * j + 1], lo[2 * j + 1]);
+                    tc_split2(c, hi[2 * j], hi[2 * j + 1], lo[2 * j], lo[2 * j + 1]);
                 }
                 tc_st8(ta + 8 * ss, hi);
                 tc_st8(ta + 32 + 8 * ss, lo);

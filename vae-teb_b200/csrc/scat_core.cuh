@@ -851,8 +851,7 @@ TEB_D float2 accelerated_product(float2 pz, float2 zj, float power) {
 #else
     __sincosf(r, &sn, &cs);
 #endif
-    const float ar = pz.x * cs, ai = pz.x * sn;
-    return make_float2(fmaf(ar, zj.x, ai * zj.y), fmaf(ai, zj.x, -ar * zj.y));     // (ar + i ai) * conj(zj)
+    return cmulc(cmul_r(make_float2(cs, sn), pz.x), zj);     // |z| (cos + i sin) * conj(zj): three packed instructions
 }
 
 TEB_D void loadpair_task(float2* S, const SignalCtx& c, const Task& t, int lt) {
