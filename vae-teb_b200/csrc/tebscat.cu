@@ -1628,6 +1628,8 @@ __global__ void g_pad_load_kernel(const float* __restrict__ x, float2* __restric
 
 // One radix-R pass (R = 2^logr <= 16) across the R blocks of 8192 samples of every length-2^n transform:
 // forward = first decimation-in-frequency pass (natural -> R blocks, twiddled), inverse = last decimation-in-time pass.
+// The R values a thread owns go through the register DFTs of the step interpreter (scat_core.cuh: Dft<R, SGN>, the
+// same index maps as fft_butterfly); the only table reads are the R - 1 twiddles W_L^(i0 q).
 template <int LOGR>
 __global__ void g_radix_kernel(float2* __restrict__ buf, long long n_transforms, int n, int inverse, const float2* __restrict__ tw) {
     constexpr int R = 1 << LOGR;
@@ -1637,53 +1639,29 @@ __global__ void g_radix_kernel(float2* __restrict__ buf, long long n_transforms,
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long s = e >> logm;
         const int i0 = (int)(e - (s << logm));
-        float2* base = buf + s * L;
-        float2 v[R], y[R];
+        float2* base = buf + s * L + i0;
+        float2 v[R];
         if (!inverse) {
 #pragma unroll
-            for (int j = 0; j < R; ++j) v[j] = base[i0 + ((long long)j << logm)];
+            for (int j = 0; j < R; ++j) v[j] = base[(long long)j << logm];
+            Dft<R, -1>::run(v);                              // register r holds X_q, q = qmap<R>(r)
 #pragma unroll
-            for (int q = 0; q < R; ++q) {                    // X_q = sum_j v_j W_R^(j q); y_q = X_q W_L^(i0 q)
-                float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const float2 w = __ldg(tw + ((((long long)j * q) & (R - 1)) << logm));      // W_R^(jq) = W_L^(jq L/R)
-                    acc.x += v[j].x * w.x - v[j].y * w.y;
-                    acc.y += v[j].x * w.y + v[j].y * w.x;
-                }
-                const float2 t = __ldg(tw + (long long)i0 * q);
-                y[q] = make_float2(acc.x * t.x - acc.y * t.y, acc.x * t.y + acc.y * t.x);
-            }
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                int rq = 0;
-#pragma unroll
-                for (int bb = 0; bb < LOGR; ++bb) rq |= ((q >> bb) & 1) << (LOGR - 1 - bb);
-                base[i0 + ((long long)rq << logm)] = y[q];
+            for (int r = 0; r < R; ++r) {
+                const int q = qmap<R>(r);
+                float2 y = v[r];
+                if (q != 0) y = cmul(y, __ldg(tw + (long long)i0 * q));                      // times W_L^(i0 q)
+                base[(long long)brev<LOGR>(q) << logm] = y;
             }
         } else {
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-                int rq = 0;
-#pragma unroll
-                for (int bb = 0; bb < LOGR; ++bb) rq |= ((q >> bb) & 1) << (LOGR - 1 - bb);
-                const float2 z = base[i0 + ((long long)rq << logm)];
-                const float2 t = __ldg(tw + (long long)i0 * q);                               // times conj(W_L^(i0 q))
-                v[q] = make_float2(z.x * t.x + z.y * t.y, z.y * t.x - z.x * t.y);
+                float2 z = base[(long long)brev<LOGR>(q) << logm];
+                if (q != 0) z = cmulc(z, __ldg(tw + (long long)i0 * q));                     // times conj(W_L^(i0 q))
+                v[q] = z;
             }
+            Dft<R, +1>::run(v);                              // register r holds x_j, j = qmap<R>(r)
 #pragma unroll
-            for (int j = 0; j < R; ++j) {                    // x_j = sum_q v_q conj(W_R^(j q))
-                float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int q = 0; q < R; ++q) {
-                    const float2 w = __ldg(tw + ((((long long)j * q) & (R - 1)) << logm));
-                    acc.x += v[q].x * w.x + v[q].y * w.y;
-                    acc.y += v[q].y * w.x - v[q].x * w.y;
-                }
-                y[j] = acc;
-            }
-#pragma unroll
-            for (int j = 0; j < R; ++j) base[i0 + ((long long)j << logm)] = y[j];
+            for (int r = 0; r < R; ++r) base[(long long)qmap<R>(r) << logm] = v[r];
         }
     }
 }
@@ -1748,42 +1726,24 @@ __global__ void g_radix_pair_kernel(float2* __restrict__ buf, long long n_transf
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long s = e >> logm;
         const int i0 = (int)(e - (s << logm));
-        float2* base = buf + s * L;
-        float2 v[R], tq[R];
-        float m[R];
+        float2* base = buf + s * L + i0;
+        float2 v[R], f[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-            int rq = 0;
-#pragma unroll
-            for (int bb = 0; bb < LOGR; ++bb) rq |= ((q >> bb) & 1) << (LOGR - 1 - bb);
-            const float2 z = base[i0 + ((long long)rq << logm)];
-            tq[q] = __ldg(tw + (long long)i0 * q);
-            v[q] = make_float2(z.x * tq[q].x + z.y * tq[q].y, z.y * tq[q].x - z.x * tq[q].y);
+            float2 z = base[(long long)brev<LOGR>(q) << logm];
+            if (q != 0) z = cmulc(z, __ldg(tw + (long long)i0 * q));
+            v[q] = z;
         }
+        Dft<R, +1>::run(v);                                  // last inverse pass: register r holds sample qmap<R>(r)
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-            float ax = 0.f, ay = 0.f;
+        for (int r = 0; r < R; ++r) f[qmap<R>(r)] = make_float2(sqrtf(fmaf(v[r].x, v[r].x, v[r].y * v[r].y)), 0.f);
+        Dft<R, -1>::run(f);                                  // first forward pass on the moduli
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const float2 w = __ldg(tw + ((((long long)j * q) & (R - 1)) << logm));
-                ax += v[q].x * w.x + v[q].y * w.y;
-                ay += v[q].y * w.x - v[q].x * w.y;
-            }
-            m[j] = sqrtf(fmaf(ax, ax, ay * ay));
-        }
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-            float ax = 0.f, ay = 0.f;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const float2 w = __ldg(tw + ((((long long)j * q) & (R - 1)) << logm));
-                ax += m[j] * w.x;
-                ay += m[j] * w.y;
-            }
-            int rq = 0;
-#pragma unroll
-            for (int bb = 0; bb < LOGR; ++bb) rq |= ((q >> bb) & 1) << (LOGR - 1 - bb);
-            base[i0 + ((long long)rq << logm)] = make_float2(ax * tq[q].x - ay * tq[q].y, ax * tq[q].y + ay * tq[q].x);
+        for (int r = 0; r < R; ++r) {
+            const int q = qmap<R>(r);
+            float2 y = f[r];
+            if (q != 0) y = cmul(y, __ldg(tw + (long long)i0 * q));
+            base[(long long)brev<LOGR>(q) << logm] = y;
         }
     }
 }
