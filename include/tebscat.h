@@ -120,6 +120,17 @@ typedef struct tebscat_epilogue {
 int tebscat_scat1d_forward_ex(const tebscat_plan* plan, const float* x_dev, int64_t B, float* out_dev,
                               const tebscat_epilogue* epilogue, void* stream);
 
+/* Fused subtrees of the large-support level (padded lengths 2^14 .. 2^17).  A plan whose schedule
+ * starts from global-source filter multiplies (OP_GMULFOLD, tebscat/schedule.py:build_hybrid_plans) runs every part of
+ * the cascade below a spectrum that is too long for one SM -- the signal's spectrum U0, or the spectrum of a
+ * first-order modulus of more than 8192 samples -- as ONE launch: psi multiply + periodisation straight from global
+ * memory, then iFFT -> modulus -> FFT -> second order -> phi leaves out of shared memory
+ * (kymatio/kymatio/scattering1d/core/scattering1d.py:300-364).  src_dev: [B][src_stride] complex64 (interleaved
+ * floats), bit-reversed bin order, 32-byte aligned; S_dev: [B, n_paths, n_out], only the plan's channels are written.
+ * Plans with such tasks are refused by the other forward entry points, and vice versa. */
+int tebscat_scat1d_forward_gsrc(const tebscat_plan* plan, const float* src_dev, int64_t src_stride_complex, int64_t B,
+                                float* S_dev, void* stream);
+
 /* Same transform with HOST buffers: pinned staging, chunked H2D / compute / D2H
  * overlap on the plan's own streams; returns when S_host is complete.  This is
  * the call the dataset builder makes per record

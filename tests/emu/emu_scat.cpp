@@ -13,13 +13,14 @@
 
 using namespace tebscat;
 
-extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths, int n_out,
-                                  int smem_complex, int n_tasks, int n_steps,
-                                  const float* arena, const int32_t* tasks, const int32_t* steps,
-                                  const int32_t* chan, const float* x, long long B, float* out,
-                                  float* zc, float* zp, int z_mode,
-                                  const float* ep_mean, const float* ep_std, const unsigned char* ep_mode,
-                                  float ep_log_eps, int ep_trim, int ep_time_major, int border) {
+static int emu_run(int N, int log2_Np, int pad_left, int n_paths, int n_out,
+                   int smem_complex, int n_tasks, int n_steps,
+                   const float* arena, const int32_t* tasks, const int32_t* steps,
+                   const int32_t* chan, const float* x, long long B, float* out,
+                   float* zc, float* zp, int z_mode,
+                   const float* ep_mean, const float* ep_std, const unsigned char* ep_mode,
+                   float ep_log_eps, int ep_trim, int ep_time_major, int border,
+                   const float* gsrc, long long gsrc_stride) {
     std::vector<float2> S((size_t)smem_complex);
     std::vector<float2> tw(kTwAP + kTwBP, make_float2(0.f, 0.f));
     const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
@@ -29,7 +30,8 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
         // poison shared memory so that reads of never-written slots show up as NaNs
         for (auto& z : S) z = make_float2(NAN, NAN);
         SignalCtx c;
-        c.x = x + b * N;
+        c.x = x ? x + b * N : nullptr;
+        c.gsrc = gsrc ? reinterpret_cast<const float2*>(gsrc) + b * gsrc_stride : nullptr;
         c.out = out + b * (long long)n_paths * (ep_mean ? n_out - 2 * ep_trim : n_out);
         c.ep_mean = ep_mean; c.ep_std = ep_std; c.ep_mode = ep_mode; c.ep_log_eps = ep_log_eps;
         c.ep_trim = ep_trim; c.ep_time_major = ep_time_major; c.n_paths = n_paths;
@@ -58,9 +60,29 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
                 memcpy(&t, tasks + kTaskInts * ti, sizeof(Task));
                 // multi-pass FFT tasks: pass by pass over all lanes (the kernel separates them by warp fences)
                 for (int k = 0; k < task_passes(t); ++k)
-                    for (int lt = 0; lt < t.nt; ++lt) exec_task(S.data(), tw.data(), tw.data() + kTwAP, arena, c, t, lt, k);
+                    for (int lt = 0; lt < t.nt; ++lt) exec_task<true>(S.data(), tw.data(), tw.data() + kTwAP, arena, c, t, lt, k);
             }
         }
     }
     return 0;
+}
+
+extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths, int n_out,
+                                  int smem_complex, int n_tasks, int n_steps,
+                                  const float* arena, const int32_t* tasks, const int32_t* steps,
+                                  const int32_t* chan, const float* x, long long B, float* out,
+                                  float* zc, float* zp, int z_mode,
+                                  const float* ep_mean, const float* ep_std, const unsigned char* ep_mode,
+                                  float ep_log_eps, int ep_trim, int ep_time_major, int border) {
+    return emu_run(N, log2_Np, pad_left, n_paths, n_out, smem_complex, n_tasks, n_steps, arena, tasks, steps, chan, x, B, out,
+                   zc, zp, z_mode, ep_mean, ep_std, ep_mode, ep_log_eps, ep_trim, ep_time_major, border, nullptr, 0);
+}
+
+// fused subtrees of the large-support level (tebscat_scat1d_forward_gsrc): job b reads the complex spectrum at
+// gsrc + b * gsrc_stride; only the plan's channels of `out` are written
+extern "C" int emu_scat1d_forward_gsrc(int n_paths, int n_out, int smem_complex, int n_tasks, int n_steps,
+                                       const float* arena, const int32_t* tasks, const int32_t* steps, const int32_t* chan,
+                                       const float* gsrc, long long gsrc_stride, long long B, float* out) {
+    return emu_run(1 << kLog2TwMax, kLog2TwMax, 0, n_paths, n_out, smem_complex, n_tasks, n_steps, arena, tasks, steps, chan,
+                   nullptr, B, out, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0.f, 0, 0, 0, gsrc, gsrc_stride);
 }

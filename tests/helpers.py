@@ -86,6 +86,29 @@ def emu_forward(plan, x, stage_a=False, epilogue=None):
     return out
 
 
+def emu_forward_gsrc(plan, src, out, chan_shift=0):
+    """Fused subtree of the large-support level through the host emulator: `src` (B, L) complex spectra in
+    bit-reversed order -> the plan's channels of `out` (B, n_paths, n_out) float32, shifted by `chan_shift`
+    channels (the C entry point takes the shifted pointer, tebscat_scat1d_forward_gsrc)."""
+    lib = ctypes.CDLL(EMU_PATH)
+    src = np.ascontiguousarray(src, np.complex64)
+    B, L = src.shape
+    assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (B, plan.n_paths, plan.n_out)
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    tasks = np.ascontiguousarray(plan.tasks, np.int32)
+    steps = np.ascontiguousarray(plan.steps, np.int32)
+    arena = np.ascontiguousarray(plan.arena, np.float32)
+    chan = np.ascontiguousarray(plan.chan, np.int32)
+    lib.emu_scat1d_forward_gsrc.argtypes = [ctypes.c_int] * 5 + [fp, ip, ip, ip, ctypes.c_void_p, ctypes.c_longlong,
+                                                                 ctypes.c_longlong, ctypes.c_void_p]
+    rc = lib.emu_scat1d_forward_gsrc(plan.n_paths, plan.n_out, plan.smem_complex, tasks.shape[0], steps.shape[0],
+                                     arena.ctypes.data_as(fp), tasks.ctypes.data_as(ip), steps.ctypes.data_as(ip),
+                                     chan.ctypes.data_as(ip), ctypes.c_void_p(src.ctypes.data), L, B,
+                                     ctypes.c_void_p(out.ctypes.data + 4 * chan_shift * plan.n_out))
+    assert rc == 0
+    return out
+
+
 def emu_pair_stage(pair_plan, zp_rows, zc_rows, powers):
     """Phase stage B in its transform form through the host emulator: rows of (|z_i|, theta_i) and
     (re, im) of z_j, one power per row -> (rows, n_out) low-passed real parts."""

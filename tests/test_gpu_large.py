@@ -113,3 +113,52 @@ def test_children_as_long_as_their_parent(graph, monkeypatch):
     ref = ScatteringOracle(J, N, Q, T, mo, oversampling=os_)(x.numpy())
     assert out.shape == ref.shape
     assert (np.linalg.norm(out - ref, axis=-1) / np.linalg.norm(ref, axis=-1)).max() < 1e-5
+
+
+@pytest.mark.parametrize('cfg', [(8, 8, 2 ** 13, 256, 2), (8, 8, 2 ** 14, 256, 2), (9, 2, 2 ** 14, 512, 1)])
+def test_fused_subtrees_agree_with_the_op_by_op_level(cfg, monkeypatch):
+    """above 2^13 the subtrees that fit one SM run on the fused kernel with a global source
+    (tebscat_scat1d_forward_gsrc).  Same result as the level's own kernels, every channel written exactly once."""
+    from tebscat import Scattering1D, large
+    J, Q, N, T, mo = cfg
+    x = torch.randn(5, N, generator=torch.Generator().manual_seed(11)).cuda()
+    S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    a = S(x)[0]
+    ldp = S._large_plan_for(0)[1]
+    assert ldp._first is not None and (mo == 1 or ldp._kids)
+    monkeypatch.setattr(large, 'HYBRID', False)
+    S2 = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    b = S2(x)[0]
+    assert S2._large_plan_for(0)[1]._first is None and not S2._large_plan_for(0)[1]._kids
+    torch.cuda.synchronize()
+    a, b = a.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64)
+    assert np.isfinite(a).all()
+    err = np.linalg.norm(a - b, axis=-1) / np.linalg.norm(b, axis=-1)
+    assert err.max() < 3e-6, float(err.max())
+    # a second call (the CUDA graph of the batch size) and another batch size give the same numbers
+    assert torch.equal(S(x)[0].cpu(), torch.from_numpy(a.astype(np.float32)))
+    assert torch.equal(S(x[:2])[0].cpu(), torch.from_numpy(a[:2].astype(np.float32)))
+
+
+def test_plans_with_a_global_source_only_run_through_their_entry_point():
+    from tebscat import Scattering1D, _lib
+    lib = _lib.load()
+    S = Scattering1D(8, 2 ** 13, 8, T=256).cuda()
+    x = torch.randn(2, 2 ** 13).cuda()
+    out = S(x)[0]
+    ldp = S._large_plan_for(0)[1]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = ctypes.c_void_p
+    with pytest.raises(ValueError, match='global source'):
+        _lib.check(lib.tebscat_scat1d_forward(ldp._first.handle, vp(x.data_ptr()), 2, vp(out.data_ptr()), st))
+    src = torch.zeros(2 << 14, 2, device='cuda')
+    with pytest.raises(ValueError, match='stride'):
+        _lib.check(lib.tebscat_scat1d_forward_gsrc(ldp._first.handle, vp(src.data_ptr()), 1 << 13, 2, vp(out.data_ptr()), st))
+    with pytest.raises(ValueError, match='aligned'):
+        _lib.check(lib.tebscat_scat1d_forward_gsrc(ldp._first.handle, vp(src.data_ptr() + 8), 1 << 14, 1, vp(out.data_ptr()), st))
+    H = Scattering1D(6, 4800, 8, T=64).cuda()
+    H(torch.randn(1, 4800).cuda())
+    with pytest.raises(ValueError, match='no global-source task'):
+        _lib.check(lib.tebscat_scat1d_forward_gsrc(H._plan_for(0).handle, vp(src.data_ptr()), 1 << 14, 1, vp(out.data_ptr()), st))
+    # the library is still usable
+    assert torch.isfinite(S(x)[0]).all()

@@ -17,6 +17,7 @@ def wrap(name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); rc = f(*a); e1.record(); torch.cuda.synchronize()
         key = name.replace('tebscat_large_', '')
+        if name == 'tebscat_scat1d_forward_gsrc': key = 'fused subtrees (source 2^%d)' % (int(a[2]).bit_length() - 1)
         if key in ('fft', 'pair'): key += '(2^%d)' % a[3]
         if key == 'mulfold': key += '(src 2^%d, k 2^%d)' % (a[5], a[6])
         acc[key] += e0.elapsed_time(e1); cnt[key] += 1
@@ -28,7 +29,7 @@ for n in dir(lib): pass
 dp = list(S._lplans.values())[0]
 class P:
     def __getattr__(self, n):
-        return wrap(n) if n.startswith('tebscat_large_') else getattr(lib, n)
+        return wrap(n) if n.startswith('tebscat_large_') or n == 'tebscat_scat1d_forward_gsrc' else getattr(lib, n)
 dp._lib = P()
 out = torch.empty(B, dp.plan.n_paths, dp.plan.n_out, device='cuda')
 dp._run(x, out); torch.cuda.synchronize()

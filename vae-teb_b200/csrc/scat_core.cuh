@@ -64,8 +64,11 @@ enum : int32_t {
     OP_LOADC = 10,   // large-support level: a=dst b=slots: complex tile of the job's global buffer -> shared memory
     OP_STOREC = 11,  //                      a=src b=slots: and back
     OP_STOREU = 9,   // average=False: a=src c=first index d=count e=offset in the output row: the modulus itself
-    OP_MULFOLD2 = 7  // like MULFOLD with k >= 1 on a PACKED source (spectrum of u_a + i u_b): a=src b=log2Lsrc c=log2k
+    OP_MULFOLD2 = 7, // like MULFOLD with k >= 1 on a PACKED source (spectrum of u_a + i u_b): a=src b=log2Lsrc c=log2k
                      // d=dst of the a-child e=filter offset f=chunk mask g=dst of the b-child h=log2 chunk width
+    OP_GMULFOLD = 12 // MULFOLD whose SOURCE is a spectrum in global memory (SignalCtx::gsrc + a, up to 2^17 bins, bit-reversed
+                     // order, unswizzled): the subtrees of <= 8192 samples under a longer parent run on the fused cascade
+                     // (DESIGN 6.1).  Fields as MULFOLD.  Only the kernel variant built with GSRC executes it.
 };
 enum : int32_t { Z_CART = 1, Z_POLAR = 2 };
 // FFT_PACK (with FFT_INV | FFT_FUSE_FWD): the moduli of two transforms -- block i at `a` and block i
@@ -111,6 +114,8 @@ struct SignalCtx {
     // padding rule of OP_LOAD / OP_LOADPAIR: the scattering transform always reflects (torch_backend.py:50-78);
     // the phase module's _pad_signal (kymatio_phase_scattering.py:162-173) also offers 'constant' and 'circular'
     int32_t border;
+    // OP_GMULFOLD: this job's source spectrum in global memory (null unless the kernel variant with GSRC runs)
+    const float2* gsrc;
 };
 enum : int32_t { EP_NONE = 0, EP_LOG = 1, EP_ASINH = 2 };
 enum : int32_t { BORDER_REFLECT = 0, BORDER_CONSTANT = 1, BORDER_CIRCULAR = 2 };
@@ -663,6 +668,114 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
     }
 }
 
+// Four consecutive complex bins of a global spectrum (32-byte aligned: two 128-bit loads through the read-only path).
+TEB_D void gload4(const float2* g, float2 (&z)[4]) {
+#ifdef TEBSCAT_HOST_EMU
+    z[0] = g[0]; z[1] = g[1]; z[2] = g[2]; z[3] = g[3];
+#else
+    const float4 lo = TEB_LDG(reinterpret_cast<const float4*>(g)), hi = TEB_LDG(reinterpret_cast<const float4*>(g) + 1);
+    z[0] = make_float2(lo.x, lo.y); z[1] = make_float2(lo.z, lo.w);
+    z[2] = make_float2(hi.x, hi.y); z[3] = make_float2(hi.z, hi.w);
+#endif
+}
+
+// MULFOLD with the source spectrum in GLOBAL memory (large-support level): the parent -- the signal's
+// spectrum U0, or the spectrum of a first-order modulus of more than 8192 samples -- was produced by the level's
+// own kernels; everything below it that fits one SM runs here.  Same arithmetic as mulfold_task (same products, same
+// order); every trip has its filter AND source loads in flight before the first use (one trip to L2 / HBM).
+TEB_D void gmulfold_task(float2* S, const float* __restrict__ arena, const SignalCtx& c, const Task& t, int lt) {
+    const int logk = t.c;
+    const float scale = ldexpf(1.0f, -(t.op >> 8));
+    const float* f = arena + t.e;
+    const float2* G = c.gsrc + t.a;
+    if (logk >= 2) {
+        const int n_dst = 1 << (t.b - logk);
+        const unsigned mask = (unsigned)t.f;
+        const int logcw = t.h;
+        const int nch = __popc(mask) << (logcw - 2);
+        const float2 zero = make_float2(0.f, 0.f);
+        for (int m0 = lt; m0 < n_dst; m0 += 4 * t.nt) {
+            float2 acc[4] = {zero, zero, zero, zero};
+            unsigned rest = mask;
+            int cc = 0;
+            while (rest) {
+                const int i_chunk = (TEB_FFS(rest) - 1) << logcw;
+                rest &= rest - 1;
+                for (int sub = 0; sub < (1 << (logcw - 2)); ++sub, ++cc) {
+                    const int i = i_chunk + (sub << 2);
+                    float4 g[4];
+                    float2 z[4][4];
+                    TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                        const int m = m0 + j * t.nt;
+                        if (m < n_dst) {
+                            g[j] = TEB_LDG(reinterpret_cast<const float4*>(f) + m * nch + cc);
+                            gload4(G + ((long long)m << logk) + i, z[j]);
+                        } else {
+                            g[j] = float4{0.f, 0.f, 0.f, 0.f};
+                            z[j][0] = z[j][1] = z[j][2] = z[j][3] = zero;
+                        }
+                    }
+                    TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                        acc[j] = cfma_r(z[j][0], g[j].x, acc[j]);
+                        acc[j] = cfma_r(z[j][1], g[j].y, acc[j]);
+                        acc[j] = cfma_r(z[j][2], g[j].z, acc[j]);
+                        acc[j] = cfma_r(z[j][3], g[j].w, acc[j]);
+                    }
+                }
+            }
+            TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                const int m = m0 + j * t.nt;
+                if (m < n_dst) S[swz(t.d + m)] = cmul_r(acc[j], scale);
+            }
+        }
+    } else {
+        const int n_items = 1 << (t.b - 2);                    // 4 source bins per item
+        for (int it0 = lt; it0 < n_items; it0 += 4 * t.nt) {
+            float4 gg[4];
+            float2 zz[4][4];
+            TEB_UNROLL for (int j = 0; j < 4; ++j) {           // four items in flight per thread
+                const int it = it0 + j * t.nt;
+                if (it < n_items) {
+                    gg[j] = TEB_LDG(reinterpret_cast<const float4*>(f + 4 * it));
+                    gload4(G + 4 * it, zz[j]);
+                } else {
+                    gg[j] = float4{0.f, 0.f, 0.f, 0.f};
+                    zz[j][0] = zz[j][1] = zz[j][2] = zz[j][3] = make_float2(0.f, 0.f);
+                }
+            }
+            TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                const int it = it0 + j * t.nt;
+                if (it >= n_items) continue;
+                const float4 g = gg[j];
+                const float2 z0 = zz[j][0], z1 = zz[j][1], z2 = zz[j][2], z3 = zz[j][3];
+                if (logk == 0) {
+                    const int o = swz(t.d + 4 * it);
+                    float2 w0 = cmul_r(z0, g.x * scale);
+                    float2 w1 = cmul_r(z1, g.y * scale);
+                    float2 w2 = cmul_r(z2, g.z * scale);
+                    float2 w3 = cmul_r(z3, g.w * scale);
+                    if (t.g == 1) {                            // first (unit-stride) inverse pass, as in mulfold_task
+                        dft2<+1>(w0, w1);
+                        dft2<+1>(w2, w3);
+                    } else if (t.g == 2) {
+                        float2 a0 = w0, a1 = w2, a2 = w1, a3 = w3;
+                        dft4<+1>(a0, a1, a2, a3);
+                        w0 = a0; w1 = a1; w2 = a2; w3 = a3;
+                    }
+                    S[o] = w0;
+                    S[o + 1] = w1;
+                    S[o + 2] = w2;
+                    S[o + 3] = w3;
+                } else {
+                    const int o = swz(t.d + 2 * it);
+                    S[o] = cmul_r(cfma_r(z0, g.x, cmul_r(z1, g.y)), scale);
+                    S[o + 1] = cmul_r(cfma_r(z2, g.z, cmul_r(z3, g.w)), scale);
+                }
+            }
+        }
+    }
+}
+
 // Slot of bin -k in a bit-reversed spectrum when p is the slot of bin k: the highest set bit of p
 // stays, every bit below it flips (the mirror image inside p's dyadic block).
 TEB_D int mirror_slot(int p) { return p ? (p ^ ((1 << (31 - TEB_CLZ(p))) - 1)) : 0; }
@@ -963,6 +1076,9 @@ TEB_D void storez_task(const float2* S, const SignalCtx& c, const Task& t, int l
 
 // `pass` selects the pass of a multi-pass FFT task; the kernel runs them back to back (fft_task), the host
 // emulator -- which executes the lanes of a task one after another -- runs pass by pass.
+// GSRC: the kernel variant of the large-support level's fused subtrees (OP_GMULFOLD); the other variants -- the
+// headline kernel among them -- do not contain the op.
+template <bool GSRC = false>
 TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const float* __restrict__ arena,
                      const SignalCtx& c, const Task& t, int lt, int pass = -1) {
     switch (t.op & 0xff) {
@@ -983,6 +1099,7 @@ TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const floa
         }
         case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
         case OP_MULFOLD2: mulfold2_task(S, arena, t, lt); break;
+        case OP_GMULFOLD: if (GSRC) gmulfold_task(S, arena, c, t, lt); break;
         case OP_LOADPAIR: loadpair_task(S, c, t, lt); break;
         case OP_STOREU: storeu_task(S, c, t, lt); break;
         case OP_LOADC: loadc_task(S, c, t, lt); break;

@@ -98,6 +98,10 @@ struct KParams {
     float2* gbuf;
     long long g_total;
     int32_t g_slots;
+    // fused subtrees of the large-support level (OP_GMULFOLD, kernel variant GSRC): job b reads the spectrum at
+    // gsrc + b * gsrc_stride (complex elements)
+    const float2* gsrc;
+    long long gsrc_stride;
 };
 
 constexpr int kThreads = 512;
@@ -118,7 +122,7 @@ __device__ __forceinline__ void fetch_record(int32_t* dst_smem, const int32_t* s
 __device__ __forceinline__ void fetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void fetch_wait_all_but_2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 
-template <bool PROF>
+template <bool PROF, bool GSRC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ out, long long B) {
     extern __shared__ __align__(16) float2 smem[];
@@ -185,6 +189,7 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
             c.log2_Np = p.log2_Np;
             c.border = p.border;
             c.n_out = p.n_out;
+            if (GSRC) c.gsrc = p.gsrc + b * p.gsrc_stride;
         }
         __syncthreads();             // (the last step of the previous signal ended in a barrier too)
         const bool prof = PROF && blockIdx.x == 0 && b == blockIdx.x && tid == 0;
@@ -225,7 +230,7 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
 #ifdef TEBSCAT_PROF_BFLY
                 if (tid == 0 && blockIdx.x == 0) tebscat::g_bfly_dbg[7] = clock64();
 #endif
-                exec_task(S, twA, twB, p.arena, c, t, tid - t.t0);
+                exec_task<GSRC>(S, twA, twB, p.arena, c, t, tid - t.t0);
 #ifdef TEBSCAT_PROF_PHASES
                 if (prof) p.prof[n_steps + 2 + 3 * s] = clock64();
 #endif
@@ -267,12 +272,14 @@ struct tebscat_plan {
     int32_t* d_chan = nullptr;
     float* d_win = nullptr;
     KParams kp;
+    int64_t gsrc_extent = 0;     // > 0: the schedule reads a global source spectrum of that many complex bins (OP_GMULFOLD)
     HostPipe pipe;
     std::mutex pipe_mu;
 };
 
 static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, const int32_t* steps,
-                             size_t n_floats, size_t n_chan) {
+                             size_t n_floats, size_t n_chan, int64_t* gsrc_extent = nullptr) {
+    if (gsrc_extent) *gsrc_extent = 0;
     const int cap = (int)(((int64_t)d.smem_complex * 16) / 17);   // logical slots (1 pad slot per 16)
     for (int s = 0; s < d.n_steps; ++s) {
         const int b = steps[2 * s], e = steps[2 * s + 1];
@@ -360,6 +367,27 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                 if ((size_t)t[7] + need > n_floats) return fail(TEBSCAT_EINVAL, "task %d: MULFOLD2 filter outside the arena", i);
                 break;
             }
+            case OP_GMULFOLD: {
+                // source in global memory (tebscat_scat1d_forward_gsrc): a = offset in complex bins, up to 2^17 bins
+                const int log_dst = t[4] - t[5];
+                if (t[3] < 0 || (t[3] & 3) || t[4] < 2 || t[4] > 17 || t[5] < 0 || t[5] > t[4] || log_dst > kLog2TwMax ||
+                    !fits(t[6] & ~15, (t[6] & 15) + ((int64_t)1 << log_dst)) || t[7] < 0 || (t[7] & 3) ||
+                    (t[5] == 0 && (t[6] & 3)) || (t[5] == 1 && (t[6] & 1)))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad GMULFOLD", i);
+                if (t[5] >= 2) {
+                    const int logcw = t[10], n_chunks = 1 << (t[5] - logcw);
+                    if (logcw < 2 || logcw > t[5] || n_chunks > 32 || (unsigned)t[8] == 0u ||
+                        (n_chunks < 32 && ((unsigned)t[8] >> n_chunks) != 0u))
+                        return fail(TEBSCAT_EINVAL, "task %d: bad GMULFOLD chunk mask", i);
+                }
+                const size_t need = t[5] >= 2 ? (((size_t)1 << log_dst) << t[10]) * __builtin_popcount((unsigned)t[8])
+                                              : ((size_t)1 << t[4]);
+                if ((size_t)t[7] + need > n_floats) return fail(TEBSCAT_EINVAL, "task %d: GMULFOLD filter outside the arena", i);
+                if (t[9] != 0 && (t[5] != 0 || t[9] < 0 || t[9] > 2))
+                    return fail(TEBSCAT_EINVAL, "task %d: a first inverse pass can only be fused into a k=1 GMULFOLD", i);
+                if (gsrc_extent && *gsrc_extent < (int64_t)t[3] + ((int64_t)1 << t[4])) *gsrc_extent = (int64_t)t[3] + ((int64_t)1 << t[4]);
+                break;
+            }
             case OP_STOREB:
                 if (t[4] < 1 || t[6] != d.n_out || t[5] < 0 || t[8] < 0 || t[8] > kLog2TwMax || t[5] + t[6] > (1 << t[8]) ||
                     !fits(t[3], (int64_t)t[4] << t[8]) || t[7] < 0 || 2 * ((size_t)t[7] + (size_t)t[4]) > n_chan)
@@ -417,7 +445,8 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     for (size_t i = 0; i < n_chan; ++i)
         if (chan[i] >= desc->n_paths || chan[i] < ((i & 1) ? -1 : 0))
             return fail(TEBSCAT_EINVAL, "channel table entry %zu out of range", i);
-    if (int rc = validate_schedule(*desc, tasks, steps, n_floats, n_chan)) return rc;
+    int64_t gsrc_extent = 0;
+    if (int rc = validate_schedule(*desc, tasks, steps, n_floats, n_chan, &gsrc_extent)) return rc;
 
     int n_dev = 0;
     CU(cudaGetDeviceCount(&n_dev));
@@ -431,6 +460,7 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     tebscat_plan* p = guard.get();
     p->desc = *desc;
     p->device = device;
+    p->gsrc_extent = gsrc_extent;
     p->n_sms = prop.multiProcessorCount;
     p->smem_bytes = ((size_t)desc->smem_complex + kTwAP + kTwBP) * sizeof(float2);
     if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
@@ -474,15 +504,19 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     CU(cudaMemcpy(p->d_arena, arena, n_floats * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     // the attribute belongs to the kernel, not to the plan: always allow the device maximum
-    cudaFuncAttributes fa0, fa1;
+    cudaFuncAttributes fa0, fa1, fa2;
     CU(cudaFuncGetAttributes(&fa0, scat1d_kernel<false>));
     CU(cudaFuncGetAttributes(&fa1, scat1d_kernel<true>));
+    CU(cudaFuncGetAttributes(&fa2, (scat1d_kernel<false, true>)));
+    CU(cudaFuncSetAttribute((scat1d_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(prop.sharedMemPerBlockOptin - fa2.sharedSizeBytes)));
     CU(cudaFuncSetAttribute(scat1d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(prop.sharedMemPerBlockOptin - fa0.sharedSizeBytes)));
     CU(cudaFuncSetAttribute(scat1d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(prop.sharedMemPerBlockOptin - fa1.sharedSizeBytes)));
     if (p->smem_bytes + fa0.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin ||
-        p->smem_bytes + fa1.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin)
+        p->smem_bytes + fa1.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin ||
+        p->smem_bytes + fa2.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin)
         return fail(TEBSCAT_EUNSUPPORTED, "schedule needs more shared memory than the device offers");   // guard frees the plan
 
     KParams& k = p->kp;
@@ -523,6 +557,8 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     k.gbuf = nullptr;
     k.g_total = 0;
     k.g_slots = 0;
+    k.gsrc = nullptr;
+    k.gsrc_stride = 0;
     *out = guard.release();
     return TEBSCAT_OK;
 }
@@ -667,6 +703,7 @@ extern "C" int tebscat_plan_set_window(tebscat_plan* p, const float* window_host
 }
 
 static int launch_scat1d(const tebscat_plan* p, const float* x, int64_t B, float* S, cudaStream_t st) {
+    if (p->gsrc_extent) return fail(TEBSCAT_EINVAL, "this plan reads a global source spectrum: use tebscat_scat1d_forward_gsrc");
     if (B == 0) return TEBSCAT_OK;
     const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
     scat1d_kernel<false><<<grid, p->desc.n_threads, p->smem_bytes, st>>>(p->kp, x, S, (long long)B);
@@ -683,6 +720,32 @@ extern "C" int tebscat_scat1d_forward(const tebscat_plan* p, const float* x_dev,
     return launch_scat1d(p, x_dev, B, S_dev, (cudaStream_t)stream);
 }
 
+/* Fused subtrees of the large-support level: the schedule's OP_GMULFOLD tasks read job b's source spectrum
+ * (complex64, bit-reversed bin order) at src_dev + b * src_stride complex elements; everything below runs out of
+ * shared memory like the cascade itself and the leaves land in S_dev [B, n_paths, n_out] at their channels. */
+extern "C" int tebscat_scat1d_forward_gsrc(const tebscat_plan* p, const float* src_dev, int64_t src_stride, int64_t B,
+                                           float* S_dev, void* stream) {
+    g_launches = 0;
+    if (!p || B < 0 || (B > 0 && (!src_dev || !S_dev))) return fail(TEBSCAT_EINVAL, "null argument");
+    if (!p->gsrc_extent) return fail(TEBSCAT_EINVAL, "this plan has no global-source task");
+    if (src_stride < p->gsrc_extent)
+        return fail(TEBSCAT_EINVAL, "source stride %lld below the %lld bins the schedule reads", (long long)src_stride,
+                    (long long)p->gsrc_extent);
+    if ((reinterpret_cast<uintptr_t>(src_dev) & 31) || (src_stride & 3))
+        return fail(TEBSCAT_EINVAL, "the source spectra must be 32-byte aligned");
+    if (B == 0) return TEBSCAT_OK;
+    ON_DEVICE(p->device);
+    KParams kp = p->kp;
+    kp.gsrc = reinterpret_cast<const float2*>(src_dev);
+    kp.gsrc_stride = src_stride;
+    const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
+    scat1d_kernel<false, true><<<grid, p->desc.n_threads, p->smem_bytes, (cudaStream_t)stream>>>(kp, nullptr, S_dev, (long long)B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TEBSCAT_ECUDA, "launch failed: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return TEBSCAT_OK;
+}
+
 extern "C" int tebscat_scat1d_forward_ex(const tebscat_plan* p, const float* x_dev, int64_t B, float* out_dev,
                                          const tebscat_epilogue* ep, void* stream) {
     g_launches = 0;
@@ -691,6 +754,7 @@ extern "C" int tebscat_scat1d_forward_ex(const tebscat_plan* p, const float* x_d
     if (!ep->mean_dev || !ep->std_dev || !ep->mode_dev) return fail(TEBSCAT_EINVAL, "epilogue: null statistics");
     if (ep->trim < 0 || 2 * ep->trim >= p->desc.n_out)
         return fail(TEBSCAT_EINVAL, "epilogue: trim %d leaves nothing of %d samples", ep->trim, p->desc.n_out);
+    if (p->gsrc_extent) return fail(TEBSCAT_EINVAL, "this plan reads a global source spectrum: use tebscat_scat1d_forward_gsrc");
     if (B == 0) return TEBSCAT_OK;
     ON_DEVICE(p->device);
     KParams kp = p->kp;

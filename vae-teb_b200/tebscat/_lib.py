@@ -75,6 +75,8 @@ def load():
     lib.tebscat_plan_destroy.argtypes = [vp]
     lib.tebscat_scat1d_forward.restype = ctypes.c_int
     lib.tebscat_scat1d_forward.argtypes = [vp, vp, ctypes.c_int64, vp, vp]
+    lib.tebscat_scat1d_forward_gsrc.restype = ctypes.c_int
+    lib.tebscat_scat1d_forward_gsrc.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int64, vp, vp]
     lib.tebscat_scat1d_forward_ex.restype = ctypes.c_int
     lib.tebscat_scat1d_forward_ex.argtypes = [vp, vp, ctypes.c_int64, vp, ctypes.POINTER(Epilogue), vp]
     lib.tebscat_scat1d_forward_host.restype = ctypes.c_int

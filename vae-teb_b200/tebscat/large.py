@@ -12,6 +12,7 @@ There is no CPU or torch fallback in here: torch only owns the buffers.
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -22,7 +23,10 @@ from . import schedule as sch
 
 LOG2_MAX = 17
 LEAF_FUSED_MAX_LOG2 = 10          # leaves of up to 1024 output-rate samples run as one launch (tebscat_large_leaf)
-FUSED_LEAVES = __import__('os').environ.get('TEBSCAT_FUSED_LEAVES', '1') != '0'
+FUSED_LEAVES = os.environ.get('TEBSCAT_FUSED_LEAVES', '1') != '0'
+# Above a padded length of 2^13 the subtrees that fit one SM run on the fused kernel with a global source
+# (schedule.build_hybrid_plans, tebscat_scat1d_forward_gsrc); TEBSCAT_HYBRID=0 keeps every op on this level (A/B)
+HYBRID = os.environ.get('TEBSCAT_HYBRID', '1') != '0'
 
 
 class _TilePlanOwner:
@@ -84,13 +88,13 @@ class LargePlan:
             if not p1.xi < 0.5 / (2 ** k1):
                 raise AssertionError('psi1 aliasing assertion of the reference violated')
             l1 = n - k1
-            entry = dict(ch=channel[(n1,)], l1=l1, mul=mf(psi1_off[n1], n, k1), leaf=mf(phi_off[k1], l1, l1 - lf), kids=[])
+            entry = dict(n1=n1, ch=channel[(n1,)], l1=l1, mul=mf(psi1_off[n1], n, k1), leaf=mf(phi_off[k1], l1, l1 - lf), kids=[])
             if max_order == 2:
                 for n2, p2 in enumerate(bank.psi2):
                     if p2.j > p1.j:
                         k2 = max(min(p2.j - k1 - os_, log2_T - k1 - os_), 0)      # :344-345
                         l2 = l1 - k2
-                        entry['kids'].append(dict(ch=channel[(n1, n2)], l2=l2, mul=mf(psi2_off[n2][k1], l1, k2),
+                        entry['kids'].append(dict(n2=n2, ch=channel[(n1, n2)], l2=l2, mul=mf(psi2_off[n2][k1], l1, k2),
                                                   leaf=mf(phi_off[k1 + k2], l2, l2 - lf)))
             self.first.append(entry)
         self.arena = arena.finish()
@@ -100,6 +104,17 @@ class LargePlan:
         # longest second-order transform: Np/2 without oversampling, but a child is not subsampled at all when
         # oversampling >= its j2 - k1 (core :344-345), and then it is as long as its parent
         self.max_l2 = max([k['l2'] for e in self.first for k in e['kids']], default=1)
+        self._channel = channel
+        self._os = os_
+        self._hybrid = False                      # built on first use (seconds of host scheduling)
+
+    def hybrid_plans(self):
+        """Schedules of the subtrees that fit one SM (padded lengths above 2^13 only), or None."""
+        if self._hybrid is False:
+            self._hybrid = None
+            if HYBRID and self.geo.J_pad > sch.LOG2_NP_MAX:
+                self._hybrid = sch.build_hybrid_plans(self.J, self.N, self.Q, self.T, self.max_order, self._os)
+        return self._hybrid
 
 
 class LargeDevicePlan:
@@ -117,6 +132,20 @@ class LargeDevicePlan:
                     _TilePlanOwner(handle, nlen, kind, device_index, slots)
         self.arena = torch.from_numpy(np.ascontiguousarray(plan.arena, np.float32)).to(torch.device('cuda', device_index))
         self._ws, self._bws, self._graphs = {}, {}, {}
+        # fused subtrees: device plans of the schedules with a global source
+        self._first, self._first_n1, self._kids = None, frozenset(), {}
+        hyb = plan.hybrid_plans() if hasattr(plan, 'hybrid_plans') else None    # (bare contexts: transforms only)
+        if hyb:
+            from .torch_frontend import _DevicePlan
+            if hyb['first'] is not None:
+                self._first, self._first_n1 = _DevicePlan(hyb['first'], device_index), frozenset(hyb['first_n1'])
+            ch = plan._channel
+            for kp, members, done in hyb['kids']:
+                dp = _DevicePlan(kp, device_index)
+                for n1 in members:                 # same children, channels a constant shift apart
+                    shift = ch[(n1, done[0])] - ch[(kp.head, done[0])]
+                    assert all(ch[(n1, n2)] - ch[(kp.head, n2)] == shift for n2 in done)
+                    self._kids[n1] = (dp, shift, frozenset(done))
 
     def __del__(self):
         try:
@@ -241,18 +270,32 @@ class LargeDevicePlan:
             _lib.check(lib.tebscat_large_store(g, ctypes.c_void_p(WL.data_ptr()), B, lf, p.i0, p.n_out, p.n_paths, ch,
                                                ctypes.c_void_p(out.data_ptr()), st))
 
+        def fused(dev_plan, src, log_len, chan_shift=0):
+            """everything below the spectra `src` (B x 2^log_len) that fits one SM: one launch of the fused kernel"""
+            _lib.check(lib.tebscat_scat1d_forward_gsrc(dev_plan.handle, ctypes.c_void_p(src.data_ptr()), 1 << log_len, B,
+                                                       ctypes.c_void_p(out.data_ptr() + 4 * chan_shift * p.n_out), st))
+
         _lib.check(lib.tebscat_large_pad_load(g, ctypes.c_void_p(x2.data_ptr()), B, p.N, p.geo.pad_left, n,
                                               ctypes.c_void_p(U0.data_ptr()), st))                    # :278
         fft(U0, n, False)                                                                             # :280
         leaf(U0, p.s0, 0)
+        if self._first is not None:                # first-order filters of <= 8192 samples with their whole subtrees
+            fused(self._first, U0, n)
         for e in p.first:
+            if e['n1'] in self._first_n1:
+                continue
             mulfold(U0, e['mul'], W1)                                                                 # :307-310
             pair(W1, e['l1'])                                                                         # :312-318
             leaf(W1, e['leaf'], e['ch'])                                                              # :320-327
+            kid_plan = self._kids.get(e['n1'])
             for k in e['kids']:
+                if kid_plan is not None and k['n2'] in kid_plan[2]:
+                    continue
                 mulfold(W1, k['mul'], W2)                                                             # :347-348
                 pair(W2, k['l2'])                                                                     # :350-355
                 leaf(W2, k['leaf'], k['ch'])                                                          # :358-364
+            if kid_plan is not None:               # the children of <= 8192 samples of a longer parent
+                fused(kid_plan[0], W1, e['l1'], kid_plan[1])
         return out
 
     # ---- backward pass (SURVEY 8f-4) --------------------------------------------------------------------------------

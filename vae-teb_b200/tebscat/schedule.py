@@ -42,6 +42,7 @@ from . import filterbank as fbk
 
 OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY, OP_MULFOLD2, OP_LOADPAIR, OP_STOREU = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 OP_LOADC, OP_STOREC = 10, 11
+OP_GMULFOLD = 12                  # MULFOLD with its source spectrum in global memory (fused subtrees of the large-support level)
 FFT_INV, FFT_MOD, FFT_FUSE_FWD, FFT_PACK = 1, 2, 4, 8
 TASK_INTS = 12
 
@@ -312,7 +313,7 @@ def _fuse_first_inverse_pass(mulfolds: List[TaskSpec], stages: List[List[TaskSpe
     every MULFOLD feeding it is a plain k=1 product, let the MULFOLD do that pass on the four
     slots each of its threads owns and drop the pass (core :307-312 in one round trip)."""
     r0 = radix_split(n)[-1]
-    if r0 <= 2 and len(radix_split(n)) > 1 and all(m.op == OP_MULFOLD and m.c == 0 for m in mulfolds):
+    if r0 <= 2 and len(radix_split(n)) > 1 and all(m.op in (OP_MULFOLD, OP_GMULFOLD) and m.c == 0 for m in mulfolds):
         first = stages[0][0]
         if first.op == OP_FFT and first.c == r0 and first.d == r0 and (first.e & FFT_INV) and not (first.e & (FFT_MOD | FFT_FUSE_FWD)):
             for m in mulfolds:
@@ -368,6 +369,26 @@ def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_of
     # mean over k blocks, 1/L of the inverse transform, and the 1/2 of the pair separation
     return TaskSpec(OP_MULFOLD2, work, lat, instr, a=src, b=log_src, c=logk, d=dst_a, e=filt_off, f=mask, g=dst_b,
                     h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst + 1, trip=trip)
+
+
+def _gmulfold(arena: _Arena, src_off: int, log_src: int, logk: int, dst, filt_off: int) -> TaskSpec:
+    """MULFOLD whose source is a spectrum of 2^log_src bins in GLOBAL memory (csrc: gmulfold_task): the parent is
+    too long for one SM, the result (<= 8192 bins) lands in shared memory.  Every trip has its filter and source
+    loads in flight together: one trip to L2 / HBM (modelled like the L2-bound trips of _mulfold, a bit longer)."""
+    log_dst = log_src - logk
+    if logk >= 2:
+        mask = arena.chunk_mask(filt_off, logk)
+        logcw = _Arena.chunk_log2(logk)
+        nch = bin(mask).count('1') << (logcw - 2)
+        filt_off = arena.compact(filt_off, logk, mask)
+        work, lat, instr, trip = -(-(1 << log_dst) // 4), 1200.0 + 1200.0 * nch, 120.0 + 140.0 * nch, 400.0 + 1100.0 * nch
+    else:
+        mask = 0
+        work, lat, instr, trip = -(-(1 << (log_src - 2)) // 4), 2800.0, 340.0, 2400.0
+    if mask >= 1 << 31:
+        mask -= 1 << 32
+    return TaskSpec(OP_GMULFOLD, work, lat, instr, a=int(src_off), b=log_src, c=logk, d=dst, e=filt_off, f=mask,
+                    h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst, trip=trip)
 
 
 # ------------------------------------------------------------------------------------
@@ -431,8 +452,13 @@ class _Allocator:
 
 
 def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int, arena: _Arena,
-                 batch_slots: int = BATCH_SLOTS, oversampling: int = 0, child_slots: Optional[int] = None):
-    """The cascade as a forest of chains of batched tasks, in the reference's channel order."""
+                 batch_slots: int = BATCH_SLOTS, oversampling: int = 0, child_slots: Optional[int] = None,
+                 global_u0: bool = False):
+    """The cascade as a forest of chains of batched tasks, in the reference's channel order.
+
+    global_u0 (large-support level, padded lengths above 2^13): the signal's spectrum U0 lives in GLOBAL memory
+    -- no root chain, no order-0 leaf -- and only the first-order filters whose subsampled length fits one SM
+    (<= 8192 samples) are scheduled, their psi1 multiply + periodisation reading U0 through OP_GMULFOLD."""
     n = geo.J_pad
     log2_T = int(math.floor(math.log2(T)))
     os_ = int(oversampling)
@@ -492,10 +518,16 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
 
     # root: pad + forward transform of the signal (core/scattering1d.py:278-280)
     u0 = Buf(1 << n, 'U0')
-    root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
-                 _merge_local_passes(_fft_stages((u0, 0), n, 1, 'fwd')), owns=[u0], depth=0)
-    chains.append(root)
-    chains.append(Chain('S0', [[leaf((u0, 0), n, 0, ())]], after=[root], reads=[u0], depth=1))   # :285-292
+    if not global_u0:
+        root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
+                     _merge_local_passes(_fft_stages((u0, 0), n, 1, 'fwd')), owns=[u0], depth=0)
+        chains.append(root)
+        chains.append(Chain('S0', [[leaf((u0, 0), n, 0, ())]], after=[root], reads=[u0], depth=1))   # :285-292
+    from_u0 = [] if global_u0 else [root]
+    reads_u0 = [] if global_u0 else [u0]
+
+    def first_mulfold(k1: int, dst, filt_off: int) -> TaskSpec:
+        return _gmulfold(arena, 0, n, k1, dst, filt_off) if global_u0 else _mulfold(arena, (u0, 0), n, k1, dst, filt_off)
 
     # first order, batched by subsampling k1 (:300-318)
     groups: Dict[int, List[int]] = {}
@@ -503,6 +535,8 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
         k1 = max(min(p1.j - os_, log2_T - os_), 0)                     # :304
         if not p1.xi < 0.5 / (2 ** k1):
             raise AssertionError('psi1 aliasing assertion of the reference violated')
+        if global_u0 and n - k1 > LOG2_NP_MAX:
+            continue                                                   # stays on the level's own kernels
         groups.setdefault(k1, []).append(n1)
     for k1 in sorted(groups):
         l1 = n - k1
@@ -515,12 +549,12 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
             lo = len(batch)
             hi = sum(1 for _, b in batch if b is not None)             # pairs come first
             x1 = Buf((lo + hi) << l1, 'U1[k1=%d:%d]' % (k1, batch[0][0]))
-            mf = [_mulfold(arena, (u0, 0), n, k1, (x1, i << l1), psi1_off[a]) for i, (a, _) in enumerate(batch)]
-            mf += [_mulfold(arena, (u0, 0), n, k1, (x1, (lo + i) << l1), psi1_off[b])
+            mf = [first_mulfold(k1, (x1, i << l1), psi1_off[a]) for i, (a, _) in enumerate(batch)]
+            mf += [first_mulfold(k1, (x1, (lo + i) << l1), psi1_off[b])
                    for i, (_, b) in enumerate(batch) if b is not None]
             st = [mf] + _merge_local_passes(
                 _fuse_first_inverse_pass(mf, _fft_stages((x1, 0), l1, lo, 'pair', hi=hi), l1))             # :307-318
-            c1 = Chain(x1.name, st, after=[root], reads=[u0], owns=[x1], depth=1)
+            c1 = Chain(x1.name, st, after=list(from_u0), reads=list(reads_u0), owns=[x1], depth=1)
             if hi:
                 c1.shrink.append((pack_stage(st), x1, lo << l1))
             chains.append(c1)
@@ -955,6 +989,15 @@ def task_accesses(t, log2_Np):
                 add(d + 4 * it[:, None] + np.arange(4)[None, :], it % nt, True)
             else:
                 add(d + 2 * it[:, None] + np.arange(2)[None, :], it % nt, True)
+    elif op == OP_GMULFOLD:                             # the source is global: only the destination slots count
+        log_src, logk = b, c
+        if logk >= 2:
+            m = np.arange(1 << (log_src - logk))
+            add(d + m, m % nt, True)
+        else:
+            it = np.arange(1 << (log_src - 2))
+            w_ = 4 >> logk
+            add(d + w_ * it[:, None] + np.arange(w_)[None, :], it % nt, True)
     elif op == OP_LOADPAIR:
         s_ = a + np.arange(1 << log2_Np)
         for w in range(nt // 32):
@@ -1247,3 +1290,143 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     logical = _round16(high)
     return ScatPlan(J, Q1, T, N, max_order, geo, bank, keys, n_out, arena.finish(), tasks, ranges,
                     np.asarray(chan, dtype=np.int32), logical + logical // 16, N_THREADS, stats)
+
+
+# ------------------------------------------------------------------------------------
+# large-support level: the subtrees that fit one SM, fused
+# ------------------------------------------------------------------------------------
+def build_kid_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, arena: _Arena, n1: int,
+                     oversampling: int = 0, child_slots: int = BATCH_SLOTS):
+    """Second-order subtrees of ONE first-order filter whose own modulus is longer than 8192 samples: the spectrum
+    of |u1| (2^l1 bins, bit-reversed) lives in global memory; every child of at most 8192 samples runs here --
+    psi2 multiply + periodisation from global memory (OP_GMULFOLD), iFFT -> modulus -> FFT, phi leaf
+    (core/scattering1d.py:337-364).  Children are not pair-packed (partners would be different psi2 octaves of
+    one parent, whose energies can differ widely).  Returns (chains, channels written, children left out)."""
+    n = geo.J_pad
+    log2_T = int(math.floor(math.log2(T)))
+    os_ = int(oversampling)
+    kf = max(log2_T - os_, 0)
+    lf = n - kf
+    i0, i1 = geo.ind_start[kf], geo.ind_end[kf]
+    phi_off = [arena.add(a) for a in bank.phi.levels]
+    psi2_off = [[arena.add(a) for a in p.levels] for p in bank.psi2]
+    keys: List[Tuple[int, ...]] = [()] + [(i,) for i in range(len(bank.psi1))]
+    for m1, q1 in enumerate(bank.psi1):
+        for n2, p2 in enumerate(bank.psi2):
+            if p2.j > q1.j:
+                keys.append((m1, n2))
+    channel = {k: c for c, k in enumerate(keys)}
+    p1 = bank.psi1[n1]
+    k1 = max(min(p1.j - os_, log2_T - os_), 0)
+    l1 = n - k1
+    kids: Dict[int, List[int]] = {}
+    left_out: List[int] = []
+    for n2, p2 in enumerate(bank.psi2):
+        if p2.j > p1.j:
+            k2 = max(min(p2.j - k1 - os_, log2_T - k1 - os_), 0)
+            if l1 - k2 <= LOG2_NP_MAX:
+                kids.setdefault(k2, []).append(n2)
+            else:
+                left_out.append(n2)
+    chains: List[Chain] = []
+    written: List[int] = []
+    for k2 in sorted(kids):
+        l2 = l1 - k2
+        per = max(1, child_slots >> l2)
+        fam = kids[k2]
+        for s2 in range(0, len(fam), per):
+            sub = fam[s2:s2 + per]
+            x2 = Buf(len(sub) << l2, 'U2[%d,k2=%d:%d]' % (n1, k2, sub[0]))
+            mf = [_gmulfold(arena, 0, l1, k2, (x2, c << l2), psi2_off[n2][k1]) for c, n2 in enumerate(sub)]      # :347-348
+            st = [mf] + _merge_local_passes(
+                _fuse_first_inverse_pass(mf, _fft_stages((x2, 0), l2, len(sub), 'pair'), l2))                   # :350-355
+            c2 = Chain(x2.name, st, owns=[x2], depth=1)
+            chains.append(c2)
+            lv = [_mulfold(arena, (x2, c << l2), l2, l2 - lf, LEAF, phi_off[k1 + k2], (channel[(n1, n2)], -1))
+                  for c, n2 in enumerate(sub)]                                                                 # :358-364
+            chains.append(Chain('S2' + x2.name, [lv], after=[c2], reads=[x2], depth=2))
+            written += [channel[(n1, n2)] for n2 in sub]
+    return chains, written, left_out, len(keys), i1 - i0, lf, i0
+
+
+def _finish_fused_plan(J, Q1, T, N, max_order, geo, bank, n_paths, n_out, lf, i0, chains, arena, pool_slots):
+    capacity = smem_capacity()
+    steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, pool_slots=pool_slots)
+    tasks, ranges = emit(steps)
+    if os.environ.get('TEBSCAT_RELAX', '1') != '0':
+        keep = elide_barriers(tasks, ranges, capacity, LOG2_NP_MAX)
+        for st in range(ranges.shape[0]):
+            if not keep[st]:
+                tasks[ranges[st, 0]:ranges[st, 1], 11] |= 1
+    logical = _round16(high)
+
+    class _F:
+        pass
+    f = _F()
+    # the device plan only needs a geometry the kernel accepts: these schedules have no LOAD (their source is global)
+    f.J, f.Q, f.T, f.max_order, f.bank = J, Q1, T, max_order, bank
+    f.N, f.geo = 1 << LOG2_NP_MAX, type('G', (), dict(J_pad=LOG2_NP_MAX, pad_left=0))()
+    f.n_paths, f.n_out = n_paths, n_out
+    f.arena, f.tasks, f.steps = arena.finish(), tasks, ranges
+    f.chan = np.asarray(chan, dtype=np.int32)
+    f.smem_complex, f.n_threads = logical + logical // 16, N_THREADS
+    f.stats = dict(n_steps=len(steps), n_tasks=tasks.shape[0], smem_logical=high, **sched)
+    return f
+
+
+def build_hybrid_plans(J: int, N: int, Q, T: int, max_order: int = 2, oversampling: int = 0):
+    """Padded lengths above 2^13 (the large-support level): the parts of the cascade that fit one SM as schedules
+    of the fused kernel with a global source.
+
+    Returns dict(first=plan or None, first_n1=[...], kids=[(plan, [n1, ...], [n2 done...])]):
+      * `first`: every first-order filter whose subsampled length is <= 8192 samples, with its whole subtree
+        (pair-packed like the cascade proper) -- ONE launch per batch reading the signal's spectrum U0;
+      * `kids`: per group of longer first-order filters of one scale j1 (same children, channels a constant shift
+        apart), the second-order children of <= 8192 samples -- one launch per filter reading the spectrum of |u1|.
+    A part whose buffers do not fit shared memory is left out (None / missing): the level's own kernels serve it."""
+    Q1 = fbk._as_Q1(Q)
+    geo = fbk.build_geometry(N, J, Q1, T)
+    n = geo.J_pad
+    if n <= LOG2_NP_MAX:
+        raise ValueError('the fused cascade serves this padded length as a whole')
+    bank = fbk.build_filter_bank(n, J, Q1, T)
+    log2_T = int(math.floor(math.log2(T)))
+    os_ = int(oversampling)
+    k1_of = [max(min(p.j - os_, log2_T - os_), 0) for p in bank.psi1]
+    out = dict(first=None, first_n1=[], kids=[])
+    small = [n1 for n1 in range(len(bank.psi1)) if n - k1_of[n1] <= LOG2_NP_MAX]
+    if small:
+        for batch_slots, pool_slots in [(BATCH_SLOTS, POOL_SLOTS), (BATCH_SLOTS, 512), (4096, 1024), (2048, 1024), (1024, 512)]:
+            arena = _Arena()
+            try:
+                chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling,
+                                                           global_u0=True)
+                out['first'] = _finish_fused_plan(J, Q1, T, N, max_order, geo, bank, len(keys), n_out, lf, i0, chains,
+                                                  arena, pool_slots)
+                out['first_n1'] = small
+                break
+            except (RuntimeError, AssertionError, NotImplementedError):
+                continue
+    if max_order == 2:
+        groups: Dict[Tuple[int, int], List[int]] = {}
+        for n1, p1 in enumerate(bank.psi1):
+            if n - k1_of[n1] > LOG2_NP_MAX:
+                groups.setdefault((p1.j, k1_of[n1]), []).append(n1)
+        for (_, _), members in sorted(groups.items()):
+            head = members[0]
+            for child_slots, pool_slots in [(BATCH_SLOTS, POOL_SLOTS), (BATCH_SLOTS, 512), (4096, 1024), (2048, 512)]:
+                arena = _Arena()
+                try:
+                    chains, written, left_out, n_paths, n_out, lf, i0 = build_kid_chains(bank, geo, T, arena, head,
+                                                                                         oversampling, child_slots)
+                    if not chains:
+                        break
+                    plan = _finish_fused_plan(J, Q1, T, N, max_order, geo, bank, n_paths, n_out, lf, i0, chains, arena,
+                                              pool_slots)
+                    plan.head, plan.written = head, written
+                    done = [n2 for n2, p2 in enumerate(bank.psi2) if p2.j > bank.psi1[head].j and n2 not in left_out]
+                    out['kids'].append((plan, members, done))
+                    break
+                except (RuntimeError, AssertionError, NotImplementedError):
+                    continue
+    return out
