@@ -59,7 +59,10 @@ typedef struct tebscat_plan_desc {
     int32_t border_mode;   /* padding rule of the plan's loads: 0 reflect (the scattering transform, always),
                               1 constant (zeros), 2 circular -- KymatioPhaseScattering1D(border_mode=...),
                               hdf5_dataset/kymatio_phase_scattering.py:162-173                          */
-    int32_t reserved[5];
+    int32_t scratch_complex; /* 0, or the complex64 elements of global scratch each CTA needs: schedules that park the
+                              signal's spectrum in L2 instead of shared memory (tebscat/schedule.py, u0_scratch);
+                              the library allocates it (n_SM x scratch_complex x 8 bytes per stream in use)  */
+    int32_t reserved[4];
 } tebscat_plan_desc;
 
 typedef struct tebscat_plan tebscat_plan;

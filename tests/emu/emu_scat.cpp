@@ -20,7 +20,8 @@ static int emu_run(int N, int log2_Np, int pad_left, int n_paths, int n_out,
                    float* zc, float* zp, int z_mode,
                    const float* ep_mean, const float* ep_std, const unsigned char* ep_mode,
                    float ep_log_eps, int ep_trim, int ep_time_major, int border,
-                   const float* gsrc, long long gsrc_stride) {
+                   const float* gsrc, long long gsrc_stride, int scratch_complex = 0) {
+    std::vector<float2> scratch((size_t)scratch_complex, make_float2(NAN, NAN));   // plans that park U0 in global memory
     std::vector<float2> S((size_t)smem_complex);
     std::vector<float2> tw(kTwAP + kTwBP, make_float2(0.f, 0.f));
     const double w0 = -2.0 * M_PI / (double)(1 << kLog2TwMax);
@@ -49,6 +50,11 @@ static int emu_run(int N, int log2_Np, int pad_left, int n_paths, int n_out,
                 c.pr_pw[q] = x[b * n_paths + q];           // the rows' powers travel in `x`
             }
         }
+        if (scratch_complex > 0) {
+            c.gbuf = scratch.data();
+            c.g_valid = scratch_complex;
+            c.gsrc = scratch.data();
+        }
         c.chan = chan;
         c.zc = reinterpret_cast<float2*>(zc) + b * (long long)n_paths * n_out;
         c.zp = reinterpret_cast<float2*>(zp) + b * (long long)n_paths * n_out;
@@ -73,9 +79,10 @@ extern "C" int emu_scat1d_forward(int N, int log2_Np, int pad_left, int n_paths,
                                   const int32_t* chan, const float* x, long long B, float* out,
                                   float* zc, float* zp, int z_mode,
                                   const float* ep_mean, const float* ep_std, const unsigned char* ep_mode,
-                                  float ep_log_eps, int ep_trim, int ep_time_major, int border) {
+                                  float ep_log_eps, int ep_trim, int ep_time_major, int border, int scratch_complex) {
     return emu_run(N, log2_Np, pad_left, n_paths, n_out, smem_complex, n_tasks, n_steps, arena, tasks, steps, chan, x, B, out,
-                   zc, zp, z_mode, ep_mean, ep_std, ep_mode, ep_log_eps, ep_trim, ep_time_major, border, nullptr, 0);
+                   zc, zp, z_mode, ep_mean, ep_std, ep_mode, ep_log_eps, ep_trim, ep_time_major, border, nullptr, 0,
+                   scratch_complex);
 }
 
 // fused subtrees of the large-support level (tebscat_scat1d_forward_gsrc): job b reads the complex spectrum at

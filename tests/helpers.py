@@ -79,7 +79,8 @@ def emu_forward(plan, x, stage_a=False, epilogue=None):
                                 ep_mean.ctypes.data_as(fp) if ep_mean is not None else None,
                                 ep_std.ctypes.data_as(fp) if ep_std is not None else None,
                                 ep_mode.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)) if ep_mode is not None else None,
-                                ctypes.c_float(ep_eps), ep_trim, ep_tm, int(getattr(plan, 'border', 0)))
+                                ctypes.c_float(ep_eps), ep_trim, ep_tm, int(getattr(plan, 'border', 0)),
+                                int(getattr(plan, 'scratch_complex', 0)))
     assert rc == 0
     if stage_a:
         return zc[..., 0] + 1j * zc[..., 1], zp
@@ -133,6 +134,6 @@ def emu_pair_stage(pair_plan, zp_rows, zc_rows, powers):
                                 arena.ctypes.data_as(fp), tasks.ctypes.data_as(ip), steps.ctypes.data_as(ip),
                                 chan.ctypes.data_as(ip), pw.ctypes.data_as(fp), ctypes.c_longlong(jobs), out.ctypes.data_as(fp),
                                 zc.ctypes.data_as(fp), zp.ctypes.data_as(fp), 4, None, None, None, ctypes.c_float(0.0), 0, 0,
-                                int(getattr(pair_plan, 'border', 0)))
+                                int(getattr(pair_plan, 'border', 0)), 0)
     assert rc == 0
     return out.reshape(jobs * rpj, pair_plan.n_out)[:rows]

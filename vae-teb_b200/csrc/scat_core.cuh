@@ -668,12 +668,13 @@ TEB_D void mulfold_task(float2* S, const float* __restrict__ arena, const Task& 
     }
 }
 
-// Four consecutive complex bins of a global spectrum (32-byte aligned: two 128-bit loads through the read-only path).
+// Four consecutive complex bins of a global spectrum (32-byte aligned: two 128-bit loads).  Plain coherent loads, not
+// the read-only path: a schedule that parks U0 in its CTA's scratch rewrites that memory for every signal.
 TEB_D void gload4(const float2* g, float2 (&z)[4]) {
 #ifdef TEBSCAT_HOST_EMU
     z[0] = g[0]; z[1] = g[1]; z[2] = g[2]; z[3] = g[3];
 #else
-    const float4 lo = TEB_LDG(reinterpret_cast<const float4*>(g)), hi = TEB_LDG(reinterpret_cast<const float4*>(g) + 1);
+    const float4 lo = *reinterpret_cast<const float4*>(g), hi = *(reinterpret_cast<const float4*>(g) + 1);
     z[0] = make_float2(lo.x, lo.y); z[1] = make_float2(lo.z, lo.w);
     z[2] = make_float2(hi.x, hi.y); z[3] = make_float2(hi.z, hi.w);
 #endif

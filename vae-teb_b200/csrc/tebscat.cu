@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -102,6 +103,10 @@ struct KParams {
     // gsrc + b * gsrc_stride (complex elements)
     const float2* gsrc;
     long long gsrc_stride;
+    // schedules that PARK the signal's spectrum in global memory (plan_desc.scratch_complex > 0): CTA c owns
+    // gscratch + c * gscratch_stride; it is the tile of OP_STOREC and the source of OP_GMULFOLD
+    float2* gscratch;
+    long long gscratch_stride;
 };
 
 constexpr int kThreads = 512;
@@ -189,7 +194,15 @@ scat1d_kernel(const KParams p, const float* __restrict__ x, float* __restrict__ 
             c.log2_Np = p.log2_Np;
             c.border = p.border;
             c.n_out = p.n_out;
-            if (GSRC) c.gsrc = p.gsrc + b * p.gsrc_stride;
+            if (GSRC) {
+                if (p.gscratch) {
+                    c.gbuf = p.gscratch + blockIdx.x * p.gscratch_stride;
+                    c.g_valid = (int)p.gscratch_stride;
+                    c.gsrc = c.gbuf;
+                } else {
+                    c.gsrc = p.gsrc + b * p.gsrc_stride;
+                }
+            }
         }
         __syncthreads();             // (the last step of the previous signal ended in a barrier too)
         const bool prof = PROF && blockIdx.x == 0 && b == blockIdx.x && tid == 0;
@@ -273,9 +286,27 @@ struct tebscat_plan {
     float* d_win = nullptr;
     KParams kp;
     int64_t gsrc_extent = 0;     // > 0: the schedule reads a global source spectrum of that many complex bins (OP_GMULFOLD)
+    // desc.scratch_complex > 0: the schedule parks U0 in a per-CTA scratch of that many complex elements.  One scratch
+    // per stream the plan has been launched on (launches on one stream are ordered; different streams may overlap).
+    int64_t scratch_complex = 0;
+    mutable std::map<cudaStream_t, float2*> scratch;
+    mutable std::mutex scratch_mu;
     HostPipe pipe;
     std::mutex pipe_mu;
 };
+
+// the scratch of `p` for launches on `st` (allocated on first use; the plan's device is current)
+static int plan_scratch(const tebscat_plan* p, cudaStream_t st, float2** out) {
+    std::lock_guard<std::mutex> lock(p->scratch_mu);
+    auto it = p->scratch.find(st);
+    if (it == p->scratch.end()) {
+        float2* d = nullptr;
+        CU(cudaMalloc(&d, (size_t)p->n_sms * (size_t)p->scratch_complex * sizeof(float2)));
+        it = p->scratch.emplace(st, d).first;
+    }
+    *out = it->second;
+    return TEBSCAT_OK;
+}
 
 static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, const int32_t* steps,
                              size_t n_floats, size_t n_chan, int64_t* gsrc_extent = nullptr) {
@@ -461,6 +492,10 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     p->desc = *desc;
     p->device = device;
     p->gsrc_extent = gsrc_extent;
+    p->scratch_complex = desc->scratch_complex;
+    if (p->scratch_complex < 0 || (p->scratch_complex & 3) || (p->scratch_complex && gsrc_extent > p->scratch_complex))
+        return fail(TEBSCAT_EINVAL, "bad scratch size %lld (the schedule reads %lld bins)", (long long)p->scratch_complex,
+                    (long long)gsrc_extent);
     p->n_sms = prop.multiProcessorCount;
     p->smem_bytes = ((size_t)desc->smem_complex + kTwAP + kTwBP) * sizeof(float2);
     if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
@@ -559,6 +594,8 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     k.g_slots = 0;
     k.gsrc = nullptr;
     k.gsrc_stride = 0;
+    k.gscratch = nullptr;
+    k.gscratch_stride = 0;
     *out = guard.release();
     return TEBSCAT_OK;
 }
@@ -677,6 +714,7 @@ extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
     cudaFree(p->d_warp_tab);
     cudaFree(p->d_chan);
     cudaFree(p->d_win);
+    for (auto& kv : p->scratch) cudaFree(kv.second);
     delete p;
 }
 
@@ -702,14 +740,27 @@ extern "C" int tebscat_plan_set_window(tebscat_plan* p, const float* window_host
     return rc;
 }
 
-static int launch_scat1d(const tebscat_plan* p, const float* x, int64_t B, float* S, cudaStream_t st) {
-    if (p->gsrc_extent) return fail(TEBSCAT_EINVAL, "this plan reads a global source spectrum: use tebscat_scat1d_forward_gsrc");
+// launch of a plan's schedule with the parameters `kp` (the plan's own, possibly with an epilogue): plans that park
+// U0 in global memory run on the kernel variant with the global-source op, on their per-stream scratch
+static int launch_plan(const tebscat_plan* p, KParams kp, const float* x, int64_t B, float* S, cudaStream_t st) {
+    if (p->gsrc_extent && !p->scratch_complex)
+        return fail(TEBSCAT_EINVAL, "this plan reads a global source spectrum: use tebscat_scat1d_forward_gsrc");
     if (B == 0) return TEBSCAT_OK;
     const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
-    scat1d_kernel<false><<<grid, p->desc.n_threads, p->smem_bytes, st>>>(p->kp, x, S, (long long)B);
+    if (p->scratch_complex) {
+        if (int rc = plan_scratch(p, st, &kp.gscratch)) return rc;
+        kp.gscratch_stride = p->scratch_complex;
+        scat1d_kernel<false, true><<<grid, p->desc.n_threads, p->smem_bytes, st>>>(kp, x, S, (long long)B);
+    } else {
+        scat1d_kernel<false><<<grid, p->desc.n_threads, p->smem_bytes, st>>>(kp, x, S, (long long)B);
+    }
     CU(cudaGetLastError());
     ++g_launches;
     return TEBSCAT_OK;
+}
+
+static int launch_scat1d(const tebscat_plan* p, const float* x, int64_t B, float* S, cudaStream_t st) {
+    return launch_plan(p, p->kp, x, B, S, st);
 }
 
 extern "C" int tebscat_scat1d_forward(const tebscat_plan* p, const float* x_dev, int64_t B, float* S_dev,
@@ -727,7 +778,7 @@ extern "C" int tebscat_scat1d_forward_gsrc(const tebscat_plan* p, const float* s
                                            float* S_dev, void* stream) {
     g_launches = 0;
     if (!p || B < 0 || (B > 0 && (!src_dev || !S_dev))) return fail(TEBSCAT_EINVAL, "null argument");
-    if (!p->gsrc_extent) return fail(TEBSCAT_EINVAL, "this plan has no global-source task");
+    if (!p->gsrc_extent || p->scratch_complex) return fail(TEBSCAT_EINVAL, "this plan has no global-source task");
     if (src_stride < p->gsrc_extent)
         return fail(TEBSCAT_EINVAL, "source stride %lld below the %lld bins the schedule reads", (long long)src_stride,
                     (long long)p->gsrc_extent);
@@ -754,7 +805,6 @@ extern "C" int tebscat_scat1d_forward_ex(const tebscat_plan* p, const float* x_d
     if (!ep->mean_dev || !ep->std_dev || !ep->mode_dev) return fail(TEBSCAT_EINVAL, "epilogue: null statistics");
     if (ep->trim < 0 || 2 * ep->trim >= p->desc.n_out)
         return fail(TEBSCAT_EINVAL, "epilogue: trim %d leaves nothing of %d samples", ep->trim, p->desc.n_out);
-    if (p->gsrc_extent) return fail(TEBSCAT_EINVAL, "this plan reads a global source spectrum: use tebscat_scat1d_forward_gsrc");
     if (B == 0) return TEBSCAT_OK;
     ON_DEVICE(p->device);
     KParams kp = p->kp;
@@ -764,18 +814,14 @@ extern "C" int tebscat_scat1d_forward_ex(const tebscat_plan* p, const float* x_d
     kp.ep_log_eps = ep->log_eps;
     kp.ep_trim = ep->trim;
     kp.ep_time_major = ep->time_major ? 1 : 0;
-    const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
-    scat1d_kernel<false><<<grid, p->desc.n_threads, p->smem_bytes, (cudaStream_t)stream>>>(kp, x_dev, out_dev, (long long)B);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(TEBSCAT_ECUDA, "launch failed: %s", cudaGetErrorString(e));
-    ++g_launches;
-    return TEBSCAT_OK;
+    return launch_plan(p, kp, x_dev, B, out_dev, (cudaStream_t)stream);
 }
 
 extern "C" int tebscat_scat1d_profile_steps(const tebscat_plan* p, const float* x_dev, int64_t B, float* S_dev,
                                             long long* step_clocks_host, void* stream) {
     g_launches = 0;
     if (!p || !x_dev || !S_dev || !step_clocks_host || B < 1) return fail(TEBSCAT_EINVAL, "null argument");
+    if (p->gsrc_extent) return fail(TEBSCAT_EUNSUPPORTED, "step profiling is not built for schedules with a global source");
     ON_DEVICE(p->device);
     long long* d_prof = nullptr;
 #ifdef TEBSCAT_PROF_PHASES

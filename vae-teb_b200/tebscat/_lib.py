@@ -19,7 +19,8 @@ class PlanDesc(ctypes.Structure):
                 ('pad_left', ctypes.c_int32), ('n_paths', ctypes.c_int32), ('n_out', ctypes.c_int32),
                 ('n_threads', ctypes.c_int32), ('smem_complex', ctypes.c_int32),
                 ('n_tasks', ctypes.c_int32), ('n_steps', ctypes.c_int32),
-                ('border_mode', ctypes.c_int32), ('reserved', ctypes.c_int32 * 5)]
+                ('border_mode', ctypes.c_int32), ('scratch_complex', ctypes.c_int32),
+                ('reserved', ctypes.c_int32 * 4)]
 
 
 class PhaseDesc(ctypes.Structure):

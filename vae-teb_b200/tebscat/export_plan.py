@@ -29,6 +29,7 @@ def plan_desc(plan):
     desc.n_tasks = plan.tasks.shape[0]
     desc.n_steps = plan.steps.shape[0]
     desc.border_mode = int(getattr(plan, 'border', 0))
+    desc.scratch_complex = int(getattr(plan, 'scratch_complex', 0))
     return desc
 
 

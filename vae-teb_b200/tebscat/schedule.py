@@ -381,10 +381,10 @@ def _gmulfold(arena: _Arena, src_off: int, log_src: int, logk: int, dst, filt_of
         logcw = _Arena.chunk_log2(logk)
         nch = bin(mask).count('1') << (logcw - 2)
         filt_off = arena.compact(filt_off, logk, mask)
-        work, lat, instr, trip = -(-(1 << log_dst) // 4), 1200.0 + 1200.0 * nch, 120.0 + 140.0 * nch, 400.0 + 1100.0 * nch
+        work, lat, instr, trip = -(-(1 << log_dst) // 4), 900.0 + 1000.0 * nch, 110.0 + 130.0 * nch, 350.0 + 900.0 * nch
     else:
         mask = 0
-        work, lat, instr, trip = -(-(1 << (log_src - 2)) // 4), 2800.0, 340.0, 2400.0
+        work, lat, instr, trip = -(-(1 << (log_src - 2)) // 4), 2400.0, 330.0, 2100.0
     if mask >= 1 << 31:
         mask -= 1 << 32
     return TaskSpec(OP_GMULFOLD, work, lat, instr, a=int(src_off), b=log_src, c=logk, d=dst, e=filt_off, f=mask,
@@ -412,6 +412,7 @@ class ScatPlan:
     smem_complex: int              # PHYSICAL complex slots (logical slots + 1 pad per 16)
     n_threads: int = N_THREADS
     stats: Dict[str, float] = field(default_factory=dict)
+    scratch_complex: int = 0       # > 0: per-CTA global scratch (complex elements) the schedule parks U0 in
 
     @property
     def n_paths(self) -> int:
@@ -518,12 +519,24 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
 
     # root: pad + forward transform of the signal (core/scattering1d.py:278-280)
     u0 = Buf(1 << n, 'U0')
-    if not global_u0:
+    scratch = global_u0 == 'scratch'
+    if scratch:
+        # U0 is computed here but PARKED in a per-CTA global scratch (L2-resident) right after its transform: its
+        # 2^n slots are free for the rest of the signal, and every consumer reads it through OP_GMULFOLD
+        root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
+                     _merge_local_passes(_fft_stages((u0, 0), n, 1, 'fwd')) +
+                     [[TaskSpec(OP_STOREC, 1 << n, 300.0, 12.0, a=(u0, 0), b=1 << n)]],
+                     owns=[u0], frees_own_at_end=True, depth=0)
+        chains.append(root)
+        s0 = _gmulfold(arena, 0, n, n - lf, LEAF, phi_off[0])
+        s0.channel = (channel[()], -1)
+        chains.append(Chain('S0', [[s0]], after=[root], depth=1))                                    # :285-292
+    elif not global_u0:
         root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
                      _merge_local_passes(_fft_stages((u0, 0), n, 1, 'fwd')), owns=[u0], depth=0)
         chains.append(root)
         chains.append(Chain('S0', [[leaf((u0, 0), n, 0, ())]], after=[root], reads=[u0], depth=1))   # :285-292
-    from_u0 = [] if global_u0 else [root]
+    from_u0 = [root] if (scratch or not global_u0) else []
     reads_u0 = [] if global_u0 else [u0]
 
     def first_mulfold(k1: int, dst, filt_off: int) -> TaskSpec:
@@ -1244,11 +1257,17 @@ def emit(steps) -> Tuple[np.ndarray, np.ndarray]:
             np.asarray(ranges, dtype=np.int32).reshape(-1, 2))
 
 
+def u0_in_scratch() -> bool:
+    """TEBSCAT_U0_GLOBAL=1: the signal's spectrum is parked in a per-CTA global scratch (A/B switch)."""
+    return os.environ.get('TEBSCAT_U0_GLOBAL', '0') == '1'
+
+
 def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int = 64,
                oversampling: int = 0, tune: Optional[dict] = None) -> ScatPlan:
     """`tune` overrides scheduler knobs (tools/sweep_sched.py): batch_slots, child_slots, pool_slots,
-    pack_gain, open_demand."""
+    pack_gain, open_demand, u0_scratch."""
     tune = dict(tune or {})
+    scratch = bool(tune.get('u0_scratch', u0_in_scratch()))
     Q1 = fbk._as_Q1(Q)
     geo = fbk.build_geometry(N, J, Q1, T)
     if geo.J_pad > LOG2_NP_MAX:
@@ -1266,7 +1285,8 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     for batch_slots, pool_slots in ladder:
         arena = _Arena()
         chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling,
-                                                   child_slots=tune.get('child_slots'))
+                                                   child_slots=tune.get('child_slots'),
+                                                   global_u0='scratch' if scratch else False)
         try:
             steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel,
                                                        pool_slots=pool_slots, pack_gain=tune.get('pack_gain', 0.97),
@@ -1282,14 +1302,20 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     if os.environ.get('TEBSCAT_RELAX', '1') != '0':
         keep = elide_barriers(tasks, ranges, capacity, geo.J_pad)
         for st in range(ranges.shape[0]):
+            # (the barrier analysis tracks shared-memory slots only: the step that parks U0 in the global scratch
+            # must end in a CTA barrier, the global-source multiplies of other warps read what it wrote)
+            if scratch and np.any((tasks[ranges[st, 0]:ranges[st, 1], 0] & 0xff) == OP_STOREC):
+                keep[st] = True
             if not keep[st]:
                 tasks[ranges[st, 0]:ranges[st, 1], 11] |= 1
                 n_relaxed += 1
     stats = dict(n_steps=len(steps), n_tasks=n_tasks, n_relaxed=n_relaxed, smem_logical=high,
                  mean_tasks_per_step=n_tasks / max(1, len(steps)), **sched)
     logical = _round16(high)
-    return ScatPlan(J, Q1, T, N, max_order, geo, bank, keys, n_out, arena.finish(), tasks, ranges,
+    plan = ScatPlan(J, Q1, T, N, max_order, geo, bank, keys, n_out, arena.finish(), tasks, ranges,
                     np.asarray(chan, dtype=np.int32), logical + logical // 16, N_THREADS, stats)
+    plan.scratch_complex = (1 << geo.J_pad) if scratch else 0
+    return plan
 
 
 # ------------------------------------------------------------------------------------

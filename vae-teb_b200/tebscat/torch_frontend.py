@@ -48,6 +48,7 @@ class _DevicePlan:
         desc.n_tasks = plan.tasks.shape[0]
         desc.n_steps = plan.steps.shape[0]
         desc.border_mode = int(getattr(plan, 'border', 0))     # phase plans only; the transform always reflects
+        desc.scratch_complex = int(getattr(plan, 'scratch_complex', 0))   # per-CTA global scratch of schedules that park U0
         arena = np.ascontiguousarray(plan.arena, np.float32)
         tasks = np.ascontiguousarray(plan.tasks, np.int32)
         steps = np.ascontiguousarray(plan.steps, np.int32)
