@@ -66,6 +66,9 @@ enum : int32_t {
     OP_STOREU = 9,   // average=False: a=src c=first index d=count e=offset in the output row: the modulus itself
     OP_MULFOLD2 = 7, // like MULFOLD with k >= 1 on a PACKED source (spectrum of u_a + i u_b): a=src b=log2Lsrc c=log2k
                      // d=dst of the a-child e=filter offset f=chunk mask g=dst of the b-child h=log2 chunk width
+    OP_GMULFOLD2 = 13, // two filters on ONE read of the global source (the partners of a packed pair): a=dst of filter B
+                     // b=log2Lsrc c=log2k d=dst of filter A e=filter A f=chunk mask (shared) g=filter B
+                     // h=log2 chunk width | fused first inverse radix << 8; the source starts at SignalCtx::gsrc
     OP_GMULFOLD = 12 // MULFOLD whose SOURCE is a spectrum in global memory (SignalCtx::gsrc + a, up to 2^17 bins, bit-reversed
                      // order, unswizzled): the subtrees of <= 8192 samples under a longer parent run on the fused cascade
                      // (DESIGN 6.1).  Fields as MULFOLD.  Only the kernel variant built with GSRC executes it.
@@ -777,6 +780,112 @@ TEB_D void gmulfold_task(float2* S, const float* __restrict__ arena, const Signa
     }
 }
 
+// Two filters of one scale on ONE read of the global source (OP_GMULFOLD2): the source bins cross the SM's L2 port
+// once per pair instead of once per filter.  Arithmetic per filter as in gmulfold_task / mulfold_task.
+TEB_D void gmulfold2_task(float2* S, const float* __restrict__ arena, const SignalCtx& c, const Task& t, int lt) {
+    const int logk = t.c;
+    const float scale = ldexpf(1.0f, -(t.op >> 8));
+    const float* fa = arena + t.e;
+    const float* fb = arena + t.g;
+    const float2* G = c.gsrc;
+    const int da = t.d, db = t.a;
+    if (logk >= 2) {
+        const int n_dst = 1 << (t.b - logk);
+        const unsigned mask = (unsigned)t.f;
+        const int logcw = t.h & 0xff;
+        const int nch = __popc(mask) << (logcw - 2);
+        const float2 zero = make_float2(0.f, 0.f);
+        for (int m0 = lt; m0 < n_dst; m0 += 2 * t.nt) {
+            float2 accA[2] = {zero, zero}, accB[2] = {zero, zero};
+            unsigned rest = mask;
+            int cc = 0;
+            while (rest) {
+                const int i_chunk = (TEB_FFS(rest) - 1) << logcw;
+                rest &= rest - 1;
+                for (int sub = 0; sub < (1 << (logcw - 2)); ++sub, ++cc) {
+                    const int i = i_chunk + (sub << 2);
+                    float4 ga[2], gb[2];
+                    float2 z[2][4];
+                    TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                        const int m = m0 + j * t.nt;
+                        if (m < n_dst) {
+                            ga[j] = TEB_LDG(reinterpret_cast<const float4*>(fa) + m * nch + cc);
+                            gb[j] = TEB_LDG(reinterpret_cast<const float4*>(fb) + m * nch + cc);
+                            gload4(G + ((long long)m << logk) + i, z[j]);
+                        } else {
+                            ga[j] = gb[j] = float4{0.f, 0.f, 0.f, 0.f};
+                            z[j][0] = z[j][1] = z[j][2] = z[j][3] = zero;
+                        }
+                    }
+                    TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                        accA[j] = cfma_r(z[j][0], ga[j].x, accA[j]); accB[j] = cfma_r(z[j][0], gb[j].x, accB[j]);
+                        accA[j] = cfma_r(z[j][1], ga[j].y, accA[j]); accB[j] = cfma_r(z[j][1], gb[j].y, accB[j]);
+                        accA[j] = cfma_r(z[j][2], ga[j].z, accA[j]); accB[j] = cfma_r(z[j][2], gb[j].z, accB[j]);
+                        accA[j] = cfma_r(z[j][3], ga[j].w, accA[j]); accB[j] = cfma_r(z[j][3], gb[j].w, accB[j]);
+                    }
+                }
+            }
+            TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                const int m = m0 + j * t.nt;
+                if (m < n_dst) {
+                    S[swz(da + m)] = cmul_r(accA[j], scale);
+                    S[swz(db + m)] = cmul_r(accB[j], scale);
+                }
+            }
+        }
+    } else {
+        const int radix = t.h >> 8;
+        const int n_items = 1 << (t.b - 2);                    // 4 source bins per item
+        for (int it0 = lt; it0 < n_items; it0 += 2 * t.nt) {
+            float4 gga[2], ggb[2];
+            float2 zz[2][4];
+            TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                const int it = it0 + j * t.nt;
+                if (it < n_items) {
+                    gga[j] = TEB_LDG(reinterpret_cast<const float4*>(fa + 4 * it));
+                    ggb[j] = TEB_LDG(reinterpret_cast<const float4*>(fb + 4 * it));
+                    gload4(G + 4 * it, zz[j]);
+                } else {
+                    gga[j] = ggb[j] = float4{0.f, 0.f, 0.f, 0.f};
+                    zz[j][0] = zz[j][1] = zz[j][2] = zz[j][3] = make_float2(0.f, 0.f);
+                }
+            }
+            TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                const int it = it0 + j * t.nt;
+                if (it >= n_items) continue;
+                TEB_UNROLL for (int which = 0; which < 2; ++which) {
+                    const float4 g = which ? ggb[j] : gga[j];
+                    const int dst = which ? db : da;
+                    const float2 z0 = zz[j][0], z1 = zz[j][1], z2 = zz[j][2], z3 = zz[j][3];
+                    if (logk == 0) {
+                        const int o = swz(dst + 4 * it);
+                        float2 w0 = cmul_r(z0, g.x * scale);
+                        float2 w1 = cmul_r(z1, g.y * scale);
+                        float2 w2 = cmul_r(z2, g.z * scale);
+                        float2 w3 = cmul_r(z3, g.w * scale);
+                        if (radix == 1) {
+                            dft2<+1>(w0, w1);
+                            dft2<+1>(w2, w3);
+                        } else if (radix == 2) {
+                            float2 a0 = w0, a1 = w2, a2 = w1, a3 = w3;
+                            dft4<+1>(a0, a1, a2, a3);
+                            w0 = a0; w1 = a1; w2 = a2; w3 = a3;
+                        }
+                        S[o] = w0;
+                        S[o + 1] = w1;
+                        S[o + 2] = w2;
+                        S[o + 3] = w3;
+                    } else {
+                        const int o = swz(dst + 2 * it);
+                        S[o] = cmul_r(cfma_r(z0, g.x, cmul_r(z1, g.y)), scale);
+                        S[o + 1] = cmul_r(cfma_r(z2, g.z, cmul_r(z3, g.w)), scale);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Slot of bin -k in a bit-reversed spectrum when p is the slot of bin k: the highest set bit of p
 // stays, every bit below it flips (the mirror image inside p's dyadic block).
 TEB_D int mirror_slot(int p) { return p ? (p ^ ((1 << (31 - TEB_CLZ(p))) - 1)) : 0; }
@@ -1101,6 +1210,7 @@ TEB_D void exec_task(float2* S, const float2* twA, const float2* twB, const floa
         case OP_MULFOLD: mulfold_task(S, arena, t, lt); break;
         case OP_MULFOLD2: mulfold2_task(S, arena, t, lt); break;
         case OP_GMULFOLD: if (GSRC) gmulfold_task(S, arena, c, t, lt); break;
+        case OP_GMULFOLD2: if (GSRC) gmulfold2_task(S, arena, c, t, lt); break;
         case OP_LOADPAIR: loadpair_task(S, c, t, lt); break;
         case OP_STOREU: storeu_task(S, c, t, lt); break;
         case OP_LOADC: loadc_task(S, c, t, lt); break;

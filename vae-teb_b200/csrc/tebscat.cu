@@ -291,12 +291,19 @@ struct tebscat_plan {
     int64_t scratch_complex = 0;
     mutable std::map<cudaStream_t, float2*> scratch;
     mutable std::mutex scratch_mu;
+    float2* d_scratch_capture = nullptr;   // used while the launch stream is being captured into a CUDA graph (no allocation there)
     HostPipe pipe;
     std::mutex pipe_mu;
 };
 
 // the scratch of `p` for launches on `st` (allocated on first use; the plan's device is current)
 static int plan_scratch(const tebscat_plan* p, cudaStream_t st, float2** out) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone) {          // replays of one graph are ordered among themselves
+        *out = p->d_scratch_capture;
+        return TEBSCAT_OK;
+    }
     std::lock_guard<std::mutex> lock(p->scratch_mu);
     auto it = p->scratch.find(st);
     if (it == p->scratch.end()) {
@@ -419,6 +426,30 @@ static int validate_schedule(const tebscat_plan_desc& d, const int32_t* tasks, c
                 if (gsrc_extent && *gsrc_extent < (int64_t)t[3] + ((int64_t)1 << t[4])) *gsrc_extent = (int64_t)t[3] + ((int64_t)1 << t[4]);
                 break;
             }
+            case OP_GMULFOLD2: {
+                // two filters (e, g) and two destinations (d, a) on one read of the global source
+                const int log_dst = t[4] - t[5];
+                const int64_t n_dst = (int64_t)1 << (log_dst < 0 ? 0 : log_dst);
+                const int radix = t[10] >> 8, logcw = t[10] & 0xff;
+                if (t[4] < 2 || t[4] > 17 || t[5] < 0 || t[5] > t[4] || log_dst > kLog2TwMax ||
+                    !fits(t[6] & ~15, (t[6] & 15) + n_dst) || !fits(t[3] & ~15, (t[3] & 15) + n_dst) || t[7] < 0 || (t[7] & 3) ||
+                    t[9] < 0 || (t[9] & 3) || (t[5] == 0 && ((t[6] | t[3]) & 3)) || (t[5] == 1 && ((t[6] | t[3]) & 1)))
+                    return fail(TEBSCAT_EINVAL, "task %d: bad GMULFOLD2", i);
+                if (t[5] >= 2) {
+                    const int n_chunks = 1 << (t[5] - logcw);
+                    if (radix != 0 || logcw < 2 || logcw > t[5] || n_chunks > 32 || (unsigned)t[8] == 0u ||
+                        (n_chunks < 32 && ((unsigned)t[8] >> n_chunks) != 0u))
+                        return fail(TEBSCAT_EINVAL, "task %d: bad GMULFOLD2 chunk mask", i);
+                } else if (logcw != 0 || radix < 0 || radix > 2 || (radix && t[5] != 0)) {
+                    return fail(TEBSCAT_EINVAL, "task %d: bad GMULFOLD2 fused pass", i);
+                }
+                const size_t need = t[5] >= 2 ? (((size_t)1 << log_dst) << logcw) * __builtin_popcount((unsigned)t[8])
+                                              : ((size_t)1 << t[4]);
+                if ((size_t)t[7] + need > n_floats || (size_t)t[9] + need > n_floats)
+                    return fail(TEBSCAT_EINVAL, "task %d: GMULFOLD2 filter outside the arena", i);
+                if (gsrc_extent && *gsrc_extent < ((int64_t)1 << t[4])) *gsrc_extent = (int64_t)1 << t[4];
+                break;
+            }
             case OP_STOREB:
                 if (t[4] < 1 || t[6] != d.n_out || t[5] < 0 || t[8] < 0 || t[8] > kLog2TwMax || t[5] + t[6] > (1 << t[8]) ||
                     !fits(t[3], (int64_t)t[4] << t[8]) || t[7] < 0 || 2 * ((size_t)t[7] + (size_t)t[4]) > n_chan)
@@ -510,6 +541,8 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
 
     CU(cudaMalloc(&p->d_arena, n_floats * sizeof(float)));
     CU(cudaMalloc(&p->d_tw, tw.size() * sizeof(float2)));
+    if (p->scratch_complex)
+        CU(cudaMalloc(&p->d_scratch_capture, (size_t)p->n_sms * (size_t)p->scratch_complex * sizeof(float2)));
     // per-warp view of the schedule: record (step, warp) = the task whose thread range covers the warp
     std::vector<int32_t> wt((size_t)desc->n_steps * kWarps * kTaskInts, 0);
     for (int st = 0; st < desc->n_steps; ++st) {
@@ -544,6 +577,8 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     CU(cudaFuncGetAttributes(&fa1, scat1d_kernel<true>));
     CU(cudaFuncGetAttributes(&fa2, (scat1d_kernel<false, true>)));
     CU(cudaFuncSetAttribute((scat1d_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(prop.sharedMemPerBlockOptin - fa2.sharedSizeBytes)));
+    CU(cudaFuncSetAttribute((scat1d_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(prop.sharedMemPerBlockOptin - fa2.sharedSizeBytes)));
     CU(cudaFuncSetAttribute(scat1d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(prop.sharedMemPerBlockOptin - fa0.sharedSizeBytes)));
@@ -715,6 +750,7 @@ extern "C" void tebscat_plan_destroy(tebscat_plan* p) {
     cudaFree(p->d_chan);
     cudaFree(p->d_win);
     for (auto& kv : p->scratch) cudaFree(kv.second);
+    cudaFree(p->d_scratch_capture);
     delete p;
 }
 
@@ -821,7 +857,8 @@ extern "C" int tebscat_scat1d_profile_steps(const tebscat_plan* p, const float* 
                                             long long* step_clocks_host, void* stream) {
     g_launches = 0;
     if (!p || !x_dev || !S_dev || !step_clocks_host || B < 1) return fail(TEBSCAT_EINVAL, "null argument");
-    if (p->gsrc_extent) return fail(TEBSCAT_EUNSUPPORTED, "step profiling is not built for schedules with a global source");
+    if (p->gsrc_extent && !p->scratch_complex)
+        return fail(TEBSCAT_EUNSUPPORTED, "step profiling needs a schedule that starts from the signal");
     ON_DEVICE(p->device);
     long long* d_prof = nullptr;
 #ifdef TEBSCAT_PROF_PHASES
@@ -834,6 +871,11 @@ extern "C" int tebscat_scat1d_profile_steps(const tebscat_plan* p, const float* 
     KParams kp = p->kp;
     kp.prof = d_prof;
     const int grid = (int)(B < (int64_t)p->n_sms ? B : (int64_t)p->n_sms);
+    if (p->scratch_complex) {
+        if (int rc = plan_scratch(p, (cudaStream_t)stream, &kp.gscratch)) { cudaFree(d_prof); return rc; }
+        kp.gscratch_stride = p->scratch_complex;
+        scat1d_kernel<true, true><<<grid, p->desc.n_threads, p->smem_bytes, (cudaStream_t)stream>>>(kp, x_dev, S_dev, (long long)B);
+    } else
     scat1d_kernel<true><<<grid, p->desc.n_threads, p->smem_bytes, (cudaStream_t)stream>>>(kp, x_dev, S_dev, (long long)B);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);

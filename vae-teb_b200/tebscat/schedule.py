@@ -43,6 +43,7 @@ from . import filterbank as fbk
 OP_NOP, OP_LOAD, OP_FFT, OP_MULFOLD, OP_STOREB, OP_STOREZ, OP_TINY, OP_MULFOLD2, OP_LOADPAIR, OP_STOREU = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 OP_LOADC, OP_STOREC = 10, 11
 OP_GMULFOLD = 12                  # MULFOLD with its source spectrum in global memory (fused subtrees of the large-support level)
+OP_GMULFOLD2 = 13                 # two filters (the partners of a packed pair) on one read of the global source
 FFT_INV, FFT_MOD, FFT_FUSE_FWD, FFT_PACK = 1, 2, 4, 8
 TASK_INTS = 12
 
@@ -126,6 +127,7 @@ class Chain:
     name: str
     stages: List[List[TaskSpec]]
     after: List['Chain'] = field(default_factory=list)
+    waits: List['Chain'] = field(default_factory=list)  # ordering only: must be complete before this chain starts
     reads: List[Buf] = field(default_factory=list)     # buffers read by stage 0
     owns: List[Buf] = field(default_factory=list)      # allocated when the chain starts
     frees_own_at_end: bool = False
@@ -313,11 +315,14 @@ def _fuse_first_inverse_pass(mulfolds: List[TaskSpec], stages: List[List[TaskSpe
     every MULFOLD feeding it is a plain k=1 product, let the MULFOLD do that pass on the four
     slots each of its threads owns and drop the pass (core :307-312 in one round trip)."""
     r0 = radix_split(n)[-1]
-    if r0 <= 2 and len(radix_split(n)) > 1 and all(m.op in (OP_MULFOLD, OP_GMULFOLD) and m.c == 0 for m in mulfolds):
+    if r0 <= 2 and len(radix_split(n)) > 1 and all(m.op in (OP_MULFOLD, OP_GMULFOLD, OP_GMULFOLD2) and m.c == 0 for m in mulfolds):
         first = stages[0][0]
         if first.op == OP_FFT and first.c == r0 and first.d == r0 and (first.e & FFT_INV) and not (first.e & (FFT_MOD | FFT_FUSE_FWD)):
             for m in mulfolds:
-                m.g = r0
+                if m.op == OP_GMULFOLD2:
+                    m.h |= r0 << 8
+                else:
+                    m.g = r0
                 m.instr += 10.0
             return stages[1:]
     return stages
@@ -371,6 +376,11 @@ def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_of
                     h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst + 1, trip=trip)
 
 
+AUTO_SCRATCH_GAIN = 0.97          # 'auto': the scratch layout must be modelled at least 3 % faster to be chosen
+GSRC_PAIRS = os.environ.get('TEBSCAT_GSRC_PAIRS', '1') != '0'     # partners of a packed pair share one read of a global source
+GSRC_BYTES_PER_CYCLE = float(os.environ.get('TEBSCAT_GSRC_BPC', '64'))   # cost-model knob (tools/ab_u0_scratch.py)
+
+
 def _gmulfold(arena: _Arena, src_off: int, log_src: int, logk: int, dst, filt_off: int) -> TaskSpec:
     """MULFOLD whose source is a spectrum of 2^log_src bins in GLOBAL memory (csrc: gmulfold_task): the parent is
     too long for one SM, the result (<= 8192 bins) lands in shared memory.  Every trip has its filter and source
@@ -381,14 +391,42 @@ def _gmulfold(arena: _Arena, src_off: int, log_src: int, logk: int, dst, filt_of
         logcw = _Arena.chunk_log2(logk)
         nch = bin(mask).count('1') << (logcw - 2)
         filt_off = arena.compact(filt_off, logk, mask)
-        work, lat, instr, trip = -(-(1 << log_dst) // 4), 900.0 + 1000.0 * nch, 110.0 + 130.0 * nch, 350.0 + 900.0 * nch
+        work, lat, instr, trip = -(-(1 << log_dst) // 4), 900.0 + 1100.0 * nch, 110.0 + 130.0 * nch, 350.0 + 1000.0 * nch
     else:
         mask = 0
         work, lat, instr, trip = -(-(1 << (log_src - 2)) // 4), 2400.0, 330.0, 2100.0
+    # the source comes through the SM's L2 port at about 64 bytes per cycle (measured on the headline and the
+    # production configuration, tools/ab_u0_scratch.py: +1000 cycles per 64 KB read): a per-trip cost when every
+    # thread of the CTA works on it
+    src_bytes = 8.0 * ((1 << log_src) if logk < 2 else (1 << log_dst) * 4 * nch)
+    per_trip = (src_bytes / GSRC_BYTES_PER_CYCLE) / max(1.0, work / 512.0)
+    lat, trip = lat + per_trip, trip + per_trip
     if mask >= 1 << 31:
         mask -= 1 << 32
     return TaskSpec(OP_GMULFOLD, work, lat, instr, a=int(src_off), b=log_src, c=logk, d=dst, e=filt_off, f=mask,
                     h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst, trip=trip)
+
+
+def _gmulfold2(arena: _Arena, log_src: int, logk: int, dst_a, dst_b, filt_a: int, filt_b: int) -> TaskSpec:
+    """Two filters of one scale on ONE read of the global source (csrc: gmulfold2_task): the partners of a packed
+    pair.  Both filters are compacted to the union of their active chunks."""
+    log_dst = log_src - logk
+    if logk >= 2:
+        mask = arena.chunk_mask(filt_a, logk) | arena.chunk_mask(filt_b, logk)
+        logcw = _Arena.chunk_log2(logk)
+        nch = bin(mask).count('1') << (logcw - 2)
+        filt_a, filt_b = arena.compact(filt_a, logk, mask), arena.compact(filt_b, logk, mask)
+        work, lat, instr, trip = -(-(1 << log_dst) // 2), 900.0 + 1100.0 * nch, 120.0 + 180.0 * nch, 350.0 + 1000.0 * nch
+    else:
+        mask, logcw = 0, 0
+        work, lat, instr, trip = -(-(1 << (log_src - 2)) // 2), 2400.0, 300.0, 2100.0
+    src_bytes = 8.0 * ((1 << log_src) if logk < 2 else (1 << log_dst) * 4 * nch)
+    per_trip = (src_bytes / GSRC_BYTES_PER_CYCLE) / max(1.0, work / 512.0)
+    lat, trip = lat + per_trip, trip + per_trip
+    if mask >= 1 << 31:
+        mask -= 1 << 32
+    return TaskSpec(OP_GMULFOLD2, work, lat, instr, a=dst_b, b=log_src, c=logk, d=dst_a, e=filt_a, f=mask, g=filt_b,
+                    h=logcw, sexp=logk + log_dst, trip=trip)
 
 
 # ------------------------------------------------------------------------------------
@@ -520,7 +558,19 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
     # root: pad + forward transform of the signal (core/scattering1d.py:278-280)
     u0 = Buf(1 << n, 'U0')
     scratch = global_u0 == 'scratch'
-    if scratch:
+    split = global_u0 == 'split'
+    if split:
+        # U0 stays in shared memory for the order-0 leaf and the SUBSAMPLED first-order filters, is copied to the
+        # per-CTA global scratch on the side, and is dropped from shared memory before the full-length filters
+        # (k1 = 0: the pairs whose working set fills the SM) start: those read it through OP_GMULFOLD.
+        root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
+                     _merge_local_passes(_fft_stages((u0, 0), n, 1, 'fwd')), owns=[u0], depth=0)
+        chains.append(root)
+        chains.append(Chain('S0', [[leaf((u0, 0), n, 0, ())]], after=[root], reads=[u0], depth=1))   # :285-292
+        park = Chain('park', [[TaskSpec(OP_STOREC, 1 << n, 300.0, 12.0, a=(u0, 0), b=1 << n)]], after=[root], reads=[u0],
+                     depth=1)
+        chains.append(park)
+    elif scratch:
         # U0 is computed here but PARKED in a per-CTA global scratch (L2-resident) right after its transform: its
         # 2^n slots are free for the rest of the signal, and every consumer reads it through OP_GMULFOLD
         root = Chain('root', [[TaskSpec(OP_LOAD, 1 << n, 300.0, 16.0, a=(u0, 0))]] +
@@ -536,10 +586,13 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
                      _merge_local_passes(_fft_stages((u0, 0), n, 1, 'fwd')), owns=[u0], depth=0)
         chains.append(root)
         chains.append(Chain('S0', [[leaf((u0, 0), n, 0, ())]], after=[root], reads=[u0], depth=1))   # :285-292
-    from_u0 = [root] if (scratch or not global_u0) else []
-    reads_u0 = [] if global_u0 else [u0]
+    from_u0 = [root] if (scratch or split or not global_u0) else []
+    reads_u0 = [] if (global_u0 and not split) else [u0]
+    subsampled_first: List[Chain] = []                 # split mode: the chains that still read U0 from shared memory
 
     def first_mulfold(k1: int, dst, filt_off: int) -> TaskSpec:
+        if split:
+            return _gmulfold(arena, 0, n, k1, dst, filt_off) if k1 == 0 else _mulfold(arena, (u0, 0), n, k1, dst, filt_off)
         return _gmulfold(arena, 0, n, k1, dst, filt_off) if global_u0 else _mulfold(arena, (u0, 0), n, k1, dst, filt_off)
 
     # first order, batched by subsampling k1 (:300-318)
@@ -551,7 +604,7 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
         if global_u0 and n - k1 > LOG2_NP_MAX:
             continue                                                   # stays on the level's own kernels
         groups.setdefault(k1, []).append(n1)
-    for k1 in sorted(groups):
+    for k1 in sorted(groups, reverse=split):           # (split mode: the subsampled filters are built -- and start -- first)
         l1 = n - k1
         pack1 = packing and l1 >= 4
         # entries (a, b): filters a and b share the forward transform; one batch = `per_batch` entries
@@ -562,12 +615,22 @@ def build_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, max_order: int
             lo = len(batch)
             hi = sum(1 for _, b in batch if b is not None)             # pairs come first
             x1 = Buf((lo + hi) << l1, 'U1[k1=%d:%d]' % (k1, batch[0][0]))
-            mf = [first_mulfold(k1, (x1, i << l1), psi1_off[a]) for i, (a, _) in enumerate(batch)]
-            mf += [first_mulfold(k1, (x1, (lo + i) << l1), psi1_off[b])
-                   for i, (_, b) in enumerate(batch) if b is not None]
+            if global_u0 and not split and GSRC_PAIRS:
+                # global source: the partners of a pair share ONE read of U0
+                mf = [_gmulfold2(arena, n, k1, (x1, i << l1), (x1, (lo + i) << l1), psi1_off[a], psi1_off[b])
+                      if b is not None else first_mulfold(k1, (x1, i << l1), psi1_off[a]) for i, (a, b) in enumerate(batch)]
+            else:
+                mf = [first_mulfold(k1, (x1, i << l1), psi1_off[a]) for i, (a, _) in enumerate(batch)]
+                mf += [first_mulfold(k1, (x1, (lo + i) << l1), psi1_off[b])
+                       for i, (_, b) in enumerate(batch) if b is not None]
             st = [mf] + _merge_local_passes(
                 _fuse_first_inverse_pass(mf, _fft_stages((x1, 0), l1, lo, 'pair', hi=hi), l1))             # :307-318
-            c1 = Chain(x1.name, st, after=list(from_u0), reads=list(reads_u0), owns=[x1], depth=1)
+            if split and k1 == 0:
+                c1 = Chain(x1.name, st, after=[root], waits=[park] + list(subsampled_first), owns=[x1], depth=1)
+            else:
+                c1 = Chain(x1.name, st, after=list(from_u0), reads=list(reads_u0), owns=[x1], depth=1)
+                if split:
+                    subsampled_first.append(c1)
             if hi:
                 c1.shrink.append((pack_stage(st), x1, lo << l1))
             chains.append(c1)
@@ -844,7 +907,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
                 if pool.fill[h] and not pool.busy[h]:
                     start_flush(h)
         # ---- start chains whose inputs are complete ------------------------------------
-        startable = [c for c in pending if all(a.done_step >= 0 and a.done_step < step_idx for a in c.after)]
+        startable = [c for c in pending if all(a.done_step >= 0 and a.done_step < step_idx for a in c.after + c.waits)]
         startable.sort(key=lambda c: -c.priority)
         demand = sum(sum(_want_threads(t.work, t.tpi) for t, done in zip(c.stages[c.stage], c.issued) if not done)
                      for c in active)
@@ -1011,6 +1074,16 @@ def task_accesses(t, log2_Np):
             it = np.arange(1 << (log_src - 2))
             w_ = 4 >> logk
             add(d + w_ * it[:, None] + np.arange(w_)[None, :], it % nt, True)
+    elif op == OP_GMULFOLD2:                            # two destinations: d (filter A) and a (filter B)
+        log_src, logk = b, c
+        if logk >= 2:
+            m = np.arange(1 << (log_src - logk))
+            add(d + m, m % nt, True); add(a + m, m % nt, True)
+        else:
+            it = np.arange(1 << (log_src - 2))
+            w_ = 4 >> logk
+            add(d + w_ * it[:, None] + np.arange(w_)[None, :], it % nt, True)
+            add(a + w_ * it[:, None] + np.arange(w_)[None, :], it % nt, True)
     elif op == OP_LOADPAIR:
         s_ = a + np.arange(1 << log2_Np)
         for w in range(nt // 32):
@@ -1257,9 +1330,12 @@ def emit(steps) -> Tuple[np.ndarray, np.ndarray]:
             np.asarray(ranges, dtype=np.int32).reshape(-1, 2))
 
 
-def u0_in_scratch() -> bool:
-    """TEBSCAT_U0_GLOBAL=1: the signal's spectrum is parked in a per-CTA global scratch (A/B switch)."""
-    return os.environ.get('TEBSCAT_U0_GLOBAL', '0') == '1'
+def u0_in_scratch():
+    """TEBSCAT_U0_GLOBAL: where the consumers of the signal's spectrum U0 find it -- '0' shared memory (False),
+    '1' a per-CTA global scratch for every consumer ('scratch'), 'split' shared memory for the subsampled first-order
+    filters and the scratch for the full-length ones ('split').  A/B switch; build_plan's `tune` overrides it."""
+    v = os.environ.get('TEBSCAT_U0_GLOBAL', '0')
+    return {'0': False, '1': 'scratch', 'split': 'split', 'auto': 'auto'}.get(v, False)
 
 
 def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int = 64,
@@ -1267,7 +1343,24 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     """`tune` overrides scheduler knobs (tools/sweep_sched.py): batch_slots, child_slots, pool_slots,
     pack_gain, open_demand, u0_scratch."""
     tune = dict(tune or {})
-    scratch = bool(tune.get('u0_scratch', u0_in_scratch()))
+    scratch = tune.get('u0_scratch', u0_in_scratch())      # False, True ('scratch': every consumer), 'split' or 'auto'
+    if scratch == 'auto':
+        # both layouts through the cost model: the scratch pays for the L2 traffic of its multiplies, shared memory
+        # for the slots U0 occupies; second-order cascades with full-length pairs gain, first-order ones lose
+        if max_order != 2:
+            scratch = False
+        else:
+            t2 = dict(tune)
+            a = build_plan(J, N, Q, T, max_order, max_parallel, oversampling, dict(t2, u0_scratch=False))
+            try:
+                b = build_plan(J, N, Q, T, max_order, max_parallel, oversampling, dict(t2, u0_scratch='scratch'))
+            except NotImplementedError:
+                return a
+            return b if b.stats['est_cycles'] < AUTO_SCRATCH_GAIN * a.stats['est_cycles'] else a
+    if scratch is True:
+        scratch = 'scratch'
+    if scratch == 'split' and max_order != 2:
+        scratch = False
     Q1 = fbk._as_Q1(Q)
     geo = fbk.build_geometry(N, J, Q1, T)
     if geo.J_pad > LOG2_NP_MAX:
@@ -1286,7 +1379,7 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
         arena = _Arena()
         chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling,
                                                    child_slots=tune.get('child_slots'),
-                                                   global_u0='scratch' if scratch else False)
+                                                   global_u0=scratch or False)
         try:
             steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel,
                                                        pool_slots=pool_slots, pack_gain=tune.get('pack_gain', 0.97),
@@ -1315,6 +1408,7 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     plan = ScatPlan(J, Q1, T, N, max_order, geo, bank, keys, n_out, arena.finish(), tasks, ranges,
                     np.asarray(chan, dtype=np.int32), logical + logical // 16, N_THREADS, stats)
     plan.scratch_complex = (1 << geo.J_pad) if scratch else 0
+    plan.u0_mode = scratch or 'shared'
     return plan
 
 
