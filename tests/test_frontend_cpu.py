@@ -173,7 +173,8 @@ def test_missing_library_fails_loudly(monkeypatch):
 def test_op_by_op_plan_workspace_geometry():
     """Host logic of the op-by-op level: the second-order workspace follows the longest child -- half the padded length
     normally, the full length when oversampling leaves a child un-subsampled (core/scattering1d.py:344-345) -- and the
-    configurations the fused schedule cannot hold are exactly the ones with output-rate lengths of 2048 and more."""
+    configurations the fused schedule cannot hold are the ones with output-rate lengths of 2048 and more while U0
+    lives in shared memory, of 8192 with U0 in the global scratch."""
     from tebscat.large import LargePlan
     from tebscat.schedule import build_plan
     assert LargePlan(6, 9000, 4, 64, 2).max_l2 == 13                      # Np = 2^14: children at most Np / 2
@@ -182,8 +183,13 @@ def test_op_by_op_plan_workspace_geometry():
     assert all(k['mul'][2] == 0 for e in lp.first for k in e['kids'])     # logk = 0 for every child
     assert LargePlan(6, 4800, 8, 64, 1).max_l2 == 1                       # first order only: no children
     with pytest.raises(NotImplementedError):
-        build_plan(4, 4827, 8, 4, 2)                                      # lf = 11
-    build_plan(4, 4827, 8, 8, 2)                                          # lf = 10 fits
+        build_plan(4, 4827, 8, 4, 2, tune=dict(u0_scratch=False))         # lf = 11 with U0 in shared memory (round 1)
+    build_plan(4, 4827, 8, 8, 2, tune=dict(u0_scratch=False))             # lf = 10 fits
+    # with U0 parked in the global scratch (the default) output-rate lengths of 2048 and 4096 fit too; 8192 does not
+    assert build_plan(4, 4827, 8, 4, 2).scratch_complex == 8192           # lf = 11
+    build_plan(4, 4827, 8, 2, 2)                                          # lf = 12
+    with pytest.raises(NotImplementedError):
+        build_plan(4, 4827, 8, 1, 2)                                      # lf = 13
 
 
 def test_plan_validation_runs_before_any_device_call():

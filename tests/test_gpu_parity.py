@@ -270,21 +270,26 @@ def test_forward_is_reentrant_across_host_threads_and_streams():
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize('cfg', [(4, 4827, 8, 4, 2), (3, 4223, 1, 4, 1), (2, 4085, 1, 2, 2)])
-def test_configurations_beyond_the_fused_schedule(cfg):
+@pytest.mark.parametrize('layout', ['shared', 'scratch'])
+@pytest.mark.parametrize('cfg', [(4, 4827, 8, 4, 2), (3, 4223, 1, 4, 1), (2, 4085, 1, 2, 2), (4, 4827, 8, 1, 2)])
+def test_configurations_beyond_the_fused_schedule(cfg, layout, monkeypatch):
     """Output-rate lengths of 2048 samples and more (T <= 4 at a padded length of 8192) do not fit the fused
-    single-kernel schedule (build_plan says so); the frontend then serves them on the op-by-op CUDA level of
-    tebscat/large.py -- same parity bar, forward and backward."""
+    single-kernel schedule while U0 lives in shared memory (build_plan says so); the frontend then serves them on the
+    op-by-op CUDA level of tebscat/large.py -- same parity bar, forward and backward.  With U0 parked in the global
+    scratch (the default layout) lengths of 2048 and 4096 fit the fused kernel; 8192 (T = 1) stays op by op."""
     from tebscat import Scattering1D
     from tebscat.schedule import build_plan
     from oracle.scattering1d_grad_oracle import GradOracle
     J, N, Q, T, mo = cfg
-    with pytest.raises(NotImplementedError):
-        build_plan(J, N, Q, T, mo)
+    monkeypatch.setenv('TEBSCAT_U0_GLOBAL', '0' if layout == 'shared' else '1')
+    fused = layout == 'scratch' and T > 1
+    if not fused:
+        with pytest.raises(NotImplementedError):
+            build_plan(J, N, Q, T, mo)
     S = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
     x = torch.randn(3, N, generator=torch.Generator().manual_seed(J)).cuda().requires_grad_(True)
     out, _ = S(x)
-    assert S._op_by_op
+    assert S._op_by_op == (not fused)
     ref = ScatteringOracle(J, N, Q, T, mo)(x.detach().cpu().numpy())
     got = out.detach().cpu().numpy().astype(np.float64)
     assert got.shape == ref.shape
@@ -294,6 +299,48 @@ def test_configurations_beyond_the_fused_schedule(cfg):
     (out * w.cuda()).sum().backward()
     _, g64 = GradOracle(J, N, Q, T, mo).vjp(x.detach().cpu().numpy(), w.numpy())
     assert rel_l2(x.grad.cpu().numpy(), g64, axis=-1).max() < 1e-5
+
+
+@pytest.mark.parametrize('name', ['H', 'P', 'K'])
+def test_u0_layouts_agree_bit_for_bit(name, monkeypatch):
+    """Where the consumers of U0 find it -- a per-CTA global scratch (default: OP_STOREC after the root transform,
+    OP_GMULFOLD / OP_GMULFOLD2 multiplies) or shared memory (round 1) -- changes the schedule, never the arithmetic:
+    same bits, on a batch of several signals per CTA (the scratch is rewritten for every signal), eagerly, on two
+    streams at once (one scratch per stream) and replayed from a CUDA graph (capture-time scratch)."""
+    from tebscat import Scattering1D
+    from helpers import CONFIGS
+    J, N, Q, T, mo = CONFIGS[name]
+    x = torch.randn(148 * 3 + 5, N, generator=torch.Generator().manual_seed(3)).cuda()
+    S1 = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    a = S1(x)[0].clone()
+    assert S1._schedule().scratch_complex == 1 << S1.J_pad
+    monkeypatch.setenv('TEBSCAT_U0_GLOBAL', '0')
+    S0 = Scattering1D(J, N, Q, max_order=mo, T=T).cuda()
+    assert S0._schedule().scratch_complex == 0
+    assert torch.equal(S0(x)[0], a)
+    # two streams at once
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        b1 = [S1(x)[0] for _ in range(3)]
+    with torch.cuda.stream(s2):
+        b2 = [S1(x.flip(0))[0] for _ in range(3)]
+    torch.cuda.synchronize()
+    assert all(torch.equal(b, a) for b in b1) and all(torch.equal(b, a.flip(0)) for b in b2)
+    # CUDA graph
+    xs = x.clone()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        S1(xs)
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(g):
+        og = S1(xs)[0]
+    xs.copy_(x.flip(0))
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(og, a.flip(0))
 
 
 @pytest.mark.gpu

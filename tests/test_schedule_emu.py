@@ -199,3 +199,30 @@ def test_fused_subtrees_of_the_large_support_level_match_oracle(cfg):
             out = np.full((2, len(keys), ref.shape[-1]), np.nan, np.float32)
             emu_forward_gsrc(plan, U1, out, chan[(n1, done[0])] - chan[(plan.head, done[0])])
             check(out, [chan[(n1, n2)] for n2 in done])
+
+
+@pytest.mark.skipif(not emu_available(), reason='host emulator not built')
+@pytest.mark.parametrize('name', ['H', 'P', 'S', 'T', 'K'])
+def test_u0_layouts_agree_bit_for_bit(name):
+    """U0 parked in the per-CTA global scratch (default), kept in shared memory (round 1), or split between the two:
+    different schedules, the same arithmetic -- identical bits through the host emulator; with a global source the
+    partners of a packed pair share one read (OP_GMULFOLD2)."""
+    from tebscat.schedule import OP_GMULFOLD, OP_GMULFOLD2, OP_STOREC
+    J, N, Q, T, mo = CONFIGS[name]
+    x = np.random.default_rng(5).standard_normal((2, N)).astype(np.float32)
+    outs = {}
+    for mode in (False, 'scratch', 'split'):
+        p = build_plan(J, N, Q, T, mo, tune=dict(u0_scratch=mode))
+        ops = set(int(v) & 0xff for v in p.tasks[:, 0])
+        if mode == 'scratch':
+            assert p.scratch_complex == 1 << p.geo.J_pad and OP_STOREC in ops and OP_GMULFOLD2 in ops
+            # the step that parks U0 ends in a CTA barrier
+            for b, e in p.steps:
+                if any((int(r[0]) & 0xff) == OP_STOREC for r in p.tasks[b:e]):
+                    assert not any(int(r[11]) & 1 for r in p.tasks[b:e])
+        elif mode is False:
+            assert p.scratch_complex == 0 and not ({OP_GMULFOLD, OP_GMULFOLD2, OP_STOREC} & ops)
+        outs[mode] = emu_forward(p, x)
+    assert np.array_equal(outs[False], outs['scratch'])
+    assert np.array_equal(outs[False], outs['split'])
+    assert np.isfinite(outs[False]).all()

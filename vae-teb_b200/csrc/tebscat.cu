@@ -1194,6 +1194,7 @@ extern "C" int tebscat_phase_plan_create(const tebscat_phase_desc* d, tebscat_pl
                                          const int32_t* i_idx, const int32_t* j_idx, const float* powers,
                                          tebscat_phase_plan** out) {
     if (!stage_a) return fail(TEBSCAT_EINVAL, "null argument");
+    if (stage_a->gsrc_extent) return fail(TEBSCAT_EINVAL, "a stage-A schedule cannot read a global source");
     return phase_plan_create_impl(d, stage_a, stage_a->device, G_host, i_idx, j_idx, powers, out);
 }
 
@@ -1350,6 +1351,7 @@ extern "C" int tebscat_phase_plan_attach_pair_plan(tebscat_phase_plan* p, tebsca
     if (pair_plan->device != p->device || pair_plan->desc.N != p->desc.N || pair_plan->desc.n_out != p->desc.n_out ||
         pair_plan->desc.n_paths < 1 || pair_plan->desc.n_paths > kMaxPairRows)
         return fail(TEBSCAT_EINVAL, "pair plan does not match the phase description");
+    if (pair_plan->gsrc_extent) return fail(TEBSCAT_EINVAL, "a pair-stage schedule cannot read a global source");
     std::lock_guard<std::mutex> lock(p->mu);
     tebscat_plan_destroy(p->pair_plan);
     p->pair_plan = pair_plan;
@@ -1748,6 +1750,7 @@ extern "C" int tebscat_large_set_tile_plan(tebscat_large* g, int log2_len, int k
         (slots & ((1 << log2_len) - 1)))
         return fail(TEBSCAT_EINVAL, "bad tile plan");
     if (plan->device != g->device) return fail(TEBSCAT_EINVAL, "tile plan lives on another device");
+    if (plan->gsrc_extent) return fail(TEBSCAT_EINVAL, "a tile schedule cannot read a global source");
     const int z = slots > 8192 ? 1 : 0;
     tebscat_plan_destroy(g->tile[log2_len][kind][z]);
     g->tile[log2_len][kind][z] = plan;

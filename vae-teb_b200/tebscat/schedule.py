@@ -378,7 +378,11 @@ def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_of
 
 AUTO_SCRATCH_GAIN = 0.97          # 'auto': the scratch layout must be modelled at least 3 % faster to be chosen
 GSRC_PAIRS = os.environ.get('TEBSCAT_GSRC_PAIRS', '1') != '0'     # partners of a packed pair share one read of a global source
-GSRC_BYTES_PER_CYCLE = float(os.environ.get('TEBSCAT_GSRC_BPC', '64'))   # cost-model knob (tools/ab_u0_scratch.py)
+# Cost-model knob: bytes per cycle at which a global-source multiply is charged for its source.  Measured, the
+# source costs about 64-100 B/cycle/SM of L2 port time -- but the schedules built AS IF it were free are the fastest
+# on the device (tools/ab_u0_scratch.py: 507 k signals/s against 493 k with 64 B/cycle at the headline configuration):
+# the list scheduler otherwise spreads those multiplies over thinner steps to "hide" a cost it cannot hide.
+GSRC_BYTES_PER_CYCLE = float(os.environ.get('TEBSCAT_GSRC_BPC', 'inf'))
 
 
 def _gmulfold(arena: _Arena, src_off: int, log_src: int, logk: int, dst, filt_off: int) -> TaskSpec:
@@ -1331,10 +1335,12 @@ def emit(steps) -> Tuple[np.ndarray, np.ndarray]:
 
 
 def u0_in_scratch():
-    """TEBSCAT_U0_GLOBAL: where the consumers of the signal's spectrum U0 find it -- '0' shared memory (False),
-    '1' a per-CTA global scratch for every consumer ('scratch'), 'split' shared memory for the subsampled first-order
-    filters and the scratch for the full-length ones ('split').  A/B switch; build_plan's `tune` overrides it."""
-    v = os.environ.get('TEBSCAT_U0_GLOBAL', '0')
+    """TEBSCAT_U0_GLOBAL: where the consumers of the signal's spectrum U0 find it -- '1' (default) a per-CTA global
+    scratch for every consumer ('scratch': measured +2.7 .. +4.4 % on the headline, production and J=4 configurations,
+    profiles/r02h_ab_u0_scratch2.txt), '0' shared memory (False, the round-1 layout), 'split' shared memory for the
+    subsampled first-order filters and the scratch for the full-length ones, 'auto' by the cost model.  A/B switch;
+    build_plan's `tune` overrides it."""
+    v = os.environ.get('TEBSCAT_U0_GLOBAL', '1')
     return {'0': False, '1': 'scratch', 'split': 'split', 'auto': 'auto'}.get(v, False)
 
 
