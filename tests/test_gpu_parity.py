@@ -357,7 +357,7 @@ def test_analysis_window_on_every_level(cfg):
     else:
         J, N, Q, T, mo = CONFIGS[name]
     if force_T is not None:
-        J, N, Q, T, mo = 6, 4800, 8, 4, 1                 # output rate 2048 at Np = 8192: op-by-op level
+        J, N, Q, T, mo = 6, 4800, 8, 1, 1                 # output rate 8192 at Np = 8192 (no averaging): op-by-op level
     g = torch.Generator().manual_seed(11)
     x = torch.randn(3, N, generator=g).cuda()
     w = torch.linspace(0.2, 1.0, N).cuda() * torch.cos(torch.linspace(0, 3.0, N)).cuda().abs()
