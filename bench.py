@@ -345,7 +345,7 @@ def run_gpu(args):
                                           'note': 'the same pinned H2D + D2H chunks on the same streams with the kernel '
                                                   'left out, all ranks at once (tebscat_scat1d_host_copies_only)'},
                     'frac_of_copy_ceiling': e2e_value / copy_value,
-                    'pipeline': '3 slots of 1184 signals: H2D, kernel and D2H on separate streams'},
+                    'pipeline': '3 slots of up to 1184 signals (chunk sizes ramp 148, 296, 592 up and down at the ends): H2D, kernel and D2H on separate streams'},
             'gpu_launches': launches,
             # 554 flop/B -- the cascade is bound by the FP32 pipe (with shared-memory bandwidth as the
             # co-limit), not by HBM; the HBM figures are reported beside it

@@ -101,10 +101,13 @@ def test_batch_shape_agnostic_and_views():
     assert e.shape[0] == 0
 
 
-def test_host_entry_point_matches_device_entry_point():
+@pytest.mark.parametrize('B', [2500, 6000])
+def test_host_entry_point_matches_device_entry_point(B):
+    """B = 2500: a few uniform chunks; B = 6000: the ramped chunk sizes of long batches (148, 296, 592 signals up and
+    down around full chunks of 1184 and one partial chunk)."""
     J, N, Q, T, mo = CONFIGS['H']
     S = module_of('H')
-    x = torch.randn(2500, N).pin_memory()          # > 2 chunks of the host pipeline
+    x = torch.randn(B, N, generator=torch.Generator().manual_seed(B)).pin_memory()
     h = S.scattering_host(x)
     d, _ = S(x.cuda())
     assert torch.equal(h, d.cpu())
