@@ -233,19 +233,24 @@ def run_gpu(args):
         pm = KymatioPhaseScattering1D(J=J, Q=Q, T=T, shape=N, device=dev)
         PB = args.phase_batch                                          # BASELINE configs[2]: 8192 FHR x UP pairs
         xb = x_dev[:PB]
-        pm(xb[:512], compute_phase=False, compute_cross_phase=True)    # builds the plans, warms up
+        pm(xb[:512], compute_phase=False, compute_cross_phase=True)    # builds the plans
+        pm(xb, compute_phase=False, compute_cross_phase=True)          # warm-up at the full batch (workspaces, allocator)
         torch.cuda.synchronize()
         ph = pm._dev_plan(local).handle
         lib = _lib.load()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 2
+        reps = 3
         _lib.check(lib.tebscat_phase_plan_profile(ph, 1))
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
         p0.record()
-        for _ in range(reps):
+        marks[0].record()
+        for r in range(reps):
             po = pm(xb, compute_phase=False, compute_cross_phase=True)['cross_phase_corr']
+            marks[r + 1].record()
         p1.record()
         torch.cuda.synchronize()
         pms = p0.elapsed_time(p1) / reps
+        rep_ms = [marks[r].elapsed_time(marks[r + 1]) for r in range(reps)]
         a_ms, b_ms, n_chunks = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
         _lib.check(lib.tebscat_phase_plan_profile_read(ph, ctypes.byref(a_ms), ctypes.byref(b_ms), ctypes.byref(n_chunks)))
         _lib.check(lib.tebscat_phase_plan_profile(ph, 0))
@@ -258,7 +263,7 @@ def run_gpu(args):
         tf32_peak = bf16_sustained / 2 if bf16_sustained else 1125.0
         ach = tensor_flops / stage_b_s / 1e12
         phase = {'metric': 'cross-channel phase scattering FHR x UP pairs/s (J=6,Q=8,N=4800, 741 pairs)',
-                 'value': PB / (pms * 1e-3), 'unit': 'signal-pairs/s', 'batch': PB, 'ms': pms,
+                 'value': PB / (pms * 1e-3), 'unit': 'signal-pairs/s', 'batch': PB, 'ms': pms, 'ms_per_pass': rep_ms,
                  'config': 'BASELINE configs[2]: batch %d two-channel signals, N=4800, all 741 pairs; output %.2f GB per pass' % (
                      PB, PB * n_pairs * n_po * 4 / 1e9),
                  'stage_ms': {'stage_a': a_ms.value / reps, 'stage_b': b_ms.value / reps, 'chunks': n_chunks.value // reps,
