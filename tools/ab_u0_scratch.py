@@ -19,6 +19,8 @@ from tebscat import schedule as sch
 CFGS = [(6, 4800, 8, 64, 2), (11, 5760, 4, 16, 1), (4, 4096, 8, 16, 2), (6, 4096, 8, 64, 2)]
 VARIANTS = [('0', 64.0, True), ('1', 1e9, False), ('1', 1e9, True), ('1', 64.0, True), ('1', 128.0, True), ('split', 64.0, True),
             ('auto', 64.0, True)]
+if os.environ.get('AB_SHORT'):                       # the two layouts only
+    VARIANTS = [('0', float('inf'), True), ('1', float('inf'), True)]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 only = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else range(len(CFGS))
 for ci in only:

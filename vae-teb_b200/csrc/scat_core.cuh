@@ -795,6 +795,74 @@ TEB_D void gmulfold2_task(float2* S, const float* __restrict__ arena, const Sign
         const int logcw = t.h & 0xff;
         const int nch = __popc(mask) << (logcw - 2);
         const float2 zero = make_float2(0.f, 0.f);
+        if (nch == 1 && logcw == 2) {
+            // one active 4-bin chunk (the usual case for folds by 4 and 8): FOUR outputs per thread and trip, their
+            // sixteen 128-bit loads (two filters + eight source bins each) in flight together -- one trip to L2
+            const int i = (TEB_FFS(mask) - 1) << 2;
+            for (int m0 = lt; m0 < n_dst; m0 += 4 * t.nt) {
+                float4 ga[4], gb[4];
+                float2 z[4][4];
+                TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + j * t.nt;
+                    if (m < n_dst) {
+                        ga[j] = TEB_LDG(reinterpret_cast<const float4*>(fa) + m);
+                        gb[j] = TEB_LDG(reinterpret_cast<const float4*>(fb) + m);
+                        gload4(G + ((long long)m << logk) + i, z[j]);
+                    } else {
+                        ga[j] = gb[j] = float4{0.f, 0.f, 0.f, 0.f};
+                        z[j][0] = z[j][1] = z[j][2] = z[j][3] = zero;
+                    }
+                }
+                TEB_UNROLL for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + j * t.nt;
+                    if (m >= n_dst) continue;
+                    float2 a = cfma_r(z[j][0], ga[j].x, zero), b = cfma_r(z[j][0], gb[j].x, zero);
+                    a = cfma_r(z[j][1], ga[j].y, a); b = cfma_r(z[j][1], gb[j].y, b);
+                    a = cfma_r(z[j][2], ga[j].z, a); b = cfma_r(z[j][2], gb[j].z, b);
+                    a = cfma_r(z[j][3], ga[j].w, a); b = cfma_r(z[j][3], gb[j].w, b);
+                    S[swz(da + m)] = cmul_r(a, scale);
+                    S[swz(db + m)] = cmul_r(b, scale);
+                }
+            }
+            return;
+        }
+        if (nch == 2 && logcw == 2) {
+            // two active chunks: two outputs per trip, the loads of BOTH chunks in flight together
+            const int i0 = (TEB_FFS(mask) - 1) << 2;
+            const int i1 = (TEB_FFS(mask & (mask - 1)) - 1) << 2;
+            for (int m0 = lt; m0 < n_dst; m0 += 2 * t.nt) {
+                float4 ga[2][2], gb[2][2];
+                float2 z[2][2][4];
+                TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                    const int m = m0 + j * t.nt;
+                    if (m < n_dst) {
+                        ga[j][0] = TEB_LDG(reinterpret_cast<const float4*>(fa) + 2 * m);
+                        ga[j][1] = TEB_LDG(reinterpret_cast<const float4*>(fa) + 2 * m + 1);
+                        gb[j][0] = TEB_LDG(reinterpret_cast<const float4*>(fb) + 2 * m);
+                        gb[j][1] = TEB_LDG(reinterpret_cast<const float4*>(fb) + 2 * m + 1);
+                        gload4(G + ((long long)m << logk) + i0, z[j][0]);
+                        gload4(G + ((long long)m << logk) + i1, z[j][1]);
+                    } else {
+                        ga[j][0] = ga[j][1] = gb[j][0] = gb[j][1] = float4{0.f, 0.f, 0.f, 0.f};
+                        TEB_UNROLL for (int q = 0; q < 4; ++q) z[j][0][q] = z[j][1][q] = zero;
+                    }
+                }
+                TEB_UNROLL for (int j = 0; j < 2; ++j) {
+                    const int m = m0 + j * t.nt;
+                    if (m >= n_dst) continue;
+                    float2 a = zero, b = zero;
+                    TEB_UNROLL for (int cidx = 0; cidx < 2; ++cidx) {
+                        a = cfma_r(z[j][cidx][0], ga[j][cidx].x, a); b = cfma_r(z[j][cidx][0], gb[j][cidx].x, b);
+                        a = cfma_r(z[j][cidx][1], ga[j][cidx].y, a); b = cfma_r(z[j][cidx][1], gb[j][cidx].y, b);
+                        a = cfma_r(z[j][cidx][2], ga[j][cidx].z, a); b = cfma_r(z[j][cidx][2], gb[j][cidx].z, b);
+                        a = cfma_r(z[j][cidx][3], ga[j][cidx].w, a); b = cfma_r(z[j][cidx][3], gb[j][cidx].w, b);
+                    }
+                    S[swz(da + m)] = cmul_r(a, scale);
+                    S[swz(db + m)] = cmul_r(b, scale);
+                }
+            }
+            return;
+        }
         for (int m0 = lt; m0 < n_dst; m0 += 2 * t.nt) {
             float2 accA[2] = {zero, zero}, accB[2] = {zero, zero};
             unsigned rest = mask;
@@ -836,10 +904,10 @@ TEB_D void gmulfold2_task(float2* S, const float* __restrict__ arena, const Sign
     } else {
         const int radix = t.h >> 8;
         const int n_items = 1 << (t.b - 2);                    // 4 source bins per item
-        for (int it0 = lt; it0 < n_items; it0 += 2 * t.nt) {
-            float4 gga[2], ggb[2];
-            float2 zz[2][4];
-            TEB_UNROLL for (int j = 0; j < 2; ++j) {
+        for (int it0 = lt; it0 < n_items; it0 += 4 * t.nt) {   // four items (sixteen 128-bit loads) in flight per thread
+            float4 gga[4], ggb[4];
+            float2 zz[4][4];
+            TEB_UNROLL for (int j = 0; j < 4; ++j) {
                 const int it = it0 + j * t.nt;
                 if (it < n_items) {
                     gga[j] = TEB_LDG(reinterpret_cast<const float4*>(fa + 4 * it));
@@ -850,7 +918,7 @@ TEB_D void gmulfold2_task(float2* S, const float* __restrict__ arena, const Sign
                     zz[j][0] = zz[j][1] = zz[j][2] = zz[j][3] = make_float2(0.f, 0.f);
                 }
             }
-            TEB_UNROLL for (int j = 0; j < 2; ++j) {
+            TEB_UNROLL for (int j = 0; j < 4; ++j) {
                 const int it = it0 + j * t.nt;
                 if (it >= n_items) continue;
                 TEB_UNROLL for (int which = 0; which < 2; ++which) {

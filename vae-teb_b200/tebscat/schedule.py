@@ -369,6 +369,7 @@ def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_of
     else:
         mask = 0
         work, lat, instr, trip = 1 << (log_src - 4), 2600.0, 500.0, 2400.0       # four 4-slot items per thread and trip
+    lat, trip = lat * MF2_SCALE, trip * MF2_SCALE
     if mask >= 1 << 31:
         mask -= 1 << 32
     # mean over k blocks, 1/L of the inverse transform, and the 1/2 of the pair separation
@@ -376,6 +377,7 @@ def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_of
                     h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst + 1, trip=trip)
 
 
+MF2_SCALE = float(os.environ.get('TEBSCAT_MF2_SCALE', '1.0'))    # cost-model knob: latency of the packed-source multiplies
 AUTO_SCRATCH_GAIN = 0.97          # 'auto': the scratch layout must be modelled at least 3 % faster to be chosen
 GSRC_PAIRS = os.environ.get('TEBSCAT_GSRC_PAIRS', '1') != '0'     # partners of a packed pair share one read of a global source
 # Cost-model knob: bytes per cycle at which a global-source multiply is charged for its source.  Measured, the
@@ -420,10 +422,15 @@ def _gmulfold2(arena: _Arena, log_src: int, logk: int, dst_a, dst_b, filt_a: int
         logcw = _Arena.chunk_log2(logk)
         nch = bin(mask).count('1') << (logcw - 2)
         filt_a, filt_b = arena.compact(filt_a, logk, mask), arena.compact(filt_b, logk, mask)
-        work, lat, instr, trip = -(-(1 << log_dst) // 2), 900.0 + 1100.0 * nch, 120.0 + 180.0 * nch, 350.0 + 1000.0 * nch
+        if nch == 1 and logcw == 2:        # four outputs per thread and trip, one trip to L2
+            work, lat, instr, trip = -(-(1 << log_dst) // 4), 2200.0, 420.0, 1900.0
+        elif nch == 2 and logcw == 2:      # two outputs per trip, both chunks in flight
+            work, lat, instr, trip = -(-(1 << log_dst) // 2), 2200.0, 420.0, 1900.0
+        else:
+            work, lat, instr, trip = -(-(1 << log_dst) // 2), 900.0 + 1100.0 * nch, 120.0 + 180.0 * nch, 350.0 + 1000.0 * nch
     else:
         mask, logcw = 0, 0
-        work, lat, instr, trip = -(-(1 << (log_src - 2)) // 2), 2400.0, 300.0, 2100.0
+        work, lat, instr, trip = -(-(1 << (log_src - 2)) // 4), 2600.0, 560.0, 2300.0    # four items per thread and trip
     src_bytes = 8.0 * ((1 << log_src) if logk < 2 else (1 << log_dst) * 4 * nch)
     per_trip = (src_bytes / GSRC_BYTES_PER_CYCLE) / max(1.0, work / 512.0)
     lat, trip = lat + per_trip, trip + per_trip
