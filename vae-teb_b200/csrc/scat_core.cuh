@@ -983,6 +983,11 @@ TEB_D void mulfold2_store(float2* S, int oa, int ob, float2 A, float2 Bc, float 
     S[ob] = cmul_r(rot90<-1>(csub(A, cb)), scale);
 }
 
+#ifndef TEBSCAT_MF2_ITEMS
+#define TEBSCAT_MF2_ITEMS 8
+#endif
+constexpr int kMf2Items = TEBSCAT_MF2_ITEMS;       // 4-slot items one thread takes per trip of a k < 4 MULFOLD2 (one trip to L2)
+
 TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task& t, int lt) {
     const int logk = t.c;
     const float scale = ldexpf(1.0f, -(t.op >> 8));
@@ -1065,13 +1070,13 @@ TEB_D void mulfold2_task(float2* S, const float* __restrict__ arena, const Task&
         }
     } else {
         const int n_items = 1 << (t.b - 2);                    // 4 source slots per item
-        for (int it0 = lt; it0 < n_items; it0 += 4 * t.nt) {
-            float4 gg[4];
-            TEB_UNROLL for (int j = 0; j < 4; ++j) {           // four filter loads in flight per thread
+        for (int it0 = lt; it0 < n_items; it0 += kMf2Items * t.nt) {
+            float4 gg[kMf2Items];
+            TEB_UNROLL for (int j = 0; j < kMf2Items; ++j) {   // the filter loads of a trip are in flight together
                 const int it = it0 + j * t.nt;
                 gg[j] = (it < n_items) ? TEB_LDG(reinterpret_cast<const float4*>(f + 4 * it)) : float4{0.f, 0.f, 0.f, 0.f};
             }
-            TEB_UNROLL for (int j = 0; j < 4; ++j) {
+            TEB_UNROLL for (int j = 0; j < kMf2Items; ++j) {
                 const int it = it0 + j * t.nt;
                 if (it >= n_items) continue;
                 const float4 g = gg[j];

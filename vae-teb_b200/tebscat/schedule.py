@@ -368,7 +368,8 @@ def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_of
             work, lat, instr, trip = -(-(1 << log_dst) // 2), 900.0 + 1100.0 * nch, 100.0 + 150.0 * nch, 300.0 + 1000.0 * nch
     else:
         mask = 0
-        work, lat, instr, trip = 1 << (log_src - 4), 2600.0, 500.0, 2400.0       # four 4-slot items per thread and trip
+        work, lat, instr, trip = max(1, -(-(1 << (log_src - 2)) // (1 << MF2_LOG_ITEMS))), 2600.0 * (1 << (MF2_LOG_ITEMS - 2)) ** 0.5, \
+            500.0 * (1 << (MF2_LOG_ITEMS - 2)), 2400.0 * (1 << (MF2_LOG_ITEMS - 2)) ** 0.5     # 2^MF2_LOG_ITEMS 4-slot items per thread and trip
     lat, trip = lat * MF2_SCALE, trip * MF2_SCALE
     if mask >= 1 << 31:
         mask -= 1 << 32
@@ -377,6 +378,7 @@ def _mulfold2(arena: _Arena, src, log_src: int, logk: int, dst_a, dst_b, filt_of
                     h=_Arena.chunk_log2(logk) if logk >= 2 else 0, sexp=logk + log_dst + 1, trip=trip)
 
 
+MF2_LOG_ITEMS = int(os.environ.get('TEBSCAT_MF2_LOG_ITEMS', '3'))    # csrc: kMf2Items = 8 items per thread and trip
 MF2_SCALE = float(os.environ.get('TEBSCAT_MF2_SCALE', '1.0'))    # cost-model knob: latency of the packed-source multiplies
 AUTO_SCRATCH_GAIN = 0.97          # 'auto': the scratch layout must be modelled at least 3 % faster to be chosen
 GSRC_PAIRS = os.environ.get('TEBSCAT_GSRC_PAIRS', '1') != '0'     # partners of a packed pair share one read of a global source
