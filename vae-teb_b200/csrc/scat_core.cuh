@@ -984,7 +984,7 @@ TEB_D void mulfold2_store(float2* S, int oa, int ob, float2 A, float2 Bc, float 
 }
 
 #ifndef TEBSCAT_MF2_ITEMS
-#define TEBSCAT_MF2_ITEMS 8
+#define TEBSCAT_MF2_ITEMS 4
 #endif
 constexpr int kMf2Items = TEBSCAT_MF2_ITEMS;       // 4-slot items one thread takes per trip of a k < 4 MULFOLD2 (one trip to L2)
 
