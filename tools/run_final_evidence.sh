@@ -29,3 +29,10 @@ tail -2 gpurun_out/ncu_${TAG}_phase.log
 [ -x build/umma_shared_acc ] && ./build/umma_shared_acc > gpurun_out/${TAG}_umma_shared_acc.txt 2>&1
 [ -f build/variants/lib_trace.so ] && TEBSCAT_LIB=$PWD/build/variants/lib_trace.so python tools/tc_trace.py > gpurun_out/${TAG}_phase_tc_timeline.txt 2>&1
 python tools/time_phase_stages.py 8192 > gpurun_out/${TAG}_phase_stages.txt 2>&1
+# BASELINE configs[3] at one GPU, the A/B of the two U0 layouts, the per-step cycles of the headline schedule and the
+# per-op breakdown of the large-support level at its two ends
+python tools/sweep_config3.py > gpurun_out/${TAG}_sweep_config3_n1.jsonl 2> gpurun_out/${TAG}_sweep_config3_n1.err
+AB_SHORT=1 python tools/ab_u0_scratch.py 16384 0,1,2,3 > gpurun_out/${TAG}_ab_u0_layouts.txt 2>&1
+python tools/step_profile.py H > gpurun_out/${TAG}_step_cycles_H.json 2> /dev/null
+python tools/large_breakdown.py 8 8192 2048 > gpurun_out/${TAG}_breakdown_2_14.txt 2>&1
+python tools/large_breakdown.py 10 65536 256 > gpurun_out/${TAG}_breakdown_2_17.txt 2>&1
