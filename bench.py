@@ -34,10 +34,11 @@ FLOPS_PER_SIGNAL = 31.56e6                # reference-equivalent F
 
 def measured_traffic(n_sig):
     """DRAM bytes of one launch of the dominant kernel from the committed ncu capture (profiles/)."""
-    path = os.path.join(ROOT, 'profiles', 'r01c_traffic.json')
-    if not os.path.exists(path):
-        path = os.path.join(ROOT, 'profiles', 'r01b_traffic.json')
-    if not os.path.exists(path):
+    for name in ('r02m_traffic.json', 'r01c_traffic.json', 'r01b_traffic.json'):     # newest capture first
+        path = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(path):
+            break
+    else:
         return None
     with open(path) as f:
         t = json.load(f)
