@@ -213,6 +213,50 @@ def test_plan_validation_runs_before_any_device_call():
     assert 'overlapping thread ranges' in str(e.value)
 
 
+def test_global_source_tasks_are_validated_on_the_host():
+    """The global-source multiplies (OP_GMULFOLD / OP_GMULFOLD2: U0 parked in the L2 scratch, fused subtrees of the
+    large-support level) are checked like every other task before any device call: source extent against the
+    scratch, alignment of the source offset, destination inside shared memory, filters inside the arena."""
+    from tebscat.schedule import OP_GMULFOLD, OP_GMULFOLD2, build_hybrid_plans, build_plan
+    from tebscat.torch_frontend import _DevicePlan
+
+    def refused(plan, text):
+        with pytest.raises(ValueError) as e:
+            _DevicePlan(plan, 0)
+        assert text in str(e.value), str(e.value)
+
+    def fresh():
+        p = build_plan(5, 700, 2, 8, 2)
+        p.tasks = p.tasks.copy()
+        return p
+
+    p = fresh()
+    assert p.scratch_complex == 1 << p.geo.J_pad
+    ops = p.tasks[:, 0] & 0xff
+    g2 = int(np.flatnonzero(ops == OP_GMULFOLD2)[0])
+    g1 = int(np.flatnonzero(ops == OP_GMULFOLD)[0])
+    p.scratch_complex = 512                         # smaller than the spectrum the schedule parks and reads
+    refused(p, 'bad scratch size')
+    p = fresh()
+    p.tasks[g1, 3] = 2                              # source offset must be a multiple of four bins
+    refused(p, 'bad GMULFOLD')
+    p = fresh()
+    p.tasks[g2, 3] = 1 << 20                        # destination of filter B outside shared memory
+    refused(p, 'bad GMULFOLD2')
+    p = fresh()
+    p.tasks[g2, 9] = p.arena.size                   # filter B outside the arena
+    refused(p, 'GMULFOLD2 filter outside the arena')
+    p = fresh()
+    p.tasks[g1, 4] = 20                             # a source of 2^20 bins
+    refused(p, 'bad GMULFOLD')
+    # a fused subtree of the large-support level: destinations are at most 8192 bins
+    h = build_hybrid_plans(5, 9000, 4, 32)['first']
+    h.tasks = h.tasks.copy()
+    g = int(np.flatnonzero((h.tasks[:, 0] & 0xff) == OP_GMULFOLD2)[0])
+    h.tasks[g, 5] = 0                               # no periodisation: 2^14 output bins
+    refused(h, 'bad GMULFOLD2')
+
+
 def test_level_selection_follows_the_current_options():
     """Which level serves a configuration (fused single kernel / op by op) is decided per schedule key, not latched:
     `oversampling` is read at call time like in the reference (core/scattering1d.py:260-261), so changing it on a

@@ -509,6 +509,9 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
             return fail(TEBSCAT_EINVAL, "channel table entry %zu out of range", i);
     int64_t gsrc_extent = 0;
     if (int rc = validate_schedule(*desc, tasks, steps, n_floats, n_chan, &gsrc_extent)) return rc;
+    if (desc->scratch_complex < 0 || (desc->scratch_complex & 3) || (desc->scratch_complex && gsrc_extent > desc->scratch_complex))
+        return fail(TEBSCAT_EINVAL, "bad scratch size %lld (the schedule reads %lld bins)", (long long)desc->scratch_complex,
+                    (long long)gsrc_extent);
 
     int n_dev = 0;
     CU(cudaGetDeviceCount(&n_dev));
@@ -524,9 +527,6 @@ extern "C" int tebscat_plan_create(const tebscat_plan_desc* desc, const float* a
     p->device = device;
     p->gsrc_extent = gsrc_extent;
     p->scratch_complex = desc->scratch_complex;
-    if (p->scratch_complex < 0 || (p->scratch_complex & 3) || (p->scratch_complex && gsrc_extent > p->scratch_complex))
-        return fail(TEBSCAT_EINVAL, "bad scratch size %lld (the schedule reads %lld bins)", (long long)p->scratch_complex,
-                    (long long)gsrc_extent);
     p->n_sms = prop.multiProcessorCount;
     p->smem_bytes = ((size_t)desc->smem_complex + kTwAP + kTwBP) * sizeof(float2);
     if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
