@@ -798,6 +798,9 @@ class _LeafPool:
                 self.cur = o
 
 
+PRIO_DEPTH = float(os.environ.get('TEBSCAT_PRIO_DEPTH', '1e12'))   # weight of a chain's depth in its priority (knob)
+
+
 def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out: int,
                     max_parallel: int = 64, pack_gain: float = 0.97, pool_slots: int = POOL_SLOTS,
                     open_demand: float = 2.0):
@@ -830,7 +833,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
             visit(c)
     parent_of = {id(c): (c.after[0] if c.after else None) for c in chains}
     for c in chains:
-        c.priority = c.depth * 1e12 + weight[id(c)]
+        c.priority = c.depth * PRIO_DEPTH + weight[id(c)]
         c.stage = 0
         c.issued = [False] * len(c.stages[0])
         c.done_step = -1
