@@ -798,12 +798,17 @@ class _LeafPool:
                 self.cur = o
 
 
-PRIO_DEPTH = float(os.environ.get('TEBSCAT_PRIO_DEPTH', '1e12'))   # weight of a chain's depth in its priority (knob)
+# Priority of a chain in the list scheduler = depth * PRIO_DEPTH + weight of its subtree.  Depth first (1e12) finishes
+# what is started before it opens something new; by weight only (0) lets the heavy full-length pairs start while the
+# tails of the subsampled groups still run.  build_plan schedules BOTH ways and keeps the one the cost model prefers
+# (headline configuration: 100 steps / 570 k modelled cycles against 107 / 586 k; measured 529 000 against 513 900
+# signals/s, profiles/r02n_ab_priority.txt); TEBSCAT_PRIO_DEPTH pins one.
+PRIO_DEPTH = os.environ.get('TEBSCAT_PRIO_DEPTH')
 
 
 def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out: int,
                     max_parallel: int = 64, pack_gain: float = 0.97, pool_slots: int = POOL_SLOTS,
-                    open_demand: float = 2.0):
+                    open_demand: float = 2.0, depth_weight: float = 1e12):
     """Greedy list scheduling of chains into steps (see module docstring)."""
     children: Dict[int, List[Chain]] = {}
     for ch in chains:
@@ -833,7 +838,7 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
             visit(c)
     parent_of = {id(c): (c.after[0] if c.after else None) for c in chains}
     for c in chains:
-        c.priority = c.depth * PRIO_DEPTH + weight[id(c)]
+        c.priority = c.depth * depth_weight + weight[id(c)]
         c.stage = 0
         c.issued = [False] * len(c.stages[0])
         c.done_step = -1
@@ -1393,20 +1398,35 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
     ladder = [(BATCH_SLOTS, POOL_SLOTS), (BATCH_SLOTS, 512), (4096, 1024), (2048, 1024), (1024, 512), (512, 256)]
     if 'batch_slots' in tune or 'pool_slots' in tune:
         ladder.insert(0, (tune.get('batch_slots', BATCH_SLOTS), tune.get('pool_slots', POOL_SLOTS)))
-    for batch_slots, pool_slots in ladder:
-        arena = _Arena()
-        chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling,
-                                                   child_slots=tune.get('child_slots'),
-                                                   global_u0=scratch or False)
-        try:
-            steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel,
-                                                       pool_slots=pool_slots, pack_gain=tune.get('pack_gain', 0.97),
-                                                       open_demand=tune.get('open_demand', 2.0))
-            break
-        except (RuntimeError, AssertionError) as e:
-            last_err = e
+    if 'depth_weight' in tune:
+        depth_modes = [float(tune['depth_weight'])]
+    elif PRIO_DEPTH is not None:
+        depth_modes = [float(PRIO_DEPTH)]
     else:
+        depth_modes = [1e12, 0.0]
+    best = None
+    for batch_slots, pool_slots in ladder:
+        for dw in depth_modes:
+            arena = _Arena()
+            chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling,
+                                                       child_slots=tune.get('child_slots'),
+                                                       global_u0=scratch or False)
+            try:
+                cand = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel,
+                                       pool_slots=pool_slots, pack_gain=tune.get('pack_gain', 0.97),
+                                       open_demand=tune.get('open_demand', 2.0), depth_weight=dw)
+            except (RuntimeError, AssertionError) as e:
+                last_err = e
+                continue
+            # (depth first unless the other order is modelled at least 1 % faster)
+            if best is None or cand[3]['est_cycles'] < 0.99 * best[0][3]['est_cycles']:
+                best = (cand, arena, keys, n_out, lf, i0, dw)
+        if best is not None:
+            break
+    if best is None:
         raise NotImplementedError('no schedule fits shared memory for this configuration: %s' % last_err)
+    (steps, high, chan, sched), arena, keys, n_out, lf, i0, depth_used = best
+    sched = dict(sched, depth_weight=depth_used)
     tasks, ranges = emit(steps)
     n_tasks = tasks.shape[0]
     n_relaxed = 0
