@@ -804,11 +804,12 @@ class _LeafPool:
 # (headline configuration: 100 steps / 570 k modelled cycles against 107 / 586 k; measured 529 000 against 513 900
 # signals/s, profiles/r02n_ab_priority.txt); TEBSCAT_PRIO_DEPTH pins one.
 PRIO_DEPTH = os.environ.get('TEBSCAT_PRIO_DEPTH')
+RESERVE_MODES = os.environ.get('TEBSCAT_RESERVE', 'sum,peak').split(',')
 
 
 def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out: int,
                     max_parallel: int = 64, pack_gain: float = 0.97, pool_slots: int = POOL_SLOTS,
-                    open_demand: float = 2.0, depth_weight: float = 1e12):
+                    open_demand: float = 2.0, depth_weight: float = 1e12, reserve: str = 'sum'):
     """Greedy list scheduling of chains into steps (see module docstring)."""
     children: Dict[int, List[Chain]] = {}
     for ch in chains:
@@ -830,6 +831,17 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
                 visit(k)
             w += weight[id(k)]
             nd += own_size[id(k)] + need[id(k)]
+        if reserve == 'peak':
+            # what the subtree needs BEYOND the chain's own buffers if its children run one after another and the
+            # chain's own buffer has shrunk (the partner half of a packed batch is dead after the packed pass):
+            # a weaker guarantee than the sum over all children -- a subtree may start while another one's tail
+            # still runs -- so a schedule built this way can dead-end; the caller then falls back to 'sum'
+            own = own_size[id(c)]
+            after = own
+            for _, buf, new_size in c.shrink:
+                after -= _round16(buf.size) - _round16(new_size)
+            kid_peak = max((own_size[id(k)] + need[id(k)] for k in children.get(id(c), [])), default=0)
+            nd = max(own, after + kid_peak) - own
         weight[id(c)] = w
         need[id(c)] = nd if c.depth > 0 else 0          # the root does not reserve for the whole tree
 
@@ -1404,9 +1416,12 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
         depth_modes = [float(PRIO_DEPTH)]
     else:
         depth_modes = [1e12, 0.0]
+    # ... and with both reservation rules (schedule_chains: 'sum' always finishes; 'peak' lets a subtree start while
+    # another one's tail still runs and may dead-end, in which case that candidate is simply dropped)
+    reserve_modes = [tune['reserve']] if 'reserve' in tune else (RESERVE_MODES if max_order == 2 else ['sum'])
     best = None
     for batch_slots, pool_slots in ladder:
-        for dw in depth_modes:
+        for dw, rs in [(d, r) for r in reserve_modes for d in depth_modes]:
             arena = _Arena()
             chains, keys, n_out, lf, i0 = build_chains(bank, geo, T, max_order, arena, batch_slots, oversampling,
                                                        child_slots=tune.get('child_slots'),
@@ -1414,19 +1429,19 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
             try:
                 cand = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel,
                                        pool_slots=pool_slots, pack_gain=tune.get('pack_gain', 0.97),
-                                       open_demand=tune.get('open_demand', 2.0), depth_weight=dw)
+                                       open_demand=tune.get('open_demand', 2.0), depth_weight=dw, reserve=rs)
             except (RuntimeError, AssertionError) as e:
                 last_err = e
                 continue
-            # (depth first unless the other order is modelled at least 1 % faster)
+            # (the round-1 rules unless another combination is modelled at least 1 % faster)
             if best is None or cand[3]['est_cycles'] < 0.99 * best[0][3]['est_cycles']:
-                best = (cand, arena, keys, n_out, lf, i0, dw)
+                best = (cand, arena, keys, n_out, lf, i0, (dw, rs))
         if best is not None:
             break
     if best is None:
         raise NotImplementedError('no schedule fits shared memory for this configuration: %s' % last_err)
     (steps, high, chan, sched), arena, keys, n_out, lf, i0, depth_used = best
-    sched = dict(sched, depth_weight=depth_used)
+    sched = dict(sched, depth_weight=depth_used[0], reserve=depth_used[1])
     tasks, ranges = emit(steps)
     n_tasks = tasks.shape[0]
     n_relaxed = 0
