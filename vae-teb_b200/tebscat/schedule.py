@@ -809,7 +809,8 @@ RESERVE_MODES = os.environ.get('TEBSCAT_RESERVE', 'sum,peak').split(',')
 
 def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out: int,
                     max_parallel: int = 64, pack_gain: float = 0.97, pool_slots: int = POOL_SLOTS,
-                    open_demand: float = 2.0, depth_weight: float = 1e12, reserve: str = 'sum'):
+                    open_demand: float = 2.0, depth_weight: float = 1e12, reserve: str = 'sum',
+                    defer_thin: bool = False):
     """Greedy list scheduling of chains into steps (see module docstring)."""
     children: Dict[int, List[Chain]] = {}
     for ch in chains:
@@ -970,25 +971,39 @@ def schedule_chains(chains: List[Chain], capacity: int, lf: int, i0: int, n_out:
             for ti, t in enumerate(c.stages[c.stage]):
                 if not c.issued[ti]:
                     cands.append((c, ti, t))
-        chosen: List[Tuple[Chain, int, TaskSpec]] = []
-        nts: List[int] = []
-        cur_time = 0.0
-        pool_room = pool.room()
-        for cand in cands:
-            t = cand[2]
-            if t.d is LEAF and pool_room <= 0:
-                continue
-            trial = chosen + [cand]
-            split = _split_threads([k[2] for k in trial])
-            if split is None:
-                break
-            tt = _step_time(list(zip([k[2] for k in trial], split)))
-            alone = _step_time([(t, _want_threads(t.work, t.tpi))])
-            if chosen and tt > pack_gain * (cur_time + alone):
-                continue
-            chosen, nts, cur_time = trial, split, tt
-            if t.d is LEAF:
-                pool_room -= 1
+        def pick(order):
+            chosen_: List[Tuple[Chain, int, TaskSpec]] = []
+            nts_: List[int] = []
+            cur = 0.0
+            room = pool.room()
+            skipped = []
+            for cand in order:
+                t = cand[2]
+                if t.d is LEAF and room <= 0:
+                    continue
+                trial = chosen_ + [cand]
+                split = _split_threads([k[2] for k in trial])
+                if split is None:
+                    break
+                tt = _step_time(list(zip([k[2] for k in trial], split)))
+                alone = _step_time([(t, _want_threads(t.work, t.tpi))])
+                if chosen_ and tt > pack_gain * (cur + alone):
+                    skipped.append(cand)
+                    continue
+                chosen_, nts_, cur = trial, split, tt
+                if t.d is LEAF:
+                    room -= 1
+            return chosen_, nts_, cur, skipped
+
+        chosen, nts, cur_time, skipped = pick(cands)
+        if defer_thin and chosen and sum(nts) <= N_THREADS // 4:
+            # A thin step (a few warps of leftovers) while a task that wants most of the CTA had to be skipped: run
+            # the wide task now, the leftovers ride along with a later step that has room for them.
+            wide = [k for k in skipped if _want_threads(k[2].work, k[2].tpi) >= 3 * N_THREADS // 4]
+            if wide:
+                again = pick(wide + [k for k in cands if not any(k is w for w in wide)])
+                if again[0] and sum(again[1]) > sum(nts):
+                    chosen, nts, cur_time, skipped = again
         if not chosen:
             raise RuntimeError('scheduler stalled on the leaf pool')
         this_step: List[List[int]] = []
@@ -1429,7 +1444,8 @@ def build_plan(J: int, N: int, Q, T: int, max_order: int = 2, max_parallel: int 
             try:
                 cand = schedule_chains(chains, capacity, lf, i0, n_out, max_parallel,
                                        pool_slots=pool_slots, pack_gain=tune.get('pack_gain', 0.97),
-                                       open_demand=tune.get('open_demand', 2.0), depth_weight=dw, reserve=rs)
+                                       open_demand=tune.get('open_demand', 2.0), depth_weight=dw, reserve=rs,
+                                       defer_thin=bool(tune.get('defer_thin', rs == 'peak')))
             except (RuntimeError, AssertionError) as e:
                 last_err = e
                 continue
@@ -1524,7 +1540,31 @@ def build_kid_chains(bank: fbk.FilterBank, geo: fbk.Geometry, T: int, arena: _Ar
 
 def _finish_fused_plan(J, Q1, T, N, max_order, geo, bank, n_paths, n_out, lf, i0, chains, arena, pool_slots):
     capacity = smem_capacity()
-    steps, high, chan, sched = schedule_chains(chains, capacity, lf, i0, n_out, pool_slots=pool_slots)
+    # the same candidates as build_plan: chain priority depth first / by weight, reservation rule 'sum' / 'peak'
+    # (schedule_chains resets the chains' and buffers' scheduling state, so one set of chains serves all of them)
+    best, last_err = None, None
+    depth_modes = [float(PRIO_DEPTH)] if PRIO_DEPTH is not None else [1e12, 0.0]
+    for rs in RESERVE_MODES:
+        for dw in depth_modes:
+            for c in chains:
+                for b in c.owns + c.reads:
+                    b.off, b.readers_left, b.producer_done = -1, 0, False
+            sizes = {id(b): b.size for c in chains for b in c.owns}
+            try:
+                cand = schedule_chains(chains, capacity, lf, i0, n_out, pool_slots=pool_slots, depth_weight=dw, reserve=rs,
+                                       defer_thin=rs == 'peak')
+            except (RuntimeError, AssertionError) as e:
+                last_err = e
+                cand = None
+            for c in chains:                                   # (a packed pass shrinks its buffer while scheduling)
+                for b in c.owns:
+                    b.size = sizes[id(b)]
+            if cand is not None and (best is None or cand[3]['est_cycles'] < 0.99 * best[0][3]['est_cycles']):
+                best = (cand, dw, rs)
+    if best is None:
+        raise RuntimeError('no schedule: %s' % last_err)
+    (steps, high, chan, sched), dw, rs = best
+    sched = dict(sched, depth_weight=dw, reserve=rs)
     tasks, ranges = emit(steps)
     if os.environ.get('TEBSCAT_RELAX', '1') != '0':
         keep = elide_barriers(tasks, ranges, capacity, LOG2_NP_MAX)
