@@ -23,6 +23,14 @@ Design (what makes the steps full):
 * Chains of tasks that do not depend on each other are packed side by side into
   steps by a list scheduler under two resources: the 512 threads of the CTA and
   the shared-memory slots of their buffers.
+* The signal's spectrum U0 is only ever READ after its transform: it is parked in a per-CTA
+  global scratch (L2-resident) and its consumers are global-source multiplies (OP_GMULFOLD,
+  OP_GMULFOLD2 for the two partners of a packed pair), which frees 8192 slots for the rest
+  of the signal (`u0_in_scratch`).  The same multiplies let the subtrees of at
+  most 8192 samples under a longer spectrum run here (`build_hybrid_plans`).
+* The scheduler is greedy, so `build_plan` builds several candidate schedules (chain priority
+  depth first / by weight, subtree reservation 'sum' / 'peak') and keeps the one the cost
+  model prefers; the model is calibrated with on-device step timings (tools/step_profile.py).
 
 Filters are cast to fp32 exactly like ``register_filters``
 (``frontend/torch_frontend.py:75-97``), permuted to bit-reversed bin order and
