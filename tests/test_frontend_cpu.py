@@ -310,3 +310,34 @@ def test_plan_files_are_validated(tmp_path):
     with pytest.raises(ValueError):
         save_plan(p, str(tmp_path / 'bad.tebplan'))
     assert not (tmp_path / 'bad.tebplan').exists()
+
+
+def test_large_plan_splits_the_cascade_between_the_levels(monkeypatch):
+    """Padded lengths above 2^13: the host plan of the large-support level hands every subtree of at most
+    8192 samples to the fused kernel -- the first-order filters whose subsampled length fits, and per longer filter the
+    children that fit -- and keeps exactly the rest; filters of one scale share a schedule with channels a constant
+    shift apart; TEBSCAT_HYBRID=0 keeps everything op by op; at 2^13 and below there is nothing to split."""
+    from tebscat import large
+    from tebscat.large import LargePlan
+    lp = LargePlan(8, 2 ** 13, 8, 256)                                     # Np = 2^14, 54 first-order filters
+    hyb = lp.hybrid_plans()
+    assert hyb is lp.hybrid_plans()                                        # built once
+    n = lp.geo.J_pad
+    small = {e['n1'] for e in lp.first if e['l1'] <= 13}
+    assert set(hyb['first_n1']) == small and 0 < len(small) < len(lp.first)
+    assert hyb['first'].n_paths == lp.n_paths and hyb['first'].n_out == lp.n_out
+    long_n1 = {e['n1'] for e in lp.first if e['l1'] > 13}
+    covered = set()
+    ch = lp._channel
+    for plan, members, done in hyb['kids']:
+        covered |= set(members)
+        assert set(members) <= long_n1 and plan.head == members[0]
+        shifts = {tuple(ch[(n1, n2)] - ch[(plan.head, n2)] for n2 in done) for n1 in members}
+        assert all(len(set(s)) == 1 for s in shifts)                       # one shift per member
+        for e in lp.first:
+            if e['n1'] in members:                                         # the children left to the level are the long ones
+                assert {k['n2'] for k in e['kids'] if k['l2'] <= 13} == set(done)
+    assert covered == {e['n1'] for e in lp.first if e['l1'] > 13 and any(k['l2'] <= 13 for k in e['kids'])}
+    assert LargePlan(6, 4800, 8, 64).hybrid_plans() is None                # Np = 2^13: the fused cascade serves it whole
+    monkeypatch.setattr(large, 'HYBRID', False)
+    assert LargePlan(8, 2 ** 13, 8, 256).hybrid_plans() is None
